@@ -1,0 +1,260 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference
+(``/root/reference``) in the build container under the import shims of ``_shims/ref_shims.py``.
+
+    python tests/golden/make_golden.py
+
+Writes, next to this file:
+  metric_vectors.json    every (predictions, positive_mask, k, expected) tuple of the reference's
+                         own metric tests (tests/test_{recall,ndcg,dcg,mrr,precision,f1}.py)
+  bert4rec_small.npz, kebert4rec_small.npz, sasrec_full_small.npz, sasrec_neg_small.npz
+                         weights (reference state-dict names), inputs, and the reference's
+                         outputs: logits / hidden stages, loss, per-parameter gradients,
+                         eval rows, metric values.
+  metrics_dense_small.npz  dense-signature metric values of the reference classes on random
+                         (B,V) scores incl. ties, with the stable tie order of SURVEY.md 8c.
+
+This script is the ONLY code that touches /root/reference; it cannot run on the GPU box.
+"""
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+import ref_shims  # noqa: E402
+
+ref_shims.install()
+
+
+def to_np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def grads_of(model, prefix="grad::"):
+    return {prefix + n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def weights_of(model, prefix="w::"):
+    return {prefix + n: v.detach().clone() for n, v in model.state_dict().items()}
+
+
+def randomize(model, gen):
+    """Replace the trivial LayerNorm(1,0) / zero-bias init by random values so that every
+    parameter influences the fixture."""
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.2 + (1.0 if "norm" in n and n.endswith("weight") else 0.0))
+            else:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.3)
+
+
+def make_sequences(gen, b, s, v, min_len=1):
+    seq = torch.randint(3, v, (b, s), generator=gen)
+    lengths = torch.randint(min_len, s + 1, (b,), generator=gen)
+    lengths[0] = s                      # at least one full row
+    for i in range(b):
+        seq[i, lengths[i]:] = 0
+    return seq, lengths
+
+
+def export_metric_vectors():
+    sys.path.insert(0, "/root/reference/tests")
+    out = {}
+    for name in ["recall", "ndcg", "dcg", "mrr", "precision", "f1"]:
+        mod = importlib.import_module(f"test_{name}")
+        samples = []
+        for fn in ("get_single_item_recommendation_samples", "get_multiple_item_recommendation_samples"):
+            if hasattr(mod, fn):
+                for pred, mask, k, val in getattr(mod, fn)():
+                    samples.append({"predictions": pred.tolist(), "positive_mask": mask.tolist(), "k": int(k),
+                                    "expected": float(val), "group": fn})
+        out[name] = samples
+    with open(os.path.join(HERE, "metric_vectors.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("metric vectors:", {k: len(v) for k, v in out.items()})
+
+
+def cloze(seq, lengths, gen, p=0.3):
+    inp = seq.clone()
+    tgt = torch.zeros_like(seq)
+    for i in range(seq.shape[0]):
+        n = int(lengths[i])
+        m = torch.rand(n, generator=gen) < p
+        if not m.any():
+            m[n - 1] = True
+        tgt[i, :n][m] = seq[i, :n][m]
+        inp[i, :n][m] = 1
+    return inp, tgt
+
+
+def bert4rec_fixture():
+    from asme.core.models.bert4rec.bert4rec_model import BERT4RecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    gen = torch.Generator().manual_seed(101)
+    V, S, H, L, heads, B = 61, 12, 16, 2, 2, 6
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V)})
+    model = BERT4RecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                          max_seq_length=S, transformer_dropout=0.0)
+    randomize(model, gen)
+    seq, lengths = make_sequences(gen, B, S, V)
+    inp, tgt = cloze(seq, lengths, gen)
+    logits = model(InputSequence(inp, inp.ne(0), {}))
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, V), tgt.view(-1))
+    loss.backward()
+    # eval: append a MASK at the end of each (shortened) sequence, one MASK per row
+    ev = seq.clone()
+    ev_t = torch.randint(3, V, (B,), generator=gen)
+    for i in range(B):
+        n = min(int(lengths[i]), S - 1)
+        ev[i, n] = 1
+        ev[i, n + 1:] = 0
+    with torch.no_grad():
+        ev_logits = model(InputSequence(ev, ev.ne(0), {}))[ev.eq(1)]
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": inp, "target": tgt, "logits": logits,
+            "loss": loss, "eval_input": ev, "eval_target": ev_t, "eval_logits": ev_logits}
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "bert4rec_small.npz"), **to_np(data))
+    print("bert4rec loss", float(loss))
+
+
+def kebert4rec_fixture():
+    from asme.core.models.kebert4rec.kebert4rec_model import KeBERT4RecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    gen = torch.Generator().manual_seed(202)
+    V, S, H, L, heads, B, VA, VT, A = 83, 10, 16, 1, 2, 5, 13, 19, 3
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V), "category": ref_shims.make_tokenizer(VA, "c"),
+                                     "tags": ref_shims.make_tokenizer(VT, "t")})
+    model = KeBERT4RecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                            max_seq_length=S, transformer_dropout=0.0,
+                            prefusion_attributes={"category": {"embedding_type": "content_embedding"},
+                                                  "tags": {"embedding_type": "linear_upscale"}})
+    randomize(model, gen)
+    seq, lengths = make_sequences(gen, B, S, V)
+    inp, tgt = cloze(seq, lengths, gen)
+    cat = torch.randint(3, VA, (B, S), generator=gen)
+    tags = torch.randint(0, VT, (B, S, A), generator=gen)       # includes pad id 0 and duplicates
+    cat[inp == 0] = 0
+    cat[inp == 1] = 1
+    tags[inp == 0] = 0
+    logits = model(InputSequence(inp, inp.ne(0), {"category": cat, "tags": tags}))
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, V), tgt.view(-1))
+    loss.backward()
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": inp, "target": tgt, "category": cat,
+            "tags": tags, "logits": logits, "loss": loss}
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "kebert4rec_small.npz"), **to_np(data))
+    print("kebert4rec loss", float(loss))
+
+
+def sasrec_fixtures():
+    from asme.core.models.sasrec.sasrec_model import SASRecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    from asme.core.losses.sasrec.sas_rec_losses import SASRecBinaryCrossEntropyLoss
+    gen = torch.Generator().manual_seed(303)
+    V, S, H, L, heads, B = 71, 9, 16, 2, 2, 7
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V)})
+    # ---- mode="full" (sasrec-cross): per-position CE + last-position eval rows
+    model = SASRecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                        max_seq_length=S, transformer_dropout=0.0, mode="full")
+    randomize(model, gen)
+    seq, lengths = make_sequences(gen, B, S, V)
+    tgt = torch.zeros_like(seq)
+    for i in range(B):
+        n = int(lengths[i])
+        tgt[i, :n] = torch.randint(3, V, (n,), generator=gen)
+    logits = model(InputSequence(seq, seq.ne(0), {}))
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.reshape(-1, V), tgt.reshape(-1))
+    loss.backward()
+    last = logits.detach()[torch.arange(B), seq.ne(0).sum(-1) - 1]
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": seq, "target": tgt, "logits": logits,
+            "loss": loss, "eval_logits": last}
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "sasrec_full_small.npz"), **to_np(data))
+    print("sasrec full loss", float(loss))
+    # ---- mode="neg_sampling" (sasrec-neg): pos/neg logits + BCE, and the all-items eval branch
+    model = SASRecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                        max_seq_length=S, transformer_dropout=0.0, mode="neg_sampling")
+    randomize(model, gen)
+    pos = torch.zeros_like(seq)
+    neg = torch.zeros_like(seq)
+    for i in range(B):
+        n = int(lengths[i])
+        pos[i, :n] = torch.randint(3, V, (n,), generator=gen)
+        neg[i, :n] = torch.randint(3, V, (n,), generator=gen)
+    p, n_ = model(InputSequence(seq, seq.ne(0), {"positive_samples": pos, "negative_samples": neg}))
+    loss = SASRecBinaryCrossEntropyLoss()(p, n_, mask=seq.ne(0))
+    loss.backward()
+    items = torch.arange(V).repeat(B, 1)
+    with torch.no_grad():
+        ev = model(InputSequence(seq, seq.ne(0), {"positive_samples": items}))
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": seq, "positive_samples": pos,
+            "negative_samples": neg, "pos_logits": p, "neg_logits": n_, "loss": loss, "eval_logits": ev}
+    data.update({k: v for k, v in weights_of(model).items() if "_projection_layer" not in k})
+    data.update({k: v for k, v in grads_of(model).items() if "_projection_layer" not in k})
+    np.savez_compressed(os.path.join(HERE, "sasrec_neg_small.npz"), **to_np(data))
+    print("sasrec neg loss", float(loss))
+
+
+def metrics_fixture():
+    """Reference metric classes on random scores; ties are made deterministic by patching
+    torch.argsort to a stable sort inside the reference call (the reference's own argsort is
+    unstable, SURVEY.md 8c fixes 'ties -> lowest item id')."""
+    import asme.core.metrics.common as common
+    from asme.core.metrics.container.metrics_container import RankingMetricsContainer
+    from asme.core.metrics.container.metrics_sampler import AllItemsSampler
+    from asme.core.metrics.recall import RecallMetric
+    from asme.core.metrics.ndcg import NormalizedDiscountedCumulativeGainMetric
+    from asme.core.metrics.mrr import MRRMetric
+    from asme.core.metrics.precision import PrecisionMetric
+    from asme.core.metrics.f1 import F1Metric
+    from asme.core.metrics.dcg import DiscountedCumulativeGainMetric
+    from asme.core.metrics.mrr_full import MRRFullMetric
+    from asme.core.metrics.rank import Rank
+
+    class _StableTorch:
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def argsort(x, descending=False):
+            return torch.sort(x, descending=descending, stable=True).indices
+
+    common.torch = _StableTorch()
+    gen = torch.Generator().manual_seed(404)
+    B, V = 32, 57
+    pred = torch.round(torch.randn(B, V, generator=gen) * 4) / 4          # coarse grid -> many ties
+    targets = torch.randint(0, V, (B,), generator=gen)
+    ks = [1, 3, 5, 10]
+    metrics = []
+    for k in ks:
+        metrics += [RecallMetric(k), NormalizedDiscountedCumulativeGainMetric(k), MRRMetric(k), PrecisionMetric(k),
+                    F1Metric(k), DiscountedCumulativeGainMetric(k)]
+    metrics += [MRRFullMetric(), Rank()]
+    container = RankingMetricsContainer(metrics, AllItemsSampler())
+    step = container.update(None, targets, pred)
+    final = container.compute()
+    data = {"predictions": pred, "targets": targets, "ks": np.array(ks)}
+    for name, v in step.items():
+        data["step::" + name] = v
+    for name, v in final.items():
+        data["final::" + name] = v
+    np.savez_compressed(os.path.join(HERE, "metrics_dense_small.npz"), **to_np(data))
+    common.torch = torch
+    print("metrics:", {k: float(v) for k, v in final.items()})
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    export_metric_vectors()
+    bert4rec_fixture()
+    kebert4rec_fixture()
+    sasrec_fixtures()
+    metrics_fixture()
