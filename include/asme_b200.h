@@ -1,0 +1,243 @@
+/* asme_b200.h -- C ABI of libasme_b200.so: the sm_100a (B200) kernels behind the ASME
+ * sequential-recommender hot path.
+ *
+ * The reference (LSX-UniWue/recsys-22-user-attributes-recommender) has NO native code and no
+ * FFI: its plug-in surface is Python (modules/registry.py:19-22, init/factories/include/
+ * import_factory.py:51-81).  Each entry point below therefore cites the reference *call site*
+ * (file:line under /root/reference/src/asme/core) whose stock-ATen arithmetic it replaces; the
+ * Python binding a maintainer adds (ctypes, no torch types crossing the boundary) is shown in
+ * INTEGRATION.md and implemented in asme_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; kernels never allocate: scratch is
+ *     passed as (ws, ws_bytes) and sized by the matching *_workspace_bytes() query;
+ *   - all launches go to the caller's `stream`; entry points are re-entrant across streams, use
+ *     no host threads and never synchronise the host;
+ *   - ids are int64 (as delivered by the reference collate, data/collate.py:42-110), catalog
+ *     indices returned as int32, activations / weights fp32 unless a `dt` argument says otherwise
+ *     (ASME_DT_F32 = 0, ASME_DT_BF16 = 1);
+ *   - return value: 0 on success, negative ASME_ERR_* otherwise, message via asme_b200_last_error().
+ */
+#ifndef ASME_B200_H
+#define ASME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* asme_stream_t; /* == cudaStream_t */
+
+#define ASME_OK 0
+#define ASME_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define ASME_ERR_CUDA (-2)      /* CUDA runtime error (launch, attribute, ...) */
+#define ASME_ERR_WORKSPACE (-3) /* workspace too small */
+
+#define ASME_DT_F32 0
+#define ASME_DT_BF16 1
+
+#define ASME_MAX_ATTR 8
+
+const char* asme_b200_last_error(void);
+int asme_b200_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1-K4  fused embedding gather-and-sum (+LayerNorm +dropout)
+ * replaces: nn.Embedding item lookup            models/common/layers/sequence_embedding.py:87
+ *           positional lookup + add             models/common/layers/transformer_layers.py:68,75
+ *           attribute lookups / LinearUpscaler  models/kebert4rec/components.py:57-60, layers.py:24-27
+ *           LayerNorm + Dropout                 transformer_layers.py:76-78, kebert4rec/components.py:61-62
+ *   x = E[item] (+ P[t mod S]);  [x = drop_a(LN1(x))];  x += sum_a A_a[attr_a] + sum_b (sum_{j: id!=0} Wt_b[bag_b[j]] + bias_b);
+ *   [x = drop_b(LN2(x))]
+ * No branch on PAD/MASK ids (quirk Q9).  BERT4Rec: P = NULL (Q1), LN1 only.  KeBERT4Rec: LN2 only.
+ * SASRec: LN1 and LN2 (Q2).  Bag tables are passed TRANSPOSED, Wt = Linear.weight^T, (Va,H).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const int64_t* item_ids; /* (T) = (B*S) */
+    const float* item_table; /* (V,H) */
+    const float* pos_table;  /* (>=S,H) or NULL */
+    int n_attr;
+    const int64_t* attr_ids[ASME_MAX_ATTR];  /* (T) each */
+    const float* attr_table[ASME_MAX_ATTR];  /* (Va,H) */
+    int n_bag;
+    const int64_t* bag_ids[ASME_MAX_ATTR];   /* (T,width) each, id 0 contributes nothing */
+    int bag_width[ASME_MAX_ATTR];
+    const float* bag_table_t[ASME_MAX_ATTR]; /* (Va,H) = Linear.weight transposed */
+    const float* bag_bias[ASME_MAX_ATTR];    /* (H), always added */
+    const float* ln1_gamma;                  /* (H) or NULL */
+    const float* ln1_beta;
+    const float* ln2_gamma;                  /* (H) or NULL */
+    const float* ln2_beta;
+    float p_drop;                            /* 0 => identity (eval) */
+    uint64_t seed;
+    uint32_t site_a, site_b;                 /* dropout site ids of drop_a / drop_b */
+} asme_embed_desc;
+
+int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* out /*T,H*/,
+                        float* stats /* (4,T): mean1,rstd1,mean2,rstd2; may be NULL in eval */, asme_stream_t stream);
+/* backward: dOut (T,H) -> d_item_rows (T,H) = gradient w.r.t. (E[item]+P) rows, d_attr_rows (T,H) = gradient w.r.t.
+ * the attribute sum (== d_item_rows when LN1 is absent; may alias); LayerNorm parameter gradients are ACCUMULATED
+ * into dln (4,H): dgamma1,dbeta1,dgamma2,dbeta2 via deterministic two-stage column sums. */
+size_t asme_b200_embed_bwd_workspace_bytes(int T, int H);
+int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H, const float* d_out, const float* stats,
+                        float* d_item_rows, float* d_attr_rows, float* dln, void* ws, size_t ws_bytes,
+                        asme_stream_t stream);
+
+/* K21  deterministic embedding-table gradient: sort (id) -> segmented reduce -> one write per distinct row.
+ * replaces: autograd embedding_dense_backward (atomic scatter-add) of K1-K3/K13.
+ * d_table[ids[t], :] += d_rows[t, :] for all t with ids[t] != skip_id (skip_id = -1 keeps everything). */
+size_t asme_b200_embgrad_workspace_bytes(int T, int H);
+int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int H, float* d_table, int V,
+                                    int64_t skip_id, void* ws, size_t ws_bytes, asme_stream_t stream);
+/* d_pos[s,:] += sum_b d_rows[b*S+s,:]   (positions are generated, t mod S; transformer_layers.py:68) */
+int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H, float* d_pos, asme_stream_t stream);
+/* bag tables: d_table_t[id,:] += d_rows[t,:] for every bag entry id != 0; d_bias += column sums of d_rows */
+int asme_b200_colsum_accumulate(const float* x, int M, int N, float* out /*N, +=*/, void* ws, size_t ws_bytes,
+                                asme_stream_t stream);
+size_t asme_b200_colsum_workspace_bytes(int M, int N);
+
+/* ------------------------------------------------------------------------------------------
+ * K4/K6/K11  LayerNorm (eps 1e-5, biased variance) forward / backward
+ * replaces: nn.LayerNorm in SublayerConnection (transformer_layers.py:120-130) and the FFN modifier
+ *           (models/common/components/representation_modifier/ffn_modifier.py:18-26)
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int H, float* y,
+                            float* stats /* (2,M) mean,rstd or NULL */, asme_stream_t stream);
+/* dx = (d_residual ? d_residual : 0) + LN'(dy); dgamma/dbeta ACCUMULATED (dgb = (2,H)) */
+size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H);
+int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
+                            const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
+                            asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7/K9/K10/K11/K12  dense layers: C = epilogue(A x op(B)), fp32 SIMT path (strict 1e-5 parity mode)
+ * replaces: nn.Linear q/k/v/o (transformer_layers.py:190-199), FFN (transformer_layers.py:220),
+ *           modifier Linear (ffn_modifier.py:19), projections (layers.py:109,142-143), and their autograd.
+ *   trans_b = 1: B is (N,K) row-major (nn.Linear weight), C = A B^T       (forward)
+ *   trans_b = 0: B is (K,N) row-major,                     C = A B         (dX = dY W)
+ * epilogue, in order:  v = acc + bias[n];  if pre_act: pre_act[m,n] = v;  act;  v *= gelu'(mul_gelu_grad_of[m,n]);
+ *                      dropout(site);  v += residual[m,n];  C[m,n] = v
+ * ------------------------------------------------------------------------------------------ */
+#define ASME_ACT_NONE 0
+#define ASME_ACT_GELU 1
+typedef struct {
+    const float* bias;             /* (N) or NULL */
+    float* pre_act;                /* (M,N) or NULL */
+    int act;                       /* ASME_ACT_* */
+    const float* mul_gelu_grad_of; /* (M,N) or NULL: multiply by gelu'(.) (backward through GELU) */
+    float p_drop;                  /* epilogue dropout, 0 = none */
+    uint64_t seed;
+    uint32_t site;
+    const float* residual;         /* (M,N) or NULL */
+} asme_gemm_epilogue;
+
+int asme_b200_gemm(const float* A, const float* B, float* C, int M, int N, int K, int trans_b,
+                   const asme_gemm_epilogue* epi /* may be NULL */, asme_stream_t stream);
+/* weight / bias gradient: dW[N,K] (+)= dY[M,N]^T X[M,K], dbias[N] (+)= colsum(dY); split over M with a
+ * deterministic second-stage reduction. accumulate = 0 overwrites. */
+size_t asme_b200_gemm_wgrad_workspace_bytes(int M, int N, int K);
+int asme_b200_gemm_wgrad(const float* dY, const float* X, int M, int N, int K, float* dW, float* dbias /*NULL ok*/,
+                         int accumulate, void* ws, size_t ws_bytes, asme_stream_t stream);
+
+/* elementwise dropout with the same (seed, site, index) masks the fused epilogues use */
+int asme_b200_dropout(const float* x, float* y, long long n, float p, uint64_t seed, uint32_t site,
+                      asme_stream_t stream);
+/* y = a (*|+) b : post-fusion merge (kebert4rec/components.py:110-113); op 0 = add, 1 = multiply */
+int asme_b200_binary(const float* a, const float* b, float* y, long long n, int op, asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5+K8  masked attention for short sequences (S <= 256, head dim <= 64), mask generated in-kernel
+ * replaces: mask materialisation (models/transformer/sequence_representation.py:33-48) and
+ *           Attention.forward (transformer_layers.py:145-155): QK^T/sqrt(d) -> masked_fill(mask==0,-1e9)
+ *           -> softmax -> dropout -> .V ; a fully masked row attends uniformly to all S keys (Q4).
+ * qkv: (B*S, 3H) = [q | k | v] per token, head h at columns h*d..h*d+d-1 of each third.
+ * key_valid: (B,S) uint8 padding mask or NULL (bidirectional without mask). ctx: (B*S, H).
+ * stats: (2, B*heads*S) row max and row sum of exp (needed by backward), may be NULL in eval.
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_attn_fwd(const float* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                       float p_drop, uint64_t seed, uint32_t site, float* ctx, float* stats, asme_stream_t stream);
+int asme_b200_attn_bwd(const float* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                       float p_drop, uint64_t seed, uint32_t site, const float* ctx, const float* d_ctx,
+                       const float* stats, float* d_qkv /* (B*S,3H) */, void* ws, size_t ws_bytes,
+                       asme_stream_t stream);
+size_t asme_b200_attn_bwd_workspace_bytes(int B, int S, int heads);
+
+/* ------------------------------------------------------------------------------------------
+ * K12+K15+K18-K20  full-catalog scoring fused with top-k + exact target rank (logits never reach HBM)
+ * replaces: ItemEmbeddingProjectionLayer / LinearProjectionLayer (layers.py:105-143) on the selected row
+ *           (masked_training_module.py:80-91, next_item_prediction_training_module.py:226-244),
+ *           AllItemsSampler multi-hot (metrics/container/metrics_sampler.py:45-71) and the per-metric
+ *           full argsort (metrics/common.py:18-27).
+ * Scores rows Hrows (R,H) against catalog slice W (Vloc,H) (+bias), global ids v0..v0+Vloc-1.
+ * Per row: top-k (score desc, id asc), n_greater = #{s_j > s_t}, n_tie_lower = #{j < t : s_j == s_t} given the
+ * target score s_t (target_score (R), computed by asme_b200_score_targets; shards all-reduce it first).
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_score_targets(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                            const int64_t* target, float* target_score /* (R) +=, owner shard only */,
+                            asme_stream_t stream);
+size_t asme_b200_score_topk_workspace_bytes(int R, int Vloc, int k);
+int asme_b200_score_topk_rank(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                              const int64_t* target, const float* target_score, int k, float* topk_val /*R,k*/,
+                              int32_t* topk_idx /*R,k*/, int32_t* n_greater /*R*/, int32_t* n_tie_lower /*R*/,
+                              void* ws, size_t ws_bytes, asme_stream_t stream);
+/* k-way merge of G partial top-k lists (vals/idx: (G,R,k)) with (score desc, id asc) order */
+int asme_b200_topk_merge(const float* vals, const int32_t* idx, int G, int R, int k, float* out_val,
+                         int32_t* out_idx, asme_stream_t stream);
+/* K20: sums over the batch of recall/NDCG/MRR/precision @ ks from the 1-based target rank
+ * (metrics/common.py:66-175, metrics/mrr.py:26-37). out: (4, n_k) sums, ACCUMULATED. */
+int asme_b200_ranking_metrics(const int32_t* rank, int R, const int32_t* ks, int n_k, float* out, asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K12+K16  scoring fused with log-softmax cross-entropy (ignore_index rows are skipped by the caller:
+ * rows = positions with target != pad).  replaces layers.py:105-143 + nn.CrossEntropyLoss
+ * (masked_training_module.py:107-111, losses/sasrec/sas_rec_losses.py:16-32).
+ * partial: per row (max, sumexp, target logit) over the slice [v0, v0+Vloc) -- shards combine with
+ * all-reduce(MAX)/(SUM).  loss_sum += sum_r (max_r + log(sumexp_r) - target_logit_r).
+ * ------------------------------------------------------------------------------------------ */
+size_t asme_b200_score_ce_workspace_bytes(int R, int Vloc);
+int asme_b200_score_ce_partial(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                               const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
+                               void* ws, size_t ws_bytes, asme_stream_t stream);
+int asme_b200_ce_loss_from_partials(const float* row_max, const float* row_sumexp, const float* target_logit, int R,
+                                    float* lse /*R*/, float* loss_sum /*1, +=*/, asme_stream_t stream);
+/* backward: dlogit = (softmax - onehot) * scale; dH (R,H) = dlogit W (overwritten; shards all-reduce),
+ * dW (Vloc,H) += dlogit^T H, dbias (Vloc) += colsum(dlogit). */
+size_t asme_b200_score_ce_bwd_workspace_bytes(int R, int H, int Vloc);
+int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                           const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
+                           void* ws, size_t ws_bytes, asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K13+K17  SASRec positive/negative dot products fused with the BCE loss
+ * replaces: SASRecProjectionComponent.forward train branch (models/sasrec/components.py:35-44) and
+ *           sas_rec_binary_cross_entropy (losses/sasrec/sas_rec_losses.py:47-75).
+ * sums[0] += sum_t mask_t (-log(sigmoid(p_t)+1e-24) - log(1-sigmoid(n_t)+1e-24)); sums[1] += sum_t mask_t
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_posneg_bce_fwd(const float* Hseq /*T,H*/, const float* E, const int64_t* pos, const int64_t* neg,
+                             const uint8_t* mask, int T, int H, float* pos_logit, float* neg_logit, float* sums,
+                             asme_stream_t stream);
+/* dH (T,H) overwritten; d_pos_rows / d_neg_rows (T,H) = per-token gradients of E[pos], E[neg] (feed embgrad). */
+int asme_b200_posneg_bce_bwd(const float* Hseq, const float* E, const int64_t* pos, const int64_t* neg,
+                             const uint8_t* mask, int T, int H, const float* pos_logit, const float* neg_logit,
+                             const float* sums, float dloss, float* dH, float* d_pos_rows, float* d_neg_rows,
+                             asme_stream_t stream);
+
+/* rows gather: out[r,:] = x[row_index[r],:]  (K15 row select) and its transpose scatter (rows are distinct) */
+int asme_b200_gather_rows(const float* x, const int64_t* row_index, int R, int H, float* out, asme_stream_t stream);
+int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, int H, float* out /*T,H*/,
+                           asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K22  fused Adam over the flat parameter arena (torch.optim.Adam semantics: L2 decay added to the gradient;
+ * reference defaults beta = (0.99, 0.998), masked_training_module.py:165-168)
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int step, asme_stream_t stream);
+int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASME_B200_H */

@@ -1,0 +1,129 @@
+"""ctypes binding of libasme_b200.so (the C ABI declared in include/asme_b200.h).
+
+Only plain pointers, sizes and scalars cross the boundary: tensors are passed as
+``tensor.data_ptr()`` and the launch stream as ``torch.cuda.current_stream().cuda_stream``.
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint32, \
+    c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libasme_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "asme_b200.h")
+
+ASME_MAX_ATTR = 8
+ACT_NONE, ACT_GELU = 0, 1
+
+
+class EmbedDesc(Structure):
+    """mirror of ``asme_embed_desc``"""
+    _fields_ = [
+        ("item_ids", c_void_p), ("item_table", c_void_p), ("pos_table", c_void_p),
+        ("n_attr", c_int), ("attr_ids", c_void_p * ASME_MAX_ATTR), ("attr_table", c_void_p * ASME_MAX_ATTR),
+        ("n_bag", c_int), ("bag_ids", c_void_p * ASME_MAX_ATTR), ("bag_width", c_int * ASME_MAX_ATTR),
+        ("bag_table_t", c_void_p * ASME_MAX_ATTR), ("bag_bias", c_void_p * ASME_MAX_ATTR),
+        ("ln1_gamma", c_void_p), ("ln1_beta", c_void_p), ("ln2_gamma", c_void_p), ("ln2_beta", c_void_p),
+        ("p_drop", c_float), ("seed", c_uint64), ("site_a", c_uint32), ("site_b", c_uint32),
+    ]
+
+
+class GemmEpilogue(Structure):
+    """mirror of ``asme_gemm_epilogue``"""
+    _fields_ = [
+        ("bias", c_void_p), ("pre_act", c_void_p), ("act", c_int), ("mul_gelu_grad_of", c_void_p),
+        ("p_drop", c_float), ("seed", c_uint64), ("site", c_uint32), ("residual", c_void_p),
+    ]
+
+
+P = c_void_p
+_PROTOTYPES = {
+    # name: (restype, argtypes)
+    "asme_b200_last_error": (c_char_p, []),
+    "asme_b200_abi_version": (c_int, []),
+    "asme_b200_embed_fwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P]),
+    "asme_b200_embed_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_embed_bwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_embgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_embgrad_sorted_reduce": (c_int, [P, c_int, P, c_int, P, c_int, c_int64, P, c_size_t, P]),
+    "asme_b200_posgrad_reduce": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "asme_b200_colsum_accumulate": (c_int, [P, c_int, c_int, P, P, c_size_t, P]),
+    "asme_b200_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_layernorm_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P]),
+    "asme_b200_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_layernorm_bwd": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "asme_b200_gemm": (c_int, [P, P, P, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), P]),
+    "asme_b200_gemm_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "asme_b200_gemm_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
+    "asme_b200_dropout": (c_int, [P, P, c_longlong, c_float, c_uint64, c_uint32, P]),
+    "asme_b200_binary": (c_int, [P, P, P, c_longlong, c_int, P]),
+    "asme_b200_attn_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P]),
+    "asme_b200_attn_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P, P, P,
+                                   c_size_t, P]),
+    "asme_b200_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "asme_b200_score_targets": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P]),
+    "asme_b200_score_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "asme_b200_score_topk_rank": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_topk_merge": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "asme_b200_ranking_metrics": (c_int, [P, c_int, P, c_int, P, P]),
+    "asme_b200_score_ce_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_ce_loss_from_partials": (c_int, [P, P, P, c_int, P, P, P]),
+    "asme_b200_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "asme_b200_score_ce_bwd": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P]),
+    "asme_b200_posneg_bce_fwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),
+    "asme_b200_posneg_bce_bwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, c_float, P, P, P, P]),
+    "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P]),
+    "asme_b200_scatter_rows": (c_int, [P, P, c_int, c_int, P, P]),
+    "asme_b200_adam_step": (c_int, [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "asme_b200_fill": (c_int, [P, c_longlong, c_float, P]),
+}
+
+_lib = None
+launch_count = 0   # number of C-ABI kernel-launching calls made (bench.py reports it)
+
+
+def header_symbols():
+    """Function names declared in include/asme_b200.h (used by the CPU-side symbol test)."""
+    import re
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(asme_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Load the library (once). Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"asme_b200: {LIB_PATH} not found. Build it with `python __graft_entry__.py` (or "
+            f"recsys-22-user-attributes-recommender_b200/build.py). There is no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().asme_b200_last_error()
+        raise RuntimeError(f"asme_b200 {what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on error."""
+    global launch_count
+    fn = getattr(load(), name)
+    launch_count += 1
+    check(fn(*args), name)
+
+
+def query(name, *args):
+    return int(getattr(load(), name)(*args))

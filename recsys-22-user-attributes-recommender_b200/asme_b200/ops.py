@@ -1,0 +1,378 @@
+"""Tensor-level wrappers around the C ABI (include/asme_b200.h).
+
+PyTorch is used for device memory and streams only: every function takes CUDA tensors, hands their
+``data_ptr()`` and the current stream to ``libasme_b200.so`` and returns freshly allocated output
+tensors.  No arithmetic happens in torch on this path and there is no fallback -- a CPU tensor or a
+missing library raises.
+"""
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EmbedDesc, GemmEpilogue
+
+# dropout "sites": every dropout application in the model has its own Philox stream
+SITE_EMBED_A, SITE_EMBED_B = 1, 2
+SITE_LAYER_BASE = 16          # + 8 * layer + {0: attn probs, 1: attn out, 2: ffn inner, 3: ffn out, 4: block end}
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t: torch.Tensor, name: str = "tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"asme_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"asme_b200: {name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64(t: torch.Tensor, name: str = "ids") -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"asme_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _u8(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype == torch.bool:
+        t = t.contiguous().view(torch.uint8)
+    elif t.dtype != torch.uint8:
+        t = t.to(torch.uint8)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def workspace(nbytes: int, device: torch.device, slot: int = 0) -> torch.Tensor:
+    """A cached, grow-only scratch buffer per (device, slot); kernels on one stream serialise on it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# embedding
+# ------------------------------------------------------------------------------------------------
+class EmbedSpec:
+    """Python-side description of one fused embedding call (mirrors ``asme_embed_desc``)."""
+
+    def __init__(self, item_ids, item_table, pos_table=None, attrs: Sequence[Tuple[torch.Tensor, torch.Tensor]] = (),
+                 bags: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = (), ln1=None, ln2=None, p_drop=0.0,
+                 seed=0, site_a=SITE_EMBED_A, site_b=SITE_EMBED_B):
+        self.item_ids = _i64(item_ids)
+        self.item_table = _f32(item_table, "item_table")
+        self.pos_table = None if pos_table is None else _f32(pos_table, "pos_table")
+        self.attrs = [(_i64(i), _f32(t, "attr_table")) for i, t in attrs]
+        # bags: (ids (T,width), table_t (Va,H) = Linear.weight^T, bias (H))
+        self.bags = [(_i64(i), _f32(t, "bag_table_t"), _f32(b, "bag_bias")) for i, t, b in bags]
+        self.ln1 = None if ln1 is None else (_f32(ln1[0]), _f32(ln1[1]))
+        self.ln2 = None if ln2 is None else (_f32(ln2[0]), _f32(ln2[1]))
+        self.p_drop, self.seed, self.site_a, self.site_b = float(p_drop), int(seed), site_a, site_b
+        if len(self.attrs) > _lib.ASME_MAX_ATTR or len(self.bags) > _lib.ASME_MAX_ATTR:
+            raise RuntimeError("asme_b200: too many attribute tables")
+
+    def desc(self) -> EmbedDesc:
+        d = EmbedDesc()
+        d.item_ids, d.item_table = self.item_ids.data_ptr(), self.item_table.data_ptr()
+        d.pos_table = None if self.pos_table is None else self.pos_table.data_ptr()
+        d.n_attr = len(self.attrs)
+        for k, (ids, tab) in enumerate(self.attrs):
+            d.attr_ids[k], d.attr_table[k] = ids.data_ptr(), tab.data_ptr()
+        d.n_bag = len(self.bags)
+        for k, (ids, tab, bias) in enumerate(self.bags):
+            d.bag_ids[k], d.bag_width[k] = ids.data_ptr(), ids.shape[-1]
+            d.bag_table_t[k], d.bag_bias[k] = tab.data_ptr(), bias.data_ptr()
+        if self.ln1 is not None:
+            d.ln1_gamma, d.ln1_beta = self.ln1[0].data_ptr(), self.ln1[1].data_ptr()
+        if self.ln2 is not None:
+            d.ln2_gamma, d.ln2_beta = self.ln2[0].data_ptr(), self.ln2[1].data_ptr()
+        d.p_drop, d.seed, d.site_a, d.site_b = self.p_drop, self.seed, self.site_a, self.site_b
+        return d
+
+
+def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False):
+    H = spec.item_table.shape[1]
+    T = B * S
+    out = torch.empty(T, H, dtype=torch.float32, device=spec.item_table.device)
+    stats = torch.empty(4, T, dtype=torch.float32, device=out.device) if save_stats else None
+    d = spec.desc()
+    _lib.call("asme_b200_embed_fwd", ctypes.byref(d), T, S, H, _p(out), _p(stats), _stream())
+    return out, stats
+
+
+def embed_bwd(spec: EmbedSpec, B: int, S: int, d_out: torch.Tensor, stats: Optional[torch.Tensor], dln: Optional[torch.Tensor]):
+    """returns (d_item_rows, d_attr_rows); accumulates LayerNorm parameter grads into dln (4,H)."""
+    H = spec.item_table.shape[1]
+    T = B * S
+    d_out = _f32(d_out)
+    d_item = torch.empty(T, H, dtype=torch.float32, device=d_out.device)
+    two = spec.ln1 is not None and (spec.attrs or spec.bags)
+    d_attr = torch.empty_like(d_item) if two else d_item
+    ws_bytes = _lib.query("asme_b200_embed_bwd_workspace_bytes", T, H)
+    ws = workspace(ws_bytes, d_out.device)
+    d = spec.desc()
+    _lib.call("asme_b200_embed_bwd", ctypes.byref(d), T, S, H, _p(d_out), _p(stats), _p(d_item), _p(d_attr), _p(dln),
+              _p(ws), ws.numel(), _stream())
+    return d_item, d_attr
+
+
+def embgrad_sorted_reduce(ids: torch.Tensor, d_rows: torch.Tensor, d_table: torch.Tensor, skip_id: int = -1):
+    """d_table[ids[t]] += d_rows[t] (deterministic: sort -> segmented reduce)."""
+    ids = _i64(ids).reshape(-1)
+    d_rows = _f32(d_rows)
+    T, H = ids.numel(), d_table.shape[1]
+    ws_bytes = _lib.query("asme_b200_embgrad_workspace_bytes", T, H)
+    ws = workspace(ws_bytes, d_rows.device)
+    _lib.call("asme_b200_embgrad_sorted_reduce", _p(ids), T, _p(d_rows), H, _p(d_table), d_table.shape[0], skip_id,
+              _p(ws), ws.numel(), _stream())
+
+
+def posgrad_reduce(d_rows: torch.Tensor, B: int, S: int, d_pos: torch.Tensor):
+    _lib.call("asme_b200_posgrad_reduce", _p(_f32(d_rows)), B, S, d_rows.shape[-1], _p(d_pos), _stream())
+
+
+def colsum_accumulate(x: torch.Tensor, out: torch.Tensor):
+    x = _f32(x)
+    M, N = x.shape
+    ws_bytes = _lib.query("asme_b200_colsum_workspace_bytes", M, N)
+    ws = workspace(ws_bytes, x.device)
+    _lib.call("asme_b200_colsum_accumulate", _p(x), M, N, _p(out), _p(ws), ws.numel(), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save_stats: bool = False):
+    x = _f32(x)
+    M, H = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(2, M, dtype=torch.float32, device=x.device) if save_stats else None
+    _lib.call("asme_b200_layernorm_fwd", _p(x), _p(gamma), _p(beta), M, H, _p(y), _p(stats), _stream())
+    return y, stats
+
+
+def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[torch.Tensor] = None):
+    """dx = d_residual + LN'(dy); accumulates (dgamma, dbeta) into dgb (2,H)."""
+    dy, x = _f32(dy), _f32(x)
+    M, H = x.shape
+    dx = torch.empty_like(x)
+    ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
+    ws = workspace(ws_bytes, x.device)
+    _lib.call("asme_b200_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
+              _p(ws), ws.numel(), _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, trans_b: bool = True, bias=None, act: int = 0, pre_act_out: bool = False,
+         mul_gelu_grad_of=None, p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out=None):
+    """C = epilogue(A @ B^T) (trans_b) or epilogue(A @ B).  Returns C or (C, pre_act)."""
+    a, b = _f32(a, "A"), _f32(b, "B")
+    M, K = a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    assert (b.shape[1] if trans_b else b.shape[0]) == K, "gemm: inner dimensions differ"
+    c = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=a.device)
+    pre = torch.empty_like(c) if pre_act_out else None
+    epi = GemmEpilogue()
+    epi.bias = None if bias is None else bias.data_ptr()
+    epi.pre_act = None if pre is None else pre.data_ptr()
+    epi.act = act
+    epi.mul_gelu_grad_of = None if mul_gelu_grad_of is None else mul_gelu_grad_of.data_ptr()
+    epi.p_drop, epi.seed, epi.site = float(p_drop), int(seed), int(site)
+    epi.residual = None if residual is None else residual.data_ptr()
+    _lib.call("asme_b200_gemm", _p(a), _p(b), _p(c), M, N, K, 1 if trans_b else 0, ctypes.byref(epi), _stream())
+    return (c, pre) if pre_act_out else c
+
+
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True):
+    """dW (+)= dY^T X, dbias (+)= colsum(dY)."""
+    dy, x = _f32(dy), _f32(x)
+    M, N = dy.shape
+    K = x.shape[1]
+    ws_bytes = _lib.query("asme_b200_gemm_wgrad_workspace_bytes", M, N, K)
+    ws = workspace(ws_bytes, x.device)
+    _lib.call("asme_b200_gemm_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws),
+              ws.numel(), _stream())
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
+    x = _f32(x)
+    y = torch.empty_like(x)
+    _lib.call("asme_b200_dropout", _p(x), _p(y), x.numel(), float(p), int(seed), int(site), _stream())
+    return y
+
+
+def binary(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
+    a, b = _f32(a), _f32(b)
+    y = torch.empty_like(a)
+    _lib.call("asme_b200_binary", _p(a), _p(b), _p(y), a.numel(), {"add": 0, "multiply": 1}[op], _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attn_fwd(qkv: torch.Tensor, key_valid: Optional[torch.Tensor], B: int, S: int, heads: int, causal: bool,
+             p_drop: float = 0.0, seed: int = 0, site: int = 0, save_stats: bool = False):
+    qkv = _f32(qkv)
+    H = qkv.shape[1] // 3
+    d = H // heads
+    kv = _u8(key_valid)
+    ctx = torch.empty(B * S, H, dtype=torch.float32, device=qkv.device)
+    stats = torch.empty(2, B * heads * S, dtype=torch.float32, device=qkv.device) if save_stats else None
+    _lib.call("asme_b200_attn_fwd", _p(qkv), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed),
+              int(site), _p(ctx), _p(stats), _stream())
+    return ctx, stats
+
+
+def attn_bwd(qkv, key_valid, B, S, heads, causal, ctx, d_ctx, stats, p_drop=0.0, seed=0, site=0):
+    qkv, ctx, d_ctx = _f32(qkv), _f32(ctx), _f32(d_ctx)
+    H = qkv.shape[1] // 3
+    d = H // heads
+    kv = _u8(key_valid)
+    d_qkv = torch.empty_like(qkv)
+    ws_bytes = _lib.query("asme_b200_attn_bwd_workspace_bytes", B, S, heads)
+    ws = workspace(ws_bytes, qkv.device)
+    _lib.call("asme_b200_attn_bwd", _p(qkv), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed),
+              int(site), _p(ctx), _p(d_ctx), _p(stats), _p(d_qkv), _p(ws), ws.numel(), _stream())
+    return d_qkv
+
+
+# ------------------------------------------------------------------------------------------------
+# catalog scoring
+# ------------------------------------------------------------------------------------------------
+def score_targets(h: torch.Tensor, w: torch.Tensor, bias, target: torch.Tensor, v0: int = 0, out=None) -> torch.Tensor:
+    h, w = _f32(h), _f32(w)
+    R, H = h.shape
+    if out is None:
+        out = torch.zeros(R, dtype=torch.float32, device=h.device)
+    _lib.call("asme_b200_score_targets", _p(h), R, H, _p(w), _p(bias), v0, w.shape[0], _p(_i64(target)), _p(out), _stream())
+    return out
+
+
+def score_topk_rank(h, w, bias, k: int, target=None, target_score=None, v0: int = 0):
+    """returns (topk_val (R,k), topk_idx (R,k) int32, n_greater (R) int32, n_tie_lower (R) int32)"""
+    h, w = _f32(h), _f32(w)
+    R, H = h.shape
+    Vloc = w.shape[0]
+    dev = h.device
+    val = torch.empty(R, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(R, k, dtype=torch.int32, device=dev)
+    ng = torch.zeros(R, dtype=torch.int32, device=dev) if target is not None else None
+    nt = torch.zeros(R, dtype=torch.int32, device=dev) if target is not None else None
+    ws_bytes = _lib.query("asme_b200_score_topk_workspace_bytes", R, Vloc, k)
+    ws = workspace(ws_bytes, dev)
+    tgt = None if target is None else _i64(target)
+    _lib.call("asme_b200_score_topk_rank", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(tgt), _p(target_score), k, _p(val),
+              _p(idx), _p(ng), _p(nt), _p(ws), ws.numel(), _stream())
+    return val, idx, ng, nt
+
+
+def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):
+    """vals/idx: (G,R,k) partial lists -> merged (R,k)"""
+    vals, idx = _f32(vals), idx.contiguous()
+    G, R, kk = vals.shape
+    assert kk == k
+    out_v = torch.empty(R, k, dtype=torch.float32, device=vals.device)
+    out_i = torch.empty(R, k, dtype=torch.int32, device=vals.device)
+    _lib.call("asme_b200_topk_merge", _p(vals), _p(idx), G, R, k, _p(out_v), _p(out_i), _stream())
+    return out_v, out_i
+
+
+def ranking_metrics(rank: torch.Tensor, ks: torch.Tensor, out: torch.Tensor):
+    """out (4, n_k) += sums of recall, NDCG, MRR, precision @ ks over the batch."""
+    _lib.call("asme_b200_ranking_metrics", _p(rank), rank.numel(), _p(ks), ks.numel(), _p(out), _stream())
+
+
+def score_ce_partial(h, w, bias, target, v0: int = 0):
+    """returns (row_max, row_sumexp, target_logit) over the slice [v0, v0+Vloc)"""
+    h, w = _f32(h), _f32(w)
+    R, H = h.shape
+    Vloc = w.shape[0]
+    dev = h.device
+    rmax = torch.empty(R, dtype=torch.float32, device=dev)
+    rsum = torch.empty_like(rmax)
+    tl = torch.empty_like(rmax)
+    ws_bytes = _lib.query("asme_b200_score_ce_workspace_bytes", R, Vloc)
+    ws = workspace(ws_bytes, dev)
+    _lib.call("asme_b200_score_ce_partial", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
+              _p(tl), _p(ws), ws.numel(), _stream())
+    return rmax, rsum, tl
+
+
+def ce_loss_from_partials(rmax, rsum, tl, loss_sum: torch.Tensor):
+    lse = torch.empty_like(rmax)
+    _lib.call("asme_b200_ce_loss_from_partials", _p(rmax), _p(rsum), _p(tl), rmax.numel(), _p(lse), _p(loss_sum), _stream())
+    return lse
+
+
+def score_ce_bwd(h, w, bias, target, lse, scale: float, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
+                 need_dh: bool = True, v0: int = 0):
+    h, w = _f32(h), _f32(w)
+    R, H = h.shape
+    Vloc = w.shape[0]
+    dh = torch.empty_like(h) if need_dh else None
+    ws_bytes = _lib.query("asme_b200_score_ce_bwd_workspace_bytes", R, H, Vloc)
+    ws = workspace(ws_bytes, h.device)
+    _lib.call("asme_b200_score_ce_bwd", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
+              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _stream())
+    return dh
+
+
+def posneg_bce_fwd(h, table, pos, neg, mask, sums: Optional[torch.Tensor]):
+    h, table = _f32(h), _f32(table)
+    T, H = h.shape
+    pl = torch.empty(T, dtype=torch.float32, device=h.device)
+    nl = torch.empty_like(pl)
+    _lib.call("asme_b200_posneg_bce_fwd", _p(h), _p(table), _p(_i64(pos)), _p(_i64(neg)), _p(_u8(mask)), T, H, _p(pl),
+              _p(nl), _p(sums), _stream())
+    return pl, nl
+
+
+def posneg_bce_bwd(h, table, pos, neg, mask, pl, nl, sums, dloss: float = 1.0):
+    h, table = _f32(h), _f32(table)
+    T, H = h.shape
+    dh = torch.empty_like(h)
+    dpos = torch.empty_like(h)
+    dneg = torch.empty_like(h)
+    _lib.call("asme_b200_posneg_bce_bwd", _p(h), _p(table), _p(_i64(pos)), _p(_i64(neg)), _p(_u8(mask)), T, H, _p(pl),
+              _p(nl), _p(sums), float(dloss), _p(dh), _p(dpos), _p(dneg), _stream())
+    return dh, dpos, dneg
+
+
+def gather_rows(x: torch.Tensor, row_index: torch.Tensor) -> torch.Tensor:
+    x = _f32(x)
+    R, H = row_index.numel(), x.shape[1]
+    out = torch.empty(R, H, dtype=torch.float32, device=x.device)
+    _lib.call("asme_b200_gather_rows", _p(x), _p(_i64(row_index)), R, H, _p(out), _stream())
+    return out
+
+
+def scatter_rows(rows: torch.Tensor, row_index: torch.Tensor, out: torch.Tensor):
+    rows = _f32(rows)
+    _lib.call("asme_b200_scatter_rows", _p(rows), _p(_i64(row_index)), rows.shape[0], rows.shape[1], _p(out), _stream())
+
+
+def adam_step(param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    _lib.call("asme_b200_adam_step", _p(param), _p(grad), _p(m), _p(v), param.numel(), float(lr), float(beta1),
+              float(beta2), float(eps), float(weight_decay), int(step), _stream())
+
+
+def fill(x: torch.Tensor, value: float):
+    _lib.call("asme_b200_fill", _p(x), x.numel(), float(value), _stream())

@@ -1,0 +1,98 @@
+// Shared device/host helpers for the asme_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/asme_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error reporting: every extern "C" entry point returns 0 or a negative code and records a message
+// ---------------------------------------------------------------------------------------------
+void asme_set_error(const char* fmt, ...);
+
+#define ASME_REQUIRE(cond, ...)                  \
+    do {                                         \
+        if (!(cond)) {                           \
+            asme_set_error(__VA_ARGS__);         \
+            return ASME_ERR_INVALID;             \
+        }                                        \
+    } while (0)
+
+#define ASME_CUDA_OK(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            asme_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return ASME_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define ASME_LAUNCH_OK() ASME_CUDA_OK(cudaGetLastError())
+
+__host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#define ASME_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// reduction over an aligned sub-group of LANES lanes (LANES power of two <= 32)
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// d/dx gelu(x) = Phi(x) + x * phi(x)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// Philox4x32-7 counter-based generator: dropout masks are a pure function of
+// (seed, site, element index) so the backward pass recomputes them instead of storing them.
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// keep-probability scale for element `idx` of dropout site `site`: 0 if dropped, 1/(1-p) if kept
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
+    const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0u, (uint32_t)seed,
+                               (uint32_t)(seed >> 32));
+    const uint32_t lane = (uint32_t)idx & 3u;
+    const uint32_t bits = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+    const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);   // [0,1)
+    return u < p ? 0.0f : inv_keep;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}

@@ -1,0 +1,593 @@
+// Row-wise HBM-bound kernels: fused embedding gather-and-sum (+LayerNorm +dropout), LayerNorm
+// forward/backward, column sums, positional-gradient reduce, elementwise helpers.
+//
+// Thread mapping (all kernels): a row of H fp32 is owned by an aligned group of LANES lanes
+// (LANES = min(32, H/4)); lane l of the group owns the 128-bit column chunks (c*LANES + l)*4..+3,
+// c < CH = H/(4*LANES).  Every global access is a coalesced float4 (128-bit) transaction and the
+// LayerNorm reductions are xor-shuffles inside the group -- no shared memory on the forward path.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+// ---------------------------------------------------------------------------------------------
+// error string (thread local) -- shared by all translation units
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+void asme_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* asme_b200_last_error(void) { return g_last_error; }
+extern "C" int asme_b200_abi_version(void) { return 1; }
+
+#define LN_EPS 1e-5f
+
+// dropout scales for 4 consecutive elements starting at idx (idx % 4 == 0): one Philox call
+__device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
+    const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0u, (uint32_t)seed,
+                               (uint32_t)(seed >> 32));
+    float4 s;
+    s.x = ((float)(r.x >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    s.y = ((float)(r.y >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    s.z = ((float)(r.z >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    s.w = ((float)(r.w >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    return s;
+}
+
+template <int LANES, int CH>
+struct Row {
+    float4 v[CH];
+    __device__ __forceinline__ void load(const float* base, int lane) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) v[c] = ldg4(base + (c * LANES + lane) * 4);
+    }
+    __device__ __forceinline__ void add(const float* base, int lane) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) add4(v[c], ldg4(base + (c * LANES + lane) * 4));
+    }
+    __device__ __forceinline__ void store(float* base, int lane) const {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) *reinterpret_cast<float4*>(base + (c * LANES + lane) * 4) = v[c];
+    }
+    __device__ __forceinline__ float sum() const {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+        return group_sum<LANES>(s);
+    }
+};
+
+// y = (x - mean) * rstd * gamma + beta ; returns xhat in `x`, y in `y`
+template <int LANES, int CH>
+__device__ __forceinline__ void ln_forward(Row<LANES, CH>& x, Row<LANES, CH>& y, const float* gamma, const float* beta,
+                                           int lane, int H, float& mean, float& rstd) {
+    mean = x.sum() / (float)H;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        x.v[c].x -= mean; x.v[c].y -= mean; x.v[c].z -= mean; x.v[c].w -= mean;
+        sq += (x.v[c].x * x.v[c].x + x.v[c].y * x.v[c].y) + (x.v[c].z * x.v[c].z + x.v[c].w * x.v[c].w);
+    }
+    sq = group_sum<LANES>(sq);
+    rstd = rsqrtf(sq / (float)H + LN_EPS);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float4 g = ldg4(gamma + (c * LANES + lane) * 4);
+        const float4 b = ldg4(beta + (c * LANES + lane) * 4);
+        x.v[c].x *= rstd; x.v[c].y *= rstd; x.v[c].z *= rstd; x.v[c].w *= rstd;
+        y.v[c].x = x.v[c].x * g.x + b.x; y.v[c].y = x.v[c].y * g.y + b.y;
+        y.v[c].z = x.v[c].z * g.z + b.z; y.v[c].w = x.v[c].w * g.w + b.w;
+    }
+}
+
+// g (in: dL/dy, out: dL/dx) ; xhat given; accumulates dgamma/dbeta into per-thread registers
+template <int LANES, int CH>
+__device__ __forceinline__ void ln_backward(Row<LANES, CH>& g, const Row<LANES, CH>& xhat, const float* gamma, int lane,
+                                            int H, float rstd, Row<LANES, CH>& dgamma, Row<LANES, CH>& dbeta) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float4 gm = ldg4(gamma + (c * LANES + lane) * 4);
+        float4& gv = g.v[c];
+        const float4& xh = xhat.v[c];
+        dgamma.v[c].x += gv.x * xh.x; dgamma.v[c].y += gv.y * xh.y; dgamma.v[c].z += gv.z * xh.z; dgamma.v[c].w += gv.w * xh.w;
+        add4(dbeta.v[c], gv);
+        gv.x *= gm.x; gv.y *= gm.y; gv.z *= gm.z; gv.w *= gm.w;
+        s1 += (gv.x + gv.y) + (gv.z + gv.w);
+        s2 += (gv.x * xh.x + gv.y * xh.y) + (gv.z * xh.z + gv.w * xh.w);
+    }
+    s1 = group_sum<LANES>(s1) / (float)H;
+    s2 = group_sum<LANES>(s2) / (float)H;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        float4& gv = g.v[c];
+        const float4& xh = xhat.v[c];
+        gv.x = rstd * (gv.x - s1 - xh.x * s2); gv.y = rstd * (gv.y - s1 - xh.y * s2);
+        gv.z = rstd * (gv.z - s1 - xh.z * s2); gv.w = rstd * (gv.w - s1 - xh.w * s2);
+    }
+}
+
+template <int LANES, int CH>
+__device__ __forceinline__ void apply_dropout(Row<LANES, CH>& x, uint64_t seed, uint32_t site, long long row, int H,
+                                              int lane, float p, float inv_keep) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float4 s = dropout_scale4(seed, site, (uint64_t)row * H + (c * LANES + lane) * 4, p, inv_keep);
+        x.v[c].x *= s.x; x.v[c].y *= s.y; x.v[c].z *= s.z; x.v[c].w *= s.w;
+    }
+}
+
+template <int LANES, int CH>
+__device__ __forceinline__ void zero_row(Row<LANES, CH>& r) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) r.v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// deterministic block-level reduction of per-group register partials into out[block][slot][H]
+template <int LANES, int CH>
+__device__ __forceinline__ void block_reduce_rows(const Row<LANES, CH>& r, float* smem /* groups*H */, float* out, int H,
+                                                  int group_in_block, int groups_per_block, int lane) {
+    __syncthreads();
+    r.store(smem + (size_t)group_in_block * H, lane);
+    __syncthreads();
+    for (int col = threadIdx.x; col < H; col += blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < groups_per_block; ++g) s += smem[(size_t)g * H + col];
+        out[col] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused embedding forward
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int CH>
+__device__ __forceinline__ void embed_gather_attrs(Row<LANES, CH>& x, const asme_embed_desc& d, long long t, int H, int lane) {
+    for (int a = 0; a < d.n_attr; ++a) {
+        const long long id = __ldg(d.attr_ids[a] + t);
+        x.add(d.attr_table[a] + id * H, lane);
+    }
+    for (int b = 0; b < d.n_bag; ++b) {
+        x.add(d.bag_bias[b], lane);
+        const int w = d.bag_width[b];
+        for (int j = 0; j < w; ++j) {
+            const long long id = __ldg(d.bag_ids[b] + t * w + j);
+            if (id != 0) x.add(d.bag_table_t[b] + id * H, lane);   // group-uniform branch
+        }
+    }
+}
+
+template <int LANES, int CH>
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d, int T, int S, int H, float* __restrict__ out,
+                                                        float* __restrict__ stats) {
+    const int lane = threadIdx.x % LANES;
+    const long long t = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
+    if (t >= T) return;
+    const float inv_keep = d.p_drop > 0.f ? 1.0f / (1.0f - d.p_drop) : 1.0f;
+    Row<LANES, CH> x, y;
+    const long long item = __ldg(d.item_ids + t);
+    x.load(d.item_table + item * H, lane);
+    if (d.pos_table) x.add(d.pos_table + (long long)(t % S) * H, lane);
+    if (d.ln1_gamma) {
+        float mean, rstd;
+        ln_forward<LANES, CH>(x, y, d.ln1_gamma, d.ln1_beta, lane, H, mean, rstd);
+        if (stats && lane == 0) { stats[t] = mean; stats[(size_t)T + t] = rstd; }
+        x = y;
+        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, d.seed, d.site_a, t, H, lane, d.p_drop, inv_keep);
+    }
+    embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
+    if (d.ln2_gamma) {
+        float mean, rstd;
+        ln_forward<LANES, CH>(x, y, d.ln2_gamma, d.ln2_beta, lane, H, mean, rstd);
+        if (stats && lane == 0) { stats[(size_t)2 * T + t] = mean; stats[(size_t)3 * T + t] = rstd; }
+        x = y;
+        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, d.seed, d.site_b, t, H, lane, d.p_drop, inv_keep);
+    }
+    x.store(out + t * H, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused embedding backward (recomputes the forward from ids + saved LayerNorm statistics)
+// partials: [gridDim.x][4][H] (dgamma1, dbeta1, dgamma2, dbeta2)
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int CH>
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d, int T, int S, int H,
+                                                        const float* __restrict__ d_out, const float* __restrict__ stats,
+                                                        float* __restrict__ d_item_rows, float* __restrict__ d_attr_rows,
+                                                        float* __restrict__ partials) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x % LANES;
+    const int groups_per_block = blockDim.x / LANES;
+    const int group_in_block = threadIdx.x / LANES;
+    const float inv_keep = d.p_drop > 0.f ? 1.0f / (1.0f - d.p_drop) : 1.0f;
+    Row<LANES, CH> dg1, db1, dg2, db2;
+    zero_row(dg1); zero_row(db1); zero_row(dg2); zero_row(db2);
+    for (long long t = (long long)blockIdx.x * groups_per_block + group_in_block; t < T;
+         t += (long long)gridDim.x * groups_per_block) {
+        Row<LANES, CH> x, xhat1, xhat2, g;
+        const long long item = __ldg(d.item_ids + t);
+        x.load(d.item_table + item * H, lane);
+        if (d.pos_table) x.add(d.pos_table + (long long)(t % S) * H, lane);
+        float rstd1 = 0.f, rstd2 = 0.f;
+        if (d.ln1_gamma) {
+            const float mean = stats[t];
+            rstd1 = stats[(size_t)T + t];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float4 gm = ldg4(d.ln1_gamma + (c * LANES + lane) * 4);
+                const float4 bt = ldg4(d.ln1_beta + (c * LANES + lane) * 4);
+                float4 h;
+                h.x = (x.v[c].x - mean) * rstd1; h.y = (x.v[c].y - mean) * rstd1;
+                h.z = (x.v[c].z - mean) * rstd1; h.w = (x.v[c].w - mean) * rstd1;
+                xhat1.v[c] = h;
+                x.v[c].x = h.x * gm.x + bt.x; x.v[c].y = h.y * gm.y + bt.y;
+                x.v[c].z = h.z * gm.z + bt.z; x.v[c].w = h.w * gm.w + bt.w;
+            }
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, d.seed, d.site_a, t, H, lane, d.p_drop, inv_keep);
+        }
+        g.load(d_out + t * H, lane);
+        if (d.ln2_gamma) {
+            embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
+            const float mean = stats[(size_t)2 * T + t];
+            rstd2 = stats[(size_t)3 * T + t];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                xhat2.v[c].x = (x.v[c].x - mean) * rstd2; xhat2.v[c].y = (x.v[c].y - mean) * rstd2;
+                xhat2.v[c].z = (x.v[c].z - mean) * rstd2; xhat2.v[c].w = (x.v[c].w - mean) * rstd2;
+            }
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, d.seed, d.site_b, t, H, lane, d.p_drop, inv_keep);
+            ln_backward<LANES, CH>(g, xhat2, d.ln2_gamma, lane, H, rstd2, dg2, db2);
+        }
+        if (d_attr_rows && d_attr_rows != d_item_rows) g.store(d_attr_rows + t * H, lane);
+        if (d.ln1_gamma) {
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, d.seed, d.site_a, t, H, lane, d.p_drop, inv_keep);
+            ln_backward<LANES, CH>(g, xhat1, d.ln1_gamma, lane, H, rstd1, dg1, db1);
+        }
+        g.store(d_item_rows + t * H, lane);
+    }
+    float* out = partials + (size_t)blockIdx.x * 4 * H;
+    block_reduce_rows<LANES, CH>(dg1, smem, out, H, group_in_block, groups_per_block, lane);
+    block_reduce_rows<LANES, CH>(db1, smem, out + H, H, group_in_block, groups_per_block, lane);
+    block_reduce_rows<LANES, CH>(dg2, smem, out + 2 * H, H, group_in_block, groups_per_block, lane);
+    block_reduce_rows<LANES, CH>(db2, smem, out + 3 * H, H, group_in_block, groups_per_block, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward / backward
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int CH>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int M, int H,
+                                                            float* __restrict__ y, float* __restrict__ stats) {
+    const int lane = threadIdx.x % LANES;
+    const long long r = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
+    if (r >= M) return;
+    Row<LANES, CH> xr, yr;
+    xr.load(x + r * H, lane);
+    float mean, rstd;
+    ln_forward<LANES, CH>(xr, yr, gamma, beta, lane, H, mean, rstd);
+    if (stats && lane == 0) { stats[r] = mean; stats[(size_t)M + r] = rstd; }
+    yr.store(y + r * H, lane);
+}
+
+template <int LANES, int CH>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                            int M, int H, const float* __restrict__ d_residual,
+                                                            float* __restrict__ dx, float* __restrict__ partials) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x % LANES;
+    const int groups_per_block = blockDim.x / LANES;
+    const int group_in_block = threadIdx.x / LANES;
+    Row<LANES, CH> dg, db;
+    zero_row(dg); zero_row(db);
+    for (long long r = (long long)blockIdx.x * groups_per_block + group_in_block; r < M;
+         r += (long long)gridDim.x * groups_per_block) {
+        Row<LANES, CH> xhat, g;
+        xhat.load(x + r * H, lane);
+        const float mean = stats[r], rstd = stats[(size_t)M + r];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            xhat.v[c].x = (xhat.v[c].x - mean) * rstd; xhat.v[c].y = (xhat.v[c].y - mean) * rstd;
+            xhat.v[c].z = (xhat.v[c].z - mean) * rstd; xhat.v[c].w = (xhat.v[c].w - mean) * rstd;
+        }
+        g.load(dy + r * H, lane);
+        ln_backward<LANES, CH>(g, xhat, gamma, lane, H, rstd, dg, db);
+        if (d_residual) g.add(d_residual + r * H, lane);
+        g.store(dx + r * H, lane);
+    }
+    float* out = partials + (size_t)blockIdx.x * 2 * H;
+    block_reduce_rows<LANES, CH>(dg, smem, out, H, group_in_block, groups_per_block, lane);
+    block_reduce_rows<LANES, CH>(db, smem, out + H, H, group_in_block, groups_per_block, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums: out[n] (+)= sum_m x[m,n]. stage 1: one block per chunk of rows; stage 2: over chunks.
+// ---------------------------------------------------------------------------------------------
+#define COLSUM_ROWS 128
+__global__ void colsum_stage1_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ partial) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m0 = blockIdx.y * COLSUM_ROWS;
+    const int m1 = min(M, m0 + COLSUM_ROWS);
+    float s = 0.f;
+    for (int m = m0; m < m1; ++m) s += x[(size_t)m * N + n];
+    partial[(size_t)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out,
+                                     int accumulate) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * N + n];
+    out[n] = accumulate ? out[n] + s : s;
+}
+
+static int launch_colsum(const float* x, int M, int N, float* out, int accumulate, void* ws, size_t ws_bytes,
+                         cudaStream_t stream) {
+    if (M <= COLSUM_ROWS) {   // small: single stage
+        colsum_stage2_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(x, M, N, out, accumulate);
+        ASME_LAUNCH_OK();
+        return ASME_OK;
+    }
+    const int chunks = ceil_div(M, COLSUM_ROWS);
+    if (ws_bytes < (size_t)chunks * N * sizeof(float)) {
+        asme_set_error("colsum: workspace too small (%zu < %zu)", ws_bytes, (size_t)chunks * N * sizeof(float));
+        return ASME_ERR_WORKSPACE;
+    }
+    float* partial = (float*)ws;
+    colsum_stage1_kernel<<<dim3(ceil_div(N, 128), chunks), 128, 0, stream>>>(x, M, N, partial);
+    ASME_LAUNCH_OK();
+    colsum_stage2_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(partial, chunks, N, out, accumulate);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+extern "C" size_t asme_b200_colsum_workspace_bytes(int M, int N) {
+    return (size_t)ceil_div(M, COLSUM_ROWS) * N * sizeof(float);
+}
+extern "C" int asme_b200_colsum_accumulate(const float* x, int M, int N, float* out, void* ws, size_t ws_bytes,
+                                           asme_stream_t stream) {
+    ASME_REQUIRE(M >= 0 && N > 0, "colsum: bad shape M=%d N=%d", M, N);
+    if (M == 0) return ASME_OK;
+    return launch_colsum(x, M, N, out, 1, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// d_pos[s,:] += sum_b d_rows[b*S+s,:]
+__global__ void posgrad_kernel(const float* __restrict__ d_rows, int B, int S, int H, float* __restrict__ d_pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over S*H/4
+    if (i >= (long long)S * H / 4) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) add4(s, ldg4(d_rows + ((long long)b * S * H) + i * 4));
+    float4* o = reinterpret_cast<float4*>(d_pos) + i;
+    float4 cur = *o;
+    add4(cur, s);
+    *o = cur;
+}
+extern "C" int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H, float* d_pos, asme_stream_t stream) {
+    ASME_REQUIRE(H % 4 == 0, "posgrad: H=%d must be a multiple of 4", H);
+    const long long n = (long long)S * H / 4;
+    posgrad_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d_rows, B, S, H, d_pos);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch on H
+// ---------------------------------------------------------------------------------------------
+#define DISPATCH_H(H, CALL)                                       \
+    switch (H) {                                                  \
+        case 16: { CALL(4, 1); break; }                           \
+        case 32: { CALL(8, 1); break; }                           \
+        case 64: { CALL(16, 1); break; }                          \
+        case 128: { CALL(32, 1); break; }                         \
+        case 256: { CALL(32, 2); break; }                         \
+        case 512: { CALL(32, 4); break; }                         \
+        default:                                                  \
+            asme_set_error("unsupported hidden size H=%d (supported: 16,32,64,128,256,512)", H); \
+            return ASME_ERR_INVALID;                              \
+    }
+
+static int lanes_for(int H) { return H / 4 < 32 ? H / 4 : 32; }
+
+extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* out, float* stats,
+                                   asme_stream_t stream) {
+    ASME_REQUIRE(d && out, "embed_fwd: null argument");
+    ASME_REQUIRE(T >= 0 && S > 0, "embed_fwd: bad shape T=%d S=%d", T, S);
+    ASME_REQUIRE(d->n_attr >= 0 && d->n_attr <= ASME_MAX_ATTR && d->n_bag >= 0 && d->n_bag <= ASME_MAX_ATTR,
+                 "embed_fwd: too many attribute tables");
+    ASME_REQUIRE(d->p_drop >= 0.f && d->p_drop < 1.f, "embed_fwd: dropout p=%f out of range", d->p_drop);
+    if (T == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+#define CALL(L, C) embed_fwd_kernel<L, C><<<ceil_div(T, groups), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+static int rowwise_bwd_grid(int M, int groups) {
+    const int need = ceil_div(M, groups);
+    const int cap = ASME_NUM_SMS * 4;
+    return need < cap ? need : cap;
+}
+
+extern "C" size_t asme_b200_embed_bwd_workspace_bytes(int T, int H) {
+    (void)T;
+    return (size_t)ASME_NUM_SMS * 4 * 4 * H * sizeof(float);
+}
+
+extern "C" int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H, const float* d_out, const float* stats,
+                                   float* d_item_rows, float* d_attr_rows, float* dln, void* ws, size_t ws_bytes,
+                                   asme_stream_t stream) {
+    ASME_REQUIRE(d && d_out && d_item_rows, "embed_bwd: null argument");
+    ASME_REQUIRE(!(d->ln1_gamma || d->ln2_gamma) || (stats && dln), "embed_bwd: LayerNorm needs stats and dln");
+    if (T == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+    const int grid = rowwise_bwd_grid(T, groups);
+    if (ws_bytes < (size_t)grid * 4 * H * sizeof(float)) {
+        asme_set_error("embed_bwd: workspace too small");
+        return ASME_ERR_WORKSPACE;
+    }
+    float* partials = (float*)ws;
+    const size_t smem = (size_t)groups * H * sizeof(float);
+#define CALL(L, C)                                                                                              \
+    embed_bwd_kernel<L, C><<<grid, 256, smem, (cudaStream_t)stream>>>(*d, T, S, H, d_out, stats, d_item_rows, \
+                                                                      d_attr_rows, partials)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    if (dln) {
+        colsum_stage2_kernel<<<ceil_div(4 * H, 128), 128, 0, (cudaStream_t)stream>>>(partials, grid, 4 * H, dln, 1);
+        ASME_LAUNCH_OK();
+    }
+    return ASME_OK;
+}
+
+extern "C" int asme_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int H, float* y,
+                                       float* stats, asme_stream_t stream) {
+    ASME_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null argument");
+    if (M == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+#define CALL(L, C) layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y, stats)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+extern "C" size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H) {
+    (void)M;
+    return (size_t)ASME_NUM_SMS * 4 * 2 * H * sizeof(float);
+}
+
+extern "C" int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M,
+                                       int H, const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
+                                       asme_stream_t stream) {
+    ASME_REQUIRE(dy && x && gamma && stats && dx && dgb, "layernorm_bwd: null argument");
+    if (M == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+    const int grid = rowwise_bwd_grid(M, groups);
+    if (ws_bytes < (size_t)grid * 2 * H * sizeof(float)) {
+        asme_set_error("layernorm_bwd: workspace too small");
+        return ASME_ERR_WORKSPACE;
+    }
+    float* partials = (float*)ws;
+    const size_t smem = (size_t)groups * H * sizeof(float);
+#define CALL(L, C)                                                                                                 \
+    layernorm_bwd_kernel<L, C><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, x, gamma, stats, M, H, d_residual, dx, \
+                                                                          partials)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    colsum_stage2_kernel<<<ceil_div(2 * H, 128), 128, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, float p, float inv_keep,
+                               uint64_t seed, uint32_t site) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = ldg4(x + i * 4);
+    const float4 s = dropout_scale4(seed, site, (uint64_t)i * 4, p, inv_keep);
+    v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    reinterpret_cast<float4*>(y)[i] = v;
+}
+extern "C" int asme_b200_dropout(const float* x, float* y, long long n, float p, uint64_t seed, uint32_t site,
+                                 asme_stream_t stream) {
+    ASME_REQUIRE(n % 4 == 0, "dropout: n=%lld must be a multiple of 4", n);
+    ASME_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f out of range", p);
+    if (n == 0) return ASME_OK;
+    dropout_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n / 4, p, 1.0f / (1.0f - p), seed, site);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+__global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long long n,
+                              int op) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = op == 0 ? a[i] + b[i] : a[i] * b[i];
+}
+extern "C" int asme_b200_binary(const float* a, const float* b, float* y, long long n, int op, asme_stream_t stream) {
+    if (n == 0) return ASME_OK;
+    binary_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, n, op);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+__global__ void fill_kernel(float* x, long long n, float v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+extern "C" int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream) {
+    if (n == 0) return ASME_OK;
+    fill_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, value);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, int R, int H4,
+                                   float* __restrict__ out, int scatter) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * H4) return;
+    const long long r = i / H4, c = i % H4;
+    const long long src = idx[r];
+    if (!scatter) reinterpret_cast<float4*>(out)[r * H4 + c] = __ldg(reinterpret_cast<const float4*>(x) + src * H4 + c);
+    else reinterpret_cast<float4*>(out)[src * H4 + c] = __ldg(reinterpret_cast<const float4*>(x) + r * H4 + c);
+}
+extern "C" int asme_b200_gather_rows(const float* x, const int64_t* row_index, int R, int H, float* out,
+                                     asme_stream_t stream) {
+    ASME_REQUIRE(H % 4 == 0, "gather_rows: H=%d must be a multiple of 4", H);
+    if (R == 0) return ASME_OK;
+    gather_rows_kernel<<<ceil_div((long long)R * H / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, row_index, R, H / 4, out, 0);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+extern "C" int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, int H, float* out,
+                                      asme_stream_t stream) {
+    ASME_REQUIRE(H % 4 == 0, "scatter_rows: H=%d must be a multiple of 4", H);
+    if (R == 0) return ASME_OK;
+    gather_rows_kernel<<<ceil_div((long long)R * H / 4, 256), 256, 0, (cudaStream_t)stream>>>(rows, row_index, R, H / 4, out, 1);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused Adam over the flat arena
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr_over_bc1, float beta1, float beta2, float eps, float wd,
+                            float inv_sqrt_bc2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi += wd * pi;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+}
+extern "C" int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
+                                   float beta2, float eps, float weight_decay, int step, asme_stream_t stream) {
+    ASME_REQUIRE(step >= 1, "adam: step must be >= 1");
+    if (n == 0) return ASME_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
+                                                                    weight_decay, (float)(1.0 / sqrt(bc2)));
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}

@@ -1,0 +1,425 @@
+"""Kernel-level parity tests: every C-ABI entry point against a CPU fp32 restatement (oracle /
+plain torch).  All tests need a B200 (``-m gpu``) and call through the C ABI via asme_b200.ops."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import asme_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-5      # fp32 tolerance stated by north_star: 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asme_b200 import ops
+    return ops
+
+
+def dev(t):
+    return t.cuda()
+
+
+def close(a, b, rtol=RTOL, atol=ATOL, msg=""):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), rtol=rtol, atol=atol, msg=lambda m: f"{msg}: {m}")
+
+
+def make_seq(gen, b, s, v):
+    seq = torch.randint(3, v, (b, s), generator=gen)
+    lengths = torch.randint(1, s + 1, (b,), generator=gen)
+    lengths[0] = s
+    for i in range(b):
+        seq[i, lengths[i]:] = 0
+    return seq
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H", [16, 64, 128, 256])
+@pytest.mark.parametrize("variant", ["bert4rec", "kebert4rec", "sasrec"])
+def test_embed_fwd_bwd(ops, H, variant):
+    gen = torch.Generator().manual_seed(H + len(variant))
+    B, S, V, VA, VT, A = 5, 11, 97, 13, 19, 3
+    seq = make_seq(gen, B, S, V)
+    E = torch.randn(V, H, generator=gen)
+    P = torch.randn(S + 2, H, generator=gen)
+    cat_tab = torch.randn(VA, H, generator=gen)
+    tag_w = torch.randn(H, VT, generator=gen)         # nn.Linear layout (H, Va)
+    tag_b = torch.randn(H, generator=gen)
+    g1, b1 = torch.randn(H, generator=gen) + 1, torch.randn(H, generator=gen)
+    g2, b2 = torch.randn(H, generator=gen) + 1, torch.randn(H, generator=gen)
+    cat = torch.randint(0, VA, (B, S), generator=gen)
+    tags = torch.randint(0, VT, (B, S, A), generator=gen)
+    leaves = [t.requires_grad_(True) for t in (E, P, cat_tab, tag_w, tag_b, g1, b1, g2, b2)]
+
+    if variant == "bert4rec":
+        ref = O.transformer_embedding(seq, E, None, (g1, b1))
+        spec = ops.EmbedSpec(dev(seq), dev(E), None, ln1=(dev(g1), dev(b1)))
+    elif variant == "kebert4rec":
+        x = O.transformer_embedding(seq, E, P, None)
+        x = x + cat_tab[cat] + O.linear_upscale(tags, tag_w, tag_b)
+        ref = O.layer_norm(x, g2, b2)
+        spec = ops.EmbedSpec(dev(seq), dev(E), dev(P), attrs=[(dev(cat).reshape(-1), dev(cat_tab))],
+                             bags=[(dev(tags).reshape(-1, A), dev(tag_w.t().contiguous()), dev(tag_b))],
+                             ln2=(dev(g2), dev(b2)))
+    else:
+        x = O.transformer_embedding(seq, E, P, (g1, b1))
+        x = x + cat_tab[cat]
+        ref = O.layer_norm(x, g2, b2)
+        spec = ops.EmbedSpec(dev(seq), dev(E), dev(P), attrs=[(dev(cat).reshape(-1), dev(cat_tab))],
+                             ln1=(dev(g1), dev(b1)), ln2=(dev(g2), dev(b2)))
+    out, stats = ops.embed_fwd(spec, B, S, save_stats=True)
+    close(out.view(B, S, H), ref, msg="embed fwd")
+
+    d_out = torch.randn(B, S, H, generator=gen)
+    ref.backward(d_out)
+    dln = torch.zeros(4, H, device="cuda")
+    d_item, d_attr = ops.embed_bwd(spec, B, S, dev(d_out).view(B * S, H), stats, dln)
+    dE = torch.zeros(V, H, device="cuda")
+    ops.embgrad_sorted_reduce(dev(seq), d_item, dE)
+    close(dE, E.grad, rtol=1e-4, atol=1e-5, msg="dE")
+    if variant != "bert4rec":
+        dP = torch.zeros(S + 2, H, device="cuda")
+        ops.posgrad_reduce(d_item, B, S, dP)
+        close(dP, P.grad, rtol=1e-4, atol=1e-5, msg="dP")
+        dcat = torch.zeros(VA, H, device="cuda")
+        ops.embgrad_sorted_reduce(dev(cat), d_attr, dcat)
+        close(dcat, cat_tab.grad, rtol=1e-4, atol=1e-5, msg="dcat")
+    if variant == "kebert4rec":
+        dtag_t = torch.zeros(VT, H, device="cuda")
+        ops.embgrad_sorted_reduce(dev(tags).reshape(-1), d_attr.repeat_interleave(A, dim=0), dtag_t, skip_id=0)
+        close(dtag_t.t(), tag_w.grad, rtol=1e-4, atol=1e-5, msg="dtag_w")
+        dbias = torch.zeros(H, device="cuda")
+        ops.colsum_accumulate(d_attr, dbias)
+        close(dbias, tag_b.grad, rtol=1e-4, atol=1e-5, msg="dtag_b")
+    if variant in ("bert4rec", "sasrec"):
+        close(dln[0], g1.grad, rtol=1e-4, atol=1e-5, msg="dgamma1")
+        close(dln[1], b1.grad, rtol=1e-4, atol=1e-5, msg="dbeta1")
+    if variant in ("kebert4rec", "sasrec"):
+        close(dln[2], g2.grad, rtol=1e-4, atol=1e-5, msg="dgamma2")
+        close(dln[3], b2.grad, rtol=1e-4, atol=1e-5, msg="dbeta2")
+
+
+def test_embed_gather_is_bit_exact(ops):
+    """no LayerNorm, no attributes: the gather (+ position add) must be bit-exact."""
+    gen = torch.Generator().manual_seed(5)
+    B, S, V, H = 7, 13, 1000, 64
+    seq = make_seq(gen, B, S, V)
+    E, P = torch.randn(V, H, generator=gen), torch.randn(S, H, generator=gen)
+    out, _ = ops.embed_fwd(ops.EmbedSpec(dev(seq), dev(E)), B, S)
+    assert torch.equal(out.cpu().view(B, S, H), E[seq])
+    out, _ = ops.embed_fwd(ops.EmbedSpec(dev(seq), dev(E), dev(P)), B, S)
+    assert torch.equal(out.cpu().view(B, S, H), E[seq] + P[torch.arange(S)].unsqueeze(0))
+
+
+@pytest.mark.parametrize("M,H", [(1, 16), (77, 64), (1000, 128), (333, 512)])
+def test_layernorm(ops, M, H):
+    gen = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, H, generator=gen) * 2 + 0.5).requires_grad_(True)
+    g = (torch.randn(H, generator=gen) + 1).requires_grad_(True)
+    b = torch.randn(H, generator=gen).requires_grad_(True)
+    ref = O.layer_norm(x, g, b)
+    y, stats = ops.layernorm_fwd(dev(x), dev(g), dev(b), save_stats=True)
+    close(y, ref, msg="ln fwd")
+    dy, res = torch.randn(M, H, generator=gen), torch.randn(M, H, generator=gen)
+    ref.backward(dy)
+    dgb = torch.zeros(2, H, device="cuda")
+    dx = ops.layernorm_bwd(dev(dy), dev(x), dev(g), stats, dgb, d_residual=dev(res))
+    close(dx, x.grad + res, rtol=1e-4, atol=1e-5, msg="ln dx")
+    close(dgb[0], g.grad, rtol=1e-4, atol=1e-4, msg="ln dgamma")
+    close(dgb[1], b.grad, rtol=1e-4, atol=1e-4, msg="ln dbeta")
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 16, 16), (130, 64, 64), (257, 192, 64), (513, 64, 256), (100, 3709, 64), (64, 61, 16)])
+def test_gemm_nt(ops, M, N, K):
+    gen = torch.Generator().manual_seed(M + N)
+    a, w, bias = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen), torch.randn(N, generator=gen)
+    res = torch.randn(M, N, generator=gen)
+    close(ops.gemm(dev(a), dev(w)), a @ w.t(), rtol=1e-5, atol=1e-4, msg="plain")
+    c, pre = ops.gemm(dev(a), dev(w), bias=dev(bias), act=1, pre_act_out=True, residual=dev(res))
+    z = a @ w.t() + bias
+    close(pre, z, rtol=1e-5, atol=1e-4, msg="pre-act")
+    close(c, O.gelu_erf(z) + res, rtol=1e-5, atol=1e-4, msg="gelu+res")
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 64, 256), (257, 64, 64), (50, 16, 61)])
+def test_gemm_nn_and_gelu_grad(ops, M, N, K):
+    gen = torch.Generator().manual_seed(M + K)
+    a, b = torch.randn(M, K, generator=gen), torch.randn(K, N, generator=gen)
+    z = torch.randn(M, N, generator=gen).requires_grad_(True)
+    close(ops.gemm(dev(a), dev(b), trans_b=False), a @ b, rtol=1e-5, atol=1e-4, msg="nn")
+    O.gelu_erf(z).backward(torch.ones(M, N))
+    got = ops.gemm(dev(a), dev(b), trans_b=False, mul_gelu_grad_of=dev(z.detach()))
+    close(got, (a @ b) * z.grad, rtol=1e-5, atol=1e-4, msg="nn * gelu'")
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 16, 16), (1000, 64, 64), (5000, 256, 64), (777, 64, 192)])
+def test_gemm_wgrad(ops, M, N, K):
+    gen = torch.Generator().manual_seed(M + N + K)
+    dy, x = torch.randn(M, N, generator=gen), torch.randn(M, K, generator=gen)
+    dw = torch.full((N, K), 0.5, device="cuda")
+    db = torch.full((N,), 0.25, device="cuda")
+    ops.gemm_wgrad(dev(dy), dev(x), dw, db, accumulate=True)
+    close(dw, dy.t() @ x + 0.5, rtol=1e-4, atol=1e-3, msg="dW")
+    close(db, dy.sum(0) + 0.25, rtol=1e-4, atol=1e-3, msg="dbias")
+    ops.gemm_wgrad(dev(dy), dev(x), dw, db, accumulate=False)
+    close(dw, dy.t() @ x, rtol=1e-4, atol=1e-3, msg="dW overwrite")
+
+
+def _attention_ref(qkv, key_valid, B, S, heads, causal):
+    H = qkv.shape[1] // 3
+    d = H // heads
+    q, k, v = [qkv[:, i * H:(i + 1) * H].view(B, S, heads, d).transpose(1, 2) for i in range(3)]
+    scores = (q @ k.transpose(-2, -1)) / math.sqrt(d)
+    mask = O.attention_mask(key_valid, B, S, not causal)
+    if mask is not None:
+        scores = scores.masked_fill(mask == 0, O.ATTENTION_FILL)
+    p = torch.softmax(scores, dim=-1)
+    return (p @ v).transpose(1, 2).contiguous().view(B * S, H)
+
+
+@pytest.mark.parametrize("B,S,heads,d", [(3, 9, 2, 8), (4, 50, 2, 32), (2, 200, 2, 32), (2, 200, 2, 64), (2, 33, 4, 16),
+                                        (1, 256, 1, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("masked", [True, False])
+def test_attention(ops, B, S, heads, d, causal, masked):
+    gen = torch.Generator().manual_seed(B * S + d)
+    H = heads * d
+    qkv = torch.randn(B * S, 3 * H, generator=gen).requires_grad_(True)
+    key_valid = None
+    if masked:
+        seq = make_seq(gen, B, S, 50)
+        if B > 1:
+            seq[1] = 0              # an all-padding sequence: every row fully masked -> uniform attention (Q4)
+        if B > 2:
+            seq[2, :2] = 0          # left padding: causal rows before the first real key are fully masked
+        key_valid = seq.ne(0)
+    ref = _attention_ref(qkv, key_valid, B, S, heads, causal)
+    ctx, stats = ops.attn_fwd(dev(qkv), None if key_valid is None else dev(key_valid), B, S, heads, causal, save_stats=True)
+    close(ctx, ref, msg="attn fwd")
+    d_ctx = torch.randn(B * S, H, generator=gen)
+    ref.backward(d_ctx)
+    d_qkv = ops.attn_bwd(dev(qkv), None if key_valid is None else dev(key_valid), B, S, heads, causal, ctx, dev(d_ctx), stats)
+    close(d_qkv, qkv.grad, rtol=1e-4, atol=1e-5, msg="attn bwd")
+
+
+def test_attention_dropout_consistency(ops):
+    """dropout masks are a pure function of (seed, site, index): forward twice is identical, the keep rate is
+    1-p, and the backward pass matches autograd through the same mask (recovered from the forward)."""
+    gen = torch.Generator().manual_seed(0)
+    B, S, heads, d, p = 2, 64, 2, 32, 0.25
+    H = heads * d
+    qkv = torch.randn(B * S, 3 * H, generator=gen)
+    a, st = ops.attn_fwd(dev(qkv), None, B, S, heads, False, p_drop=p, seed=7, site=3, save_stats=True)
+    b, _ = ops.attn_fwd(dev(qkv), None, B, S, heads, False, p_drop=p, seed=7, site=3)
+    assert torch.equal(a, b)
+    c, _ = ops.attn_fwd(dev(qkv), None, B, S, heads, False, p_drop=p, seed=8, site=3)
+    assert not torch.equal(a, c)
+    # recover the mask with V = identity-like probes: use dropout op on ones with the same index space
+    ones = torch.ones(B * heads * S * S, device="cuda")
+    mask = ops.dropout(ones, p, 7, 3).view(B, heads, S, S).cpu()
+    keep = (mask > 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01
+    qkv_r = qkv.clone().requires_grad_(True)
+    q, k, v = [qkv_r[:, i * H:(i + 1) * H].view(B, S, heads, d).transpose(1, 2) for i in range(3)]
+    pr = torch.softmax((q @ k.transpose(-2, -1)) / math.sqrt(d), dim=-1) * mask
+    ref = (pr @ v).transpose(1, 2).contiguous().view(B * S, H)
+    close(a, ref, msg="attn fwd with dropout")
+    d_ctx = torch.randn(B * S, H, generator=gen)
+    ref.backward(d_ctx)
+    d_qkv = ops.attn_bwd(dev(qkv), None, B, S, heads, False, a, dev(d_ctx), st, p_drop=p, seed=7, site=3)
+    close(d_qkv, qkv_r.grad, rtol=1e-4, atol=1e-5, msg="attn bwd with dropout")
+
+
+def test_dropout_elementwise(ops):
+    x = torch.ones(1 << 16, device="cuda")
+    y = ops.dropout(x, 0.2, 123, 5)
+    vals = torch.unique(y).cpu()
+    assert torch.allclose(vals, torch.tensor([0.0, 1.25]))
+    assert abs((y > 0).float().mean().item() - 0.8) < 0.01
+    assert torch.equal(y, ops.dropout(x, 0.2, 123, 5))
+    assert not torch.equal(y, ops.dropout(x, 0.2, 123, 6))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R,V,H,k", [(5, 57, 16, 10), (70, 1000, 64, 10), (130, 3709, 64, 5), (64, 20011, 128, 32), (3, 7, 16, 10)])
+def test_score_topk_rank_exact_grid(ops, R, V, H, k):
+    """Inputs on a coarse dyadic grid: every product and partial sum is exact in fp32 in any order, so the
+    scores are bit-identical to the oracle's, ties are plentiful, and top-k ids / rank must be bit-exact."""
+    gen = torch.Generator().manual_seed(R + V)
+    h = torch.randint(-2, 3, (R, H), generator=gen).float() / 2
+    w = torch.randint(-2, 3, (V, H), generator=gen).float() / 2
+    bias = torch.randint(-4, 5, (V,), generator=gen).float() / 4
+    target = torch.randint(0, V, (R,), generator=gen)
+    logits = (h.double() @ w.double().t() + bias.double()).float()
+    ts = ops.score_targets(dev(h), dev(w), dev(bias), dev(target))
+    assert torch.equal(ts.cpu(), logits[torch.arange(R), target])
+    val, idx, ng, nt = ops.score_topk_rank(dev(h), dev(w), dev(bias), k, dev(target), ts)
+    kk = min(k, V)
+    want_idx = O.topk_ids(logits.numpy(), kk)
+    assert np.array_equal(idx.cpu().numpy()[:, :kk], want_idx)
+    assert np.array_equal(val.cpu().numpy()[:, :kk], np.take_along_axis(logits.numpy(), want_idx, 1))
+    if kk < k:
+        assert (idx.cpu().numpy()[:, kk:] == -1).all()
+    rank = 1 + ng.cpu().numpy() + nt.cpu().numpy()
+    assert np.array_equal(rank, O.target_rank(logits.numpy(), target.numpy()))
+
+
+def test_score_topk_random_and_sharded_merge(ops):
+    """random fp32 weights; vocabulary split into 3 shards, merged with topk_merge == single pass."""
+    gen = torch.Generator().manual_seed(11)
+    R, V, H, k = 96, 5000, 64, 10
+    h, w, bias = torch.randn(R, H, generator=gen), torch.randn(V, H, generator=gen) * 0.1, torch.randn(V, generator=gen) * 0.1
+    target = torch.randint(0, V, (R,), generator=gen)
+    hd, wd, bd, td = dev(h), dev(w), dev(bias), dev(target)
+    ts = ops.score_targets(hd, wd, bd, td)
+    val, idx, ng, nt = ops.score_topk_rank(hd, wd, bd, k, td, ts)
+    logits = h @ w.t() + bias
+    close(val, torch.topk(logits, k).values, msg="topk values")
+    # index sets agree wherever the oracle's k-th/(k+1)-th gap exceeds the fp32 noise
+    srt = torch.sort(logits, descending=True)
+    safe = (srt.values[:, k - 1] - srt.values[:, k]) > 1e-5
+    got = np.sort(idx.cpu().numpy(), axis=1)
+    want = np.sort(srt.indices[:, :k].numpy(), axis=1)
+    assert np.array_equal(got[safe.numpy()], want[safe.numpy()])
+    bounds = [0, 1700, 3333, V]
+    parts_v, parts_i, tsum, g_sum, t_sum = [], [], torch.zeros(R, device="cuda"), 0, 0
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        ops.score_targets(hd, wd[a:b].contiguous(), bd[a:b].contiguous(), td, v0=a, out=tsum)
+    assert torch.equal(tsum, ts)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        v_, i_, g_, t_ = ops.score_topk_rank(hd, wd[a:b].contiguous(), bd[a:b].contiguous(), k, td, tsum, v0=a)
+        parts_v.append(v_); parts_i.append(i_); g_sum = g_sum + g_; t_sum = t_sum + t_
+    mv, mi = ops.topk_merge(torch.stack(parts_v), torch.stack(parts_i), k)
+    assert torch.equal(mv, val) and torch.equal(mi, idx)
+    assert torch.equal(g_sum, ng) and torch.equal(t_sum, nt)
+
+
+def test_ranking_metrics(ops):
+    rank = torch.tensor([1, 2, 3, 7, 10, 11, 50, 1, 5, 6], dtype=torch.int32)
+    ks = torch.tensor([1, 5, 10], dtype=torch.int32)
+    out = torch.zeros(4, 3, device="cuda")
+    ops.ranking_metrics(dev(rank), dev(ks), out)
+    ops.ranking_metrics(dev(rank), dev(ks), out)          # accumulates
+    want = O.metrics_from_rank(rank.numpy(), [1, 5, 10])
+    for j, k in enumerate([1, 5, 10]):
+        for i, name in enumerate(["recall", "NDCG", "MRR", "precision"]):
+            assert abs(out[i, j].item() - 2 * want[f"{name}@{k}"]) < 1e-4, (name, k)
+
+
+@pytest.mark.parametrize("R,V,H", [(1, 7, 16), (100, 61, 16), (300, 3709, 64), (65, 12104, 64), (40, 1000, 128), (70, 500, 256)])
+def test_score_ce_fwd_bwd(ops, R, V, H):
+    gen = torch.Generator().manual_seed(R + V)
+    h = torch.randn(R, H, generator=gen).requires_grad_(True)
+    w = (torch.randn(V, H, generator=gen) * 0.2).requires_grad_(True)
+    bias = (torch.randn(V, generator=gen) * 0.2).requires_grad_(True)
+    target = torch.randint(0, V, (R,), generator=gen)
+    logits = h @ w.t() + bias
+    loss = torch.nn.functional.cross_entropy(logits, target, reduction="sum")
+    loss.backward()
+    rmax, rsum, tl = ops.score_ce_partial(dev(h), dev(w), dev(bias), dev(target))
+    loss_sum = torch.zeros(1, device="cuda")
+    lse = ops.ce_loss_from_partials(rmax, rsum, tl, loss_sum)
+    close(lse, torch.logsumexp(logits, dim=-1), msg="lse")
+    close(loss_sum[0], loss, rtol=1e-5, atol=1e-4, msg="loss")
+    dW = torch.zeros(V, H, device="cuda")
+    db = torch.zeros(V, device="cuda")
+    dh = ops.score_ce_bwd(dev(h), dev(w), dev(bias), dev(target), lse, 1.0, dW, db)
+    close(dh, h.grad, rtol=1e-4, atol=1e-5, msg="dH")
+    close(dW, w.grad, rtol=1e-4, atol=1e-5, msg="dW")
+    close(db, bias.grad, rtol=1e-4, atol=1e-5, msg="dbias")
+
+
+def test_score_ce_sharded(ops):
+    """two vocabulary shards combined the way NCCL all-reduce(MAX)/(SUM) would combine them."""
+    gen = torch.Generator().manual_seed(3)
+    R, V, H = 50, 900, 64
+    h, w, bias = torch.randn(R, H, generator=gen), torch.randn(V, H, generator=gen) * 0.2, torch.randn(V, generator=gen)
+    target = torch.randint(0, V, (R,), generator=gen)
+    hd, wd, bd, td = dev(h), dev(w), dev(bias), dev(target)
+    parts = [ops.score_ce_partial(hd, wd[a:b].contiguous(), bd[a:b].contiguous(), td, v0=a) for a, b in ((0, 400), (400, V))]
+    m = torch.maximum(parts[0][0], parts[1][0])
+    s = parts[0][1] * torch.exp(parts[0][0] - m) + parts[1][1] * torch.exp(parts[1][0] - m)
+    tl = parts[0][2] + parts[1][2]
+    logits = h @ w.t() + bias
+    close(m + torch.log(s), torch.logsumexp(logits, -1), msg="sharded lse")
+    close(tl, logits[torch.arange(R), target], msg="sharded target logit")
+
+
+def test_posneg_bce(ops):
+    gen = torch.Generator().manual_seed(9)
+    B, S, V, H = 6, 10, 200, 64
+    T = B * S
+    h = torch.randn(T, H, generator=gen).requires_grad_(True)
+    E = (torch.randn(V, H, generator=gen) * 0.3).requires_grad_(True)
+    seq = make_seq(gen, B, S, V).reshape(-1)
+    pos, neg = torch.randint(3, V, (T,), generator=gen), torch.randint(3, V, (T,), generator=gen)
+    mask = seq.ne(0)
+    p, n = O.sasrec_pos_neg(h, E, pos, neg)
+    loss = O.sasrec_bce(p, n, mask)
+    loss.backward()
+    sums = torch.zeros(2, device="cuda")
+    pl, nl = ops.posneg_bce_fwd(dev(h), dev(E), dev(pos), dev(neg), dev(mask), sums)
+    close(pl, p, msg="pos logits"); close(nl, n, msg="neg logits")
+    close(sums[0] / sums[1], loss, msg="bce loss")
+    dh, dpos, dneg = ops.posneg_bce_bwd(dev(h), dev(E), dev(pos), dev(neg), dev(mask), pl, nl, sums)
+    close(dh, h.grad, rtol=1e-4, atol=1e-6, msg="bce dH")
+    dE = torch.zeros(V, H, device="cuda")
+    ops.embgrad_sorted_reduce(torch.cat([dev(pos), dev(neg)]), torch.cat([dpos, dneg]), dE)
+    close(dE, E.grad, rtol=1e-4, atol=1e-6, msg="bce dE")
+
+
+@pytest.mark.parametrize("T,V,H", [(1, 5, 16), (31, 7, 64), (32, 3, 64), (5000, 50, 64), (51200, 3709, 64), (4097, 100000, 128)])
+def test_embgrad_sorted_reduce(ops, T, V, H):
+    gen = torch.Generator().manual_seed(T)
+    ids = torch.randint(0, V, (T,), generator=gen)
+    ids[: T // 2] = torch.randint(0, min(V, 3), (T // 2,), generator=gen)   # long runs (PAD / MASK heavy)
+    rows = torch.randn(T, H, generator=gen)
+    want = torch.ones(V, H).index_add_(0, ids, rows)
+    got = torch.ones(V, H, device="cuda")
+    ops.embgrad_sorted_reduce(dev(ids), dev(rows), got)
+    close(got, want, rtol=1e-4, atol=1e-3, msg="embgrad")
+    again = torch.ones(V, H, device="cuda")
+    ops.embgrad_sorted_reduce(dev(ids), dev(rows), again)
+    assert torch.equal(got, again), "embedding gradient must be bit-deterministic"
+    keep = ids.ne(0)
+    want0 = torch.zeros(V, H).index_add_(0, ids[keep], rows[keep])
+    got0 = torch.zeros(V, H, device="cuda")
+    ops.embgrad_sorted_reduce(dev(ids), dev(rows), got0, skip_id=0)
+    close(got0, want0, rtol=1e-4, atol=1e-3, msg="embgrad skip")
+
+
+def test_adam_matches_oracle(ops):
+    gen = torch.Generator().manual_seed(1)
+    n = 10007
+    p, g = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    m, v = torch.zeros(n), torch.zeros(n)
+    pd, md, vd = dev(p), dev(m), dev(v)
+    for step in range(1, 4):
+        g = torch.randn(n, generator=gen)
+        O.adam_step([p], [g], [m], [v], step, 1e-3, 0.99, 0.998, 1e-8, 1e-3)
+        ops.adam_step(pd, dev(g), md, vd, 1e-3, 0.99, 0.998, 1e-8, 1e-3, step)
+    close(pd, p, rtol=1e-5, atol=1e-6, msg="adam param")
+    close(vd, v, rtol=1e-5, atol=1e-8, msg="adam v")
+
+
+def test_gather_scatter_rows(ops):
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(100, 64, generator=gen)
+    idx = torch.randperm(100, generator=gen)[:37]
+    rows = ops.gather_rows(dev(x), dev(idx))
+    assert torch.equal(rows.cpu(), x[idx])
+    out = torch.zeros(100, 64, device="cuda")
+    ops.scatter_rows(rows, dev(idx), out)
+    want = torch.zeros(100, 64)
+    want[idx] = x[idx]
+    assert torch.equal(out.cpu(), want)
+
+
+def test_errors_are_loud(ops):
+    with pytest.raises(RuntimeError):
+        ops.layernorm_fwd(torch.randn(4, 24, device="cuda"), torch.ones(24, device="cuda"), torch.zeros(24, device="cuda"))
+    with pytest.raises(RuntimeError):
+        ops.layernorm_fwd(torch.randn(4, 64), torch.ones(64), torch.zeros(64))     # CPU tensors: no CPU path
