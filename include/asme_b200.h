@@ -87,10 +87,11 @@ int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H, const flo
 
 /* K21  deterministic embedding-table gradient: sort (id) -> segmented reduce -> one write per distinct row.
  * replaces: autograd embedding_dense_backward (atomic scatter-add) of K1-K3/K13.
- * d_table[ids[t], :] += d_rows[t, :] for all t with ids[t] != skip_id (skip_id = -1 keeps everything). */
+ * d_table[ids[t], :] += d_rows[t / row_divisor, :] for all t with ids[t] != skip_id (skip_id = -1 keeps everything;
+ * row_divisor = bag width for (T,width) id bags that share one gradient row per token, else 1). */
 size_t asme_b200_embgrad_workspace_bytes(int T, int H);
-int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int H, float* d_table, int V,
-                                    int64_t skip_id, void* ws, size_t ws_bytes, asme_stream_t stream);
+int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int row_divisor, int H, float* d_table,
+                                    int V, int64_t skip_id, void* ws, size_t ws_bytes, asme_stream_t stream);
 /* d_pos[s,:] += sum_b d_rows[b*S+s,:]   (positions are generated, t mod S; transformer_layers.py:68) */
 int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H, float* d_pos, asme_stream_t stream);
 /* bag tables: d_table_t[id,:] += d_rows[t,:] for every bag entry id != 0; d_bias += column sums of d_rows */
@@ -144,6 +145,8 @@ int asme_b200_gemm_wgrad(const float* dY, const float* X, int M, int N, int K, f
 /* elementwise dropout with the same (seed, site, index) masks the fused epilogues use */
 int asme_b200_dropout(const float* x, float* y, long long n, float p, uint64_t seed, uint32_t site,
                       asme_stream_t stream);
+/* dz = dy * gelu'(z) (exact erf GELU, ffn_modifier.py:20) */
+int asme_b200_gelu_bwd(const float* dy, const float* z, float* dz, long long n, asme_stream_t stream);
 /* y = a (*|+) b : post-fusion merge (kebert4rec/components.py:110-113); op 0 = add, 1 = multiply */
 int asme_b200_binary(const float* a, const float* b, float* y, long long n, int op, asme_stream_t stream);
 
@@ -188,6 +191,13 @@ int asme_b200_topk_merge(const float* vals, const int32_t* idx, int G, int R, in
 /* K20: sums over the batch of recall/NDCG/MRR/precision @ ks from the 1-based target rank
  * (metrics/common.py:66-175, metrics/mrr.py:26-37). out: (4, n_k) sums, ACCUMULATED. */
 int asme_b200_ranking_metrics(const int32_t* rank, int R, const int32_t* ks, int n_k, float* out, asme_stream_t stream);
+
+/* dense-signature compatibility path of RankingMetric.update(predictions (N,I), positive_item_mask (N,I) int64,
+ * metric_mask (N,I) int64 or NULL) (metrics/metric.py:57-83, metrics/common.py:4-175): per row, O(I) scan with
+ * (score desc, id asc) order. out (7,N): recall, precision, DCG, NDCG, MRR, F1 @k and the full-sort rank of the
+ * worst relevant item (metrics/common.py:30-46). */
+int asme_b200_dense_ranking(const float* pred, const int64_t* pos_mask, const int64_t* metric_mask, int N, int I, int k,
+                            float* out, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K12+K16  scoring fused with log-softmax cross-entropy (ignore_index rows are skipped by the caller:

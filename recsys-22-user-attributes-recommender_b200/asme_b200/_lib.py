@@ -46,7 +46,7 @@ _PROTOTYPES = {
     "asme_b200_embed_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_embed_bwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "asme_b200_embgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "asme_b200_embgrad_sorted_reduce": (c_int, [P, c_int, P, c_int, P, c_int, c_int64, P, c_size_t, P]),
+    "asme_b200_embgrad_sorted_reduce": (c_int, [P, c_int, P, c_int, c_int, P, c_int, c_int64, P, c_size_t, P]),
     "asme_b200_posgrad_reduce": (c_int, [P, c_int, c_int, c_int, P, P]),
     "asme_b200_colsum_accumulate": (c_int, [P, c_int, c_int, P, P, c_size_t, P]),
     "asme_b200_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -58,6 +58,7 @@ _PROTOTYPES = {
     "asme_b200_gemm_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "asme_b200_dropout": (c_int, [P, P, c_longlong, c_float, c_uint64, c_uint32, P]),
     "asme_b200_binary": (c_int, [P, P, P, c_longlong, c_int, P]),
+    "asme_b200_gelu_bwd": (c_int, [P, P, P, c_longlong, P]),
     "asme_b200_attn_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P]),
     "asme_b200_attn_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P, P, P,
                                    c_size_t, P]),
@@ -67,6 +68,7 @@ _PROTOTYPES = {
     "asme_b200_score_topk_rank": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "asme_b200_topk_merge": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
     "asme_b200_ranking_metrics": (c_int, [P, c_int, P, c_int, P, P]),
+    "asme_b200_dense_ranking": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "asme_b200_score_ce_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     "asme_b200_ce_loss_from_partials": (c_int, [P, P, P, c_int, P, P, P]),

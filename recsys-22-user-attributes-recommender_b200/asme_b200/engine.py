@@ -1,0 +1,191 @@
+"""Execution engine of the transformer-encoder recommenders on top of the C-ABI kernels.
+
+``EncoderEngine`` owns no parameters: it reads weights (and writes gradients) through an
+:class:`~asme_b200.arena.ArenaModule` using the reference's state-dict names, and strings the fused
+kernels together:
+
+  embed (K1-K4) -> L x [LN -> QKV GEMM -> attention (K5,K8) -> out-proj (+residual) -> LN -> FFN (+residual)]
+  -> row select (K15) -> modifier (K11) -> fused scoring with CE / top-k+rank / BCE (K12-K20)
+
+Every activation needed by the backward pass is saved explicitly (``Saved``); dropout masks are
+recomputed from (seed, site, index).  Nothing here does arithmetic in torch.
+"""
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE
+
+BLOCKS = "_sequence_representation_layer.transformer_layer.transformer_blocks"
+MODIFIER = "_sequence_representation_modifier_layer"
+
+
+@dataclass
+class EncoderConfig:
+    hidden: int
+    heads: int
+    layers: int
+    intermediate: int
+    bidirectional: bool
+    dropout: float = 0.0
+    attention_dropout: float = 0.0
+
+
+@dataclass
+class LayerSaved:
+    x: torch.Tensor = None
+    y1: torch.Tensor = None
+    st1: torch.Tensor = None
+    qkv: torch.Tensor = None
+    ctx: torch.Tensor = None
+    ast: torch.Tensor = None
+    x2: torch.Tensor = None
+    y2: torch.Tensor = None
+    st2: torch.Tensor = None
+    z: torch.Tensor = None
+    a: torch.Tensor = None
+
+
+@dataclass
+class Saved:
+    B: int = 0
+    S: int = 0
+    seed: int = 0
+    training: bool = False
+    key_valid: Optional[torch.Tensor] = None
+    embed_spec: Any = None
+    embed_stats: Optional[torch.Tensor] = None
+    layers: List[LayerSaved] = field(default_factory=list)
+    extra: Dict[str, Any] = field(default_factory=dict)
+
+
+def block_param_specs(cfg: EncoderConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Arena layout of the encoder blocks: Wq|Wk|Wv and bq|bk|bv glued so that one GEMM computes QKV,
+    (gamma, beta) pairs glued so that LayerNorm backward writes one (2,H) target."""
+    H, FF = cfg.hidden, cfg.intermediate
+    specs = []
+    for l in range(cfg.layers):
+        p = f"{BLOCKS}.{l}"
+        specs += [(f"{p}.attention.linear_layers.0.weight+", (H, H)), (f"{p}.attention.linear_layers.1.weight+", (H, H)),
+                  (f"{p}.attention.linear_layers.2.weight", (H, H)),
+                  (f"{p}.attention.linear_layers.0.bias+", (H,)), (f"{p}.attention.linear_layers.1.bias+", (H,)),
+                  (f"{p}.attention.linear_layers.2.bias", (H,)),
+                  (f"{p}.attention.output_linear.weight", (H, H)), (f"{p}.attention.output_linear.bias", (H,)),
+                  (f"{p}.feed_forward.w_1.weight", (FF, H)), (f"{p}.feed_forward.w_1.bias", (FF,)),
+                  (f"{p}.feed_forward.w_2.weight", (H, FF)), (f"{p}.feed_forward.w_2.bias", (H,)),
+                  (f"{p}.input_sublayer.norm.weight+", (H,)), (f"{p}.input_sublayer.norm.bias", (H,)),
+                  (f"{p}.output_sublayer.norm.weight+", (H,)), (f"{p}.output_sublayer.norm.bias", (H,))]
+    return specs
+
+
+def modifier_param_specs(H: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    return [(f"{MODIFIER}.transform.0.weight", (H, H)), (f"{MODIFIER}.transform.0.bias", (H,)),
+            (f"{MODIFIER}.transform.2.weight+", (H,)), (f"{MODIFIER}.transform.2.bias", (H,))]
+
+
+class EncoderEngine:
+    def __init__(self, module, cfg: EncoderConfig):
+        self.m = module        # ArenaModule: weight(path[, buf]) / weights_span(...)
+        self.cfg = cfg
+
+    # ---------------------------------------------------------------- helpers
+    def _w(self, path, grad=False):
+        return self.m.weight(path, self.m._arena.ensure_grad() if grad else None)
+
+    def _site(self, layer, k):
+        return ops.SITE_LAYER_BASE + 8 * layer + k
+
+    # ---------------------------------------------------------------- encoder blocks
+    def blocks_forward(self, x: torch.Tensor, saved: Saved) -> torch.Tensor:
+        cfg, m = self.cfg, self.m
+        H = cfg.hidden
+        train = saved.training
+        p = cfg.dropout if train else 0.0
+        pa = cfg.attention_dropout if train else 0.0
+        B, S = saved.B, saved.S
+        for l in range(cfg.layers):
+            pre = f"{BLOCKS}.{l}"
+            ls = LayerSaved()
+            ls.x = x
+            ls.y1, ls.st1 = ops.layernorm_fwd(x, self._w(f"{pre}.input_sublayer.norm.weight"),
+                                              self._w(f"{pre}.input_sublayer.norm.bias"), save_stats=train)
+            wqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
+            bqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,))
+            ls.qkv = ops.gemm(ls.y1, wqkv, bias=bqkv)
+            ls.ctx, ls.ast = ops.attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa, saved.seed,
+                                          self._site(l, 0), save_stats=train)
+            ls.x2 = ops.gemm(ls.ctx, self._w(f"{pre}.attention.output_linear.weight"),
+                             bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,
+                             site=self._site(l, 1), residual=x)
+            ls.y2, ls.st2 = ops.layernorm_fwd(ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"),
+                                              self._w(f"{pre}.output_sublayer.norm.bias"), save_stats=train)
+            if train:
+                ls.a, ls.z = ops.gemm(ls.y2, self._w(f"{pre}.feed_forward.w_1.weight"), bias=self._w(f"{pre}.feed_forward.w_1.bias"),
+                                      act=ACT_GELU, pre_act_out=True, p_drop=p, seed=saved.seed, site=self._site(l, 2))
+            else:
+                ls.a = ops.gemm(ls.y2, self._w(f"{pre}.feed_forward.w_1.weight"), bias=self._w(f"{pre}.feed_forward.w_1.bias"),
+                                act=ACT_GELU)
+            x3 = ops.gemm(ls.a, self._w(f"{pre}.feed_forward.w_2.weight"), bias=self._w(f"{pre}.feed_forward.w_2.bias"),
+                          p_drop=p, seed=saved.seed, site=self._site(l, 3), residual=ls.x2)
+            x = ops.dropout(x3, p, saved.seed, self._site(l, 4)) if p > 0 else x3
+            if train:
+                saved.layers.append(ls)
+        return x
+
+    def blocks_backward(self, dx: torch.Tensor, saved: Saved) -> torch.Tensor:
+        cfg, m = self.cfg, self.m
+        H = cfg.hidden
+        p, pa = cfg.dropout, cfg.attention_dropout
+        B, S = saved.B, saved.S
+        g = m._arena.ensure_grad()
+        for l in reversed(range(cfg.layers)):
+            pre = f"{BLOCKS}.{l}"
+            ls = saved.layers[l]
+            dx3 = ops.dropout(dx, p, saved.seed, self._site(l, 4)) if p > 0 else dx
+            # ---- feed forward: x3 = x2 + drop(W2 a + b2), a = drop(gelu(z)), z = W1 y2 + b1
+            dy = ops.dropout(dx3, p, saved.seed, self._site(l, 3)) if p > 0 else dx3
+            ops.gemm_wgrad(dy, ls.a, self._w(f"{pre}.feed_forward.w_2.weight", True), self._w(f"{pre}.feed_forward.w_2.bias", True))
+            dz = ops.gemm(dy, self._w(f"{pre}.feed_forward.w_2.weight"), trans_b=False, mul_gelu_grad_of=ls.z, p_drop=p,
+                          seed=saved.seed, site=self._site(l, 2))
+            ops.gemm_wgrad(dz, ls.y2, self._w(f"{pre}.feed_forward.w_1.weight", True), self._w(f"{pre}.feed_forward.w_1.bias", True))
+            dy2 = ops.gemm(dz, self._w(f"{pre}.feed_forward.w_1.weight"), trans_b=False)
+            dgb2 = m.weights_span(f"{pre}.output_sublayer.norm.weight", f"{pre}.output_sublayer.norm.bias", (2, H), g)
+            dx2 = ops.layernorm_bwd(dy2, ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"), ls.st2, dgb2, d_residual=dx3)
+            # ---- attention: x2 = x + drop(ctx Wo^T + bo)
+            do = ops.dropout(dx2, p, saved.seed, self._site(l, 1)) if p > 0 else dx2
+            ops.gemm_wgrad(do, ls.ctx, self._w(f"{pre}.attention.output_linear.weight", True),
+                           self._w(f"{pre}.attention.output_linear.bias", True))
+            dctx = ops.gemm(do, self._w(f"{pre}.attention.output_linear.weight"), trans_b=False)
+            dqkv = ops.attn_bwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, ls.ctx, dctx, ls.ast, pa,
+                                saved.seed, self._site(l, 0))
+            wqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
+            dwqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H), g)
+            dbqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,), g)
+            ops.gemm_wgrad(dqkv, ls.y1, dwqkv, dbqkv)
+            dy1 = ops.gemm(dqkv, wqkv, trans_b=False)
+            dgb1 = m.weights_span(f"{pre}.input_sublayer.norm.weight", f"{pre}.input_sublayer.norm.bias", (2, H), g)
+            dx = ops.layernorm_bwd(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, d_residual=dx2)
+        return dx
+
+    # ---------------------------------------------------------------- FFN modifier  LN(GELU(Wx+b))  (K11)
+    def modifier_forward(self, x: torch.Tensor, save: bool):
+        w, b = self._w(f"{MODIFIER}.transform.0.weight"), self._w(f"{MODIFIER}.transform.0.bias")
+        if save:
+            a, z = ops.gemm(x, w, bias=b, act=ACT_GELU, pre_act_out=True)
+        else:
+            a, z = ops.gemm(x, w, bias=b, act=ACT_GELU), None
+        y, st = ops.layernorm_fwd(a, self._w(f"{MODIFIER}.transform.2.weight"), self._w(f"{MODIFIER}.transform.2.bias"),
+                                  save_stats=save)
+        return y, (x, z, a, st)
+
+    def modifier_backward(self, dy: torch.Tensor, saved) -> torch.Tensor:
+        x, z, a, st = saved
+        H = self.cfg.hidden
+        g = self.m._arena.ensure_grad()
+        dgb = self.m.weights_span(f"{MODIFIER}.transform.2.weight", f"{MODIFIER}.transform.2.bias", (2, H), g)
+        da = ops.layernorm_bwd(dy, a, self._w(f"{MODIFIER}.transform.2.weight"), st, dgb)
+        dz = ops.gelu_backward(da, z)
+        ops.gemm_wgrad(dz, x, self._w(f"{MODIFIER}.transform.0.weight", True), self._w(f"{MODIFIER}.transform.0.bias", True))
+        return ops.gemm(dz, self._w(f"{MODIFIER}.transform.0.weight"), trans_b=False)

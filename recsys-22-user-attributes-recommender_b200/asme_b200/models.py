@@ -1,0 +1,517 @@
+"""Drop-in model classes: ``BERT4RecModel``, ``KeBERT4RecModel``, ``SASRecModel``.
+
+Same class names, constructor keywords and parameter (state-dict) names as the reference
+(models/bert4rec/bert4rec_model.py:24-56, models/kebert4rec/kebert4rec_model.py:24-84,
+models/sasrec/sasrec_model.py:28-95), including its quirks, but every stage runs
+on the sm_100a kernels of ``libasme_b200.so``:
+
+  forward(InputSequence)            -> logits (N,S,V) / (pos,neg) / (N,I)   reference-compatible, inference
+  loss(...) / loss_backward(...)    -> fused training step: scoring + CE (or BCE) without materialising logits
+  evaluate_rank(...)                -> fused scoring + top-k + exact target rank for the metrics
+
+There is no PyTorch arithmetic on these paths and no CPU fallback.
+"""
+import math
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .arena import ArenaModule
+from .data import InputSequence
+from .engine import BLOCKS, MODIFIER, EncoderConfig, EncoderEngine, Saved, block_param_specs, modifier_param_specs
+
+PAD_TOKEN_ID = 0
+MASK_TOKEN_ID = 1
+
+_EMB = "_sequence_embedding_layer"
+_PRE_ATTR = f"{_EMB}.prefusion_attribute_embeddings"
+_POST_ATTR = f"{MODIFIER}.postfusion_attribute_embeddings"
+
+
+def _attr_vocab_size(name, tokenizers, sizes):
+    if sizes and name in sizes:
+        return int(sizes[name])
+    if tokenizers is not None:
+        tok = tokenizers.get("tokenizers." + name, tokenizers.get(name))
+        if tok is not None:
+            return len(tok)
+    raise KeyError(f"no vocabulary size for attribute '{name}': pass additional_attributes_tokenizer or attribute_vocab_sizes")
+
+
+class TransformerRecommenderModel(ArenaModule):
+    """Common machinery; subclasses only describe where their parameters live."""
+
+    # ---- filled in by subclasses -------------------------------------------------------------
+    item_table_path: str
+    pos_table_path: Optional[str] = None
+    ln1_paths: Optional[Tuple[str, str]] = None
+    ln2_paths: Optional[Tuple[str, str]] = None
+    modifier_kind: str = "identity"            # "ffn" | "identity"
+    projection_kind: str = "linear"            # "tied" | "linear" | "sasrec_neg"
+    embed_dropout_a: bool = True               # dropout after LN1 (TransformerEmbedding.dropout)
+
+    def _setup(self, cfg: EncoderConfig, item_vocab_size: int, max_seq_length: int, specs, prefusion, postfusion,
+               tokenizers, attr_sizes, merge: str):
+        self.cfg = cfg
+        self.item_vocab_size = int(item_vocab_size)
+        self.max_seq_length = int(max_seq_length)
+        self.postfusion_merge_function = merge
+        H = cfg.hidden
+        self.prefusion: List[Tuple[str, str, int]] = []      # (name, type, vocab)
+        self.postfusion: List[Tuple[str, str, int]] = []
+        attr_specs = []
+        for store, attrs, prefix in ((self.prefusion, prefusion, _PRE_ATTR), (self.postfusion, postfusion, _POST_ATTR)):
+            for name, info in (attrs or {}).items():
+                kind = info["embedding_type"]
+                va = _attr_vocab_size(name, tokenizers, attr_sizes)
+                store.append((name, kind, va))
+                if kind == "content_embedding":
+                    attr_specs.append((f"{prefix}.{name}.weight", (va, H)))
+                elif kind == "linear_upscale":
+                    attr_specs.append((f"{prefix}.{name}.linear.weight", (va, H), "T"))   # stored transposed (Va,H)
+                    attr_specs.append((f"{prefix}.{name}.linear.bias", (H,)))
+                else:
+                    raise KeyError(f"{kind} invalid attribute embedding type")
+        self.additional_metadata_keys = [n for n, _, _ in self.prefusion] + [n for n, _, _ in self.postfusion]
+        self._init_arena(list(specs) + attr_specs + [("_ghost_zero_row", (H,))])
+        self.engine = EncoderEngine(self, cfg)
+        self._seed = 0
+        self._step_counter = 0
+        self.loss_scale = 1.0
+
+    # ---- reference API --------------------------------------------------------------------------
+    def required_metadata_keys(self) -> List[str]:
+        return self.additional_metadata_keys
+
+    def optional_metadata_keys(self) -> List[str]:
+        return []
+
+    # ---- embedding ------------------------------------------------------------------------------
+    def _attr_operands(self, attrs: Dict[str, torch.Tensor], which, prefix, T):
+        singles, bags = [], []
+        for name, kind, _va in which:
+            ids = attrs[name]
+            if kind == "content_embedding":
+                singles.append((ids.reshape(T), self.weight(f"{prefix}.{name}.weight")))
+            else:
+                width = ids.shape[-1] if ids.dim() == 3 else 1
+                bags.append((ids.reshape(T, width), self.weight(f"{prefix}.{name}.linear.weight"),
+                             self.weight(f"{prefix}.{name}.linear.bias")))
+        return singles, bags
+
+    def _embed_spec(self, seq: torch.Tensor, attrs, training: bool, seed: int) -> ops.EmbedSpec:
+        B, S = seq.shape
+        singles, bags = self._attr_operands(attrs, self.prefusion, _PRE_ATTR, B * S)
+        ln1 = None if self.ln1_paths is None else (self.weight(self.ln1_paths[0]), self.weight(self.ln1_paths[1]))
+        ln2 = None if self.ln2_paths is None else (self.weight(self.ln2_paths[0]), self.weight(self.ln2_paths[1]))
+        pos = None if self.pos_table_path is None else self.weight(self.pos_table_path)
+        if pos is not None and S > pos.shape[0]:
+            raise RuntimeError(f"sequence length {S} exceeds max_seq_length {pos.shape[0]}")
+        return ops.EmbedSpec(seq.reshape(-1), self.weight(self.item_table_path), pos, singles, bags, ln1, ln2,
+                             self.cfg.dropout if training else 0.0, seed)
+
+    def _embed_backward(self, saved: Saved, d_x: torch.Tensor):
+        spec: ops.EmbedSpec = saved.embed_spec
+        B, S, H = saved.B, saved.S, self.cfg.hidden
+        g = self._arena.ensure_grad()
+        dln = None
+        if self.ln1_paths is not None or self.ln2_paths is not None:
+            off = self._arena.offsets[self._spec_name(self._dln_first)]     # [gamma1, beta1, gamma2, beta2] are glued
+            dln = g[off:off + 4 * H].view(4, H)
+        d_item, d_attr = ops.embed_bwd(spec, B, S, d_x, saved.embed_stats, dln)
+        ops.embgrad_sorted_reduce(spec.item_ids, d_item, self.weight(self.item_table_path, g))
+        if self.pos_table_path is not None:
+            ops.posgrad_reduce(d_item, B, S, self.weight(self.pos_table_path, g))
+        self._attr_backward(saved.extra["attrs"], self.prefusion, _PRE_ATTR, d_attr, B * S)
+
+    def _attr_backward(self, attrs, which, prefix, d_rows, T):
+        g = self._arena.ensure_grad()
+        for name, kind, _va in which:
+            ids = attrs[name]
+            if kind == "content_embedding":
+                ops.embgrad_sorted_reduce(ids.reshape(T), d_rows, self.weight(f"{prefix}.{name}.weight", g))
+            else:
+                width = ids.shape[-1] if ids.dim() == 3 else 1
+                ops.embgrad_sorted_reduce(ids.reshape(-1), d_rows, self.weight(f"{prefix}.{name}.linear.weight", g), skip_id=0,
+                                          row_divisor=width)
+                ops.colsum_accumulate(d_rows, self.weight(f"{prefix}.{name}.linear.bias", g))
+
+    # ---- hidden states ----------------------------------------------------------------------------
+    def _next_seed(self) -> int:
+        self._step_counter += 1
+        return (int(self._seed) << 32) + self._step_counter
+
+    def encode(self, seq: torch.Tensor, padding_mask: Optional[torch.Tensor], attrs: Dict[str, torch.Tensor],
+               training: bool = False) -> Tuple[torch.Tensor, Saved]:
+        """embed + encoder blocks (+ post-fusion merge): (T,H) hidden states of every position."""
+        if not self.arena_is_intact():
+            self._repack()
+        B, S = seq.shape
+        saved = Saved(B=B, S=S, seed=self._next_seed() if training else 0, training=training, key_valid=padding_mask)
+        saved.extra["attrs"] = attrs
+        spec = self._embed_spec(seq, attrs, training, saved.seed)
+        saved.embed_spec = spec
+        x, saved.embed_stats = ops.embed_fwd(spec, B, S, save_stats=training)
+        x = self.engine.blocks_forward(x, saved)
+        if self.postfusion:
+            singles, bags = self._attr_operands(attrs, self.postfusion, _POST_ATTR, B * S)
+            zero_ids = torch.zeros(B * S, dtype=torch.int64, device=seq.device)
+            ctx_spec = ops.EmbedSpec(zero_ids, self.weight("_ghost_zero_row").view(1, -1), None, singles, bags)
+            ctx, _ = ops.embed_fwd(ctx_spec, B, S)
+            saved.extra["post"] = (x, ctx)
+            if self.postfusion_merge_function in ("add", "multiply"):
+                x = ops.binary(x, ctx, self.postfusion_merge_function)
+        return x, saved
+
+    def encode_backward(self, d_hidden: torch.Tensor, saved: Saved):
+        if self.postfusion and self.postfusion_merge_function in ("add", "multiply"):
+            x, ctx = saved.extra["post"]
+            if self.postfusion_merge_function == "add":
+                d_ctx = d_hidden
+            else:
+                d_ctx = ops.binary(d_hidden, x, "multiply")
+                d_hidden = ops.binary(d_hidden, ctx, "multiply")
+            self._attr_backward(saved.extra["attrs"], self.postfusion, _POST_ATTR, d_ctx, saved.B * saved.S)
+        d_x = self.engine.blocks_backward(d_hidden, saved)
+        self._embed_backward(saved, d_x)
+
+    # ---- projection -------------------------------------------------------------------------------
+    def projection_operands(self, grad: bool = False):
+        buf = self._arena.ensure_grad() if grad else None
+        if self.projection_kind == "tied":
+            return self.weight(self.item_table_path, buf), self.weight("_projection_layer.output_bias", buf)
+        if self.projection_kind == "linear":
+            return self.weight("_projection_layer.linear.weight", buf), self.weight("_projection_layer.linear.bias", buf)
+        return self.weight(self.item_table_path, buf), None     # sasrec neg_sampling: h . E[item], no bias
+
+    def modify(self, rows: torch.Tensor, save: bool = False):
+        if self.modifier_kind == "ffn":
+            return self.engine.modifier_forward(rows, save)
+        return rows, None
+
+    def modify_backward(self, d_rows: torch.Tensor, saved_mod):
+        if self.modifier_kind == "ffn":
+            return self.engine.modifier_backward(d_rows, saved_mod)
+        return d_rows
+
+    # ---- reference-compatible forward (inference; materialises the logits the reference returns) --------
+    @torch.no_grad()
+    def forward(self, sequence: InputSequence):
+        seq = sequence.sequence
+        if seq.dim() != 2:
+            raise NotImplementedError("basket sequences (N,S,BS) are outside the B200 hot path (SURVEY.md 2.1 #3)")
+        B, S = seq.shape
+        hidden, _ = self.encode(seq, sequence.padding_mask, sequence.attributes, training=False)
+        if self.projection_kind == "sasrec_neg":
+            return self._sasrec_forward(sequence, hidden)
+        rows, _ = self.modify(hidden)
+        w, b = self.projection_operands()
+        return ops.gemm(rows, w, bias=b).view(B, S, self.item_vocab_size)
+
+    def _sasrec_forward(self, sequence: InputSequence, hidden: torch.Tensor):
+        pos = sequence.get_attribute("positive_samples")
+        neg = sequence.get_attribute("negative_samples")
+        B, S = sequence.sequence.shape
+        table = self.weight(self.item_table_path)
+        if neg is not None:
+            pl, nl = ops.posneg_bce_fwd(hidden, table, pos.reshape(-1), neg.reshape(-1), None, None)
+            return pl.view(B, S), nl.view(B, S)
+        last = last_position_rows(sequence.sequence, sequence.padding_mask)
+        h_last = ops.gather_rows(hidden, last)
+        all_scores = ops.gemm(h_last, table)                    # (B,V)
+        return all_scores if pos is None else torch.gather(all_scores, 1, pos)
+
+    # ---- fused training: scoring + cross entropy --------------------------------------------------------
+    def loss_ce(self, seq, padding_mask, attrs, target, pad_id: int = PAD_TOKEN_ID, rows: Optional[torch.Tensor] = None):
+        """Cross entropy over the positions with target != pad (== nn.CrossEntropyLoss(ignore_index=pad) over all
+        B*S rows, masked_training_module.py:107-111), without materialising logits.  Returns (loss, ctx)."""
+        hidden, saved = self.encode(seq, padding_mask, attrs, training=self.training)
+        flat_t = target.reshape(-1)
+        if rows is None:
+            rows = torch.nonzero(flat_t != pad_id).reshape(-1)          # index plumbing (one host sync for the count)
+        row_targets = flat_t.index_select(0, rows)
+        h_rows = ops.gather_rows(hidden, rows)
+        m_rows, saved_mod = self.modify(h_rows, save=self.training)
+        w, b = self.projection_operands()
+        rmax, rsum, tl = ops.score_ce_partial(m_rows, w, b, row_targets)
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=seq.device)
+        lse = ops.ce_loss_from_partials(rmax, rsum, tl, loss_sum)
+        n_rows = int(rows.numel())
+        loss = loss_sum[0] / n_rows if n_rows > 0 else loss_sum[0] * float("nan")
+        ctx = dict(saved=saved, rows=rows, row_targets=row_targets, m_rows=m_rows, saved_mod=saved_mod, lse=lse, n_rows=n_rows,
+                   T=hidden.shape[0])
+        return loss, ctx
+
+    def loss_ce_backward(self, ctx, dloss: float = 1.0):
+        if ctx["n_rows"] == 0:
+            return
+        g = self._prepare_grads()
+        w, b = self.projection_operands()
+        dw, db = self.projection_operands(grad=True)
+        d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], dw, db)
+        d_h = self.modify_backward(d_m, ctx["saved_mod"])
+        d_hidden = torch.zeros(ctx["T"], self.cfg.hidden, dtype=torch.float32, device=d_h.device)
+        ops.scatter_rows(d_h, ctx["rows"], d_hidden)
+        self.encode_backward(d_hidden, ctx["saved"])
+        self.attach_grads()
+
+    # ---- fused training: SASRec positive / negative BCE -----------------------------------------------
+    def loss_bce(self, seq, padding_mask, attrs, pos, neg, mask):
+        hidden, saved = self.encode(seq, padding_mask, attrs, training=self.training)
+        table = self.weight(self.item_table_path)
+        sums = torch.zeros(2, dtype=torch.float32, device=seq.device)
+        pl, nl = ops.posneg_bce_fwd(hidden, table, pos.reshape(-1), neg.reshape(-1), mask.reshape(-1), sums)
+        loss = sums[0] / sums[1]
+        ctx = dict(saved=saved, hidden=hidden, pos=pos.reshape(-1), neg=neg.reshape(-1), mask=mask.reshape(-1), pl=pl, nl=nl,
+                   sums=sums)
+        return loss, ctx
+
+    def loss_bce_backward(self, ctx, dloss: float = 1.0):
+        g = self._prepare_grads()
+        table = self.weight(self.item_table_path)
+        d_hidden, d_pos, d_neg = ops.posneg_bce_bwd(ctx["hidden"], table, ctx["pos"], ctx["neg"], ctx["mask"], ctx["pl"],
+                                                    ctx["nl"], ctx["sums"], dloss)
+        dtable = self.weight(self.item_table_path, g)
+        ops.embgrad_sorted_reduce(ctx["pos"], d_pos, dtable)
+        ops.embgrad_sorted_reduce(ctx["neg"], d_neg, dtable)
+        self.encode_backward(d_hidden, ctx["saved"])
+        self.attach_grads()
+
+    def _prepare_grads(self) -> torch.Tensor:
+        """Zero the flat gradient buffer unless the caller is accumulating (param.grad already attached)."""
+        g = self._arena.ensure_grad()
+        first = next(iter(self._named_arena_params()))[1]
+        if first.grad is None:
+            ops.fill(g, 0.0)
+        return g
+
+    # ---- fused evaluation: scoring + top-k + exact target rank --------------------------------------------
+    @torch.no_grad()
+    def evaluate_rank(self, seq, padding_mask, attrs, target, k: int = 10, rows: Optional[torch.Tensor] = None,
+                      select: str = "mask", mask_id: int = MASK_TOKEN_ID, with_loss: bool = False, pad_id: int = PAD_TOKEN_ID):
+        """returns dict(topk_val (B,k), topk_idx (B,k) int32, rank (B) int32 1-based, target_score (B)[, loss])"""
+        hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
+        if rows is None:
+            rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
+        h_rows = ops.gather_rows(hidden, rows)
+        m_rows, _ = self.modify(h_rows)
+        w, b = self.projection_operands()
+        out = score_rows(m_rows, w, b, target, k)
+        if with_loss:      # nn.CrossEntropyLoss(ignore_index=pad) on the selected rows (masked_training_module.py:150)
+            rmax, rsum, _tl = ops.score_ce_partial(m_rows, w, b, target)
+            nll = rmax + torch.log(rsum) - out["target_score"]
+            keep = target.ne(pad_id)
+            out["loss"] = (nll * keep).sum() / keep.sum()
+        return out
+
+
+def score_rows(m_rows, w, b, target, k):
+    ts = ops.score_targets(m_rows, w, b, target)
+    val, idx, ng, nt = ops.score_topk_rank(m_rows, w, b, k, target, ts)
+    rank = (ng + nt + 1).to(torch.int32)
+    return dict(topk_val=val, topk_idx=idx, rank=rank, target_score=ts, n_greater=ng, n_tie_lower=nt)
+
+
+def mask_position_rows(seq: torch.Tensor, mask_id: int) -> torch.Tensor:
+    """flat row index b*S + (position of the MASK token) -- one MASK per row (masked_training_module.py:80-91)."""
+    B, S = seq.shape
+    pos = (seq == mask_id).to(torch.int32).argmax(dim=1)
+    return torch.arange(B, device=seq.device, dtype=torch.int64) * S + pos
+
+
+def last_position_rows(seq: torch.Tensor, padding_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """flat row index of the last real item (next_item_prediction_training_module.py:226-244); python-style
+    wrap-around (-1 -> S-1) for all-padding rows, as advanced indexing does in the reference."""
+    B, S = seq.shape
+    pm = padding_mask if padding_mask is not None else seq.ne(PAD_TOKEN_ID)
+    last = pm.sum(dim=-1).to(torch.int64) - 1
+    last = torch.where(last < 0, last + S, last)
+    return torch.arange(B, device=seq.device, dtype=torch.int64) * S + last
+
+
+# ----------------------------------------------------------------------------------------------------
+# initialisers (a19)
+# ----------------------------------------------------------------------------------------------------
+def _is_norm(path: str) -> bool:
+    return "norm" in path or path.endswith("transform.2.weight") or path.endswith("transform.2.bias")
+
+
+def _is_matrix_weight(path: str, p: torch.Tensor) -> bool:
+    return p.dim() == 2
+
+
+@torch.no_grad()
+def _init_normal(model: ArenaModule, std: float):
+    """normal_initialize_weights (bert4rec_model.py:59-68): Linear/Embedding weights N(0,std), LN 1/0, biases 0;
+    ``output_bias`` keeps U(+-1/sqrt(V)) (layers.py:134-136)."""
+    for path, p in model._named_arena_params():
+        if path.endswith("output_bias"):
+            bound = 1.0 / math.sqrt(p.numel())
+            p.uniform_(-bound, bound)
+        elif _is_norm(path):
+            p.fill_(1.0) if path.endswith("weight") else p.zero_()
+        elif p.dim() == 2:
+            p.copy_(torch.randn(p.shape) * std)
+        else:
+            p.zero_()
+
+
+@torch.no_grad()
+def _init_xavier(model: ArenaModule):
+    """TransformerEncoderModel._init_weights (transformer_encoder_model.py:63-73): xavier-normal Linear+Embedding."""
+    for path, p in model._named_arena_params():
+        if _is_norm(path):
+            p.fill_(1.0) if path.endswith("weight") else p.zero_()
+        elif p.dim() == 2:
+            fan_out, fan_in = p.shape
+            p.copy_(torch.randn(p.shape) * math.sqrt(2.0 / (fan_in + fan_out)))
+        else:
+            p.zero_()
+
+
+def _encoder_config(hidden, heads, layers, dropout, bidirectional, intermediate, attention_dropout) -> EncoderConfig:
+    if hidden % heads != 0:
+        raise AssertionError("transformer_hidden_size must be divisible by num_transformer_heads")
+    return EncoderConfig(hidden=hidden, heads=heads, layers=layers,
+                         intermediate=4 * hidden if intermediate is None else intermediate, bidirectional=bidirectional,
+                         dropout=float(dropout), attention_dropout=float(dropout if attention_dropout is None else attention_dropout))
+
+
+def _alias(model: nn.Module, alias_path: str, param: nn.Parameter):
+    """Register the SAME Parameter under a second path (the reference's tied modules appear twice in state_dict)."""
+    mod = model
+    parts = alias_path.split(".")
+    for part in parts[:-1]:
+        if not hasattr(mod, part):
+            setattr(mod, part, nn.Module())
+        mod = getattr(mod, part)
+    mod.register_parameter(parts[-1], param)
+
+
+def _get_param(model: nn.Module, path: str) -> nn.Parameter:
+    mod = model
+    parts = path.split(".")
+    for part in parts[:-1]:
+        mod = getattr(mod, part)
+    return mod._parameters[parts[-1]]
+
+
+# ----------------------------------------------------------------------------------------------------
+# the three models
+# ----------------------------------------------------------------------------------------------------
+class BERT4RecModel(TransformerRecommenderModel):
+    """bidirectional encoder, NO positional embedding (quirk Q1), FFN modifier, tied projection by default."""
+
+    item_table_path = f"{_EMB}.item_embedding.embedding.weight"
+    ln1_paths = (f"{_EMB}.embedding_norm.weight", f"{_EMB}.embedding_norm.bias")
+    modifier_kind = "ffn"
+    _dln_first = f"{_EMB}.embedding_norm.weight"
+
+    def __init__(self, transformer_hidden_size: int, num_transformer_heads: int, num_transformer_layers: int,
+                 item_vocab_size: int, max_seq_length: int, transformer_dropout: float,
+                 project_layer_type: str = "transpose_embedding", embedding_pooling_type: str = None,
+                 initializer_range: float = 0.02, transformer_intermediate_size: int = None,
+                 transformer_attention_dropout: float = None):
+        super().__init__()
+        if embedding_pooling_type:
+            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        H, V = transformer_hidden_size, item_vocab_size
+        cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, True,
+                              transformer_intermediate_size, transformer_attention_dropout)
+        specs = [(self.item_table_path, (V, H)),
+                 (f"{_EMB}.embedding_norm.weight+", (H,)), (f"{_EMB}.embedding_norm.bias+", (H,)), ("_ghost_ln2", (2 * H,))]
+        specs += block_param_specs(cfg) + modifier_param_specs(H)
+        if project_layer_type == "transpose_embedding":
+            self.projection_kind = "tied"
+            specs.append(("_projection_layer.output_bias", (V,)))
+        elif project_layer_type == "linear":
+            self.projection_kind = "linear"
+            specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
+        else:
+            raise KeyError(f"{project_layer_type} invalid projection layer")
+        self._setup(cfg, V, max_seq_length, specs, None, None, None, None, "add")
+        if self.projection_kind == "tied":
+            _alias(self, "_projection_layer.embedding.weight", _get_param(self, self.item_table_path))
+        _init_normal(self, initializer_range)
+
+
+class KeBERT4RecModel(TransformerRecommenderModel):
+    """BERT4Rec + positional embedding + pre-/post-fused attribute embeddings; untied Linear projection."""
+
+    item_table_path = f"{_EMB}.item_embedding_layer.item_embedding.embedding.weight"
+    ln2_paths = (f"{_EMB}.norm_embedding.weight", f"{_EMB}.norm_embedding.bias")
+    modifier_kind = "ffn"
+    projection_kind = "linear"
+    _dln_first = "_ghost_ln1"
+
+    def __init__(self, transformer_hidden_size: int, num_transformer_heads: int, num_transformer_layers: int,
+                 item_vocab_size: int, max_seq_length: int, transformer_dropout: float,
+                 prefusion_attributes: Dict[str, Dict[str, Any]] = None, postfusion_attributes: Dict[str, Dict[str, Any]] = None,
+                 additional_attributes_tokenizer: Dict[str, Any] = None, postfusion_merge_function: str = "add",
+                 positional_embedding: bool = True, embedding_pooling_type: str = None, initializer_range: float = 0.02,
+                 transformer_intermediate_size: Optional[int] = None, transformer_attention_dropout: Optional[float] = None,
+                 attribute_vocab_sizes: Dict[str, int] = None):
+        super().__init__()
+        if embedding_pooling_type:
+            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        H, V = transformer_hidden_size, item_vocab_size
+        cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, True,
+                              transformer_intermediate_size, transformer_attention_dropout)
+        # NOTE the reference passes positional_embedding positionally-correct here (keyword), but TransformerEmbedding's
+        # default is True and the kwarg is not forwarded (kebert4rec_model.py:47-49): positions are always on.
+        self.pos_table_path = f"{_EMB}.item_embedding_layer.position_embedding.weight"
+        specs = [(self.item_table_path, (V, H)), (self.pos_table_path, (max_seq_length, H)),
+                 ("_ghost_ln1+", (2 * H,)), (f"{_EMB}.norm_embedding.weight+", (H,)), (f"{_EMB}.norm_embedding.bias", (H,))]
+        specs += block_param_specs(cfg) + modifier_param_specs(H)
+        specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
+        self._setup(cfg, V, max_seq_length, specs, prefusion_attributes, postfusion_attributes,
+                    additional_attributes_tokenizer, attribute_vocab_sizes, postfusion_merge_function)
+        _init_normal(self, initializer_range)
+
+
+class SASRecModel(TransformerRecommenderModel):
+    """causal encoder; LayerNorm (+dropout) applied TWICE to the embedding (quirk Q2); ``mode`` selects the
+    projection: "neg_sampling" (dot with positive / negative item embeddings) or "full" (Linear over the catalog)."""
+
+    item_table_path = f"{_EMB}.item_embedding_layer.item_embedding.embedding.weight"
+    pos_table_path = f"{_EMB}.item_embedding_layer.position_embedding.weight"
+    ln1_paths = (f"{_EMB}.item_embedding_layer.embedding_norm.weight", f"{_EMB}.item_embedding_layer.embedding_norm.bias")
+    ln2_paths = (f"{_EMB}.norm_embedding.weight", f"{_EMB}.norm_embedding.bias")
+    modifier_kind = "identity"
+    _dln_first = f"{_EMB}.item_embedding_layer.embedding_norm.weight"
+
+    def __init__(self, transformer_hidden_size: int, num_transformer_heads: int, num_transformer_layers: int,
+                 item_vocab_size: int, max_seq_length: int, transformer_dropout: float,
+                 prefusion_attributes: Dict[str, Dict[str, Any]] = None, postfusion_attributes: Dict[str, Dict[str, Any]] = None,
+                 additional_attributes_tokenizer: Dict[str, Any] = None, postfusion_merge_function: str = "add",
+                 embedding_pooling_type: str = None, transformer_intermediate_size: int = None,
+                 transformer_attention_dropout: float = None, mode: str = "neg_sampling",
+                 attribute_vocab_sizes: Dict[str, int] = None):
+        super().__init__()
+        if embedding_pooling_type:
+            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        H, V = transformer_hidden_size, item_vocab_size
+        cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, False,
+                              transformer_intermediate_size, transformer_attention_dropout)
+        self.mode = mode
+        specs = [(self.item_table_path, (V, H)), (self.pos_table_path, (max_seq_length, H)),
+                 (self.ln1_paths[0] + "+", (H,)), (self.ln1_paths[1] + "+", (H,)),
+                 (self.ln2_paths[0] + "+", (H,)), (self.ln2_paths[1], (H,))]
+        specs += block_param_specs(cfg)
+        if mode == "neg_sampling":
+            self.projection_kind = "sasrec_neg"
+        elif mode == "full":
+            self.projection_kind = "linear"
+            specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
+        else:
+            raise Exception(f"{mode} is an unknown projection mode. Choose either <full> or <neg_sampling>.")
+        self._setup(cfg, V, max_seq_length, specs, prefusion_attributes, postfusion_attributes,
+                    additional_attributes_tokenizer, attribute_vocab_sizes, postfusion_merge_function)
+        if mode == "neg_sampling":      # SASRecProjectionComponent holds the TransformerEmbedding again (components.py:16-19)
+            base = f"{_EMB}.item_embedding_layer"
+            for sub in ("item_embedding.embedding.weight", "position_embedding.weight", "embedding_norm.weight",
+                        "embedding_norm.bias"):
+                _alias(self, f"_projection_layer.embedding.{sub}", _get_param(self, f"{base}.{sub}"))
+        _init_xavier(self)

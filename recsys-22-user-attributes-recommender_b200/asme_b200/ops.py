@@ -130,14 +130,15 @@ def embed_bwd(spec: EmbedSpec, B: int, S: int, d_out: torch.Tensor, stats: Optio
     return d_item, d_attr
 
 
-def embgrad_sorted_reduce(ids: torch.Tensor, d_rows: torch.Tensor, d_table: torch.Tensor, skip_id: int = -1):
-    """d_table[ids[t]] += d_rows[t] (deterministic: sort -> segmented reduce)."""
+def embgrad_sorted_reduce(ids: torch.Tensor, d_rows: torch.Tensor, d_table: torch.Tensor, skip_id: int = -1,
+                          row_divisor: int = 1):
+    """d_table[ids[t]] += d_rows[t // row_divisor] (deterministic: sort -> segmented reduce)."""
     ids = _i64(ids).reshape(-1)
     d_rows = _f32(d_rows)
     T, H = ids.numel(), d_table.shape[1]
     ws_bytes = _lib.query("asme_b200_embgrad_workspace_bytes", T, H)
     ws = workspace(ws_bytes, d_rows.device)
-    _lib.call("asme_b200_embgrad_sorted_reduce", _p(ids), T, _p(d_rows), H, _p(d_table), d_table.shape[0], skip_id,
+    _lib.call("asme_b200_embgrad_sorted_reduce", _p(ids), T, _p(d_rows), int(row_divisor), H, _p(d_table), d_table.shape[0], skip_id,
               _p(ws), ws.numel(), _stream())
 
 
@@ -216,6 +217,13 @@ def dropout(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
     y = torch.empty_like(x)
     _lib.call("asme_b200_dropout", _p(x), _p(y), x.numel(), float(p), int(seed), int(site), _stream())
     return y
+
+
+def gelu_backward(dy: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    dy, z = _f32(dy), _f32(z)
+    dz = torch.empty_like(dy)
+    _lib.call("asme_b200_gelu_bwd", _p(dy), _p(z), _p(dz), dy.numel(), _stream())
+    return dz
 
 
 def binary(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
@@ -298,6 +306,17 @@ def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):
 def ranking_metrics(rank: torch.Tensor, ks: torch.Tensor, out: torch.Tensor):
     """out (4, n_k) += sums of recall, NDCG, MRR, precision @ ks over the batch."""
     _lib.call("asme_b200_ranking_metrics", _p(rank), rank.numel(), _p(ks), ks.numel(), _p(out), _stream())
+
+
+def dense_ranking(pred: torch.Tensor, pos_mask: torch.Tensor, metric_mask: Optional[torch.Tensor], k: int) -> torch.Tensor:
+    """(7,N): recall, precision, DCG, NDCG, MRR, F1 @k and full rank, from dense (N,I) predictions."""
+    pred = _f32(pred, "predictions")
+    N, I = pred.shape
+    pm = _i64(pos_mask, "positive_item_mask")
+    mm = None if metric_mask is None else _i64(metric_mask, "metric_mask")
+    out = torch.empty(7, N, dtype=torch.float32, device=pred.device)
+    _lib.call("asme_b200_dense_ranking", _p(pred), _p(pm), _p(mm), N, I, int(k), _p(out), _stream())
+    return out
 
 
 def score_ce_partial(h, w, bias, target, v0: int = 0):

@@ -18,13 +18,13 @@
 #define CHUNK 32
 #define MAXQ 4   // H <= 512 : up to 4 float4 per lane
 
-__global__ void embgrad_keys_kernel(const int64_t* __restrict__ ids, int T, int V, int64_t skip_id, int* __restrict__ keys,
-                                    int* __restrict__ vals) {
+__global__ void embgrad_keys_kernel(const int64_t* __restrict__ ids, int T, int V, int64_t skip_id, int row_divisor,
+                                    int* __restrict__ keys, int* __restrict__ vals) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int64_t id = ids[t];
     keys[t] = (id == skip_id || id < 0 || id >= V) ? V : (int)id;   // V = 'skipped' sentinel, sorts last
-    vals[t] = t;
+    vals[t] = t / row_divisor;   // index of the gradient row this entry reads
 }
 
 struct Acc {
@@ -136,8 +136,10 @@ extern "C" size_t asme_b200_embgrad_workspace_bytes(int T, int H) {
            2 * align256(chunks * sizeof(int));
 }
 
-extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int H, float* d_table, int V,
-                                               int64_t skip_id, void* ws, size_t ws_bytes, asme_stream_t stream) {
+extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int row_divisor, int H,
+                                               float* d_table, int V, int64_t skip_id, void* ws, size_t ws_bytes,
+                                               asme_stream_t stream) {
+    ASME_REQUIRE(row_divisor >= 1, "embgrad: row_divisor=%d", row_divisor);
     ASME_REQUIRE(ids && d_rows && d_table, "embgrad: null argument");
     ASME_REQUIRE(H % 4 == 0 && H >= 4 && H <= 512, "embgrad: H=%d unsupported (4..512, multiple of 4)", H);
     ASME_REQUIRE(V >= 1, "embgrad: V=%d", V);
@@ -160,7 +162,7 @@ extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const 
     int* tail_key = (int*)p; p += align256((size_t)chunks * sizeof(int));
     int* flags = (int*)p;
 
-    embgrad_keys_kernel<<<ceil_div(T, 256), 256, 0, st>>>(ids, T, V, skip_id, keys_in, vals_in);
+    embgrad_keys_kernel<<<ceil_div(T, 256), 256, 0, st>>>(ids, T, V, skip_id, row_divisor, keys_in, vals_in);
     ASME_LAUNCH_OK();
     int bits = 1;
     while ((1LL << bits) <= (long long)V) ++bits;   // keys are in [0, V]

@@ -526,6 +526,18 @@ extern "C" int asme_b200_binary(const float* a, const float* b, float* y, long l
     return ASME_OK;
 }
 
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, float* __restrict__ dz, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dz[i] = dy[i] * gelu_erf_grad(z[i]);
+}
+extern "C" int asme_b200_gelu_bwd(const float* dy, const float* z, float* dz, long long n, asme_stream_t stream) {
+    ASME_REQUIRE(dy && z && dz, "gelu_bwd: null argument");
+    if (n == 0) return ASME_OK;
+    gelu_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, z, dz, n);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
 __global__ void fill_kernel(float* x, long long n, float v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;

@@ -785,3 +785,84 @@ extern "C" int asme_b200_posneg_bce_bwd(const float* Hseq, const float* E, const
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// dense-signature ranking metrics (compatibility path of RankingMetric.update(predictions, positive_item_mask,
+// metric_mask), metrics/metric.py:57-83): one warp per row, O(I) scan instead of the reference's full argsort.
+// out (7, N): recall, precision, dcg, ndcg, mrr, f1 @k and the full rank of the worst relevant item.
+// ---------------------------------------------------------------------------------------------
+__global__ void dense_ranking_kernel(const float* __restrict__ pred, const int64_t* __restrict__ pos_mask,
+                                     const int64_t* __restrict__ metric_mask, int N, int I, int k, float* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= N) return;
+    const float* p = pred + (size_t)row * I;
+    const int64_t* pm = pos_mask + (size_t)row * I;
+    const int64_t* mm = metric_mask ? metric_mask + (size_t)row * I : nullptr;
+    const float FMIN = -3.402823466e+38f;
+    // pass 1: top-k list, number of relevant items, worst relevant item
+    float lv = -INFINITY, thr_v = -INFINITY, worst_v = INFINITY;
+    int li = INT_MAX, thr_i = INT_MAX, worst_i = -1, n_rel = 0;
+    for (int base = 0; base < I; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < I;
+        float v = valid ? p[j] : -INFINITY;
+        if (valid && mm && mm[j] == 0) v = FMIN;
+        topk_offer(lv, li, thr_v, thr_i, v, j, valid, lane, k < 32 ? k : 32);
+        if (valid && pm[j] != 0) {
+            ++n_rel;
+            if (worst_i < 0 || v < worst_v || (v == worst_v && j > worst_i)) { worst_v = v; worst_i = j; }   // lowest score, ties -> largest id
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        n_rel += __shfl_xor_sync(0xffffffffu, n_rel, s);
+        const float ov = __shfl_xor_sync(0xffffffffu, worst_v, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, worst_i, s);
+        if (oi >= 0 && (worst_i < 0 || ov < worst_v || (ov == worst_v && oi > worst_i))) { worst_v = ov; worst_i = oi; }
+    }
+    // pass 2: rank of the worst relevant item = 1 + #items ranked before it
+    int before = 0;
+    if (worst_i >= 0) {
+        for (int j = lane; j < I; j += 32) {
+            float v = p[j];
+            if (mm && mm[j] == 0) v = FMIN;
+            before += (j != worst_i) && better(v, j, worst_v, worst_i);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) before += __shfl_xor_sync(0xffffffffu, before, s);
+    }
+    // metrics from the true-positive flags of the top-k list
+    const int kk = min(k, I);
+    const bool hit = lane < kk && li != INT_MAX && pm[li] != 0;
+    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    const float tp = (float)__popc(hits);
+    float dcg = hit ? 1.0f / log2f((float)lane + 2.0f) : 0.f;
+    float idcg = (lane < min(n_rel, k)) ? 1.0f / log2f((float)lane + 2.0f) : 0.f;
+    dcg = warp_sum(dcg);
+    idcg = warp_sum(idcg);
+    if (lane == 0) {
+        const float recall = n_rel > 0 ? tp / (float)n_rel : 0.f;
+        const float precision = tp / (float)k;
+        const int last_hit = hits ? 32 - __clz(hits) : 0;     // mrr.py:31: max(rank * tp)
+        const float f1 = (recall + precision) > 0.f ? 2.f * recall * precision / (recall + precision) : 0.f;
+        out[0 * (size_t)N + row] = recall;
+        out[1 * (size_t)N + row] = precision;
+        out[2 * (size_t)N + row] = dcg;
+        out[3 * (size_t)N + row] = idcg > 0.f ? dcg / idcg : 0.f;
+        out[4 * (size_t)N + row] = last_hit ? 1.0f / (float)last_hit : 0.f;
+        out[5 * (size_t)N + row] = f1;
+        out[6 * (size_t)N + row] = worst_i >= 0 ? (float)(before + 1) : 0.f;
+    }
+}
+
+extern "C" int asme_b200_dense_ranking(const float* pred, const int64_t* pos_mask, const int64_t* metric_mask, int N, int I, int k,
+                                       float* out, asme_stream_t stream) {
+    ASME_REQUIRE(pred && pos_mask && out, "dense_ranking: null argument");
+    ASME_REQUIRE(k >= 1 && k <= 32, "dense_ranking: k=%d unsupported (1..32)", k);
+    ASME_REQUIRE(I >= 1, "dense_ranking: I=%d", I);
+    if (N == 0) return ASME_OK;
+    dense_ranking_kernel<<<ceil_div(N, 4), 128, 0, (cudaStream_t)stream>>>(pred, pos_mask, metric_mask, N, I, k, out);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}

@@ -1,0 +1,118 @@
+"""CPU-side tests of the host logic: state-dict compatibility with the reference checkpoints (fixture keys and
+shapes), arena packing, plug-in registration table, metric bookkeeping that needs no kernel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from asme_b200.models import BERT4RecModel, KeBERT4RecModel, SASRecModel
+from asme_b200 import plugin
+
+
+def _fixture_weights(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    return z, {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+
+
+def build_from_fixture(golden_dir, name):
+    z, w = _fixture_weights(golden_dir, name)
+    kw = dict(transformer_hidden_size=int(z["H"]), num_transformer_heads=int(z["heads"]), num_transformer_layers=int(z["L"]),
+              item_vocab_size=int(z["V"]), max_seq_length=int(z["S"]), transformer_dropout=0.0)
+    if name.startswith("bert4rec"):
+        model = BERT4RecModel(**kw)
+    elif name.startswith("kebert4rec"):
+        model = KeBERT4RecModel(prefusion_attributes={"category": {"embedding_type": "content_embedding"},
+                                                      "tags": {"embedding_type": "linear_upscale"}},
+                                attribute_vocab_sizes={"category": w["_sequence_embedding_layer.prefusion_attribute_embeddings.category.weight"].shape[0],
+                                                       "tags": w["_sequence_embedding_layer.prefusion_attribute_embeddings.tags.linear.weight"].shape[1]},
+                                **kw)
+    elif name.startswith("sasrec_full"):
+        model = SASRecModel(mode="full", **kw)
+    else:
+        model = SASRecModel(mode="neg_sampling", **kw)
+    return z, w, model
+
+
+@pytest.mark.parametrize("name", ["bert4rec_small.npz", "kebert4rec_small.npz", "sasrec_full_small.npz", "sasrec_neg_small.npz"])
+def test_state_dict_is_checkpoint_compatible(golden_dir, name):
+    """every key of the reference's state_dict exists with the same shape, and loads strictly"""
+    z, w, model = build_from_fixture(golden_dir, name)
+    sd = model.state_dict()
+    for k, v in w.items():
+        assert k in sd, f"missing reference key {k}"
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    if not name.startswith("sasrec_neg"):      # that fixture omits the aliased _projection_layer.* duplicates
+        assert set(sd) == set(w)
+        model.load_state_dict(w, strict=True)
+    else:
+        model.load_state_dict(w, strict=False)
+    for k, v in w.items():
+        assert torch.equal(model.state_dict()[k], v), k
+    assert model.arena_is_intact()
+
+
+def test_arena_layout_glues_qkv_and_layernorm_pairs():
+    m = BERT4RecModel(16, 2, 2, 50, 12, 0.0)
+    pre = "_sequence_representation_layer.transformer_layer.transformer_blocks.0"
+    wqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (48, 16))
+    sd = m.state_dict()
+    assert torch.equal(wqkv, torch.cat([sd[f"{pre}.attention.linear_layers.{i}.weight"] for i in range(3)]))
+    gb = m.weights_span(f"{pre}.input_sublayer.norm.weight", f"{pre}.input_sublayer.norm.bias", (2, 16))
+    assert torch.equal(gb[0], sd[f"{pre}.input_sublayer.norm.weight"]) and torch.equal(gb[1], sd[f"{pre}.input_sublayer.norm.bias"])
+    # tied projection: same storage, both keys present
+    assert sd["_projection_layer.embedding.weight"].data_ptr() == sd["_sequence_embedding_layer.item_embedding.embedding.weight"].data_ptr()
+    # every parameter is 256-byte aligned inside the flat arena unless glued
+    assert m._arena.flat.numel() % 64 == 0
+
+
+def test_arena_survives_module_apply():
+    m = SASRecModel(16, 2, 1, 50, 12, 0.0, mode="full")
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.double().float()          # _apply replaces .data -> arena must be re-packed
+    assert m.arena_is_intact()
+    for k, v in before.items():
+        assert torch.equal(m.state_dict()[k], v)
+    opt_params = list(m.parameters())
+    m.attach_grads()
+    assert all(p.grad is not None and p.grad.shape == p.shape for p in opt_params)
+
+
+def test_linear_upscale_weight_is_stored_transposed():
+    m = KeBERT4RecModel(16, 2, 1, 50, 12, 0.0, prefusion_attributes={"tags": {"embedding_type": "linear_upscale"}},
+                        attribute_vocab_sizes={"tags": 17})
+    p = dict(m.named_parameters())["_sequence_embedding_layer.prefusion_attribute_embeddings.tags.linear.weight"]
+    assert tuple(p.shape) == (16, 17) and not p.is_contiguous()          # reference layout, (Va,H) storage underneath
+    assert m.weight("_sequence_embedding_layer.prefusion_attribute_embeddings.tags.linear.weight").shape == (17, 16)
+    assert m.required_metadata_keys() == ["tags"]
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(KeyError):
+        BERT4RecModel(16, 2, 1, 50, 12, 0.0, project_layer_type="nope")
+    with pytest.raises(Exception, match="unknown projection mode"):
+        SASRecModel(16, 2, 1, 50, 12, 0.0, mode="nope")
+    with pytest.raises(AssertionError):
+        BERT4RecModel(10, 3, 1, 50, 12, 0.0)
+
+
+def test_plugin_registration_table():
+    assert set(plugin.REGISTRATIONS) == {"bert4rec", "kebert4rec", "sasrec-cross", "sasrec-neg"}
+    mod_cls, model_cls = plugin.REGISTRATIONS["sasrec-neg"]
+    assert mod_cls.__name__ == "SequenceNextItemPredictionTrainingModule" and model_cls.__name__ == "SASRecModel"
+
+
+def test_missing_metadata_raises_like_reference():
+    from asme_b200.modules import get_additional_meta_data
+    m = KeBERT4RecModel(16, 2, 1, 50, 12, 0.0, prefusion_attributes={"cat": {"embedding_type": "content_embedding"}},
+                        attribute_vocab_sizes={"cat": 9})
+    with pytest.raises(Exception, match="does not contain the following additional metadata: cat"):
+        get_additional_meta_data(m, {"item": torch.zeros(1, 2, dtype=torch.long)})
+
+
+def test_model_forward_without_gpu_fails_loudly():
+    from asme_b200.data import InputSequence
+    m = BERT4RecModel(16, 2, 1, 50, 12, 0.0)
+    seq = torch.randint(3, 50, (2, 12))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(InputSequence(seq, seq.ne(0), {}))
