@@ -243,8 +243,8 @@ int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, i
  * K22  fused Adam over the flat parameter arena (torch.optim.Adam semantics: L2 decay added to the gradient;
  * reference defaults beta = (0.99, 0.998), masked_training_module.py:165-168)
  * ------------------------------------------------------------------------------------------ */
-int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
-                        float beta2, float eps, float weight_decay, int step, asme_stream_t stream);
+int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, int step, asme_stream_t stream);
 int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream);
 
 #ifdef __cplusplus

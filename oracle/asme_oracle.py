@@ -33,6 +33,15 @@ BCE_EPS = 1e-24                  # losses/sasrec/sas_rec_losses.py:48
 
 Weights = Dict[str, torch.Tensor]
 
+# Training-mode dropout probability of every nn.Dropout site of the reference path (transformer_layers.py:40,78,
+# 116,130,152,171,215,249,258; kebert4rec/components.py:51,62).  0 = eval mode / parity mode.  Only the CPU baseline
+# timing sets it (the masks are torch's, parity tests always run with 0).
+DROPOUT_P = 0.0
+
+
+def _drop(x: torch.Tensor) -> torch.Tensor:
+    return F.dropout(x, DROPOUT_P, training=True) if DROPOUT_P > 0.0 else x
+
 
 # --------------------------------------------------------------------------------------------
 # a1  padding mask                                  modules/util/module_util.py:13-30
@@ -65,7 +74,7 @@ def transformer_embedding(seq: torch.Tensor, item_table: torch.Tensor,
         s = seq.shape[1]
         x = x + position_table[torch.arange(s)].unsqueeze(0)
     if norm is not None:
-        x = layer_norm(x, norm[0], norm[1])
+        x = _drop(layer_norm(x, norm[0], norm[1]))
     return x
 
 
@@ -128,13 +137,13 @@ def multi_head_attention(x: torch.Tensor, w: Weights, prefix: str, heads: int,
     scores = (q @ k.transpose(-2, -1)) / math.sqrt(d)
     if mask is not None:
         scores = scores.masked_fill(mask == 0, ATTENTION_FILL)       # -1e9, not -inf (Q4)
-    p = torch.softmax(scores, dim=-1)
+    p = _drop(torch.softmax(scores, dim=-1))
     ctx = (p @ v).transpose(1, 2).contiguous().view(b, s, h)
     return ctx @ w[f"{prefix}.output_linear.weight"].t() + w[f"{prefix}.output_linear.bias"]
 
 
 def feed_forward(x: torch.Tensor, w: Weights, prefix: str) -> torch.Tensor:
-    inner = gelu_erf(x @ w[f"{prefix}.w_1.weight"].t() + w[f"{prefix}.w_1.bias"])
+    inner = _drop(gelu_erf(x @ w[f"{prefix}.w_1.weight"].t() + w[f"{prefix}.w_1.bias"]))
     return inner @ w[f"{prefix}.w_2.weight"].t() + w[f"{prefix}.w_2.bias"]
 
 
@@ -142,10 +151,10 @@ def transformer_block(x: torch.Tensor, w: Weights, prefix: str, heads: int,
                       mask: Optional[torch.Tensor]) -> torch.Tensor:
     """pre-LN residual sublayers, NO final LayerNorm (transformer_layers.py:251-258)."""
     y = layer_norm(x, w[f"{prefix}.input_sublayer.norm.weight"], w[f"{prefix}.input_sublayer.norm.bias"])
-    x = x + multi_head_attention(y, w, f"{prefix}.attention", heads, mask)
+    x = x + _drop(multi_head_attention(y, w, f"{prefix}.attention", heads, mask))
     y = layer_norm(x, w[f"{prefix}.output_sublayer.norm.weight"], w[f"{prefix}.output_sublayer.norm.bias"])
-    x = x + feed_forward(y, w, f"{prefix}.feed_forward")
-    return x
+    x = x + _drop(feed_forward(y, w, f"{prefix}.feed_forward"))
+    return _drop(x)
 
 
 def transformer_encoder(x: torch.Tensor, w: Weights, heads: int, layers: int,
@@ -264,8 +273,8 @@ def kebert4rec_hidden(w: Weights, seq: torch.Tensor, attrs: Dict[str, torch.Tens
     ctx = attribute_sum(attrs, w, _ATTR, prefusion)
     if ctx is not None:
         x = x + ctx
-    x = layer_norm(x, w["_sequence_embedding_layer.norm_embedding.weight"],
-                   w["_sequence_embedding_layer.norm_embedding.bias"])
+    x = _drop(layer_norm(x, w["_sequence_embedding_layer.norm_embedding.weight"],
+                         w["_sequence_embedding_layer.norm_embedding.bias"]))
     x = transformer_encoder(x, w, heads, layers, attention_mask(pm, seq.shape[0], seq.shape[1], True))
     if postfusion:
         ctx = attribute_sum(attrs, w, "_sequence_representation_modifier_layer.postfusion_attribute_embeddings",
@@ -289,8 +298,8 @@ def sasrec_hidden(w: Weights, seq: torch.Tensor, attrs: Dict[str, torch.Tensor],
     ctx = attribute_sum(attrs, w, _ATTR, prefusion)
     if ctx is not None:
         x = x + ctx
-    x = layer_norm(x, w["_sequence_embedding_layer.norm_embedding.weight"],
-                   w["_sequence_embedding_layer.norm_embedding.bias"])
+    x = _drop(layer_norm(x, w["_sequence_embedding_layer.norm_embedding.weight"],
+                         w["_sequence_embedding_layer.norm_embedding.bias"]))
     x = transformer_encoder(x, w, heads, layers, attention_mask(pm, seq.shape[0], seq.shape[1], False))
     if postfusion:
         ctx = attribute_sum(attrs, w, "_sequence_representation_modifier_layer.postfusion_attribute_embeddings",

@@ -6,7 +6,7 @@ There is NO fallback: if the library is missing or a call fails, a RuntimeError 
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint32, \
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint32, \
     c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -78,7 +78,7 @@ _PROTOTYPES = {
     "asme_b200_posneg_bce_bwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, c_float, P, P, P, P]),
     "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P]),
     "asme_b200_scatter_rows": (c_int, [P, P, c_int, c_int, P, P]),
-    "asme_b200_adam_step": (c_int, [P, P, P, P, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "asme_b200_adam_step": (c_int, [P, P, P, P, c_longlong, c_double, c_double, c_double, c_double, c_double, c_int, P]),
     "asme_b200_fill": (c_int, [P, c_longlong, c_float, P]),
 }
 

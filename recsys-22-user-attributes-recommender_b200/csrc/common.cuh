@@ -49,10 +49,18 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 // reduction over an aligned sub-group of LANES lanes (LANES power of two <= 32)
+// The member mask names ONLY the group's lanes: groups of one warp may run different trip counts of a
+// grid-stride loop, so a full-warp mask would wait for lanes that already left the loop (deadlock).
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask() {
+    if (LANES >= 32) return 0xffffffffu;
+    return ((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES);
+}
 template <int LANES>
 __device__ __forceinline__ float group_sum(float v) {
+    const unsigned mask = group_mask<LANES>();
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
 

@@ -579,27 +579,28 @@ extern "C" int asme_b200_scatter_rows(const float* rows, const int64_t* row_inde
 // fused Adam over the flat arena
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr_over_bc1, float beta1, float beta2, float eps, float wd,
-                            float inv_sqrt_bc2) {
+                            long long n, float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps,
+                            float wd, float inv_sqrt_bc2) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float gi = g[i];
     const float pi = p[i];
     if (wd != 0.f) gi += wd * pi;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float mi = beta1 * m[i] + omb1 * gi;          // omb = 1 - beta evaluated in double on the host, as torch does
+    const float vi = beta2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     p[i] = pi - lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
 }
-extern "C" int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
-                                   float beta2, float eps, float weight_decay, int step, asme_stream_t stream) {
+extern "C" int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
+                                   double beta2, double eps, double weight_decay, int step, asme_stream_t stream) {
     ASME_REQUIRE(step >= 1, "adam: step must be >= 1");
     if (n == 0) return ASME_OK;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
-                                                                    weight_decay, (float)(1.0 / sqrt(bc2)));
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    adam_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, m, v, n, (float)(lr / bc1), (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+        (float)eps, (float)weight_decay, (float)(1.0 / sqrt(bc2)));
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
