@@ -42,6 +42,8 @@ typedef struct CUstream_st* asme_stream_t; /* == cudaStream_t */
 
 const char* asme_b200_last_error(void);
 int asme_b200_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (diagnostics / bench.py "gpu_launches") */
+long long asme_b200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1-K4  fused embedding gather-and-sum (+LayerNorm +dropout)

@@ -42,6 +42,7 @@ _PROTOTYPES = {
     # name: (restype, argtypes)
     "asme_b200_last_error": (c_char_p, []),
     "asme_b200_abi_version": (c_int, []),
+    "asme_b200_launch_count": (c_longlong, []),
     "asme_b200_embed_fwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P]),
     "asme_b200_embed_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_embed_bwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
@@ -83,7 +84,9 @@ _PROTOTYPES = {
 }
 
 _lib = None
-launch_count = 0   # number of C-ABI kernel-launching calls made (bench.py reports it)
+launch_count = 0   # number of C-ABI calls made; kernel launches are counted by the library itself
+timing = None      # when set to a list, every call is bracketed by CUDA events: (name, note, start_event, end_event)
+note = ""          # shape annotation of the next call (set by ops.py, consumed by the timing hook)
 
 
 def header_symbols():
@@ -121,10 +124,23 @@ def check(rc, what=""):
 
 def call(name, *args):
     """Call an int-returning entry point and raise on error."""
-    global launch_count
+    global launch_count, note
     fn = getattr(load(), name)
     launch_count += 1
+    if timing is None:
+        check(fn(*args), name)
+        return
+    this_note, note = note, ""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()          # torch's current stream == the stream the kernels are launched on
     check(fn(*args), name)
+    e1.record()
+    timing.append((name, this_note, e0, e1))
+
+
+def kernel_launches() -> int:
+    return int(load().asme_b200_launch_count())
 
 
 def query(name, *args):

@@ -110,6 +110,8 @@ def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False):
     out = torch.empty(T, H, dtype=torch.float32, device=spec.item_table.device)
     stats = torch.empty(4, T, dtype=torch.float32, device=out.device) if save_stats else None
     d = spec.desc()
+    if _lib.timing is not None:
+        _lib.note = f"T={T},H={H},tables={1 + (spec.pos_table is not None) + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)},ids={1 + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)}"
     _lib.call("asme_b200_embed_fwd", ctypes.byref(d), T, S, H, _p(out), _p(stats), _stream())
     return out, stats
 
@@ -125,6 +127,8 @@ def embed_bwd(spec: EmbedSpec, B: int, S: int, d_out: torch.Tensor, stats: Optio
     ws_bytes = _lib.query("asme_b200_embed_bwd_workspace_bytes", T, H)
     ws = workspace(ws_bytes, d_out.device)
     d = spec.desc()
+    if _lib.timing is not None:
+        _lib.note = f"T={T},H={H},tables={1 + (spec.pos_table is not None) + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)},ids={1 + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)}"
     _lib.call("asme_b200_embed_bwd", ctypes.byref(d), T, S, H, _p(d_out), _p(stats), _p(d_item), _p(d_attr), _p(dln),
               _p(ws), ws.numel(), _stream())
     return d_item, d_attr
@@ -138,6 +142,8 @@ def embgrad_sorted_reduce(ids: torch.Tensor, d_rows: torch.Tensor, d_table: torc
     T, H = ids.numel(), d_table.shape[1]
     ws_bytes = _lib.query("asme_b200_embgrad_workspace_bytes", T, H)
     ws = workspace(ws_bytes, d_rows.device)
+    if _lib.timing is not None:
+        _lib.note = f"T={T},H={H}"
     _lib.call("asme_b200_embgrad_sorted_reduce", _p(ids), T, _p(d_rows), int(row_divisor), H, _p(d_table), d_table.shape[0], skip_id,
               _p(ws), ws.numel(), _stream())
 
@@ -162,6 +168,8 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save
     M, H = x.shape
     y = torch.empty_like(x)
     stats = torch.empty(2, M, dtype=torch.float32, device=x.device) if save_stats else None
+    if _lib.timing is not None:
+        _lib.note = f"M={M},H={H}"
     _lib.call("asme_b200_layernorm_fwd", _p(x), _p(gamma), _p(beta), M, H, _p(y), _p(stats), _stream())
     return y, stats
 
@@ -173,6 +181,8 @@ def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[t
     dx = torch.empty_like(x)
     ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
     ws = workspace(ws_bytes, x.device)
+    if _lib.timing is not None:
+        _lib.note = f"M={M},H={H},res={int(d_residual is not None)}"
     _lib.call("asme_b200_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
               _p(ws), ws.numel(), _stream())
     return dx
@@ -197,6 +207,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_b: bool = True, bias=None, act:
     epi.mul_gelu_grad_of = None if mul_gelu_grad_of is None else mul_gelu_grad_of.data_ptr()
     epi.p_drop, epi.seed, epi.site = float(p_drop), int(seed), int(site)
     epi.residual = None if residual is None else residual.data_ptr()
+    if _lib.timing is not None:
+        _lib.note = f"M={M},N={N},K={K},tb={int(trans_b)},res={int(residual is not None)},pre={int(pre is not None)},aux={int(mul_gelu_grad_of is not None)}"
     _lib.call("asme_b200_gemm", _p(a), _p(b), _p(c), M, N, K, 1 if trans_b else 0, ctypes.byref(epi), _stream())
     return (c, pre) if pre_act_out else c
 
@@ -208,6 +220,8 @@ def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optio
     K = x.shape[1]
     ws_bytes = _lib.query("asme_b200_gemm_wgrad_workspace_bytes", M, N, K)
     ws = workspace(ws_bytes, x.device)
+    if _lib.timing is not None:
+        _lib.note = f"M={M},N={N},K={K}"
     _lib.call("asme_b200_gemm_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws),
               ws.numel(), _stream())
 
@@ -215,6 +229,8 @@ def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optio
 def dropout(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
     x = _f32(x)
     y = torch.empty_like(x)
+    if _lib.timing is not None:
+        _lib.note = f"n={x.numel()}"
     _lib.call("asme_b200_dropout", _p(x), _p(y), x.numel(), float(p), int(seed), int(site), _stream())
     return y
 
@@ -222,6 +238,8 @@ def dropout(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
 def gelu_backward(dy: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     dy, z = _f32(dy), _f32(z)
     dz = torch.empty_like(dy)
+    if _lib.timing is not None:
+        _lib.note = f"n={dy.numel()}"
     _lib.call("asme_b200_gelu_bwd", _p(dy), _p(z), _p(dz), dy.numel(), _stream())
     return dz
 
@@ -244,6 +262,8 @@ def attn_fwd(qkv: torch.Tensor, key_valid: Optional[torch.Tensor], B: int, S: in
     kv = _u8(key_valid)
     ctx = torch.empty(B * S, H, dtype=torch.float32, device=qkv.device)
     stats = torch.empty(2, B * heads * S, dtype=torch.float32, device=qkv.device) if save_stats else None
+    if _lib.timing is not None:
+        _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
     _lib.call("asme_b200_attn_fwd", _p(qkv), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed),
               int(site), _p(ctx), _p(stats), _stream())
     return ctx, stats
@@ -257,6 +277,8 @@ def attn_bwd(qkv, key_valid, B, S, heads, causal, ctx, d_ctx, stats, p_drop=0.0,
     d_qkv = torch.empty_like(qkv)
     ws_bytes = _lib.query("asme_b200_attn_bwd_workspace_bytes", B, S, heads)
     ws = workspace(ws_bytes, qkv.device)
+    if _lib.timing is not None:
+        _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
     _lib.call("asme_b200_attn_bwd", _p(qkv), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed),
               int(site), _p(ctx), _p(d_ctx), _p(stats), _p(d_qkv), _p(ws), ws.numel(), _stream())
     return d_qkv
@@ -287,6 +309,8 @@ def score_topk_rank(h, w, bias, k: int, target=None, target_score=None, v0: int 
     ws_bytes = _lib.query("asme_b200_score_topk_workspace_bytes", R, Vloc, k)
     ws = workspace(ws_bytes, dev)
     tgt = None if target is None else _i64(target)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={H},k={k}"
     _lib.call("asme_b200_score_topk_rank", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(tgt), _p(target_score), k, _p(val),
               _p(idx), _p(ng), _p(nt), _p(ws), ws.numel(), _stream())
     return val, idx, ng, nt
@@ -330,6 +354,8 @@ def score_ce_partial(h, w, bias, target, v0: int = 0):
     tl = torch.empty_like(rmax)
     ws_bytes = _lib.query("asme_b200_score_ce_workspace_bytes", R, Vloc)
     ws = workspace(ws_bytes, dev)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={H}"
     _lib.call("asme_b200_score_ce_partial", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
               _p(tl), _p(ws), ws.numel(), _stream())
     return rmax, rsum, tl
@@ -349,6 +375,8 @@ def score_ce_bwd(h, w, bias, target, lse, scale: float, dW: Optional[torch.Tenso
     dh = torch.empty_like(h) if need_dh else None
     ws_bytes = _lib.query("asme_b200_score_ce_bwd_workspace_bytes", R, H, Vloc)
     ws = workspace(ws_bytes, h.device)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={H}"
     _lib.call("asme_b200_score_ce_bwd", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
               _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _stream())
     return dh
@@ -389,6 +417,8 @@ def scatter_rows(rows: torch.Tensor, row_index: torch.Tensor, out: torch.Tensor)
 
 
 def adam_step(param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    if _lib.timing is not None:
+        _lib.note = f"n={param.numel()}"
     _lib.call("asme_b200_adam_step", _p(param), _p(grad), _p(m), _p(v), param.numel(), float(lr), float(beta1),
               float(beta2), float(eps), float(weight_decay), int(step), _stream())
 

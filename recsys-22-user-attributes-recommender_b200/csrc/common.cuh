@@ -29,7 +29,12 @@ void asme_set_error(const char* fmt, ...);
         }                                                                                    \
     } while (0)
 
-#define ASME_LAUNCH_OK() ASME_CUDA_OK(cudaGetLastError())
+void asme_count_launch();   // every kernel launch of this library is counted (bench.py reports it)
+#define ASME_LAUNCH_OK()                  \
+    do {                                  \
+        asme_count_launch();              \
+        ASME_CUDA_OK(cudaGetLastError()); \
+    } while (0)
 
 __host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

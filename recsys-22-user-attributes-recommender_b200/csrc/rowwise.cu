@@ -21,6 +21,10 @@ void asme_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 extern "C" const char* asme_b200_last_error(void) { return g_last_error; }
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void asme_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long asme_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int asme_b200_abi_version(void) { return 1; }
 
 #define LN_EPS 1e-5f
