@@ -222,6 +222,33 @@ int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const float* W, con
                            void* ws, size_t ws_bytes, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 + TMEM + TMA) scoring path, bf16 operands / fp32 accumulation.
+ * Same reference call sites as the fp32 entry points above (layers.py:105-143 + metrics/common.py:18-27 /
+ * masked_training_module.py:107-111); the (R x V) logits exist only as 128x256 accumulator tiles in tensor memory.
+ * Operands are prepared with asme_b200_cast_bf16: Hb (R,Kp) and Wb (Vloc,Kp) bf16 row-major, Kp = hidden size
+ * zero-padded to a multiple of 64 (<= 256).
+ * ------------------------------------------------------------------------------------------ */
+/* y[r, 0..ld_out) = bf16(x[r, 0..cols)) zero padded; ld_out % 4 == 0 */
+int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, asme_stream_t stream);
+/* One sweep over the catalog slice [v0, v0+Vloc):
+ *   k > 0                      -> per row top-k (score desc, id asc): topk_val / topk_idx (R,k)
+ *   target_score_out != NULL   -> score of the row's target column exactly as this kernel computes it (written by the
+ *                                 shard that owns the column; caller zero-fills, shards all-reduce(SUM))
+ *   target_score_in != NULL    -> n_greater = #{s_j > s_t}, n_tie_lower = #{j < t : s_j == s_t}   (exact full rank)
+ * When only @k metrics are needed the rank is the target's position in the top-k list and no count pass is run. */
+size_t asme_b200_tc_score_topk_workspace_bytes(int R, int Kp, int Vloc, int k);
+int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                            const int64_t* target, const float* target_score_in, int k, float* topk_val,
+                            int32_t* topk_idx, float* target_score_out, int32_t* n_greater, int32_t* n_tie_lower,
+                            void* ws, size_t ws_bytes, asme_stream_t stream);
+/* cross-entropy partials over the slice: row_max, row_sumexp (natural units, combine across shards as for the fp32
+ * entry point) and target_logit (owner shard writes; caller zero-fills) */
+size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc);
+int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                                  const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
+                                  void* ws, size_t ws_bytes, asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K13+K17  SASRec positive/negative dot products fused with the BCE loss
  * replaces: SASRecProjectionComponent.forward train branch (models/sasrec/components.py:35-44) and
  *           sas_rec_binary_cross_entropy (losses/sasrec/sas_rec_losses.py:47-75).

@@ -316,6 +316,74 @@ def score_topk_rank(h, w, bias, k: int, target=None, target_score=None, v0: int 
     return val, idx, ng, nt
 
 
+# ------------------------------------------------------------------------------------------------
+# catalog scoring on the tensor cores (tcgen05 / TMEM / TMA): bf16 operands, fp32 accumulation
+# ------------------------------------------------------------------------------------------------
+def padded_k(H: int) -> int:
+    """hidden size zero-padded to the 64-element (128-byte) swizzle chunk the TMA / UMMA path works in"""
+    return (H + 63) // 64 * 64
+
+
+def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
+    """(rows, cols) fp32 -> (rows, ld_out) bf16, round-to-nearest-even, zero padded"""
+    x = _f32(x)
+    rows, cols = x.shape
+    ld_out = padded_k(cols) if ld_out is None else ld_out
+    y = torch.empty(rows, ld_out, dtype=torch.bfloat16, device=x.device)
+    if _lib.timing is not None:
+        _lib.note = f"rows={rows},cols={cols},ld={ld_out}"
+    _lib.call("asme_b200_cast_bf16", _p(x), _p(y), rows, cols, cols, ld_out, _stream())
+    return y
+
+
+def _bf16(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous():
+        raise RuntimeError(f"asme_b200: {name} must be a contiguous CUDA bfloat16 tensor")
+    return t
+
+
+def tc_score_topk(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, target=None, target_score_in=None, v0: int = 0,
+                  capture_target: bool = True):
+    """hb (R,Kp) / wb (Vloc,Kp) bf16.  returns dict(topk_val, topk_idx, target_score, n_greater, n_tie_lower)
+    (entries are None when not requested)."""
+    hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
+    R, Kp = hb.shape
+    Vloc = wb.shape[0]
+    dev = hb.device
+    val = torch.empty(R, k, dtype=torch.float32, device=dev) if k > 0 else None
+    idx = torch.empty(R, k, dtype=torch.int32, device=dev) if k > 0 else None
+    tgt = None if target is None else _i64(target)
+    ts_out = torch.zeros(R, dtype=torch.float32, device=dev) if (tgt is not None and capture_target) else None
+    count = target_score_in is not None
+    ng = torch.zeros(R, dtype=torch.int32, device=dev) if count else None
+    nt = torch.zeros(R, dtype=torch.int32, device=dev) if count else None
+    ws_bytes = _lib.query("asme_b200_tc_score_topk_workspace_bytes", R, Kp, Vloc, k)
+    ws = workspace(ws_bytes, dev)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={Kp},k={k},count={int(count)}"
+    _lib.call("asme_b200_tc_score_topk", _p(hb), R, Kp, _p(wb), _p(bias), v0, Vloc, _p(tgt), _p(target_score_in), k, _p(val),
+              _p(idx), _p(ts_out), _p(ng), _p(nt), _p(ws), ws.numel(), _stream())
+    return dict(topk_val=val, topk_idx=idx, target_score=ts_out, n_greater=ng, n_tie_lower=nt)
+
+
+def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: int = 0):
+    """per row (max, sumexp, target logit) over the catalog slice [v0, v0+Vloc), tensor-core path"""
+    hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
+    R, Kp = hb.shape
+    Vloc = wb.shape[0]
+    dev = hb.device
+    rmax = torch.empty(R, dtype=torch.float32, device=dev)
+    rsum = torch.empty_like(rmax)
+    tl = torch.zeros_like(rmax)
+    ws_bytes = _lib.query("asme_b200_tc_score_ce_workspace_bytes", R, Kp, Vloc)
+    ws = workspace(ws_bytes, dev)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={Kp}"
+    _lib.call("asme_b200_tc_score_ce_partial", _p(hb), R, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
+              _p(tl), _p(ws), ws.numel(), _stream())
+    return rmax, rsum, tl
+
+
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):
     """vals/idx: (G,R,k) partial lists -> merged (R,k)"""
     vals, idx = _f32(vals), idx.contiguous()

@@ -1,0 +1,673 @@
+// Full-catalog scoring on the 5th-generation tensor cores (tcgen05 + TMEM, operands staged by TMA), fused with
+//   * top-k (score desc, id asc) + capture of the target's score          (evaluation, K12+K15+K18-K20)
+//   * exact rank counts  #{s_j > s_t}, #{j < t : s_j == s_t}              (rank / full-MRR metrics)
+//   * online log-softmax partials (max, sum-exp, target logit)            (cross-entropy forward, K12+K16)
+// so the (rows x V) logits only ever exist as 128 x 256 fp32 accumulator tiles in tensor memory.
+//
+// replaces: ItemEmbeddingProjectionLayer / LinearProjectionLayer (models/common/layers/layers.py:105-143) followed by
+//           AllItemsSampler + per-metric argsort (metrics/container/metrics_sampler.py:45-71, metrics/common.py:18-27)
+//           or nn.CrossEntropyLoss (modules/masked_training_module.py:107-111).
+//
+// Kernel shape (one CTA per SM, 384 threads, cta_group::1):
+//   warp 0      TMA producer: A = 128 hidden rows (loaded once, stationary), B = 256-item table tiles, ring of stages
+//   warp 1      MMA issuer  : per tile kch*4 tcgen05.mma (M=128, N=256, K=16), accumulators double-buffered in TMEM
+//   warp 2      TMEM allocator (512 columns = 2 accumulator stages)
+//   warps 4-11  epilogue: two warpgroups, each owning 128 of the tile's 256 columns; thread = one row (TMEM lane)
+// CTA (m_tile, split) sweeps the item tiles [split*tps, (split+1)*tps); per-(split, warpgroup) partial results are
+// merged by a second tiny kernel.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <limits.h>
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------------------
+// host: tensor-map encoder through the runtime's driver entry point
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+int asme_tc_make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ASME_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            asme_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return ASME_ERR_CUDA;
+        }
+        g_encode = (PFN_encodeTiled)fn;
+    }
+    ASME_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "tensor map: base / row stride must be 16-byte aligned");
+    ASME_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box_rows=%d", box_rows);
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)CHUNK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        asme_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box_rows=%d)", (int)r, rows, cols,
+                       ld, box_rows);
+        return ASME_ERR_CUDA;
+    }
+    return ASME_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 -> bf16 operand preparation (round to nearest even), zero padded to ld_out columns
+// ------------------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int cols, int ld_in,
+                                 int ld_out) {
+    const int per_row = ld_out / 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * per_row) return;
+    const long long r = i / per_row;
+    const int c = (int)(i % per_row) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = x + r * ld_in + c;
+    if (c + 3 < cols && (ld_in % 4) == 0) v = ldg4(src);
+    else {
+        if (c + 0 < cols) v.x = src[0];
+        if (c + 1 < cols) v.y = src[1];
+        if (c + 2 < cols) v.z = src[2];
+        if (c + 3 < cols) v.w = src[3];
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y + r * ld_out + c) = o;
+}
+
+extern "C" int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, asme_stream_t stream) {
+    ASME_REQUIRE(x && y, "cast_bf16: null argument");
+    ASME_REQUIRE(cols >= 1 && ld_in >= cols && ld_out >= cols && ld_out % 4 == 0, "cast_bf16: cols=%d ld_in=%d ld_out=%d", cols, ld_in,
+                 ld_out);
+    if (rows == 0) return ASME_OK;
+    const long long n = rows * (ld_out / 4);
+    cast_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, rows, cols, ld_in, ld_out);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the scoring kernel
+// ------------------------------------------------------------------------------------------------------------
+#define BM 128
+#define BN 256
+#define A_CHUNK_BYTES (BM * CHUNK_ROW_BYTES)   // 16 KB
+#define B_CHUNK_BYTES (BN * CHUNK_ROW_BYTES)   // 32 KB
+#define TC_THREADS 384
+#define EPI_WARP0 4
+#define MAX_STAGES 6
+#define L2E 1.4426950408889634f
+
+enum { EPI_TOPK = 0, EPI_CE = 1 };
+
+struct ScoreTcArgs {
+    int R, Vloc, v0, k, kch, stages;
+    int n_tiles, tiles_per_split;
+    int tile_lo, tile_hi;        // this launch sweeps tiles [split*tps + tile_lo, min(n_tiles, split*tps + tile_hi)) of every split
+    int part0;                   // first partial-result slot written by this launch
+    const float* thr_init;       // (R, thr_stride) or NULL: a lower bound of each row's k-th best score (from a sample sweep)
+    int thr_stride, thr_col;
+    const float* bias;
+    const int64_t* target;
+    const float* target_score;   // count mode: the pivot
+    float* pv;                   // top-k partial values  [parts][R][k]      | CE: partial row max    [parts][R]
+    int* pi;                     // top-k partial ids     [parts][R][k]
+    int* pg;                     // partial #greater      [parts][R]
+    int* pt;                     // partial #tie-lower    [parts][R]
+    float* ps;                   // CE: partial sum-exp   [parts][R]
+    float* captured;             // [R]: score of the target column as computed by this kernel (owner writes)
+};
+
+struct __align__(8) ScoreTcBarriers {
+    uint64_t a_full;
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+};
+
+// Sorted insertion into this thread's REGISTER-resident list (descending; equal scores keep stream order, and a thread
+// sees its columns in ascending id order, so ties resolve to the lowest item id).  Branch-free and fully unrolled: an
+// insertion is ~6 instructions per entry with no memory latency (the first version kept the lists in shared memory and
+// was latency-bound: ~800 cycles per insertion).
+template <int KC>
+__device__ __forceinline__ void reg_insert(float (&lv)[KC], int (&li)[KC], float x, int id) {
+#pragma unroll
+    for (int p = KC - 1; p > 0; --p) {
+        const bool shift = lv[p - 1] < x;            // the entry above moves down into slot p
+        const bool here = !shift && (lv[p] < x);     // x lands in slot p
+        lv[p] = shift ? lv[p - 1] : (here ? x : lv[p]);
+        li[p] = shift ? li[p - 1] : (here ? id : li[p]);
+    }
+    const bool here0 = lv[0] < x;
+    lv[0] = here0 ? x : lv[0];
+    li[0] = here0 ? id : li[0];
+}
+
+// v[c] for a run-time c in 0..31 without dynamic register indexing: 5-level select tree (31 SEL)
+__device__ __forceinline__ float sel32(const float (&v)[32], int c) {
+    float a[16], b[8], d[4], e[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (c & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (c & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = (c & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) e[i] = (c & 8) ? d[2 * i + 1] : d[2 * i];
+    return (c & 16) ? e[1] : e[0];
+}
+
+__device__ __forceinline__ float max8(const float* v) {
+    return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+}
+
+// KC = capacity of the per-thread top-k list (0: no top-k); the first a.k (<= KC) entries are reported
+template <int EPI, int KC, bool COUNT>
+__global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, const ScoreTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kch = a.kch, stages = a.stages;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + (size_t)kch * A_CHUNK_BYTES;
+    // `stages` ring slots of ONE 64-wide K chunk each
+    ScoreTcBarriers* bars = reinterpret_cast<ScoreTcBarriers*>(sB + (size_t)stages * B_CHUNK_BYTES);
+    constexpr bool TOPK = KC > 0;
+    constexpr int KL = KC > 0 ? KC : 1;
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m0 = blockIdx.x * BM;
+    const int split = blockIdx.y;
+    const int t0 = min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
+    const int t1 = min(a.n_tiles, split * a.tiles_per_split + a.tile_hi);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(&bars->a_full, 1);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->tfull[s], 1);
+            mbar_init(&bars->tempty[s], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars->a_full, (uint32_t)kch * A_CHUNK_BYTES);
+            for (int c = 0; c < kch; ++c) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
+            int j = 0;                                    // chunk counter: ring slot = j % stages
+            for (int t = t0; t < t1; ++t) {
+                for (int c = 0; c < kch; ++c, ++j) {
+                    const int s = j % stages;
+                    const uint32_t ph = (uint32_t)(j / stages) & 1u;
+                    mbar_wait(&bars->empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&bars->full[s], (uint32_t)B_CHUNK_BYTES);
+                    tma_load_2d(sB + (size_t)s * B_CHUNK_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16_f32(BM, BN);
+            mbar_wait(&bars->a_full, 0);
+            tc_fence_after();
+            int i = 0, j = 0;
+            for (int t = t0; t < t1; ++t, ++i) {
+                const int as = i & 1;
+                const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(&bars->tempty[as], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
+                for (int c = 0; c < kch; ++c, ++j) {
+                    const int s = j % stages;
+                    const uint32_t ph = (uint32_t)(j / stages) & 1u;
+                    mbar_wait(&bars->full[s], ph);
+                    tc_fence_after();
+                    const uint64_t ad = smem_desc_sw128(smem_u32(sA + (size_t)c * A_CHUNK_BYTES));
+                    const uint64_t bd = smem_desc_sw128(smem_u32(sB + (size_t)s * B_CHUNK_BYTES));
+#pragma unroll
+                    for (int k4 = 0; k4 < CHUNK_K / UMMA_K; ++k4)
+                        umma_bf16(d_tmem, smem_desc_advance(ad, k4 * UMMA_K * 2), smem_desc_advance(bd, k4 * UMMA_K * 2), idesc,
+                                  (uint32_t)((c | k4) != 0));
+                    umma_commit(&bars->empty[s]);     // the slot may be refilled once these MMAs have read it
+                }
+                umma_commit(&bars->tfull[as]);        // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================================== epilogue =====================================
+        const int wg = (warp - EPI_WARP0) / 4;       // which 128-column half of the tile
+        const int q = warp % 4;                      // TMEM lane quarter this warp may access
+        const int tid = q * 32 + lane;               // row within the M tile == TMEM lane
+        const int row = m0 + tid;
+        const bool row_ok = row < a.R;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+        long long tgl_ll = -1;
+        if (a.target && row_ok) tgl_ll = a.target[row] - (long long)a.v0;
+        // local target column; targets owned by a lower / higher shard become -1 / INT_MAX (ties: "id < target")
+        const int tgl = tgl_ll < 0 ? -1 : (tgl_ll >= (long long)a.Vloc ? INT_MAX : (int)tgl_ll);
+
+        // --- per-thread state ---
+        float lv[KL];
+        int li[KL];
+#pragma unroll
+        for (int p = 0; p < KL; ++p) {
+            lv[p] = -INFINITY;
+            li[p] = INT_MAX;
+        }
+        // threshold: nothing at or below it can enter the list.  thr0 comes from a sample sweep (strictly below the
+        // sample's k-th best, so ties with it still pass the strict compare); once the own list is full its tail takes over.
+        float thr0 = -INFINITY;
+        if (TOPK && a.thr_init && row_ok) {
+            const float t_row = a.thr_init[(size_t)row * a.thr_stride + a.thr_col];
+            thr0 = t_row == -INFINITY ? t_row : nextafterf(t_row, -INFINITY);
+        }
+        float thr = thr0;
+        int cg = 0, ct = 0;
+        float st = INFINITY;
+        if (EPI == EPI_TOPK && COUNT && row_ok) st = a.target_score[row];
+        float run_m = -INFINITY, run_s = 0.f;     // CE: running max (in log2 units) and sum of exp2
+
+        int i = 0;
+        for (int t = t0; t < t1; ++t, ++i) {
+            const int as = i & 1;
+            const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(&bars->tfull[as], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int col0 = t * BN + wg * 128 + ch * 32;     // local column of v[0]
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * 128 + ch * 32), v);
+                tmem_ld_wait();
+                if (ch == 3) {   // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                }
+                if (col0 >= a.Vloc) continue;                   // warp-uniform
+                const bool full_valid = col0 + 32 <= a.Vloc;
+                if (a.bias) {
+                    if (full_valid) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + c));
+                            v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (col0 + c < a.Vloc) v[c] += __ldg(a.bias + col0 + c);
+                    }
+                }
+                if (!full_valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (col0 + c >= a.Vloc) v[c] = -INFINITY;
+                }
+                // score of the target column exactly as this kernel computes it
+                if (a.captured && tgl >= col0 && tgl < col0 + 32) {
+                    float x = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (col0 + c == tgl) x = v[c];
+                    a.captured[row] = x;
+                }
+                if (EPI == EPI_CE) {
+                    float m8[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m8[j] = max8(v + 8 * j);
+                    const float mc = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) * L2E;
+                    const float m_new = fmaxf(run_m, mc);
+                    float s = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) s += exp2f(fmaf(v[c], L2E, -m_new));
+                    run_s = run_s * exp2f(run_m - m_new) + s;
+                    run_m = m_new;
+                } else {
+                    if (COUNT) {
+                        bool any_eq = false;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            cg += v[c] > st;
+                            any_eq |= v[c] == st;
+                        }
+                        if (any_eq) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) ct += (v[c] == st) && (col0 + c < tgl);
+                        }
+                    }
+                    if (TOPK) {
+                        float m8[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m8[j] = max8(v + 8 * j);
+                        const float mc = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                        if (mc > thr) {      // rare once the threshold has converged: gather the candidates, ONE insertion site
+                            uint32_t cand = 0;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) cand |= (v[c] > thr) ? (1u << c) : 0u;
+                            while (cand) {
+                                const int c = __ffs(cand) - 1;
+                                cand &= cand - 1;
+                                const float x = sel32(v, c);
+                                if (x > thr) {
+                                    reg_insert<KL>(lv, li, x, a.v0 + col0 + c);
+                                    thr = fmaxf(thr0, lv[KL - 1]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // --- write this (split, warpgroup)'s partial results ---
+        if (row_ok) {
+            const size_t part = (size_t)a.part0 + (size_t)split * 2 + wg;
+            const size_t o = part * a.R + row;
+            if (EPI == EPI_CE) {
+                a.pv[o] = run_m;      // log2 units
+                a.ps[o] = run_s;
+            } else {
+                if (TOPK) {
+#pragma unroll
+                    for (int p = 0; p < KL; ++p) {
+                        if (p < a.k) {
+                            a.pv[o * a.k + p] = lv[p];
+                            a.pi[o * a.k + p] = li[p];
+                        }
+                    }
+                }
+                if (COUNT) {
+                    a.pg[o] = cg;
+                    a.pt[o] = ct;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// merge of the partial results: one warp per row
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tc_better(float v, int id, float v2, int id2) { return v > v2 || (v == v2 && id < id2); }
+
+__global__ void tc_topk_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, const int* __restrict__ pg,
+                                     const int* __restrict__ pt, int parts, int R, int k, float* __restrict__ out_v,
+                                     int32_t* __restrict__ out_i, int32_t* __restrict__ out_g, int32_t* __restrict__ out_t) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= R) return;
+    if (pv) {
+        // lane-distributed sorted list: lane i holds the i-th best
+        float lv = -INFINITY;
+        int li = INT_MAX;
+        for (int p = 0; p < parts; ++p) {
+            const size_t o = ((size_t)p * R + row) * k;
+            float v = -INFINITY;
+            int id = INT_MAX;
+            if (lane < k) { v = pv[o + lane]; id = pi[o + lane]; }
+            // candidates of one part arrive sorted; offer them one by one while they can still enter the list
+            for (int j = 0; j < k; ++j) {
+                const float cv = __shfl_sync(0xffffffffu, v, j);
+                const int ci = __shfl_sync(0xffffffffu, id, j);
+                if (ci == INT_MAX) break;                                   // warp-uniform: rest of this part is empty
+                const float tail_v = __shfl_sync(0xffffffffu, lv, k - 1);
+                const int tail_i = __shfl_sync(0xffffffffu, li, k - 1);
+                if (!tc_better(cv, ci, tail_v, tail_i)) break;              // sorted part: nothing further can enter
+                const unsigned keep = __ballot_sync(0xffffffffu, tc_better(lv, li, cv, ci));
+                const int pos = __popc(keep);
+                const float up_v = __shfl_up_sync(0xffffffffu, lv, 1);
+                const int up_i = __shfl_up_sync(0xffffffffu, li, 1);
+                if (lane == pos) { lv = cv; li = ci; }
+                else if (lane > pos) { lv = up_v; li = up_i; }
+            }
+        }
+        if (lane < k) {
+            out_v[(size_t)row * k + lane] = lv;
+            out_i[(size_t)row * k + lane] = li == INT_MAX ? -1 : li;
+        }
+    }
+    if (pg) {
+        int g = 0, t = 0;
+        for (int p = lane; p < parts; p += 32) {
+            g += pg[(size_t)p * R + row];
+            t += pt[(size_t)p * R + row];
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, s);
+            t += __shfl_xor_sync(0xffffffffu, t, s);
+        }
+        if (lane == 0) { out_g[row] = g; out_t[row] = t; }
+    }
+}
+
+// CE partials: (max in log2 units, sum of exp2) per part -> natural-log row max and sum-exp
+__global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps, int parts, int R,
+                                   float* __restrict__ row_max, float* __restrict__ row_sumexp) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float m = -INFINITY;
+    for (int p = 0; p < parts; ++p) m = fmaxf(m, pm[(size_t)p * R + r]);
+    float s = 0.f;
+    for (int p = 0; p < parts; ++p) {
+        const float mp = pm[(size_t)p * R + r];
+        if (mp > -INFINITY) s += ps[(size_t)p * R + r] * exp2f(mp - m);
+    }
+    row_max[r] = m * 0.6931471805599453f;
+    row_sumexp[r] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------------------
+struct ScorePlan {
+    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages;
+    size_t smem;
+};
+
+static int make_plan(int R, int Kp, int Vloc, ScorePlan* p) {
+    ASME_REQUIRE(R >= 1 && Vloc >= 1, "tc score: bad shape R=%d Vloc=%d", R, Vloc);
+    ASME_REQUIRE(Kp >= 64 && Kp <= 256 && Kp % 64 == 0, "tc score: padded hidden size %d unsupported (64, 128, 192, 256)", Kp);
+    p->kch = Kp / CHUNK_K;
+    p->m_tiles = ceil_div(R, BM);
+    p->n_tiles = ceil_div(Vloc, BN);
+    int splits = ASME_NUM_SMS / p->m_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > p->n_tiles) splits = p->n_tiles;
+    p->tiles_per_split = ceil_div(p->n_tiles, splits);
+    p->splits = ceil_div(p->n_tiles, p->tiles_per_split);
+    p->parts = p->splits * 2;
+    const size_t fixed = 1024 + (size_t)p->kch * A_CHUNK_BYTES + sizeof(ScoreTcBarriers);
+    const size_t stage = (size_t)B_CHUNK_BYTES;
+    const size_t budget = 227 * 1024;
+    ASME_REQUIRE(fixed + 2 * stage <= budget, "tc score: shared memory budget exceeded (Kp=%d)", Kp);
+    int stages = (int)((budget - fixed) / stage);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p->stages = stages;
+    p->smem = fixed + stages * stage;
+    return ASME_OK;
+}
+
+// Sample sweep: with per-thread lists every row pays ~k*ln(n/k) insertions in EACH of its 2*splits lists while the local
+// thresholds converge.  For long sweeps a first launch scores 1/16 of every split's tiles, the merged k-th best of that
+// sample becomes every list's initial threshold in the second launch (a valid lower bound of the true k-th best), and
+// insertions become rare.  Results are identical either way; only the work differs.
+static int sample_tiles(const ScorePlan& p) { return p.tiles_per_split >= 32 ? p.tiles_per_split / 16 : 0; }
+
+extern "C" size_t asme_b200_tc_score_topk_workspace_bytes(int R, int Kp, int Vloc, int k) {
+    ScorePlan p;
+    if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
+    return (size_t)2 * p.parts * (R < 1 ? 1 : R) * ((size_t)k * 8 + 8);
+}
+
+template <typename K>
+static int tc_set_smem(K kernel, size_t bytes) {
+    ASME_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return ASME_OK;
+}
+
+static int launch_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreTcArgs& a, const ScorePlan& p, bool topk,
+                       bool count, cudaStream_t st) {
+    int rc = ASME_OK;
+    dim3 grid(p.m_tiles, p.splits);
+#define LAUNCH_TOPK(KC, C)                                                                  \
+    {                                                                                       \
+        rc = tc_set_smem(score_tc_kernel<EPI_TOPK, KC, C>, p.smem);                         \
+        if (rc) return rc;                                                                  \
+        score_tc_kernel<EPI_TOPK, KC, C><<<grid, TC_THREADS, p.smem, st>>>(tmA, tmB, a);    \
+    }
+#define LAUNCH_KC(KC)                         \
+    {                                         \
+        if (count) LAUNCH_TOPK(KC, true)      \
+        else LAUNCH_TOPK(KC, false)           \
+    }
+    if (!topk) LAUNCH_TOPK(0, true)
+    else if (a.k == 1) LAUNCH_KC(1)
+    else if (a.k <= 5) LAUNCH_KC(5)
+    else if (a.k <= 10) LAUNCH_KC(10)
+    else if (a.k <= 20) LAUNCH_KC(20)
+    else LAUNCH_KC(32)
+#undef LAUNCH_KC
+#undef LAUNCH_TOPK
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                                       const int64_t* target, const float* target_score_in, int k, float* topk_val,
+                                       int32_t* topk_idx, float* target_score_out, int32_t* n_greater, int32_t* n_tie_lower,
+                                       void* ws, size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(Hb && Wb, "tc_score_topk: null operand");
+    ASME_REQUIRE(k >= 0 && k <= 32, "tc_score_topk: k=%d unsupported (0..32)", k);
+    const bool topk = k > 0, count = target_score_in != nullptr;
+    ASME_REQUIRE(topk || count, "tc_score_topk: nothing to do (k = 0 and no target_score_in)");
+    ASME_REQUIRE(!topk || (topk_val && topk_idx), "tc_score_topk: top-k outputs missing");
+    ASME_REQUIRE(!count || (target && n_greater && n_tie_lower), "tc_score_topk: count mode needs target, n_greater, n_tie_lower");
+    ASME_REQUIRE(!target_score_out || target, "tc_score_topk: target_score_out needs target");
+    ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_topk: bias must be 16-byte aligned");
+    if (R == 0) return ASME_OK;
+    ScorePlan p;
+    int rc = make_plan(R, Kp, Vloc, &p);
+    if (rc) return rc;
+    const size_t need = (size_t)2 * p.parts * R * ((size_t)k * 8 + 8);
+    if (ws_bytes < need) {
+        asme_set_error("tc_score_topk: workspace too small (%zu < %zu)", ws_bytes, need);
+        return ASME_ERR_WORKSPACE;
+    }
+    CUtensorMap tmA, tmB;
+    rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
+    if (rc) return rc;
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    if (rc) return rc;
+    const int n_sample = topk ? sample_tiles(p) : 0;
+    const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
+    ScoreTcArgs a{};
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages;
+    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
+    a.bias = bias; a.target = target; a.target_score = target_score_in;
+    a.pv = (float*)ws;
+    a.pi = (int*)(a.pv + (size_t)total_parts * R * k);
+    a.pg = a.pi + (size_t)total_parts * R * k;
+    a.pt = a.pg + (size_t)total_parts * R;
+    a.ps = nullptr;
+    a.captured = target_score_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_sample > 0) {
+        // launch 1: the sample tiles of every split -> partial slots [0, parts); their merged top-k is the threshold source
+        a.tile_lo = 0; a.tile_hi = n_sample; a.part0 = 0; a.thr_init = nullptr;
+        rc = launch_topk(tmA, tmB, a, p, topk, count, st);
+        if (rc) return rc;
+        tc_topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(a.pv, a.pi, nullptr, nullptr, p.parts, R, k, topk_val, topk_idx, nullptr,
+                                                             nullptr);
+        ASME_LAUNCH_OK();
+        // launch 2: everything else, thresholds seeded with the sample's k-th best
+        a.tile_lo = n_sample; a.tile_hi = p.tiles_per_split; a.part0 = p.parts;
+        a.thr_init = topk_val; a.thr_stride = k; a.thr_col = k - 1;
+        rc = launch_topk(tmA, tmB, a, p, topk, count, st);
+        if (rc) return rc;
+    } else {
+        a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
+        rc = launch_topk(tmA, tmB, a, p, topk, count, st);
+        if (rc) return rc;
+    }
+    tc_topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(topk ? a.pv : nullptr, a.pi, count ? a.pg : nullptr, a.pt, total_parts, R, k,
+                                                         topk_val, topk_idx, n_greater, n_tie_lower);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+extern "C" size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc) {
+    ScorePlan p;
+    if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
+    return (size_t)p.parts * (R < 1 ? 1 : R) * 8;
+}
+
+extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                                             const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
+                                             void* ws, size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(Hb && Wb && target && row_max && row_sumexp && target_logit, "tc_score_ce_partial: null argument");
+    ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_ce_partial: bias must be 16-byte aligned");
+    if (R == 0) return ASME_OK;
+    ScorePlan p;
+    int rc = make_plan(R, Kp, Vloc, &p);
+    if (rc) return rc;
+    const size_t need = (size_t)p.parts * R * 8;
+    if (ws_bytes < need) {
+        asme_set_error("tc_score_ce_partial: workspace too small (%zu < %zu)", ws_bytes, need);
+        return ASME_ERR_WORKSPACE;
+    }
+    CUtensorMap tmA, tmB;
+    rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
+    if (rc) return rc;
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    if (rc) return rc;
+    ScoreTcArgs a{};
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages;
+    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
+    a.bias = bias; a.target = target; a.target_score = nullptr;
+    a.pv = (float*)ws;
+    a.ps = a.pv + (size_t)p.parts * R;
+    a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
+    a.captured = target_logit;      // the caller zero-fills: only the shard that owns the target column writes
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = tc_set_smem(score_tc_kernel<EPI_CE, 0, false>, p.smem);
+    if (rc) return rc;
+    score_tc_kernel<EPI_CE, 0, false><<<dim3(p.m_tiles, p.splits), TC_THREADS, p.smem, st>>>(tmA, tmB, a);
+    ASME_LAUNCH_OK();
+    tc_ce_merge_kernel<<<ceil_div(R, 128), 128, 0, st>>>(a.pv, a.ps, p.parts, R, row_max, row_sumexp);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
