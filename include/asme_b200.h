@@ -249,6 +249,24 @@ int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb,
                                   void* ws, size_t ws_bytes, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tensor-core dense layers (tcgen05 + TMEM + TMA), bf16 operands / fp32 accumulation.  Same call sites as asme_b200_gemm.
+ *   b_is_kn = 0: B is (N,K) row-major (nn.Linear weight), C = A B^T      forward
+ *   b_is_kn = 1: B is (K,N) row-major,                     C = A B        dX = dY W   (MN-major operand, no transpose copy)
+ * A (M,K) bf16; N in 32..256 (multiple of 32), K in {64,128,192,256}.  Epilogue, in order: + bias[n]; pre_act_bf16 = v;
+ * GELU; v *= gelu'(gelu_grad_of[m,n]); Philox dropout(seed, site, m*N+n); + residual[m,n]; out_f32 and/or out_bf16 (row
+ * stride ld_bf16).
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
+                      const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
+                      const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
+                      asme_stream_t stream);
+/* dW (N,K) fp32 (+)= dY(M,N)^T X(M,K), dbias (N) (+)= colsum(dY); dY, X bf16; token contraction split over the SMs with a
+ * deterministic second-stage reduction */
+size_t asme_b200_tc_wgrad_workspace_bytes(int M, int N, int K);
+int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, float* dbias, int accumulate,
+                       void* ws, size_t ws_bytes, asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K13+K17  SASRec positive/negative dot products fused with the BCE loss
  * replaces: SASRecProjectionComponent.forward train branch (models/sasrec/components.py:35-44) and
  *           sas_rec_binary_cross_entropy (losses/sasrec/sas_rec_losses.py:47-75).

@@ -384,6 +384,38 @@ def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: in
     return rmax, rsum, tl
 
 
+def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, act: int = 0, gelu_grad_of=None,
+            p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out_f32: bool = True, out_bf16: bool = False,
+            pre_act: bool = False, bf16_into: Optional[torch.Tensor] = None):
+    """tensor-core dense layer; a (M,K) bf16, b (N,K) [or (K,N) when b_is_kn] bf16.
+    returns dict(f32=..., bf16=..., pre=...) with the requested outputs"""
+    a, b = _bf16(a, "a"), _bf16(b, "b")
+    M, K = a.shape
+    N = b.shape[1] if b_is_kn else b.shape[0]
+    dev = a.device
+    c32 = torch.empty(M, N, dtype=torch.float32, device=dev) if out_f32 else None
+    c16 = bf16_into if bf16_into is not None else (torch.empty(M, N, dtype=torch.bfloat16, device=dev) if out_bf16 else None)
+    ld16 = c16.stride(0) if c16 is not None else 0
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if pre_act else None
+    if _lib.timing is not None:
+        _lib.note = f"M={M},N={N},K={K},kn={int(b_is_kn)},res={int(residual is not None)},f32={int(out_f32)},bf16={int(c16 is not None)},pre={int(pre_act)},aux={int(gelu_grad_of is not None)}"
+    _lib.call("asme_b200_tc_gemm", _p(a), _p(b), M, N, K, 1 if b_is_kn else 0, _p(bias), int(act), _p(gelu_grad_of), float(p_drop),
+              int(seed), int(site), _p(residual), _p(c32), _p(c16), int(ld16), _p(pre), _stream())
+    return dict(f32=c32, bf16=c16, pre=pre)
+
+
+def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True):
+    """dw (N,K) fp32 (+)= dy(M,N)^T x(M,K); dbias (N) (+)= colsum(dy); dy, x bf16"""
+    dy, x = _bf16(dy, "dy"), _bf16(x, "x")
+    M, N = dy.shape
+    K = x.shape[1]
+    ws_bytes = _lib.query("asme_b200_tc_wgrad_workspace_bytes", M, N, K)
+    ws = workspace(ws_bytes, x.device)
+    if _lib.timing is not None:
+        _lib.note = f"M={M},N={N},K={K}"
+    _lib.call("asme_b200_tc_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws), ws.numel(), _stream())
+
+
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):
     """vals/idx: (G,R,k) partial lists -> merged (R,k)"""
     vals, idx = _f32(vals), idx.contiguous()

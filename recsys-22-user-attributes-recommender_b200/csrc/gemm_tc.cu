@@ -1,0 +1,445 @@
+// Dense layers of the encoder on the tensor cores (tcgen05 + TMEM, operands staged by TMA): bf16 operands, fp32 accumulation.
+//   replaces: nn.Linear q/k/v/o (models/common/layers/transformer_layers.py:190-199), FFN (:220), FFN modifier
+//             (models/common/components/representation_modifier/ffn_modifier.py:19) and their autograd.
+//
+// Two kernel shapes, both fed by 128-byte-swizzled TMA boxes of 64 bf16 columns:
+//   "tall"   C[M,N] = A[M,K] x op(B)   M = tokens (large), N, K <= 256.      forward (B = W, K-major) and dX (B = W, MN-major).
+//            One CTA per 128 rows: whole A tile + whole weight in shared memory, one accumulator (N TMEM columns), fused
+//            epilogue (bias, GELU, gelu' multiply, Philox dropout, residual) writing fp32 and / or bf16 rows.
+//            Several CTAs are resident per SM, so loads, MMAs and epilogues of different tiles overlap.
+//   "wgrad"  dW[N,K] = dY[M,N]^T x X[M,K]   contraction over the tokens.  Both operands are MN-major views of row-major
+//            activations; split over token ranges, 4-stage TMA ring, fp32 partials reduced deterministically.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+#define G_BM 128
+#define G_THREADS 256          // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+
+// instruction descriptor with selectable operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__host__ __device__ constexpr uint32_t idesc_major(int M, int N, int a_mn, int b_mn) {
+    return idesc_bf16_f32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+// MN-major operand, SWIZZLE_128B: rows of the shared-memory chunk are K indices, the 64 contiguous elements of a row are
+// MN indices.  LBO = distance between 64-element MN blocks, SBO = distance between 8-row K groups (1024 B, dense).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TcGemmArgs {
+    int M, N, K;
+    const float* bias;                 // (N) or NULL
+    int act;                           // ASME_ACT_*
+    const __nv_bfloat16* gelu_grad_of; // (M,N) or NULL: multiply by gelu'(z)
+    float p_drop;
+    unsigned long long seed;
+    unsigned int site;
+    const float* residual;             // (M,N) fp32 or NULL
+    float* out_f32;                    // (M,N) or NULL
+    __nv_bfloat16* out_bf16;           // (M,N) or NULL
+    __nv_bfloat16* pre_act_bf16;       // (M,N) or NULL: value before the activation
+    int ld_bf16;                       // row stride of out_bf16 (>= N), lets QKV land in a wider buffer
+};
+
+struct __align__(8) GemmBars {
+    uint64_t full;
+    uint64_t done;
+    uint32_t tmem_base;
+};
+
+// four dropout scales for elements idx4*4 .. idx4*4+3 of a site (same stream as dropout_scale in common.cuh)
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx4, float p, float inv_keep, float (&s)[4]) {
+    const uint4 r = philox4x32((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    s[0] = ((float)(r.x >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    s[1] = ((float)(r.y >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    s[2] = ((float)(r.z >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    s[3] = ((float)(r.w >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int kch = a.K / CHUNK_K;                       // 64-wide K chunks of A (and of a K-major B)
+    const int nblk = (a.N + 63) / 64;                    // 64-wide N blocks of an MN-major B
+    uint8_t* sA = smem;                                  // [kch][128 rows][128 B]
+    uint8_t* sB = sA + (size_t)kch * G_BM * 128;         // K-major: [kch][N rows][128 B]   MN-major: [nblk][K rows][128 B]
+    const size_t b_bytes = B_MN ? (size_t)nblk * a.K * 128 : (size_t)kch * a.N * 128;
+    GemmBars* bars = reinterpret_cast<GemmBars*>(sB + b_bytes);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m0 = blockIdx.x * G_BM;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.N) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        mbar_init(&bars->full, 1);
+        mbar_init(&bars->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars->full, (uint32_t)(kch * G_BM * 128 + b_bytes));
+            for (int c = 0; c < kch; ++c) tma_load_2d(sA + (size_t)c * G_BM * 128, &tmA, &bars->full, c * CHUNK_K, m0);
+            if (B_MN) {
+                for (int j = 0; j < nblk; ++j) tma_load_2d(sB + (size_t)j * a.K * 128, &tmB, &bars->full, j * 64, 0);
+            } else {
+                for (int c = 0; c < kch; ++c) tma_load_2d(sB + (size_t)c * a.N * 128, &tmB, &bars->full, c * CHUNK_K, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_major(G_BM, a.N, 0, B_MN ? 1 : 0);
+            mbar_wait(&bars->full, 0);
+            tc_fence_after();
+            const int ksteps = a.K / UMMA_K;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int c = ks / 4, k4 = ks % 4;
+                const uint64_t ad = smem_desc_advance(smem_desc_sw128(smem_u32(sA + (size_t)c * G_BM * 128)), k4 * 32);
+                uint64_t bd;
+                if (B_MN) bd = smem_desc_mn_sw128(smem_u32(sB + (size_t)ks * 2048), (uint32_t)a.K * 128);   // 16 K rows = 2 KB per step
+                else bd = smem_desc_advance(smem_desc_sw128(smem_u32(sB + (size_t)c * a.N * 128)), k4 * 32);
+                umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
+            }
+            umma_commit(&bars->done);
+        }
+    } else if (warp >= 4) {
+        const int q = warp % 4;
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < a.M;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float inv_keep = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
+        mbar_wait(&bars->done, 0);
+        tc_fence_after();
+        for (int n0 = 0; n0 < a.N; n0 += 32) {
+            float v[32];
+            tmem_ld32(lane_addr + (uint32_t)n0, v);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            const size_t o = (size_t)row * a.N + n0;
+            if (a.bias) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c));
+                    v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+                }
+            }
+            if (a.pre_act_bf16) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 w;
+                    w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
+                    w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
+                    *reinterpret_cast<uint4*>(a.pre_act_bf16 + o + c) = w;
+                }
+            }
+            if (a.act == ASME_ACT_GELU) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = gelu_erf(v[c]);
+            }
+            if (a.gelu_grad_of) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.gelu_grad_of + o + c));
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
+                        v[c + 2 * e] *= gelu_erf_grad(__low2float(z2));
+                        v[c + 2 * e + 1] *= gelu_erf_grad(__high2float(z2));
+                    }
+                }
+            }
+            if (a.p_drop > 0.f) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    float s[4];
+                    dropout_scale4(a.seed, a.site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
+                    v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
+                }
+            }
+            if (a.residual) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o + c));
+                    v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
+                }
+            }
+            if (a.out_f32) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<float4*>(a.out_f32 + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
+            if (a.out_bf16) {
+                __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + n0;
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 w;
+                    w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
+                    w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
+                    *reinterpret_cast<uint4*>(dst + c) = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
+                                 const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
+                                 const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
+                                 asme_stream_t stream) {
+    ASME_REQUIRE(A && B && (out_f32 || out_bf16), "tc_gemm: null argument");
+    ASME_REQUIRE(M >= 0 && N >= 32 && N <= 256 && N % 32 == 0, "tc_gemm: N=%d unsupported (32..256, multiple of 32)", N);
+    ASME_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "tc_gemm: K=%d unsupported (64, 128, 192, 256)", K);
+    ASME_REQUIRE(!out_bf16 || (ld_bf16 >= N && ld_bf16 % 8 == 0), "tc_gemm: ld_bf16=%d", ld_bf16);
+    if (M == 0) return ASME_OK;
+    CUtensorMap tmA, tmB;
+    int rc = asme_tc_make_tmap_bf16(&tmA, A, M, K, K, G_BM);
+    if (rc) return rc;
+    // b_is_kn = 0: B is (N,K) row-major (nn.Linear weight, C = A B^T).  b_is_kn = 1: B is (K,N) row-major (C = A B).
+    rc = b_is_kn ? asme_tc_make_tmap_bf16(&tmB, B, K, N, N, K) : asme_tc_make_tmap_bf16(&tmB, B, N, K, K, N);
+    if (rc) return rc;
+    TcGemmArgs a{};
+    a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act; a.gelu_grad_of = (const __nv_bfloat16*)gelu_grad_of;
+    a.p_drop = p_drop; a.seed = seed; a.site = site; a.residual = residual; a.out_f32 = out_f32;
+    a.out_bf16 = (__nv_bfloat16*)out_bf16; a.pre_act_bf16 = (__nv_bfloat16*)pre_act_bf16; a.ld_bf16 = ld_bf16;
+    const int kch = K / 64, nblk = (N + 63) / 64;
+    const size_t b_bytes = b_is_kn ? (size_t)nblk * K * 128 : (size_t)kch * N * 128;
+    const size_t smem = 1024 + (size_t)kch * G_BM * 128 + b_bytes + sizeof(GemmBars);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ceil_div(M, G_BM);
+    if (b_is_kn) {
+        ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_gemm_tall_kernel<true><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a);
+    } else {
+        ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_gemm_tall_kernel<false><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a);
+    }
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight gradient: dW[N,K] (+)= dY[M,N]^T X[M,K], contraction over the M tokens, split over token ranges
+// ------------------------------------------------------------------------------------------------------------
+#define W_SLAB 64              // tokens per pipeline stage
+#define W_STAGES 4
+struct TcWgradArgs {
+    int M, N, K;               // M tokens; output is (N, K)
+    int slabs_per_split, n_slabs;
+    float* partial;            // [splits][N][K]
+};
+struct __align__(8) WgradBars {
+    uint64_t full[W_STAGES];
+    uint64_t empty[W_STAGES];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                                const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nb_y = (a.N + 63) / 64;                    // 64-wide blocks of dY columns   (the output rows)
+    const int nb_x = (a.K + 63) / 64;                    // 64-wide blocks of X columns    (the output columns)
+    const size_t blk = (size_t)W_SLAB * 128;             // one block of one slab: 64 tokens x 128 B
+    const size_t stage_bytes = (size_t)(nb_y + nb_x) * blk;
+    WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * stage_bytes);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int split = blockIdx.x;
+    const int s0 = split * a.slabs_per_split;
+    const int s1 = min(a.n_slabs, s0 + a.slabs_per_split);
+    const int m_tiles = (a.N + 127) / 128;               // output row tiles of 128 (N <= 256 -> at most 2)
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < m_tiles * a.K) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmX);
+        for (int s = 0; s < W_STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int i = 0;
+            for (int sl = s0; sl < s1; ++sl, ++i) {
+                const int s = i % W_STAGES;
+                const uint32_t ph = (uint32_t)(i / W_STAGES) & 1u;
+                mbar_wait(&bars->empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&bars->full[s], (uint32_t)stage_bytes);
+                uint8_t* base = smem + (size_t)s * stage_bytes;
+                for (int j = 0; j < nb_y; ++j) tma_load_2d(base + (size_t)j * blk, &tmY, &bars->full[s], j * 64, sl * W_SLAB);
+                for (int j = 0; j < nb_x; ++j) tma_load_2d(base + (size_t)(nb_y + j) * blk, &tmX, &bars->full[s], j * 64, sl * W_SLAB);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // A = dY^T (M-dim = dY columns, MN-major), B = X^T viewed as [N = X columns][K = tokens] (MN-major)
+            // always M = 128: for N = 64 / 192 the upper 64 rows of the last tile read the neighbouring block and are
+            // simply not stored (UMMA_M = 64 would use a different TMEM lane layout)
+            const uint32_t idesc = idesc_major(128, a.K, 1, 1);
+            int i = 0;
+            for (int sl = s0; sl < s1; ++sl, ++i) {
+                const int s = i % W_STAGES;
+                const uint32_t ph = (uint32_t)(i / W_STAGES) & 1u;
+                mbar_wait(&bars->full[s], ph);
+                tc_fence_after();
+                uint8_t* base = smem + (size_t)s * stage_bytes;
+                for (int mt = 0; mt < m_tiles; ++mt) {
+                    for (int ks = 0; ks < W_SLAB / UMMA_K; ++ks) {
+                        const uint64_t ad = smem_desc_mn_sw128(smem_u32(base + (size_t)(mt * 2) * blk + (size_t)ks * 2048), (uint32_t)blk);
+                        const uint64_t bd = smem_desc_mn_sw128(smem_u32(base + (size_t)nb_y * blk + (size_t)ks * 2048), (uint32_t)blk);
+                        umma_bf16(tmem_base + (uint32_t)(mt * a.K), ad, bd, idesc, (uint32_t)((i | ks) != 0));
+                    }
+                }
+                umma_commit(&bars->empty[s]);
+            }
+            umma_commit(&bars->done);
+        }
+    } else if (warp >= 4) {
+        const int q = warp % 4;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        mbar_wait(&bars->done, 0);
+        tc_fence_after();
+        float* out = a.partial + (size_t)split * a.N * a.K;
+        for (int mt = 0; mt < m_tiles; ++mt) {
+            const int n = mt * 128 + q * 32 + lane;           // output row (= dY column)
+            for (int k0 = 0; k0 < a.K; k0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)(mt * a.K + k0), v);
+                tmem_ld_wait();
+                if (n < a.N) {
+                    if (s0 >= s1) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = 0.f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(out + (size_t)n * a.K + k0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long long n, float* __restrict__ out, int accumulate) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < splits; ++p) add4(s, ldg4(partial + (size_t)p * n + i));
+    float4* o = reinterpret_cast<float4*>(out + i);
+    if (accumulate) {
+        const float4 c = *o;
+        s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+    }
+    *o = s;
+}
+
+// column sums of a bf16 matrix (bias gradients): two-stage, deterministic.  out[n] (+)= sum_m x[m,n]
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, int rows_per_block, float* __restrict__ partial) {
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += __bfloat162float(x[(size_t)r * N + n]);
+    partial[(size_t)blockIdx.x * N + n] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, int N, float* __restrict__ out, int accumulate) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * N + n];
+    out[n] = accumulate ? out[n] + s : s;
+}
+
+static int wgrad_splits(int M) {
+    const int n_slabs = ceil_div(M, W_SLAB);
+    const int s = n_slabs < ASME_NUM_SMS ? n_slabs : ASME_NUM_SMS;
+    return ceil_div(n_slabs, ceil_div(n_slabs, s));      // no empty splits
+}
+#define COLSUM_BLOCKS 296
+
+extern "C" size_t asme_b200_tc_wgrad_workspace_bytes(int M, int N, int K) {
+    return ((size_t)wgrad_splits(M < 1 ? 1 : M) * N * K + (size_t)COLSUM_BLOCKS * N) * sizeof(float);
+}
+
+extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, float* dbias, int accumulate,
+                                  void* ws, size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(dY && X && dW, "tc_wgrad: null argument");
+    ASME_REQUIRE(N >= 64 && N <= 256 && N % 64 == 0, "tc_wgrad: N=%d unsupported (64, 128, 192, 256)", N);
+    ASME_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "tc_wgrad: K=%d unsupported (64, 128, 192, 256)", K);
+    if (M == 0) return ASME_OK;
+    ASME_REQUIRE(ws_bytes >= asme_b200_tc_wgrad_workspace_bytes(M, N, K), "tc_wgrad: workspace too small");
+    CUtensorMap tmY, tmX;
+    int rc = asme_tc_make_tmap_bf16(&tmY, dY, M, N, N, W_SLAB);
+    if (rc) return rc;
+    rc = asme_tc_make_tmap_bf16(&tmX, X, M, K, K, W_SLAB);
+    if (rc) return rc;
+    TcWgradArgs a{};
+    a.M = M; a.N = N; a.K = K;
+    a.n_slabs = ceil_div(M, W_SLAB);
+    const int splits = wgrad_splits(M);
+    a.slabs_per_split = ceil_div(a.n_slabs, splits);
+    a.partial = (float*)ws;
+    const size_t stage_bytes = (size_t)((N + 63) / 64 + (K + 63) / 64) * W_SLAB * 128;
+    const size_t smem = 1024 + W_STAGES * stage_bytes + sizeof(WgradBars);
+    cudaStream_t st = (cudaStream_t)stream;
+    ASME_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgrad_kernel<<<splits, G_THREADS, smem, st>>>(tmY, tmX, a);
+    ASME_LAUNCH_OK();
+    const long long n = (long long)N * K;
+    wgrad_reduce_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(a.partial, splits, n, dW, accumulate);
+    ASME_LAUNCH_OK();
+    if (dbias) {
+        float* cp = a.partial + (size_t)splits * N * K;
+        const int rpb = ceil_div(M, COLSUM_BLOCKS);
+        const int blocks = ceil_div(M, rpb);
+        colsum_bf16_kernel<<<dim3(blocks, ceil_div(N, 64)), 64, 0, st>>>((const __nv_bfloat16*)dY, M, N, rpb, cp);
+        ASME_LAUNCH_OK();
+        colsum_final_kernel<<<ceil_div(N, 128), 128, 0, st>>>(cp, blocks, N, dbias, accumulate);
+        ASME_LAUNCH_OK();
+    }
+    return ASME_OK;
+}

@@ -1,0 +1,94 @@
+"""Parity tests of the tensor-core dense layers (asme_b200_tc_gemm / asme_b200_tc_wgrad) against float64 restatements
+of the reference's nn.Linear arithmetic (transformer_layers.py:190-220) on the same bf16-rounded operands.
+Small-integer operands make every product / partial sum exact, so results must match bit for bit whatever the
+accumulation order -- this pins the K-major and MN-major shared-memory descriptors."""
+import math
+
+import pytest
+import torch
+
+from oracle import asme_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1, 64, 64), (100, 192, 64), (128, 256, 64), (300, 64, 256), (257, 128, 128), (130, 96, 192), (51200, 192, 64)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asme_b200 import ops
+    return ops
+
+
+def ints(gen, *shape, lo=-3, hi=4):
+    return torch.randint(lo, hi, shape, generator=gen, device="cuda").float()
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_tc_gemm_forward_integer_exact(ops, M, N, K):
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a, w, bias = ints(gen, M, K), ints(gen, N, K), ints(gen, N)
+    out = ops.tc_gemm(a.bfloat16(), w.bfloat16(), bias=bias)
+    assert torch.equal(out["f32"].double(), a.double() @ w.double().t() + bias.double())
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_tc_gemm_dgrad_mn_major_integer_exact(ops, M, N, K):
+    """C = A B with B (K,N) row-major: the MN-major B descriptor (dX = dY W without a transposed copy of W)"""
+    gen = torch.Generator(device="cuda").manual_seed(M + N + 2 * K)
+    a, b = ints(gen, M, K), ints(gen, K, N)
+    out = ops.tc_gemm(a.bfloat16(), b.bfloat16(), b_is_kn=True)
+    assert torch.equal(out["f32"].double(), a.double() @ b.double())
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (100, 192, 64), (1000, 256, 64), (5000, 64, 256), (333, 128, 192), (51200, 256, 64)])
+def test_tc_wgrad_integer_exact(ops, M, N, K):
+    gen = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
+    dy, x = ints(gen, M, N, lo=-2, hi=3), ints(gen, M, K, lo=-2, hi=3)
+    dw = ints(gen, N, K)
+    db = ints(gen, N)
+    want_w = dw.double() + dy.double().t() @ x.double()
+    want_b = db.double() + dy.double().sum(0)
+    ops.tc_wgrad(dy.bfloat16(), x.bfloat16(), dw, db, accumulate=True)
+    assert torch.equal(dw.double(), want_w)
+    assert torch.equal(db.double(), want_b)
+    ops.tc_wgrad(dy.bfloat16(), x.bfloat16(), dw, db, accumulate=False)
+    assert torch.equal(dw.double(), dy.double().t() @ x.double())
+
+
+def test_tc_gemm_epilogue_matches_oracle(ops):
+    """bias -> (pre-activation copy) -> exact-erf GELU -> residual, fp32 + bf16 outputs; gaussian operands"""
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 1000, 256, 64
+    a = torch.randn(M, K, generator=gen, device="cuda").bfloat16()
+    w = (torch.randn(N, K, generator=gen, device="cuda") * 0.2).bfloat16()
+    bias = torch.randn(N, generator=gen, device="cuda")
+    res = torch.randn(M, N, generator=gen, device="cuda")
+    out = ops.tc_gemm(a, w, bias=bias, act=1, residual=res, out_bf16=True, pre_act=True)
+    z = a.double() @ w.double().t() + bias.double()
+    want = O.gelu_erf(z) + res.double()
+    torch.testing.assert_close(out["f32"].double(), want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["pre"].double(), z, rtol=2 ** -8, atol=1e-6)        # bf16 rounding of the stored copy
+    torch.testing.assert_close(out["bf16"].double(), want, rtol=2 ** -8, atol=1e-6)
+    # backward through GELU: (dy W) * gelu'(z)
+    dy = torch.randn(M, N, generator=gen, device="cuda").bfloat16()
+    w2 = (torch.randn(N, K, generator=gen, device="cuda") * 0.2).bfloat16()              # (N_out=N, K_in=K): dX = dY W
+    zz = torch.randn(M, K, generator=gen, device="cuda").bfloat16()
+    got = ops.tc_gemm(dy, w2, b_is_kn=True, gelu_grad_of=zz)["f32"]
+    zd = zz.double()
+    grad = 0.5 * (1 + torch.erf(zd / math.sqrt(2))) + zd * torch.exp(-0.5 * zd * zd) / math.sqrt(2 * math.pi)
+    torch.testing.assert_close(got.double(), (dy.double() @ w2.double()) * grad, rtol=1e-5, atol=1e-5)
+
+
+def test_tc_gemm_dropout_uses_the_shared_philox_stream(ops):
+    """the fused epilogue dropout must produce exactly the mask of the stand-alone dropout kernel (same seed / site /
+    element index), because the backward pass re-creates masks instead of storing them"""
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    M, N, K = 700, 192, 64
+    a, w = ints(gen, M, K), ints(gen, N, K)
+    plain = ops.tc_gemm(a.bfloat16(), w.bfloat16())["f32"]
+    dropped = ops.tc_gemm(a.bfloat16(), w.bfloat16(), p_drop=0.25, seed=1234567, site=21)["f32"]
+    want = ops.dropout(plain, 0.25, 1234567, 21)
+    assert torch.equal(dropped, want)
+    keep = (want != 0).float().mean().item()
+    assert abs(keep - 0.75 * (plain != 0).float().mean().item()) < 0.02
