@@ -108,6 +108,12 @@ size_t asme_b200_colsum_workspace_bytes(int M, int N);
  * ------------------------------------------------------------------------------------------ */
 int asme_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int H, float* y,
                             float* stats /* (2,M) mean,rstd or NULL */, asme_stream_t stream);
+/* LayerNorm whose output feeds a tensor-core GEMM: bf16 copy of y (y_f32 optional) */
+int asme_b200_layernorm_fwd_bf16(const float* x, const float* gamma, const float* beta, int M, int H, float* y_f32 /*NULL ok*/,
+                                 void* y_bf16, float* stats, asme_stream_t stream);
+/* y_f32 = x * mask(site_a); y_bf16 = bf16(y_f32 * mask(site_b)); a site of 0 (or p = 0) means no mask; y_f32 may be NULL */
+int asme_b200_dropout_cast(const float* x, long long n, float p, uint64_t seed, uint32_t site_a, uint32_t site_b,
+                           float* y_f32, void* y_bf16, asme_stream_t stream);
 /* dx = (d_residual ? d_residual : 0) + LN'(dy); dgamma/dbeta ACCUMULATED (dgb = (2,H)) */
 size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H);
 int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
@@ -253,12 +259,12 @@ int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb,
  *   b_is_kn = 0: B is (N,K) row-major (nn.Linear weight), C = A B^T      forward
  *   b_is_kn = 1: B is (K,N) row-major,                     C = A B        dX = dY W   (MN-major operand, no transpose copy)
  * A (M,K) bf16; N in 32..256 (multiple of 32), K in {64,128,192,256}.  Epilogue, in order: + bias[n]; pre_act_bf16 = v;
- * GELU; v *= gelu'(gelu_grad_of[m,n]); Philox dropout(seed, site, m*N+n); + residual[m,n]; out_f32 and/or out_bf16 (row
- * stride ld_bf16).
+ * GELU; v *= gelu'(gelu_grad_of[m,n]); Philox dropout(seed, site, m*N+n); + residual[m,n]; second dropout(post_site, 0 = none);
+ * out_f32 and/or out_bf16 (row stride ld_bf16).
  * ------------------------------------------------------------------------------------------ */
 int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
                       const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
-                      const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
+                      unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
                       asme_stream_t stream);
 /* dW (N,K) fp32 (+)= dY(M,N)^T X(M,K), dbias (N) (+)= colsum(dY); dY, X bf16; token contraction split over the SMs with a
  * deterministic second-stage reduction */

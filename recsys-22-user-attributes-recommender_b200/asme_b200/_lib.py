@@ -52,6 +52,8 @@ _PROTOTYPES = {
     "asme_b200_colsum_accumulate": (c_int, [P, c_int, c_int, P, P, c_size_t, P]),
     "asme_b200_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_layernorm_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P]),
+    "asme_b200_layernorm_fwd_bf16": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
+    "asme_b200_dropout_cast": (c_int, [P, c_longlong, c_float, c_uint64, c_uint32, c_uint32, P, P, P]),
     "asme_b200_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_layernorm_bwd": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
     "asme_b200_gemm": (c_int, [P, P, P, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), P]),
@@ -80,7 +82,7 @@ _PROTOTYPES = {
     "asme_b200_tc_score_topk": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_size_t, P]),
     "asme_b200_tc_score_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
-    "asme_b200_tc_gemm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, P, P, P, c_int, P, P]),
+    "asme_b200_tc_gemm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P, P]),
     "asme_b200_tc_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "asme_b200_posneg_bce_fwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),

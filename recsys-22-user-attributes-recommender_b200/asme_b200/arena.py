@@ -36,6 +36,21 @@ class ParamArena:
         self.grad = None
         self.exp_avg = None
         self.exp_avg_sq = None
+        self.version = 0            # bumped by everything that rewrites the weights behind torch's back (fused Adam, repack)
+        self.flat_bf16 = None       # bf16 shadow of ``flat`` for the tensor-core kernels (same layout, same views)
+        self._bf16_stamp = None
+
+    def bump(self):
+        self.version += 1
+
+    def bf16(self, refresh: bool = True) -> torch.Tensor:
+        """bf16 copy of the whole arena, re-cast (one kernel) whenever the fp32 weights changed"""
+        from . import ops
+        stamp = (self.version, self.flat._version, self.flat.data_ptr())
+        if self.flat_bf16 is None or self.flat_bf16.device != self.flat.device or (refresh and stamp != self._bf16_stamp):
+            self.flat_bf16 = ops.cast_bf16(self.flat.view(1, -1), ld_out=self.numel).view(-1)
+            self._bf16_stamp = stamp
+        return self.flat_bf16
 
     def _numel(self, name):
         shape = self.shapes[name]
@@ -131,6 +146,8 @@ class ArenaModule(nn.Module):
         new_flat = torch.zeros(self._arena.numel, dtype=torch.float32, device=device)
         old_flat = self._arena.flat
         self._arena.flat = new_flat
+        self._arena.bump()
+        self._arena.flat_bf16 = None
         self._arena.grad = None
         self._arena.exp_avg = None
         self._arena.exp_avg_sq = None
@@ -150,6 +167,18 @@ class ArenaModule(nn.Module):
         if params:
             self._repack(params[0][1].device)
         return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._arena.bump()
+        return out
+
+    def weight_bf16(self, path: str) -> torch.Tensor:
+        """view of a parameter inside the bf16 shadow arena (tensor-core operand)"""
+        return self._arena.view(self._spec_name(path), self._arena.bf16())
+
+    def weights_span_bf16(self, first: str, last: str, shape) -> torch.Tensor:
+        return self._arena.span(self._spec_name(first), self._spec_name(last), shape, self._arena.bf16())
 
     def arena_is_intact(self) -> bool:
         base = self._arena.flat.data_ptr()

@@ -46,6 +46,7 @@ class LayerSaved:
     st2: torch.Tensor = None
     z: torch.Tensor = None
     a: torch.Tensor = None
+    ctx16: torch.Tensor = None       # bf16 copies kept by the tensor-core path (GEMM operands of the backward pass)
 
 
 @dataclass
@@ -97,8 +98,92 @@ class EncoderEngine:
     def _site(self, layer, k):
         return ops.SITE_LAYER_BASE + 8 * layer + k
 
-    # ---------------------------------------------------------------- encoder blocks
+    # ---------------------------------------------------------------- precision policy
+    def use_tc(self) -> bool:
+        """tensor-core (tcgen05, bf16 operands / fp32 accumulation) encoder, when the model asks for it and the shapes fit
+        the 64-column TMA boxes; otherwise the strict fp32 SIMT path"""
+        cfg = self.cfg
+        return getattr(self.m, "precision", "fp32") == "bf16" and cfg.hidden % 64 == 0 and cfg.intermediate % 64 == 0
+
+    # ---------------------------------------------------------------- encoder blocks, tensor-core path
+    def _blocks_forward_tc(self, x: torch.Tensor, saved: Saved) -> torch.Tensor:
+        cfg, m = self.cfg, self.m
+        H = cfg.hidden
+        train = saved.training
+        p = cfg.dropout if train else 0.0
+        pa = cfg.attention_dropout if train else 0.0
+        B, S = saved.B, saved.S
+        for l in range(cfg.layers):
+            pre = f"{BLOCKS}.{l}"
+            ls = LayerSaved()
+            ls.x = x
+            ls.y1, _, ls.st1 = ops.layernorm_fwd_bf16(x, self._w(f"{pre}.input_sublayer.norm.weight"),
+                                                      self._w(f"{pre}.input_sublayer.norm.bias"), save_stats=train)
+            wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
+            bqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,))
+            ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv)["f32"]
+            ls.ctx, ls.ast = ops.attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa, saved.seed,
+                                          self._site(l, 0), save_stats=train)
+            ls.ctx16 = ops.cast_bf16(ls.ctx, ld_out=H)
+            ls.x2 = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
+                                bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,
+                                site=self._site(l, 1), residual=x)["f32"]
+            ls.y2, _, ls.st2 = ops.layernorm_fwd_bf16(ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"),
+                                                      self._w(f"{pre}.output_sublayer.norm.bias"), save_stats=train)
+            r = ops.tc_gemm(ls.y2, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), bias=self._w(f"{pre}.feed_forward.w_1.bias"),
+                            act=ACT_GELU, p_drop=p, seed=saved.seed, site=self._site(l, 2), out_f32=False, out_bf16=True,
+                            pre_act=train)
+            ls.a, ls.z = r["bf16"], r["pre"]
+            x = ops.tc_gemm(ls.a, m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), bias=self._w(f"{pre}.feed_forward.w_2.bias"),
+                            p_drop=p, seed=saved.seed, site=self._site(l, 3), residual=ls.x2,
+                            post_site=self._site(l, 4) if p > 0 else 0)["f32"]
+            if train:
+                saved.layers.append(ls)
+        return x
+
+    def _blocks_backward_tc(self, dx: torch.Tensor, saved: Saved) -> torch.Tensor:
+        cfg, m = self.cfg, self.m
+        H = cfg.hidden
+        p, pa = cfg.dropout, cfg.attention_dropout
+        B, S = saved.B, saved.S
+        g = m._arena.ensure_grad()
+        for l in reversed(range(cfg.layers)):
+            pre = f"{BLOCKS}.{l}"
+            ls = saved.layers[l]
+            # ---- feed forward: out = drop4(x2 + drop3(W2 a + b2)), a = drop2(gelu(z)), z = W1 y2 + b1
+            if p > 0:
+                dx3, dy16 = ops.dropout_cast(dx, p, saved.seed, self._site(l, 4), self._site(l, 3), want_f32=True)
+            else:
+                dx3, dy16 = dx, ops.cast_bf16(dx, ld_out=H)
+            ops.tc_wgrad(dy16, ls.a, self._w(f"{pre}.feed_forward.w_2.weight", True), self._w(f"{pre}.feed_forward.w_2.bias", True))
+            dz16 = ops.tc_gemm(dy16, m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), b_is_kn=True, gelu_grad_of=ls.z, p_drop=p,
+                               seed=saved.seed, site=self._site(l, 2), out_f32=False, out_bf16=True)["bf16"]
+            ops.tc_wgrad(dz16, ls.y2, self._w(f"{pre}.feed_forward.w_1.weight", True), self._w(f"{pre}.feed_forward.w_1.bias", True))
+            dy2 = ops.tc_gemm(dz16, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), b_is_kn=True)["f32"]
+            dgb2 = m.weights_span(f"{pre}.output_sublayer.norm.weight", f"{pre}.output_sublayer.norm.bias", (2, H), g)
+            dx2 = ops.layernorm_bwd(dy2, ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"), ls.st2, dgb2, d_residual=dx3)
+            # ---- attention: x2 = x + drop1(ctx Wo^T + bo)
+            _, do16 = ops.dropout_cast(dx2, p, saved.seed, 0, self._site(l, 1), want_f32=False)
+            ops.tc_wgrad(do16, ls.ctx16, self._w(f"{pre}.attention.output_linear.weight", True),
+                         self._w(f"{pre}.attention.output_linear.bias", True))
+            dctx = ops.tc_gemm(do16, m.weight_bf16(f"{pre}.attention.output_linear.weight"), b_is_kn=True)["f32"]
+            dqkv = ops.attn_bwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, ls.ctx, dctx, ls.ast, pa,
+                                saved.seed, self._site(l, 0))
+            dqkv16 = ops.cast_bf16(dqkv, ld_out=3 * H)
+            wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
+            dwqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H), g)
+            dbqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,), g)
+            ops.tc_wgrad(dqkv16, ls.y1, dwqkv, dbqkv)
+            dy1 = ops.tc_gemm(dqkv16, wqkv, b_is_kn=True)["f32"]
+            dgb1 = m.weights_span(f"{pre}.input_sublayer.norm.weight", f"{pre}.input_sublayer.norm.bias", (2, H), g)
+            dx = ops.layernorm_bwd(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, d_residual=dx2)
+        return dx
+
+    # ---------------------------------------------------------------- encoder blocks, strict fp32 path
     def blocks_forward(self, x: torch.Tensor, saved: Saved) -> torch.Tensor:
+        if self.use_tc():
+            saved.extra["tc"] = True
+            return self._blocks_forward_tc(x, saved)
         cfg, m = self.cfg, self.m
         H = cfg.hidden
         train = saved.training
@@ -135,6 +220,8 @@ class EncoderEngine:
         return x
 
     def blocks_backward(self, dx: torch.Tensor, saved: Saved) -> torch.Tensor:
+        if saved.extra.get("tc"):
+            return self._blocks_backward_tc(dx, saved)
         cfg, m = self.cfg, self.m
         H = cfg.hidden
         p, pa = cfg.dropout, cfg.attention_dropout

@@ -257,6 +257,10 @@ class RankingMetricsContainer(MetricsContainer):
     def max_k(self) -> int:
         return max([m._k for m in self.metrics if m._k is not None] + [1])
 
+    def needs_full_rank(self) -> bool:
+        """only ``rank`` and the full ``MRR`` need the target's exact rank beyond the top-k list"""
+        return any(m._metric_id in ("rank", "mrr_full") for m in self.metrics)
+
 
 class AggregateMetricsContainer(MetricsContainer):
     def __init__(self, containers: List[MetricsContainer]):
@@ -291,6 +295,9 @@ class AggregateMetricsContainer(MetricsContainer):
 
     def max_k(self) -> int:
         return max([c.max_k() for c in self.containers] + [1])
+
+    def needs_full_rank(self) -> bool:
+        return any(getattr(c, "needs_full_rank", lambda: True)() for c in self.containers)
 
 
 def build_metrics(spec: Dict[str, List[int]], sampler=None) -> AggregateMetricsContainer:

@@ -12,6 +12,7 @@ on the sm_100a kernels of ``libasme_b200.so``:
 There is no PyTorch arithmetic on these paths and no CPU fallback.
 """
 import math
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -24,6 +25,19 @@ from .engine import BLOCKS, MODIFIER, EncoderConfig, EncoderEngine, Saved, block
 
 PAD_TOKEN_ID = 0
 MASK_TOKEN_ID = 1
+
+# Precision policy of newly built models (``model.precision`` can be changed afterwards):
+#   "bf16": tensor-core path -- tcgen05 GEMMs / catalog scoring with bf16 operands and fp32 accumulation; residual stream,
+#           LayerNorm, softmax statistics, losses and optimizer state stay fp32 (north_star tolerance 1e-3)
+#   "fp32": strict-parity SIMT path (1e-5)
+DEFAULT_PRECISION = os.environ.get("ASME_B200_PRECISION", "bf16")
+
+
+def set_default_precision(precision: str) -> None:
+    global DEFAULT_PRECISION
+    if precision not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    DEFAULT_PRECISION = precision
 
 _EMB = "_sequence_embedding_layer"
 _PRE_ATTR = f"{_EMB}.prefusion_attribute_embeddings"
@@ -77,6 +91,8 @@ class TransformerRecommenderModel(ArenaModule):
         self.additional_metadata_keys = [n for n, _, _ in self.prefusion] + [n for n, _, _ in self.postfusion]
         self._init_arena(list(specs) + attr_specs + [("_ghost_zero_row", (H,))])
         self.engine = EncoderEngine(self, cfg)
+        self.precision = DEFAULT_PRECISION
+        self._wb_cache = None
         self._seed = 0
         self._step_counter = 0
         self.loss_scale = 1.0
@@ -186,6 +202,19 @@ class TransformerRecommenderModel(ArenaModule):
             return self.weight("_projection_layer.linear.weight", buf), self.weight("_projection_layer.linear.bias", buf)
         return self.weight(self.item_table_path, buf), None     # sasrec neg_sampling: h . E[item], no bias
 
+    def projection_operands_bf16(self):
+        """(catalog table as (V, Kp) bf16, bias fp32 or None) for the tensor-core scoring kernels.  With hidden % 64 == 0 the
+        table is a view into the arena's bf16 shadow; otherwise a zero-padded copy cached until the weights change."""
+        w, b = self.projection_operands()
+        H = w.shape[1]
+        if H % 64 == 0:
+            path = {"tied": self.item_table_path, "linear": "_projection_layer.linear.weight"}.get(self.projection_kind, self.item_table_path)
+            return self.weight_bf16(path), b
+        stamp = (self._arena.version, self._arena.flat._version, w.data_ptr())
+        if self._wb_cache is None or self._wb_cache[0] != stamp:
+            self._wb_cache = (stamp, ops.cast_bf16(w))
+        return self._wb_cache[1], b
+
     def modify(self, rows: torch.Tensor, save: bool = False):
         if self.modifier_kind == "ffn":
             return self.engine.modifier_forward(rows, save)
@@ -290,13 +319,24 @@ class TransformerRecommenderModel(ArenaModule):
     # ---- fused evaluation: scoring + top-k + exact target rank --------------------------------------------
     @torch.no_grad()
     def evaluate_rank(self, seq, padding_mask, attrs, target, k: int = 10, rows: Optional[torch.Tensor] = None,
-                      select: str = "mask", mask_id: int = MASK_TOKEN_ID, with_loss: bool = False, pad_id: int = PAD_TOKEN_ID):
+                      select: str = "mask", mask_id: int = MASK_TOKEN_ID, with_loss: bool = False, pad_id: int = PAD_TOKEN_ID,
+                      full_rank: bool = True):
         """returns dict(topk_val (B,k), topk_idx (B,k) int32, rank (B) int32 1-based, target_score (B)[, loss])"""
         hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
         if rows is None:
             rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
         h_rows = ops.gather_rows(hidden, rows)
         m_rows, _ = self.modify(h_rows)
+        if self.precision == "bf16":
+            wb, b = self.projection_operands_bf16()
+            hb = ops.cast_bf16(m_rows, ld_out=wb.shape[1])
+            out = score_rows_tc(hb, wb, b, target, k, full_rank)
+            if with_loss:
+                rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, target)
+                nll = rmax + torch.log(rsum) - tl
+                keep = target.ne(pad_id)
+                out["loss"] = (nll * keep).sum() / keep.sum()
+            return out
         w, b = self.projection_operands()
         out = score_rows(m_rows, w, b, target, k)
         if with_loss:      # nn.CrossEntropyLoss(ignore_index=pad) on the selected rows (masked_training_module.py:150)
@@ -312,6 +352,23 @@ def score_rows(m_rows, w, b, target, k):
     val, idx, ng, nt = ops.score_topk_rank(m_rows, w, b, k, target, ts)
     rank = (ng + nt + 1).to(torch.int32)
     return dict(topk_val=val, topk_idx=idx, rank=rank, target_score=ts, n_greater=ng, n_tie_lower=nt)
+
+
+def score_rows_tc(hb, wb, b, target, k, full_rank: bool = True):
+    """tensor-core scoring: one sweep gives the top-k list and the target's score; the exact full rank (needed only by the
+    ``rank`` / full ``MRR`` metrics) costs a second, count-only sweep.  Without it the rank is the target's position in the
+    list, or k+1 ("not in the top k"), which is all the @k metrics depend on."""
+    o = ops.tc_score_topk(hb, wb, b, k, target=target)
+    out = dict(topk_val=o["topk_val"], topk_idx=o["topk_idx"], target_score=o["target_score"])
+    if full_rank:
+        c = ops.tc_score_topk(hb, wb, b, 0, target=target, target_score_in=o["target_score"], capture_target=False)
+        out["n_greater"], out["n_tie_lower"] = c["n_greater"], c["n_tie_lower"]
+        out["rank"] = (c["n_greater"] + c["n_tie_lower"] + 1).to(torch.int32)
+    else:
+        hit = o["topk_idx"].eq(target.to(torch.int32).unsqueeze(1))
+        pos = hit.to(torch.int32).argmax(dim=1).to(torch.int32)
+        out["rank"] = torch.where(hit.any(dim=1), pos + 1, torch.full_like(pos, k + 1))
+    return out
 
 
 def mask_position_rows(seq: torch.Tensor, mask_id: int) -> torch.Tensor:

@@ -136,6 +136,10 @@ class _ModuleBase(nn.Module):
     def _eval_k(self) -> int:
         return min(32, max(self.metrics.max_k(), 1)) if hasattr(self.metrics, "max_k") else 10
 
+    def _full_rank(self) -> bool:
+        fn = getattr(self.metrics, "needs_full_rank", None)
+        return True if fn is None else bool(fn())
+
     def _adam(self, weight_decay: float):
         if self.use_fused_adam:
             from .optim import FusedAdam
@@ -188,7 +192,7 @@ class MaskedTrainingModule(_ModuleBase):
             return build_eval_step_return_dict(seq, prediction, targets)
         out = self.model.evaluate_rank(seq, pm, meta, targets, k=self._eval_k(), select="mask",
                                        mask_id=self.item_tokenizer.mask_token_id, with_loss=self.eval_loss,
-                                       pad_id=self.item_tokenizer.pad_token_id)
+                                       pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_TEST_LOSS if is_test else LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
@@ -257,7 +261,8 @@ class NextItemPredictionTrainingModule(_ModuleBase):
             logits = self(batch, batch_idx)
             return build_eval_step_return_dict(seq, self._extract_target_logits(seq, logits), target)
         out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), target, k=self._eval_k(),
-                                       select="last", with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id)
+                                       select="last", with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id,
+                                       full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
@@ -311,7 +316,7 @@ class SequenceNextItemPredictionTrainingModule(_ModuleBase):
         if not self.fused_eval or targets.dim() != 1:
             return build_eval_step_return_dict(seq, self.predict_step(batch, batch_idx), targets)
         out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), targets, k=self._eval_k(),
-                                       select="last")
+                                       select="last", full_rank=self._full_rank())
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
         return build_eval_step_return_dict(seq, pred, targets)
 

@@ -174,6 +174,30 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save
     return y, stats
 
 
+def layernorm_fwd_bf16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save_stats: bool = False, want_f32: bool = False):
+    """LayerNorm whose result feeds a tensor-core GEMM: returns (y_bf16, y_f32 or None, stats or None)"""
+    x = _f32(x)
+    M, H = x.shape
+    y16 = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
+    y32 = torch.empty_like(x) if want_f32 else None
+    stats = torch.empty(2, M, dtype=torch.float32, device=x.device) if save_stats else None
+    if _lib.timing is not None:
+        _lib.note = f"M={M},H={H},f32={int(want_f32)}"
+    _lib.call("asme_b200_layernorm_fwd_bf16", _p(x), _p(gamma), _p(beta), M, H, _p(y32), _p(y16), _p(stats), _stream())
+    return y16, y32, stats
+
+
+def dropout_cast(x: torch.Tensor, p: float, seed: int, site_a: int, site_b: int, want_f32: bool):
+    """(x * mask_a as fp32 or None, bf16(x * mask_a * mask_b)); site 0 = no mask"""
+    x = _f32(x)
+    y16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    y32 = torch.empty_like(x) if want_f32 else None
+    if _lib.timing is not None:
+        _lib.note = f"n={x.numel()},f32={int(want_f32)}"
+    _lib.call("asme_b200_dropout_cast", _p(x), x.numel(), float(p), int(seed), int(site_a), int(site_b), _p(y32), _p(y16), _stream())
+    return y32, y16
+
+
 def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[torch.Tensor] = None):
     """dx = d_residual + LN'(dy); accumulates (dgamma, dbeta) into dgb (2,H)."""
     dy, x = _f32(dy), _f32(x)
@@ -386,7 +410,7 @@ def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: in
 
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, act: int = 0, gelu_grad_of=None,
             p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out_f32: bool = True, out_bf16: bool = False,
-            pre_act: bool = False, bf16_into: Optional[torch.Tensor] = None):
+            pre_act: bool = False, post_site: int = 0, bf16_into: Optional[torch.Tensor] = None):
     """tensor-core dense layer; a (M,K) bf16, b (N,K) [or (K,N) when b_is_kn] bf16.
     returns dict(f32=..., bf16=..., pre=...) with the requested outputs"""
     a, b = _bf16(a, "a"), _bf16(b, "b")
@@ -400,7 +424,7 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, 
     if _lib.timing is not None:
         _lib.note = f"M={M},N={N},K={K},kn={int(b_is_kn)},res={int(residual is not None)},f32={int(out_f32)},bf16={int(c16 is not None)},pre={int(pre_act)},aux={int(gelu_grad_of is not None)}"
     _lib.call("asme_b200_tc_gemm", _p(a), _p(b), M, N, K, 1 if b_is_kn else 0, _p(bias), int(act), _p(gelu_grad_of), float(p_drop),
-              int(seed), int(site), _p(residual), _p(c32), _p(c16), int(ld16), _p(pre), _stream())
+              int(seed), int(site), int(post_site), _p(residual), _p(c32), _p(c16), int(ld16), _p(pre), _stream())
     return dict(f32=c32, bf16=c16, pre=pre)
 
 

@@ -27,6 +27,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._steps += 1
         ops.adam_step(arena.flat, g, m, v, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
                       group["weight_decay"], self._steps)
+        arena.bump()        # the kernel wrote the weights through raw pointers: invalidate the bf16 shadow
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

@@ -30,6 +30,7 @@ def run(verbose: bool = True):
         target[i, :lengths[i]][m] = seq[i, :lengths[i]][m]
         seq[i, :lengths[i]][m] = 1
     model = model.cuda().train()
+    model.precision = "fp32"      # strict-parity pass first (1e-4 / exact ranks up to fp32 near-ties), tensor-core pass below
     seq_d, target_d = seq.cuda(), target.cuda()
 
     # training step: fused CE loss + backward
@@ -59,8 +60,22 @@ def run(verbose: bool = True):
     assert (np.abs(got_rank - want_rank) <= 1).all() and (got_rank == want_rank).mean() >= 0.75, (got_rank, want_rank)
     logits = model(InputSequence(ev.cuda(), ev.cuda().ne(0), {}))
     assert logits.shape == (B, S, V)
+
+    # the same two steps under the tensor-core policy (tcgen05 GEMMs + catalog scoring, bf16 operands): bf16 tolerances
+    model.precision = "bf16"
+    model.train()
+    loss16, ctx16 = model.loss_ce(seq_d, seq_d.ne(0), {}, target_d)
+    model.loss_ce_backward(ctx16)
+    assert abs(float(loss16) - float(ref_loss)) < 1e-3 * max(1.0, abs(float(ref_loss))), (float(loss16), float(ref_loss))
+    model.eval()
+    out16 = model.evaluate_rank(ev.cuda(), ev.cuda().ne(0), {}, tgt.cuda(), k=10)
+    scale = np.abs(rows).max()
+    got16 = np.take_along_axis(rows, out16["topk_idx"].cpu().numpy().astype(np.int64), 1)
+    assert np.abs(got16 - srt[:, :10]).max() < 4e-3 * scale, np.abs(got16 - srt[:, :10]).max()
+    assert (np.abs(out16["rank"].cpu().numpy() - want_rank) <= 3).all()
     if verbose:
-        print(f"[asme_b200 smoke] loss={float(loss):.6f} (oracle {float(ref_loss):.6f}); ranks={got_rank.tolist()} OK")
+        print(f"[asme_b200 smoke] fp32 loss={float(loss):.6f} bf16/tcgen05 loss={float(loss16):.6f} (oracle {float(ref_loss):.6f}); "
+              f"ranks={got_rank.tolist()} OK")
 
 
 if __name__ == "__main__":

@@ -41,6 +41,7 @@ struct TcGemmArgs {
     float p_drop;
     unsigned long long seed;
     unsigned int site;
+    unsigned int post_site;            // second dropout applied AFTER the residual add (block-end dropout); 0 = none
     const float* residual;             // (M,N) fp32 or NULL
     float* out_f32;                    // (M,N) or NULL
     __nv_bfloat16* out_bf16;           // (M,N) or NULL
@@ -48,8 +49,10 @@ struct TcGemmArgs {
     int ld_bf16;                       // row stride of out_bf16 (>= N), lets QKV land in a wider buffer
 };
 
+#define G_STAGES 4
 struct __align__(8) GemmBars {
-    uint64_t full;
+    uint64_t full[G_STAGES];
+    uint64_t empty[G_STAGES];
     uint64_t done;
     uint32_t tmem_base;
 };
@@ -68,26 +71,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// CTA (m_tile, n_tile): 128 rows x NT (<= 256) columns; K streamed in 64-wide chunks through a ring of `stages` slots
+// (slot = A chunk 16 KB + B chunk NT x 128 B [K-major] or ceil(NT/64) x 8 KB [MN-major]).
 template <bool B_MN>
 __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a) {
+                                                                  const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
+                                                                  int stages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int kch = a.K / CHUNK_K;                       // 64-wide K chunks of A (and of a K-major B)
-    const int nblk = (a.N + 63) / 64;                    // 64-wide N blocks of an MN-major B
-    uint8_t* sA = smem;                                  // [kch][128 rows][128 B]
-    uint8_t* sB = sA + (size_t)kch * G_BM * 128;         // K-major: [kch][N rows][128 B]   MN-major: [nblk][K rows][128 B]
-    const size_t b_bytes = B_MN ? (size_t)nblk * a.K * 128 : (size_t)kch * a.N * 128;
-    GemmBars* bars = reinterpret_cast<GemmBars*>(sB + b_bytes);
+    const int kch = a.K / CHUNK_K;
+    const int n0 = blockIdx.y * 256;
+    const int NT = min(256, a.N - n0);                   // columns of this CTA (multiple of 32)
+    const int nblk = (NT + 63) / 64;
+    const size_t a_bytes = (size_t)G_BM * 128;
+    const size_t b_bytes = B_MN ? (size_t)nblk * 64 * 128 : (size_t)min(256, a.N) * 128;   // = bytes the TMA boxes deliver (OOB rows are zero-filled)
+    const size_t b_slot = (size_t)256 * 128;             // slot stride sized for the widest tile: keeps every chunk 1024-aligned
+    const size_t slot = a_bytes + b_slot;
+    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)stages * slot);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int m0 = blockIdx.x * G_BM;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < a.N) tmem_cols <<= 1;
+    while ((int)tmem_cols < NT) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        mbar_init(&bars->full, 1);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
         mbar_init(&bars->done, 1);
         fence_barrier_init();
     }
@@ -99,27 +111,40 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->full, (uint32_t)(kch * G_BM * 128 + b_bytes));
-            for (int c = 0; c < kch; ++c) tma_load_2d(sA + (size_t)c * G_BM * 128, &tmA, &bars->full, c * CHUNK_K, m0);
-            if (B_MN) {
-                for (int j = 0; j < nblk; ++j) tma_load_2d(sB + (size_t)j * a.K * 128, &tmB, &bars->full, j * 64, 0);
-            } else {
-                for (int c = 0; c < kch; ++c) tma_load_2d(sB + (size_t)c * a.N * 128, &tmB, &bars->full, c * CHUNK_K, 0);
+            for (int c = 0; c < kch; ++c) {
+                const int s = c % stages;
+                const uint32_t ph = (uint32_t)(c / stages) & 1u;
+                mbar_wait(&bars->empty[s], ph ^ 1u);
+                uint8_t* sA = smem + (size_t)s * slot;
+                uint8_t* sB = sA + a_bytes;
+                mbar_arrive_expect_tx(&bars->full[s], (uint32_t)(a_bytes + b_bytes));
+                tma_load_2d(sA, &tmA, &bars->full[s], c * CHUNK_K, m0);
+                if (B_MN) {
+                    for (int j = 0; j < nblk; ++j) tma_load_2d(sB + (size_t)j * 64 * 128, &tmB, &bars->full[s], n0 + j * 64, c * CHUNK_K);
+                } else {
+                    tma_load_2d(sB, &tmB, &bars->full[s], c * CHUNK_K, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = idesc_major(G_BM, a.N, 0, B_MN ? 1 : 0);
-            mbar_wait(&bars->full, 0);
-            tc_fence_after();
-            const int ksteps = a.K / UMMA_K;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int c = ks / 4, k4 = ks % 4;
-                const uint64_t ad = smem_desc_advance(smem_desc_sw128(smem_u32(sA + (size_t)c * G_BM * 128)), k4 * 32);
-                uint64_t bd;
-                if (B_MN) bd = smem_desc_mn_sw128(smem_u32(sB + (size_t)ks * 2048), (uint32_t)a.K * 128);   // 16 K rows = 2 KB per step
-                else bd = smem_desc_advance(smem_desc_sw128(smem_u32(sB + (size_t)c * a.N * 128)), k4 * 32);
-                umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
+            const uint32_t idesc = idesc_major(G_BM, NT, 0, B_MN ? 1 : 0);
+            for (int c = 0; c < kch; ++c) {
+                const int s = c % stages;
+                const uint32_t ph = (uint32_t)(c / stages) & 1u;
+                mbar_wait(&bars->full[s], ph);
+                tc_fence_after();
+                uint8_t* sA = smem + (size_t)s * slot;
+                uint8_t* sB = sA + a_bytes;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t ad = smem_desc_advance(smem_desc_sw128(smem_u32(sA)), k4 * 32);
+                    uint64_t bd;
+                    if (B_MN) bd = smem_desc_mn_sw128(smem_u32(sB + (size_t)k4 * 2048), 64 * 128);   // 16 K rows = 2 KB per step
+                    else bd = smem_desc_advance(smem_desc_sw128(smem_u32(sB)), k4 * 32);
+                    umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((c | k4) != 0));
+                }
+                umma_commit(&bars->empty[s]);
             }
             umma_commit(&bars->done);
         }
@@ -131,16 +156,17 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
         const float inv_keep = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
         mbar_wait(&bars->done, 0);
         tc_fence_after();
-        for (int n0 = 0; n0 < a.N; n0 += 32) {
+        for (int nn = 0; nn < NT; nn += 32) {
             float v[32];
-            tmem_ld32(lane_addr + (uint32_t)n0, v);
+            tmem_ld32(lane_addr + (uint32_t)nn, v);
             tmem_ld_wait();
             if (!row_ok) continue;
-            const size_t o = (size_t)row * a.N + n0;
+            const int nc = n0 + nn;                         // first global column of this chunk
+            const size_t o = (size_t)row * a.N + nc;
             if (a.bias) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nc + c));
                     v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
                 }
             }
@@ -170,7 +196,7 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
                     }
                 }
             }
-            if (a.p_drop > 0.f) {
+            if (a.p_drop > 0.f && a.site) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     float s[4];
@@ -185,13 +211,21 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
                     v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
                 }
             }
+            if (a.p_drop > 0.f && a.post_site) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    float s[4];
+                    dropout_scale4(a.seed, a.post_site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
+                    v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
+                }
+            }
             if (a.out_f32) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4)
                     *reinterpret_cast<float4*>(a.out_f32 + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
             }
             if (a.out_bf16) {
-                __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + n0;
+                __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + nc;
 #pragma unroll
                 for (int c = 0; c < 32; c += 8) {
                     uint4 w;
@@ -212,34 +246,35 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
 
 extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
                                  const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
-                                 const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
-                                 asme_stream_t stream) {
+                                 unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
+                                 void* pre_act_bf16, asme_stream_t stream) {
     ASME_REQUIRE(A && B && (out_f32 || out_bf16), "tc_gemm: null argument");
-    ASME_REQUIRE(M >= 0 && N >= 32 && N <= 256 && N % 32 == 0, "tc_gemm: N=%d unsupported (32..256, multiple of 32)", N);
-    ASME_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "tc_gemm: K=%d unsupported (64, 128, 192, 256)", K);
+    ASME_REQUIRE(M >= 0 && N >= 32 && N % 32 == 0, "tc_gemm: N=%d unsupported (multiple of 32)", N);
+    ASME_REQUIRE(K >= 64 && K % 64 == 0, "tc_gemm: K=%d unsupported (multiple of 64)", K);
     ASME_REQUIRE(!out_bf16 || (ld_bf16 >= N && ld_bf16 % 8 == 0), "tc_gemm: ld_bf16=%d", ld_bf16);
     if (M == 0) return ASME_OK;
     CUtensorMap tmA, tmB;
     int rc = asme_tc_make_tmap_bf16(&tmA, A, M, K, K, G_BM);
     if (rc) return rc;
-    // b_is_kn = 0: B is (N,K) row-major (nn.Linear weight, C = A B^T).  b_is_kn = 1: B is (K,N) row-major (C = A B).
-    rc = b_is_kn ? asme_tc_make_tmap_bf16(&tmB, B, K, N, N, K) : asme_tc_make_tmap_bf16(&tmB, B, N, K, K, N);
+    // b_is_kn = 0: B is (N,K) row-major (nn.Linear weight, C = A B^T): box 64 x min(N,256) rows.
+    // b_is_kn = 1: B is (K,N) row-major (C = A B): box 64 columns x 64 K rows.
+    rc = b_is_kn ? asme_tc_make_tmap_bf16(&tmB, B, K, N, N, 64) : asme_tc_make_tmap_bf16(&tmB, B, N, K, K, N < 256 ? N : 256);
     if (rc) return rc;
     TcGemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act; a.gelu_grad_of = (const __nv_bfloat16*)gelu_grad_of;
-    a.p_drop = p_drop; a.seed = seed; a.site = site; a.residual = residual; a.out_f32 = out_f32;
+    a.p_drop = p_drop; a.seed = seed; a.site = site; a.post_site = post_site; a.residual = residual; a.out_f32 = out_f32;
     a.out_bf16 = (__nv_bfloat16*)out_bf16; a.pre_act_bf16 = (__nv_bfloat16*)pre_act_bf16; a.ld_bf16 = ld_bf16;
-    const int kch = K / 64, nblk = (N + 63) / 64;
-    const size_t b_bytes = b_is_kn ? (size_t)nblk * K * 128 : (size_t)kch * N * 128;
-    const size_t smem = 1024 + (size_t)kch * G_BM * 128 + b_bytes + sizeof(GemmBars);
+    const int kch = K / 64;
+    const int stages = kch < G_STAGES ? kch : G_STAGES;
+    const size_t smem = 1024 + (size_t)stages * ((size_t)G_BM * 128 + 256 * 128) + sizeof(GemmBars);
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = ceil_div(M, G_BM);
+    const dim3 grid(ceil_div(M, G_BM), ceil_div(N, 256));
     if (b_is_kn) {
         ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_tall_kernel<true><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a);
+        tc_gemm_tall_kernel<true><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
     } else {
         ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gemm_tall_kernel<false><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a);
+        tc_gemm_tall_kernel<false><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
     }
     ASME_LAUNCH_OK();
     return ASME_OK;
@@ -262,22 +297,25 @@ struct __align__(8) WgradBars {
     uint32_t tmem_base;
 };
 
+// CTA (split, n_tile, k_tile): output rows n_tile*128..+127 (dY columns), output columns k_tile*256..+255 (X columns),
+// tokens of `split`.
 __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                 const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int nb_y = (a.N + 63) / 64;                    // 64-wide blocks of dY columns   (the output rows)
-    const int nb_x = (a.K + 63) / 64;                    // 64-wide blocks of X columns    (the output columns)
-    const size_t blk = (size_t)W_SLAB * 128;             // one block of one slab: 64 tokens x 128 B
-    const size_t stage_bytes = (size_t)(nb_y + nb_x) * blk;
+    const int nrow0 = blockIdx.y * 128;                  // first output row  (dY column) of this CTA
+    const int kcol0 = blockIdx.z * 256;                  // first output column (X column) of this CTA
+    const int KT = min(256, a.K - kcol0);                // output columns of this CTA (multiple of 64)
+    const int nb_x = KT / 64;
+    const size_t blk = (size_t)W_SLAB * 128;             // one 64-column block of one slab: 64 tokens x 128 B
+    const size_t stage_bytes = (size_t)(2 + 4) * blk;    // 2 dY blocks + up to 4 X blocks (fixed slot size)
     WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * stage_bytes);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int split = blockIdx.x;
     const int s0 = split * a.slabs_per_split;
     const int s1 = min(a.n_slabs, s0 + a.slabs_per_split);
-    const int m_tiles = (a.N + 127) / 128;               // output row tiles of 128 (N <= 256 -> at most 2)
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < m_tiles * a.K) tmem_cols <<= 1;
+    while ((int)tmem_cols < KT) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
@@ -302,18 +340,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
                 const int s = i % W_STAGES;
                 const uint32_t ph = (uint32_t)(i / W_STAGES) & 1u;
                 mbar_wait(&bars->empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&bars->full[s], (uint32_t)stage_bytes);
+                mbar_arrive_expect_tx(&bars->full[s], (uint32_t)((2 + nb_x) * blk));
                 uint8_t* base = smem + (size_t)s * stage_bytes;
-                for (int j = 0; j < nb_y; ++j) tma_load_2d(base + (size_t)j * blk, &tmY, &bars->full[s], j * 64, sl * W_SLAB);
-                for (int j = 0; j < nb_x; ++j) tma_load_2d(base + (size_t)(nb_y + j) * blk, &tmX, &bars->full[s], j * 64, sl * W_SLAB);
+                // dY columns beyond N are out of bounds of the tensor map: zero-filled, the extra output rows are not stored
+                for (int j = 0; j < 2; ++j) tma_load_2d(base + (size_t)j * blk, &tmY, &bars->full[s], nrow0 + j * 64, sl * W_SLAB);
+                for (int j = 0; j < nb_x; ++j) tma_load_2d(base + (size_t)(2 + j) * blk, &tmX, &bars->full[s], kcol0 + j * 64, sl * W_SLAB);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // A = dY^T (M-dim = dY columns, MN-major), B = X^T viewed as [N = X columns][K = tokens] (MN-major)
-            // always M = 128: for N = 64 / 192 the upper 64 rows of the last tile read the neighbouring block and are
-            // simply not stored (UMMA_M = 64 would use a different TMEM lane layout)
-            const uint32_t idesc = idesc_major(128, a.K, 1, 1);
+            const uint32_t idesc = idesc_major(128, KT, 1, 1);
             int i = 0;
             for (int sl = s0; sl < s1; ++sl, ++i) {
                 const int s = i % W_STAGES;
@@ -321,12 +358,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
                 mbar_wait(&bars->full[s], ph);
                 tc_fence_after();
                 uint8_t* base = smem + (size_t)s * stage_bytes;
-                for (int mt = 0; mt < m_tiles; ++mt) {
-                    for (int ks = 0; ks < W_SLAB / UMMA_K; ++ks) {
-                        const uint64_t ad = smem_desc_mn_sw128(smem_u32(base + (size_t)(mt * 2) * blk + (size_t)ks * 2048), (uint32_t)blk);
-                        const uint64_t bd = smem_desc_mn_sw128(smem_u32(base + (size_t)nb_y * blk + (size_t)ks * 2048), (uint32_t)blk);
-                        umma_bf16(tmem_base + (uint32_t)(mt * a.K), ad, bd, idesc, (uint32_t)((i | ks) != 0));
-                    }
+#pragma unroll
+                for (int ks = 0; ks < W_SLAB / UMMA_K; ++ks) {
+                    const uint64_t ad = smem_desc_mn_sw128(smem_u32(base + (size_t)ks * 2048), (uint32_t)blk);
+                    const uint64_t bd = smem_desc_mn_sw128(smem_u32(base + 2 * blk + (size_t)ks * 2048), (uint32_t)blk);
+                    umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((i | ks) != 0));
                 }
                 umma_commit(&bars->empty[s]);
             }
@@ -338,21 +374,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
         mbar_wait(&bars->done, 0);
         tc_fence_after();
         float* out = a.partial + (size_t)split * a.N * a.K;
-        for (int mt = 0; mt < m_tiles; ++mt) {
-            const int n = mt * 128 + q * 32 + lane;           // output row (= dY column)
-            for (int k0 = 0; k0 < a.K; k0 += 32) {
-                float v[32];
-                tmem_ld32(lane_addr + (uint32_t)(mt * a.K + k0), v);
-                tmem_ld_wait();
-                if (n < a.N) {
-                    if (s0 >= s1) {
+        const int n = nrow0 + q * 32 + lane;               // output row (= dY column)
+        for (int k0 = 0; k0 < KT; k0 += 32) {
+            float v[32];
+            tmem_ld32(lane_addr + (uint32_t)k0, v);
+            tmem_ld_wait();
+            if (n < a.N) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = 0.f;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4)
-                        *reinterpret_cast<float4*>(out + (size_t)n * a.K + k0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                }
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<float4*>(out + (size_t)n * a.K + kcol0 + k0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
             }
         }
     }
@@ -408,8 +438,8 @@ extern "C" size_t asme_b200_tc_wgrad_workspace_bytes(int M, int N, int K) {
 extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, float* dbias, int accumulate,
                                   void* ws, size_t ws_bytes, asme_stream_t stream) {
     ASME_REQUIRE(dY && X && dW, "tc_wgrad: null argument");
-    ASME_REQUIRE(N >= 64 && N <= 256 && N % 64 == 0, "tc_wgrad: N=%d unsupported (64, 128, 192, 256)", N);
-    ASME_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "tc_wgrad: K=%d unsupported (64, 128, 192, 256)", K);
+    ASME_REQUIRE(N >= 64 && N % 64 == 0, "tc_wgrad: N=%d unsupported (multiple of 64)", N);
+    ASME_REQUIRE(K >= 64 && K % 64 == 0, "tc_wgrad: K=%d unsupported (multiple of 64)", K);
     if (M == 0) return ASME_OK;
     ASME_REQUIRE(ws_bytes >= asme_b200_tc_wgrad_workspace_bytes(M, N, K), "tc_wgrad: workspace too small");
     CUtensorMap tmY, tmX;
@@ -423,11 +453,11 @@ extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, i
     const int splits = wgrad_splits(M);
     a.slabs_per_split = ceil_div(a.n_slabs, splits);
     a.partial = (float*)ws;
-    const size_t stage_bytes = (size_t)((N + 63) / 64 + (K + 63) / 64) * W_SLAB * 128;
+    const size_t stage_bytes = (size_t)(2 + 4) * W_SLAB * 128;
     const size_t smem = 1024 + W_STAGES * stage_bytes + sizeof(WgradBars);
     cudaStream_t st = (cudaStream_t)stream;
     ASME_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<<<splits, G_THREADS, smem, st>>>(tmY, tmX, a);
+    tc_wgrad_kernel<<<dim3(splits, ceil_div(N, 128), ceil_div(K, 256)), G_THREADS, smem, st>>>(tmY, tmX, a);
     ASME_LAUNCH_OK();
     const long long n = (long long)N * K;
     wgrad_reduce_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(a.partial, splits, n, dW, accumulate);

@@ -6,6 +6,7 @@
 // c < CH = H/(4*LANES).  Every global access is a coalesced float4 (128-bit) transaction and the
 // LayerNorm reductions are xor-shuffles inside the group -- no shared memory on the forward path.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 #include <stdarg.h>
 #include <string.h>
@@ -55,6 +56,16 @@ struct Row {
     __device__ __forceinline__ void store(float* base, int lane) const {
 #pragma unroll
         for (int c = 0; c < CH; ++c) *reinterpret_cast<float4*>(base + (c * LANES + lane) * 4) = v[c];
+    }
+    __device__ __forceinline__ void store_bf16(__nv_bfloat16* base, int lane) const {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[c].x, v[c].y), hi = __floats2bfloat162_rn(v[c].z, v[c].w);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(base + (c * LANES + lane) * 4) = o;
+        }
     }
     __device__ __forceinline__ float sum() const {
         float s = 0.f;
@@ -264,7 +275,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
 template <int LANES, int CH>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int M, int H,
-                                                            float* __restrict__ y, float* __restrict__ stats) {
+                                                            float* __restrict__ y, float* __restrict__ stats,
+                                                            __nv_bfloat16* __restrict__ y16) {
     const int lane = threadIdx.x % LANES;
     const long long r = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
     if (r >= M) return;
@@ -273,7 +285,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     float mean, rstd;
     ln_forward<LANES, CH>(xr, yr, gamma, beta, lane, H, mean, rstd);
     if (stats && lane == 0) { stats[r] = mean; stats[(size_t)M + r] = rstd; }
-    yr.store(y + r * H, lane);
+    if (y) yr.store(y + r * H, lane);
+    if (y16) yr.store_bf16(y16 + r * H, lane);
 }
 
 template <int LANES, int CH>
@@ -458,7 +471,23 @@ extern "C" int asme_b200_layernorm_fwd(const float* x, const float* gamma, const
     if (M == 0) return ASME_OK;
     const int lanes = lanes_for(H);
     const int groups = 256 / lanes;
-#define CALL(L, C) layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y, stats)
+#define CALL(L, C) layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y, stats, nullptr)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// LayerNorm whose output feeds a tensor-core GEMM: y as bf16 (and optionally fp32 too)
+extern "C" int asme_b200_layernorm_fwd_bf16(const float* x, const float* gamma, const float* beta, int M, int H, float* y_f32,
+                                            void* y_bf16, float* stats, asme_stream_t stream) {
+    ASME_REQUIRE(x && gamma && beta && y_bf16, "layernorm_fwd_bf16: null argument");
+    if (M == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+#define CALL(L, C)                                                                                                     \
+    layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y_f32, stats, \
+                                                                                      (__nv_bfloat16*)y_bf16)
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
@@ -513,6 +542,40 @@ extern "C" int asme_b200_dropout(const float* x, float* y, long long n, float p,
     ASME_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f out of range", p);
     if (n == 0) return ASME_OK;
     dropout_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n / 4, p, 1.0f / (1.0f - p), seed, site);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// y_f32 = x * mask_a ; y_bf16 = bf16(y_f32 * mask_b): the gradient entering a residual block is needed both as the fp32
+// residual gradient (after the block-end dropout, site_a) and as the bf16 GEMM operand (after the sub-layer dropout, site_b)
+__global__ void dropout_cast_kernel(const float* __restrict__ x, long long n4, float p, float inv_keep, uint64_t seed,
+                                    uint32_t site_a, uint32_t site_b, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = ldg4(x + i * 4);
+    if (p > 0.f && site_a) {
+        const float4 s = dropout_scale4(seed, site_a, (uint64_t)i * 4, p, inv_keep);
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    }
+    if (y32) reinterpret_cast<float4*>(y32)[i] = v;
+    if (p > 0.f && site_b) {
+        const float4 s = dropout_scale4(seed, site_b, (uint64_t)i * 4, p, inv_keep);
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    }
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y16)[i] = o;
+}
+extern "C" int asme_b200_dropout_cast(const float* x, long long n, float p, uint64_t seed, uint32_t site_a, uint32_t site_b,
+                                      float* y_f32, void* y_bf16, asme_stream_t stream) {
+    ASME_REQUIRE(x && y_bf16, "dropout_cast: null argument");
+    ASME_REQUIRE(n % 4 == 0, "dropout_cast: n=%lld must be a multiple of 4", n);
+    ASME_REQUIRE(p >= 0.f && p < 1.f, "dropout_cast: p=%f out of range", p);
+    if (n == 0) return ASME_OK;
+    dropout_cast_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n / 4, p, 1.0f / (1.0f - p), seed, site_a, site_b,
+                                                                               y_f32, (__nv_bfloat16*)y_bf16);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

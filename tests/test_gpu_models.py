@@ -11,6 +11,18 @@ from oracle import asme_oracle as O
 from test_host_cpu import build_from_fixture
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32_policy():
+    """these tests pin the strict-parity (fp32 SIMT) path at 1e-5; the tensor-core policy is covered by test_gpu_models_bf16.py"""
+    from asme_b200 import models
+    old = models.DEFAULT_PRECISION
+    models.set_default_precision("fp32")
+    yield
+    models.set_default_precision(old)
+
+
 RTOL, ATOL = 1e-5, 2e-5
 
 

@@ -11,7 +11,8 @@ from oracle import asme_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(1, 64, 64), (100, 192, 64), (128, 256, 64), (300, 64, 256), (257, 128, 128), (130, 96, 192), (51200, 192, 64)]
+SHAPES = [(1, 64, 64), (100, 192, 64), (128, 256, 64), (300, 64, 256), (257, 128, 128), (130, 96, 192), (51200, 192, 64),
+          (300, 384, 128), (200, 512, 128), (200, 128, 512), (77, 640, 320)]
 
 
 @pytest.fixture(scope="module")
@@ -41,7 +42,8 @@ def test_tc_gemm_dgrad_mn_major_integer_exact(ops, M, N, K):
     assert torch.equal(out["f32"].double(), a.double() @ b.double())
 
 
-@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (100, 192, 64), (1000, 256, 64), (5000, 64, 256), (333, 128, 192), (51200, 256, 64)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (100, 192, 64), (1000, 256, 64), (5000, 64, 256), (333, 128, 192), (51200, 256, 64),
+                                   (700, 384, 128), (700, 512, 128), (700, 128, 512)])
 def test_tc_wgrad_integer_exact(ops, M, N, K):
     gen = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
     dy, x = ints(gen, M, N, lo=-2, hi=3), ints(gen, M, K, lo=-2, hi=3)
