@@ -273,6 +273,15 @@ int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, int K, float
                        void* ws, size_t ws_bytes, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5+K8 on the tensor cores: masked attention for S <= 256, head dim 16/32/64, hidden % 64 == 0.
+ * qkv: (B*S, 3H) bf16 = [q | k | v] per token (the bf16 output of the QKV projection, read by TMA); ctx: (B*S, H) bf16.
+ * Same semantics, statistics layout and Philox dropout stream as asme_b200_attn_fwd.
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                          float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
+                          asme_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K13+K17  SASRec positive/negative dot products fused with the BCE loss
  * replaces: SASRecProjectionComponent.forward train branch (models/sasrec/components.py:35-44) and
  *           sas_rec_binary_cross_entropy (losses/sasrec/sas_rec_losses.py:47-75).

@@ -440,6 +440,22 @@ def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optiona
     _lib.call("asme_b200_tc_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws), ws.numel(), _stream())
 
 
+def tc_attn_fwd(qkv16: torch.Tensor, key_valid: Optional[torch.Tensor], B: int, S: int, heads: int, causal: bool,
+                p_drop: float = 0.0, seed: int = 0, site: int = 0, save_stats: bool = False):
+    """tensor-core attention: qkv16 (B*S, 3H) bf16 -> (ctx (B*S, H) bf16, stats (2, B*heads*S) or None)"""
+    qkv16 = _bf16(qkv16, "qkv")
+    H = qkv16.shape[1] // 3
+    d = H // heads
+    kv = _u8(key_valid)
+    ctx = torch.empty(B * S, H, dtype=torch.bfloat16, device=qkv16.device)
+    stats = torch.empty(2, B * heads * S, dtype=torch.float32, device=qkv16.device) if save_stats else None
+    if _lib.timing is not None:
+        _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
+    _lib.call("asme_b200_tc_attn_fwd", _p(qkv16), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed), int(site),
+              _p(ctx), _p(stats), _stream())
+    return ctx, stats
+
+
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):
     """vals/idx: (G,R,k) partial lists -> merged (R,k)"""
     vals, idx = _f32(vals), idx.contiguous()

@@ -1,0 +1,290 @@
+// Masked self-attention for short sequences (S <= 256, head dim 16 / 32 / 64) on the tensor cores:
+// tcgen05.mma with fp32 accumulators in tensor memory, Q / K / V tiles staged by TMA straight out of the (T, 3H) bf16
+// output of the QKV projection, probabilities handed to the second MMA through 128-byte-swizzled shared memory.
+//
+// replaces: mask materialisation (models/transformer/sequence_representation.py:33-48) and Attention.forward
+//           (models/common/layers/transformer_layers.py:145-155): QK^T/sqrt(d) -> masked_fill(mask==0,-1e9) -> softmax
+//           -> dropout -> .V.  The (B,1,S,S) mask never exists: validity comes from the (B,S) key-padding bits and the
+//           causal flag; a fully masked row attends uniformly to all S keys (quirk Q4, -1e9 not -inf).
+//
+// One CTA = one sequence b x one 64-column slice of the hidden size (64/d heads).  Shared memory holds that slice of Q, K
+// and V for the whole sequence (3 x 32 KB) plus one probability tile (128 queries x 256 keys bf16, 64 KB).
+//   warp 0   TMA producer (three boxes)           warp 1   MMA issuer           warp 2   TMEM allocator
+//   warps 4-7  softmax / epilogue: thread = one query row (TMEM lane)
+// Per (head, 128-query tile):  S = Q K^T (K-major operands, the head's 32-byte K-steps inside the 128-byte rows)
+//   -> softmax in registers (two passes over TMEM: max, then exp / sum / dropout), P -> shared memory (bf16, K-major)
+//   -> O = P V (V consumed as an MN-major operand: no transposed copy) -> O / rowsum -> ctx (bf16).
+// Row max / row sum-exp and the Philox dropout stream use the conventions of the fp32 SIMT kernels (attention_simt.cu),
+// so forward and backward kernels of either flavour can be mixed and compared.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+#define AT_THREADS 256
+#define AT_MAXS 256
+#define MASK_FILL (-1e9f)
+#define LOG2E 1.4426950408889634f
+
+__host__ __device__ constexpr uint32_t at_idesc(int M, int N, int a_mn, int b_mn) {
+    return idesc_bf16_f32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+__device__ __forceinline__ uint64_t at_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t at_pack(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+struct AttnTcArgs {
+    const uint8_t* key_valid;    // (B,S) or NULL
+    int B, S, heads, d, H, causal;
+    float scale, p_drop, inv_keep;
+    unsigned long long seed;
+    unsigned int site;
+    __nv_bfloat16* ctx;          // (B*S, H)
+    float* stats;                // (2, B*heads*S) or NULL
+};
+
+struct __align__(8) AttnBars {
+    uint64_t loaded;
+    uint64_t s_full;
+    uint64_t p_full;
+    uint64_t o_full;
+    uint32_t tmem_base;
+    uint32_t kvb[8];             // key-validity bits of the sequence (bit j of word w: key 32w+j may be attended)
+};
+
+// dropout scales of 32 consecutive elements idx0 .. idx0+31 of a site (element-indexed Philox stream of common.cuh)
+__device__ __forceinline__ void dropout_scales32(uint64_t seed, uint32_t site, uint64_t idx0, float p, float inv_keep, float (&s)[32]) {
+    const uint32_t off = (uint32_t)idx0 & 3u;
+    uint64_t g = idx0 >> 2;
+    uint4 r = philox4x32((uint32_t)g, (uint32_t)(g >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const uint32_t l = (off + (uint32_t)c) & 3u;
+        if (c > 0 && l == 0) {
+            ++g;
+            r = philox4x32((uint32_t)g, (uint32_t)(g >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        }
+        const uint32_t bits = l == 0 ? r.x : l == 1 ? r.y : l == 2 ? r.z : r.w;
+        s[c] = ((float)(bits >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    }
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                       // [256 tokens][128 B]   (64 hidden columns of this slice)
+    uint8_t* sK = sQ + 32768;
+    uint8_t* sV = sK + 32768;
+    uint8_t* sP = sV + 32768;                 // [4 key chunks][128 queries][128 B]
+    AttnBars* bars = reinterpret_cast<AttnBars*>(sP + 65536);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.x, slice = blockIdx.y;
+    const int S = a.S, d = a.d;
+    const int hps = 64 / d;                   // heads per 64-column slice
+    const int n_qt = (S + 127) / 128;
+    const int NS = (S + 15) / 16 * 16;        // score columns computed by the first MMA
+    const int units = hps * n_qt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_init(&bars->loaded, 1);
+        mbar_init(&bars->s_full, 1);
+        mbar_init(&bars->p_full, 128);
+        mbar_init(&bars->o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_o = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars->loaded, 3 * 32768);
+            tma_load_2d(sQ, &tmQKV, &bars->loaded, slice * 64, b * S);
+            tma_load_2d(sK, &tmQKV, &bars->loaded, a.H + slice * 64, b * S);
+            tma_load_2d(sV, &tmQKV, &bars->loaded, 2 * a.H + slice * 64, b * S);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = at_idesc(128, NS, 0, 0);
+            const uint32_t idesc_o = at_idesc(128, d, 0, 1);
+            const int ks_qk = d / 16;                        // K-steps of Q K^T
+            const int ks_pv = (S + 15) / 16;                 // K-steps of P V
+            mbar_wait(&bars->loaded, 0);
+            tc_fence_after();
+            auto issue_s = [&](int u) {
+                const int hh = u / n_qt, qt = u % n_qt;
+                const uint64_t qd = smem_desc_sw128(smem_u32(sQ + (size_t)qt * 128 * 128));
+                const uint64_t kd = smem_desc_sw128(smem_u32(sK));
+                for (int ks = 0; ks < ks_qk; ++ks)
+                    umma_bf16(tmem_base, smem_desc_advance(qd, (hh * d + ks * 16) * 2), smem_desc_advance(kd, (hh * d + ks * 16) * 2),
+                              idesc_s, (uint32_t)(ks != 0));
+                umma_commit(&bars->s_full);
+            };
+            issue_s(0);
+            for (int u = 0; u < units; ++u) {
+                const int hh = u / n_qt;
+                mbar_wait(&bars->p_full, (uint32_t)u & 1u);
+                tc_fence_after();
+                for (int ks = 0; ks < ks_pv; ++ks) {
+                    const uint64_t pd = smem_desc_advance(smem_desc_sw128(smem_u32(sP + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
+                    const uint64_t vd = at_desc_mn(smem_u32(sV + (size_t)ks * 2048 + (size_t)hh * d * 2), 0);
+                    umma_bf16(tmem_o, pd, vd, idesc_o, (uint32_t)(ks != 0));
+                }
+                umma_commit(&bars->o_full);
+                if (u + 1 < units) issue_s(u + 1);           // S of the next unit overlaps this unit's epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        const int q4 = warp % 4;
+        const int r = q4 * 32 + lane;                        // row of the query tile == TMEM lane
+        const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
+        // key-validity bits of this sequence: one ballot per 32 keys, shared through shared memory
+        if (q4 == 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int key = w * 32 + lane;
+                bool ok = key < S;
+                if (ok && a.key_valid) ok = a.key_valid[(size_t)b * S + key] != 0;
+                const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) bars->kvb[w] = bits;
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four softmax warps only
+        const int n_chunks = (NS + 31) / 32;
+        for (int u = 0; u < units; ++u) {
+            const int hh = u / n_qt, qt = u % n_qt;
+            const int head = slice * hps + hh;
+            const int qi = qt * 128 + r;                     // query position in the sequence
+            const bool q_ok = qi < S;
+            const long long bh = (long long)b * a.heads + head;
+            mbar_wait(&bars->s_full, (uint32_t)u & 1u);
+            tc_fence_after();
+            // ---- pass 1: row maximum of the masked, scaled scores
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
+                tmem_ld_wait();
+                const uint32_t bits = bars->kvb[ch];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int key = ch * 32 + c;
+                    float s = v[c] * a.scale;
+                    const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
+                    s = ok ? s : MASK_FILL;
+                    s = key < S ? s : -INFINITY;
+                    m = fmaxf(m, s);
+                }
+            }
+            // ---- pass 2: exp, row sum, dropout, P -> shared memory (bf16, 128B-swizzled K-major tile)
+            float l = 0.f;
+            const float m2 = m * LOG2E;
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
+                tmem_ld_wait();
+                const uint32_t bits = bars->kvb[ch];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int key = ch * 32 + c;
+                    float s = v[c] * a.scale;
+                    const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
+                    s = ok ? s : MASK_FILL;
+                    const float e = key < S ? exp2f(fmaf(s, LOG2E, -m2)) : 0.f;
+                    l += e;
+                    v[c] = e;
+                }
+                if (a.p_drop > 0.f) {
+                    float ds[32];
+                    dropout_scales32(a.seed, a.site, ((uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0)) * S + (uint64_t)(ch * 32), a.p_drop,
+                                     a.inv_keep, ds);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] *= ds[c];
+                }
+                uint8_t* chunk = sP + (size_t)(ch / 2) * 16384;     // 64 keys per chunk, this 32-key half = units (ch&1)*4 .. +3
+#pragma unroll
+                for (int u16 = 0; u16 < 4; ++u16) {
+                    uint4 w;
+                    w.x = at_pack(v[u16 * 8 + 0], v[u16 * 8 + 1]); w.y = at_pack(v[u16 * 8 + 2], v[u16 * 8 + 3]);
+                    w.z = at_pack(v[u16 * 8 + 4], v[u16 * 8 + 5]); w.w = at_pack(v[u16 * 8 + 6], v[u16 * 8 + 7]);
+                    *reinterpret_cast<uint4*>(chunk + sw128_offset(r, (ch & 1) * 4 + u16)) = w;
+                }
+            }
+            // a 16-key K-step may reach past the last 32-column chunk written above only if NS % 32 != 0: columns NS..+15 of
+            // that chunk were written (as zeros) because the loops run over whole 32-column chunks.
+            fence_proxy_async_smem();                         // make the generic-proxy P writes visible to the tensor core
+            tc_fence_before();
+            mbar_arrive(&bars->p_full);
+            // ---- O = P V done: normalise and store
+            mbar_wait(&bars->o_full, (uint32_t)u & 1u);
+            tc_fence_after();
+            const float inv_l = 1.0f / l;
+            if (a.stats && q_ok) {
+                a.stats[bh * S + qi] = m;
+                a.stats[(long long)a.B * a.heads * S + bh * S + qi] = l;
+            }
+            for (int c0 = 0; c0 < d; c0 += 16) {
+                float o[16];
+                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+                tmem_ld_wait();
+                if (q_ok) {
+                    __nv_bfloat16* dst = a.ctx + ((size_t)b * S + qi) * a.H + slice * 64 + hh * d + c0;
+                    uint4 w0, w1;
+                    w0.x = at_pack(o[0] * inv_l, o[1] * inv_l); w0.y = at_pack(o[2] * inv_l, o[3] * inv_l);
+                    w0.z = at_pack(o[4] * inv_l, o[5] * inv_l); w0.w = at_pack(o[6] * inv_l, o[7] * inv_l);
+                    w1.x = at_pack(o[8] * inv_l, o[9] * inv_l); w1.y = at_pack(o[10] * inv_l, o[11] * inv_l);
+                    w1.z = at_pack(o[12] * inv_l, o[13] * inv_l); w1.w = at_pack(o[14] * inv_l, o[15] * inv_l);
+                    reinterpret_cast<uint4*>(dst)[0] = w0;
+                    reinterpret_cast<uint4*>(dst)[1] = w1;
+                }
+            }
+            tc_fence_before();      // O (and S) TMEM reads are ordered before the MMAs of the next unit via p_full / o_full
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                                     float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
+                                     asme_stream_t stream) {
+    ASME_REQUIRE(qkv && ctx, "tc_attn_fwd: null argument");
+    ASME_REQUIRE(S >= 1 && S <= AT_MAXS, "tc_attn_fwd: S=%d unsupported (1..%d)", S, AT_MAXS);
+    ASME_REQUIRE(d == 16 || d == 32 || d == 64, "tc_attn_fwd: head dim %d unsupported (16, 32, 64)", d);
+    const int H = heads * d;
+    ASME_REQUIRE(H % 64 == 0, "tc_attn_fwd: hidden size %d must be a multiple of 64", H);
+    ASME_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "tc_attn_fwd: p_drop=%f", p_drop);
+    if (B == 0) return ASME_OK;
+    CUtensorMap tm;
+    int rc = asme_tc_make_tmap_bf16(&tm, qkv, (long long)B * S, 3 * H, 3 * H, 256);
+    if (rc) return rc;
+    AttnTcArgs a{};
+    a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
+    a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats;
+    const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnBars);
+    ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_fwd_kernel<<<dim3(B, H / 64), AT_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}

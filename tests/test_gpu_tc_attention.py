@@ -1,0 +1,64 @@
+"""Parity of the tensor-core attention kernels against the fp32 SIMT kernels (themselves pinned to the oracle's
+restatement of Attention.forward, transformer_layers.py:145-155, in test_gpu_kernels.py) on the same bf16-rounded q/k/v,
+with identical Philox dropout masks.  Tolerance: the probabilities are rounded to bf16 before the second MMA and the
+context is stored as bf16, i.e. 2^-8 relative per element -> 1e-2 of the output scale element-wise, 3e-3 in norm."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # B, S, heads, d
+    (3, 200, 2, 32), (2, 50, 2, 32), (2, 256, 1, 64), (2, 37, 4, 16), (1, 130, 4, 32), (5, 1, 2, 32), (2, 129, 2, 64)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asme_b200 import ops
+    return ops
+
+
+def make(gen, B, S, heads, d, pad="right"):
+    H = heads * d
+    qkv = (torch.randn(B * S, 3 * H, generator=gen, device="cuda") * 0.7).bfloat16()
+    lengths = torch.randint(1, S + 1, (B,), generator=gen, device="cuda")
+    lengths[0] = S
+    pos = torch.arange(S, device="cuda").unsqueeze(0)
+    valid = pos < lengths.unsqueeze(1) if pad == "right" else pos >= (S - lengths).unsqueeze(1)
+    return qkv, valid
+
+
+def norm_err(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("B,S,heads,d", CASES)
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("p_drop", [0.0, 0.2])
+def test_tc_attn_fwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
+    gen = torch.Generator(device="cuda").manual_seed(B * 1000 + S + heads + d)
+    qkv, valid = make(gen, B, S, heads, d)
+    ref, rst = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
+    got, gst = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
+    assert norm_err(got, ref) < 4e-3
+    torch.testing.assert_close(got.float(), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+    torch.testing.assert_close(gst[0], rst[0], rtol=1e-5, atol=1e-5)          # row max: fp32 accumulation noise only
+    torch.testing.assert_close(gst[1], rst[1], rtol=1e-4, atol=1e-5)          # row sum-exp
+
+
+def test_tc_attn_fwd_no_mask_and_fully_masked_rows(ops):
+    """bidirectional without a padding mask (key_valid = NULL) and left padding under a causal mask: rows left of the first
+    real token see no valid key and must attend uniformly to all S keys (-1e9 fill, quirk Q4)"""
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    B, S, heads, d = 3, 70, 2, 32
+    qkv, valid = make(gen, B, S, heads, d, pad="left")
+    ref, _ = ops.attn_fwd(qkv.float(), None, B, S, heads, False)
+    got, _ = ops.tc_attn_fwd(qkv, None, B, S, heads, False)
+    assert norm_err(got, ref) < 4e-3
+    ref, _ = ops.attn_fwd(qkv.float(), valid, B, S, heads, True)
+    got, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, True)
+    assert norm_err(got, ref) < 4e-3
+    H = heads * d
+    v = qkv.float().view(B, S, 3, heads, d)[:, :, 2]                          # (B,S,heads,d)
+    b = int((~valid[:, 0]).nonzero()[0])                                       # a sequence whose first position is padding
+    uniform = v[b].mean(dim=0).reshape(H)                                      # query 0 sees no valid key -> mean of all V rows
+    torch.testing.assert_close(got.float().view(B, S, H)[b, 0], uniform, rtol=2e-2, atol=2e-2)
