@@ -189,13 +189,38 @@ def algorithmic_cost(name, note):
     if name == "asme_b200_gemm_wgrad":
         M, N, K = g("M"), g("N"), g("K")
         return 4 * (M * N + M * K + N * K), 2 * M * N * K
+    if name == "asme_b200_tc_gemm":
+        M, N, K = g("M"), g("N"), g("K")
+        b = 2 * (M * K + N * K) + M * N * (4 * g("f32") + 2 * g("bf16") + 2 * g("pre") + 2 * g("aux") + 4 * g("res"))
+        return b, 2 * M * N * K
+    if name == "asme_b200_tc_wgrad":
+        M, N, K = g("M"), g("N"), g("K")
+        return 2 * (M * N + M * K) + 4 * N * K, 2 * M * N * K
+    if name == "asme_b200_tc_attn_fwd":
+        T, H, S = g("T"), g("H"), g("S")
+        return 2 * 4 * T * H, 4 * T * S * H
+    if name == "asme_b200_tc_attn_bwd":
+        T, H, S = g("T"), g("H"), g("S")
+        return 2 * 9 * T * H, 16 * T * S * H
+    if name == "asme_b200_cast_bf16":
+        n = g("rows") * g("ld")
+        return 6 * n, n
+    if name == "asme_b200_dropout_cast":
+        n = g("n")
+        return (4 + 2 + 4 * g("f32")) * n, n
+    if name in ("asme_b200_tc_score_topk",):
+        R, V, H, k = g("R"), g("V"), g("H"), g("k")
+        return 2 * (R * H + V * H) + 4 * V + R * (k * 8 + 8), 2 * R * V * H
+    if name == "asme_b200_tc_score_ce_partial":
+        R, V, H = g("R"), g("V"), g("H")
+        return 2 * (R * H + V * H) + 4 * V + 12 * R, 2 * R * V * H
     if name == "asme_b200_attn_fwd":
         T, H, S, heads = g("T"), g("H"), g("S"), g("heads")
         return 4 * 4 * T * H, 4 * T * S * H
     if name == "asme_b200_attn_bwd":
         T, H, S = g("T"), g("H"), g("S")
         return 4 * 8 * T * H, 10 * T * S * H
-    if name in ("asme_b200_layernorm_fwd",):
+    if name in ("asme_b200_layernorm_fwd", "asme_b200_layernorm_fwd_bf16"):
         M, H = g("M"), g("H")
         return 4 * 2 * M * H, 8 * M * H
     if name in ("asme_b200_layernorm_bwd",):
@@ -403,11 +428,13 @@ def main():
                "sample": f"{B_cpu} sequences of one C2 batch per step, median of 3 steps after 1 warm-up ({t_cpu:.2f} s/step); "
                          f"oracle/asme_oracle.py port of the reference path, dropout 0.2, fwd+CE+bwd+Adam"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16" if model.precision == "bf16" else "f32",
            "data": "synthetic",
            "config": {"workload": "C2 BERT4Rec cloze training, ML-1M shape", "items": cfg["V"], "seq_len": cfg["S"], "hidden": cfg["H"],
                       "layers": cfg["L"], "heads": cfg["heads"], "batch_per_gpu": cfg["B"], "global_batch": cfg["B"] * world,
                       "dropout": cfg["dropout"], "optimizer": "Adam(0.99,0.998) fused, LambdaLR warm-up",
+                      "precision": f"{model.precision}: tcgen05 GEMMs/attention/scoring with bf16 operands, fp32 accumulation, residual stream, LayerNorm, loss and Adam state",
                       "parallelism": f"dp{world}" if world > 1 else "single",
                       "l2": "inputs larger than L2: each step streams ~0.9 GB of activations (> 126 MB L2), 4 distinct batches rotate"},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -440,7 +467,7 @@ def bench_eval_c5(device, pk, steps=5, warmup=2):
     from asme_b200.metrics import FusedPredictions
 
     def step():
-        out = model.evaluate_rank(seq_d, seq_d.ne(0), {}, target_d, k=cfg["k"])
+        out = model.evaluate_rank(seq_d, seq_d.ne(0), {}, target_d, k=cfg["k"], full_rank=metrics.needs_full_rank())
         return metrics.update(seq_d, target_d, FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], V))
 
     for _ in range(warmup):
@@ -459,11 +486,11 @@ def bench_eval_c5(device, pk, steps=5, warmup=2):
     rec = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
     table, _ = summarise_kernels(rec, 1, pk)
-    score = next((r for r in table if r["kernel"] == "score_topk_rank"), None)
+    score = next((r for r in table if r["kernel"] in ("tc_score_topk", "score_topk_rank")), None)
     res = metrics.compute()
     return {"metric": "eval_users_per_sec", "value": B / (ms / 1e3), "unit": "users/s", "ms_per_step": ms,
             "config": {"workload": "C5 full-catalog scoring + top-k eval, synthetic 1M-item catalog", "items": V, "hidden": cfg["H"],
-                       "seq_len": S, "users_per_step": B, "k": cfg["k"], "dtype": "f32 (SIMT strict-parity path)"},
+                       "seq_len": S, "users_per_step": B, "k": cfg["k"], "dtype": model.precision},
             "recall@10": float(res["recall@10"]), "NDCG@10": float(res["NDCG@10"]),
             "scoring_kernel": None if score is None else {k: score[k] for k in ("avg_ms", "bound", "achieved", "peak", "unit", "frac", "share")}}
 

@@ -279,7 +279,13 @@ int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, int K, float
  * ------------------------------------------------------------------------------------------ */
 int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                           float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
+                          uint32_t* keep_bits /* (B*heads*S, 8) dropout keep bits for the backward pass, or NULL */,
                           asme_stream_t stream);
+/* d_qkv (B*S, 3H) bf16 from d_ctx (B*S, H) bf16; scores and dP are recomputed in tensor memory, transposed quantities come
+ * from transposed MMAs; needs the forward's ctx, stats and (when p_drop > 0) keep_bits */
+int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                          float p_drop, const void* ctx, const void* d_ctx, const float* stats,
+                          const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K13+K17  SASRec positive/negative dot products fused with the BCE loss

@@ -47,6 +47,8 @@ class LayerSaved:
     z: torch.Tensor = None
     a: torch.Tensor = None
     ctx16: torch.Tensor = None       # bf16 copies kept by the tensor-core path (GEMM operands of the backward pass)
+    keep: torch.Tensor = None        # dropout keep bits of the attention probabilities (tensor-core attention)
+    attn_tc: bool = False
 
 
 @dataclass
@@ -121,10 +123,16 @@ class EncoderEngine:
                                                       self._w(f"{pre}.input_sublayer.norm.bias"), save_stats=train)
             wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
             bqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,))
-            ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv)["f32"]
-            ls.ctx, ls.ast = ops.attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa, saved.seed,
-                                          self._site(l, 0), save_stats=train)
-            ls.ctx16 = ops.cast_bf16(ls.ctx, ld_out=H)
+            ls.attn_tc = S <= 256 and (H // cfg.heads) in (16, 32, 64)
+            if ls.attn_tc:      # tcgen05 attention straight on the bf16 QKV projection
+                ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv, out_f32=False, out_bf16=True)["bf16"]
+                ls.ctx16, ls.ast, ls.keep = ops.tc_attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa,
+                                                            saved.seed, self._site(l, 0), save_stats=train)
+            else:               # long sequences / odd head sizes: fp32 SIMT attention between tensor-core GEMMs
+                ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv)["f32"]
+                ls.ctx, ls.ast = ops.attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa, saved.seed,
+                                              self._site(l, 0), save_stats=train)
+                ls.ctx16 = ops.cast_bf16(ls.ctx, ld_out=H)
             ls.x2 = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
                                 bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,
                                 site=self._site(l, 1), residual=x)["f32"]
@@ -166,10 +174,16 @@ class EncoderEngine:
             _, do16 = ops.dropout_cast(dx2, p, saved.seed, 0, self._site(l, 1), want_f32=False)
             ops.tc_wgrad(do16, ls.ctx16, self._w(f"{pre}.attention.output_linear.weight", True),
                          self._w(f"{pre}.attention.output_linear.bias", True))
-            dctx = ops.tc_gemm(do16, m.weight_bf16(f"{pre}.attention.output_linear.weight"), b_is_kn=True)["f32"]
-            dqkv = ops.attn_bwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, ls.ctx, dctx, ls.ast, pa,
-                                saved.seed, self._site(l, 0))
-            dqkv16 = ops.cast_bf16(dqkv, ld_out=3 * H)
+            if ls.attn_tc:
+                dctx16 = ops.tc_gemm(do16, m.weight_bf16(f"{pre}.attention.output_linear.weight"), b_is_kn=True, out_f32=False,
+                                     out_bf16=True)["bf16"]
+                dqkv16 = ops.tc_attn_bwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, ls.ctx16, dctx16, ls.ast,
+                                         ls.keep, pa)
+            else:
+                dctx = ops.tc_gemm(do16, m.weight_bf16(f"{pre}.attention.output_linear.weight"), b_is_kn=True)["f32"]
+                dqkv = ops.attn_bwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, ls.ctx, dctx, ls.ast, pa,
+                                    saved.seed, self._site(l, 0))
+                dqkv16 = ops.cast_bf16(dqkv, ld_out=3 * H)
             wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
             dwqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H), g)
             dbqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,), g)

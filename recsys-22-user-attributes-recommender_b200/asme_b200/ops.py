@@ -442,18 +442,34 @@ def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optiona
 
 def tc_attn_fwd(qkv16: torch.Tensor, key_valid: Optional[torch.Tensor], B: int, S: int, heads: int, causal: bool,
                 p_drop: float = 0.0, seed: int = 0, site: int = 0, save_stats: bool = False):
-    """tensor-core attention: qkv16 (B*S, 3H) bf16 -> (ctx (B*S, H) bf16, stats (2, B*heads*S) or None)"""
+    """tensor-core attention: qkv16 (B*S, 3H) bf16 -> (ctx (B*S, H) bf16, stats (2, B*heads*S) or None,
+    keep_bits (B*heads*S, 8) int32 or None [dropout keep bits, saved for the backward pass])"""
     qkv16 = _bf16(qkv16, "qkv")
     H = qkv16.shape[1] // 3
     d = H // heads
     kv = _u8(key_valid)
     ctx = torch.empty(B * S, H, dtype=torch.bfloat16, device=qkv16.device)
     stats = torch.empty(2, B * heads * S, dtype=torch.float32, device=qkv16.device) if save_stats else None
+    keep = torch.empty(B * heads * S, 8, dtype=torch.int32, device=qkv16.device) if (save_stats and p_drop > 0) else None
     if _lib.timing is not None:
         _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
     _lib.call("asme_b200_tc_attn_fwd", _p(qkv16), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed), int(site),
-              _p(ctx), _p(stats), _stream())
-    return ctx, stats
+              _p(ctx), _p(stats), _p(keep), _stream())
+    return ctx, stats, keep
+
+
+def tc_attn_bwd(qkv16, key_valid, B, S, heads, causal, ctx16, d_ctx16, stats, keep_bits, p_drop=0.0):
+    """d_qkv (B*S, 3H) bf16"""
+    qkv16, ctx16, d_ctx16 = _bf16(qkv16, "qkv"), _bf16(ctx16, "ctx"), _bf16(d_ctx16, "d_ctx")
+    H = qkv16.shape[1] // 3
+    d = H // heads
+    kv = _u8(key_valid)
+    d_qkv = torch.empty_like(qkv16)
+    if _lib.timing is not None:
+        _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
+    _lib.call("asme_b200_tc_attn_bwd", _p(qkv16), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), _p(ctx16),
+              _p(d_ctx16), _p(stats), _p(keep_bits), _p(d_qkv), _stream())
+    return d_qkv
 
 
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):

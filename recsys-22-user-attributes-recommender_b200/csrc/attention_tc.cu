@@ -51,6 +51,7 @@ struct AttnTcArgs {
     unsigned int site;
     __nv_bfloat16* ctx;          // (B*S, H)
     float* stats;                // (2, B*heads*S) or NULL
+    uint32_t* keep_bits;         // (B*heads*S, 8) or NULL: bit j of word w of row (b,h,q) = key 32w+j survived the dropout
 };
 
 struct __align__(8) AttnBars {
@@ -214,8 +215,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid
                     float ds[32];
                     dropout_scales32(a.seed, a.site, ((uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0)) * S + (uint64_t)(ch * 32), a.p_drop,
                                      a.inv_keep, ds);
+                    uint32_t kb = 0;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] *= ds[c];
+                    for (int c = 0; c < 32; ++c) {
+                        v[c] *= ds[c];
+                        kb |= (ds[c] != 0.f ? 1u : 0u) << c;
+                    }
+                    if (a.keep_bits && q_ok) a.keep_bits[((size_t)bh * S + qi) * 8 + ch] = kb;
                 }
                 uint8_t* chunk = sP + (size_t)(ch / 2) * 16384;     // 64 keys per chunk, this 32-key half = units (ch&1)*4 .. +3
 #pragma unroll
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid
 
 extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                                      float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
-                                     asme_stream_t stream) {
+                                     uint32_t* keep_bits, asme_stream_t stream) {
     ASME_REQUIRE(qkv && ctx, "tc_attn_fwd: null argument");
     ASME_REQUIRE(S >= 1 && S <= AT_MAXS, "tc_attn_fwd: S=%d unsupported (1..%d)", S, AT_MAXS);
     ASME_REQUIRE(d == 16 || d == 32 || d == 64, "tc_attn_fwd: head dim %d unsupported (16, 32, 64)", d);
@@ -281,10 +287,309 @@ extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, 
     AttnTcArgs a{};
     a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
     a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-    a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats;
+    a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits;
     const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnBars);
     ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_tc_fwd_kernel<<<dim3(B, H / 64), AT_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+// One CTA = one sequence b x one 64-column slice (64/d heads); shared memory holds that slice of Q, K, V and dO for the
+// whole sequence (4 x 32 KB), two 128 x 128 bf16 operand tiles (2 x 32 KB), the per-query constants and the dropout bits.
+// Per head, two sweeps of 128 x 128 sub-tiles (MMAs: T1 = scores, T2 = dP, both recomputed in tensor memory):
+//   sweep A, rows = queries:  dS -> tile X;                 dQ[rows]  += X  K[cols]    (K consumed MN-major)
+//   sweep B, rows = keys   :  P^T.drop -> Y1, dS^T -> Y2;   dV[rows]  += Y1 dO[cols],  dK[rows] += Y2 Q[cols]
+// The transposed quantities come from transposed MMAs (K Q^T, V dO^T), never from a data transpose.  Gradients through
+// masked_fill positions are zero (the reference replaces the value), also in fully masked rows.
+struct AttnBwdArgs {
+    const uint8_t* key_valid;
+    int B, S, heads, d, H, causal;
+    float scale, p_drop, inv_keep;
+    const __nv_bfloat16* ctx;      // (B*S, H) forward output
+    const __nv_bfloat16* d_ctx;    // (B*S, H) (also read through its tensor map)
+    const float* stats;            // (2, B*heads*S)
+    const uint32_t* keep_bits;     // (B*heads*S, 8) or NULL when p_drop == 0
+    __nv_bfloat16* d_qkv;          // (B*S, 3H)
+};
+struct __align__(16) AttnBwdShared {
+    float4 qc[AT_MAXS];            // per query of the current head: {rowmax * log2e, 1 / rowsum, D = sum_d dO.O, 0}
+    uint32_t keep[AT_MAXS * 8];    // dropout keep bits of the current head
+    uint64_t loaded, t_full, x_full, acc_done;
+    uint32_t tmem_base;
+    uint32_t kvb[8];
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                    const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + 32768;
+    uint8_t* sV = sK + 32768;
+    uint8_t* sDO = sV + 32768;
+    uint8_t* sX = sDO + 32768;                // [2 chunks of 64 columns][128 rows][128 B]
+    uint8_t* sY = sX + 32768;
+    AttnBwdShared* sh = reinterpret_cast<AttnBwdShared*>(sY + 32768);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.x, slice = blockIdx.y;
+    const int S = a.S, d = a.d;
+    const int hps = 64 / d;
+    const int n_t = (S + 127) / 128;          // 128-wide tiles of the sequence (rows and columns alike)
+    const int subs_per_head = 2 * n_t * n_t;  // sweep A then sweep B
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        mbar_init(&sh->loaded, 1);
+        mbar_init(&sh->t_full, 1);
+        mbar_init(&sh->x_full, 128);
+        mbar_init(&sh->acc_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+    const uint32_t tm_t1 = tmem_base, tm_t2 = tmem_base + 128, tm_acc0 = tmem_base + 256, tm_acc1 = tmem_base + 320;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&sh->loaded, 4 * 32768);
+            tma_load_2d(sQ, &tmQKV, &sh->loaded, slice * 64, b * S);
+            tma_load_2d(sK, &tmQKV, &sh->loaded, a.H + slice * 64, b * S);
+            tma_load_2d(sV, &tmQKV, &sh->loaded, 2 * a.H + slice * 64, b * S);
+            tma_load_2d(sDO, &tmDO, &sh->loaded, slice * 64, b * S);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(&sh->loaded, 0);
+            tc_fence_after();
+            const int ks_d = d / 16;
+            // sub-tile i of a head: sweep = i / (n_t*n_t), rt = row tile, ct = column tile
+            auto issue_t = [&](int hh, int i) {
+                const int sweep = i / (n_t * n_t), rt = (i / n_t) % n_t, ct = i % n_t;
+                const int ncols = min(128, S - ct * 128);
+                const uint32_t idesc = at_idesc(128, (ncols + 15) / 16 * 16, 0, 0);
+                // sweep A: T1 = Q[rt] K[ct]^T, T2 = dO[rt] V[ct]^T      sweep B: T1 = K[rt] Q[ct]^T, T2 = V[rt] dO[ct]^T
+                uint8_t* a1 = sweep == 0 ? sQ : sK;
+                uint8_t* b1 = sweep == 0 ? sK : sQ;
+                uint8_t* a2 = sweep == 0 ? sDO : sV;
+                uint8_t* b2 = sweep == 0 ? sV : sDO;
+                const uint32_t koff = (uint32_t)(hh * d * 2);
+                for (int ks = 0; ks < ks_d; ++ks)
+                    umma_bf16(tm_t1, smem_desc_advance(smem_desc_sw128(smem_u32(a1 + (size_t)rt * 16384)), koff + ks * 32),
+                              smem_desc_advance(smem_desc_sw128(smem_u32(b1 + (size_t)ct * 16384)), koff + ks * 32), idesc, (uint32_t)(ks != 0));
+                for (int ks = 0; ks < ks_d; ++ks)
+                    umma_bf16(tm_t2, smem_desc_advance(smem_desc_sw128(smem_u32(a2 + (size_t)rt * 16384)), koff + ks * 32),
+                              smem_desc_advance(smem_desc_sw128(smem_u32(b2 + (size_t)ct * 16384)), koff + ks * 32), idesc, (uint32_t)(ks != 0));
+                umma_commit(&sh->t_full);
+            };
+            int g = 0;                                        // global sub-tile counter (barrier phases)
+            issue_t(0, 0);
+            for (int hh = 0; hh < hps; ++hh) {
+                for (int i = 0; i < subs_per_head; ++i, ++g) {
+                    const int sweep = i / (n_t * n_t), ct = i % n_t;
+                    const int ncols = min(128, S - ct * 128);
+                    const int ks_c = (ncols + 15) / 16;
+                    const uint32_t idesc_acc = at_idesc(128, d, 0, 1);
+                    mbar_wait(&sh->x_full, (uint32_t)g & 1u);
+                    tc_fence_after();
+                    const uint32_t acc_on = ct != 0;          // first column tile of a row tile overwrites the accumulators
+                    const uint32_t coff = (uint32_t)(hh * d * 2);
+                    for (int ks = 0; ks < ks_c; ++ks) {
+                        const uint64_t xd = smem_desc_advance(smem_desc_sw128(smem_u32(sX + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
+                        uint8_t* bsrc = sweep == 0 ? sK : sQ;  // dQ += dS K        |  dK += dS^T Q
+                        const uint64_t bd = at_desc_mn(smem_u32(bsrc + (size_t)(ct * 128 + ks * 16) * 128 + coff), 0);
+                        umma_bf16(tm_acc0, xd, bd, idesc_acc, (uint32_t)(acc_on | (ks != 0)));
+                    }
+                    if (sweep == 1) {
+                        for (int ks = 0; ks < ks_c; ++ks) {   // dV += (P^T . drop) dO
+                            const uint64_t yd = smem_desc_advance(smem_desc_sw128(smem_u32(sY + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
+                            const uint64_t bd = at_desc_mn(smem_u32(sDO + (size_t)(ct * 128 + ks * 16) * 128 + coff), 0);
+                            umma_bf16(tm_acc1, yd, bd, idesc_acc, (uint32_t)(acc_on | (ks != 0)));
+                        }
+                    }
+                    umma_commit(&sh->acc_done);
+                    // next sub-tile's T MMAs (its t_full commit also covers the accumulate MMAs above)
+                    if (i + 1 < subs_per_head) issue_t(hh, i + 1);
+                    else if (hh + 1 < hps) issue_t(hh + 1, 0);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q4 = warp % 4;
+        const int r = q4 * 32 + lane;
+        const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
+        if (q4 == 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int key = w * 32 + lane;
+                bool ok = key < S;
+                if (ok && a.key_valid) ok = a.key_valid[(size_t)b * S + key] != 0;
+                const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) sh->kvb[w] = bits;
+            }
+        }
+        int g = 0;
+        for (int hh = 0; hh < hps; ++hh) {
+            const int head = slice * hps + hh;
+            const long long bh = (long long)b * a.heads + head;
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous head's constants no longer in use
+            // per-query constants and dropout bits of this head
+            for (int q = r; q < S; q += 128) {
+                const __nv_bfloat16* o = a.ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
+                const __nv_bfloat16* go = a.d_ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
+                float D = 0.f;
+                for (int c = 0; c < d; c += 8) {
+                    const uint4 ov = *reinterpret_cast<const uint4*>(o + c);
+                    const uint4 gv = *reinterpret_cast<const uint4*>(go + c);
+                    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
+                        const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
+                        D += __low2float(o2) * __low2float(g2) + __high2float(o2) * __high2float(g2);
+                    }
+                }
+                const float m = a.stats[bh * S + q];
+                const float l = a.stats[(long long)a.B * a.heads * S + bh * S + q];
+                sh->qc[q] = make_float4(m * LOG2E, 1.0f / l, D, 0.f);
+                if (a.keep_bits) {
+                    const uint4* kb = reinterpret_cast<const uint4*>(a.keep_bits + ((size_t)bh * S + q) * 8);
+                    reinterpret_cast<uint4*>(sh->keep + q * 8)[0] = kb[0];
+                    reinterpret_cast<uint4*>(sh->keep + q * 8)[1] = kb[1];
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = 0; i < subs_per_head; ++i, ++g) {
+                const int sweep = i / (n_t * n_t), rt = (i / n_t) % n_t, ct = i % n_t;
+                const int row = rt * 128 + r;                  // sweep A: query, sweep B: key
+                const bool row_ok = row < S;
+                const int ncols = min(128, S - ct * 128);
+                const int n_chunks = (ncols + 31) / 32;
+                mbar_wait(&sh->t_full, (uint32_t)g & 1u);
+                tc_fence_after();
+                float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
+                if (sweep == 0 && row_ok) rc = sh->qc[row];
+                const bool key_row_ok = sweep == 1 && row_ok && ((sh->kvb[row >> 5] >> (row & 31)) & 1u);
+#pragma unroll 1
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    float t1[32], t2[32];
+                    tmem_ld32(tm_t1 + lane_addr + (uint32_t)(ch * 32), t1);
+                    tmem_ld32(tm_t2 + lane_addr + (uint32_t)(ch * 32), t2);
+                    tmem_ld_wait();
+                    uint32_t keep_w = 0xffffffffu, kv_w = 0;
+                    if (sweep == 0) {
+                        kv_w = sh->kvb[ct * 4 + ch];
+                        if (a.keep_bits && row_ok) keep_w = sh->keep[row * 8 + ct * 4 + ch];
+                    }
+                    float pd[32], ds[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int col = ct * 128 + ch * 32 + c;           // sweep A: key, sweep B: query
+                        float p = 0.f, dsv = 0.f, pdv = 0.f;
+                        if (sweep == 0) {
+                            const bool ok = ((kv_w >> c) & 1u) && (!a.causal || col <= row);
+                            const float sc = ok ? t1[c] * a.scale : MASK_FILL;
+                            p = (col < S && row_ok) ? exp2f(fmaf(sc, LOG2E, -rc.x)) * rc.y : 0.f;
+                            const float keep = ((keep_w >> c) & 1u) ? a.inv_keep : 0.f;
+                            dsv = ok ? p * (t2[c] * keep - rc.z) * a.scale : 0.f;
+                        } else {
+                            const bool col_ok = col < S;
+                            const float4 cc = col_ok ? sh->qc[col] : make_float4(0.f, 1.f, 0.f, 0.f);
+                            const bool ok = key_row_ok && col_ok && (!a.causal || row <= col);
+                            const float sc = ok ? t1[c] * a.scale : MASK_FILL;
+                            p = (col_ok && row_ok) ? exp2f(fmaf(sc, LOG2E, -cc.x)) * cc.y : 0.f;
+                            float keep = a.inv_keep;
+                            if (a.keep_bits && col_ok) keep = ((sh->keep[col * 8 + (row >> 5)] >> (row & 31)) & 1u) ? a.inv_keep : 0.f;
+                            pdv = p * keep;
+                            dsv = ok ? p * (t2[c] * keep - cc.z) * a.scale : 0.f;
+                        }
+                        pd[c] = pdv;
+                        ds[c] = dsv;
+                    }
+                    uint8_t* xchunk = sX + (size_t)(ch / 2) * 16384;
+                    uint8_t* ychunk = sY + (size_t)(ch / 2) * 16384;
+#pragma unroll
+                    for (int u16 = 0; u16 < 4; ++u16) {
+                        uint4 w;
+                        w.x = at_pack(ds[u16 * 8 + 0], ds[u16 * 8 + 1]); w.y = at_pack(ds[u16 * 8 + 2], ds[u16 * 8 + 3]);
+                        w.z = at_pack(ds[u16 * 8 + 4], ds[u16 * 8 + 5]); w.w = at_pack(ds[u16 * 8 + 6], ds[u16 * 8 + 7]);
+                        *reinterpret_cast<uint4*>(xchunk + sw128_offset(r, (ch & 1) * 4 + u16)) = w;
+                        if (sweep == 1) {
+                            w.x = at_pack(pd[u16 * 8 + 0], pd[u16 * 8 + 1]); w.y = at_pack(pd[u16 * 8 + 2], pd[u16 * 8 + 3]);
+                            w.z = at_pack(pd[u16 * 8 + 4], pd[u16 * 8 + 5]); w.w = at_pack(pd[u16 * 8 + 6], pd[u16 * 8 + 7]);
+                            *reinterpret_cast<uint4*>(ychunk + sw128_offset(r, (ch & 1) * 4 + u16)) = w;
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&sh->x_full);
+                if (ct == n_t - 1) {
+                    // all column tiles of this row tile accumulated: store dQ (sweep A) or dK, dV (sweep B)
+                    mbar_wait(&sh->acc_done, (uint32_t)g & 1u);
+                    tc_fence_after();
+                    const int n_out = sweep == 0 ? 1 : 2;
+                    for (int which = 0; which < n_out; ++which) {
+                        const uint32_t tm = which == 0 ? tm_acc0 : tm_acc1;
+                        const int col0 = (sweep == 0 ? 0 : (which == 0 ? a.H : 2 * a.H)) + slice * 64 + hh * d;
+                        for (int c0 = 0; c0 < d; c0 += 16) {
+                            float o[16];
+                            tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
+                            tmem_ld_wait();
+                            if (row_ok) {
+                                __nv_bfloat16* dst = a.d_qkv + ((size_t)b * S + row) * 3 * a.H + col0 + c0;
+                                uint4 w0, w1;
+                                w0.x = at_pack(o[0], o[1]); w0.y = at_pack(o[2], o[3]); w0.z = at_pack(o[4], o[5]); w0.w = at_pack(o[6], o[7]);
+                                w1.x = at_pack(o[8], o[9]); w1.y = at_pack(o[10], o[11]); w1.z = at_pack(o[12], o[13]); w1.w = at_pack(o[14], o[15]);
+                                reinterpret_cast<uint4*>(dst)[0] = w0;
+                                reinterpret_cast<uint4*>(dst)[1] = w1;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+extern "C" int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                                     float p_drop, const void* ctx, const void* d_ctx, const float* stats,
+                                     const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream) {
+    ASME_REQUIRE(qkv && ctx && d_ctx && stats && d_qkv, "tc_attn_bwd: null argument");
+    ASME_REQUIRE(S >= 1 && S <= AT_MAXS, "tc_attn_bwd: S=%d unsupported (1..%d)", S, AT_MAXS);
+    ASME_REQUIRE(d == 16 || d == 32 || d == 64, "tc_attn_bwd: head dim %d unsupported (16, 32, 64)", d);
+    const int H = heads * d;
+    ASME_REQUIRE(H % 64 == 0, "tc_attn_bwd: hidden size %d must be a multiple of 64", H);
+    ASME_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "tc_attn_bwd: p_drop=%f", p_drop);
+    ASME_REQUIRE(p_drop == 0.f || keep_bits, "tc_attn_bwd: keep_bits of the forward pass are required when p_drop > 0");
+    if (B == 0) return ASME_OK;
+    CUtensorMap tmQ, tmD;
+    int rc = asme_tc_make_tmap_bf16(&tmQ, qkv, (long long)B * S, 3 * H, 3 * H, 256);
+    if (rc) return rc;
+    rc = asme_tc_make_tmap_bf16(&tmD, d_ctx, (long long)B * S, H, H, 256);
+    if (rc) return rc;
+    AttnBwdArgs a{};
+    a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
+    a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    a.ctx = (const __nv_bfloat16*)ctx; a.d_ctx = (const __nv_bfloat16*)d_ctx; a.stats = stats;
+    a.keep_bits = p_drop > 0.f ? keep_bits : nullptr; a.d_qkv = (__nv_bfloat16*)d_qkv;
+    const size_t smem = 1024 + 6 * 32768 + sizeof(AttnBwdShared);
+    ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_tc_bwd_kernel<<<dim3(B, H / 64), AT_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

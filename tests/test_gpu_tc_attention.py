@@ -38,7 +38,7 @@ def test_tc_attn_fwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
     gen = torch.Generator(device="cuda").manual_seed(B * 1000 + S + heads + d)
     qkv, valid = make(gen, B, S, heads, d)
     ref, rst = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
-    got, gst = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
+    got, gst, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
     assert norm_err(got, ref) < 4e-3
     torch.testing.assert_close(got.float(), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
     torch.testing.assert_close(gst[0], rst[0], rtol=1e-5, atol=1e-5)          # row max: fp32 accumulation noise only
@@ -52,13 +52,52 @@ def test_tc_attn_fwd_no_mask_and_fully_masked_rows(ops):
     B, S, heads, d = 3, 70, 2, 32
     qkv, valid = make(gen, B, S, heads, d, pad="left")
     ref, _ = ops.attn_fwd(qkv.float(), None, B, S, heads, False)
-    got, _ = ops.tc_attn_fwd(qkv, None, B, S, heads, False)
+    got, _, _ = ops.tc_attn_fwd(qkv, None, B, S, heads, False)
     assert norm_err(got, ref) < 4e-3
     ref, _ = ops.attn_fwd(qkv.float(), valid, B, S, heads, True)
-    got, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, True)
+    got, _, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, True)
     assert norm_err(got, ref) < 4e-3
     H = heads * d
     v = qkv.float().view(B, S, 3, heads, d)[:, :, 2]                          # (B,S,heads,d)
     b = int((~valid[:, 0]).nonzero()[0])                                       # a sequence whose first position is padding
     uniform = v[b].mean(dim=0).reshape(H)                                      # query 0 sees no valid key -> mean of all V rows
     torch.testing.assert_close(got.float().view(B, S, H)[b, 0], uniform, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,S,heads,d", CASES)
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("p_drop", [0.0, 0.2])
+def test_tc_attn_bwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
+    """d_qkv of the tensor-core backward vs the fp32 SIMT backward fed with the same (bf16-valued) tensors and the same
+    dropout mask; bf16 rounding of P / dS / outputs -> 1e-2 in norm"""
+    gen = torch.Generator(device="cuda").manual_seed(B * 77 + S + heads + d)
+    qkv, valid = make(gen, B, S, heads, d)
+    H = heads * d
+    d_ctx = (torch.randn(B * S, H, generator=gen, device="cuda") * 0.5).bfloat16()
+    ctx_ref, st_ref = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, p_drop, 5, 23, save_stats=True)
+    want = ops.attn_bwd(qkv.float(), valid, B, S, heads, causal, ctx_ref, d_ctx.float(), st_ref, p_drop, 5, 23)
+    ctx, st, keep = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 5, 23, save_stats=True)
+    got = ops.tc_attn_bwd(qkv, valid, B, S, heads, causal, ctx, d_ctx, st, keep, p_drop)
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        if S == 1 and name != "dv":
+            # a single key: dQ = dK = 0 analytically (dS = P (dP - D) cancels); what is left on either side is the rounding
+            # residual of that cancellation -- bounded relative to the gradient scale instead of compared
+            assert float(got[:, sl].float().norm()) < 1e-2 * float(want.norm())
+            continue
+        err = float((got[:, sl].float() - want[:, sl]).norm() / (want[:, sl].norm() + 1e-3 * want.norm()))
+        assert err < 1.5e-2, f"{name}: relative norm error {err:.4f}"
+    # padded positions beyond each sequence's valid keys receive no dK / dV only through masked keys; rows must be finite
+    assert torch.isfinite(got.float()).all()
+
+
+def test_tc_attn_bwd_fully_masked_rows(ops):
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    B, S, heads, d = 3, 70, 2, 32
+    qkv, valid = make(gen, B, S, heads, d, pad="left")
+    H = heads * d
+    d_ctx = (torch.randn(B * S, H, generator=gen, device="cuda") * 0.5).bfloat16()
+    ctx_ref, st_ref = ops.attn_fwd(qkv.float(), valid, B, S, heads, True, save_stats=True)
+    want = ops.attn_bwd(qkv.float(), valid, B, S, heads, True, ctx_ref, d_ctx.float(), st_ref)
+    ctx, st, keep = ops.tc_attn_fwd(qkv, valid, B, S, heads, True, save_stats=True)
+    got = ops.tc_attn_bwd(qkv, valid, B, S, heads, True, ctx, d_ctx, st, keep)
+    assert norm_err(got, want) < 1.5e-2
