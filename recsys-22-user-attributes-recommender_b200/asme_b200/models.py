@@ -347,6 +347,33 @@ class TransformerRecommenderModel(ArenaModule):
         return out
 
 
+def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, rows: Optional[torch.Tensor] = None,
+                           select: str = "mask", mask_id: int = MASK_TOKEN_ID, full_rank: bool = False, group=None):
+    """vocab-sharded variant of :meth:`evaluate_rank` (asme_b200.sharded): this rank encodes ITS users, all ranks exchange the
+    selected hidden rows, every rank scores all users against its own slice of the catalog on the tensor cores, and the
+    per-shard top-k lists / target scores are merged with three NCCL calls.  Returns the rows of this rank's users."""
+    import torch.distributed as dist
+    from . import sharded
+    hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
+    if rows is None:
+        rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
+    m_rows, _ = self.modify(ops.gather_rows(hidden, rows))
+    G = dist.get_world_size(group) if dist.is_initialized() else 1
+    g = dist.get_rank(group) if dist.is_initialized() else 0
+    wb, b = self.projection_operands_bf16()
+    stamp = (self._arena.version, self._arena.flat._version, wb.data_ptr(), G, g)
+    if getattr(self, "_shard_cache", None) is None or self._shard_cache[0] != stamp:
+        v0, v1 = sharded.shard_range(wb.shape[0], G, g)
+        bias = None if b is None else b[v0:v1].clone()        # fresh allocation: 16-byte aligned whatever v0 is
+        self._shard_cache = (stamp, wb[v0:v1], bias, v0)
+    _, wb_s, bias_s, v0 = self._shard_cache
+    return sharded.sharded_topk_rank(m_rows, target, k, sharded.tc_local_scorer(wb_s, bias_s, v0), sharded.tc_merge,
+                                     full_rank=full_rank, group=group)
+
+
+TransformerRecommenderModel.evaluate_rank_sharded = torch.no_grad()(_evaluate_rank_sharded)
+
+
 def score_rows(m_rows, w, b, target, k):
     ts = ops.score_targets(m_rows, w, b, target)
     val, idx, ng, nt = ops.score_topk_rank(m_rows, w, b, k, target, ts)

@@ -40,6 +40,13 @@ struct Acc {
             if (c < H) add4(v[q], ldg4(row + c));
         }
     }
+    __device__ __forceinline__ void add_row_plain(const float* row, int H, int lane) {      // generic loads (shared memory)
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            const int c = lane * 4 + 128 * q;
+            if (c < H) add4(v[q], *reinterpret_cast<const float4*>(row + c));
+        }
+    }
     __device__ __forceinline__ void store(float* __restrict__ row, int H, int lane) const {
 #pragma unroll
         for (int q = 0; q < MAXQ; ++q) {
@@ -103,22 +110,48 @@ __global__ void __launch_bounds__(128) embgrad_chunk_kernel(const int* __restric
     if (lane == 0) flags[c] = fl;
 }
 
-__global__ void __launch_bounds__(128) embgrad_carry_kernel(const float* __restrict__ head, const float* __restrict__ tail,
-                                                            const int* __restrict__ tail_key, const int* __restrict__ flags,
-                                                            int chunks, int H, float* __restrict__ d_table) {
-    const int c = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-    const int lane = threadIdx.x % 32;
-    if (c >= chunks || !(flags[c] & 4)) return;
+// One CTA per chunk whose tail starts a run that continues into later chunks.  Long runs (PAD / MASK ids cover thousands
+// of tokens = hundreds of chunks) used to be summed by ONE warp, one dependent 256-byte load after another (~370 us per
+// call); now warp 0 finds the length of the run with ballots over the chunk flags, the CARRY_WARPS warps sum a strided
+// subset of the head partials each, and the warp partials are combined in a fixed order (deterministic).
+#define CARRY_WARPS 16
+__global__ void __launch_bounds__(CARRY_WARPS * 32) embgrad_carry_kernel(const float* __restrict__ head, const float* __restrict__ tail,
+                                                                         const int* __restrict__ tail_key,
+                                                                         const int* __restrict__ flags, int chunks, int H,
+                                                                         float* __restrict__ d_table) {
+    extern __shared__ float carry_smem[];      // [CARRY_WARPS][H]
+    __shared__ int run_len;
+    const int c = blockIdx.x;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (!(flags[c] & 4)) return;               // CTA-uniform
+    if (warp == 0) {
+        // number of following chunks that hold a head piece of this run
+        int len = 0;
+        for (int base = c + 1; base < chunks; base += 32) {
+            const int cc = base + lane;
+            const int f = cc < chunks ? flags[cc] : 0;
+            const unsigned full = __ballot_sync(0xffffffffu, (f & 3) == 3);     // head piece, run goes on
+            const unsigned any = __ballot_sync(0xffffffffu, (f & 1) != 0);      // head piece
+            const int n_full = full == 0xffffffffu ? 32 : __ffs(~full) - 1;     // leading chunks that continue the run
+            if (n_full == 32) { len += 32; continue; }
+            len += n_full + (((any >> n_full) & 1u) ? 1 : 0);                   // the last piece ends inside its chunk
+            break;
+        }
+        if (lane == 0) run_len = len;
+    }
+    __syncthreads();
+    const int len = run_len;
     Acc acc;
     acc.zero();
-    acc.add_row(tail + (size_t)c * H, H, lane);
-    for (int cc = c + 1; cc < chunks; ++cc) {
-        const int f = flags[cc];
-        if (!(f & 1)) break;
-        acc.add_row(head + (size_t)cc * H, H, lane);
-        if (!(f & 2)) break;
+    if (warp == 0) acc.add_row(tail + (size_t)c * H, H, lane);
+    for (int i = warp; i < len; i += CARRY_WARPS) acc.add_row(head + (size_t)(c + 1 + i) * H, H, lane);
+    acc.store(carry_smem + (size_t)warp * H, H, lane);
+    __syncthreads();
+    if (warp == 0) {
+        acc.zero();
+        for (int w = 0; w < CARRY_WARPS; ++w) acc.add_row_plain(carry_smem + (size_t)w * H, H, lane);
+        acc.add_to(d_table + (size_t)tail_key[c] * H, H, lane);
     }
-    acc.add_to(d_table + (size_t)tail_key[c] * H, H, lane);
 }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -170,7 +203,8 @@ extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const 
     embgrad_chunk_kernel<<<ceil_div(chunks, 4), 128, 0, st>>>(keys_out, vals_out, T, V, d_rows, H, d_table, head, tail, tail_key,
                                                               flags, chunks);
     ASME_LAUNCH_OK();
-    embgrad_carry_kernel<<<ceil_div(chunks, 4), 128, 0, st>>>(head, tail, tail_key, flags, chunks, H, d_table);
+    embgrad_carry_kernel<<<chunks, CARRY_WARPS * 32, (size_t)CARRY_WARPS * H * sizeof(float), st>>>(head, tail, tail_key, flags, chunks, H,
+                                                                                                   d_table);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

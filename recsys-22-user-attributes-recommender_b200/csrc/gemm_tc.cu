@@ -16,6 +16,8 @@ using namespace tc;
 
 #define G_BM 128
 #define G_THREADS 256          // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+#define G_NT 128               // output columns per CTA: 128 TMEM columns and ~33 KB of shared memory -> 4 CTAs per SM, whose loads,
+                               // MMAs and (latency-bound) epilogues overlap
 
 // instruction descriptor with selectable operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
 __host__ __device__ constexpr uint32_t idesc_major(int M, int N, int a_mn, int b_mn) {
@@ -71,7 +73,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// CTA (m_tile, n_tile): 128 rows x NT (<= 256) columns; K streamed in 64-wide chunks through a ring of `stages` slots
+// CTA (m_tile, n_tile): 128 rows x NT (<= G_NT) columns; K streamed in 64-wide chunks through a ring of `stages` slots
 // (slot = A chunk 16 KB + B chunk NT x 128 B [K-major] or ceil(NT/64) x 8 KB [MN-major]).
 template <bool B_MN>
 __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -80,12 +82,12 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int kch = a.K / CHUNK_K;
-    const int n0 = blockIdx.y * 256;
-    const int NT = min(256, a.N - n0);                   // columns of this CTA (multiple of 32)
+    const int n0 = blockIdx.y * G_NT;
+    const int NT = min(G_NT, a.N - n0);                   // columns of this CTA (multiple of 32)
     const int nblk = (NT + 63) / 64;
     const size_t a_bytes = (size_t)G_BM * 128;
-    const size_t b_bytes = B_MN ? (size_t)nblk * 64 * 128 : (size_t)min(256, a.N) * 128;   // = bytes the TMA boxes deliver (OOB rows are zero-filled)
-    const size_t b_slot = (size_t)256 * 128;             // slot stride sized for the widest tile: keeps every chunk 1024-aligned
+    const size_t b_bytes = B_MN ? (size_t)nblk * 64 * 128 : (size_t)min(G_NT, a.N) * 128;   // = bytes the TMA boxes deliver (OOB rows are zero-filled)
+    const size_t b_slot = (size_t)G_NT * 128;             // slot stride sized for the widest tile: keeps every chunk 1024-aligned
     const size_t slot = a_bytes + b_slot;
     GemmBars* bars = reinterpret_cast<GemmBars*>(smem + (size_t)stages * slot);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -256,9 +258,9 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     CUtensorMap tmA, tmB;
     int rc = asme_tc_make_tmap_bf16(&tmA, A, M, K, K, G_BM);
     if (rc) return rc;
-    // b_is_kn = 0: B is (N,K) row-major (nn.Linear weight, C = A B^T): box 64 x min(N,256) rows.
+    // b_is_kn = 0: B is (N,K) row-major (nn.Linear weight, C = A B^T): box 64 x min(N,G_NT) rows.
     // b_is_kn = 1: B is (K,N) row-major (C = A B): box 64 columns x 64 K rows.
-    rc = b_is_kn ? asme_tc_make_tmap_bf16(&tmB, B, K, N, N, 64) : asme_tc_make_tmap_bf16(&tmB, B, N, K, K, N < 256 ? N : 256);
+    rc = b_is_kn ? asme_tc_make_tmap_bf16(&tmB, B, K, N, N, 64) : asme_tc_make_tmap_bf16(&tmB, B, N, K, K, N < G_NT ? N : G_NT);
     if (rc) return rc;
     TcGemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act; a.gelu_grad_of = (const __nv_bfloat16*)gelu_grad_of;
@@ -266,9 +268,9 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     a.out_bf16 = (__nv_bfloat16*)out_bf16; a.pre_act_bf16 = (__nv_bfloat16*)pre_act_bf16; a.ld_bf16 = ld_bf16;
     const int kch = K / 64;
     const int stages = kch < G_STAGES ? kch : G_STAGES;
-    const size_t smem = 1024 + (size_t)stages * ((size_t)G_BM * 128 + 256 * 128) + sizeof(GemmBars);
+    const size_t smem = 1024 + (size_t)stages * ((size_t)G_BM * 128 + G_NT * 128) + sizeof(GemmBars);
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid(ceil_div(M, G_BM), ceil_div(N, 256));
+    const dim3 grid(ceil_div(M, G_BM), ceil_div(N, G_NT));
     if (b_is_kn) {
         ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_gemm_tall_kernel<true><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
@@ -289,6 +291,7 @@ struct TcWgradArgs {
     int M, N, K;               // M tokens; output is (N, K)
     int slabs_per_split, n_slabs;
     float* partial;            // [splits][N][K]
+    float* partial_bias;       // [splits][N] or NULL: column sums of dY, computed by one extra N=16 MMA against a ones column
 };
 struct __align__(8) WgradBars {
     uint64_t full[W_STAGES];
@@ -309,13 +312,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
     const int nb_x = KT / 64;
     const size_t blk = (size_t)W_SLAB * 128;             // one 64-column block of one slab: 64 tokens x 128 B
     const size_t stage_bytes = (size_t)(2 + 4) * blk;    // 2 dY blocks + up to 4 X blocks (fixed slot size)
-    WgradBars* bars = reinterpret_cast<WgradBars*>(smem + W_STAGES * stage_bytes);
+    uint8_t* sOnes = smem + W_STAGES * stage_bytes;      // [64 tokens][128 B]: bf16 1.0 in column 0 (MN-major B of the bias MMA)
+    WgradBars* bars = reinterpret_cast<WgradBars*>(sOnes + blk);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int split = blockIdx.x;
     const int s0 = split * a.slabs_per_split;
     const int s1 = min(a.n_slabs, s0 + a.slabs_per_split);
+    const bool do_bias = a.partial_bias != nullptr && blockIdx.z == 0;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < KT) tmem_cols <<= 1;
+    while ((int)tmem_cols < KT + (do_bias ? 16 : 0)) tmem_cols <<= 1;
+    if (do_bias) {
+        for (int i = threadIdx.x; i < (int)(blk / 16); i += blockDim.x) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (threadIdx.x < W_SLAB) *reinterpret_cast<uint16_t*>(sOnes + sw128_offset(threadIdx.x, 0)) = 0x3F80;   // bf16(1.0)
+        fence_proxy_async_smem();
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
@@ -351,6 +362,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
         if (lane == 0) {
             // A = dY^T (M-dim = dY columns, MN-major), B = X^T viewed as [N = X columns][K = tokens] (MN-major)
             const uint32_t idesc = idesc_major(128, KT, 1, 1);
+            const uint32_t idesc_b = idesc_major(128, 16, 1, 1);
             int i = 0;
             for (int sl = s0; sl < s1; ++sl, ++i) {
                 const int s = i % W_STAGES;
@@ -363,6 +375,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
                     const uint64_t ad = smem_desc_mn_sw128(smem_u32(base + (size_t)ks * 2048), (uint32_t)blk);
                     const uint64_t bd = smem_desc_mn_sw128(smem_u32(base + 2 * blk + (size_t)ks * 2048), (uint32_t)blk);
                     umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((i | ks) != 0));
+                    if (do_bias)
+                        umma_bf16(tmem_base + (uint32_t)KT, ad, smem_desc_mn_sw128(smem_u32(sOnes + (size_t)ks * 2048), 0), idesc_b,
+                                  (uint32_t)((i | ks) != 0));
                 }
                 umma_commit(&bars->empty[s]);
             }
@@ -385,6 +400,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
                     *reinterpret_cast<float4*>(out + (size_t)n * a.K + kcol0 + k0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
             }
         }
+        if (do_bias) {
+            float v[16];
+            tmem_ld16(lane_addr + (uint32_t)KT, v);
+            tmem_ld_wait();
+            if (n < a.N) a.partial_bias[(size_t)split * a.N + n] = v[0];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -394,34 +415,35 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
     }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long long n, float* __restrict__ out, int accumulate) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= n) return;
+// out[i] (+)= sum over splits of partial[split][i]: 32 float4 columns x 8 split groups per block, fixed summation order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long long n,
+                                                           float* __restrict__ out, int accumulate) {
+    __shared__ float4 red[8][32];
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    const long long i = ((long long)blockIdx.x * 32 + tx) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < splits; ++p) add4(s, ldg4(partial + (size_t)p * n + i));
-    float4* o = reinterpret_cast<float4*>(out + i);
-    if (accumulate) {
-        const float4 c = *o;
-        s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+    if (i < n) {
+        float4 s1 = s;
+        int p = ty;
+        for (; p + 8 < splits; p += 16) {
+            add4(s, ldg4(partial + (size_t)p * n + i));
+            add4(s1, ldg4(partial + (size_t)(p + 8) * n + i));
+        }
+        if (p < splits) add4(s, ldg4(partial + (size_t)p * n + i));
+        add4(s, s1);
     }
-    *o = s;
-}
-
-// column sums of a bf16 matrix (bias gradients): two-stage, deterministic.  out[n] (+)= sum_m x[m,n]
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, int rows_per_block, float* __restrict__ partial) {
-    const int n = blockIdx.y * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += __bfloat162float(x[(size_t)r * N + n]);
-    partial[(size_t)blockIdx.x * N + n] = s;
-}
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, int N, float* __restrict__ out, int accumulate) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * N + n];
-    out[n] = accumulate ? out[n] + s : s;
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < n) {
+#pragma unroll
+        for (int g = 1; g < 8; ++g) add4(s, red[g][tx]);
+        float4* o = reinterpret_cast<float4*>(out + i);
+        if (accumulate) {
+            const float4 c = *o;
+            s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+        }
+        *o = s;
+    }
 }
 
 static int wgrad_splits(int M) {
@@ -429,10 +451,8 @@ static int wgrad_splits(int M) {
     const int s = n_slabs < ASME_NUM_SMS ? n_slabs : ASME_NUM_SMS;
     return ceil_div(n_slabs, ceil_div(n_slabs, s));      // no empty splits
 }
-#define COLSUM_BLOCKS 296
-
 extern "C" size_t asme_b200_tc_wgrad_workspace_bytes(int M, int N, int K) {
-    return ((size_t)wgrad_splits(M < 1 ? 1 : M) * N * K + (size_t)COLSUM_BLOCKS * N) * sizeof(float);
+    return ((size_t)wgrad_splits(M < 1 ? 1 : M) * N * K + (size_t)wgrad_splits(M < 1 ? 1 : M) * N) * sizeof(float);
 }
 
 extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, int K, float* dW, float* dbias, int accumulate,
@@ -453,22 +473,18 @@ extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, i
     const int splits = wgrad_splits(M);
     a.slabs_per_split = ceil_div(a.n_slabs, splits);
     a.partial = (float*)ws;
+    a.partial_bias = dbias ? a.partial + (size_t)splits * N * K : nullptr;
     const size_t stage_bytes = (size_t)(2 + 4) * W_SLAB * 128;
-    const size_t smem = 1024 + W_STAGES * stage_bytes + sizeof(WgradBars);
+    const size_t smem = 1024 + W_STAGES * stage_bytes + (size_t)W_SLAB * 128 + sizeof(WgradBars);
     cudaStream_t st = (cudaStream_t)stream;
     ASME_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<<<dim3(splits, ceil_div(N, 128), ceil_div(K, 256)), G_THREADS, smem, st>>>(tmY, tmX, a);
     ASME_LAUNCH_OK();
     const long long n = (long long)N * K;
-    wgrad_reduce_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(a.partial, splits, n, dW, accumulate);
+    wgrad_reduce_kernel<<<ceil_div(n / 4, 32), 256, 0, st>>>(a.partial, splits, n, dW, accumulate);
     ASME_LAUNCH_OK();
     if (dbias) {
-        float* cp = a.partial + (size_t)splits * N * K;
-        const int rpb = ceil_div(M, COLSUM_BLOCKS);
-        const int blocks = ceil_div(M, rpb);
-        colsum_bf16_kernel<<<dim3(blocks, ceil_div(N, 64)), 64, 0, st>>>((const __nv_bfloat16*)dY, M, N, rpb, cp);
-        ASME_LAUNCH_OK();
-        colsum_final_kernel<<<ceil_div(N, 128), 128, 0, st>>>(cp, blocks, N, dbias, accumulate);
+        wgrad_reduce_kernel<<<ceil_div(N / 4, 32), 256, 0, st>>>(a.partial_bias, splits, N, dbias, accumulate);
         ASME_LAUNCH_OK();
     }
     return ASME_OK;

@@ -333,19 +333,36 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ x, int M, int N, 
     for (int m = m0; m < m1; ++m) s += x[(size_t)m * N + n];
     partial[(size_t)blockIdx.y * N + n] = s;
 }
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out,
-                                     int accumulate) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * N + n];
-    out[n] = accumulate ? out[n] + s : s;
+// out[n] (+)= sum_c partial[c][n].  Launched with 128 threads per block: 32 columns x 4 chunk groups (the single-thread loop
+// over several hundred partial rows used to take ~30 us per call); fixed summation order -> deterministic.
+__global__ void __launch_bounds__(128) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N,
+                                                            float* __restrict__ out, int accumulate) {
+    __shared__ float red[4][32];
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    const int n = blockIdx.x * 32 + tx;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (n < N) {
+        int c = ty;
+        for (; c + 12 < chunks; c += 16) {
+            s0 += partial[(size_t)c * N + n];
+            s1 += partial[(size_t)(c + 4) * N + n];
+            s2 += partial[(size_t)(c + 8) * N + n];
+            s3 += partial[(size_t)(c + 12) * N + n];
+        }
+        for (; c < chunks; c += 4) s0 += partial[(size_t)c * N + n];
+    }
+    red[ty][tx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        const float s = (red[0][tx] + red[1][tx]) + (red[2][tx] + red[3][tx]);
+        out[n] = accumulate ? out[n] + s : s;
+    }
 }
 
 static int launch_colsum(const float* x, int M, int N, float* out, int accumulate, void* ws, size_t ws_bytes,
                          cudaStream_t stream) {
     if (M <= COLSUM_ROWS) {   // small: single stage
-        colsum_stage2_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(x, M, N, out, accumulate);
+        colsum_stage2_kernel<<<ceil_div(N, 32), 128, 0, stream>>>(x, M, N, out, accumulate);
         ASME_LAUNCH_OK();
         return ASME_OK;
     }
@@ -357,7 +374,7 @@ static int launch_colsum(const float* x, int M, int N, float* out, int accumulat
     float* partial = (float*)ws;
     colsum_stage1_kernel<<<dim3(ceil_div(N, 128), chunks), 128, 0, stream>>>(x, M, N, partial);
     ASME_LAUNCH_OK();
-    colsum_stage2_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(partial, chunks, N, out, accumulate);
+    colsum_stage2_kernel<<<ceil_div(N, 32), 128, 0, stream>>>(partial, chunks, N, out, accumulate);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -459,7 +476,7 @@ extern "C" int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H
 #undef CALL
     ASME_LAUNCH_OK();
     if (dln) {
-        colsum_stage2_kernel<<<ceil_div(4 * H, 128), 128, 0, (cudaStream_t)stream>>>(partials, grid, 4 * H, dln, 1);
+        colsum_stage2_kernel<<<ceil_div(4 * H, 32), 128, 0, (cudaStream_t)stream>>>(partials, grid, 4 * H, dln, 1);
         ASME_LAUNCH_OK();
     }
     return ASME_OK;
@@ -519,7 +536,7 @@ extern "C" int asme_b200_layernorm_bwd(const float* dy, const float* x, const fl
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
-    colsum_stage2_kernel<<<ceil_div(2 * H, 128), 128, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
+    colsum_stage2_kernel<<<ceil_div(2 * H, 32), 128, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
