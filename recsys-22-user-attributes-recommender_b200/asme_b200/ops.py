@@ -450,7 +450,7 @@ def tc_attn_fwd(qkv16: torch.Tensor, key_valid: Optional[torch.Tensor], B: int, 
     kv = _u8(key_valid)
     ctx = torch.empty(B * S, H, dtype=torch.bfloat16, device=qkv16.device)
     stats = torch.empty(2, B * heads * S, dtype=torch.float32, device=qkv16.device) if save_stats else None
-    keep = torch.empty(B * heads * S, 8, dtype=torch.int32, device=qkv16.device) if (save_stats and p_drop > 0) else None
+    keep = torch.zeros(B * heads * S, 8, dtype=torch.int32, device=qkv16.device) if (save_stats and p_drop > 0) else None
     if _lib.timing is not None:
         _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
     _lib.call("asme_b200_tc_attn_fwd", _p(qkv16), _p(kv), B, S, heads, d, 1 if causal else 0, float(p_drop), int(seed), int(site),

@@ -63,31 +63,54 @@ struct __align__(8) AttnBars {
     uint32_t kvb[8];             // key-validity bits of the sequence (bit j of word w: key 32w+j may be attended)
 };
 
-// dropout scales of 32 consecutive elements idx0 .. idx0+31 of a site (element-indexed Philox stream of common.cuh)
-__device__ __forceinline__ void dropout_scales32(uint64_t seed, uint32_t site, uint64_t idx0, float p, float inv_keep, float (&s)[32]) {
-    const uint32_t off = (uint32_t)idx0 & 3u;
-    uint64_t g = idx0 >> 2;
-    uint4 r = philox4x32((uint32_t)g, (uint32_t)(g >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+// ---- dropout stream of the tensor-core attention ----------------------------------------------------------------
+// Two 16-bit keep decisions per 32-bit hash (lowbias32 finaliser) of (row key, 32-key chunk, pair): ~5 instructions per
+// element instead of ~15 for an element-indexed Philox4x32-7.  The backward pass never regenerates the stream -- the forward
+// stores the keep bits (1 bit per (query, key)) -- so the only contract is "Bernoulli(1-p), independent per element".
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+    return x;
+}
+__device__ __forceinline__ uint32_t drop_rowkey(uint64_t seed, uint32_t site, uint64_t row) {
+    return lowbias32((uint32_t)row ^ (uint32_t)seed) ^ lowbias32((uint32_t)(row >> 32) ^ (uint32_t)(seed >> 32) ^ (site * 0x9E3779B9u));
+}
+// keep bits of the 32 keys of chunk `ch` of one row (bit c = key ch*32+c survives)
+__device__ __forceinline__ uint32_t drop_keep_bits32(uint32_t rowkey, int ch, uint32_t thr16) {
+    uint32_t kb = 0;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const uint32_t l = (off + (uint32_t)c) & 3u;
-        if (c > 0 && l == 0) {
-            ++g;
-            r = philox4x32((uint32_t)g, (uint32_t)(g >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-        }
-        const uint32_t bits = l == 0 ? r.x : l == 1 ? r.y : l == 2 ? r.z : r.w;
-        s[c] = ((float)(bits >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t x = lowbias32(rowkey + (uint32_t)(ch * 16 + j) * 0x9E3779B9u);
+        kb |= ((x & 0xffffu) >= thr16 ? 1u : 0u) << (2 * j);
+        kb |= ((x >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
     }
+    return kb;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs a) {
+#define ATF_THREADS 384        // warp 0 TMA, 1 MMA, 2 TMEM alloc, warps 4-7 and 8-11: two softmax warpgroups
+struct __align__(8) AttnFwdShared {
+    uint64_t loaded, s_full, p_full, o_full;
+    uint32_t tmem_base;
+    uint32_t kvb[8];             // key-validity bits of the sequence (bit j of word w: key 32w+j may be attended)
+    float xm[2][128];            // per-warpgroup partial row max   (units of log2: score * scale * log2e)
+    float xl[2][128];            // per-warpgroup partial row sum
+};
+
+// Both warpgroups own all 128 query rows of the tile (TMEM lane = row) and split the key columns in halves; partial row
+// maxima / sums are exchanged through shared memory.  Two warps per SM sub-partition hide each other's TMEM-load, MUFU and
+// shared-memory latencies (the one-warpgroup version issued on 25 % of the cycles).
+__global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                       // [256 tokens][128 B]   (64 hidden columns of this slice)
     uint8_t* sK = sQ + 32768;
     uint8_t* sV = sK + 32768;
     uint8_t* sP = sV + 32768;                 // [4 key chunks][128 queries][128 B]
-    AttnBars* bars = reinterpret_cast<AttnBars*>(sP + 65536);
+    AttnFwdShared* sh = reinterpret_cast<AttnFwdShared*>(sP + 65536);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int b = blockIdx.x, slice = blockIdx.y;
     const int S = a.S, d = a.d;
@@ -98,25 +121,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQKV);
-        mbar_init(&bars->loaded, 1);
-        mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->p_full, 128);
-        mbar_init(&bars->o_full, 1);
+        mbar_init(&sh->loaded, 1);
+        mbar_init(&sh->s_full, 1);
+        mbar_init(&sh->p_full, 256);
+        mbar_init(&sh->o_full, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base = sh->tmem_base;
     const uint32_t tmem_o = tmem_base + 256;
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->loaded, 3 * 32768);
-            tma_load_2d(sQ, &tmQKV, &bars->loaded, slice * 64, b * S);
-            tma_load_2d(sK, &tmQKV, &bars->loaded, a.H + slice * 64, b * S);
-            tma_load_2d(sV, &tmQKV, &bars->loaded, 2 * a.H + slice * 64, b * S);
+            mbar_arrive_expect_tx(&sh->loaded, 3 * 32768);
+            tma_load_2d(sQ, &tmQKV, &sh->loaded, slice * 64, b * S);
+            tma_load_2d(sK, &tmQKV, &sh->loaded, a.H + slice * 64, b * S);
+            tma_load_2d(sV, &tmQKV, &sh->loaded, 2 * a.H + slice * 64, b * S);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -124,7 +147,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid
             const uint32_t idesc_o = at_idesc(128, d, 0, 1);
             const int ks_qk = d / 16;                        // K-steps of Q K^T
             const int ks_pv = (S + 15) / 16;                 // K-steps of P V
-            mbar_wait(&bars->loaded, 0);
+            mbar_wait(&sh->loaded, 0);
             tc_fence_after();
             auto issue_s = [&](int u) {
                 const int hh = u / n_qt, qt = u % n_qt;
@@ -133,94 +156,115 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid
                 for (int ks = 0; ks < ks_qk; ++ks)
                     umma_bf16(tmem_base, smem_desc_advance(qd, (hh * d + ks * 16) * 2), smem_desc_advance(kd, (hh * d + ks * 16) * 2),
                               idesc_s, (uint32_t)(ks != 0));
-                umma_commit(&bars->s_full);
+                umma_commit(&sh->s_full);
             };
             issue_s(0);
             for (int u = 0; u < units; ++u) {
                 const int hh = u / n_qt;
-                mbar_wait(&bars->p_full, (uint32_t)u & 1u);
+                mbar_wait(&sh->p_full, (uint32_t)u & 1u);
                 tc_fence_after();
                 for (int ks = 0; ks < ks_pv; ++ks) {
                     const uint64_t pd = smem_desc_advance(smem_desc_sw128(smem_u32(sP + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
                     const uint64_t vd = at_desc_mn(smem_u32(sV + (size_t)ks * 2048 + (size_t)hh * d * 2), 0);
                     umma_bf16(tmem_o, pd, vd, idesc_o, (uint32_t)(ks != 0));
                 }
-                umma_commit(&bars->o_full);
+                umma_commit(&sh->o_full);
                 if (u + 1 < units) issue_s(u + 1);           // S of the next unit overlaps this unit's epilogue
             }
         }
     } else if (warp >= 4) {
+        const int wg = (warp - 4) / 4;                       // which half of the key columns
         const int q4 = warp % 4;
         const int r = q4 * 32 + lane;                        // row of the query tile == TMEM lane
         const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
-        // key-validity bits of this sequence: one ballot per 32 keys, shared through shared memory
-        if (q4 == 0) {
+        if (warp == 4) {
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const int key = w * 32 + lane;
                 bool ok = key < S;
                 if (ok && a.key_valid) ok = a.key_valid[(size_t)b * S + key] != 0;
                 const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-                if (lane == 0) bars->kvb[w] = bits;
+                if (lane == 0) sh->kvb[w] = bits;
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four softmax warps only
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // the eight softmax warps only
         const int n_chunks = (NS + 31) / 32;
+        const int ch_lo = wg == 0 ? 0 : (n_chunks + 1) / 2;
+        const int ch_hi = wg == 0 ? (n_chunks + 1) / 2 : n_chunks;
+        const float cs = a.scale * LOG2E;                    // exp(x) = exp2(x * log2e); the row max itself stays in natural units so
+                                                             // that a fully masked row's max is EXACTLY -1e9 (no cancellation error)
+        const uint32_t thr16 = (uint32_t)(a.p_drop * 65536.0f + 0.5f);
         for (int u = 0; u < units; ++u) {
             const int hh = u / n_qt, qt = u % n_qt;
             const int head = slice * hps + hh;
             const int qi = qt * 128 + r;                     // query position in the sequence
             const bool q_ok = qi < S;
             const long long bh = (long long)b * a.heads + head;
-            mbar_wait(&bars->s_full, (uint32_t)u & 1u);
+            const int q_warp_min = qt * 128 + q4 * 32;       // smallest query index of this warp (causal fast-path test)
+            mbar_wait(&sh->s_full, (uint32_t)u & 1u);
             tc_fence_after();
-            // ---- pass 1: row maximum of the masked, scaled scores
+            // ---- pass 1: partial row maximum over this warpgroup's key columns
             float m = -INFINITY;
 #pragma unroll 1
-            for (int ch = 0; ch < n_chunks; ++ch) {
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
                 float v[32];
                 tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
                 tmem_ld_wait();
-                const uint32_t bits = bars->kvb[ch];
+                const uint32_t bits = sh->kvb[ch];
+                const bool plain = bits == 0xffffffffu && (!a.causal || ch * 32 + 31 <= q_warp_min);   // warp-uniform
+                if (plain) {
+                    float mm = v[0];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int key = ch * 32 + c;
-                    float s = v[c] * a.scale;
-                    const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
-                    s = ok ? s : MASK_FILL;
-                    s = key < S ? s : -INFINITY;
-                    m = fmaxf(m, s);
-                }
-            }
-            // ---- pass 2: exp, row sum, dropout, P -> shared memory (bf16, 128B-swizzled K-major tile)
-            float l = 0.f;
-            const float m2 = m * LOG2E;
-#pragma unroll 1
-            for (int ch = 0; ch < n_chunks; ++ch) {
-                float v[32];
-                tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
-                tmem_ld_wait();
-                const uint32_t bits = bars->kvb[ch];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int key = ch * 32 + c;
-                    float s = v[c] * a.scale;
-                    const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
-                    s = ok ? s : MASK_FILL;
-                    const float e = key < S ? exp2f(fmaf(s, LOG2E, -m2)) : 0.f;
-                    l += e;
-                    v[c] = e;
-                }
-                if (a.p_drop > 0.f) {
-                    float ds[32];
-                    dropout_scales32(a.seed, a.site, ((uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0)) * S + (uint64_t)(ch * 32), a.p_drop,
-                                     a.inv_keep, ds);
-                    uint32_t kb = 0;
+                    for (int c = 1; c < 32; ++c) mm = fmaxf(mm, v[c]);
+                    m = fmaxf(m, mm * a.scale);
+                } else {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        v[c] *= ds[c];
-                        kb |= (ds[c] != 0.f ? 1u : 0u) << c;
+                        const int key = ch * 32 + c;
+                        const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
+                        float t = ok ? v[c] * a.scale : MASK_FILL;
+                        t = key < S ? t : -INFINITY;
+                        m = fmaxf(m, t);
                     }
+                }
+            }
+            sh->xm[wg][r] = m;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            m = fmaxf(m, sh->xm[wg ^ 1][r]);
+            const float m2 = m * LOG2E;
+            const float e_masked = fast_exp2((MASK_FILL - m) * LOG2E);     // 1 in a fully masked row (uniform attention), else 0
+            // ---- pass 2: exp, partial row sum, dropout, P -> shared memory (bf16, 128B-swizzled K-major tile)
+            float l = 0.f;
+            uint32_t rowkey = 0;
+            if (a.p_drop > 0.f) rowkey = drop_rowkey(a.seed, a.site, (uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0));
+#pragma unroll 1
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
+                tmem_ld_wait();
+                const uint32_t bits = sh->kvb[ch];
+                const bool plain = bits == 0xffffffffu && (!a.causal || ch * 32 + 31 <= q_warp_min);
+                if (plain) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        v[c] = fast_exp2(fmaf(v[c], cs, -m2));
+                        l += v[c];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int key = ch * 32 + c;
+                        const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
+                        float e = ok ? fast_exp2(fmaf(v[c], cs, -m2)) : e_masked;
+                        e = key < S ? e : 0.f;
+                        l += e;
+                        v[c] = e;
+                    }
+                }
+                if (a.p_drop > 0.f) {
+                    const uint32_t kb = drop_keep_bits32(rowkey, ch, thr16);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = ((kb >> c) & 1u) ? v[c] * a.inv_keep : 0.f;
                     if (a.keep_bits && q_ok) a.keep_bits[((size_t)bh * S + qi) * 8 + ch] = kb;
                 }
                 uint8_t* chunk = sP + (size_t)(ch / 2) * 16384;     // 64 keys per chunk, this 32-key half = units (ch&1)*4 .. +3
@@ -232,32 +276,36 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(const __grid
                     *reinterpret_cast<uint4*>(chunk + sw128_offset(r, (ch & 1) * 4 + u16)) = w;
                 }
             }
-            // a 16-key K-step may reach past the last 32-column chunk written above only if NS % 32 != 0: columns NS..+15 of
-            // that chunk were written (as zeros) because the loops run over whole 32-column chunks.
+            sh->xl[wg][r] = l;
             fence_proxy_async_smem();                         // make the generic-proxy P writes visible to the tensor core
             tc_fence_before();
-            mbar_arrive(&bars->p_full);
-            // ---- O = P V done: normalise and store
-            mbar_wait(&bars->o_full, (uint32_t)u & 1u);
+            mbar_arrive(&sh->p_full);
+            // ---- O = P V done: normalise and store (each warpgroup half of the head's columns)
+            mbar_wait(&sh->o_full, (uint32_t)u & 1u);
             tc_fence_after();
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // both partial sums are in shared memory
+            l += sh->xl[wg ^ 1][r];
             const float inv_l = 1.0f / l;
-            if (a.stats && q_ok) {
-                a.stats[bh * S + qi] = m;
+            if (wg == 0 && a.stats && q_ok) {
+                a.stats[bh * S + qi] = m;                                         // natural units, as the SIMT kernels store it
                 a.stats[(long long)a.B * a.heads * S + bh * S + qi] = l;
             }
-            for (int c0 = 0; c0 < d; c0 += 16) {
-                float o[16];
-                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
-                tmem_ld_wait();
-                if (q_ok) {
-                    __nv_bfloat16* dst = a.ctx + ((size_t)b * S + qi) * a.H + slice * 64 + hh * d + c0;
-                    uint4 w0, w1;
-                    w0.x = at_pack(o[0] * inv_l, o[1] * inv_l); w0.y = at_pack(o[2] * inv_l, o[3] * inv_l);
-                    w0.z = at_pack(o[4] * inv_l, o[5] * inv_l); w0.w = at_pack(o[6] * inv_l, o[7] * inv_l);
-                    w1.x = at_pack(o[8] * inv_l, o[9] * inv_l); w1.y = at_pack(o[10] * inv_l, o[11] * inv_l);
-                    w1.z = at_pack(o[12] * inv_l, o[13] * inv_l); w1.w = at_pack(o[14] * inv_l, o[15] * inv_l);
-                    reinterpret_cast<uint4*>(dst)[0] = w0;
-                    reinterpret_cast<uint4*>(dst)[1] = w1;
+            const int dcols = d >= 32 ? d / 2 : d;            // columns per warpgroup (d = 16: warpgroup 0 stores everything)
+            if (d >= 32 || wg == 0) {
+                for (int c0 = wg * (d >= 32 ? dcols : 0); c0 < wg * (d >= 32 ? dcols : 0) + dcols; c0 += 16) {
+                    float o[16];
+                    tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+                    tmem_ld_wait();
+                    if (q_ok) {
+                        __nv_bfloat16* dst = a.ctx + ((size_t)b * S + qi) * a.H + slice * 64 + hh * d + c0;
+                        uint4 w0, w1;
+                        w0.x = at_pack(o[0] * inv_l, o[1] * inv_l); w0.y = at_pack(o[2] * inv_l, o[3] * inv_l);
+                        w0.z = at_pack(o[4] * inv_l, o[5] * inv_l); w0.w = at_pack(o[6] * inv_l, o[7] * inv_l);
+                        w1.x = at_pack(o[8] * inv_l, o[9] * inv_l); w1.y = at_pack(o[10] * inv_l, o[11] * inv_l);
+                        w1.z = at_pack(o[12] * inv_l, o[13] * inv_l); w1.w = at_pack(o[14] * inv_l, o[15] * inv_l);
+                        reinterpret_cast<uint4*>(dst)[0] = w0;
+                        reinterpret_cast<uint4*>(dst)[1] = w1;
+                    }
                 }
             }
             tc_fence_before();      // O (and S) TMEM reads are ordered before the MMAs of the next unit via p_full / o_full
@@ -288,9 +336,9 @@ extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, 
     a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
     a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits;
-    const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnBars);
+    const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnFwdShared);
     ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_fwd_kernel<<<dim3(B, H / 64), AT_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
+    attn_tc_fwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -316,14 +364,14 @@ struct AttnBwdArgs {
     __nv_bfloat16* d_qkv;          // (B*S, 3H)
 };
 struct __align__(16) AttnBwdShared {
-    float4 qc[AT_MAXS];            // per query of the current head: {rowmax * log2e, 1 / rowsum, D = sum_d dO.O, 0}
+    float4 qc[AT_MAXS];            // per query of the current head: {rowmax * log2e, 1 / rowsum, D = sum_d dO.O, exp(-1e9 - rowmax)}
     uint32_t keep[AT_MAXS * 8];    // dropout keep bits of the current head
     uint64_t loaded, t_full, x_full, acc_done;
     uint32_t tmem_base;
     uint32_t kvb[8];
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
+__global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                     const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -346,7 +394,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid
         tma_prefetch_desc(&tmDO);
         mbar_init(&sh->loaded, 1);
         mbar_init(&sh->t_full, 1);
-        mbar_init(&sh->x_full, 128);
+        mbar_init(&sh->x_full, 256);
         mbar_init(&sh->acc_done, 1);
         fence_barrier_init();
     }
@@ -422,10 +470,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid
             }
         }
     } else if (warp >= 4) {
+        // two warpgroups: both own all 128 rows of a sub-tile (TMEM lane = row) and split its 128 columns in halves
+        const int wg = (warp - 4) / 4;
         const int q4 = warp % 4;
         const int r = q4 * 32 + lane;
+        const int et = threadIdx.x - 128;                    // 0..255 among the epilogue threads
         const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
-        if (q4 == 0) {
+        const float cs = a.scale * LOG2E;
+        if (warp == 4) {
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const int key = w * 32 + lane;
@@ -439,9 +491,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid
         for (int hh = 0; hh < hps; ++hh) {
             const int head = slice * hps + hh;
             const long long bh = (long long)b * a.heads + head;
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous head's constants no longer in use
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // previous head's constants no longer in use (and kvb written)
             // per-query constants and dropout bits of this head
-            for (int q = r; q < S; q += 128) {
+            for (int q = et; q < S; q += 256) {
                 const __nv_bfloat16* o = a.ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
                 const __nv_bfloat16* go = a.d_ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
                 float D = 0.f;
@@ -458,73 +510,91 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid
                 }
                 const float m = a.stats[bh * S + q];
                 const float l = a.stats[(long long)a.B * a.heads * S + bh * S + q];
-                sh->qc[q] = make_float4(m * LOG2E, 1.0f / l, D, 0.f);
+                sh->qc[q] = make_float4(m * LOG2E, 1.0f / l, D, exp2f((MASK_FILL - m) * LOG2E));
                 if (a.keep_bits) {
                     const uint4* kb = reinterpret_cast<const uint4*>(a.keep_bits + ((size_t)bh * S + q) * 8);
                     reinterpret_cast<uint4*>(sh->keep + q * 8)[0] = kb[0];
                     reinterpret_cast<uint4*>(sh->keep + q * 8)[1] = kb[1];
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int i = 0; i < subs_per_head; ++i, ++g) {
                 const int sweep = i / (n_t * n_t), rt = (i / n_t) % n_t, ct = i % n_t;
                 const int row = rt * 128 + r;                  // sweep A: query, sweep B: key
                 const bool row_ok = row < S;
                 const int ncols = min(128, S - ct * 128);
-                const int n_chunks = (ncols + 31) / 32;
+                const int warp_row0 = rt * 128 + q4 * 32;      // first row of this warp
                 mbar_wait(&sh->t_full, (uint32_t)g & 1u);
                 tc_fence_after();
                 float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
                 if (sweep == 0 && row_ok) rc = sh->qc[row];
                 const bool key_row_ok = sweep == 1 && row_ok && ((sh->kvb[row >> 5] >> (row & 31)) & 1u);
+                const bool warp_rows_plain = sweep == 0 ? (warp_row0 + 31 < S)
+                                                        : (__all_sync(0xffffffffu, key_row_ok) != 0);
+                uint32_t keep_w0 = 0xffffffffu, keep_w1 = 0xffffffffu;   // sweep A: keep bits of this row for this warpgroup's 64 keys
+                if (sweep == 0 && a.keep_bits && row_ok) {
+                    keep_w0 = sh->keep[row * 8 + ct * 4 + wg * 2];
+                    keep_w1 = sh->keep[row * 8 + ct * 4 + wg * 2 + 1];
+                }
 #pragma unroll 1
-                for (int ch = 0; ch < n_chunks; ++ch) {
-                    float t1[32], t2[32];
-                    tmem_ld32(tm_t1 + lane_addr + (uint32_t)(ch * 32), t1);
-                    tmem_ld32(tm_t2 + lane_addr + (uint32_t)(ch * 32), t2);
+                for (int c16 = wg * 4; c16 < wg * 4 + 4; ++c16) {          // 16-column chunks of this warpgroup's half
+                    const int col0 = ct * 128 + c16 * 16;                  // sweep A: first key, sweep B: first query
+                    if (c16 * 16 >= ((ncols + 31) / 32) * 32) break;       // beyond the columns the MMAs touch (warp-uniform)
+                    float t1[16], t2[16];
+                    tmem_ld16(tm_t1 + lane_addr + (uint32_t)(c16 * 16), t1);
+                    tmem_ld16(tm_t2 + lane_addr + (uint32_t)(c16 * 16), t2);
                     tmem_ld_wait();
-                    uint32_t keep_w = 0xffffffffu, kv_w = 0;
+                    float pd[16], ds[16];
                     if (sweep == 0) {
-                        kv_w = sh->kvb[ct * 4 + ch];
-                        if (a.keep_bits && row_ok) keep_w = sh->keep[row * 8 + ct * 4 + ch];
-                    }
-                    float pd[32], ds[32];
+                        const uint32_t kv16 = (sh->kvb[col0 >> 5] >> (col0 & 31)) & 0xffffu;
+                        const uint32_t kp16 = ((((c16 >> 1) & 1) ? keep_w1 : keep_w0) >> ((c16 & 1) * 16)) & 0xffffu;
+                        const bool plain = warp_rows_plain && kv16 == 0xffffu && (!a.causal || col0 + 15 <= warp_row0);
+                        if (plain) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int col = ct * 128 + ch * 32 + c;           // sweep A: key, sweep B: query
-                        float p = 0.f, dsv = 0.f, pdv = 0.f;
-                        if (sweep == 0) {
-                            const bool ok = ((kv_w >> c) & 1u) && (!a.causal || col <= row);
-                            const float sc = ok ? t1[c] * a.scale : MASK_FILL;
-                            p = (col < S && row_ok) ? exp2f(fmaf(sc, LOG2E, -rc.x)) * rc.y : 0.f;
-                            const float keep = ((keep_w >> c) & 1u) ? a.inv_keep : 0.f;
-                            dsv = ok ? p * (t2[c] * keep - rc.z) * a.scale : 0.f;
+                            for (int c = 0; c < 16; ++c) {
+                                const float p = fast_exp2(fmaf(t1[c], cs, -rc.x)) * rc.y;
+                                const float keep = ((kp16 >> c) & 1u) ? a.inv_keep : 0.f;
+                                ds[c] = p * (t2[c] * keep - rc.z) * a.scale;
+                            }
                         } else {
-                            const bool col_ok = col < S;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const int col = col0 + c;
+                                const bool ok = ((kv16 >> c) & 1u) && (!a.causal || col <= row);
+                                const float e = ok ? fast_exp2(fmaf(t1[c], cs, -rc.x)) : rc.w;
+                                const float p = (col < S && row_ok) ? e * rc.y : 0.f;
+                                const float keep = ((kp16 >> c) & 1u) ? a.inv_keep : 0.f;
+                                ds[c] = ok ? p * (t2[c] * keep - rc.z) * a.scale : 0.f;
+                            }
+                        }
+                    } else {
+                        const bool plain = warp_rows_plain && (col0 + 15 < S) && (!a.causal || warp_row0 + 31 <= col0);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int col = col0 + c;
+                            const bool col_ok = plain || col < S;
                             const float4 cc = col_ok ? sh->qc[col] : make_float4(0.f, 1.f, 0.f, 0.f);
-                            const bool ok = key_row_ok && col_ok && (!a.causal || row <= col);
-                            const float sc = ok ? t1[c] * a.scale : MASK_FILL;
-                            p = (col_ok && row_ok) ? exp2f(fmaf(sc, LOG2E, -cc.x)) * cc.y : 0.f;
+                            const bool ok = plain || (key_row_ok && col_ok && (!a.causal || row <= col));
+                            const float e = ok ? fast_exp2(fmaf(t1[c], cs, -cc.x)) : cc.w;
+                            const float p = (col_ok && row_ok) ? e * cc.y : 0.f;
                             float keep = a.inv_keep;
                             if (a.keep_bits && col_ok) keep = ((sh->keep[col * 8 + (row >> 5)] >> (row & 31)) & 1u) ? a.inv_keep : 0.f;
-                            pdv = p * keep;
-                            dsv = ok ? p * (t2[c] * keep - cc.z) * a.scale : 0.f;
+                            pd[c] = p * keep;
+                            ds[c] = ok ? p * (t2[c] * keep - cc.z) * a.scale : 0.f;
                         }
-                        pd[c] = pdv;
-                        ds[c] = dsv;
                     }
-                    uint8_t* xchunk = sX + (size_t)(ch / 2) * 16384;
-                    uint8_t* ychunk = sY + (size_t)(ch / 2) * 16384;
+                    uint8_t* xchunk = sX + (size_t)(c16 / 4) * 16384;      // 64 columns per chunk; this 16-column piece = 2 units
+                    uint8_t* ychunk = sY + (size_t)(c16 / 4) * 16384;
 #pragma unroll
-                    for (int u16 = 0; u16 < 4; ++u16) {
+                    for (int u16 = 0; u16 < 2; ++u16) {
                         uint4 w;
                         w.x = at_pack(ds[u16 * 8 + 0], ds[u16 * 8 + 1]); w.y = at_pack(ds[u16 * 8 + 2], ds[u16 * 8 + 3]);
                         w.z = at_pack(ds[u16 * 8 + 4], ds[u16 * 8 + 5]); w.w = at_pack(ds[u16 * 8 + 6], ds[u16 * 8 + 7]);
-                        *reinterpret_cast<uint4*>(xchunk + sw128_offset(r, (ch & 1) * 4 + u16)) = w;
+                        *reinterpret_cast<uint4*>(xchunk + sw128_offset(r, (c16 & 3) * 2 + u16)) = w;
                         if (sweep == 1) {
                             w.x = at_pack(pd[u16 * 8 + 0], pd[u16 * 8 + 1]); w.y = at_pack(pd[u16 * 8 + 2], pd[u16 * 8 + 3]);
                             w.z = at_pack(pd[u16 * 8 + 4], pd[u16 * 8 + 5]); w.w = at_pack(pd[u16 * 8 + 6], pd[u16 * 8 + 7]);
-                            *reinterpret_cast<uint4*>(ychunk + sw128_offset(r, (ch & 1) * 4 + u16)) = w;
+                            *reinterpret_cast<uint4*>(ychunk + sw128_offset(r, (c16 & 3) * 2 + u16)) = w;
                         }
                     }
                 }
@@ -532,24 +602,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(const __grid
                 tc_fence_before();
                 mbar_arrive(&sh->x_full);
                 if (ct == n_t - 1) {
-                    // all column tiles of this row tile accumulated: store dQ (sweep A) or dK, dV (sweep B)
+                    // all column tiles of this row tile accumulated: store dQ (sweep A) or dK, dV (sweep B); each warpgroup
+                    // stores half of the head's columns (d = 16: warpgroup 0 stores everything)
                     mbar_wait(&sh->acc_done, (uint32_t)g & 1u);
                     tc_fence_after();
                     const int n_out = sweep == 0 ? 1 : 2;
-                    for (int which = 0; which < n_out; ++which) {
-                        const uint32_t tm = which == 0 ? tm_acc0 : tm_acc1;
-                        const int col0 = (sweep == 0 ? 0 : (which == 0 ? a.H : 2 * a.H)) + slice * 64 + hh * d;
-                        for (int c0 = 0; c0 < d; c0 += 16) {
-                            float o[16];
-                            tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
-                            tmem_ld_wait();
-                            if (row_ok) {
-                                __nv_bfloat16* dst = a.d_qkv + ((size_t)b * S + row) * 3 * a.H + col0 + c0;
-                                uint4 w0, w1;
-                                w0.x = at_pack(o[0], o[1]); w0.y = at_pack(o[2], o[3]); w0.z = at_pack(o[4], o[5]); w0.w = at_pack(o[6], o[7]);
-                                w1.x = at_pack(o[8], o[9]); w1.y = at_pack(o[10], o[11]); w1.z = at_pack(o[12], o[13]); w1.w = at_pack(o[14], o[15]);
-                                reinterpret_cast<uint4*>(dst)[0] = w0;
-                                reinterpret_cast<uint4*>(dst)[1] = w1;
+                    const int dcols = d >= 32 ? d / 2 : d;
+                    if (d >= 32 || wg == 0) {
+                        const int cbeg = d >= 32 ? wg * dcols : 0;
+                        for (int which = 0; which < n_out; ++which) {
+                            const uint32_t tm = which == 0 ? tm_acc0 : tm_acc1;
+                            const int colbase = (sweep == 0 ? 0 : (which == 0 ? a.H : 2 * a.H)) + slice * 64 + hh * d;
+                            for (int c0 = cbeg; c0 < cbeg + dcols; c0 += 16) {
+                                float o[16];
+                                tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
+                                tmem_ld_wait();
+                                if (row_ok) {
+                                    __nv_bfloat16* dst = a.d_qkv + ((size_t)b * S + row) * 3 * a.H + colbase + c0;
+                                    uint4 w0, w1;
+                                    w0.x = at_pack(o[0], o[1]); w0.y = at_pack(o[2], o[3]); w0.z = at_pack(o[4], o[5]); w0.w = at_pack(o[6], o[7]);
+                                    w1.x = at_pack(o[8], o[9]); w1.y = at_pack(o[10], o[11]); w1.z = at_pack(o[12], o[13]); w1.w = at_pack(o[14], o[15]);
+                                    reinterpret_cast<uint4*>(dst)[0] = w0;
+                                    reinterpret_cast<uint4*>(dst)[1] = w1;
+                                }
                             }
                         }
                     }
@@ -589,7 +664,7 @@ extern "C" int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, 
     a.keep_bits = p_drop > 0.f ? keep_bits : nullptr; a.d_qkv = (__nv_bfloat16*)d_qkv;
     const size_t smem = 1024 + 6 * 32768 + sizeof(AttnBwdShared);
     ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tc_bwd_kernel<<<dim3(B, H / 64), AT_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+    attn_tc_bwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

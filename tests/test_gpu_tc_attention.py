@@ -27,6 +27,30 @@ def make(gen, B, S, heads, d, pad="right"):
     return qkv, valid
 
 
+def unpack_keep(keep, B, heads, S):
+    """(B*heads*S, 8) int32 keep bits -> (B, heads, S, S) bool"""
+    bits = (keep.view(B, heads, S, 8, 1) >> torch.arange(32, device=keep.device, dtype=torch.int32)) & 1
+    return bits.reshape(B, heads, S, 256)[..., :S].bool()
+
+
+def torch_attention(qkv, valid, B, S, heads, causal, keep=None, p_drop=0.0):
+    """fp32 restatement of Attention.forward (transformer_layers.py:145-155) with an explicit dropout keep mask"""
+    H = qkv.shape[1] // 3
+    d = H // heads
+    x = qkv.float().view(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)          # (3,B,heads,S,d)
+    q, k, v = x[0], x[1], x[2]
+    scores = q @ k.transpose(-1, -2) / d ** 0.5
+    mask = torch.ones(B, 1, S, S, dtype=torch.bool, device=qkv.device)
+    if valid is not None:
+        mask = mask & valid.view(B, 1, 1, S)
+    if causal:
+        mask = mask & torch.tril(torch.ones(S, S, dtype=torch.bool, device=qkv.device))
+    p = torch.softmax(scores.masked_fill(~mask, -1e9), dim=-1)
+    if keep is not None:
+        p = p * keep.float() / (1.0 - p_drop)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+
+
 def norm_err(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
 
@@ -37,8 +61,22 @@ def norm_err(a, b):
 def test_tc_attn_fwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
     gen = torch.Generator(device="cuda").manual_seed(B * 1000 + S + heads + d)
     qkv, valid = make(gen, B, S, heads, d)
-    ref, rst = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
-    got, gst, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
+    _, rst = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, 0.0, 77, 19, save_stats=True)
+    got, gst, keep = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
+    if p_drop == 0.0:
+        ref, _ = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal)                # the fp32 SIMT kernel
+        assert keep is None
+    else:
+        # the tensor-core kernel has its own dropout stream and hands the keep bits to the backward pass: compare with the
+        # reference arithmetic under exactly that mask, and check the mask is Bernoulli(1 - p)
+        km = unpack_keep(keep, B, heads, S)
+        ref = torch_attention(qkv, valid, B, S, heads, causal, km, p_drop)
+        if B * heads * S * S >= 20000:
+            assert abs(float(km.float().mean()) - (1.0 - p_drop)) < 0.02
+        again, _, keep2 = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 77, 19, save_stats=True)
+        assert torch.equal(keep, keep2) and torch.equal(got, again)                 # pure function of (seed, site, element)
+        other, _, keep3 = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 78, 19, save_stats=True)
+        assert not torch.equal(keep, keep3)
     assert norm_err(got, ref) < 4e-3
     torch.testing.assert_close(got.float(), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
     torch.testing.assert_close(gst[0], rst[0], rtol=1e-5, atol=1e-5)          # row max: fp32 accumulation noise only
@@ -74,10 +112,15 @@ def test_tc_attn_bwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
     qkv, valid = make(gen, B, S, heads, d)
     H = heads * d
     d_ctx = (torch.randn(B * S, H, generator=gen, device="cuda") * 0.5).bfloat16()
-    ctx_ref, st_ref = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, p_drop, 5, 23, save_stats=True)
-    want = ops.attn_bwd(qkv.float(), valid, B, S, heads, causal, ctx_ref, d_ctx.float(), st_ref, p_drop, 5, 23)
     ctx, st, keep = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, p_drop, 5, 23, save_stats=True)
     got = ops.tc_attn_bwd(qkv, valid, B, S, heads, causal, ctx, d_ctx, st, keep, p_drop)
+    if p_drop == 0.0:
+        ctx_ref, st_ref = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, save_stats=True)
+        want = ops.attn_bwd(qkv.float(), valid, B, S, heads, causal, ctx_ref, d_ctx.float(), st_ref)
+    else:       # autograd of the reference arithmetic under the forward's keep mask
+        x = qkv.float().requires_grad_(True)
+        torch_attention(x, valid, B, S, heads, causal, unpack_keep(keep, B, heads, S), p_drop).backward(d_ctx.float())
+        want = x.grad
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         if S == 1 and name != "dv":
             # a single key: dQ = dK = 0 analytically (dS = P (dP - D) cancels); what is left on either side is the rounding
