@@ -214,6 +214,9 @@ def algorithmic_cost(name, note):
     if name in ("asme_b200_tc_score_topk",):
         R, V, H, k = g("R"), g("V"), g("H"), g("k")
         return 2 * (R * H + V * H) + 4 * V + R * (k * 8 + 8), 2 * R * V * H
+    if name == "asme_b200_tc_score_ce_bwd":
+        R, V, H = g("R"), g("V"), g("H")
+        return 2 * 2 * (R * H + V * H) + 4 * (R * H + 2 * V * H + 3 * V), 12 * R * V * H
     if name == "asme_b200_tc_score_ce_partial":
         R, V, H = g("R"), g("V"), g("H")
         return 2 * (R * H + V * H) + 4 * V + 12 * R, 2 * R * V * H
@@ -290,6 +293,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-eval", action="store_true", help="skip the secondary C5 full-catalog evaluation measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying its CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -352,6 +356,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The step is ~90 launches; issued from Python the host is the bottleneck, so the product path replays the step's CUDA graph
+    # (asme_b200.graphs.GraphedTrainStep: one graph per batch signature, seed / Adam step / lr in device memory).
+    graphed = None
+    if not args.no_graph:
+        from asme_b200.graphs import GraphedTrainStep
+        try:
+            graphed = GraphedTrainStep(module, optimizer, scheduler, grad_hook=allreduce_grads if world > 1 else None)
+            for j in range(NB):
+                graphed(dev_batches[j], key=j)
+            torch.cuda.synchronize()
+        except Exception as e:      # e.g. a collective that cannot be captured: fall back to launch-by-launch
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graphed = None
+            module.model._step_state = None
+            optimizer.step_state = None
+
+    def run_step(batch, i):
+        if graphed is not None:
+            return graphed(batch, key=i % NB)
+        return train_step(batch, i)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -375,10 +400,11 @@ def main():
 
     # ---- (1) device-resident throughput -------------------------------------------------------------------------
     for i in range(args.warmup):
-        train_step(dev_batches[i % NB], i)
+        run_step(dev_batches[i % NB], i)
     launches0 = _lib.kernel_launches()
-    ms, win1 = timed(lambda i: train_step(dev_batches[i % NB], i), args.steps)
+    ms, win1 = timed(lambda i: run_step(dev_batches[i % NB], i), args.steps)
     launches = _lib.kernel_launches() - launches0
+    launches_per_step_eager = None
     value = args.steps * cfg["B"] * world / (ms / 1e3)
 
     # ---- (2) end to end through the public module API with HOST buffers ------------------------------------------
@@ -386,8 +412,11 @@ def main():
 
     def e2e_step(i):
         hb = host_batches[i % NB]
-        batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}     # H2D of this step's inputs
-        loss = train_step(batch, i)
+        if graphed is not None:
+            loss = graphed(hb, key=i % NB)                                      # H2D of this step's inputs into the graph's static buffers
+        else:
+            batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
+            loss = train_step(batch, i)
         return float(loss)                                                      # D2H read of the step's result
 
     for i in range(3):
@@ -397,10 +426,16 @@ def main():
 
     # ---- (3) per-kernel CUDA-event timing of the same step (roofline of the dominant kernel) -----------------------
     prof_steps = min(5, args.steps)
+    if graphed is not None:          # the per-kernel pass (and the launch count) runs the same step launch by launch
+        module.model._step_state = None
+        optimizer.step_state = None
     _lib.timing = []
     barrier()
+    l0 = _lib.kernel_launches()
     for i in range(prof_steps):
         train_step(dev_batches[i % NB], i)
+    if graphed is not None:
+        launches = (_lib.kernel_launches() - l0) * args.steps // prof_steps   # kernels of this library per step x timed steps (graph replays launch the same nodes)
     torch.cuda.synchronize()
     records = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
@@ -456,6 +491,7 @@ def main():
                       "dropout": cfg["dropout"], "optimizer": "Adam(0.99,0.998) fused, LambdaLR warm-up",
                       "precision": f"{model.precision}: tcgen05 GEMMs/attention/scoring with bf16 operands, fp32 accumulation, residual stream, LayerNorm, loss and Adam state",
                       "parallelism": f"dp{world}" if world > 1 else "single",
+                      "launch": "CUDA graph replay of the whole step (one graph per batch signature)" if graphed is not None else "launch by launch",
                       "l2": "inputs larger than L2: each step streams ~0.9 GB of activations (> 126 MB L2), 4 distinct batches rotate"},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,

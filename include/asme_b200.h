@@ -254,6 +254,14 @@ int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb,
                                   const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
                                   void* ws, size_t ws_bytes, asme_stream_t stream);
 
+/* backward of the fused scoring + cross-entropy layer on the tensor cores: dlogit = (softmax - onehot) * scale is recomputed tile
+ * by tile in tensor memory; dH (R,H) fp32 is overwritten, dW (Vloc,H) and dbias (Vloc) are accumulated (+=); any of the three
+ * may be NULL (dbias needs dW).  lse = row_max + log(row_sumexp) over the WHOLE catalog (shards combine first). */
+size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp, int Vloc);
+int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                              const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
+                              void* ws, size_t ws_bytes, asme_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Tensor-core dense layers (tcgen05 + TMEM + TMA), bf16 operands / fp32 accumulation.  Same call sites as asme_b200_gemm.
  *   b_is_kn = 0: B is (N,K) row-major (nn.Linear weight), C = A B^T      forward
@@ -314,6 +322,12 @@ int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, i
 int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
                         double beta2, double eps, double weight_decay, int step, asme_stream_t stream);
 int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream);
+/* Device-resident step state for CUDA-graph replays of a whole training step: struct {uint64 seed; int32 adam_step; float lr}.
+ * asme_b200_step_state_advance (first node of the graph) bumps seed and adam_step; every dropout `seed` argument may be passed
+ * as (1<<63 | device pointer to the state) instead of a value; asme_b200_adam_step_dev reads step and lr from the state. */
+int asme_b200_step_state_advance(void* state, asme_stream_t stream);
+int asme_b200_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, const void* state, double beta1,
+                            double beta2, double eps, double weight_decay, asme_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,8 @@ _PROTOTYPES = {
     "asme_b200_tc_score_topk": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_size_t, P]),
     "asme_b200_tc_score_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_tc_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "asme_b200_tc_score_ce_bwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P]),
     "asme_b200_tc_gemm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P, P]),
     "asme_b200_tc_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
@@ -92,6 +94,8 @@ _PROTOTYPES = {
     "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P]),
     "asme_b200_scatter_rows": (c_int, [P, P, c_int, c_int, P, P]),
     "asme_b200_adam_step": (c_int, [P, P, P, P, c_longlong, c_double, c_double, c_double, c_double, c_double, c_int, P]),
+    "asme_b200_step_state_advance": (c_int, [P, P]),
+    "asme_b200_adam_step_dev": (c_int, [P, P, P, P, c_longlong, P, c_double, c_double, c_double, c_double, P]),
     "asme_b200_fill": (c_int, [P, c_longlong, c_float, P]),
 }
 

@@ -1,0 +1,92 @@
+"""Whole-step CUDA graphs.  A training step of the C2-C4 shapes is ~90 kernel launches of 5-300 us each; issued one by one
+from Python the host needs ~2.7 ms per step while the kernels need ~2 ms, i.e. the GPU idles.  ``GraphedTrainStep`` captures
+zero_grad -> training_step -> backward -> fused Adam for one batch signature into a CUDA graph and replays it; everything
+that changes from step to step lives in device memory (:class:`StepState`): the dropout seed and the Adam step count are
+bumped by the first node of the graph, the learning rate is written by the host before each replay.
+
+The captured step is exactly the eager step (same kernels, same order, same arithmetic); eager mode stays the default and the
+reference API (training_step / loss.backward() / optimizer.step()) is unchanged."""
+from typing import Any, Callable, Dict
+
+import torch
+
+from . import ops
+
+
+class StepState:
+    """device struct {uint64 seed; int32 adam_step; float32 lr} (include/asme_b200.h, asme_b200_step_state_advance)"""
+
+    def __init__(self, device, seed: int = 0, adam_step: int = 0, lr: float = 0.0):
+        self.tensor = torch.zeros(4, dtype=torch.int32, device=device)
+        self.tensor[:2] = torch.tensor([seed & 0xFFFFFFFF, (seed >> 32) & 0x7FFFFFFF], dtype=torch.int64).to(torch.int32).to(device)
+        self.tensor[2] = adam_step
+        self._lr_view = self.tensor.view(torch.float32)[3:4]
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.set_lr(lr)
+
+    def set_lr(self, lr: float):
+        self._lr_host[0] = lr
+        self._lr_view.copy_(self._lr_host, non_blocking=True)
+
+    def indirect_seed(self) -> int:
+        return (1 << 63) | self.tensor.data_ptr()
+
+
+class GraphedTrainStep:
+    """captures ``step_fn(batch)`` (zero_grad + training_step + backward + optimizer.step) once per batch signature"""
+
+    def __init__(self, module, optimizer, scheduler=None, warmup_iters: int = 3, grad_hook: Callable[[], None] = None):
+        self.module, self.optimizer, self.scheduler = module, optimizer, scheduler
+        self.grad_hook = grad_hook          # e.g. the data-parallel all-reduce of the flat gradient arena (captured too)
+        self.model = module.model
+        dev = next(self.model.parameters()).device
+        lr = optimizer.param_groups[0]["lr"]
+        self.state = StepState(dev, seed=(int(self.model._seed) << 32) + self.model._step_counter, adam_step=optimizer._steps, lr=lr)
+        self.model._step_state = self.state
+        optimizer.step_state = self.state
+        self.graphs: Dict[Any, Any] = {}
+        self.warmup_iters = warmup_iters
+
+    def _eager(self, batch):
+        ops.step_state_advance(self.state.tensor)
+        self.optimizer.zero_grad()
+        with torch.no_grad():                       # direct mode: modules.fused_loss parks the fused backward on the model
+            out = self.module.training_step(batch, 0)
+            self.model._pending_backward()
+            self.model._pending_backward = None
+        if self.grad_hook is not None:
+            self.grad_hook()
+        self.optimizer.step()
+        return out["loss"].detach()
+
+    def _capture(self, key, batch):
+        static = {k: v.clone() for k, v in batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup_iters):       # grows workspaces / allocator pools, fetches driver entry points
+                self._eager(static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._eager(static)
+        self.graphs[key] = (graph, static, loss)
+        return self.graphs[key]
+
+    def __call__(self, batch: Dict[str, torch.Tensor], key=None) -> torch.Tensor:
+        """batch tensors are copied into the graph's static inputs (device-to-device or pinned host-to-device); returns the
+        loss tensor of the replayed step (static: read it before the next replay of the same graph)"""
+        if key is None:
+            key = tuple((k, tuple(v.shape)) for k, v in sorted(batch.items()))
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, batch)
+        graph, static, loss = entry
+        for k, v in batch.items():
+            if static[k].data_ptr() != v.data_ptr():
+                static[k].copy_(v, non_blocking=True)
+        self.state.set_lr(self.optimizer.param_groups[0]["lr"])
+        graph.replay()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        return loss

@@ -157,6 +157,9 @@ class TransformerRecommenderModel(ArenaModule):
     # ---- hidden states ----------------------------------------------------------------------------
     def _next_seed(self) -> int:
         self._step_counter += 1
+        state = getattr(self, "_step_state", None)
+        if state is not None:      # CUDA-graph mode: kernels re-read the seed from device memory on every replay
+            return state.indirect_seed()
         return (int(self._seed) << 32) + self._step_counter
 
     def encode(self, seq: torch.Tensor, padding_mask: Optional[torch.Tensor], attrs: Dict[str, torch.Tensor],
@@ -263,13 +266,20 @@ class TransformerRecommenderModel(ArenaModule):
         row_targets = flat_t.index_select(0, rows)
         h_rows = ops.gather_rows(hidden, rows)
         m_rows, saved_mod = self.modify(h_rows, save=self.training)
-        w, b = self.projection_operands()
-        rmax, rsum, tl = ops.score_ce_partial(m_rows, w, b, row_targets)
+        use_tc = self.precision == "bf16"
+        if use_tc:      # tcgen05 scoring + CE partials on bf16 operands; the backward recomputes the same tiles
+            wb, b = self.projection_operands_bf16()
+            hb = ops.cast_bf16(m_rows, ld_out=wb.shape[1])
+            rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, row_targets)
+        else:
+            hb = None
+            w, b = self.projection_operands()
+            rmax, rsum, tl = ops.score_ce_partial(m_rows, w, b, row_targets)
         loss_sum = torch.zeros(1, dtype=torch.float32, device=seq.device)
         lse = ops.ce_loss_from_partials(rmax, rsum, tl, loss_sum)
         n_rows = int(rows.numel())
         loss = loss_sum[0] / n_rows if n_rows > 0 else loss_sum[0] * float("nan")
-        ctx = dict(saved=saved, rows=rows, row_targets=row_targets, m_rows=m_rows, saved_mod=saved_mod, lse=lse, n_rows=n_rows,
+        ctx = dict(saved=saved, rows=rows, row_targets=row_targets, m_rows=m_rows, hb=hb, saved_mod=saved_mod, lse=lse, n_rows=n_rows,
                    T=hidden.shape[0])
         return loss, ctx
 
@@ -277,9 +287,13 @@ class TransformerRecommenderModel(ArenaModule):
         if ctx["n_rows"] == 0:
             return
         g = self._prepare_grads()
-        w, b = self.projection_operands()
         dw, db = self.projection_operands(grad=True)
-        d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], dw, db)
+        if ctx["hb"] is not None:
+            wb, b = self.projection_operands_bf16()
+            d_m = ops.tc_score_ce_bwd(ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], self.cfg.hidden, dw, db)
+        else:
+            w, b = self.projection_operands()
+            d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], dw, db)
         d_h = self.modify_backward(d_m, ctx["saved_mod"])
         d_hidden = torch.zeros(ctx["T"], self.cfg.hidden, dtype=torch.float32, device=d_h.device)
         ops.scatter_rows(d_h, ctx["rows"], d_hidden)

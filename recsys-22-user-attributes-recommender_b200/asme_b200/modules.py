@@ -46,6 +46,9 @@ class _FusedLoss(torch.autograd.Function):
 
 def fused_loss(model: TransformerRecommenderModel, loss_value: torch.Tensor, backward_fn) -> torch.Tensor:
     if not torch.is_grad_enabled():
+        # direct mode (asme_b200.graphs.GraphedTrainStep captures the step under no_grad and runs the fused backward itself:
+        # the autograd engine's worker thread cannot take part in a CUDA-graph capture of these ctypes launches)
+        model._pending_backward = backward_fn
         return loss_value
     anchor = next(model.parameters())
     return _FusedLoss.apply(anchor, loss_value, backward_fn)

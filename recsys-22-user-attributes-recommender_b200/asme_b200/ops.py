@@ -408,6 +408,22 @@ def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: in
     return rmax, rsum, tl
 
 
+def tc_score_ce_bwd(hb, wb, bias, target, lse, scale: float, H: int, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
+                    v0: int = 0, need_dh: bool = True) -> Optional[torch.Tensor]:
+    """tensor-core backward of scoring + CE: returns dH (R,H) fp32; accumulates into dW (Vloc,H) / dbias (Vloc)"""
+    hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
+    R, Kp = hb.shape
+    Vloc = wb.shape[0]
+    dh = torch.empty(R, H, dtype=torch.float32, device=hb.device) if need_dh else None
+    ws_bytes = _lib.query("asme_b200_tc_score_ce_bwd_workspace_bytes", R, H, Kp, Vloc)
+    ws = workspace(ws_bytes, hb.device)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={Kp}"
+    _lib.call("asme_b200_tc_score_ce_bwd", _p(hb), R, H, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
+              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _stream())
+    return dh
+
+
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, act: int = 0, gelu_grad_of=None,
             p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out_f32: bool = True, out_bf16: bool = False,
             pre_act: bool = False, post_site: int = 0, bf16_into: Optional[torch.Tensor] = None):
@@ -577,6 +593,17 @@ def adam_step(param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step):
         _lib.note = f"n={param.numel()}"
     _lib.call("asme_b200_adam_step", _p(param), _p(grad), _p(m), _p(v), param.numel(), float(lr), float(beta1),
               float(beta2), float(eps), float(weight_decay), int(step), _stream())
+
+
+def step_state_advance(state: torch.Tensor):
+    _lib.call("asme_b200_step_state_advance", _p(state), _stream())
+
+
+def adam_step_dev(param, grad, m, v, state: torch.Tensor, beta1, beta2, eps, weight_decay):
+    if _lib.timing is not None:
+        _lib.note = f"n={param.numel()}"
+    _lib.call("asme_b200_adam_step_dev", _p(param), _p(grad), _p(m), _p(v), param.numel(), _p(state), float(beta1), float(beta2),
+              float(eps), float(weight_decay), _stream())
 
 
 def fill(x: torch.Tensor, value: float):

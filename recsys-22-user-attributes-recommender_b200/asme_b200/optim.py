@@ -13,6 +13,7 @@ class FusedAdam(torch.optim.Optimizer):
         params = [p for _, p in model._named_arena_params()]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._steps = 0
+        self.step_state = None      # graphs.StepState: when set, step count and learning rate are read from device memory
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -25,8 +26,12 @@ class FusedAdam(torch.optim.Optimizer):
         g = arena.ensure_grad()
         m, v = arena.ensure_moments()
         self._steps += 1
-        ops.adam_step(arena.flat, g, m, v, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
-                      group["weight_decay"], self._steps)
+        if self.step_state is not None:
+            ops.adam_step_dev(arena.flat, g, m, v, self.step_state.tensor, group["betas"][0], group["betas"][1], group["eps"],
+                              group["weight_decay"])
+        else:
+            ops.adam_step(arena.flat, g, m, v, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
+                          group["weight_decay"], self._steps)
         arena.bump()        # the kernel wrote the weights through raw pointers: invalidate the bf16 shadow
         return loss
 

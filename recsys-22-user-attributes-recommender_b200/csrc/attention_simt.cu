@@ -183,10 +183,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_query_kernel(AttnParams p
                     float4 pv = make_float4(s[0][i], s[1][i], s[2][i], s[3][i]);
                     if (p.p_drop > 0.f) {
                         const uint64_t base = ((uint64_t)bh * S + q0) * S + j;
-                        pv.x *= dropout_scale(p.seed, p.site, base, p.p_drop, p.inv_keep);
-                        pv.y *= dropout_scale(p.seed, p.site, base + S, p.p_drop, p.inv_keep);
-                        pv.z *= dropout_scale(p.seed, p.site, base + 2 * (uint64_t)S, p.p_drop, p.inv_keep);
-                        pv.w *= dropout_scale(p.seed, p.site, base + 3 * (uint64_t)S, p.p_drop, p.inv_keep);
+                        pv.x *= dropout_scale(asme_seed(p.seed), p.site, base, p.p_drop, p.inv_keep);
+                        pv.y *= dropout_scale(asme_seed(p.seed), p.site, base + S, p.p_drop, p.inv_keep);
+                        pv.z *= dropout_scale(asme_seed(p.seed), p.site, base + 2 * (uint64_t)S, p.p_drop, p.inv_keep);
+                        pv.w *= dropout_scale(asme_seed(p.seed), p.site, base + 3 * (uint64_t)S, p.p_drop, p.inv_keep);
                     }
                     *reinterpret_cast<float4*>(Pw + j * 4) = pv;
                 }
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_query_kernel(AttnParams p
                         const int q = q0 + r;
                         float g = dp[r][i];
                         if (p.p_drop > 0.f)
-                            g *= dropout_scale(p.seed, p.site, ((uint64_t)bh * S + q) * S + j, p.p_drop, p.inv_keep);
+                            g *= dropout_scale(asme_seed(p.seed), p.site, ((uint64_t)bh * S + q) * S + j, p.p_drop, p.inv_keep);
                         const bool ok = q < S && key_ok(p, b, q, j);
                         ds[r] = ok ? s[r][i] * (g - D[r]) * p.scale : 0.f;
                     }
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_key_kernel(AttnParams p, 
                     const float prob = in ? expf(sc - m) * inv : 0.f;
                     float dscale = 1.f;
                     if (p.p_drop > 0.f && in)
-                        dscale = dropout_scale(p.seed, p.site, ((uint64_t)bh * S + q) * S + j, p.p_drop, p.inv_keep);
+                        dscale = dropout_scale(asme_seed(p.seed), p.site, ((uint64_t)bh * S + q) * S + j, p.p_drop, p.inv_keep);
                     pd[r] = prob * dscale;
                     ds[r] = ok ? prob * (dp[r][i] * dscale - D) * p.scale : 0.f;
                 }
@@ -363,7 +363,7 @@ static AttnParams make_params(const float* qkv, const uint8_t* key_valid, int B,
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-    ASME_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    { const int _rc = asme_ensure_max_smem((const void*)kernel); if (_rc) return _rc; }
     return ASME_OK;
 }
 

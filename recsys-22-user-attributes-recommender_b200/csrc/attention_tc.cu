@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             // ---- pass 2: exp, partial row sum, dropout, P -> shared memory (bf16, 128B-swizzled K-major tile)
             float l = 0.f;
             uint32_t rowkey = 0;
-            if (a.p_drop > 0.f) rowkey = drop_rowkey(a.seed, a.site, (uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0));
+            if (a.p_drop > 0.f) rowkey = drop_rowkey(asme_seed(a.seed), a.site, (uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0));
 #pragma unroll 1
             for (int ch = ch_lo; ch < ch_hi; ++ch) {
                 float v[32];
@@ -337,7 +337,7 @@ extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, 
     a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits;
     const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnFwdShared);
-    ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _rc = asme_ensure_max_smem((const void*)attn_tc_fwd_kernel); if (_rc) return _rc; }
     attn_tc_fwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
     ASME_LAUNCH_OK();
     return ASME_OK;
@@ -663,7 +663,7 @@ extern "C" int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, 
     a.ctx = (const __nv_bfloat16*)ctx; a.d_ctx = (const __nv_bfloat16*)d_ctx; a.stats = stats;
     a.keep_bits = p_drop > 0.f ? keep_bits : nullptr; a.d_qkv = (__nv_bfloat16*)d_qkv;
     const size_t smem = 1024 + 6 * 32768 + sizeof(AttnBwdShared);
-    ASME_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd_kernel); if (_rc) return _rc; }
     attn_tc_bwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
     ASME_LAUNCH_OK();
     return ASME_OK;

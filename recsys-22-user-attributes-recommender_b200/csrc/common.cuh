@@ -29,6 +29,10 @@ void asme_set_error(const char* fmt, ...);
         }                                                                                    \
     } while (0)
 
+// Opt a kernel in to the full 227 KB of dynamic shared memory ONCE per process (the attribute call is not something to repeat
+// on every launch, and it must not happen while a stream is being captured into a CUDA graph).
+int asme_ensure_max_smem(const void* kernel);
+#define ASME_MAX_DYN_SMEM 232448
 void asme_count_launch();   // every kernel launch of this library is counted (bench.py reports it)
 #define ASME_LAUNCH_OK()                  \
     do {                                  \
@@ -95,6 +99,14 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
     }
     return make_uint4(c0, c1, c2, c3);
 }
+// A dropout seed argument with bit 63 set is a DEVICE POINTER (low 48 bits) to the seed: a training step captured in a CUDA
+// graph re-reads the seed that a tiny "advance" kernel bumps at the start of every replay (asme_b200_step_state_advance),
+// so the by-value launch arguments baked into the graph never change.  Real seeds always have bit 63 clear.
+#define ASME_SEED_INDIRECT (1ull << 63)
+__device__ __forceinline__ uint64_t asme_seed(uint64_t s) {
+    return (s & ASME_SEED_INDIRECT) ? *reinterpret_cast<const uint64_t*>(s & ~ASME_SEED_INDIRECT) : s;
+}
+
 // keep-probability scale for element `idx` of dropout site `site`: 0 if dropped, 1/(1-p) if kept
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
     const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0u, (uint32_t)seed,

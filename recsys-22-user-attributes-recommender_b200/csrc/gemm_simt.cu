@@ -39,7 +39,7 @@ __device__ __forceinline__ float apply_epilogue(float v, long long m, int n, int
     if (e.pre_act) e.pre_act[idx] = v;
     if (e.act == ASME_ACT_GELU) v = gelu_erf(v);
     if (e.mul_gelu_grad_of) v *= gelu_erf_grad(__ldg(e.mul_gelu_grad_of + idx));
-    if (e.p_drop > 0.f) v *= dropout_scale(e.seed, e.site, (uint64_t)idx, e.p_drop, e.inv_keep);
+    if (e.p_drop > 0.f) v *= dropout_scale(asme_seed(e.seed), e.site, (uint64_t)idx, e.p_drop, e.inv_keep);
     if (e.residual) v += __ldg(e.residual + idx);
     return v;
 }

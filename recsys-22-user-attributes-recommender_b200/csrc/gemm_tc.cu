@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     float s[4];
-                    dropout_scale4(a.seed, a.site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
+                    dropout_scale4(asme_seed(a.seed), a.site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
                     v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
                 }
             }
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     float s[4];
-                    dropout_scale4(a.seed, a.post_site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
+                    dropout_scale4(asme_seed(a.seed), a.post_site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
                     v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
                 }
             }
@@ -272,10 +272,10 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(ceil_div(M, G_BM), ceil_div(N, G_NT));
     if (b_is_kn) {
-        ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_tall_kernel<true>); if (_rc) return _rc; }
         tc_gemm_tall_kernel<true><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
     } else {
-        ASME_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tall_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_tall_kernel<false>); if (_rc) return _rc; }
         tc_gemm_tall_kernel<false><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
     }
     ASME_LAUNCH_OK();
@@ -477,7 +477,7 @@ extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, i
     const size_t stage_bytes = (size_t)(2 + 4) * W_SLAB * 128;
     const size_t smem = 1024 + W_STAGES * stage_bytes + (size_t)W_SLAB * 128 + sizeof(WgradBars);
     cudaStream_t st = (cudaStream_t)stream;
-    ASME_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _rc = asme_ensure_max_smem((const void*)tc_wgrad_kernel); if (_rc) return _rc; }
     tc_wgrad_kernel<<<dim3(splits, ceil_div(N, 128), ceil_div(K, 256)), G_THREADS, smem, st>>>(tmY, tmX, a);
     ASME_LAUNCH_OK();
     const long long n = (long long)N * K;

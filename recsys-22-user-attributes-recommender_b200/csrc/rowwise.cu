@@ -28,6 +28,19 @@ void asme_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long asme_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int asme_b200_abi_version(void) { return 1; }
 
+#include <mutex>
+int asme_ensure_max_smem(const void* kernel) {
+    static const void* done[256];
+    static int n_done = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_done; ++i)
+        if (done[i] == kernel) return ASME_OK;
+    ASME_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ASME_MAX_DYN_SMEM));
+    if (n_done < 256) done[n_done++] = kernel;
+    return ASME_OK;
+}
+
 #define LN_EPS 1e-5f
 
 // dropout scales for 4 consecutive elements starting at idx (idx % 4 == 0): one Philox call
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d,
         ln_forward<LANES, CH>(x, y, d.ln1_gamma, d.ln1_beta, lane, H, mean, rstd);
         if (stats && lane == 0) { stats[t] = mean; stats[(size_t)T + t] = rstd; }
         x = y;
-        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, d.seed, d.site_a, t, H, lane, d.p_drop, inv_keep);
+        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
     }
     embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
     if (d.ln2_gamma) {
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d,
         ln_forward<LANES, CH>(x, y, d.ln2_gamma, d.ln2_beta, lane, H, mean, rstd);
         if (stats && lane == 0) { stats[(size_t)2 * T + t] = mean; stats[(size_t)3 * T + t] = rstd; }
         x = y;
-        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, d.seed, d.site_b, t, H, lane, d.p_drop, inv_keep);
+        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_b, t, H, lane, d.p_drop, inv_keep);
     }
     x.store(out + t * H, lane);
 }
@@ -240,7 +253,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
                 x.v[c].x = h.x * gm.x + bt.x; x.v[c].y = h.y * gm.y + bt.y;
                 x.v[c].z = h.z * gm.z + bt.z; x.v[c].w = h.w * gm.w + bt.w;
             }
-            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, d.seed, d.site_a, t, H, lane, d.p_drop, inv_keep);
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
         }
         g.load(d_out + t * H, lane);
         if (d.ln2_gamma) {
@@ -252,12 +265,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
                 xhat2.v[c].x = (x.v[c].x - mean) * rstd2; xhat2.v[c].y = (x.v[c].y - mean) * rstd2;
                 xhat2.v[c].z = (x.v[c].z - mean) * rstd2; xhat2.v[c].w = (x.v[c].w - mean) * rstd2;
             }
-            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, d.seed, d.site_b, t, H, lane, d.p_drop, inv_keep);
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, asme_seed(d.seed), d.site_b, t, H, lane, d.p_drop, inv_keep);
             ln_backward<LANES, CH>(g, xhat2, d.ln2_gamma, lane, H, rstd2, dg2, db2);
         }
         if (d_attr_rows && d_attr_rows != d_item_rows) g.store(d_attr_rows + t * H, lane);
         if (d.ln1_gamma) {
-            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, d.seed, d.site_a, t, H, lane, d.p_drop, inv_keep);
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
             ln_backward<LANES, CH>(g, xhat1, d.ln1_gamma, lane, H, rstd1, dg1, db1);
         }
         g.store(d_item_rows + t * H, lane);
@@ -548,6 +561,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
                                uint64_t seed, uint32_t site) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    seed = asme_seed(seed);
     float4 v = ldg4(x + i * 4);
     const float4 s = dropout_scale4(seed, site, (uint64_t)i * 4, p, inv_keep);
     v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
@@ -569,6 +583,7 @@ __global__ void dropout_cast_kernel(const float* __restrict__ x, long long n4, f
                                     uint32_t site_a, uint32_t site_b, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    seed = asme_seed(seed);
     float4 v = ldg4(x + i * 4);
     if (p > 0.f && site_a) {
         const float4 s = dropout_scale4(seed, site_a, (uint64_t)i * 4, p, inv_keep);
@@ -626,6 +641,50 @@ __global__ void fill_kernel(float* x, long long n, float v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;
 }
+// ---- device-resident step state (CUDA-graph replays): {seed, adam step, learning rate} ----------------------------------------
+struct asme_step_state_t { unsigned long long seed; int adam_step; float lr; };
+__global__ void step_state_advance_kernel(asme_step_state_t* s) { s->seed += 1ull; s->adam_step += 1; }
+extern "C" int asme_b200_step_state_advance(void* state, asme_stream_t stream) {
+    ASME_REQUIRE(state, "step_state_advance: null argument");
+    step_state_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((asme_step_state_t*)state);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n4, const asme_step_state_t* __restrict__ st, float b1, float b2, float omb1, float omb2,
+                                float eps, float wd, double b1d, double b2d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int step = st->adam_step;
+    const float lr = st->lr;
+    const float bc1 = (float)(1.0 - pow(b1d, (double)step));
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(b2d, (double)step)));
+    const float step_size = (float)((double)lr / (1.0 - pow(b1d, (double)step)));
+    (void)bc1;
+    float4 pv = reinterpret_cast<float4*>(p)[i], gv = ldg4(g + i * 4), mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float grad = gp[e];
+        if (wd != 0.f) grad += wd * pp[e];
+        mp[e] = b1 * mp[e] + omb1 * grad;              // same arithmetic as adam_kernel (omb = 1 - beta evaluated in double on the host)
+        vp[e] = b2 * vp[e] + omb2 * grad * grad;
+        pp[e] = pp[e] - step_size * mp[e] / (sqrtf(vp[e]) * inv_sqrt_bc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+}
+extern "C" int asme_b200_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, const void* state,
+                                       double beta1, double beta2, double eps, double weight_decay, asme_stream_t stream) {
+    ASME_REQUIRE(param && grad && m && v && state, "adam_step_dev: null argument");
+    ASME_REQUIRE(n % 4 == 0, "adam_step_dev: n=%lld must be a multiple of 4", n);
+    if (n == 0) return ASME_OK;
+    adam_dev_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n / 4, (const asme_step_state_t*)state,
+                                                                           (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                                           (float)eps, (float)weight_decay, beta1, beta2);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
 extern "C" int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream) {
     if (n == 0) return ASME_OK;
     fill_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, value);

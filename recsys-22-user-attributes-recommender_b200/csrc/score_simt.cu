@@ -76,7 +76,7 @@ static int check_score(int R, int H, int Vloc) {
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-    ASME_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    { const int _rc = asme_ensure_max_smem((const void*)kernel); if (_rc) return _rc; }
     return ASME_OK;
 }
 

@@ -535,7 +535,7 @@ extern "C" size_t asme_b200_tc_score_topk_workspace_bytes(int R, int Kp, int Vlo
 
 template <typename K>
 static int tc_set_smem(K kernel, size_t bytes) {
-    ASME_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    { const int _rc = asme_ensure_max_smem((const void*)kernel); if (_rc) return _rc; }
     return ASME_OK;
 }
 
