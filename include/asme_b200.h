@@ -322,7 +322,7 @@ int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, i
 int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
                         double beta2, double eps, double weight_decay, int step, asme_stream_t stream);
 int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream);
-/* Device-resident step state for CUDA-graph replays of a whole training step: struct {uint64 seed; int32 adam_step; float lr}.
+/* Device-resident step state for CUDA-graph replays of a whole training step: struct {uint64 seed; double lr; int64 adam_step}.
  * asme_b200_step_state_advance (first node of the graph) bumps seed and adam_step; every dropout `seed` argument may be passed
  * as (1<<63 | device pointer to the state) instead of a value; asme_b200_adam_step_dev reads step and lr from the state. */
 int asme_b200_step_state_advance(void* state, asme_stream_t stream);

@@ -14,14 +14,12 @@ from . import ops
 
 
 class StepState:
-    """device struct {uint64 seed; int32 adam_step; float32 lr} (include/asme_b200.h, asme_b200_step_state_advance)"""
+    """device struct {uint64 seed; float64 lr; int64 adam_step} (include/asme_b200.h, asme_b200_step_state_advance)"""
 
     def __init__(self, device, seed: int = 0, adam_step: int = 0, lr: float = 0.0):
-        self.tensor = torch.zeros(4, dtype=torch.int32, device=device)
-        self.tensor[:2] = torch.tensor([seed & 0xFFFFFFFF, (seed >> 32) & 0x7FFFFFFF], dtype=torch.int64).to(torch.int32).to(device)
-        self.tensor[2] = adam_step
-        self._lr_view = self.tensor.view(torch.float32)[3:4]
-        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.tensor = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0, adam_step], dtype=torch.int64).to(device)
+        self._lr_view = self.tensor.view(torch.float64)[1:2]
+        self._lr_host = torch.zeros(1, dtype=torch.float64).pin_memory()
         self.set_lr(lr)
 
     def set_lr(self, lr: float):

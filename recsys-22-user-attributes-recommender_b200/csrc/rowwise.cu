@@ -642,7 +642,7 @@ __global__ void fill_kernel(float* x, long long n, float v) {
     if (i < n) x[i] = v;
 }
 // ---- device-resident step state (CUDA-graph replays): {seed, adam step, learning rate} ----------------------------------------
-struct asme_step_state_t { unsigned long long seed; int adam_step; float lr; };
+struct asme_step_state_t { unsigned long long seed; double lr; long long adam_step; };
 __global__ void step_state_advance_kernel(asme_step_state_t* s) { s->seed += 1ull; s->adam_step += 1; }
 extern "C" int asme_b200_step_state_advance(void* state, asme_stream_t stream) {
     ASME_REQUIRE(state, "step_state_advance: null argument");
@@ -650,35 +650,24 @@ extern "C" int asme_b200_step_state_advance(void* state, asme_stream_t stream) {
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
+__device__ __forceinline__ void adam_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                            float* __restrict__ v, long long i, float lr_over_bc1, float beta1, float beta2, float omb1,
+                                            float omb2, float eps, float wd, float inv_sqrt_bc2);
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                long long n4, const asme_step_state_t* __restrict__ st, float b1, float b2, float omb1, float omb2,
+                                long long n, const asme_step_state_t* __restrict__ st, float b1, float b2, float omb1, float omb2,
                                 float eps, float wd, double b1d, double b2d) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int step = st->adam_step;
-    const float lr = st->lr;
-    const float bc1 = (float)(1.0 - pow(b1d, (double)step));
-    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(b2d, (double)step)));
-    const float step_size = (float)((double)lr / (1.0 - pow(b1d, (double)step)));
-    (void)bc1;
-    float4 pv = reinterpret_cast<float4*>(p)[i], gv = ldg4(g + i * 4), mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        float grad = gp[e];
-        if (wd != 0.f) grad += wd * pp[e];
-        mp[e] = b1 * mp[e] + omb1 * grad;              // same arithmetic as adam_kernel (omb = 1 - beta evaluated in double on the host)
-        vp[e] = b2 * vp[e] + omb2 * grad * grad;
-        pp[e] = pp[e] - step_size * mp[e] / (sqrtf(vp[e]) * inv_sqrt_bc2 + eps);
-    }
-    reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+    if (i >= n) return;
+    const double step = (double)st->adam_step;
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(b2d, step)));       // same double-precision scalars the host computes
+    const float lr_over_bc1 = (float)(st->lr / (1.0 - pow(b1d, step)));         // for asme_b200_adam_step
+    adam_update(p, g, m, v, i, lr_over_bc1, b1, b2, omb1, omb2, eps, wd, inv_sqrt_bc2);
 }
 extern "C" int asme_b200_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, const void* state,
                                        double beta1, double beta2, double eps, double weight_decay, asme_stream_t stream) {
     ASME_REQUIRE(param && grad && m && v && state, "adam_step_dev: null argument");
-    ASME_REQUIRE(n % 4 == 0, "adam_step_dev: n=%lld must be a multiple of 4", n);
     if (n == 0) return ASME_OK;
-    adam_dev_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n / 4, (const asme_step_state_t*)state,
+    adam_dev_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, (const asme_step_state_t*)state,
                                                                            (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
                                                                            (float)eps, (float)weight_decay, beta1, beta2);
     ASME_LAUNCH_OK();
@@ -721,11 +710,9 @@ extern "C" int asme_b200_scatter_rows(const float* rows, const int64_t* row_inde
 // ---------------------------------------------------------------------------------------------
 // fused Adam over the flat arena
 // ---------------------------------------------------------------------------------------------
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps,
-                            float wd, float inv_sqrt_bc2) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void adam_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                            float* __restrict__ v, long long i, float lr_over_bc1, float beta1, float beta2, float omb1,
+                                            float omb2, float eps, float wd, float inv_sqrt_bc2) {
     float gi = g[i];
     const float pi = p[i];
     if (wd != 0.f) gi += wd * pi;
@@ -734,6 +721,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     m[i] = mi;
     v[i] = vi;
     p[i] = pi - lr_over_bc1 * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr_over_bc1, float beta1, float beta2, float omb1, float omb2, float eps,
+                            float wd, float inv_sqrt_bc2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    adam_update(p, g, m, v, i, lr_over_bc1, beta1, beta2, omb1, omb2, eps, wd, inv_sqrt_bc2);
 }
 extern "C" int asme_b200_adam_step(float* param, const float* grad, float* m, float* v, long long n, double lr, double beta1,
                                    double beta2, double eps, double weight_decay, int step, asme_stream_t stream) {

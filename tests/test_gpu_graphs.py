@@ -19,6 +19,7 @@ def _setup(seed=0):
     module = MaskedTrainingModule(model, metrics=build_metrics({"recall": [10]}), learning_rate=3e-3, num_warmup_steps=1).cuda()
     module.train()
     (opt,), _ = module.configure_optimizers()
+    opt.param_groups[0]["lr"] = 3e-3          # the warm-up LambdaLR starts at 0; these tests drive the rate by hand
     return module, opt
 
 
