@@ -463,9 +463,17 @@ def main():
     if not args.no_eval:
         eval_info = bench_eval_c5(device, pk, world=world, rank=rank)
 
-    if rank != 0:
+    def finish():
+        # CUDA graphs that captured NCCL collectives keep communicator resources alive and ncclCommDestroy can then block for ever:
+        # flush what was printed and leave without tearing the process group down.
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     top = table[0] if table else None
@@ -501,8 +509,7 @@ def main():
            "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()} for row in table[:30]],
            "kernel_ms_per_step": kernel_ms_per_step, "eval": eval_info}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0):

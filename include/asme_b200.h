@@ -232,10 +232,15 @@ int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const float* W, con
  * Same reference call sites as the fp32 entry points above (layers.py:105-143 + metrics/common.py:18-27 /
  * masked_training_module.py:107-111); the (R x V) logits exist only as 128x256 accumulator tiles in tensor memory.
  * Operands are prepared with asme_b200_cast_bf16: Hb (R,Kp) and Wb (Vloc,Kp) bf16 row-major, Kp = hidden size
- * zero-padded to a multiple of 64 (<= 256).
+ * zero-padded to a multiple of 16 (<= 272; a multiple of 64 for the CE backward).
  * ------------------------------------------------------------------------------------------ */
 /* y[r, 0..ld_out) = bf16(x[r, 0..cols)) zero padded; ld_out % 4 == 0 */
 int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, asme_stream_t stream);
+/* as above plus two extra columns right after `cols` that fold a per-row bias into the contraction (h.w + b == [h,1,1].[w,b_hi,b_lo]):
+ * mode 1 appends (1, 1) (activations), mode 2 appends bf16 hi / lo parts of bias[r] (weights); ld_out >= cols + 2, multiple of 16
+ * for the scoring kernels, which then take bias = NULL and Kp = ld_out */
+int asme_b200_cast_bf16_ext(const float* x, const float* bias, void* y, long long rows, int cols, int ld_in, int ld_out, int mode,
+                            asme_stream_t stream);
 /* One sweep over the catalog slice [v0, v0+Vloc):
  *   k > 0                      -> per row top-k (score desc, id asc): topk_val / topk_idx (R,k)
  *   target_score_out != NULL   -> score of the row's target column exactly as this kernel computes it (written by the

@@ -360,6 +360,19 @@ def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
     return y
 
 
+def cast_bf16_ext(x: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(rows, cols) fp32 -> (rows, Kp) bf16 with the two bias-folding columns appended (ones for activations when ``bias`` is
+    None, bf16 hi/lo parts of ``bias`` for weights); Kp = cols + 2 rounded up to a multiple of 16"""
+    x = _f32(x)
+    rows, cols = x.shape
+    ld_out = (cols + 2 + 15) // 16 * 16
+    y = torch.empty(rows, ld_out, dtype=torch.bfloat16, device=x.device)
+    if _lib.timing is not None:
+        _lib.note = f"rows={rows},cols={cols},ld={ld_out}"
+    _lib.call("asme_b200_cast_bf16_ext", _p(x), _p(bias), _p(y), rows, cols, cols, ld_out, 1 if bias is None else 2, _stream())
+    return y
+
+
 def _bf16(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous():
         raise RuntimeError(f"asme_b200: {name} must be a contiguous CUDA bfloat16 tensor")

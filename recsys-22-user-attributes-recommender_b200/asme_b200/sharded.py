@@ -96,12 +96,13 @@ def sharded_topk_rank(hidden_local: torch.Tensor, target_local: torch.Tensor, k:
     return out
 
 
-def tc_local_scorer(wb_shard: torch.Tensor, bias_shard: Optional[torch.Tensor], v0: int):
-    """the production per-shard scorer: tcgen05 scoring kernel over the rank's (Vloc, Kp) bf16 slice"""
+def tc_local_scorer(wb_shard: torch.Tensor, bias_shard: Optional[torch.Tensor], v0: int, folded: bool = False):
+    """the production per-shard scorer: tcgen05 scoring kernel over the rank's (Vloc, Kp) bf16 slice; ``folded``: the slice
+    carries the bias in two extra K columns (models.projection_operands_folded) and the hidden rows get the matching ones"""
     from . import ops
 
     def score(hidden_all, target_all, k, target_score_in):
-        hb = ops.cast_bf16(hidden_all, ld_out=wb_shard.shape[1])
+        hb = ops.cast_bf16_ext(hidden_all) if folded else ops.cast_bf16(hidden_all, ld_out=wb_shard.shape[1])
         return ops.tc_score_topk(hb, wb_shard, bias_shard, k, target=target_all, target_score_in=target_score_in, v0=v0,
                                  capture_target=target_score_in is None)
 

@@ -84,6 +84,38 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     *reinterpret_cast<uint2*>(y + r * ld_out + c) = o;
 }
 
+// y[r, :cols] = bf16(x[r, :cols]); y[r, cols], y[r, cols+1] = the two extra columns that fold a bias into the contraction:
+//   mode 1 (activations): 1, 1        mode 2 (weights): bf16(bias[r]), bf16(bias[r] - bf16(bias[r]))   (hi + lo: 2^-17 relative)
+// remaining columns up to ld_out are zero.  h.w + b  ==  [h, 1, 1].[w, b_hi, b_lo]  -- the scoring epilogue no longer adds a bias.
+__global__ void cast_bf16_ext_kernel(const float* __restrict__ x, const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                     long long rows, int cols, int ld_in, int ld_out, int mode) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld_out) return;
+    const long long r = i / ld_out;
+    const int c = (int)(i % ld_out);
+    float v = 0.f;
+    if (c < cols) v = x[r * ld_in + c];
+    else if (c < cols + 2) {
+        if (mode == 1) v = 1.f;
+        else {
+            const float b = bias[r];
+            const float hi = __bfloat162float(__float2bfloat16_rn(b));
+            v = c == cols ? hi : b - hi;
+        }
+    }
+    y[i] = __float2bfloat16_rn(v);
+}
+extern "C" int asme_b200_cast_bf16_ext(const float* x, const float* bias, void* y, long long rows, int cols, int ld_in, int ld_out,
+                                       int mode, asme_stream_t stream) {
+    ASME_REQUIRE(x && y && (mode == 1 || (mode == 2 && bias)), "cast_bf16_ext: bad argument");
+    ASME_REQUIRE(cols >= 1 && ld_in >= cols && ld_out >= cols + 2, "cast_bf16_ext: cols=%d ld_in=%d ld_out=%d", cols, ld_in, ld_out);
+    if (rows == 0) return ASME_OK;
+    const long long n = rows * ld_out;
+    cast_bf16_ext_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, bias, (__nv_bfloat16*)y, rows, cols, ld_in, ld_out, mode);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
 extern "C" int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, asme_stream_t stream) {
     ASME_REQUIRE(x && y, "cast_bf16: null argument");
     ASME_REQUIRE(cols >= 1 && ld_in >= cols && ld_out >= cols && ld_out % 4 == 0, "cast_bf16: cols=%d ld_in=%d ld_out=%d", cols, ld_in,
@@ -111,6 +143,7 @@ enum { EPI_TOPK = 0, EPI_CE = 1 };
 
 struct ScoreTcArgs {
     int R, Vloc, v0, k, kch, stages;
+    int last_ksteps;             // K-steps (of 16 columns) in the last 64-wide chunk: 4, or fewer when Kp % 64 != 0 (bias columns)
     int n_tiles, tiles_per_split;
     int tile_lo, tile_hi;        // this launch sweeps tiles [split*tps + tile_lo, min(n_tiles, split*tps + tile_hi)) of every split
     int part0;                   // first partial-result slot written by this launch
@@ -250,8 +283,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                     tc_fence_after();
                     const uint64_t ad = smem_desc_sw128(smem_u32(sA + (size_t)c * A_CHUNK_BYTES));
                     const uint64_t bd = smem_desc_sw128(smem_u32(sB + (size_t)s * B_CHUNK_BYTES));
-#pragma unroll
-                    for (int k4 = 0; k4 < CHUNK_K / UMMA_K; ++k4)
+                    const int nk4 = c == kch - 1 ? a.last_ksteps : CHUNK_K / UMMA_K;
+                    for (int k4 = 0; k4 < nk4; ++k4)
                         umma_bf16(d_tmem, smem_desc_advance(ad, k4 * UMMA_K * 2), smem_desc_advance(bd, k4 * UMMA_K * 2), idesc,
                                   (uint32_t)((c | k4) != 0));
                     umma_commit(&bars->empty[s]);     // the slot may be refilled once these MMAs have read it
@@ -494,14 +527,15 @@ __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 struct ScorePlan {
-    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages;
+    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps;
     size_t smem;
 };
 
 static int make_plan(int R, int Kp, int Vloc, ScorePlan* p) {
     ASME_REQUIRE(R >= 1 && Vloc >= 1, "tc score: bad shape R=%d Vloc=%d", R, Vloc);
-    ASME_REQUIRE(Kp >= 64 && Kp <= 256 && Kp % 64 == 0, "tc score: padded hidden size %d unsupported (64, 128, 192, 256)", Kp);
-    p->kch = Kp / CHUNK_K;
+    ASME_REQUIRE(Kp >= 16 && Kp <= 272 && Kp % 16 == 0, "tc score: padded hidden size %d unsupported (multiple of 16, <= 272)", Kp);
+    p->kch = ceil_div(Kp, CHUNK_K);
+    p->last_ksteps = (Kp % CHUNK_K) ? (Kp % CHUNK_K) / UMMA_K : CHUNK_K / UMMA_K;
     p->m_tiles = ceil_div(R, BM);
     p->n_tiles = ceil_div(Vloc, BN);
     int splits = ASME_NUM_SMS / p->m_tiles;
@@ -595,7 +629,7 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     const int n_sample = topk ? sample_tiles(p) : 0;
     const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
     a.bias = bias; a.target = target; a.target_score = target_score_in;
     a.pv = (float*)ws;
@@ -655,7 +689,7 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
     if (rc) return rc;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
     a.bias = bias; a.target = target; a.target_score = nullptr;
     a.pv = (float*)ws;

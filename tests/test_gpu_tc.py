@@ -284,3 +284,30 @@ def test_tc_ce_bwd_sharded(ops):
     torch.nn.functional.cross_entropy(hd @ wd.t() + bd, target).backward()
     for name, got, want in (("dH", dh, hd.grad), ("dW", dW, wd.grad), ("dbias", db, bd.grad)):
         assert float((got.double() - want).norm() / want.norm()) < 6e-3, name
+
+
+@pytest.mark.parametrize("R,V,H,k", [(130, 5000, 128, 10), (64, 1031, 100, 7), (300, 3709, 64, 10)])
+def test_tc_topk_bias_folded_into_the_contraction_exact(ops, R, V, H, k):
+    """[h,1,1].[w,b_hi,b_lo] == h.w + b: with integer data the folded operands (Kp = H+2 rounded to 16, not a multiple of 64)
+    must give exactly the ids / scores of the epilogue-bias path and of the oracle"""
+    gen = torch.Generator().manual_seed(R + V + H)
+    h, w, b = int_data(gen, R, V, H)
+    b = b + 0.5                                                     # 0.5 steps: still exact in bf16 (hi part, lo = 0)
+    target = torch.randint(0, V, (R,), generator=gen)
+    logits = ref_logits(h, w, b).float().numpy()
+    hb, wb = ops.cast_bf16_ext(h.cuda()), ops.cast_bf16_ext(w.cuda(), b.cuda())
+    assert hb.shape[1] == wb.shape[1] == (H + 2 + 15) // 16 * 16
+    out = ops.tc_score_topk(hb, wb, None, k, target=target.cuda())
+    want_ids = O.topk_ids(logits, k)
+    np.testing.assert_array_equal(out["topk_idx"].cpu().numpy(), want_ids)
+    np.testing.assert_array_equal(out["topk_val"].cpu().numpy(), np.take_along_axis(logits, want_ids, axis=1))
+    np.testing.assert_array_equal(out["target_score"].cpu().numpy(), logits[np.arange(R), target.numpy()])
+    rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, None, target.cuda())
+    want = torch.logsumexp(torch.from_numpy(logits).double(), dim=1)
+    torch.testing.assert_close((rmax + torch.log(rsum)).cpu().double(), want, rtol=1e-5, atol=1e-4)
+    # a real-valued bias: hi + lo keeps 16 mantissa bits
+    bias = torch.randn(V, generator=gen) * 0.3
+    wb2 = ops.cast_bf16_ext(w.cuda(), bias.cuda())
+    got = ops.tc_score_topk(hb, wb2, None, k, target=target.cuda())["target_score"].cpu()
+    want = torch.from_numpy(ref_logits(h, w, None).float().numpy())[torch.arange(R), target] + bias[target]
+    torch.testing.assert_close(got, want, rtol=0, atol=2e-5)
