@@ -573,7 +573,9 @@ def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0):
             "config": {"workload": "C5 full-catalog scoring + top-k eval, synthetic 1M-item catalog", "items": V, "hidden": cfg["H"],
                        "seq_len": S, "users_per_step_per_gpu": B, "k": cfg["k"], "dtype": model.precision},
             "recall@10": float(res["recall@10"]), "NDCG@10": float(res["NDCG@10"]),
-            "scoring_kernel": None if score is None else {k: score[k] for k in ("avg_ms", "bound", "achieved", "peak", "unit", "frac", "share")}}
+            "scoring_kernel": None if score is None else {k: score[k] for k in ("avg_ms", "bound", "achieved", "peak", "unit", "frac", "share")},
+            "kernels": [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in row.items() if k in ("kernel", "shape", "launches_per_step", "avg_ms", "share", "bound", "frac")}
+                        for row in table[:14]]}
 
 
 if __name__ == "__main__":

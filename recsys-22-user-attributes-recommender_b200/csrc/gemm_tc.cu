@@ -15,7 +15,8 @@
 using namespace tc;
 
 #define G_BM 128
-#define G_THREADS 256          // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+#define G_THREADS 256          // wgrad kernel: warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+#define G_TALL_THREADS 384     // tall kernel: two epilogue warpgroups (warps 4-7 and 8-11) split the tile's columns
 #define G_NT 128               // output columns per CTA: 128 TMEM columns and ~33 KB of shared memory -> 4 CTAs per SM, whose loads,
                                // MMAs and (latency-bound) epilogues overlap
 
@@ -51,7 +52,8 @@ struct TcGemmArgs {
     int ld_bf16;                       // row stride of out_bf16 (>= N), lets QKV land in a wider buffer
 };
 
-#define G_STAGES 4
+#define G_STAGES 2               // K ring depth: the MMAs of a 64-wide chunk take ~100 cycles, two slots keep TMA ahead; a small
+                                 // footprint (<= 65 KB) keeps 3-4 CTAs resident per SM, which is what hides the epilogue latency
 struct __align__(8) GemmBars {
     uint64_t full[G_STAGES];
     uint64_t empty[G_STAGES];
@@ -76,7 +78,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // CTA (m_tile, n_tile): 128 rows x NT (<= G_NT) columns; K streamed in 64-wide chunks through a ring of `stages` slots
 // (slot = A chunk 16 KB + B chunk NT x 128 B [K-major] or ceil(NT/64) x 8 KB [MN-major]).
 template <bool B_MN>
-__global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
                                                                   int stages) {
     extern __shared__ uint8_t smem_raw[];
@@ -151,14 +153,17 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_tall_kernel(const __grid_co
             umma_commit(&bars->done);
         }
     } else if (warp >= 4) {
+        const int wg = (warp - 4) / 4;                       // both warpgroups own all 128 rows, each half of the 32-column chunks
         const int q = warp % 4;
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < a.M;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const float inv_keep = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
+        const int n_chunks = NT / 32;
+        const int c_lo = wg == 0 ? 0 : (n_chunks + 1) / 2, c_hi = wg == 0 ? (n_chunks + 1) / 2 : n_chunks;
         mbar_wait(&bars->done, 0);
         tc_fence_after();
-        for (int nn = 0; nn < NT; nn += 32) {
+        for (int nn = c_lo * 32; nn < c_hi * 32; nn += 32) {
             float v[32];
             tmem_ld32(lane_addr + (uint32_t)nn, v);
             tmem_ld_wait();
@@ -273,10 +278,10 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     const dim3 grid(ceil_div(M, G_BM), ceil_div(N, G_NT));
     if (b_is_kn) {
         { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_tall_kernel<true>); if (_rc) return _rc; }
-        tc_gemm_tall_kernel<true><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
+        tc_gemm_tall_kernel<true><<<grid, G_TALL_THREADS, smem, st>>>(tmA, tmB, a, stages);
     } else {
         { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_tall_kernel<false>); if (_rc) return _rc; }
-        tc_gemm_tall_kernel<false><<<grid, G_THREADS, smem, st>>>(tmA, tmB, a, stages);
+        tc_gemm_tall_kernel<false><<<grid, G_TALL_THREADS, smem, st>>>(tmA, tmB, a, stages);
     }
     ASME_LAUNCH_OK();
     return ASME_OK;

@@ -38,6 +38,7 @@ def run(R, V, H, k):
         "count": lambda: ops.tc_score_topk(hb, wb, None, 0, target=tgt, target_score_in=ts, capture_target=False),
         "topk+count": lambda: ops.tc_score_topk(hb, wb, None, k, target=tgt, target_score_in=ts),
         "ce": lambda: ops.tc_score_ce_partial(hb, wb, None, tgt),
+        "topk+bias_folded": (lambda hbf=ops.cast_bf16_ext(h), wbf=ops.cast_bf16_ext(w, b): ops.tc_score_topk(hbf, wbf, None, k, target=tgt)),
         "cast_w": lambda: ops.cast_bf16(w),
     }
     only = os.environ.get("CASES")
