@@ -108,7 +108,11 @@ class EncoderEngine:
         return getattr(self.m, "precision", "fp32") == "bf16" and cfg.hidden % 64 == 0 and cfg.intermediate % 64 == 0
 
     # ---------------------------------------------------------------- encoder blocks, tensor-core path
-    def _blocks_forward_tc(self, x: torch.Tensor, saved: Saved) -> torch.Tensor:
+    def _blocks_forward_tc(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``select_rows`` (evaluation only): flat indices of the positions whose hidden state is needed.  Every layer but the
+        last runs on all tokens; in the last layer only K and V depend on the other positions, so everything after the attention
+        (output projection, LayerNorm, feed-forward: ~half of the layer) runs on the selected rows alone.  The selected rows are
+        bit-identical to the full computation; returns (len(select_rows), H)."""
         cfg, m = self.cfg, self.m
         H = cfg.hidden
         train = saved.training
@@ -133,6 +137,9 @@ class EncoderEngine:
                 ls.ctx, ls.ast = ops.attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa, saved.seed,
                                               self._site(l, 0), save_stats=train)
                 ls.ctx16 = ops.cast_bf16(ls.ctx, ld_out=H)
+            if select_rows is not None and l == cfg.layers - 1 and not train:
+                ls.ctx16 = ls.ctx16.index_select(0, select_rows)      # row selection (index plumbing, no arithmetic)
+                x = x.index_select(0, select_rows)
             ls.x2 = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
                                 bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,
                                 site=self._site(l, 1), residual=x)["f32"]
@@ -194,10 +201,12 @@ class EncoderEngine:
         return dx
 
     # ---------------------------------------------------------------- encoder blocks, strict fp32 path
-    def blocks_forward(self, x: torch.Tensor, saved: Saved) -> torch.Tensor:
+    def blocks_forward(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.use_tc():
             saved.extra["tc"] = True
-            return self._blocks_forward_tc(x, saved)
+            return self._blocks_forward_tc(x, saved, select_rows)
+        if select_rows is not None:
+            raise RuntimeError("row-selective encoding is implemented by the tensor-core path only")
         cfg, m = self.cfg, self.m
         H = cfg.hidden
         train = saved.training

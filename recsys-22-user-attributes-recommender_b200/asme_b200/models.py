@@ -162,6 +162,20 @@ class TransformerRecommenderModel(ArenaModule):
             return state.indirect_seed()
         return (int(self._seed) << 32) + self._step_counter
 
+    def encode_rows(self, seq: torch.Tensor, padding_mask: Optional[torch.Tensor], attrs: Dict[str, torch.Tensor],
+                    rows: torch.Tensor) -> torch.Tensor:
+        """evaluation: hidden states of the selected positions only, (len(rows), H).  Identical to ``encode(...)[rows]``; on the
+        tensor-core path the last encoder layer skips the output projection / feed-forward of every other position."""
+        if self.engine.use_tc() and not self.postfusion:
+            if not self.arena_is_intact():
+                self._repack()
+            B, S = seq.shape
+            saved = Saved(B=B, S=S, seed=0, training=False, key_valid=padding_mask)
+            x, _ = ops.embed_fwd(self._embed_spec(seq, attrs, False, 0), B, S)
+            return self.engine.blocks_forward(x, saved, select_rows=rows)
+        hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
+        return ops.gather_rows(hidden, rows)
+
     def encode(self, seq: torch.Tensor, padding_mask: Optional[torch.Tensor], attrs: Dict[str, torch.Tensor],
                training: bool = False) -> Tuple[torch.Tensor, Saved]:
         """embed + encoder blocks (+ post-fusion merge): (T,H) hidden states of every position."""
@@ -351,10 +365,9 @@ class TransformerRecommenderModel(ArenaModule):
                       select: str = "mask", mask_id: int = MASK_TOKEN_ID, with_loss: bool = False, pad_id: int = PAD_TOKEN_ID,
                       full_rank: bool = True):
         """returns dict(topk_val (B,k), topk_idx (B,k) int32, rank (B) int32 1-based, target_score (B)[, loss])"""
-        hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
         if rows is None:
             rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
-        h_rows = ops.gather_rows(hidden, rows)
+        h_rows = self.encode_rows(seq, padding_mask, attrs, rows)
         m_rows, _ = self.modify(h_rows)
         if self.precision == "bf16":
             wb, folded = self.projection_operands_folded()
@@ -384,10 +397,9 @@ def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, 
     per-shard top-k lists / target scores are merged with three NCCL calls.  Returns the rows of this rank's users."""
     import torch.distributed as dist
     from . import sharded
-    hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
     if rows is None:
         rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
-    m_rows, _ = self.modify(ops.gather_rows(hidden, rows))
+    m_rows, _ = self.modify(self.encode_rows(seq, padding_mask, attrs, rows))
     G = dist.get_world_size(group) if dist.is_initialized() else 1
     g = dist.get_rank(group) if dist.is_initialized() else 0
     wb, folded = self.projection_operands_folded()          # bias (if any) rides in two extra K columns of the table

@@ -176,3 +176,20 @@ def test_training_with_dropout_runs_and_learns_bf16():
         losses.append(float(out["loss"].detach()))
     assert all(np.isfinite(losses))
     assert np.mean(losses[-5:]) < 0.93 * np.mean(losses[:5]), losses
+
+
+def test_encode_rows_equals_full_encode_on_selected_rows():
+    """evaluation encodes only the selected positions in the last layer: bit-identical to gathering from the full encode"""
+    from asme_b200 import ops
+    from asme_b200.models import BERT4RecModel, SASRecModel, mask_position_rows, last_position_rows
+    torch.manual_seed(0)
+    for cls, kw in ((BERT4RecModel, {}), (SASRecModel, {"mode": "full"})):
+        V, S, H, B = 997, 70, 128, 37
+        model = cls(H, 2, 2, V, S, 0.1, **kw).cuda().eval()
+        seq, _, lengths = _random_batch(torch.Generator().manual_seed(2), B, S, V, p_mask=0.0)
+        seq = seq.cuda()
+        seq[torch.arange(B), (lengths - 1).cuda()] = 1
+        rows = mask_position_rows(seq, 1) if cls is BERT4RecModel else last_position_rows(seq, seq.ne(0))
+        full, _ = model.encode(seq, seq.ne(0), {}, training=False)
+        sel = model.encode_rows(seq, seq.ne(0), {}, rows)
+        assert torch.equal(sel, ops.gather_rows(full, rows))
