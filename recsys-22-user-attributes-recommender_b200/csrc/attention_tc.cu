@@ -105,7 +105,7 @@ struct __align__(8) AttnFwdShared {
 // shared-memory latencies (the one-warpgroup version issued on 25 % of the cycles).
 __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     uint8_t* sQ = smem;                       // [256 tokens][128 B]   (64 hidden columns of this slice)
     uint8_t* sK = sQ + 32768;
     uint8_t* sV = sK + 32768;
@@ -374,7 +374,7 @@ struct __align__(16) AttnBwdShared {
 __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                     const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + 32768;
     uint8_t* sV = sK + 32768;

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
                                                                   const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
                                                                   int stages) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     const int kch = a.K / CHUNK_K;
     const int n0 = blockIdx.y * G_NT;
     const int NT = min(G_NT, a.N - n0);                   // columns of this CTA (multiple of 32)
@@ -310,7 +310,7 @@ struct __align__(8) WgradBars {
 __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                 const __grid_constant__ CUtensorMap tmX, const TcWgradArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     const int nrow0 = blockIdx.y * 128;                  // first output row  (dY column) of this CTA
     const int kcol0 = blockIdx.z * 256;                  // first output column (X column) of this CTA
     const int KT = min(256, a.K - kcol0);                // output columns of this CTA (multiple of 64)

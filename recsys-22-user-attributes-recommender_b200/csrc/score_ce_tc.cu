@@ -70,7 +70,7 @@ template <int MODE>
 __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmRow,
                                                                   const __grid_constant__ CUtensorMap tmCol, const CeBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     const int kch = a.kch, stages = a.stages;
     uint8_t* sRow = smem;                                        // [kch][128 rows][128 B]
     uint8_t* sCol = sRow + (size_t)kch * CE_CHUNK_BYTES;         // [stages][kch][128 rows][128 B]

@@ -210,7 +210,7 @@ template <int EPI, int KC, bool COUNT>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     const int kch = a.kch, stages = a.stages;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)kch * A_CHUNK_BYTES;
