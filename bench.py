@@ -259,6 +259,35 @@ def algorithmic_cost(name, note):
     return 0, 0
 
 
+NCU_NAMES = {"tc_attn_bwd": "attn_tc_bwd_kernel", "tc_attn_fwd": "attn_tc_fwd_kernel", "tc_gemm": "tc_gemm_tall_kernel",
+             "tc_wgrad": "tc_wgrad_kernel", "tc_score_topk": "score_tc_kernel", "tc_score_ce_bwd": "ce_bwd_tc_kernel",
+             "tc_score_ce_partial": "score_tc_kernel"}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind a C-ABI entry point, from the committed
+    `ncu --set full` summary of this same step (profiles/*_ncu_full.json); None when there is no capture of it"""
+    import glob
+    want = NCU_NAMES.get(kernel)
+    if want is None:
+        return None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full.json")), reverse=True):
+        try:
+            recs = json.load(open(path))
+        except Exception:
+            continue
+        for r in recs:
+            if want in r.get("kernel", ""):
+                def mb(x):
+                    v, u = x.split()[:2]
+                    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+                try:
+                    return {"bytes_per_launch": mb(r["dram__bytes_read.sum"]) + mb(r["dram__bytes_write.sum"]), "source": os.path.basename(path)}
+                except Exception:
+                    return None
+    return None
+
+
 def summarise_kernels(records, steps, pk):
     """records: (name, note, ms). Returns per-entry-point table (sorted by share) and the roofline of the top one."""
     groups = {}
@@ -480,7 +509,7 @@ def main():
     roofline = None
     if top:
         roofline = {"kernel": top["kernel"], "shape": top["shape"], "bound": top["bound"], "achieved": top["achieved"],
-                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": ncu_traffic(top["kernel"]),
                     "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"], "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "algorithmic_flops_per_launch": top["algorithmic_flops"]}
     cpu = None

@@ -69,10 +69,15 @@ def run(verbose: bool = True):
     assert abs(float(loss16) - float(ref_loss)) < 1e-3 * max(1.0, abs(float(ref_loss))), (float(loss16), float(ref_loss))
     model.eval()
     out16 = model.evaluate_rank(ev.cuda(), ev.cuda().ne(0), {}, tgt.cuda(), k=10)
+    # bf16 operands through two encoder layers with N(0, 0.2) weights: scores within 3e-2 of the logit scale; ranks may move
+    # only past competitors whose oracle score is that close to the target's
     scale = np.abs(rows).max()
+    tol = 3e-2 * scale
     got16 = np.take_along_axis(rows, out16["topk_idx"].cpu().numpy().astype(np.int64), 1)
-    assert np.abs(got16 - srt[:, :10]).max() < 4e-3 * scale, np.abs(got16 - srt[:, :10]).max()
-    assert (np.abs(out16["rank"].cpu().numpy() - want_rank) <= 3).all()
+    assert np.abs(got16 - srt[:, :10]).max() < tol, (np.abs(got16 - srt[:, :10]).max(), scale)
+    st = rows[np.arange(B), tgt.numpy()][:, None]
+    near = (np.abs(rows - st) <= tol).sum(axis=1) - 1
+    assert (np.abs(out16["rank"].cpu().numpy() - want_rank) <= near).all(), (out16["rank"].cpu().numpy(), want_rank, near)
     if verbose:
         print(f"[asme_b200 smoke] fp32 loss={float(loss):.6f} bf16/tcgen05 loss={float(loss16):.6f} (oracle {float(ref_loss):.6f}); "
               f"ranks={got_rank.tolist()} OK")

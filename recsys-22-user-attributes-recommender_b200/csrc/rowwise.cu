@@ -346,28 +346,31 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ x, int M, int N, 
     for (int m = m0; m < m1; ++m) s += x[(size_t)m * N + n];
     partial[(size_t)blockIdx.y * N + n] = s;
 }
-// out[n] (+)= sum_c partial[c][n].  Launched with 128 threads per block: 32 columns x 4 chunk groups (the single-thread loop
-// over several hundred partial rows used to take ~30 us per call); fixed summation order -> deterministic.
-__global__ void __launch_bounds__(128) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N,
-                                                            float* __restrict__ out, int accumulate) {
-    __shared__ float red[4][32];
+// out[n] (+)= sum_c partial[c][n].  1024 threads per block: 32 columns x 32 chunk groups, four independent accumulators per
+// thread, so a reduction over several hundred partial rows is ~5 dependent load rounds instead of hundreds (it used to take
+// 25-30 us per call, ~10 % of a training step); fixed summation order -> deterministic.
+__global__ void __launch_bounds__(1024) colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N,
+                                                             float* __restrict__ out, int accumulate) {
+    __shared__ float red[32][33];
     const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
     const int n = blockIdx.x * 32 + tx;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (n < N) {
         int c = ty;
-        for (; c + 12 < chunks; c += 16) {
+        for (; c + 96 < chunks; c += 128) {
             s0 += partial[(size_t)c * N + n];
-            s1 += partial[(size_t)(c + 4) * N + n];
-            s2 += partial[(size_t)(c + 8) * N + n];
-            s3 += partial[(size_t)(c + 12) * N + n];
+            s1 += partial[(size_t)(c + 32) * N + n];
+            s2 += partial[(size_t)(c + 64) * N + n];
+            s3 += partial[(size_t)(c + 96) * N + n];
         }
-        for (; c < chunks; c += 4) s0 += partial[(size_t)c * N + n];
+        for (; c < chunks; c += 32) s0 += partial[(size_t)c * N + n];
     }
     red[ty][tx] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (ty == 0 && n < N) {
-        const float s = (red[0][tx] + red[1][tx]) + (red[2][tx] + red[3][tx]);
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) s += red[g][tx];
         out[n] = accumulate ? out[n] + s : s;
     }
 }
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(128) colsum_stage2_kernel(const float* __restr
 static int launch_colsum(const float* x, int M, int N, float* out, int accumulate, void* ws, size_t ws_bytes,
                          cudaStream_t stream) {
     if (M <= COLSUM_ROWS) {   // small: single stage
-        colsum_stage2_kernel<<<ceil_div(N, 32), 128, 0, stream>>>(x, M, N, out, accumulate);
+        colsum_stage2_kernel<<<ceil_div(N, 32), 1024, 0, stream>>>(x, M, N, out, accumulate);
         ASME_LAUNCH_OK();
         return ASME_OK;
     }
@@ -387,7 +390,7 @@ static int launch_colsum(const float* x, int M, int N, float* out, int accumulat
     float* partial = (float*)ws;
     colsum_stage1_kernel<<<dim3(ceil_div(N, 128), chunks), 128, 0, stream>>>(x, M, N, partial);
     ASME_LAUNCH_OK();
-    colsum_stage2_kernel<<<ceil_div(N, 32), 128, 0, stream>>>(partial, chunks, N, out, accumulate);
+    colsum_stage2_kernel<<<ceil_div(N, 32), 1024, 0, stream>>>(partial, chunks, N, out, accumulate);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -489,7 +492,7 @@ extern "C" int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H
 #undef CALL
     ASME_LAUNCH_OK();
     if (dln) {
-        colsum_stage2_kernel<<<ceil_div(4 * H, 32), 128, 0, (cudaStream_t)stream>>>(partials, grid, 4 * H, dln, 1);
+        colsum_stage2_kernel<<<ceil_div(4 * H, 32), 1024, 0, (cudaStream_t)stream>>>(partials, grid, 4 * H, dln, 1);
         ASME_LAUNCH_OK();
     }
     return ASME_OK;
@@ -549,7 +552,7 @@ extern "C" int asme_b200_layernorm_bwd(const float* dy, const float* x, const fl
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
-    colsum_stage2_kernel<<<ceil_div(2 * H, 32), 128, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
+    colsum_stage2_kernel<<<ceil_div(2 * H, 32), 1024, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
