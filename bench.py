@@ -509,7 +509,9 @@ def main():
     roofline = None
     if top:
         roofline = {"kernel": top["kernel"], "shape": top["shape"], "bound": top["bound"], "achieved": top["achieved"],
-                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": ncu_traffic(top["kernel"]),
+                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+                    "traffic": (ncu_traffic(top["kernel"]) or {}).get("bytes_per_launch"),
+                    "traffic_source": (ncu_traffic(top["kernel"]) or {}).get("source"),
                     "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"], "peak_source": pk["source"],
                     "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "algorithmic_flops_per_launch": top["algorithmic_flops"]}
     cpu = None
