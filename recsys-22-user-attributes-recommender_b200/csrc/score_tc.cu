@@ -252,14 +252,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         if (lane == 0) {
             mbar_arrive_expect_tx(&bars->a_full, (uint32_t)kch * A_CHUNK_BYTES);
             for (int c = 0; c < kch; ++c) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
-            int j = 0;                                    // chunk counter: ring slot = j % stages
+            int s = 0;                                    // ring slot and its phase, advanced without integer division
+            uint32_t ph = 0;
             for (int t = t0; t < t1; ++t) {
-                for (int c = 0; c < kch; ++c, ++j) {
-                    const int s = j % stages;
-                    const uint32_t ph = (uint32_t)(j / stages) & 1u;
+                for (int c = 0; c < kch; ++c) {
                     mbar_wait(&bars->empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&bars->full[s], (uint32_t)B_CHUNK_BYTES);
                     tma_load_2d(sB + (size_t)s * B_CHUNK_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -269,25 +269,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const uint32_t idesc = idesc_bf16_f32(BM, BN);
             mbar_wait(&bars->a_full, 0);
             tc_fence_after();
-            int i = 0, j = 0;
+            // This single thread paces the tensor core: one 128x256x16 MMA is 128 cycles, so a whole tile (kch*4 MMAs) must be
+            // issued in well under kch*512 cycles.  Descriptors are therefore built once and advanced by adds, the ring slot /
+            // phase are tracked without integer division, and the four MMAs of a chunk are issued back to back.
+            const uint64_t adesc0 = smem_desc_sw128(smem_u32(sA));
+            const uint64_t bdesc0 = smem_desc_sw128(smem_u32(sB));
+            int i = 0, s = 0;
+            uint32_t ph = 0;
             for (int t = t0; t < t1; ++t, ++i) {
                 const int as = i & 1;
                 const uint32_t aph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bars->tempty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
-                for (int c = 0; c < kch; ++c, ++j) {
-                    const int s = j % stages;
-                    const uint32_t ph = (uint32_t)(j / stages) & 1u;
+                for (int c = 0; c < kch; ++c) {
                     mbar_wait(&bars->full[s], ph);
                     tc_fence_after();
-                    const uint64_t ad = smem_desc_sw128(smem_u32(sA + (size_t)c * A_CHUNK_BYTES));
-                    const uint64_t bd = smem_desc_sw128(smem_u32(sB + (size_t)s * B_CHUNK_BYTES));
-                    const int nk4 = c == kch - 1 ? a.last_ksteps : CHUNK_K / UMMA_K;
-                    for (int k4 = 0; k4 < nk4; ++k4)
-                        umma_bf16(d_tmem, smem_desc_advance(ad, k4 * UMMA_K * 2), smem_desc_advance(bd, k4 * UMMA_K * 2), idesc,
-                                  (uint32_t)((c | k4) != 0));
+                    const uint64_t ad = adesc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
+                    const uint64_t bd = bdesc0 + (uint64_t)(s * (B_CHUNK_BYTES >> 4));
+                    if (c < kch - 1 || a.last_ksteps == 4) {
+                        umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(c != 0));
+                        umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                    } else {
+                        for (int k4 = 0; k4 < a.last_ksteps; ++k4) umma_bf16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (uint32_t)((c | k4) != 0));
+                    }
                     umma_commit(&bars->empty[s]);     // the slot may be refilled once these MMAs have read it
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(&bars->tfull[as]);        // accumulator ready for the epilogue
             }
