@@ -252,6 +252,9 @@ int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void* Wb, const
                             const int64_t* target, const float* target_score_in, int k, float* topk_val,
                             int32_t* topk_idx, float* target_score_out, int32_t* n_greater, int32_t* n_tie_lower,
                             void* ws, size_t ws_bytes, asme_stream_t stream);
+/* diagnostic: the same sweep with an empty epilogue -- the ceiling of the TMA -> tcgen05.mma -> TMEM pipeline for this shape */
+int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, const void* Wb, int Vloc, int read_tmem /* also read (and
+    discard) every accumulator: TMEM read throughput */, asme_stream_t stream);
 /* cross-entropy partials over the slice: row_max, row_sumexp (natural units, combine across shards as for the fp32
  * entry point) and target_logit (owner shard writes; caller zero-fills) */
 size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc);

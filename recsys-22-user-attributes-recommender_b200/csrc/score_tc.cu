@@ -139,7 +139,7 @@ extern "C" int asme_b200_cast_bf16(const float* x, void* y, long long rows, int 
 #define MAX_STAGES 6
 #define L2E 1.4426950408889634f
 
-enum { EPI_TOPK = 0, EPI_CE = 1 };
+enum { EPI_TOPK = 0, EPI_CE = 1, EPI_PROBE = 2 };   // EPI_PROBE: diagnostic, epilogue = TMEM handshake only (pipeline ceiling)
 
 struct ScoreTcArgs {
     int R, Vloc, v0, k, kch, stages;
@@ -342,6 +342,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const uint32_t aph = (uint32_t)(i >> 1) & 1u;
             mbar_wait(&bars->tfull[as], aph);
             tc_fence_after();
+            if (EPI == EPI_PROBE) {          // a.k == 0: no TMEM reads at all (what TMA + MMA + handshakes sustain);
+                if (a.k != 0) {              // a.k != 0: read the whole accumulator and discard it (TMEM read throughput)
+                    float v[32];
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * 128 + ch * 32), v);
+                        tmem_ld_wait();
+                    }
+                    if (v[0] == 12345.678f) a.captured[0] = v[1];      // keep the loads alive (a.captured is NULL in the probe)
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                continue;
+            }
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 const int col0 = t * BN + wg * 128 + ch * 32;     // local column of v[0]
@@ -668,6 +683,28 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     }
     tc_topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(topk ? a.pv : nullptr, a.pi, count ? a.pg : nullptr, a.pt, total_parts, R, k,
                                                          topk_val, topk_idx, n_greater, n_tie_lower);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// diagnostic: the scoring sweep with an empty epilogue (upper bound of what the TMA -> MMA -> TMEM pipeline sustains)
+extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, const void* Wb, int Vloc, int read_tmem,
+                                                 asme_stream_t stream) {
+    ASME_REQUIRE(Hb && Wb, "tc_score_pipeline_probe: null operand");
+    ScorePlan p;
+    int rc = make_plan(R, Kp, Vloc, &p);
+    if (rc) return rc;
+    CUtensorMap tmA, tmB;
+    rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
+    if (rc) return rc;
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    if (rc) return rc;
+    ScoreTcArgs a{};
+    a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.k = read_tmem ? 1 : 0;
+    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_lo = 0; a.tile_hi = p.tiles_per_split;
+    rc = tc_set_smem(score_tc_kernel<EPI_PROBE, 0, false>, p.smem);
+    if (rc) return rc;
+    score_tc_kernel<EPI_PROBE, 0, false><<<dim3(p.m_tiles, p.splits), TC_THREADS, p.smem, (cudaStream_t)stream>>>(tmA, tmB, a);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

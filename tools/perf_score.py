@@ -39,6 +39,8 @@ def run(R, V, H, k):
         "topk+count": lambda: ops.tc_score_topk(hb, wb, None, k, target=tgt, target_score_in=ts),
         "ce": lambda: ops.tc_score_ce_partial(hb, wb, None, tgt),
         "topk+bias_folded": (lambda hbf=ops.cast_bf16_ext(h), wbf=ops.cast_bf16_ext(w, b): ops.tc_score_topk(hbf, wbf, None, k, target=tgt)),
+        "probe": lambda: ops._lib.call("asme_b200_tc_score_pipeline_probe", ops._p(hb), R, hb.shape[1], ops._p(wb), V, 0, ops._stream()),
+        "probe_ld": lambda: ops._lib.call("asme_b200_tc_score_pipeline_probe", ops._p(hb), R, hb.shape[1], ops._p(wb), V, 1, ops._stream()),
         "cast_w": lambda: ops.cast_bf16(w),
     }
     only = os.environ.get("CASES")
