@@ -187,33 +187,50 @@ __device__ __forceinline__ void embed_gather_attrs(Row<LANES, CH>& x, const asme
     }
 }
 
-template <int LANES, int CH>
+// TOK tokens per lane group: all ids, then all item rows are requested before anything is consumed, so every group keeps
+// TOK independent 128-bit gathers in flight (a random 256-512 B row per token is latency-bound otherwise).  A block covers
+// TOK * groups consecutive tokens; token j of group g is base + j * groups + g, so stores stay coalesced across groups.
+template <int LANES, int CH, int TOK>
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d, int T, int S, int H, float* __restrict__ out,
                                                         float* __restrict__ stats) {
     const int lane = threadIdx.x % LANES;
-    const long long t = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
-    if (t >= T) return;
+    const int groups = blockDim.x / LANES;
+    const long long base = (long long)blockIdx.x * (groups * TOK) + threadIdx.x / LANES;
     const float inv_keep = d.p_drop > 0.f ? 1.0f / (1.0f - d.p_drop) : 1.0f;
-    Row<LANES, CH> x, y;
-    const long long item = __ldg(d.item_ids + t);
-    x.load(d.item_table + item * H, lane);
-    if (d.pos_table) x.add(d.pos_table + (long long)(t % S) * H, lane);
-    if (d.ln1_gamma) {
-        float mean, rstd;
-        ln_forward<LANES, CH>(x, y, d.ln1_gamma, d.ln1_beta, lane, H, mean, rstd);
-        if (stats && lane == 0) { stats[t] = mean; stats[(size_t)T + t] = rstd; }
-        x = y;
-        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
+    long long item[TOK];
+    Row<LANES, CH> xs[TOK];
+#pragma unroll
+    for (int j = 0; j < TOK; ++j) {
+        const long long t = base + (long long)j * groups;
+        item[j] = t < T ? __ldg(d.item_ids + t) : 0;
     }
-    embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
-    if (d.ln2_gamma) {
-        float mean, rstd;
-        ln_forward<LANES, CH>(x, y, d.ln2_gamma, d.ln2_beta, lane, H, mean, rstd);
-        if (stats && lane == 0) { stats[(size_t)2 * T + t] = mean; stats[(size_t)3 * T + t] = rstd; }
-        x = y;
-        if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_b, t, H, lane, d.p_drop, inv_keep);
+#pragma unroll
+    for (int j = 0; j < TOK; ++j) xs[j].load(d.item_table + item[j] * H, lane);
+    // no early exit below: the TOK iterations stay independent straight-line code, so their shuffle / LayerNorm chains interleave
+#pragma unroll
+    for (int j = 0; j < TOK; ++j) {
+        const long long tj = base + (long long)j * groups;
+        const bool ok = tj < T;
+        const long long t = ok ? tj : 0;
+        Row<LANES, CH> x = xs[j], y;
+        if (d.pos_table) x.add(d.pos_table + (long long)(t % S) * H, lane);
+        if (d.ln1_gamma) {
+            float mean, rstd;
+            ln_forward<LANES, CH>(x, y, d.ln1_gamma, d.ln1_beta, lane, H, mean, rstd);
+            if (stats && lane == 0 && ok) { stats[t] = mean; stats[(size_t)T + t] = rstd; }
+            x = y;
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
+        }
+        if (d.n_attr | d.n_bag) embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
+        if (d.ln2_gamma) {
+            float mean, rstd;
+            ln_forward<LANES, CH>(x, y, d.ln2_gamma, d.ln2_beta, lane, H, mean, rstd);
+            if (stats && lane == 0 && ok) { stats[(size_t)2 * T + t] = mean; stats[(size_t)3 * T + t] = rstd; }
+            x = y;
+            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_b, t, H, lane, d.p_drop, inv_keep);
+        }
+        if (ok) x.store(out + t * H, lane);
     }
-    x.store(out + t * H, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -452,7 +469,14 @@ extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H
     if (T == 0) return ASME_OK;
     const int lanes = lanes_for(H);
     const int groups = 256 / lanes;
-#define CALL(L, C) embed_fwd_kernel<L, C><<<ceil_div(T, groups), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats)
+    // tokens per lane group: as many as still leave >= 4 blocks per SM
+    const int tok = ceil_div(T, groups * 4) >= ASME_NUM_SMS * 4 ? 4 : (ceil_div(T, groups * 2) >= ASME_NUM_SMS * 4 ? 2 : 1);
+#define CALL(L, C)                                                                                                             \
+    {                                                                                                                          \
+        if (tok == 4) embed_fwd_kernel<L, C, 4><<<ceil_div(T, groups * 4), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats);      \
+        else if (tok == 2) embed_fwd_kernel<L, C, 2><<<ceil_div(T, groups * 2), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats); \
+        else embed_fwd_kernel<L, C, 1><<<ceil_div(T, groups), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats);                   \
+    }
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();

@@ -134,7 +134,8 @@ extern "C" int asme_b200_cast_bf16(const float* x, void* y, long long rows, int 
 #define BN 256
 #define A_CHUNK_BYTES (BM * CHUNK_ROW_BYTES)   // 16 KB
 #define B_CHUNK_BYTES (BN * CHUNK_ROW_BYTES)   // 32 KB
-#define TC_THREADS 384
+#define MAX_EPI_WGS 4           // epilogue warpgroups (template parameter WGS: 2 or 4): each owns 256/WGS columns of every tile
+#define TC_THREADS(WGS) (128 + 128 * (WGS))
 #define EPI_WARP0 4
 #define MAX_STAGES 6
 #define L2E 1.4426950408889634f
@@ -149,6 +150,9 @@ struct ScoreTcArgs {
     int part0;                   // first partial-result slot written by this launch
     const float* thr_init;       // (R, thr_stride) or NULL: a lower bound of each row's k-th best score (from a sample sweep)
     int thr_stride, thr_col;
+    int sample_mode;             // 1: threshold pass -- only the maximum of every 32-column chunk is offered to the lists (the k-th best
+                                 //    chunk maximum is a lower bound of the k-th best score: k distinct chunks hold a score >= it)
+    float thr_floor;             // diagnostic: -inf normally; +inf makes every list reject everything (cost of the insertion-free sweep)
     const float* bias;
     const int64_t* target;
     const float* target_score;   // count mode: the pivot
@@ -187,6 +191,43 @@ __device__ __forceinline__ void reg_insert(float (&lv)[KC], int (&li)[KC], float
     li[0] = here0 ? id : li[0];
 }
 
+__device__ __forceinline__ bool tc_better(float v, int id, float v2, int id2) { return v > v2 || (v == v2 && id < id2); }
+
+// insertion with the full order (score desc, id asc): parts arrive in arbitrary id order
+template <int KC>
+__device__ __forceinline__ void tie_insert(float (&lv)[KC], int (&li)[KC], float x, int id) {
+#pragma unroll
+    for (int p = KC - 1; p > 0; --p) {
+        const bool shift = tc_better(x, id, lv[p - 1], li[p - 1]);
+        const bool here = !shift && tc_better(x, id, lv[p], li[p]);
+        lv[p] = shift ? lv[p - 1] : (here ? x : lv[p]);
+        li[p] = shift ? li[p - 1] : (here ? id : li[p]);
+    }
+    const bool here0 = tc_better(x, id, lv[0], li[0]);
+    lv[0] = here0 ? x : lv[0];
+    li[0] = here0 ? id : li[0];
+}
+
+// Deferred insertion.  A candidate (score above the thread's threshold) is rare once the thresholds have converged, but
+// handling it on the spot costs the whole warp ~1000 cycles with one active lane.  Candidates are therefore only PUSHED
+// (8 bytes into a per-thread shared-memory FIFO) where they are found and INSERTED later in batches: the warp drains all
+// its FIFOs together when any of them may overflow and once at the end, so the serial insertion code runs with many
+// lanes active.  FIFO order == stream order == ascending item id, so ties still resolve to the lowest id.
+#define PEND_CAP 16             // FIFO entries per epilogue thread; drained when more than PEND_CAP - 8 are pending
+template <int KC>
+__device__ __forceinline__ void pend_drain(float (&lv)[KC], int (&li)[KC], float& thr, float thr0, int& cnt, const uint2* pend,
+                                           int stride) {
+    for (int e = 0; e < cnt; ++e) {
+        const uint2 u = pend[(size_t)e * stride];
+        const float x = __uint_as_float(u.x);
+        if (x > thr) {
+            reg_insert<KC>(lv, li, x, (int)u.y);
+            thr = fmaxf(thr0, lv[KC - 1]);
+        }
+    }
+    cnt = 0;
+}
+
 // v[c] for a run-time c in 0..31 without dynamic register indexing: 5-level select tree (31 SEL)
 __device__ __forceinline__ float sel32(const float (&v)[32], int c) {
     float a[16], b[8], d[4], e[2];
@@ -206,8 +247,8 @@ __device__ __forceinline__ float max8(const float* v) {
 }
 
 // KC = capacity of the per-thread top-k list (0: no top-k); the first a.k (<= KC) entries are reported
-template <int EPI, int KC, bool COUNT>
-__global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int EPI, int KC, bool COUNT, int WGS>
+__global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
@@ -218,6 +259,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     ScoreTcBarriers* bars = reinterpret_cast<ScoreTcBarriers*>(sB + (size_t)stages * B_CHUNK_BYTES);
     constexpr bool TOPK = KC > 0;
     constexpr int KL = KC > 0 ? KC : 1;
+    constexpr int EPI_COLS = 256 / WGS;
+    // top-k only: FIFO of pending candidates, entry e of epilogue thread i at pend[e * (WGS * 128) + i]
+    uint2* pend_base = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(ScoreTcBarriers) + 15) & ~(size_t)15));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int m0 = blockIdx.x * BM;
@@ -237,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars->tfull[s], 1);
-            mbar_init(&bars->tempty[s], 8);
+            mbar_init(&bars->tempty[s], 4 * WGS);
         }
         fence_barrier_init();
     }
@@ -303,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         }
     } else if (warp >= EPI_WARP0) {
         // ===================================== epilogue =====================================
-        const int wg = (warp - EPI_WARP0) / 4;       // which 128-column half of the tile
+        const int wg = (warp - EPI_WARP0) / 4;       // which EPI_COLS-column slice of the tile
         const int q = warp % 4;                      // TMEM lane quarter this warp may access
         const int tid = q * 32 + lane;               // row within the M tile == TMEM lane
         const int row = m0 + tid;
@@ -330,7 +374,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             const float t_row = a.thr_init[(size_t)row * a.thr_stride + a.thr_col];
             thr0 = t_row == -INFINITY ? t_row : nextafterf(t_row, -INFINITY);
         }
+        thr0 = fmaxf(thr0, a.thr_floor);
         float thr = thr0;
+        uint2* pend = pend_base + ((warp - EPI_WARP0) * 32 + lane);
+        int cnt = 0;
         int cg = 0, ct = 0;
         float st = INFINITY;
         if (EPI == EPI_TOPK && COUNT && row_ok) st = a.target_score[row];
@@ -346,8 +393,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 if (a.k != 0) {              // a.k != 0: read the whole accumulator and discard it (TMEM read throughput)
                     float v[32];
 #pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * 128 + ch * 32), v);
+                    for (int ch = 0; ch < EPI_COLS / 32; ++ch) {
+                        tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * EPI_COLS + ch * 32), v);
                         tmem_ld_wait();
                     }
                     if (v[0] == 12345.678f) a.captured[0] = v[1];      // keep the loads alive (a.captured is NULL in the probe)
@@ -358,12 +405,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 continue;
             }
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                const int col0 = t * BN + wg * 128 + ch * 32;     // local column of v[0]
+            for (int ch = 0; ch < EPI_COLS / 32; ++ch) {
+                const int col0 = t * BN + wg * EPI_COLS + ch * 32;     // local column of v[0]
                 float v[32];
-                tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * 128 + ch * 32), v);
+                tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * EPI_COLS + ch * 32), v);
                 tmem_ld_wait();
-                if (ch == 3) {   // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                if (ch == EPI_COLS / 32 - 1) {   // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tempty[as]);
@@ -425,17 +472,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < 4; ++j) m8[j] = max8(v + 8 * j);
                         const float mc = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-                        if (mc > thr) {      // rare once the threshold has converged: gather the candidates, ONE insertion site
-                            uint32_t cand = 0;
+                        if (__any_sync(0xffffffffu, mc > thr)) {      // rare once the thresholds have converged
+                            if (a.sample_mode) {      // warp-uniform
+                                if (__any_sync(0xffffffffu, cnt > PEND_CAP - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
+                                if (mc > thr) {
+                                    pend[(size_t)cnt * (WGS * 128)] = make_uint2(__float_as_uint(mc), (uint32_t)(a.v0 + col0));
+                                    ++cnt;
+                                }
+                            } else
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) cand |= (v[c] > thr) ? (1u << c) : 0u;
-                            while (cand) {
-                                const int c = __ffs(cand) - 1;
-                                cand &= cand - 1;
-                                const float x = sel32(v, c);
-                                if (x > thr) {
-                                    reg_insert<KL>(lv, li, x, a.v0 + col0 + c);
-                                    thr = fmaxf(thr0, lv[KL - 1]);
+                            for (int j = 0; j < 4; ++j) {
+                                if (__any_sync(0xffffffffu, cnt > PEND_CAP - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
+                                if (m8[j] > thr) {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) {
+                                        const float x = v[8 * j + c];
+                                        if (x > thr) {
+                                            pend[(size_t)cnt * (WGS * 128)] = make_uint2(__float_as_uint(x), (uint32_t)(a.v0 + col0 + 8 * j + c));
+                                            ++cnt;
+                                        }
+                                    }
                                 }
                             }
                         }
@@ -443,9 +499,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
                 }
             }
         }
-        // --- write this (split, warpgroup)'s partial results ---
-        if (row_ok) {
-            const size_t part = (size_t)a.part0 + (size_t)split * 2 + wg;
+        if (TOPK) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
+        // --- fold the warpgroups' results into warpgroup 0 through the table ring (idle: every MMA of this CTA has completed),
+        //     so that the CTA emits ONE partial result per row
+        if (EPI != EPI_PROBE) {
+            constexpr int SLOTS = EPI == EPI_CE ? 2 : (2 * KL + 2);       // 32-bit words staged per row and warpgroup
+            uint32_t* xs = reinterpret_cast<uint32_t*>(sB);               // [WGS-1][SLOTS][128]
+            if (wg > 0) {
+                uint32_t* mine = xs + (size_t)(wg - 1) * SLOTS * 128 + tid;
+                if (EPI == EPI_CE) {
+                    mine[0] = __float_as_uint(run_m);
+                    mine[128] = __float_as_uint(run_s);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < KL; ++p) {
+                        mine[(size_t)(2 * p) * 128] = __float_as_uint(lv[p]);
+                        mine[(size_t)(2 * p + 1) * 128] = (uint32_t)li[p];
+                    }
+                    mine[(size_t)(2 * KL) * 128] = (uint32_t)cg;
+                    mine[(size_t)(2 * KL + 1) * 128] = (uint32_t)ct;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");      // the epilogue warps only
+            if (wg == 0) {
+#pragma unroll 1
+                for (int w = 0; w < WGS - 1; ++w) {
+                    const uint32_t* other = xs + (size_t)w * SLOTS * 128 + tid;
+                    if (EPI == EPI_CE) {
+                        const float m2 = __uint_as_float(other[0]), s2 = __uint_as_float(other[128]);
+                        const float m_new = fmaxf(run_m, m2);
+                        if (m_new > -INFINITY) run_s = run_s * exp2f(run_m - m_new) + s2 * exp2f(m2 - m_new);
+                        run_m = m_new;
+                    } else {
+                        if (TOPK) {
+#pragma unroll 1
+                            for (int p = 0; p < KL; ++p) {                 // sorted: stop at the first entry that cannot enter
+                                const float x = __uint_as_float(other[(size_t)(2 * p) * 128]);
+                                const int id = (int)other[(size_t)(2 * p + 1) * 128];
+                                if (id == INT_MAX || !tc_better(x, id, lv[KL - 1], li[KL - 1])) break;
+                                tie_insert<KL>(lv, li, x, id);
+                            }
+                        }
+                        if (COUNT) {
+                            cg += (int)other[(size_t)(2 * KL) * 128];
+                            ct += (int)other[(size_t)(2 * KL + 1) * 128];
+                        }
+                    }
+                }
+            }
+        }
+        // --- write this split's partial results ---
+        if (row_ok && wg == 0) {
+            const size_t part = (size_t)a.part0 + (size_t)split;
             const size_t o = part * a.R + row;
             if (EPI == EPI_CE) {
                 a.pv[o] = run_m;      // log2 units
@@ -478,42 +583,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------------------
 // merge of the partial results: one warp per row
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool tc_better(float v, int id, float v2, int id2) { return v > v2 || (v == v2 && id < id2); }
-
-__global__ void tc_topk_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, const int* __restrict__ pg,
-                                     const int* __restrict__ pt, int parts, int R, int k, float* __restrict__ out_v,
-                                     int32_t* __restrict__ out_i, int32_t* __restrict__ out_g, int32_t* __restrict__ out_t) {
+// One warp per row.  Phase 1: lane l folds parts l, l+32, ... into a register list (all loads of a part are independent and
+// the lanes work on different parts, so the kernel pays a handful of memory latencies instead of one per part).  Phase 2:
+// k rounds of warp arg-max over the list heads; the winning lane pops its head.
+template <int KC>
+__global__ void __launch_bounds__(128) tc_topk_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi,
+                                                            const int* __restrict__ pg, const int* __restrict__ pt, int parts, int R,
+                                                            int k, float* __restrict__ out_v, int32_t* __restrict__ out_i,
+                                                            int32_t* __restrict__ out_g, int32_t* __restrict__ out_t) {
     const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= R) return;
-    if (pv) {
-        // lane-distributed sorted list: lane i holds the i-th best
-        float lv = -INFINITY;
-        int li = INT_MAX;
-        for (int p = 0; p < parts; ++p) {
+    if (KC > 0 && pv) {
+        constexpr int KL = KC > 0 ? KC : 1;
+        float lv[KL];
+        int li[KL];
+#pragma unroll
+        for (int p = 0; p < KL; ++p) { lv[p] = -INFINITY; li[p] = INT_MAX; }
+        for (int p = lane; p < parts; p += 32) {
             const size_t o = ((size_t)p * R + row) * k;
-            float v = -INFINITY;
-            int id = INT_MAX;
-            if (lane < k) { v = pv[o + lane]; id = pi[o + lane]; }
-            // candidates of one part arrive sorted; offer them one by one while they can still enter the list
-            for (int j = 0; j < k; ++j) {
-                const float cv = __shfl_sync(0xffffffffu, v, j);
-                const int ci = __shfl_sync(0xffffffffu, id, j);
-                if (ci == INT_MAX) break;                                   // warp-uniform: rest of this part is empty
-                const float tail_v = __shfl_sync(0xffffffffu, lv, k - 1);
-                const int tail_i = __shfl_sync(0xffffffffu, li, k - 1);
-                if (!tc_better(cv, ci, tail_v, tail_i)) break;              // sorted part: nothing further can enter
-                const unsigned keep = __ballot_sync(0xffffffffu, tc_better(lv, li, cv, ci));
-                const int pos = __popc(keep);
-                const float up_v = __shfl_up_sync(0xffffffffu, lv, 1);
-                const int up_i = __shfl_up_sync(0xffffffffu, li, 1);
-                if (lane == pos) { lv = cv; li = ci; }
-                else if (lane > pos) { lv = up_v; li = up_i; }
+            float cv[KL];
+            int ci[KL];
+#pragma unroll
+            for (int j = 0; j < KL; ++j) {
+                cv[j] = j < k ? __ldg(pv + o + j) : -INFINITY;
+                ci[j] = j < k ? __ldg(pi + o + j) : INT_MAX;
+            }
+#pragma unroll
+            for (int j = 0; j < KL; ++j) {
+                // a part is sorted: once an entry is empty or cannot enter, neither can the rest
+                if (ci[j] == INT_MAX || !tc_better(cv[j], ci[j], lv[KL - 1], li[KL - 1])) break;
+                tie_insert<KL>(lv, li, cv[j], ci[j]);
             }
         }
+        float ov = -INFINITY;
+        int oi = INT_MAX;
+        for (int r = 0; r < k; ++r) {
+            float bv = lv[0];
+            int bi = li[0];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const float v2 = __shfl_xor_sync(0xffffffffu, bv, s);
+                const int i2 = __shfl_xor_sync(0xffffffffu, bi, s);
+                if (tc_better(v2, i2, bv, bi)) { bv = v2; bi = i2; }
+            }
+            if (bi != INT_MAX && li[0] == bi) {      // item ids are unique across parts: exactly one lane pops
+#pragma unroll
+                for (int p = 0; p < KL - 1; ++p) { lv[p] = lv[p + 1]; li[p] = li[p + 1]; }
+                lv[KL - 1] = -INFINITY;
+                li[KL - 1] = INT_MAX;
+            }
+            if (lane == r) { ov = bv; oi = bi; }
+        }
         if (lane < k) {
-            out_v[(size_t)row * k + lane] = lv;
-            out_i[(size_t)row * k + lane] = li == INT_MAX ? -1 : li;
+            out_v[(size_t)row * k + lane] = ov;
+            out_i[(size_t)row * k + lane] = oi == INT_MAX ? -1 : oi;
         }
     }
     if (pg) {
@@ -529,6 +653,21 @@ __global__ void tc_topk_merge_kernel(const float* __restrict__ pv, const int* __
         }
         if (lane == 0) { out_g[row] = g; out_t[row] = t; }
     }
+}
+
+static int launch_merge(const float* pv, const int* pi, const int* pg, const int* pt, int parts, int R, int k, float* out_v,
+                        int32_t* out_i, int32_t* out_g, int32_t* out_t, cudaStream_t st) {
+    const int grid = ceil_div(R, 4);
+#define MERGE(KC) tc_topk_merge_kernel<KC><<<grid, 128, 0, st>>>(pv, pi, pg, pt, parts, R, k, out_v, out_i, out_g, out_t)
+    if (!pv) MERGE(0);
+    else if (k == 1) MERGE(1);
+    else if (k <= 5) MERGE(5);
+    else if (k <= 10) MERGE(10);
+    else if (k <= 20) MERGE(20);
+    else MERGE(32);
+#undef MERGE
+    ASME_LAUNCH_OK();
+    return ASME_OK;
 }
 
 // CE partials: (max in log2 units, sum of exp2) per part -> natural-log row max and sum-exp
@@ -551,11 +690,28 @@ __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 struct ScorePlan {
-    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps;
+    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps, wgs;
     size_t smem;
 };
 
-static int make_plan(int R, int Kp, int Vloc, ScorePlan* p) {
+// Tuning knobs (diagnostics; defaults are what the product path uses).  Results do not depend on them.
+static int g_epi_wgs = 4;          // epilogue warpgroups of the top-k sweeps: 4 (measured best; k > 10 needs the registers of 2)
+static int g_epi_wgs_other = 4;    // ... of the CE / count-only sweeps (their epilogues are ALU-bound: 4 is faster)
+static int g_sample_div = 16;      // the sample sweep scores 1/g_sample_div of every split's tiles (0: no sample sweep)
+static float g_thr_floor = -INFINITY;
+
+extern "C" int asme_b200_tc_score_tune(int knob, int value) {
+    switch (knob) {
+        case 0: ASME_REQUIRE(value == 2 || value == 4, "tc_score_tune: epilogue warpgroups must be 2 or 4"); g_epi_wgs = value; break;
+        case 1: ASME_REQUIRE(value >= 0, "tc_score_tune: sample divisor must be >= 0"); g_sample_div = value; break;
+        case 2: g_thr_floor = value ? INFINITY : -INFINITY; break;
+        case 3: ASME_REQUIRE(value == 2 || value == 4, "tc_score_tune: epilogue warpgroups must be 2 or 4"); g_epi_wgs_other = value; break;
+        default: ASME_REQUIRE(false, "tc_score_tune: unknown knob %d", knob);
+    }
+    return ASME_OK;
+}
+
+static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
     ASME_REQUIRE(R >= 1 && Vloc >= 1, "tc score: bad shape R=%d Vloc=%d", R, Vloc);
     ASME_REQUIRE(Kp >= 16 && Kp <= 272 && Kp % 16 == 0, "tc score: padded hidden size %d unsupported (multiple of 16, <= 272)", Kp);
     p->kch = ceil_div(Kp, CHUNK_K);
@@ -567,8 +723,10 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p) {
     if (splits > p->n_tiles) splits = p->n_tiles;
     p->tiles_per_split = ceil_div(p->n_tiles, splits);
     p->splits = ceil_div(p->n_tiles, p->tiles_per_split);
-    p->parts = p->splits * 2;
-    const size_t fixed = 1024 + (size_t)p->kch * A_CHUNK_BYTES + sizeof(ScoreTcBarriers);
+    p->wgs = topk ? g_epi_wgs : g_epi_wgs_other;
+    p->parts = p->splits;      // the warpgroups of a CTA fold their results before writing
+    const size_t fixed = 1024 + (size_t)p->kch * A_CHUNK_BYTES + ((sizeof(ScoreTcBarriers) + 15) & ~(size_t)15) +
+                         (topk ? (size_t)p->wgs * 128 * PEND_CAP * sizeof(uint2) : 0);
     const size_t stage = (size_t)B_CHUNK_BYTES;
     const size_t budget = 227 * 1024;
     ASME_REQUIRE(fixed + 2 * stage <= budget, "tc score: shared memory budget exceeded (Kp=%d)", Kp);
@@ -579,16 +737,16 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p) {
     return ASME_OK;
 }
 
-// Sample sweep: with per-thread lists every row pays ~k*ln(n/k) insertions in EACH of its 2*splits lists while the local
-// thresholds converge.  For long sweeps a first launch scores 1/16 of every split's tiles, the merged k-th best of that
-// sample becomes every list's initial threshold in the second launch (a valid lower bound of the true k-th best), and
-// insertions become rare.  Results are identical either way; only the work differs.
-static int sample_tiles(const ScorePlan& p) { return p.tiles_per_split >= 32 ? p.tiles_per_split / 16 : 0; }
+// Threshold pass: with per-thread lists every row pays ~k*ln(n/k) insertions in EACH of its lists while the local thresholds
+// converge.  For long sweeps a first launch scores 1/16 of every split's tiles and keeps only chunk maxima (one candidate per
+// 32 columns: cheap); the merged k-th best chunk maximum becomes every list's initial threshold in the second launch, which
+// sweeps everything (the 1/16 is scored twice) with rare insertions.  Results are identical either way; only the work differs.
+static int sample_tiles(const ScorePlan& p) { return (g_sample_div > 0 && p.tiles_per_split >= 2 * g_sample_div) ? p.tiles_per_split / g_sample_div : 0; }
 
 extern "C" size_t asme_b200_tc_score_topk_workspace_bytes(int R, int Kp, int Vloc, int k) {
     ScorePlan p;
     if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
-    return (size_t)2 * p.parts * (R < 1 ? 1 : R) * ((size_t)k * 8 + 8);
+    return (size_t)2 * p.splits * MAX_EPI_WGS * (R < 1 ? 1 : R) * ((size_t)k * 8 + 8);
 }
 
 template <typename K>
@@ -601,11 +759,17 @@ static int launch_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const Sco
                        bool count, cudaStream_t st) {
     int rc = ASME_OK;
     dim3 grid(p.m_tiles, p.splits);
-#define LAUNCH_TOPK(KC, C)                                                                  \
-    {                                                                                       \
-        rc = tc_set_smem(score_tc_kernel<EPI_TOPK, KC, C>, p.smem);                         \
-        if (rc) return rc;                                                                  \
-        score_tc_kernel<EPI_TOPK, KC, C><<<grid, TC_THREADS, p.smem, st>>>(tmA, tmB, a);    \
+#define LAUNCH_TOPK(KC, C)                                                                                   \
+    {                                                                                                        \
+        if (p.wgs == 4) {                                                                                    \
+            rc = tc_set_smem(score_tc_kernel<EPI_TOPK, KC, C, 4>, p.smem);                                   \
+            if (rc) return rc;                                                                               \
+            score_tc_kernel<EPI_TOPK, KC, C, 4><<<grid, TC_THREADS(4), p.smem, st>>>(tmA, tmB, a);           \
+        } else {                                                                                             \
+            rc = tc_set_smem(score_tc_kernel<EPI_TOPK, KC, C, 2>, p.smem);                                   \
+            if (rc) return rc;                                                                               \
+            score_tc_kernel<EPI_TOPK, KC, C, 2><<<grid, TC_THREADS(2), p.smem, st>>>(tmA, tmB, a);           \
+        }                                                                                                    \
     }
 #define LAUNCH_KC(KC)                         \
     {                                         \
@@ -638,9 +802,16 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_topk: bias must be 16-byte aligned");
     if (R == 0) return ASME_OK;
     ScorePlan p;
-    int rc = make_plan(R, Kp, Vloc, &p);
+    int rc = make_plan(R, Kp, Vloc, &p, topk);
     if (rc) return rc;
-    const size_t need = (size_t)2 * p.parts * R * ((size_t)k * 8 + 8);
+    if (k > 10 && p.wgs != 2) {      // the 20- and 32-entry register lists do not fit 96 registers per thread
+        const int keep = g_epi_wgs;
+        g_epi_wgs = 2;
+        rc = make_plan(R, Kp, Vloc, &p, topk);
+        g_epi_wgs = keep;
+        if (rc) return rc;
+    }
+    const size_t need = (size_t)2 * p.splits * MAX_EPI_WGS * R * ((size_t)k * 8 + 8);
     if (ws_bytes < need) {
         asme_set_error("tc_score_topk: workspace too small (%zu < %zu)", ws_bytes, need);
         return ASME_ERR_WORKSPACE;
@@ -655,7 +826,7 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
-    a.bias = bias; a.target = target; a.target_score = target_score_in;
+    a.bias = bias; a.target = target; a.target_score = target_score_in; a.thr_floor = g_thr_floor;
     a.pv = (float*)ws;
     a.pi = (int*)(a.pv + (size_t)total_parts * R * k);
     a.pg = a.pi + (size_t)total_parts * R * k;
@@ -664,27 +835,28 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     a.captured = target_score_out;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_sample > 0) {
-        // launch 1: the sample tiles of every split -> partial slots [0, parts); their merged top-k is the threshold source
-        a.tile_lo = 0; a.tile_hi = n_sample; a.part0 = 0; a.thr_init = nullptr;
-        rc = launch_topk(tmA, tmB, a, p, topk, count, st);
+        // launch 1 (threshold pass): the first tiles of every split, chunk maxima only -> partial slots [0, parts); the k-th best
+        // of their merge seeds every list's threshold in launch 2 (a valid lower bound of the true k-th best score)
+        a.tile_lo = 0; a.tile_hi = n_sample; a.part0 = 0; a.thr_init = nullptr; a.sample_mode = 1;
+        a.captured = nullptr;
+        rc = launch_topk(tmA, tmB, a, p, topk, false, st);
         if (rc) return rc;
-        tc_topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(a.pv, a.pi, nullptr, nullptr, p.parts, R, k, topk_val, topk_idx, nullptr,
-                                                             nullptr);
-        ASME_LAUNCH_OK();
-        // launch 2: everything else, thresholds seeded with the sample's k-th best
-        a.tile_lo = n_sample; a.tile_hi = p.tiles_per_split; a.part0 = p.parts;
+        rc = launch_merge(a.pv, a.pi, nullptr, nullptr, p.parts, R, k, topk_val, topk_idx, nullptr, nullptr, st);
+        if (rc) return rc;
+        // launch 2: the whole sweep -> partial slots [parts, 2 parts)
+        a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = p.parts; a.sample_mode = 0;
+        a.captured = target_score_out;
         a.thr_init = topk_val; a.thr_stride = k; a.thr_col = k - 1;
         rc = launch_topk(tmA, tmB, a, p, topk, count, st);
         if (rc) return rc;
-    } else {
-        a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
-        rc = launch_topk(tmA, tmB, a, p, topk, count, st);
-        if (rc) return rc;
+        return launch_merge(a.pv + (size_t)p.parts * R * k, a.pi + (size_t)p.parts * R * k, count ? a.pg + (size_t)p.parts * R : nullptr,
+                            a.pt + (size_t)p.parts * R, p.parts, R, k, topk_val, topk_idx, n_greater, n_tie_lower, st);
     }
-    tc_topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(topk ? a.pv : nullptr, a.pi, count ? a.pg : nullptr, a.pt, total_parts, R, k,
-                                                         topk_val, topk_idx, n_greater, n_tie_lower);
-    ASME_LAUNCH_OK();
-    return ASME_OK;
+    a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
+    rc = launch_topk(tmA, tmB, a, p, topk, count, st);
+    if (rc) return rc;
+    return launch_merge(topk ? a.pv : nullptr, a.pi, count ? a.pg : nullptr, a.pt, total_parts, R, k, topk_val, topk_idx, n_greater,
+                        n_tie_lower, st);
 }
 
 // diagnostic: the scoring sweep with an empty epilogue (upper bound of what the TMA -> MMA -> TMEM pipeline sustains)
@@ -702,9 +874,15 @@ extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, 
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.k = read_tmem ? 1 : 0;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_lo = 0; a.tile_hi = p.tiles_per_split;
-    rc = tc_set_smem(score_tc_kernel<EPI_PROBE, 0, false>, p.smem);
-    if (rc) return rc;
-    score_tc_kernel<EPI_PROBE, 0, false><<<dim3(p.m_tiles, p.splits), TC_THREADS, p.smem, (cudaStream_t)stream>>>(tmA, tmB, a);
+    if (p.wgs == 4) {
+        rc = tc_set_smem(score_tc_kernel<EPI_PROBE, 0, false, 4>, p.smem);
+        if (rc) return rc;
+        score_tc_kernel<EPI_PROBE, 0, false, 4><<<dim3(p.m_tiles, p.splits), TC_THREADS(4), p.smem, (cudaStream_t)stream>>>(tmA, tmB, a);
+    } else {
+        rc = tc_set_smem(score_tc_kernel<EPI_PROBE, 0, false, 2>, p.smem);
+        if (rc) return rc;
+        score_tc_kernel<EPI_PROBE, 0, false, 2><<<dim3(p.m_tiles, p.splits), TC_THREADS(2), p.smem, (cudaStream_t)stream>>>(tmA, tmB, a);
+    }
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -712,7 +890,7 @@ extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, 
 extern "C" size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc) {
     ScorePlan p;
     if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
-    return (size_t)p.parts * (R < 1 ? 1 : R) * 8;
+    return (size_t)p.splits * MAX_EPI_WGS * (R < 1 ? 1 : R) * 8;
 }
 
 extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
@@ -724,7 +902,7 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     ScorePlan p;
     int rc = make_plan(R, Kp, Vloc, &p);
     if (rc) return rc;
-    const size_t need = (size_t)p.parts * R * 8;
+    const size_t need = (size_t)p.splits * MAX_EPI_WGS * R * 8;
     if (ws_bytes < need) {
         asme_set_error("tc_score_ce_partial: workspace too small (%zu < %zu)", ws_bytes, need);
         return ASME_ERR_WORKSPACE;
@@ -737,15 +915,21 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
-    a.bias = bias; a.target = target; a.target_score = nullptr;
+    a.bias = bias; a.target = target; a.target_score = nullptr; a.thr_floor = -INFINITY;
     a.pv = (float*)ws;
     a.ps = a.pv + (size_t)p.parts * R;
     a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
     a.captured = target_logit;      // the caller zero-fills: only the shard that owns the target column writes
     cudaStream_t st = (cudaStream_t)stream;
-    rc = tc_set_smem(score_tc_kernel<EPI_CE, 0, false>, p.smem);
-    if (rc) return rc;
-    score_tc_kernel<EPI_CE, 0, false><<<dim3(p.m_tiles, p.splits), TC_THREADS, p.smem, st>>>(tmA, tmB, a);
+    if (p.wgs == 4) {
+        rc = tc_set_smem(score_tc_kernel<EPI_CE, 0, false, 4>, p.smem);
+        if (rc) return rc;
+        score_tc_kernel<EPI_CE, 0, false, 4><<<dim3(p.m_tiles, p.splits), TC_THREADS(4), p.smem, st>>>(tmA, tmB, a);
+    } else {
+        rc = tc_set_smem(score_tc_kernel<EPI_CE, 0, false, 2>, p.smem);
+        if (rc) return rc;
+        score_tc_kernel<EPI_CE, 0, false, 2><<<dim3(p.m_tiles, p.splits), TC_THREADS(2), p.smem, st>>>(tmA, tmB, a);
+    }
     ASME_LAUNCH_OK();
     tc_ce_merge_kernel<<<ceil_div(R, 128), 128, 0, st>>>(a.pv, a.ps, p.parts, R, row_max, row_sumexp);
     ASME_LAUNCH_OK();
