@@ -17,6 +17,7 @@
 // merged by a second tiny kernel.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 #include <limits.h>
 
@@ -247,7 +248,11 @@ __device__ __forceinline__ float max8(const float* v) {
 }
 
 // KC = capacity of the per-thread top-k list (0: no top-k); the first a.k (<= KC) entries are reported
-template <int EPI, int KC, bool COUNT, int WGS>
+// PAIR: the CTA and its cluster neighbour (the next row tile) form a cta_group::2 pair -- one M=256 MMA per K-step issued by the
+// even CTA, each CTA staging its own 128 rows of A and its own 128 of the tile's 256 table rows, so that shared memory
+// moves every table byte once per pair instead of once per CTA (a single CTA is shared-memory-bandwidth bound: per tile it
+// writes 64 KB and reads 96 KB of operands in the 1024 cycles the MMAs need).
+template <int EPI, int KC, bool COUNT, int WGS, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -256,7 +261,10 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)kch * A_CHUNK_BYTES;
     // `stages` ring slots of ONE 64-wide K chunk each
-    ScoreTcBarriers* bars = reinterpret_cast<ScoreTcBarriers*>(sB + (size_t)stages * B_CHUNK_BYTES);
+    constexpr uint32_t B_SLOT_BYTES = PAIR ? B_CHUNK_BYTES / 2 : B_CHUNK_BYTES;   // table rows of one K chunk staged by this CTA
+    ScoreTcBarriers* bars = reinterpret_cast<ScoreTcBarriers*>(sB + (size_t)stages * B_SLOT_BYTES);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     constexpr bool TOPK = KC > 0;
     constexpr int KL = KC > 0 ? KC : 1;
     constexpr int EPI_COLS = 256 / WGS;
@@ -281,36 +289,49 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars->tfull[s], 1);
-            mbar_init(&bars->tempty[s], 4 * WGS);
+            mbar_init(&bars->tempty[s], (PAIR ? 2 : 1) * 4 * WGS);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+    __syncwarp();
+    if (PAIR) cluster_sync_all();      // the neighbour's barriers exist before anything signals them
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair(&bars->tmem_base, 512);
+        else tmem_alloc(&bars->tmem_base, 512);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // programmatic dependent launch: the next kernel of the stream (the merge) may be scheduled now; it waits for this grid's
+    // completion itself before it reads anything
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
-            mbar_arrive_expect_tx(&bars->a_full, (uint32_t)kch * A_CHUNK_BYTES);
-            for (int c = 0; c < kch; ++c) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
+            // pair: the leader's barriers count the bytes of both CTAs
+            if (leader) mbar_arrive_expect_tx(&bars->a_full, (PAIR ? 2u : 1u) * (uint32_t)kch * A_CHUNK_BYTES);
+            for (int c = 0; c < kch; ++c) {
+                if (PAIR) tma_load_2d_pair(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
+                else tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
+            }
             int s = 0;                                    // ring slot and its phase, advanced without integer division
             uint32_t ph = 0;
             for (int t = t0; t < t1; ++t) {
                 for (int c = 0; c < kch; ++c) {
                     mbar_wait(&bars->empty[s], ph ^ 1u);
-                    mbar_arrive_expect_tx(&bars->full[s], (uint32_t)B_CHUNK_BYTES);
-                    tma_load_2d(sB + (size_t)s * B_CHUNK_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN);
+                    if (leader) mbar_arrive_expect_tx(&bars->full[s], (uint32_t)B_CHUNK_BYTES);
+                    if (PAIR) tma_load_2d_pair(sB + (size_t)s * B_SLOT_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN + (int)rank * (BN / 2));
+                    else tma_load_2d(sB + (size_t)s * B_SLOT_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN);
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0) {
-            const uint32_t idesc = idesc_bf16_f32(BM, BN);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = idesc_bf16_f32(PAIR ? 2 * BM : BM, BN);
             mbar_wait(&bars->a_full, 0);
             tc_fence_after();
             // This single thread paces the tensor core: one 128x256x16 MMA is 128 cycles, so a whole tile (kch*4 MMAs) must be
@@ -330,19 +351,26 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                     mbar_wait(&bars->full[s], ph);
                     tc_fence_after();
                     const uint64_t ad = adesc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
-                    const uint64_t bd = bdesc0 + (uint64_t)(s * (B_CHUNK_BYTES >> 4));
-                    if (c < kch - 1 || a.last_ksteps == 4) {
-                        umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(c != 0));
-                        umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                    const uint64_t bd = bdesc0 + (uint64_t)(s * (B_SLOT_BYTES >> 4));
+                    const int ksteps = (c < kch - 1) ? 4 : a.last_ksteps;
+                    if (PAIR) {
+                        for (int k4 = 0; k4 < ksteps; ++k4) umma_bf16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (uint32_t)((c | k4) != 0));
+                        umma_commit_pair(&bars->empty[s]);
                     } else {
-                        for (int k4 = 0; k4 < a.last_ksteps; ++k4) umma_bf16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (uint32_t)((c | k4) != 0));
+                        if (ksteps == 4) {
+                            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(c != 0));
+                            umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                            umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                            umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                        } else {
+                            for (int k4 = 0; k4 < ksteps; ++k4) umma_bf16(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (uint32_t)((c | k4) != 0));
+                        }
+                        umma_commit(&bars->empty[s]);     // the slot may be refilled once these MMAs have read it
                     }
-                    umma_commit(&bars->empty[s]);     // the slot may be refilled once these MMAs have read it
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&bars->tfull[as]);        // accumulator ready for the epilogue
+                if (PAIR) umma_commit_pair(&bars->tfull[as]);
+                else umma_commit(&bars->tfull[as]);        // accumulator ready for the epilogue
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -370,6 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         // threshold: nothing at or below it can enter the list.  thr0 comes from a sample sweep (strictly below the
         // sample's k-th best, so ties with it still pass the strict compare); once the own list is full its tail takes over.
         float thr0 = -INFINITY;
+        if (TOPK && a.thr_init) asm volatile("griddepcontrol.wait;" ::: "memory");      // thresholds come from the previous launch
         if (TOPK && a.thr_init && row_ok) {
             const float t_row = a.thr_init[(size_t)row * a.thr_stride + a.thr_col];
             thr0 = t_row == -INFINITY ? t_row : nextafterf(t_row, -INFINITY);
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         for (int t = t0; t < t1; ++t, ++i) {
             const int as = i & 1;
             const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-            mbar_wait(&bars->tfull[as], aph);
+            mbar_wait_lean(&bars->tfull[as], aph);
             tc_fence_after();
             if (EPI == EPI_PROBE) {          // a.k == 0: no TMEM reads at all (what TMA + MMA + handshakes sustain);
                 if (a.k != 0) {              // a.k != 0: read the whole accumulator and discard it (TMEM read throughput)
@@ -401,11 +430,16 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                if (lane == 0) {
+                        if (PAIR) mbar_arrive_leader(&bars->tempty[as]);
+                        else mbar_arrive(&bars->tempty[as]);
+                    }
                 continue;
             }
-#pragma unroll 1
-            for (int ch = 0; ch < EPI_COLS / 32; ++ch) {
+            // PLAIN tiles (all 256 columns valid, no bias vector, no target column of this warp's rows inside) skip the per-chunk
+            // bookkeeping: the epilogue warps are issue-bound, every instruction per chunk counts
+            auto chunk = [&](auto plain_c, const int ch) {
+                constexpr bool PLAIN = decltype(plain_c)::value;
                 const int col0 = t * BN + wg * EPI_COLS + ch * 32;     // local column of v[0]
                 float v[32];
                 tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * EPI_COLS + ch * 32), v);
@@ -413,11 +447,14 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                 if (ch == EPI_COLS / 32 - 1) {   // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_leader(&bars->tempty[as]);
+                        else mbar_arrive(&bars->tempty[as]);
+                    }
                 }
-                if (col0 >= a.Vloc) continue;                   // warp-uniform
-                const bool full_valid = col0 + 32 <= a.Vloc;
-                if (a.bias) {
+                if (!PLAIN && col0 >= a.Vloc) return;           // warp-uniform
+                const bool full_valid = PLAIN || col0 + 32 <= a.Vloc;
+                if (!PLAIN && a.bias) {
                     if (full_valid) {
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
@@ -436,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                         if (col0 + c >= a.Vloc) v[c] = -INFINITY;
                 }
                 // score of the target column exactly as this kernel computes it
-                if (a.captured && tgl >= col0 && tgl < col0 + 32) {
+                if (!PLAIN && a.captured && tgl >= col0 && tgl < col0 + 32) {
                     float x = 0.f;
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
@@ -497,6 +534,15 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                         }
                     }
                 }
+            };
+            const bool tile_full = (t + 1) * BN <= a.Vloc;
+            const bool target_here = a.captured && tgl >= t * BN && tgl < (t + 1) * BN;
+            if (tile_full && !a.bias && !__any_sync(0xffffffffu, target_here)) {
+#pragma unroll 1
+                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::true_type{}, ch);
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::false_type{}, ch);
             }
         }
         if (TOPK) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
@@ -573,10 +619,12 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // neither CTA frees tensor memory (or exits) while the pair's MMAs / signals may touch it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -593,6 +641,8 @@ __global__ void __launch_bounds__(128) tc_topk_merge_kernel(const float* __restr
                                                             int32_t* __restrict__ out_g, int32_t* __restrict__ out_t) {
     const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
+    asm volatile("griddepcontrol.wait;" ::: "memory");                 // the partial lists come from the previous launch
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (row >= R) return;
     if (KC > 0 && pv) {
         constexpr int KL = KC > 0 ? KC : 1;
@@ -655,10 +705,25 @@ __global__ void __launch_bounds__(128) tc_topk_merge_kernel(const float* __restr
     }
 }
 
+extern int g_pdl_merge;
+template <int KC>
+static cudaError_t launch_merge_one(const float* pv, const int* pi, const int* pg, const int* pt, int parts, int R, int k, float* out_v,
+                                    int32_t* out_i, int32_t* out_g, int32_t* out_t, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(R, 4));
+    cfg.blockDim = dim3(128);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl_merge ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, tc_topk_merge_kernel<KC>, pv, pi, pg, pt, parts, R, k, out_v, out_i, out_g, out_t);
+}
+
 static int launch_merge(const float* pv, const int* pi, const int* pg, const int* pt, int parts, int R, int k, float* out_v,
                         int32_t* out_i, int32_t* out_g, int32_t* out_t, cudaStream_t st) {
-    const int grid = ceil_div(R, 4);
-#define MERGE(KC) tc_topk_merge_kernel<KC><<<grid, 128, 0, st>>>(pv, pi, pg, pt, parts, R, k, out_v, out_i, out_g, out_t)
+#define MERGE(KC) ASME_CUDA_OK(launch_merge_one<KC>(pv, pi, pg, pt, parts, R, k, out_v, out_i, out_g, out_t, st))
     if (!pv) MERGE(0);
     else if (k == 1) MERGE(1);
     else if (k <= 5) MERGE(5);
@@ -690,7 +755,7 @@ __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 struct ScorePlan {
-    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps, wgs;
+    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps, wgs, pair, grid_x;
     size_t smem;
 };
 
@@ -699,6 +764,11 @@ static int g_epi_wgs = 4;          // epilogue warpgroups of the top-k sweeps: 4
 static int g_epi_wgs_other = 4;    // ... of the CE / count-only sweeps (their epilogues are ALU-bound: 4 is faster)
 static int g_sample_div = 16;      // the sample sweep scores 1/g_sample_div of every split's tiles (0: no sample sweep)
 static float g_thr_floor = -INFINITY;
+static int g_pair = 0;             // 1: CTA pairs (cta_group::2) whenever there are at least two row tiles; 0: single CTAs.  Measured:
+                                   // no gain (the single-CTA pipeline already runs at the power-capped tensor peak, it is not shared-
+                                   // memory bound) and the pair couples the two epilogues' jitter -> off by default, kept as a knob
+static int g_pdl = 0;              // programmatic dependent launch between the launches of one top-k call
+int g_pdl_merge = 0;            // measured: slower (early-scheduled dependents take SM resources from the sweep) -> off, kept as a knob
 
 extern "C" int asme_b200_tc_score_tune(int knob, int value) {
     switch (knob) {
@@ -706,6 +776,8 @@ extern "C" int asme_b200_tc_score_tune(int knob, int value) {
         case 1: ASME_REQUIRE(value >= 0, "tc_score_tune: sample divisor must be >= 0"); g_sample_div = value; break;
         case 2: g_thr_floor = value ? INFINITY : -INFINITY; break;
         case 3: ASME_REQUIRE(value == 2 || value == 4, "tc_score_tune: epilogue warpgroups must be 2 or 4"); g_epi_wgs_other = value; break;
+        case 4: g_pair = value ? 1 : 0; break;
+        case 5: g_pdl = g_pdl_merge = value ? 1 : 0; break;
         default: ASME_REQUIRE(false, "tc_score_tune: unknown knob %d", knob);
     }
     return ASME_OK;
@@ -718,7 +790,9 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
     p->last_ksteps = (Kp % CHUNK_K) ? (Kp % CHUNK_K) / UMMA_K : CHUNK_K / UMMA_K;
     p->m_tiles = ceil_div(R, BM);
     p->n_tiles = ceil_div(Vloc, BN);
-    int splits = ASME_NUM_SMS / p->m_tiles;
+    p->pair = (g_pair && p->m_tiles >= 2) ? 1 : 0;
+    p->grid_x = p->pair ? (p->m_tiles + 1) / 2 * 2 : p->m_tiles;      // an odd last row tile is paired with an empty one
+    int splits = ASME_NUM_SMS / p->grid_x;
     if (splits < 1) splits = 1;
     if (splits > p->n_tiles) splits = p->n_tiles;
     p->tiles_per_split = ceil_div(p->n_tiles, splits);
@@ -727,7 +801,7 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
     p->parts = p->splits;      // the warpgroups of a CTA fold their results before writing
     const size_t fixed = 1024 + (size_t)p->kch * A_CHUNK_BYTES + ((sizeof(ScoreTcBarriers) + 15) & ~(size_t)15) +
                          (topk ? (size_t)p->wgs * 128 * PEND_CAP * sizeof(uint2) : 0);
-    const size_t stage = (size_t)B_CHUNK_BYTES;
+    const size_t stage = (size_t)B_CHUNK_BYTES / (p->pair ? 2 : 1);
     const size_t budget = 227 * 1024;
     ASME_REQUIRE(fixed + 2 * stage <= budget, "tc score: shared memory budget exceeded (Kp=%d)", Kp);
     int stages = (int)((budget - fixed) / stage);
@@ -746,7 +820,7 @@ static int sample_tiles(const ScorePlan& p) { return (g_sample_div > 0 && p.tile
 extern "C" size_t asme_b200_tc_score_topk_workspace_bytes(int R, int Kp, int Vloc, int k) {
     ScorePlan p;
     if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
-    return (size_t)2 * p.splits * MAX_EPI_WGS * (R < 1 ? 1 : R) * ((size_t)k * 8 + 8);
+    return (size_t)2 * (p.splits + 1) * MAX_EPI_WGS * (R < 1 ? 1 : R) * ((size_t)k * 8 + 8);    // + 1: either pairing mode fits
 }
 
 template <typename K>
@@ -755,37 +829,50 @@ static int tc_set_smem(K kernel, size_t bytes) {
     return ASME_OK;
 }
 
-static int launch_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreTcArgs& a, const ScorePlan& p, bool topk,
-                       bool count, cudaStream_t st) {
-    int rc = ASME_OK;
-    dim3 grid(p.m_tiles, p.splits);
-#define LAUNCH_TOPK(KC, C)                                                                                   \
-    {                                                                                                        \
-        if (p.wgs == 4) {                                                                                    \
-            rc = tc_set_smem(score_tc_kernel<EPI_TOPK, KC, C, 4>, p.smem);                                   \
-            if (rc) return rc;                                                                               \
-            score_tc_kernel<EPI_TOPK, KC, C, 4><<<grid, TC_THREADS(4), p.smem, st>>>(tmA, tmB, a);           \
-        } else {                                                                                             \
-            rc = tc_set_smem(score_tc_kernel<EPI_TOPK, KC, C, 2>, p.smem);                                   \
-            if (rc) return rc;                                                                               \
-            score_tc_kernel<EPI_TOPK, KC, C, 2><<<grid, TC_THREADS(2), p.smem, st>>>(tmA, tmB, a);           \
-        }                                                                                                    \
-    }
-#define LAUNCH_KC(KC)                         \
-    {                                         \
-        if (count) LAUNCH_TOPK(KC, true)      \
-        else LAUNCH_TOPK(KC, false)           \
-    }
-    if (!topk) LAUNCH_TOPK(0, true)
-    else if (a.k == 1) LAUNCH_KC(1)
-    else if (a.k <= 5) LAUNCH_KC(5)
-    else if (a.k <= 10) LAUNCH_KC(10)
-    else if (a.k <= 20) LAUNCH_KC(20)
-    else LAUNCH_KC(32)
-#undef LAUNCH_KC
-#undef LAUNCH_TOPK
-    ASME_LAUNCH_OK();
+template <int EPI, int KC, bool COUNT, int WGS, bool PAIR>
+static int launch_score_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreTcArgs& a, const ScorePlan& p, cudaStream_t st,
+                            bool pdl) {
+    auto kernel = score_tc_kernel<EPI, KC, COUNT, WGS, PAIR>;
+    int rc = tc_set_smem(kernel, p.smem);
+    if (rc) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid_x, p.splits);
+    cfg.blockDim = dim3(TC_THREADS(WGS));
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 2 : 1;
+    ASME_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, a));
+    asme_count_launch();
     return ASME_OK;
+}
+template <int EPI, int KC, bool COUNT>
+static int launch_score(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreTcArgs& a, const ScorePlan& p, cudaStream_t st,
+                        bool pdl = false) {
+    if (p.wgs == 4)
+        return p.pair ? launch_score_one<EPI, KC, COUNT, 4, true>(tmA, tmB, a, p, st, pdl)
+                      : launch_score_one<EPI, KC, COUNT, 4, false>(tmA, tmB, a, p, st, pdl);
+    return p.pair ? launch_score_one<EPI, KC, COUNT, 2, true>(tmA, tmB, a, p, st, pdl)
+                  : launch_score_one<EPI, KC, COUNT, 2, false>(tmA, tmB, a, p, st, pdl);
+}
+
+static int launch_topk(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreTcArgs& a, const ScorePlan& p, bool topk,
+                       bool count, cudaStream_t st, bool pdl = false) {
+#define LAUNCH_KC(KC) return count ? launch_score<EPI_TOPK, KC, true>(tmA, tmB, a, p, st, pdl) : launch_score<EPI_TOPK, KC, false>(tmA, tmB, a, p, st, pdl)
+    if (!topk) return launch_score<EPI_TOPK, 0, true>(tmA, tmB, a, p, st, pdl);
+    if (a.k == 1) LAUNCH_KC(1);
+    if (a.k <= 5) LAUNCH_KC(5);
+    if (a.k <= 10) LAUNCH_KC(10);
+    if (a.k <= 20) LAUNCH_KC(20);
+    LAUNCH_KC(32);
+#undef LAUNCH_KC
 }
 
 extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
@@ -819,7 +906,7 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     CUtensorMap tmA, tmB;
     rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
     if (rc) return rc;
-    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, p.pair ? BN / 2 : BN);
     if (rc) return rc;
     const int n_sample = topk ? sample_tiles(p) : 0;
     const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
@@ -847,7 +934,7 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
         a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = p.parts; a.sample_mode = 0;
         a.captured = target_score_out;
         a.thr_init = topk_val; a.thr_stride = k; a.thr_col = k - 1;
-        rc = launch_topk(tmA, tmB, a, p, topk, count, st);
+        rc = launch_topk(tmA, tmB, a, p, topk, count, st, g_pdl != 0);
         if (rc) return rc;
         return launch_merge(a.pv + (size_t)p.parts * R * k, a.pi + (size_t)p.parts * R * k, count ? a.pg + (size_t)p.parts * R : nullptr,
                             a.pt + (size_t)p.parts * R, p.parts, R, k, topk_val, topk_idx, n_greater, n_tie_lower, st);
@@ -869,28 +956,18 @@ extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, 
     CUtensorMap tmA, tmB;
     rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
     if (rc) return rc;
-    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, p.pair ? BN / 2 : BN);
     if (rc) return rc;
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.k = read_tmem ? 1 : 0;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_lo = 0; a.tile_hi = p.tiles_per_split;
-    if (p.wgs == 4) {
-        rc = tc_set_smem(score_tc_kernel<EPI_PROBE, 0, false, 4>, p.smem);
-        if (rc) return rc;
-        score_tc_kernel<EPI_PROBE, 0, false, 4><<<dim3(p.m_tiles, p.splits), TC_THREADS(4), p.smem, (cudaStream_t)stream>>>(tmA, tmB, a);
-    } else {
-        rc = tc_set_smem(score_tc_kernel<EPI_PROBE, 0, false, 2>, p.smem);
-        if (rc) return rc;
-        score_tc_kernel<EPI_PROBE, 0, false, 2><<<dim3(p.m_tiles, p.splits), TC_THREADS(2), p.smem, (cudaStream_t)stream>>>(tmA, tmB, a);
-    }
-    ASME_LAUNCH_OK();
-    return ASME_OK;
+    return launch_score<EPI_PROBE, 0, false>(tmA, tmB, a, p, (cudaStream_t)stream);
 }
 
 extern "C" size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc) {
     ScorePlan p;
     if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
-    return (size_t)p.splits * MAX_EPI_WGS * (R < 1 ? 1 : R) * 8;
+    return (size_t)(p.splits + 1) * MAX_EPI_WGS * (R < 1 ? 1 : R) * 8;
 }
 
 extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
@@ -910,7 +987,7 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     CUtensorMap tmA, tmB;
     rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
     if (rc) return rc;
-    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, p.pair ? BN / 2 : BN);
     if (rc) return rc;
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
@@ -921,16 +998,8 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
     a.captured = target_logit;      // the caller zero-fills: only the shard that owns the target column writes
     cudaStream_t st = (cudaStream_t)stream;
-    if (p.wgs == 4) {
-        rc = tc_set_smem(score_tc_kernel<EPI_CE, 0, false, 4>, p.smem);
-        if (rc) return rc;
-        score_tc_kernel<EPI_CE, 0, false, 4><<<dim3(p.m_tiles, p.splits), TC_THREADS(4), p.smem, st>>>(tmA, tmB, a);
-    } else {
-        rc = tc_set_smem(score_tc_kernel<EPI_CE, 0, false, 2>, p.smem);
-        if (rc) return rc;
-        score_tc_kernel<EPI_CE, 0, false, 2><<<dim3(p.m_tiles, p.splits), TC_THREADS(2), p.smem, st>>>(tmA, tmB, a);
-    }
-    ASME_LAUNCH_OK();
+    rc = launch_score<EPI_CE, 0, false>(tmA, tmB, a, p, st);
+    if (rc) return rc;
     tc_ce_merge_kernel<<<ceil_div(R, 128), 128, 0, st>>>(a.pv, a.ps, p.parts, R, row_max, row_sumexp);
     ASME_LAUNCH_OK();
     return ASME_OK;

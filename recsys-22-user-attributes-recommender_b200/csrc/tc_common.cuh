@@ -72,6 +72,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// The same for waits on the hot path of issue-bound warps: the poll loop is 3 instructions instead of 9 (no clock reads);
+// still bounded (2^28 polls, each of which may suspend the warp for a while, is far beyond any legitimate wait).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        if (spin > (1u << 28)) asm volatile("trap;");
+    }
+}
+
 // 2-D tiled TMA load: box (CHUNK_K x rows) at element coordinates (k0, row0) -> shared memory, completes on `bar`
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int k0, int row0) {
     asm volatile(
@@ -107,6 +115,61 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC execute ONE M=256 MMA ---------------------
+// Rank 0 of the pair (the leader) issues the MMAs and owns the pipeline barriers the MMA thread waits on; each CTA stages its
+// own 128 rows of A and its own half of the N rows of B, so every operand byte crosses shared memory once per pair.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of a variable -> the same variable in the LEADER's shared memory (shared::cluster address)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on the leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int k0, int row0) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(k0), "r"(row0)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows per CTA) * B^T (N/2 rows per CTA); issued by ONE thread of the leader
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued pair MMAs arrive on `bar` (same offset) in BOTH CTAs when they complete
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 
 // ---- descriptors ----------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart (dense chunk layout)
