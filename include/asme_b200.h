@@ -75,6 +75,14 @@ typedef struct {
     float p_drop;                            /* 0 => identity (eval) */
     uint64_t seed;
     uint32_t site_a, site_b;                 /* dropout site ids of drop_a / drop_b */
+    /* user prefix (models/ubert4rec/components.py:96-133): with n_user > 0 every sequence has S positions of which position 0
+     * is sum_u U_u[user_ids_u[b]] (no positional row, no LN1, no item attributes) and positions 1..S-1 are the item tokens
+     * b*(S-1) .. b*(S-1)+S-2 (item_ids / attr_ids / bag_ids stay (B*(S-1)) long, positional rows 0..S-2).  seg_table (2,H) or
+     * NULL: row 0 is added to the user position, row 1 to the item positions, before LN2. */
+    int n_user;
+    const int64_t* user_ids[ASME_MAX_ATTR];  /* (B) each */
+    const float* user_table[ASME_MAX_ATTR];  /* (Vu,H) */
+    const float* seg_table;
 } asme_embed_desc;
 
 int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* out /*T,H*/,
@@ -83,6 +91,7 @@ int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* ou
  * the attribute sum (== d_item_rows when LN1 is absent; may alias); LayerNorm parameter gradients are ACCUMULATED
  * into dln (4,H): dgamma1,dbeta1,dgamma2,dbeta2 via deterministic two-stage column sums. */
 size_t asme_b200_embed_bwd_workspace_bytes(int T, int H);
+/* with a user prefix d_item_rows / d_attr_rows of a user position hold the gradient w.r.t. the user-embedding sum */
 int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H, const float* d_out, const float* stats,
                         float* d_item_rows, float* d_attr_rows, float* dln, void* ws, size_t ws_bytes,
                         asme_stream_t stream);
@@ -96,6 +105,9 @@ int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_ro
                                     int V, int64_t skip_id, void* ws, size_t ws_bytes, asme_stream_t stream);
 /* d_pos[s,:] += sum_b d_rows[b*S+s,:]   (positions are generated, t mod S; transformer_layers.py:68) */
 int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H, float* d_pos, asme_stream_t stream);
+/* the same for sequences that are seq_stride_rows rows apart (user prefix: d_rows points at position 1 of sequence 0) */
+int asme_b200_posgrad_reduce_strided(const float* d_rows, int B, int S, int seq_stride_rows, int H, float* d_pos,
+                                     asme_stream_t stream);
 /* bag tables: d_table_t[id,:] += d_rows[t,:] for every bag entry id != 0; d_bias += column sums of d_rows */
 int asme_b200_colsum_accumulate(const float* x, int M, int N, float* out /*N, +=*/, void* ws, size_t ws_bytes,
                                 asme_stream_t stream);

@@ -158,10 +158,10 @@ def transformer_block(x: torch.Tensor, w: Weights, prefix: str, heads: int,
 
 
 def transformer_encoder(x: torch.Tensor, w: Weights, heads: int, layers: int,
-                        mask: Optional[torch.Tensor]) -> torch.Tensor:
+                        mask: Optional[torch.Tensor],
+                        prefix: str = "_sequence_representation_layer.transformer_layer") -> torch.Tensor:
     for l in range(layers):
-        x = transformer_block(
-            x, w, f"_sequence_representation_layer.transformer_layer.transformer_blocks.{l}", heads, mask)
+        x = transformer_block(x, w, f"{prefix}.transformer_blocks.{l}", heads, mask)
     return x
 
 
@@ -316,6 +316,63 @@ def sasrec_full_logits(w: Weights, seq, attrs, heads, layers, **kw) -> torch.Ten
 def sasrec_neg_logits(w: Weights, seq, pos, neg, heads, layers, **kw):
     h = sasrec_hidden(w, seq, {}, heads, layers, **kw)
     return sasrec_pos_neg(h, w[f"{_PRE}.item_embedding.embedding.weight"], pos, neg)
+
+
+# --------------------------------------------------------------------------------------------
+# 8f row 1  user-attribute models                    models/ubert4rec/components.py:96-133, :170-200
+#           UBERT4Rec                                models/ubert4rec/ubert4rec_model.py:19-92
+#           UserSASRec                               models/user_sasrec/user_sasrec_model.py:21-107
+# --------------------------------------------------------------------------------------------
+_ADD_ATTR = "_sequence_embedding_layer.additional_attribute_embeddings"
+_USER_ATTR = "_sequence_embedding_layer.user_attribute_embeddings"
+_USER_ENC = "_sequence_representation_layer.transformer_encoder"
+
+
+def user_prefixed_embedding(w: Weights, seq: torch.Tensor, attrs: Dict[str, torch.Tensor], additional: Sequence[str],
+                            user: Sequence[str], item_norm: bool) -> torch.Tensor:
+    """(B,S) -> (B,S+1,H): the user token (sum of the user-attribute embeddings of column 0 of each user feature) is
+    prepended to the item embeddings (+ item attributes); an optional segment embedding (row 0: user, row 1: items) is added,
+    then LayerNorm (+ dropout).  The item embedding itself is E[ids] + P[0..S-1] and, for UserSASRec, already normed once."""
+    norm1 = (w[f"{_PRE}.embedding_norm.weight"], w[f"{_PRE}.embedding_norm.bias"]) if item_norm else None
+    x = transformer_embedding(seq, w[f"{_PRE}.item_embedding.embedding.weight"], w.get(f"{_PRE}.position_embedding.weight"), norm1)
+    ctx = attribute_sum(attrs, w, _ADD_ATTR, additional)
+    if ctx is not None:
+        x = x + ctx
+    u = None
+    for name in user:
+        part = w[f"{_USER_ATTR}.{name}.weight"][attrs[name][:, 0:1]]
+        u = part if u is None else u + part
+    if u is not None:
+        x = torch.cat([u, x], dim=1)
+    seg = w.get("_sequence_embedding_layer.segment_embedding.weight")
+    if seg is not None:
+        segments = torch.ones(seq.shape, dtype=torch.int64)
+        if u is not None:
+            segments = torch.cat([torch.zeros(seq.shape[0], 1, dtype=torch.int64), segments], dim=1)
+        x = x + seg[segments]
+    return _drop(layer_norm(x, w["_sequence_embedding_layer.norm_embedding.weight"],
+                            w["_sequence_embedding_layer.norm_embedding.bias"]))
+
+
+def user_encoder(w: Weights, x: torch.Tensor, seq: torch.Tensor, heads: int, layers: int, has_user: bool) -> torch.Tensor:
+    """causal mask over the S+1 positions; the user position is never padding (components.py:170-174, bidirectional=False)."""
+    pm = padding_mask(seq)
+    if has_user:
+        pm = torch.cat([torch.ones(pm.shape[0], 1, dtype=pm.dtype), pm], dim=1)
+    return transformer_encoder(x, w, heads, layers, attention_mask(pm, x.shape[0], x.shape[1], False), prefix=_USER_ENC)
+
+
+def ubert4rec_logits(w: Weights, seq, attrs, heads, layers, additional=(), user=()) -> torch.Tensor:
+    """(B,S+1,V) when user attributes are configured"""
+    x = user_prefixed_embedding(w, seq, attrs, additional, user, item_norm=False)
+    h = ffn_modifier(user_encoder(w, x, seq, heads, layers, bool(user)), w)
+    return project(h, w["_projection_layer.linear.weight"], w["_projection_layer.linear.bias"])
+
+
+def usasrec_full_logits(w: Weights, seq, attrs, heads, layers, additional=(), user=()) -> torch.Tensor:
+    x = user_prefixed_embedding(w, seq, attrs, additional, user, item_norm=True)
+    h = user_encoder(w, x, seq, heads, layers, bool(user))
+    return project(h, w["_projection_layer.linear.weight"], w["_projection_layer.linear.bias"])
 
 
 # --------------------------------------------------------------------------------------------

@@ -26,6 +26,8 @@ class EmbedDesc(Structure):
         ("bag_table_t", c_void_p * ASME_MAX_ATTR), ("bag_bias", c_void_p * ASME_MAX_ATTR),
         ("ln1_gamma", c_void_p), ("ln1_beta", c_void_p), ("ln2_gamma", c_void_p), ("ln2_beta", c_void_p),
         ("p_drop", c_float), ("seed", c_uint64), ("site_a", c_uint32), ("site_b", c_uint32),
+        ("n_user", c_int), ("user_ids", c_void_p * ASME_MAX_ATTR), ("user_table", c_void_p * ASME_MAX_ATTR),
+        ("seg_table", c_void_p),
     ]
 
 
@@ -49,6 +51,7 @@ _PROTOTYPES = {
     "asme_b200_embgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_embgrad_sorted_reduce": (c_int, [P, c_int, P, c_int, c_int, P, c_int, c_int64, P, c_size_t, P]),
     "asme_b200_posgrad_reduce": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "asme_b200_posgrad_reduce_strided": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "asme_b200_colsum_accumulate": (c_int, [P, c_int, c_int, P, P, c_size_t, P]),
     "asme_b200_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_layernorm_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P]),

@@ -64,13 +64,13 @@ class Saved:
     extra: Dict[str, Any] = field(default_factory=dict)
 
 
-def block_param_specs(cfg: EncoderConfig) -> List[Tuple[str, Tuple[int, ...]]]:
+def block_param_specs(cfg: EncoderConfig, blocks: str = BLOCKS) -> List[Tuple[str, Tuple[int, ...]]]:
     """Arena layout of the encoder blocks: Wq|Wk|Wv and bq|bk|bv glued so that one GEMM computes QKV,
     (gamma, beta) pairs glued so that LayerNorm backward writes one (2,H) target."""
     H, FF = cfg.hidden, cfg.intermediate
     specs = []
     for l in range(cfg.layers):
-        p = f"{BLOCKS}.{l}"
+        p = f"{blocks}.{l}"
         specs += [(f"{p}.attention.linear_layers.0.weight+", (H, H)), (f"{p}.attention.linear_layers.1.weight+", (H, H)),
                   (f"{p}.attention.linear_layers.2.weight", (H, H)),
                   (f"{p}.attention.linear_layers.0.bias+", (H,)), (f"{p}.attention.linear_layers.1.bias+", (H,)),
@@ -92,6 +92,7 @@ class EncoderEngine:
     def __init__(self, module, cfg: EncoderConfig):
         self.m = module        # ArenaModule: weight(path[, buf]) / weights_span(...)
         self.cfg = cfg
+        self.blocks = getattr(module, "blocks_path", BLOCKS)
 
     # ---------------------------------------------------------------- helpers
     def _w(self, path, grad=False):
@@ -120,7 +121,7 @@ class EncoderEngine:
         pa = cfg.attention_dropout if train else 0.0
         B, S = saved.B, saved.S
         for l in range(cfg.layers):
-            pre = f"{BLOCKS}.{l}"
+            pre = f"{self.blocks}.{l}"
             ls = LayerSaved()
             ls.x = x
             ls.y1, _, ls.st1 = ops.layernorm_fwd_bf16(x, self._w(f"{pre}.input_sublayer.norm.weight"),
@@ -163,7 +164,7 @@ class EncoderEngine:
         B, S = saved.B, saved.S
         g = m._arena.ensure_grad()
         for l in reversed(range(cfg.layers)):
-            pre = f"{BLOCKS}.{l}"
+            pre = f"{self.blocks}.{l}"
             ls = saved.layers[l]
             # ---- feed forward: out = drop4(x2 + drop3(W2 a + b2)), a = drop2(gelu(z)), z = W1 y2 + b1
             if p > 0:
@@ -214,7 +215,7 @@ class EncoderEngine:
         pa = cfg.attention_dropout if train else 0.0
         B, S = saved.B, saved.S
         for l in range(cfg.layers):
-            pre = f"{BLOCKS}.{l}"
+            pre = f"{self.blocks}.{l}"
             ls = LayerSaved()
             ls.x = x
             ls.y1, ls.st1 = ops.layernorm_fwd(x, self._w(f"{pre}.input_sublayer.norm.weight"),
@@ -251,7 +252,7 @@ class EncoderEngine:
         B, S = saved.B, saved.S
         g = m._arena.ensure_grad()
         for l in reversed(range(cfg.layers)):
-            pre = f"{BLOCKS}.{l}"
+            pre = f"{self.blocks}.{l}"
             ls = saved.layers[l]
             dx3 = ops.dropout(dx, p, saved.seed, self._site(l, 4)) if p > 0 else dx
             # ---- feed forward: x3 = x2 + drop(W2 a + b2), a = drop(gelu(z)), z = W1 y2 + b1

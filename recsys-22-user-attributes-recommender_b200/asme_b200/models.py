@@ -42,6 +42,9 @@ def set_default_precision(precision: str) -> None:
 _EMB = "_sequence_embedding_layer"
 _PRE_ATTR = f"{_EMB}.prefusion_attribute_embeddings"
 _POST_ATTR = f"{MODIFIER}.postfusion_attribute_embeddings"
+_ADD_ATTR = f"{_EMB}.additional_attribute_embeddings"          # UBERT4Rec / UserSASRec name for the pre-fused item attributes
+_USER_ATTR = f"{_EMB}.user_attribute_embeddings"
+_SEGMENT = f"{_EMB}.segment_embedding.weight"
 
 
 def _attr_vocab_size(name, tokenizers, sizes):
@@ -65,9 +68,11 @@ class TransformerRecommenderModel(ArenaModule):
     modifier_kind: str = "identity"            # "ffn" | "identity"
     projection_kind: str = "linear"            # "tied" | "linear" | "sasrec_neg"
     embed_dropout_a: bool = True               # dropout after LN1 (TransformerEmbedding.dropout)
+    pre_attr_prefix: str = _PRE_ATTR           # module path of the pre-fused item-attribute tables
+    blocks_path: str = BLOCKS                  # module path of the encoder blocks (state-dict prefix)
 
     def _setup(self, cfg: EncoderConfig, item_vocab_size: int, max_seq_length: int, specs, prefusion, postfusion,
-               tokenizers, attr_sizes, merge: str):
+               tokenizers, attr_sizes, merge: str, user_attributes=None, segment_rows: int = 0):
         self.cfg = cfg
         self.item_vocab_size = int(item_vocab_size)
         self.max_seq_length = int(max_seq_length)
@@ -76,7 +81,19 @@ class TransformerRecommenderModel(ArenaModule):
         self.prefusion: List[Tuple[str, str, int]] = []      # (name, type, vocab)
         self.postfusion: List[Tuple[str, str, int]] = []
         attr_specs = []
-        for store, attrs, prefix in ((self.prefusion, prefusion, _PRE_ATTR), (self.postfusion, postfusion, _POST_ATTR)):
+        # user attributes (UBERT4Rec / UserSASRec): plain tables whose sum becomes an extra token at position 0
+        self.user_attrs: List[Tuple[str, int]] = []
+        for name, info in (user_attributes or {}).items():
+            kind = info["embedding_type"]
+            if kind not in ("user_embedding", "content_embedding"):
+                raise NotImplementedError(f"user attribute embedding type {kind!r}: only table look-ups are on the B200 path")
+            vu = _attr_vocab_size(name, tokenizers, attr_sizes)
+            self.user_attrs.append((name, vu))
+            attr_specs.append((f"{_USER_ATTR}.{name}.weight", (vu, H)))
+        self.segment_rows = int(segment_rows)
+        if self.segment_rows:
+            attr_specs.append((_SEGMENT, (self.segment_rows, H)))
+        for store, attrs, prefix in ((self.prefusion, prefusion, self.pre_attr_prefix), (self.postfusion, postfusion, _POST_ATTR)):
             for name, info in (attrs or {}).items():
                 kind = info["embedding_type"]
                 va = _attr_vocab_size(name, tokenizers, attr_sizes)
@@ -88,7 +105,9 @@ class TransformerRecommenderModel(ArenaModule):
                     attr_specs.append((f"{prefix}.{name}.linear.bias", (H,)))
                 else:
                     raise KeyError(f"{kind} invalid attribute embedding type")
-        self.additional_metadata_keys = [n for n, _, _ in self.prefusion] + [n for n, _, _ in self.postfusion]
+        self.additional_userdata_keys = [n for n, _ in self.user_attrs]
+        self.additional_metadata_keys = self.additional_userdata_keys + [n for n, _, _ in self.prefusion] + \
+            [n for n, _, _ in self.postfusion]
         self._init_arena(list(specs) + attr_specs + [("_ghost_zero_row", (H,))])
         self.engine = EncoderEngine(self, cfg)
         self.precision = DEFAULT_PRECISION
@@ -102,7 +121,12 @@ class TransformerRecommenderModel(ArenaModule):
         return self.additional_metadata_keys
 
     def optional_metadata_keys(self) -> List[str]:
-        return []
+        return self.additional_userdata_keys
+
+    @property
+    def user_prefix(self) -> int:
+        """1 when a user token is prepended to every sequence (hidden states then have S+1 positions)"""
+        return 1 if self.user_attrs else 0
 
     # ---- embedding ------------------------------------------------------------------------------
     def _attr_operands(self, attrs: Dict[str, torch.Tensor], which, prefix, T):
@@ -119,14 +143,18 @@ class TransformerRecommenderModel(ArenaModule):
 
     def _embed_spec(self, seq: torch.Tensor, attrs, training: bool, seed: int) -> ops.EmbedSpec:
         B, S = seq.shape
-        singles, bags = self._attr_operands(attrs, self.prefusion, _PRE_ATTR, B * S)
+        singles, bags = self._attr_operands(attrs, self.prefusion, self.pre_attr_prefix, B * S)
+        # only column 0 of a user feature is read (models/ubert4rec/components.py:112-113)
+        users = [(attrs[name][:, 0].contiguous() if attrs[name].dim() > 1 else attrs[name], self.weight(f"{_USER_ATTR}.{name}.weight"))
+                 for name, _vu in self.user_attrs]
+        seg = self.weight(_SEGMENT) if self.segment_rows else None
         ln1 = None if self.ln1_paths is None else (self.weight(self.ln1_paths[0]), self.weight(self.ln1_paths[1]))
         ln2 = None if self.ln2_paths is None else (self.weight(self.ln2_paths[0]), self.weight(self.ln2_paths[1]))
         pos = None if self.pos_table_path is None else self.weight(self.pos_table_path)
         if pos is not None and S > pos.shape[0]:
             raise RuntimeError(f"sequence length {S} exceeds max_seq_length {pos.shape[0]}")
         return ops.EmbedSpec(seq.reshape(-1), self.weight(self.item_table_path), pos, singles, bags, ln1, ln2,
-                             self.cfg.dropout if training else 0.0, seed)
+                             self.cfg.dropout if training else 0.0, seed, users=users, seg_table=seg)
 
     def _embed_backward(self, saved: Saved, d_x: torch.Tensor):
         spec: ops.EmbedSpec = saved.embed_spec
@@ -137,10 +165,36 @@ class TransformerRecommenderModel(ArenaModule):
             off = self._arena.offsets[self._spec_name(self._dln_first)]     # [gamma1, beta1, gamma2, beta2] are glued
             dln = g[off:off + 4 * H].view(4, H)
         d_item, d_attr = ops.embed_bwd(spec, B, S, d_x, saved.embed_stats, dln)
-        ops.embgrad_sorted_reduce(spec.item_ids, d_item, self.weight(self.item_table_path, g))
+        if not self.user_attrs:
+            ops.embgrad_sorted_reduce(spec.item_ids, d_item, self.weight(self.item_table_path, g))
+            if self.pos_table_path is not None:
+                ops.posgrad_reduce(d_item, B, S, self.weight(self.pos_table_path, g))
+            self._attr_backward(saved.extra["attrs"], self.prefusion, self.pre_attr_prefix, d_attr, B * S)
+            return
+        # user prefix: S counts the user position.  Rows of the user position carry the gradient of the user-embedding sum;
+        # for the item-side tables they are skipped by giving them the id -1.
+        Si = S - 1
+        dev = d_item.device
+
+        def with_user_column(ids, fill):
+            ids = ids.reshape(B, Si, *ids.shape[2:]) if ids.dim() > 2 else ids.reshape(B, Si)
+            col = torch.full((B, 1) + tuple(ids.shape[2:]), fill, dtype=torch.int64, device=dev)
+            return torch.cat([col, ids], dim=1)
+
+        ops.embgrad_sorted_reduce(with_user_column(spec.item_ids, -1).reshape(-1), d_item, self.weight(self.item_table_path, g))
         if self.pos_table_path is not None:
-            ops.posgrad_reduce(d_item, B, S, self.weight(self.pos_table_path, g))
-        self._attr_backward(saved.extra["attrs"], self.prefusion, _PRE_ATTR, d_attr, B * S)
+            ops.posgrad_reduce(d_item, B, Si, self.weight(self.pos_table_path, g), prefix=1)
+        attrs = saved.extra["attrs"]
+        shifted = {name: with_user_column(attrs[name], -1) for name, _k, _v in self.prefusion}
+        self._attr_backward(shifted, self.prefusion, self.pre_attr_prefix, d_attr, B * S)
+        user_rows = torch.arange(B, device=dev, dtype=torch.int64) * S
+        d_user = ops.gather_rows(d_attr, user_rows)
+        for (ids, _tab), (name, _vu) in zip(spec.users, self.user_attrs):
+            ops.embgrad_sorted_reduce(ids, d_user, self.weight(f"{_USER_ATTR}.{name}.weight", g))
+        if self.segment_rows:
+            seg_ids = torch.ones(B, S, dtype=torch.int64, device=dev)
+            seg_ids[:, 0] = 0
+            ops.embgrad_sorted_reduce(seg_ids.reshape(-1), d_attr, self.weight(_SEGMENT, g))
 
     def _attr_backward(self, attrs, which, prefix, d_rows, T):
         g = self._arena.ensure_grad()
@@ -170,11 +224,19 @@ class TransformerRecommenderModel(ArenaModule):
             if not self.arena_is_intact():
                 self._repack()
             B, S = seq.shape
-            saved = Saved(B=B, S=S, seed=0, training=False, key_valid=padding_mask)
+            S += self.user_prefix
+            saved = Saved(B=B, S=S, seed=0, training=False, key_valid=self._key_valid(padding_mask, seq))
             x, _ = ops.embed_fwd(self._embed_spec(seq, attrs, False, 0), B, S)
             return self.engine.blocks_forward(x, saved, select_rows=rows)
         hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
         return ops.gather_rows(hidden, rows)
+
+    def _key_valid(self, padding_mask: Optional[torch.Tensor], seq: torch.Tensor) -> Optional[torch.Tensor]:
+        """key-validity bits of the encoder; the user position is never padding (models/ubert4rec/components.py:170-174)"""
+        if not self.user_prefix or padding_mask is None:
+            return padding_mask
+        ones = torch.ones(seq.shape[0], 1, dtype=padding_mask.dtype, device=padding_mask.device)
+        return torch.cat([ones, padding_mask], dim=1)
 
     def encode(self, seq: torch.Tensor, padding_mask: Optional[torch.Tensor], attrs: Dict[str, torch.Tensor],
                training: bool = False) -> Tuple[torch.Tensor, Saved]:
@@ -182,13 +244,17 @@ class TransformerRecommenderModel(ArenaModule):
         if not self.arena_is_intact():
             self._repack()
         B, S = seq.shape
-        saved = Saved(B=B, S=S, seed=self._next_seed() if training else 0, training=training, key_valid=padding_mask)
+        S += self.user_prefix          # hidden states cover the prepended user token as well
+        saved = Saved(B=B, S=S, seed=self._next_seed() if training else 0, training=training,
+                      key_valid=self._key_valid(padding_mask, seq))
         saved.extra["attrs"] = attrs
         spec = self._embed_spec(seq, attrs, training, saved.seed)
         saved.embed_spec = spec
         x, saved.embed_stats = ops.embed_fwd(spec, B, S, save_stats=training)
         x = self.engine.blocks_forward(x, saved)
         if self.postfusion:
+            if self.user_prefix:
+                raise NotImplementedError("post-fusion attributes together with user attributes")
             singles, bags = self._attr_operands(attrs, self.postfusion, _POST_ATTR, B * S)
             zero_ids = torch.zeros(B * S, dtype=torch.int64, device=seq.device)
             ctx_spec = ops.EmbedSpec(zero_ids, self.weight("_ghost_zero_row").view(1, -1), None, singles, bags)
@@ -269,7 +335,7 @@ class TransformerRecommenderModel(ArenaModule):
             return self._sasrec_forward(sequence, hidden)
         rows, _ = self.modify(hidden)
         w, b = self.projection_operands()
-        return ops.gemm(rows, w, bias=b).view(B, S, self.item_vocab_size)
+        return ops.gemm(rows, w, bias=b).view(B, S + self.user_prefix, self.item_vocab_size)
 
     def _sasrec_forward(self, sequence: InputSequence, hidden: torch.Tensor):
         pos = sequence.get_attribute("positive_samples")
@@ -635,4 +701,116 @@ class SASRecModel(TransformerRecommenderModel):
             for sub in ("item_embedding.embedding.weight", "position_embedding.weight", "embedding_norm.weight",
                         "embedding_norm.bias"):
                 _alias(self, f"_projection_layer.embedding.{sub}", _get_param(self, f"{base}.{sub}"))
+        _init_xavier(self)
+
+
+# ----------------------------------------------------------------------------------------------------
+# user-attribute models: a user token built from user-attribute embeddings is prepended to the sequence
+# ----------------------------------------------------------------------------------------------------
+def _tokenizer_sizes(additional_tokenizers, attribute_vocab_sizes):
+    """the reference receives ``InjectTokenizers()`` = {"tokenizers.<name>": tokenizer}; plain sizes may be given instead"""
+    toks = {}
+    for key, tok in (additional_tokenizers or {}).items():
+        toks[key] = tok
+        if key.startswith("tokenizers."):
+            toks[key[len("tokenizers."):]] = tok
+    return toks, attribute_vocab_sizes
+
+
+class UBERT4RecModel(TransformerRecommenderModel):
+    """models/ubert4rec/ubert4rec_model.py:19-92: item + position embeddings (no LayerNorm of their own) + item attributes,
+    user token at position 0, optional segment embedding, LayerNorm + dropout, CAUSAL encoder (``bidirectional=False`` in the
+    reference), FFN modifier, untied Linear projection.  Outputs have S+1 positions when user attributes are configured."""
+
+    item_table_path = f"{_EMB}.item_embedding_layer.item_embedding.embedding.weight"
+    ln2_paths = (f"{_EMB}.norm_embedding.weight", f"{_EMB}.norm_embedding.bias")
+    modifier_kind = "ffn"
+    projection_kind = "linear"
+    pre_attr_prefix = _ADD_ATTR
+    blocks_path = "_sequence_representation_layer.transformer_encoder.transformer_blocks"
+    _dln_first = "_ghost_ln1"
+
+    def __init__(self, transformer_hidden_size: int, num_transformer_heads: int, num_transformer_layers: int,
+                 item_vocab_size: int, max_seq_length: int, transformer_dropout: float,
+                 additional_attributes: Dict[str, Dict[str, Any]] = None, additional_tokenizers: Dict[str, Any] = None,
+                 user_attributes: Dict[str, Dict[str, Any]] = None, positional_embedding: bool = True,
+                 segment_embedding: bool = False, embedding_pooling_type: str = None, initializer_range: float = 0.02,
+                 transformer_intermediate_size: Optional[int] = None, transformer_attention_dropout: Optional[float] = None,
+                 attribute_vocab_sizes: Dict[str, int] = None):
+        super().__init__()
+        if embedding_pooling_type:
+            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        H, V = transformer_hidden_size, item_vocab_size
+        if user_attributes:
+            max_seq_length += 1                                   # ubert4rec_model.py:40-43
+        cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, False,
+                              transformer_intermediate_size, transformer_attention_dropout)
+        specs = [(self.item_table_path, (V, H))]
+        if positional_embedding:
+            self.pos_table_path = f"{_EMB}.item_embedding_layer.position_embedding.weight"
+            specs.append((self.pos_table_path, (max_seq_length, H)))
+        specs += [("_ghost_ln1+", (2 * H,)), (self.ln2_paths[0] + "+", (H,)), (self.ln2_paths[1], (H,))]
+        specs += block_param_specs(cfg, self.blocks_path) + modifier_param_specs(H)
+        specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
+        toks, sizes = _tokenizer_sizes(additional_tokenizers, attribute_vocab_sizes)
+        # rows of the segment table as the reference counts them (components.py:75-90): one for the item attributes as a
+        # whole plus one per user attribute; rows 0 (user) and 1 (items) are the ones ever read
+        seg_rows = ((1 if additional_attributes else 0) + len(user_attributes or {})) if segment_embedding else 0
+        if segment_embedding and (not user_attributes or seg_rows < 2):
+            raise NotImplementedError("segment_embedding needs user attributes and at least two segment rows (the reference "
+                                      "indexes row 1)")
+        self._setup(cfg, V, max_seq_length, specs, additional_attributes, None, toks, sizes, "add",
+                    user_attributes=user_attributes, segment_rows=seg_rows)
+        _init_normal(self, initializer_range)
+
+
+class UserSASRecModel(TransformerRecommenderModel):
+    """models/user_sasrec/user_sasrec_model.py:21-107: SASRec whose sequence starts with a user token.  The item embedding is
+    normed + dropped once by its TransformerEmbedding, the concatenated sequence once more (quirk Q2 applies to the item
+    positions only); causal encoder, identity modifier; ``mode="full"`` scores the catalog with a Linear layer."""
+
+    item_table_path = f"{_EMB}.item_embedding_layer.item_embedding.embedding.weight"
+    ln1_paths = (f"{_EMB}.item_embedding_layer.embedding_norm.weight", f"{_EMB}.item_embedding_layer.embedding_norm.bias")
+    ln2_paths = (f"{_EMB}.norm_embedding.weight", f"{_EMB}.norm_embedding.bias")
+    modifier_kind = "identity"
+    projection_kind = "linear"
+    pre_attr_prefix = _ADD_ATTR
+    blocks_path = "_sequence_representation_layer.transformer_encoder.transformer_blocks"
+    _dln_first = f"{_EMB}.item_embedding_layer.embedding_norm.weight"
+
+    def __init__(self, transformer_hidden_size: int, num_transformer_heads: int, num_transformer_layers: int,
+                 item_vocab_size: int, max_seq_length: int, transformer_dropout: float,
+                 additional_attributes: Dict[str, Dict[str, Any]] = None, additional_tokenizers: Dict[str, Any] = None,
+                 user_attributes: Dict[str, Dict[str, Any]] = None, segment_embedding: bool = False,
+                 embedding_pooling_type: str = None, transformer_intermediate_size: int = None,
+                 transformer_attention_dropout: float = None, mode: str = "neg_sampling", positional_embedding: bool = True,
+                 replace_first_item: bool = False, attribute_vocab_sizes: Dict[str, int] = None):
+        super().__init__()
+        if embedding_pooling_type:
+            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        if replace_first_item:
+            raise NotImplementedError("replace_first_item=True is not on the B200 path")
+        if mode != "full":
+            raise NotImplementedError("UserSASRecModel: only mode='full' is on the B200 path (the sampled projection of the "
+                                      "reference, user_sasrec/components.py, is a next row)")
+        H, V = transformer_hidden_size, item_vocab_size
+        if user_attributes:
+            max_seq_length += 1
+        cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, False,
+                              transformer_intermediate_size, transformer_attention_dropout)
+        self.mode = mode
+        specs = [(self.item_table_path, (V, H))]
+        if positional_embedding:
+            self.pos_table_path = f"{_EMB}.item_embedding_layer.position_embedding.weight"
+            specs.append((self.pos_table_path, (max_seq_length, H)))
+        specs += [(self.ln1_paths[0] + "+", (H,)), (self.ln1_paths[1] + "+", (H,)),
+                  (self.ln2_paths[0] + "+", (H,)), (self.ln2_paths[1], (H,))]
+        specs += block_param_specs(cfg, self.blocks_path)
+        specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
+        toks, sizes = _tokenizer_sizes(additional_tokenizers, attribute_vocab_sizes)
+        seg_rows = ((1 if additional_attributes else 0) + len(user_attributes or {})) if segment_embedding else 0
+        if segment_embedding and (not user_attributes or seg_rows < 2):
+            raise NotImplementedError("segment_embedding needs user attributes and at least two segment rows")
+        self._setup(cfg, V, max_seq_length, specs, additional_attributes, None, toks, sizes, "add",
+                    user_attributes=user_attributes, segment_rows=seg_rows)
         _init_xavier(self)

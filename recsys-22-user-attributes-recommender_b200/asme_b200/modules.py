@@ -330,10 +330,125 @@ class SequenceNextItemPredictionTrainingModule(_ModuleBase):
         return self._adam(self.weight_decay)
 
 
+def _prepend_pad_column(target: torch.Tensor, pad_id: int) -> torch.Tensor:
+    """targets of the S item positions -> targets of the S+1 encoder positions: the user position never contributes
+    (ubert_masked_training_module.py:75-77 prepends a False/0 column, = the pad id = ignore_index)"""
+    col = torch.full((target.shape[0], 1), pad_id, dtype=target.dtype, device=target.device)
+    return torch.cat([col, target], dim=1)
+
+
+class UBERTMaskedTrainingModule(MaskedTrainingModule):
+    """modules/ubert_masked_training_module.py: cloze training of UBERT4Rec.  The model's outputs have one more position than
+    the item sequence (the user token at position 0); targets and the MASK selection are shifted accordingly.  Like the
+    reference (:183-186) weight decay is accepted and ignored."""
+
+    def __init__(self, model: TransformerRecommenderModel, item_tokenizer=None, metrics: MetricsContainer = None,
+                 learning_rate: float = 0.001, beta_1: float = 0.99, beta_2: float = 0.998, weight_decay: float = 0.001,
+                 num_warmup_steps: int = 10000):
+        super().__init__(model, item_tokenizer, metrics, learning_rate, beta_1, beta_2, weight_decay, num_warmup_steps)
+        self.user_key_len = len(model.optional_metadata_keys())
+
+    def training_step(self, batch, batch_idx):
+        seq, pm, meta = self._input(batch)
+        target = batch[TARGET_ENTRY_NAME]
+        if target.dim() > 2:
+            raise NotImplementedError("basket targets are outside the B200 hot path")
+        if self.user_key_len > 0:
+            target = _prepend_pad_column(target, self.item_tokenizer.pad_token_id)
+        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id, rows=batch.get("_target_rows"))
+        loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
+        self.log(LOG_KEY_TRAINING_LOSS, loss, prog_bar=False)
+        return {"loss": loss}
+
+    def _mask_rows(self, seq: torch.Tensor) -> torch.Tensor:
+        """flat row (into the B x (S+1) hidden states) of every sequence's MASK token (:93-101)"""
+        B, S = seq.shape
+        shift = 1 if self.user_key_len > 0 else 0
+        pos = (seq == self.item_tokenizer.mask_token_id).to(torch.int32).argmax(dim=1).to(torch.int64)
+        return torch.arange(B, device=seq.device, dtype=torch.int64) * (S + shift) + pos + shift
+
+    def _get_prediction_for_masked_item(self, batch, batch_idx):
+        seq = batch[ITEM_SEQ_ENTRY_NAME]
+        logits = self(batch, batch_idx)
+        return logits.reshape(-1, logits.shape[-1])[self._mask_rows(seq)]
+
+    def _eval_step(self, batch, batch_idx, is_test=False):
+        seq, pm, meta = self._input(batch)
+        targets = batch[TARGET_ENTRY_NAME]
+        if not self.fused_eval or targets.dim() != 1:
+            prediction = self._get_prediction_for_masked_item(batch, batch_idx)
+            return build_eval_step_return_dict(seq, prediction, targets)
+        out = self.model.evaluate_rank(seq, pm, meta, targets, k=self._eval_k(), rows=self._mask_rows(seq),
+                                       with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id,
+                                       full_rank=self._full_rank())
+        if self.eval_loss:
+            self.log(LOG_KEY_TEST_LOSS if is_test else LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        return build_eval_step_return_dict(seq, pred, targets)
+
+
+class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
+    """modules/user_next_item_prediction_training_module.py: UserSASRec with ``mode="full"``.  Training drops the user
+    position from the logits (:151-155) -- here the targets get a pad column instead, which selects the same rows.  Evaluation
+    reproduces the reference's row choice exactly: ``logits[b, length_b - 1]`` of the S+1 positions (:124-135), i.e. the
+    position BEFORE the last item (position 0 is the user token)."""
+
+    def __init__(self, model: TransformerRecommenderModel, item_tokenizer=None, metrics: MetricsContainer = None,
+                 learning_rate: float = 0.001, beta_1: float = 0.99, beta_2: float = 0.998, weight_decay: float = 0,
+                 loss_function=None, first_item: bool = False):
+        super().__init__(model, item_tokenizer, metrics, learning_rate, beta_1, beta_2, weight_decay, loss_function)
+        if first_item:
+            raise NotImplementedError("first_item=True (replace_first_item models) is not on the B200 path")
+        self.user_key_len = len(model.optional_metadata_keys())
+        self.first_item = first_item
+
+    def training_step(self, batch, batch_idx):
+        seq = batch[ITEM_SEQ_ENTRY_NAME]
+        pm = get_padding_mask(seq, self.item_tokenizer.pad_token_id)
+        target = batch[TARGET_ENTRY_NAME]
+        if target.dim() != 2:
+            raise NotImplementedError("UserNextItemPredictionTrainingModule: per-position targets (N,S) expected")
+        if self.user_key_len > 0:
+            target = _prepend_pad_column(target, self.item_tokenizer.pad_token_id)
+        meta = get_additional_meta_data(self.model, batch)
+        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id, rows=batch.get("_target_rows"))
+        loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
+        self.log(LOG_KEY_TRAINING_LOSS, loss)
+        return {"loss": loss}
+
+    def _target_rows(self, seq: torch.Tensor, pm: torch.Tensor) -> torch.Tensor:
+        B, S = seq.shape
+        S1 = S + (1 if self.user_key_len > 0 else 0)
+        last = pm.sum(dim=-1).to(torch.int64) - 1
+        last = torch.where(last < 0, last + S1, last)            # advanced indexing wraps -1 around
+        return torch.arange(B, device=seq.device, dtype=torch.int64) * S1 + last
+
+    def _extract_target_logits(self, input_seq, logits):
+        pm = get_padding_mask(input_seq, self.item_tokenizer.pad_token_id)
+        return logits.reshape(-1, logits.shape[-1])[self._target_rows(input_seq, pm)]
+
+    def validation_step(self, batch, batch_idx):
+        seq = batch[ITEM_SEQ_ENTRY_NAME]
+        target = batch[TARGET_ENTRY_NAME]
+        pm = get_padding_mask(seq, self.item_tokenizer.pad_token_id)
+        if not self.fused_eval or target.dim() != 1:
+            logits = self(batch, batch_idx)
+            return build_eval_step_return_dict(seq, self._extract_target_logits(seq, logits), target)
+        out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), target, k=self._eval_k(),
+                                       rows=self._target_rows(seq, pm), with_loss=self.eval_loss,
+                                       pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
+        if self.eval_loss:
+            self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        return build_eval_step_return_dict(seq, pred, target)
+
+
 REGISTRY = {
     # key -> (module class, model class name, model kwargs) ; mirrors modules/config.py:30-55
     "bert4rec": (MaskedTrainingModule, "BERT4RecModel", {}),
     "kebert4rec": (MaskedTrainingModule, "KeBERT4RecModel", {}),
     "sasrec-cross": (NextItemPredictionTrainingModule, "SASRecModel", {}),
     "sasrec-neg": (SequenceNextItemPredictionTrainingModule, "SASRecModel", {}),
+    "ubert4rec": (UBERTMaskedTrainingModule, "UBERT4RecModel", {}),
+    "user-sasrec-full": (UserNextItemPredictionTrainingModule, "UserSASRecModel", {"mode": "full"}),
 }

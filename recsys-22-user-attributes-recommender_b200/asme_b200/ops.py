@@ -72,7 +72,8 @@ class EmbedSpec:
 
     def __init__(self, item_ids, item_table, pos_table=None, attrs: Sequence[Tuple[torch.Tensor, torch.Tensor]] = (),
                  bags: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = (), ln1=None, ln2=None, p_drop=0.0,
-                 seed=0, site_a=SITE_EMBED_A, site_b=SITE_EMBED_B):
+                 seed=0, site_a=SITE_EMBED_A, site_b=SITE_EMBED_B, users: Sequence[Tuple[torch.Tensor, torch.Tensor]] = (),
+                 seg_table=None):
         self.item_ids = _i64(item_ids)
         self.item_table = _f32(item_table, "item_table")
         self.pos_table = None if pos_table is None else _f32(pos_table, "pos_table")
@@ -82,6 +83,13 @@ class EmbedSpec:
         self.ln1 = None if ln1 is None else (_f32(ln1[0]), _f32(ln1[1]))
         self.ln2 = None if ln2 is None else (_f32(ln2[0]), _f32(ln2[1]))
         self.p_drop, self.seed, self.site_a, self.site_b = float(p_drop), int(seed), site_a, site_b
+        # user prefix: (ids (B), table (Vu,H)) per user attribute; the output then has one more position per sequence
+        self.users = [(_i64(i).reshape(-1), _f32(t, "user_table")) for i, t in users]
+        self.seg_table = None if seg_table is None else _f32(seg_table, "seg_table")
+        if self.seg_table is not None and not self.users:
+            raise RuntimeError("asme_b200: a segment embedding needs user attributes (the reference indexes row 1 of it)")
+        if len(self.users) > _lib.ASME_MAX_ATTR:
+            raise RuntimeError("asme_b200: too many user-attribute tables")
         if len(self.attrs) > _lib.ASME_MAX_ATTR or len(self.bags) > _lib.ASME_MAX_ATTR:
             raise RuntimeError("asme_b200: too many attribute tables")
 
@@ -101,10 +109,15 @@ class EmbedSpec:
         if self.ln2 is not None:
             d.ln2_gamma, d.ln2_beta = self.ln2[0].data_ptr(), self.ln2[1].data_ptr()
         d.p_drop, d.seed, d.site_a, d.site_b = self.p_drop, self.seed, self.site_a, self.site_b
+        d.n_user = len(self.users)
+        for k, (ids, tab) in enumerate(self.users):
+            d.user_ids[k], d.user_table[k] = ids.data_ptr(), tab.data_ptr()
+        d.seg_table = None if self.seg_table is None else self.seg_table.data_ptr()
         return d
 
 
 def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False):
+    """S counts the user position when ``spec.users`` is not empty (item ids are then (B, S-1))."""
     H = spec.item_table.shape[1]
     T = B * S
     out = torch.empty(T, H, dtype=torch.float32, device=spec.item_table.device)
@@ -122,7 +135,7 @@ def embed_bwd(spec: EmbedSpec, B: int, S: int, d_out: torch.Tensor, stats: Optio
     T = B * S
     d_out = _f32(d_out)
     d_item = torch.empty(T, H, dtype=torch.float32, device=d_out.device)
-    two = spec.ln1 is not None and (spec.attrs or spec.bags)
+    two = spec.ln1 is not None and (spec.attrs or spec.bags or spec.users)
     d_attr = torch.empty_like(d_item) if two else d_item
     ws_bytes = _lib.query("asme_b200_embed_bwd_workspace_bytes", T, H)
     ws = workspace(ws_bytes, d_out.device)
@@ -148,8 +161,14 @@ def embgrad_sorted_reduce(ids: torch.Tensor, d_rows: torch.Tensor, d_table: torc
               _p(ws), ws.numel(), _stream())
 
 
-def posgrad_reduce(d_rows: torch.Tensor, B: int, S: int, d_pos: torch.Tensor):
-    _lib.call("asme_b200_posgrad_reduce", _p(_f32(d_rows)), B, S, d_rows.shape[-1], _p(d_pos), _stream())
+def posgrad_reduce(d_rows: torch.Tensor, B: int, S: int, d_pos: torch.Tensor, prefix: int = 0):
+    """d_pos[s] += sum_b d_rows[b, prefix + s]; d_rows is (B*(S+prefix), H)"""
+    d_rows = _f32(d_rows)
+    H = d_rows.shape[-1]
+    if prefix == 0:
+        _lib.call("asme_b200_posgrad_reduce", _p(d_rows), B, S, H, _p(d_pos), _stream())
+    else:
+        _lib.call("asme_b200_posgrad_reduce_strided", d_rows.data_ptr() + prefix * H * 4, B, S, S + prefix, H, _p(d_pos), _stream())
 
 
 def colsum_accumulate(x: torch.Tensor, out: torch.Tensor):

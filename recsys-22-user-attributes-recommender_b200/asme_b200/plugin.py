@@ -1,4 +1,5 @@
-"""ASME plug-in: re-registers ``bert4rec``, ``kebert4rec``, ``sasrec-cross`` and ``sasrec-neg`` in the reference's
+"""ASME plug-in: re-registers ``bert4rec``, ``kebert4rec``, ``sasrec-cross``, ``sasrec-neg``, ``ubert4rec`` and
+``user-sasrec-full`` in the reference's
 module registry with the B200 model / module classes (modules/registry.py:19-22 ``register_module(...,
 overwrite=True)``; activated through the reference's own ``imports:`` hook,
 init/factories/include/import_factory.py:51-81).  Add to any existing ASME config:
@@ -11,14 +12,17 @@ init/factories/include/import_factory.py:51-81).  Add to any existing ASME confi
 Importing this module outside an ASME process (asme not importable) is a no-op apart from exposing
 ``REGISTRATIONS``, so that the boundary can be tested without the reference installed.
 """
-from .models import BERT4RecModel, KeBERT4RecModel, SASRecModel
-from .modules import MaskedTrainingModule, NextItemPredictionTrainingModule, SequenceNextItemPredictionTrainingModule
+from .models import BERT4RecModel, KeBERT4RecModel, SASRecModel, UBERT4RecModel, UserSASRecModel
+from .modules import (MaskedTrainingModule, NextItemPredictionTrainingModule, SequenceNextItemPredictionTrainingModule,
+                      UBERTMaskedTrainingModule, UserNextItemPredictionTrainingModule)
 
 REGISTRATIONS = {
     "bert4rec": (MaskedTrainingModule, BERT4RecModel),
     "kebert4rec": (MaskedTrainingModule, KeBERT4RecModel),
     "sasrec-cross": (NextItemPredictionTrainingModule, SASRecModel),
     "sasrec-neg": (SequenceNextItemPredictionTrainingModule, SASRecModel),
+    "ubert4rec": (UBERTMaskedTrainingModule, UBERT4RecModel),                      # modules/config.py:33
+    "user-sasrec-full": (UserNextItemPredictionTrainingModule, UserSASRecModel),   # modules/config.py:49
 }
 
 

@@ -197,31 +197,47 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d,
     const int groups = blockDim.x / LANES;
     const long long base = (long long)blockIdx.x * (groups * TOK) + threadIdx.x / LANES;
     const float inv_keep = d.p_drop > 0.f ? 1.0f / (1.0f - d.p_drop) : 1.0f;
-    long long item[TOK];
+    // user prefix (UBERT4Rec / UserSASRec): position 0 of every sequence is the sum of the user-attribute embeddings and the
+    // items follow at positions 1..S-1, i.e. output row (b, s) reads item token b*(S-1) + s-1.  pre = 0: plain layout.
+    const int pre = d.n_user > 0 ? 1 : 0;
+    const float* first[TOK];
     Row<LANES, CH> xs[TOK];
 #pragma unroll
     for (int j = 0; j < TOK; ++j) {
-        const long long t = base + (long long)j * groups;
-        item[j] = t < T ? __ldg(d.item_ids + t) : 0;
+        const long long tj = base + (long long)j * groups;
+        const long long t = tj < T ? tj : 0;
+        const long long b = t / S;
+        const int sp = (int)(t - b * S);
+        if (pre && sp == 0) first[j] = d.user_table[0] + __ldg(d.user_ids[0] + b) * H;
+        else first[j] = d.item_table + __ldg(d.item_ids + (pre ? b * (S - 1) + sp - 1 : t)) * H;
     }
 #pragma unroll
-    for (int j = 0; j < TOK; ++j) xs[j].load(d.item_table + item[j] * H, lane);
+    for (int j = 0; j < TOK; ++j) xs[j].load(first[j], lane);
     // no early exit below: the TOK iterations stay independent straight-line code, so their shuffle / LayerNorm chains interleave
 #pragma unroll
     for (int j = 0; j < TOK; ++j) {
         const long long tj = base + (long long)j * groups;
         const bool ok = tj < T;
         const long long t = ok ? tj : 0;
+        const long long b = t / S;
+        const int sp = (int)(t - b * S);
+        const bool is_user = pre && sp == 0;                  // uniform inside the lane group
+        const long long src = pre ? b * (S - 1) + sp - 1 : t;  // item token feeding this row (unused for the user row)
         Row<LANES, CH> x = xs[j], y;
-        if (d.pos_table) x.add(d.pos_table + (long long)(t % S) * H, lane);
-        if (d.ln1_gamma) {
-            float mean, rstd;
-            ln_forward<LANES, CH>(x, y, d.ln1_gamma, d.ln1_beta, lane, H, mean, rstd);
-            if (stats && lane == 0 && ok) { stats[t] = mean; stats[(size_t)T + t] = rstd; }
-            x = y;
-            if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
+        if (is_user) {
+            for (int u = 1; u < d.n_user; ++u) x.add(d.user_table[u] + __ldg(d.user_ids[u] + b) * H, lane);
+        } else {
+            if (d.pos_table) x.add(d.pos_table + (long long)(sp - pre) * H, lane);
+            if (d.ln1_gamma) {
+                float mean, rstd;
+                ln_forward<LANES, CH>(x, y, d.ln1_gamma, d.ln1_beta, lane, H, mean, rstd);
+                if (stats && lane == 0 && ok) { stats[t] = mean; stats[(size_t)T + t] = rstd; }
+                x = y;
+                if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
+            }
+            if (d.n_attr | d.n_bag) embed_gather_attrs<LANES, CH>(x, d, src, H, lane);
         }
-        if (d.n_attr | d.n_bag) embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
+        if (d.seg_table) x.add(d.seg_table + (is_user ? 0 : H), lane);     // segment 0 = user token, 1 = items
         if (d.ln2_gamma) {
             float mean, rstd;
             ln_forward<LANES, CH>(x, y, d.ln2_gamma, d.ln2_beta, lane, H, mean, rstd);
@@ -249,14 +265,23 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
     const float inv_keep = d.p_drop > 0.f ? 1.0f / (1.0f - d.p_drop) : 1.0f;
     Row<LANES, CH> dg1, db1, dg2, db2;
     zero_row(dg1); zero_row(db1); zero_row(dg2); zero_row(db2);
+    const int pre = d.n_user > 0 ? 1 : 0;
     for (long long t = (long long)blockIdx.x * groups_per_block + group_in_block; t < T;
          t += (long long)gridDim.x * groups_per_block) {
         Row<LANES, CH> x, xhat1, xhat2, g;
-        const long long item = __ldg(d.item_ids + t);
-        x.load(d.item_table + item * H, lane);
-        if (d.pos_table) x.add(d.pos_table + (long long)(t % S) * H, lane);
+        const long long b = t / S;
+        const int sp = (int)(t - b * S);
+        const bool is_user = pre && sp == 0;
+        const long long src = pre ? b * (S - 1) + sp - 1 : t;
+        if (is_user) {
+            x.load(d.user_table[0] + __ldg(d.user_ids[0] + b) * H, lane);
+            for (int u = 1; u < d.n_user; ++u) x.add(d.user_table[u] + __ldg(d.user_ids[u] + b) * H, lane);
+        } else {
+            x.load(d.item_table + __ldg(d.item_ids + src) * H, lane);
+            if (d.pos_table) x.add(d.pos_table + (long long)(sp - pre) * H, lane);
+        }
         float rstd1 = 0.f, rstd2 = 0.f;
-        if (d.ln1_gamma) {
+        if (d.ln1_gamma && !is_user) {
             const float mean = stats[t];
             rstd1 = stats[(size_t)T + t];
 #pragma unroll
@@ -274,7 +299,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
         }
         g.load(d_out + t * H, lane);
         if (d.ln2_gamma) {
-            embed_gather_attrs<LANES, CH>(x, d, t, H, lane);
+            if (!is_user) embed_gather_attrs<LANES, CH>(x, d, src, H, lane);
+            if (d.seg_table) x.add(d.seg_table + (is_user ? 0 : H), lane);
             const float mean = stats[(size_t)2 * T + t];
             rstd2 = stats[(size_t)3 * T + t];
 #pragma unroll
@@ -286,7 +312,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
             ln_backward<LANES, CH>(g, xhat2, d.ln2_gamma, lane, H, rstd2, dg2, db2);
         }
         if (d_attr_rows && d_attr_rows != d_item_rows) g.store(d_attr_rows + t * H, lane);
-        if (d.ln1_gamma) {
+        if (d.ln1_gamma && !is_user) {
             if (d.p_drop > 0.f) apply_dropout<LANES, CH>(g, asme_seed(d.seed), d.site_a, t, H, lane, d.p_drop, inv_keep);
             ln_backward<LANES, CH>(g, xhat1, d.ln1_gamma, lane, H, rstd1, dg1, db1);
         }
@@ -433,6 +459,26 @@ __global__ void posgrad_kernel(const float* __restrict__ d_rows, int B, int S, i
     add4(cur, s);
     *o = cur;
 }
+__global__ void posgrad_strided_kernel(const float* __restrict__ d_rows, int B, int S, long long seq_stride, int H, float* __restrict__ d_pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over S*H/4
+    if (i >= (long long)S * H / 4) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) add4(s, ldg4(d_rows + (long long)b * seq_stride + i * 4));
+    float4* o = reinterpret_cast<float4*>(d_pos) + i;
+    float4 cur = *o;
+    add4(cur, s);
+    *o = cur;
+}
+extern "C" int asme_b200_posgrad_reduce_strided(const float* d_rows, int B, int S, int seq_stride_rows, int H, float* d_pos,
+                                                asme_stream_t stream) {
+    ASME_REQUIRE(H % 4 == 0, "posgrad: H=%d must be a multiple of 4", H);
+    ASME_REQUIRE(seq_stride_rows >= S, "posgrad: sequence stride %d < S=%d", seq_stride_rows, S);
+    const long long n = (long long)S * H / 4;
+    if (n == 0 || B == 0) return ASME_OK;
+    posgrad_strided_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d_rows, B, S, (long long)seq_stride_rows * H, H, d_pos);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
 extern "C" int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H, float* d_pos, asme_stream_t stream) {
     ASME_REQUIRE(H % 4 == 0, "posgrad: H=%d must be a multiple of 4", H);
     const long long n = (long long)S * H / 4;
@@ -466,6 +512,8 @@ extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H
     ASME_REQUIRE(d->n_attr >= 0 && d->n_attr <= ASME_MAX_ATTR && d->n_bag >= 0 && d->n_bag <= ASME_MAX_ATTR,
                  "embed_fwd: too many attribute tables");
     ASME_REQUIRE(d->p_drop >= 0.f && d->p_drop < 1.f, "embed_fwd: dropout p=%f out of range", d->p_drop);
+    ASME_REQUIRE(d->n_user >= 0 && d->n_user <= ASME_MAX_ATTR, "embed_fwd: too many user-attribute tables");
+    ASME_REQUIRE(d->n_user == 0 || (S >= 2 && T % S == 0), "embed_fwd: user prefix needs S >= 2 (S counts the user position) and T = B*S");
     if (T == 0) return ASME_OK;
     const int lanes = lanes_for(H);
     const int groups = 256 / lanes;

@@ -6,7 +6,8 @@
 Writes, next to this file:
   metric_vectors.json    every (predictions, positive_mask, k, expected) tuple of the reference's
                          own metric tests (tests/test_{recall,ndcg,dcg,mrr,precision,f1}.py)
-  bert4rec_small.npz, kebert4rec_small.npz, sasrec_full_small.npz, sasrec_neg_small.npz
+  bert4rec_small.npz, kebert4rec_small.npz, sasrec_full_small.npz, sasrec_neg_small.npz,
+  ubert4rec_small.npz, usasrec_full_small.npz
                          weights (reference state-dict names), inputs, and the reference's
                          outputs: logits / hidden stages, loss, per-parameter gradients,
                          eval rows, metric values.
@@ -203,6 +204,84 @@ def sasrec_fixtures():
     print("sasrec neg loss", float(loss))
 
 
+def user_fixtures():
+    """UBERT4Rec (cloze, user token prepended, segment embedding) and UserSASRec (mode="full") -- SURVEY.md 8f row 1."""
+    from asme.core.models.ubert4rec.ubert4rec_model import UBERT4RecModel
+    from asme.core.models.user_sasrec.user_sasrec_model import UserSASRecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    gen = torch.Generator().manual_seed(505)
+    V, S, H, L, heads, B, VU, VG, VC = 67, 11, 16, 2, 2, 6, 9, 7, 13
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V), "user_id": ref_shims.make_tokenizer(VU, "u"),
+                                     "gender": ref_shims.make_tokenizer(VG, "g"), "category": ref_shims.make_tokenizer(VC, "c")})
+    toks = {"tokenizers.user_id": ref_shims.make_tokenizer(VU, "u"), "tokenizers.gender": ref_shims.make_tokenizer(VG, "g"),
+            "tokenizers.category": ref_shims.make_tokenizer(VC, "c")}      # the factory resolves these annotations, not @inject
+    user_attributes = {"user_id": {"embedding_type": "user_embedding"}, "gender": {"embedding_type": "content_embedding"}}
+    additional = {"category": {"embedding_type": "content_embedding"}}
+    seq, lengths = make_sequences(gen, B, S, V)
+    # user attributes arrive as (B,S) sequence features of which only column 0 is read (ubert4rec/components.py:112-113)
+    uid = torch.randint(3, VU, (B, 1), generator=gen).repeat(1, S)
+    gender = torch.randint(3, VG, (B, 1), generator=gen).repeat(1, S)
+    cat = torch.randint(3, VC, (B, S), generator=gen)
+    # ---- UBERT4Rec
+    model = UBERT4RecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                           item_vocab_size=V, additional_tokenizers=toks,
+                           max_seq_length=S, transformer_dropout=0.0, additional_attributes=additional,
+                           user_attributes=user_attributes, positional_embedding=True, segment_embedding=True)
+    randomize(model, gen)
+    inp, tgt = cloze(seq, lengths, gen)
+    c = cat.clone()
+    c[inp == 0] = 0
+    c[inp == 1] = 1
+    attrs = {"user_id": uid, "gender": gender, "category": c}
+    logits = model(InputSequence(inp, inp.ne(0), attrs))                       # (B, S+1, V)
+    tgt1 = torch.cat([torch.zeros(B, 1, dtype=tgt.dtype), tgt], dim=1)         # ubert_masked_training_module.py:75-77
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.reshape(-1, V), tgt1.reshape(-1))
+    loss.backward()
+    ev = seq.clone()
+    for i in range(B):
+        n = min(int(lengths[i]), S - 1)
+        ev[i, n] = 1
+        ev[i, n + 1:] = 0
+    ce = cat.clone()
+    ce[ev == 0] = 0
+    ce[ev == 1] = 1
+    with torch.no_grad():
+        full = model(InputSequence(ev, ev.ne(0), {"user_id": uid, "gender": gender, "category": ce}))
+        mask1 = torch.cat([torch.zeros(B, 1, dtype=torch.bool), ev.eq(1)], dim=1)   # ubert_masked_training_module.py:93-97
+        ev_logits = full[mask1]
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": inp, "target": tgt, "user_id": uid, "gender": gender,
+            "category": c, "logits": logits, "loss": loss, "eval_input": ev, "eval_category": ce, "eval_logits": ev_logits}
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "ubert4rec_small.npz"), **to_np(data))
+    print("ubert4rec loss", float(loss))
+    # ---- UserSASRec, mode="full"
+    model = UserSASRecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                            item_vocab_size=V, additional_tokenizers=toks,
+                            max_seq_length=S, transformer_dropout=0.0, additional_attributes=additional,
+                            user_attributes=user_attributes, segment_embedding=False, mode="full")
+    randomize(model, gen)
+    tgt = torch.zeros_like(seq)
+    for i in range(B):
+        n = int(lengths[i])
+        tgt[i, :n] = torch.randint(3, V, (n,), generator=gen)
+    c = cat.clone()
+    c[seq == 0] = 0
+    attrs = {"user_id": uid, "gender": gender, "category": c}
+    logits = model(InputSequence(seq, seq.ne(0), attrs))                        # (B, S+1, V)
+    item_logits = logits[:, 1:, :]                                              # user_next_item_prediction_training_module.py:151-155
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(item_logits.reshape(-1, V), tgt.reshape(-1))
+    loss.backward()
+    # evaluation rows exactly as the reference module picks them: index (length - 1) of the S+1 positions (:124-135)
+    last = logits.detach()[torch.arange(B), seq.ne(0).sum(-1) - 1]
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": seq, "target": tgt, "user_id": uid, "gender": gender,
+            "category": c, "logits": logits, "loss": loss, "eval_logits": last}
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "usasrec_full_small.npz"), **to_np(data))
+    print("usasrec full loss", float(loss))
+
+
 def metrics_fixture():
     """Reference metric classes on random scores; ties are made deterministic by patching
     torch.argsort to a stable sort inside the reference call (the reference's own argsort is
@@ -253,8 +332,9 @@ def metrics_fixture():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    export_metric_vectors()
-    bert4rec_fixture()
-    kebert4rec_fixture()
-    sasrec_fixtures()
-    metrics_fixture()
+    only = sys.argv[1:]
+    steps = {"metric_vectors": export_metric_vectors, "bert4rec": bert4rec_fixture, "kebert4rec": kebert4rec_fixture,
+             "sasrec": sasrec_fixtures, "user": user_fixtures, "metrics": metrics_fixture}
+    for name, fn in steps.items():
+        if not only or name in only:
+            fn()

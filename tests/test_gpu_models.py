@@ -122,6 +122,63 @@ def test_sasrec_neg_vs_reference_fixture(golden_dir):
     close(model(InputSequence(inp, inp.ne(0), {"positive_samples": items})), z["eval_logits"], msg="eval logits (items)")
 
 
+def _user_attrs(z, category_key="category"):
+    return {"user_id": torch.from_numpy(z["user_id"]).cuda(), "gender": torch.from_numpy(z["gender"]).cuda(),
+            "category": torch.from_numpy(z[category_key]).cuda()}
+
+
+def test_ubert4rec_vs_reference_fixture(golden_dir):
+    """SURVEY.md 8f row 1: user token prepended (two user-attribute tables), item attribute, segment embedding, causal encoder;
+    logits have S+1 positions; training / evaluation through the drop-in module exactly as the reference module slices them"""
+    from asme_b200.data import InputSequence
+    from asme_b200.modules import UBERTMaskedTrainingModule
+    z, w, model = build_from_fixture(golden_dir, "ubert4rec_small.npz")
+    model.load_state_dict(w)
+    model = model.cuda().train()
+    inp, tgt = torch.from_numpy(z["input"]).cuda(), torch.from_numpy(z["target"]).cuda()
+    attrs = _user_attrs(z)
+    logits = model(InputSequence(inp, inp.ne(0), attrs))
+    assert tuple(logits.shape) == tuple(z["logits"].shape)
+    close(logits, z["logits"], msg="logits")
+    module = UBERTMaskedTrainingModule(model, num_warmup_steps=0)
+    module.fused_eval = True
+    out = module.training_step({"item": inp, "item.target": tgt, **attrs}, 0)
+    close(out["loss"], z["loss"], rtol=1e-5, atol=1e-5, msg="loss")
+    out["loss"].backward()
+    _check_grads(model, z)
+    model.eval()
+    ev = torch.from_numpy(z["eval_input"]).cuda()
+    rows = z["eval_logits"]
+    et = torch.randint(3, int(z["V"]), (ev.shape[0],), generator=torch.Generator().manual_seed(1))
+    res = model.evaluate_rank(ev, ev.ne(0), _user_attrs(z, "eval_category"), et.cuda(), k=10, rows=module._mask_rows(ev))
+    close(res["target_score"], rows[np.arange(rows.shape[0]), et.numpy()], msg="target score")
+    assert np.array_equal(res["rank"].cpu().numpy(), O.target_rank(rows, et.numpy()))
+    assert np.array_equal(res["topk_idx"].cpu().numpy(), O.topk_ids(rows, 10))
+    pred = module._get_prediction_for_masked_item({"item": ev, **_user_attrs(z, "eval_category")}, 0)
+    close(pred, rows, msg="masked-item logits")
+
+
+def test_usasrec_full_vs_reference_fixture(golden_dir):
+    from asme_b200.data import InputSequence
+    from asme_b200.modules import UserNextItemPredictionTrainingModule
+    z, w, model = build_from_fixture(golden_dir, "usasrec_full_small.npz")
+    model.load_state_dict(w)
+    model = model.cuda().train()
+    inp, tgt = torch.from_numpy(z["input"]).cuda(), torch.from_numpy(z["target"]).cuda()
+    attrs = _user_attrs(z)
+    close(model(InputSequence(inp, inp.ne(0), attrs)), z["logits"], msg="logits")
+    module = UserNextItemPredictionTrainingModule(model)
+    out = module.training_step({"item": inp, "item.target": tgt, **attrs}, 0)
+    close(out["loss"], z["loss"], rtol=1e-5, atol=1e-5, msg="loss")
+    out["loss"].backward()
+    _check_grads(model, z)
+    model.eval()
+    close(module.predict_step({"item": inp, **attrs}, 0), z["eval_logits"], msg="eval rows (reference row choice)")
+    et = torch.randint(3, int(z["V"]), (inp.shape[0],), generator=torch.Generator().manual_seed(0))
+    res = model.evaluate_rank(inp, inp.ne(0), attrs, et.cuda(), k=5, rows=module._target_rows(inp, inp.ne(0)))
+    assert np.array_equal(res["rank"].cpu().numpy(), O.target_rank(z["eval_logits"], et.numpy()))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # fresh seeded inputs vs the oracle at the BASELINE.json shapes (reduced batch so that the CPU oracle takes seconds)
 # ------------------------------------------------------------------------------------------------------------

@@ -27,6 +27,16 @@ def build_from_fixture(golden_dir, name):
                                 attribute_vocab_sizes={"category": w["_sequence_embedding_layer.prefusion_attribute_embeddings.category.weight"].shape[0],
                                                        "tags": w["_sequence_embedding_layer.prefusion_attribute_embeddings.tags.linear.weight"].shape[1]},
                                 **kw)
+    elif name.startswith("ubert4rec") or name.startswith("usasrec"):
+        from asme_b200.models import UBERT4RecModel, UserSASRecModel
+        emb = "_sequence_embedding_layer"
+        sizes = {"user_id": w[f"{emb}.user_attribute_embeddings.user_id.weight"].shape[0],
+                 "gender": w[f"{emb}.user_attribute_embeddings.gender.weight"].shape[0],
+                 "category": w[f"{emb}.additional_attribute_embeddings.category.weight"].shape[0]}
+        ukw = dict(additional_attributes={"category": {"embedding_type": "content_embedding"}},
+                   user_attributes={"user_id": {"embedding_type": "user_embedding"}, "gender": {"embedding_type": "content_embedding"}},
+                   attribute_vocab_sizes=sizes, **kw)
+        model = UBERT4RecModel(segment_embedding=True, **ukw) if name.startswith("ubert4rec") else UserSASRecModel(mode="full", **ukw)
     elif name.startswith("sasrec_full"):
         model = SASRecModel(mode="full", **kw)
     else:
@@ -34,7 +44,8 @@ def build_from_fixture(golden_dir, name):
     return z, w, model
 
 
-@pytest.mark.parametrize("name", ["bert4rec_small.npz", "kebert4rec_small.npz", "sasrec_full_small.npz", "sasrec_neg_small.npz"])
+@pytest.mark.parametrize("name", ["bert4rec_small.npz", "kebert4rec_small.npz", "sasrec_full_small.npz", "sasrec_neg_small.npz",
+                                  "ubert4rec_small.npz", "usasrec_full_small.npz"])
 def test_state_dict_is_checkpoint_compatible(golden_dir, name):
     """every key of the reference's state_dict exists with the same shape, and loads strictly"""
     z, w, model = build_from_fixture(golden_dir, name)
@@ -97,7 +108,9 @@ def test_constructor_errors_match_reference():
 
 
 def test_plugin_registration_table():
-    assert set(plugin.REGISTRATIONS) == {"bert4rec", "kebert4rec", "sasrec-cross", "sasrec-neg"}
+    assert set(plugin.REGISTRATIONS) == {"bert4rec", "kebert4rec", "sasrec-cross", "sasrec-neg", "ubert4rec", "user-sasrec-full"}
+    mod_cls, model_cls = plugin.REGISTRATIONS["ubert4rec"]
+    assert mod_cls.__name__ == "UBERTMaskedTrainingModule" and model_cls.__name__ == "UBERT4RecModel"
     mod_cls, model_cls = plugin.REGISTRATIONS["sasrec-neg"]
     assert mod_cls.__name__ == "SequenceNextItemPredictionTrainingModule" and model_cls.__name__ == "SASRecModel"
 
@@ -116,3 +129,23 @@ def test_model_forward_without_gpu_fails_loudly():
     seq = torch.randint(3, 50, (2, 12))
     with pytest.raises(RuntimeError, match="CUDA"):
         m(InputSequence(seq, seq.ne(0), {}))
+
+
+def test_user_models_expose_user_keys_and_extra_position():
+    """models/ubert4rec/ubert4rec_model.py:36-50, :88-92: user attributes are required AND optional metadata, and reserve one more
+    position; the item-side tables keep the reference's names"""
+    from asme_b200.models import UBERT4RecModel, UserSASRecModel
+    kw = dict(additional_attributes={"cat": {"embedding_type": "content_embedding"}},
+              user_attributes={"uid": {"embedding_type": "user_embedding"}}, attribute_vocab_sizes={"cat": 9, "uid": 5})
+    m = UBERT4RecModel(16, 2, 1, 50, 12, 0.0, segment_embedding=True, **kw)
+    assert m.required_metadata_keys() == ["uid", "cat"] and m.optional_metadata_keys() == ["uid"] and m.user_prefix == 1
+    sd = m.state_dict()
+    assert tuple(sd["_sequence_embedding_layer.item_embedding_layer.position_embedding.weight"].shape) == (13, 16)
+    assert tuple(sd["_sequence_embedding_layer.segment_embedding.weight"].shape) == (2, 16)
+    assert "_sequence_representation_layer.transformer_encoder.transformer_blocks.0.attention.output_linear.weight" in sd
+    assert not m.cfg.bidirectional                      # the reference builds UBERT4Rec's encoder with bidirectional=False
+    with pytest.raises(NotImplementedError):
+        UserSASRecModel(16, 2, 1, 50, 12, 0.0, mode="neg_sampling", **kw)
+    with pytest.raises(NotImplementedError):
+        UBERT4RecModel(16, 2, 1, 50, 12, 0.0, user_attributes={"uid": {"embedding_type": "user_linear_upscale"}},
+                       attribute_vocab_sizes={"uid": 5})

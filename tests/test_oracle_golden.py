@@ -112,6 +112,43 @@ def test_sasrec_full_vs_reference(golden_dir):
                                atol=1e-5)
 
 
+def _user_attrs(z, category="category"):
+    return {"user_id": torch.from_numpy(z["user_id"]), "gender": torch.from_numpy(z["gender"]), "category": torch.from_numpy(z[category])}
+
+
+def test_ubert4rec_vs_reference(golden_dir):
+    """user token + segment embedding + item attribute; (B, S+1, V) logits; loss with the pad column the
+    reference module prepends to the targets; evaluation rows = MASK position shifted by the user position"""
+    z, w, g = _load(golden_dir, "ubert4rec_small.npz")
+    inp, tgt = torch.from_numpy(z["input"]), torch.from_numpy(z["target"])
+    heads, layers = int(z["heads"]), int(z["L"])
+    kw = dict(additional=("category",), user=("user_id", "gender"))
+    f = lambda lw, seq=inp, a=_user_attrs(z): O.ubert4rec_logits(lw, seq, a, heads, layers, **kw)
+    torch.testing.assert_close(f(w), torch.from_numpy(z["logits"]), rtol=1e-5, atol=1e-5)
+    tgt1 = torch.cat([torch.zeros(tgt.shape[0], 1, dtype=tgt.dtype), tgt], dim=1)
+    g.pop("_sequence_embedding_layer.segment_embedding.weight")     # row 2 of the table is never read: autograd leaves zeros there
+    loss = _check_grads(w, g, lambda lw: O.cross_entropy_ignore_pad(f(lw), tgt1))
+    torch.testing.assert_close(loss, torch.from_numpy(z["loss"]), rtol=1e-6, atol=1e-6)
+    ev = torch.from_numpy(z["eval_input"])
+    full = f(w, ev, _user_attrs(z, "eval_category"))
+    rows = full[torch.cat([torch.zeros(ev.shape[0], 1, dtype=torch.bool), ev.eq(1)], dim=1)]
+    torch.testing.assert_close(rows, torch.from_numpy(z["eval_logits"]), rtol=1e-5, atol=1e-5)
+
+
+def test_usasrec_full_vs_reference(golden_dir):
+    z, w, g = _load(golden_dir, "usasrec_full_small.npz")
+    inp, tgt = torch.from_numpy(z["input"]), torch.from_numpy(z["target"])
+    heads, layers = int(z["heads"]), int(z["L"])
+    f = lambda lw: O.usasrec_full_logits(lw, inp, _user_attrs(z), heads, layers, additional=("category",), user=("user_id", "gender"))
+    logits = f(w)
+    torch.testing.assert_close(logits, torch.from_numpy(z["logits"]), rtol=1e-5, atol=2e-5)
+    loss = _check_grads(w, g, lambda lw: O.cross_entropy_ignore_pad(f(lw)[:, 1:, :], tgt))
+    torch.testing.assert_close(loss, torch.from_numpy(z["loss"]), rtol=1e-6, atol=1e-6)
+    # the reference module's evaluation rows: index (length - 1) of the S+1 positions
+    rows = logits[torch.arange(inp.shape[0]), inp.ne(0).sum(-1) - 1]
+    torch.testing.assert_close(rows, torch.from_numpy(z["eval_logits"]), rtol=1e-5, atol=2e-5)
+
+
 def test_sasrec_neg_vs_reference(golden_dir):
     z, w, g = _load(golden_dir, "sasrec_neg_small.npz")
     inp = torch.from_numpy(z["input"])
