@@ -317,6 +317,8 @@ int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int 
 int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                           float p_drop, const void* ctx, const void* d_ctx, const float* stats,
                           const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream);
+/* diagnostic: knob 0 selects the backward kernel (1 = single sweep, default; 0 = two sweeps); results agree to rounding */
+int asme_b200_tc_attn_tune(int knob, int value);
 
 /* ------------------------------------------------------------------------------------------
  * K13+K17  SASRec positive/negative dot products fused with the BCE loss

@@ -641,6 +641,272 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, single sweep (default).  The two-sweep kernel above recomputes every score tile twice (once with queries as rows
+// for dQ, once transposed for dK / dV) and its transposed sweep is the expensive one (per-element constants from shared
+// memory).  Here each 128 x 128 sub-tile is visited ONCE with queries as rows: dS -> X and P.drop -> Y are written to shared
+// memory as before, and the same two tiles feed three accumulations
+//     dQ[rt] += X    K[ct]      (X as a K-major A operand, as before)
+//     dK[ct] += X^T  Q[rt]      (X as an MN-major A operand: the same bytes, contraction running down the query rows)
+//     dV[ct] += Y^T  dO[rt]
+// Loop order: key tile ct outer, query tile rt inner, so dK / dV accumulate over the inner loop and every query tile keeps
+// its own dQ accumulator: tensor memory = 2 x 128 (T1, T2) + (2 + n_t) x d <= 512 columns.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                     const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + 32768;
+    uint8_t* sV = sK + 32768;
+    uint8_t* sDO = sV + 32768;
+    uint8_t* sX = sDO + 32768;                // dS:     [2 chunks of 64 keys][128 queries][128 B]
+    uint8_t* sY = sX + 32768;                 // P.drop: same layout
+    AttnBwdShared* sh = reinterpret_cast<AttnBwdShared*>(sY + 32768);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.x, slice = blockIdx.y;
+    const int S = a.S, d = a.d;
+    const int hps = 64 / d;
+    const int n_t = (S + 127) / 128;
+    const int subs_per_head = n_t * n_t;      // sub-tile i: key tile ct = i / n_t, query tile rt = i % n_t
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+        mbar_init(&sh->loaded, 1);
+        mbar_init(&sh->t_full, 1);
+        mbar_init(&sh->x_full, 256);
+        mbar_init(&sh->acc_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+    const uint32_t tm_t1 = tmem_base, tm_t2 = tmem_base + 128, tm_dk = tmem_base + 256, tm_dv = tmem_base + 256 + d,
+                   tm_dq0 = tmem_base + 256 + 2 * d;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&sh->loaded, 4 * 32768);
+            tma_load_2d(sQ, &tmQKV, &sh->loaded, slice * 64, b * S);
+            tma_load_2d(sK, &tmQKV, &sh->loaded, a.H + slice * 64, b * S);
+            tma_load_2d(sV, &tmQKV, &sh->loaded, 2 * a.H + slice * 64, b * S);
+            tma_load_2d(sDO, &tmDO, &sh->loaded, slice * 64, b * S);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(&sh->loaded, 0);
+            tc_fence_after();
+            const int ks_d = d / 16;
+            auto issue_t = [&](int hh, int i) {
+                const int ct = i / n_t, rt = i % n_t;
+                const int ncols = min(128, S - ct * 128);
+                const uint32_t idesc = at_idesc(128, (ncols + 15) / 16 * 16, 0, 0);
+                const uint32_t koff = (uint32_t)(hh * d * 2);
+                // T1 = Q[rt] K[ct]^T (scores),  T2 = dO[rt] V[ct]^T (dP)
+                for (int ks = 0; ks < ks_d; ++ks)
+                    umma_bf16(tm_t1, smem_desc_advance(smem_desc_sw128(smem_u32(sQ + (size_t)rt * 16384)), koff + ks * 32),
+                              smem_desc_advance(smem_desc_sw128(smem_u32(sK + (size_t)ct * 16384)), koff + ks * 32), idesc, (uint32_t)(ks != 0));
+                for (int ks = 0; ks < ks_d; ++ks)
+                    umma_bf16(tm_t2, smem_desc_advance(smem_desc_sw128(smem_u32(sDO + (size_t)rt * 16384)), koff + ks * 32),
+                              smem_desc_advance(smem_desc_sw128(smem_u32(sV + (size_t)ct * 16384)), koff + ks * 32), idesc, (uint32_t)(ks != 0));
+                umma_commit(&sh->t_full);
+            };
+            const uint32_t idesc_k = at_idesc(128, d, 0, 1);      // A K-major  (X),    B MN-major
+            const uint32_t idesc_mn = at_idesc(128, d, 1, 1);     // A MN-major (X^T),  B MN-major
+            int g = 0;
+            issue_t(0, 0);
+            for (int hh = 0; hh < hps; ++hh) {
+                const uint32_t coff = (uint32_t)(hh * d * 2);
+                for (int i = 0; i < subs_per_head; ++i, ++g) {
+                    const int ct = i / n_t, rt = i % n_t;
+                    const int ks_c = (min(128, S - ct * 128) + 15) / 16;      // K-steps over the keys of the tile
+                    const int ks_r = (min(128, S - rt * 128) + 15) / 16;      // K-steps over the queries of the tile
+                    mbar_wait(&sh->x_full, (uint32_t)g & 1u);
+                    tc_fence_after();
+                    const uint32_t tm_dq = tm_dq0 + (uint32_t)(rt * d);
+                    for (int ks = 0; ks < ks_c; ++ks) {       // dQ[rt] += dS K[ct]
+                        const uint64_t xd = smem_desc_advance(smem_desc_sw128(smem_u32(sX + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
+                        const uint64_t bd = at_desc_mn(smem_u32(sK + (size_t)(ct * 128 + ks * 16) * 128 + coff), 0);
+                        umma_bf16(tm_dq, xd, bd, idesc_k, (uint32_t)((ct != 0) | (ks != 0)));
+                    }
+                    for (int ks = 0; ks < ks_r; ++ks) {       // dK[ct] += dS^T Q[rt]
+                        const uint64_t ad = at_desc_mn(smem_u32(sX + (size_t)ks * 2048), 16384);
+                        const uint64_t bd = at_desc_mn(smem_u32(sQ + (size_t)(rt * 128 + ks * 16) * 128 + coff), 0);
+                        umma_bf16(tm_dk, ad, bd, idesc_mn, (uint32_t)((rt != 0) | (ks != 0)));
+                    }
+                    for (int ks = 0; ks < ks_r; ++ks) {       // dV[ct] += (P.drop)^T dO[rt]
+                        const uint64_t ad = at_desc_mn(smem_u32(sY + (size_t)ks * 2048), 16384);
+                        const uint64_t bd = at_desc_mn(smem_u32(sDO + (size_t)(rt * 128 + ks * 16) * 128 + coff), 0);
+                        umma_bf16(tm_dv, ad, bd, idesc_mn, (uint32_t)((rt != 0) | (ks != 0)));
+                    }
+                    umma_commit(&sh->acc_done);
+                    if (i + 1 < subs_per_head) issue_t(hh, i + 1);
+                    else if (hh + 1 < hps) issue_t(hh + 1, 0);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int wg = (warp - 4) / 4;
+        const int q4 = warp % 4;
+        const int r = q4 * 32 + lane;
+        const int et = threadIdx.x - 128;
+        const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
+        const float cs = a.scale * LOG2E;
+        if (warp == 4) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int key = w * 32 + lane;
+                bool ok = key < S;
+                if (ok && a.key_valid) ok = a.key_valid[(size_t)b * S + key] != 0;
+                const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) sh->kvb[w] = bits;
+            }
+        }
+        int g = 0;
+        for (int hh = 0; hh < hps; ++hh) {
+            const int head = slice * hps + hh;
+            const long long bh = (long long)b * a.heads + head;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int q = et; q < S; q += 256) {
+                const __nv_bfloat16* o = a.ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
+                const __nv_bfloat16* go = a.d_ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
+                float D = 0.f;
+                for (int c = 0; c < d; c += 8) {
+                    const uint4 ov = *reinterpret_cast<const uint4*>(o + c);
+                    const uint4 gv = *reinterpret_cast<const uint4*>(go + c);
+                    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
+                        const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
+                        D += __low2float(o2) * __low2float(g2) + __high2float(o2) * __high2float(g2);
+                    }
+                }
+                const float m = a.stats[bh * S + q];
+                const float l = a.stats[(long long)a.B * a.heads * S + bh * S + q];
+                sh->qc[q] = make_float4(m * LOG2E, 1.0f / l, D, exp2f((MASK_FILL - m) * LOG2E));
+                if (a.keep_bits) {
+                    const uint4* kb = reinterpret_cast<const uint4*>(a.keep_bits + ((size_t)bh * S + q) * 8);
+                    reinterpret_cast<uint4*>(sh->keep + q * 8)[0] = kb[0];
+                    reinterpret_cast<uint4*>(sh->keep + q * 8)[1] = kb[1];
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = 0; i < subs_per_head; ++i, ++g) {
+                const int ct = i / n_t, rt = i % n_t;
+                const int row = rt * 128 + r;                  // query of this thread
+                const bool row_ok = row < S;
+                const int ncols = min(128, S - ct * 128);
+                const int warp_row0 = rt * 128 + q4 * 32;
+                mbar_wait(&sh->t_full, (uint32_t)g & 1u);
+                tc_fence_after();
+                float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
+                if (row_ok) rc = sh->qc[row];
+                const bool warp_rows_plain = warp_row0 + 31 < S;
+                uint32_t keep_w0 = 0xffffffffu, keep_w1 = 0xffffffffu;
+                if (a.keep_bits && row_ok) {
+                    keep_w0 = sh->keep[row * 8 + ct * 4 + wg * 2];
+                    keep_w1 = sh->keep[row * 8 + ct * 4 + wg * 2 + 1];
+                }
+#pragma unroll 1
+                for (int c16 = wg * 4; c16 < wg * 4 + 4; ++c16) {
+                    const int col0 = ct * 128 + c16 * 16;                  // first key of the chunk
+                    if (c16 * 16 >= ((ncols + 31) / 32) * 32) break;
+                    float t1[16], t2[16];
+                    tmem_ld16(tm_t1 + lane_addr + (uint32_t)(c16 * 16), t1);
+                    tmem_ld16(tm_t2 + lane_addr + (uint32_t)(c16 * 16), t2);
+                    tmem_ld_wait();
+                    float pd[16], ds[16];
+                    const uint32_t kv16 = (sh->kvb[col0 >> 5] >> (col0 & 31)) & 0xffffu;
+                    const uint32_t kp16 = ((((c16 >> 1) & 1) ? keep_w1 : keep_w0) >> ((c16 & 1) * 16)) & 0xffffu;
+                    const bool plain = warp_rows_plain && kv16 == 0xffffu && (!a.causal || col0 + 15 <= warp_row0);
+                    if (plain) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float p = fast_exp2(fmaf(t1[c], cs, -rc.x)) * rc.y;
+                            const float keep = ((kp16 >> c) & 1u) ? a.inv_keep : 0.f;
+                            pd[c] = p * keep;
+                            ds[c] = p * (t2[c] * keep - rc.z) * a.scale;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int col = col0 + c;
+                            const bool ok = ((kv16 >> c) & 1u) && (!a.causal || col <= row);
+                            const float e = ok ? fast_exp2(fmaf(t1[c], cs, -rc.x)) : rc.w;
+                            const float p = (col < S && row_ok) ? e * rc.y : 0.f;
+                            const float keep = ((kp16 >> c) & 1u) ? a.inv_keep : 0.f;
+                            pd[c] = p * keep;
+                            ds[c] = ok ? p * (t2[c] * keep - rc.z) * a.scale : 0.f;
+                        }
+                    }
+                    uint8_t* xchunk = sX + (size_t)(c16 / 4) * 16384;
+                    uint8_t* ychunk = sY + (size_t)(c16 / 4) * 16384;
+#pragma unroll
+                    for (int u16 = 0; u16 < 2; ++u16) {
+                        uint4 w;
+                        w.x = at_pack(ds[u16 * 8 + 0], ds[u16 * 8 + 1]); w.y = at_pack(ds[u16 * 8 + 2], ds[u16 * 8 + 3]);
+                        w.z = at_pack(ds[u16 * 8 + 4], ds[u16 * 8 + 5]); w.w = at_pack(ds[u16 * 8 + 6], ds[u16 * 8 + 7]);
+                        *reinterpret_cast<uint4*>(xchunk + sw128_offset(r, (c16 & 3) * 2 + u16)) = w;
+                        w.x = at_pack(pd[u16 * 8 + 0], pd[u16 * 8 + 1]); w.y = at_pack(pd[u16 * 8 + 2], pd[u16 * 8 + 3]);
+                        w.z = at_pack(pd[u16 * 8 + 4], pd[u16 * 8 + 5]); w.w = at_pack(pd[u16 * 8 + 6], pd[u16 * 8 + 7]);
+                        *reinterpret_cast<uint4*>(ychunk + sw128_offset(r, (c16 & 3) * 2 + u16)) = w;
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(&sh->x_full);
+                const bool store_kv = rt == n_t - 1, store_q = ct == n_t - 1;
+                if (store_kv || store_q) {
+                    mbar_wait(&sh->acc_done, (uint32_t)g & 1u);
+                    tc_fence_after();
+                    const int dcols = d >= 32 ? d / 2 : d;
+                    if (d >= 32 || wg == 0) {
+                        const int cbeg = d >= 32 ? wg * dcols : 0;
+                        // which: 0 = dQ (row = query rt*128 + r), 1 = dK, 2 = dV (row = key ct*128 + r)
+                        for (int which = store_q ? 0 : 1; which < (store_kv ? 3 : 1); ++which) {
+                            const uint32_t tm = which == 0 ? tm_dq0 + (uint32_t)(rt * d) : (which == 1 ? tm_dk : tm_dv);
+                            const int out_row = which == 0 ? row : ct * 128 + r;
+                            const int colbase = which * a.H + slice * 64 + hh * d;
+                            for (int c0 = cbeg; c0 < cbeg + dcols; c0 += 16) {
+                                float o[16];
+                                tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
+                                tmem_ld_wait();
+                                if (out_row < S) {
+                                    __nv_bfloat16* dst = a.d_qkv + ((size_t)b * S + out_row) * 3 * a.H + colbase + c0;
+                                    uint4 w0, w1;
+                                    w0.x = at_pack(o[0], o[1]); w0.y = at_pack(o[2], o[3]); w0.z = at_pack(o[4], o[5]); w0.w = at_pack(o[6], o[7]);
+                                    w1.x = at_pack(o[8], o[9]); w1.y = at_pack(o[10], o[11]); w1.z = at_pack(o[12], o[13]); w1.w = at_pack(o[14], o[15]);
+                                    reinterpret_cast<uint4*>(dst)[0] = w0;
+                                    reinterpret_cast<uint4*>(dst)[1] = w1;
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int g_attn_bwd_variant = 1;      // 1: single sweep (default), 0: the two-sweep kernel (kept for A/B measurements)
+extern "C" int asme_b200_tc_attn_tune(int knob, int value) {
+    ASME_REQUIRE(knob == 0 && (value == 0 || value == 1), "tc_attn_tune: knob 0 (backward variant) takes 0 or 1");
+    g_attn_bwd_variant = value;
+    return ASME_OK;
+}
+
 extern "C" int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                                      float p_drop, const void* ctx, const void* d_ctx, const float* stats,
                                      const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream) {
@@ -663,8 +929,13 @@ extern "C" int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, 
     a.ctx = (const __nv_bfloat16*)ctx; a.d_ctx = (const __nv_bfloat16*)d_ctx; a.stats = stats;
     a.keep_bits = p_drop > 0.f ? keep_bits : nullptr; a.d_qkv = (__nv_bfloat16*)d_qkv;
     const size_t smem = 1024 + 6 * 32768 + sizeof(AttnBwdShared);
-    { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd_kernel); if (_rc) return _rc; }
-    attn_tc_bwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+    if (g_attn_bwd_variant == 1) {
+        { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd1_kernel); if (_rc) return _rc; }
+        attn_tc_bwd1_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+    } else {
+        { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd_kernel); if (_rc) return _rc; }
+        attn_tc_bwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+    }
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

@@ -102,10 +102,18 @@ def test_tc_attn_fwd_no_mask_and_fully_masked_rows(ops):
     torch.testing.assert_close(got.float().view(B, S, H)[b, 0], uniform, rtol=2e-2, atol=2e-2)
 
 
+@pytest.fixture(params=[1, 0], ids=["single_sweep", "two_sweeps"])
+def bwd_variant(request, ops):
+    """both tensor-core backward kernels: the single-sweep one (default) and the older two-sweep one"""
+    ops._lib.call("asme_b200_tc_attn_tune", 0, request.param)
+    yield request.param
+    ops._lib.call("asme_b200_tc_attn_tune", 0, 1)
+
+
 @pytest.mark.parametrize("B,S,heads,d", CASES)
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("p_drop", [0.0, 0.2])
-def test_tc_attn_bwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
+def test_tc_attn_bwd_matches_simt(ops, bwd_variant, B, S, heads, d, causal, p_drop):
     """d_qkv of the tensor-core backward vs the fp32 SIMT backward fed with the same (bf16-valued) tensors and the same
     dropout mask; bf16 rounding of P / dS / outputs -> 1e-2 in norm"""
     gen = torch.Generator(device="cuda").manual_seed(B * 77 + S + heads + d)
@@ -133,7 +141,7 @@ def test_tc_attn_bwd_matches_simt(ops, B, S, heads, d, causal, p_drop):
     assert torch.isfinite(got.float()).all()
 
 
-def test_tc_attn_bwd_fully_masked_rows(ops):
+def test_tc_attn_bwd_fully_masked_rows(ops, bwd_variant):
     gen = torch.Generator(device="cuda").manual_seed(9)
     B, S, heads, d = 3, 70, 2, 32
     qkv, valid = make(gen, B, S, heads, d, pad="left")
