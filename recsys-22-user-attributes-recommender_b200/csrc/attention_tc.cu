@@ -207,10 +207,14 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             float m = -INFINITY;
 #pragma unroll 1
             for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                const uint32_t bits = sh->kvb[ch];
+                if (bits == 0u) {            // a chunk of padding keys only (warp-uniform): every score is the mask fill value
+                    if (ch * 32 < S) m = fmaxf(m, MASK_FILL);
+                    continue;
+                }
                 float v[32];
                 tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
                 tmem_ld_wait();
-                const uint32_t bits = sh->kvb[ch];
                 const bool plain = bits == 0xffffffffu && (!a.causal || ch * 32 + 31 <= q_warp_min);   // warp-uniform
                 if (plain) {
                     float mm = v[0];
@@ -239,10 +243,20 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             if (a.p_drop > 0.f) rowkey = drop_rowkey(asme_seed(a.seed), a.site, (uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0));
 #pragma unroll 1
             for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                const uint32_t bits = sh->kvb[ch];
+                uint8_t* chunk_p = sP + (size_t)(ch / 2) * 16384;
+                // a chunk of padding keys only, and no row of this warp is fully masked (e_masked == 0 everywhere): the
+                // probabilities are exactly zero -- no exponentials, no dropout stream (the keep bits stay zero: they only ever
+                // multiply these zeros), just the zero tile the second MMA reads
+                if (bits == 0u && __all_sync(0xffffffffu, e_masked == 0.f)) {
+#pragma unroll
+                    for (int u16 = 0; u16 < 4; ++u16)
+                        *reinterpret_cast<uint4*>(chunk_p + sw128_offset(r, (ch & 1) * 4 + u16)) = make_uint4(0u, 0u, 0u, 0u);
+                    continue;
+                }
                 float v[32];
                 tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
                 tmem_ld_wait();
-                const uint32_t bits = sh->kvb[ch];
                 const bool plain = bits == 0xffffffffu && (!a.causal || ch * 32 + 31 <= q_warp_min);
                 if (plain) {
 #pragma unroll
@@ -816,12 +830,22 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
                 for (int c16 = wg * 4; c16 < wg * 4 + 4; ++c16) {
                     const int col0 = ct * 128 + c16 * 16;                  // first key of the chunk
                     if (c16 * 16 >= ((ncols + 31) / 32) * 32) break;
+                    const uint32_t kv16 = (sh->kvb[col0 >> 5] >> (col0 & 31)) & 0xffffu;
+                    // padding keys only and no fully masked row in this warp: P = dS = 0 exactly (warp-uniform test)
+                    if (kv16 == 0u && __all_sync(0xffffffffu, rc.w == 0.f)) {
+#pragma unroll
+                        for (int u16 = 0; u16 < 2; ++u16) {
+                            const uint32_t off = sw128_offset(r, (c16 & 3) * 2 + u16);
+                            *reinterpret_cast<uint4*>(sX + (size_t)(c16 / 4) * 16384 + off) = make_uint4(0u, 0u, 0u, 0u);
+                            *reinterpret_cast<uint4*>(sY + (size_t)(c16 / 4) * 16384 + off) = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        continue;
+                    }
                     float t1[16], t2[16];
                     tmem_ld16(tm_t1 + lane_addr + (uint32_t)(c16 * 16), t1);
                     tmem_ld16(tm_t2 + lane_addr + (uint32_t)(c16 * 16), t2);
                     tmem_ld_wait();
                     float pd[16], ds[16];
-                    const uint32_t kv16 = (sh->kvb[col0 >> 5] >> (col0 & 31)) & 0xffffu;
                     const uint32_t kp16 = ((((c16 >> 1) & 1) ? keep_w1 : keep_w0) >> ((c16 & 1) * 16)) & 0xffffu;
                     const bool plain = warp_rows_plain && kv16 == 0xffffu && (!a.causal || col0 + 15 <= warp_row0);
                     if (plain) {
