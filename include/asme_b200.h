@@ -297,6 +297,8 @@ int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_i
                       const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
                       unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
                       asme_stream_t stream);
+/* diagnostic: knob 0 selects the tall kernel (1 = persistent CTAs with a resident weight tile, default; 0 = one CTA per tile) */
+int asme_b200_tc_gemm_tune(int knob, int value);
 /* dW (N,K) fp32 (+)= dY(M,N)^T X(M,K), dbias (N) (+)= colsum(dY); dY, X bf16; token contraction split over the SMs with a
  * deterministic second-stage reduction */
 size_t asme_b200_tc_wgrad_workspace_bytes(int M, int N, int K);

@@ -81,6 +81,38 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// Tensor-core (bf16 policy) epilogues: the GELU evaluations are what the FFN GEMM epilogues spend their issue slots on (erff is
+// ~25 instructions, erff + expf ~45).  Abramowitz & Stegun 7.1.26, |erf error| <= 1.5e-7 in exact arithmetic (~3e-7 here), which
+// is far below the bf16 rounding of the values these epilogues store; one MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe instructions,
+// and the gradient shares the exponential.  The fp32 strict-parity path keeps erff / expf.
+__device__ __forceinline__ float exp2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// returns erf(|x|) given e = exp(-x*x)
+__device__ __forceinline__ float erf_abs_fast(float ax, float e) {
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    return fmaf(-p * t, e, 1.0f);
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float ax = fabsf(x) * 0.70710678118654752440f;
+    const float e = exp2_approx(-ax * ax * 1.4426950408889634f);
+    const float y = erf_abs_fast(ax, e);                       // erf(|x| / sqrt 2)
+    return 0.5f * x * (1.0f + copysignf(y, x));
+}
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+    const float ax = fabsf(x) * 0.70710678118654752440f;
+    const float e = exp2_approx(-ax * ax * 1.4426950408889634f);   // exp(-x^2 / 2)
+    const float y = erf_abs_fast(ax, e);
+    const float cdf = 0.5f * (1.0f + copysignf(y, x));
+    return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 // Philox4x32-7 counter-based generator: dropout masks are a pure function of
 // (seed, site, element index) so the backward pass recomputes them instead of storing them.
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,

@@ -75,6 +75,83 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// epilogue of one 32-column chunk of one output row (shared by both tall kernels): bias, pre-activation copy, GELU, gelu'
+// multiply, dropout, residual, block-end dropout, fp32 / bf16 stores
+__device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (&v)[32], const int row, const int nc, const float inv_keep) {
+    const size_t o = (size_t)row * a.N + nc;
+    if (a.bias) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nc + c));
+            v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+        }
+    }
+    if (a.pre_act_bf16) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+            uint4 w;
+            w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
+            w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
+            *reinterpret_cast<uint4*>(a.pre_act_bf16 + o + c) = w;
+        }
+    }
+    if (a.act == ASME_ACT_GELU) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = gelu_erf_fast(v[c]);
+    }
+    if (a.gelu_grad_of) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.gelu_grad_of + o + c));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
+                v[c + 2 * e] *= gelu_erf_grad_fast(__low2float(z2));
+                v[c + 2 * e + 1] *= gelu_erf_grad_fast(__high2float(z2));
+            }
+        }
+    }
+    if (a.p_drop > 0.f && a.site) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            float s[4];
+            dropout_scale4(asme_seed(a.seed), a.site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
+            v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
+        }
+    }
+    if (a.residual) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o + c));
+            v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
+        }
+    }
+    if (a.p_drop > 0.f && a.post_site) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            float s[4];
+            dropout_scale4(asme_seed(a.seed), a.post_site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
+            v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
+        }
+    }
+    if (a.out_f32) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(a.out_f32 + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+    if (a.out_bf16) {
+        __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + nc;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+            uint4 w;
+            w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
+            w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
+            *reinterpret_cast<uint4*>(dst + c) = w;
+        }
+    }
+}
+
 // CTA (m_tile, n_tile): 128 rows x NT (<= G_NT) columns; K streamed in 64-wide chunks through a ring of `stages` slots
 // (slot = A chunk 16 KB + B chunk NT x 128 B [K-major] or ceil(NT/64) x 8 KB [MN-major]).
 template <bool B_MN>
@@ -168,79 +245,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
             tmem_ld32(lane_addr + (uint32_t)nn, v);
             tmem_ld_wait();
             if (!row_ok) continue;
-            const int nc = n0 + nn;                         // first global column of this chunk
-            const size_t o = (size_t)row * a.N + nc;
-            if (a.bias) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nc + c));
-                    v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
-                }
-            }
-            if (a.pre_act_bf16) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 w;
-                    w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
-                    w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
-                    *reinterpret_cast<uint4*>(a.pre_act_bf16 + o + c) = w;
-                }
-            }
-            if (a.act == ASME_ACT_GELU) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = gelu_erf(v[c]);
-            }
-            if (a.gelu_grad_of) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.gelu_grad_of + o + c));
-                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
-                        v[c + 2 * e] *= gelu_erf_grad(__low2float(z2));
-                        v[c + 2 * e + 1] *= gelu_erf_grad(__high2float(z2));
-                    }
-                }
-            }
-            if (a.p_drop > 0.f && a.site) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    float s[4];
-                    dropout_scale4(asme_seed(a.seed), a.site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
-                    v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
-                }
-            }
-            if (a.residual) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o + c));
-                    v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
-                }
-            }
-            if (a.p_drop > 0.f && a.post_site) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    float s[4];
-                    dropout_scale4(asme_seed(a.seed), a.post_site, (uint64_t)(o + c) >> 2, a.p_drop, inv_keep, s);
-                    v[c] *= s[0]; v[c + 1] *= s[1]; v[c + 2] *= s[2]; v[c + 3] *= s[3];
-                }
-            }
-            if (a.out_f32) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4)
-                    *reinterpret_cast<float4*>(a.out_f32 + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-            }
-            if (a.out_bf16) {
-                __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + nc;
-#pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 w;
-                    w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
-                    w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
-                    *reinterpret_cast<uint4*>(dst + c) = w;
-                }
-            }
+            tall_epilogue_chunk(a, v, row, n0 + nn, inv_keep);
         }
     }
     tc_fence_before();
@@ -249,6 +254,162 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent tall kernel (default).  The kernel above pays one TMA round trip, one TMEM allocation and one pipeline fill per
+// 128-row tile and is latency-bound (15 % issue utilisation, 1.35 waves of short-lived CTAs).  Here a CTA owns one column tile
+// for the whole launch: the weight tile is loaded ONCE and stays in shared memory, activation tiles stream through a ring of
+// K-chunk slots filled ahead across tile boundaries, and two accumulator stages in tensor memory let the MMAs of tile i+1
+// overlap the epilogue of tile i.
+// ------------------------------------------------------------------------------------------------------------
+#define GP_MAX_STAGES 6
+struct __align__(8) GemmPBars {
+    uint64_t b_full;
+    uint64_t full[GP_MAX_STAGES];
+    uint64_t empty[GP_MAX_STAGES];
+    uint64_t tfull[2];
+    uint64_t tempty[2];
+    uint32_t tmem_base;
+};
+
+template <bool B_MN>
+__global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
+                                                                     int stages) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int kch = a.K / CHUNK_K;
+    const int n0 = blockIdx.y * G_NT;
+    const int NT = min(G_NT, a.N - n0);
+    const int nblk = (NT + 63) / 64;
+    const size_t a_bytes = (size_t)G_BM * 128;
+    const size_t b_bytes = B_MN ? (size_t)nblk * 64 * 128 : (size_t)min(G_NT, a.N) * 128;   // bytes the TMA boxes of one K chunk deliver
+    const size_t b_slot = (size_t)G_NT * 128;
+    uint8_t* sB = smem;                                   // [kch][b_slot]: the weight tile, resident for the whole launch
+    uint8_t* sA = sB + (size_t)kch * b_slot;              // [stages][a_bytes]
+    GemmPBars* bars = reinterpret_cast<GemmPBars*>(sA + (size_t)stages * a_bytes);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m_tiles = (a.M + G_BM - 1) / G_BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        mbar_init(&bars->b_full, 1);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->tfull[s], 1);
+            mbar_init(&bars->tempty[s], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, 2 * G_NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars->b_full, (uint32_t)(kch * b_bytes));
+            for (int c = 0; c < kch; ++c) {
+                uint8_t* dst = sB + (size_t)c * b_slot;
+                if (B_MN) {
+                    for (int j = 0; j < nblk; ++j) tma_load_2d(dst + (size_t)j * 64 * 128, &tmB, &bars->b_full, n0 + j * 64, c * CHUNK_K);
+                } else {
+                    tma_load_2d(dst, &tmB, &bars->b_full, c * CHUNK_K, n0);
+                }
+            }
+            int s = 0;
+            uint32_t ph = 0;
+            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+                for (int c = 0; c < kch; ++c) {
+                    mbar_wait(&bars->empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&bars->full[s], (uint32_t)a_bytes);
+                    tma_load_2d(sA + (size_t)s * a_bytes, &tmA, &bars->full[s], c * CHUNK_K, mt * G_BM);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_major(G_BM, NT, 0, B_MN ? 1 : 0);
+            mbar_wait(&bars->b_full, 0);
+            tc_fence_after();
+            int s = 0, i = 0;
+            uint32_t ph = 0;
+            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++i) {
+                const int as = i & 1;
+                mbar_wait(&bars->tempty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * G_NT);
+                for (int c = 0; c < kch; ++c) {
+                    mbar_wait(&bars->full[s], ph);
+                    tc_fence_after();
+                    const uint8_t* pa = sA + (size_t)s * a_bytes;
+                    const uint8_t* pb = sB + (size_t)c * b_slot;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t ad = smem_desc_advance(smem_desc_sw128(smem_u32(pa)), k4 * 32);
+                        uint64_t bd;
+                        if (B_MN) bd = smem_desc_mn_sw128(smem_u32(pb + (size_t)k4 * 2048), 64 * 128);
+                        else bd = smem_desc_advance(smem_desc_sw128(smem_u32(pb)), k4 * 32);
+                        umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((c | k4) != 0));
+                    }
+                    umma_commit(&bars->empty[s]);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&bars->tfull[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int wg = (warp - 4) / 4;                       // both warpgroups own all 128 rows, each half of the 32-column chunks
+        const int q = warp % 4;
+        const float inv_keep = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
+        const int n_chunks = NT / 32;
+        const int c_lo = wg == 0 ? 0 : (n_chunks + 1) / 2, c_hi = wg == 0 ? (n_chunks + 1) / 2 : n_chunks;
+        int i = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++i) {
+            const int as = i & 1;
+            const int row = mt * G_BM + q * 32 + lane;
+            const bool row_ok = row < a.M;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G_NT);
+            mbar_wait(&bars->tfull[as], (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            if (c_lo == c_hi) {                              // a warpgroup without columns (NT = 32) still hands the stage back
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                continue;
+            }
+            for (int nn = c_lo * 32; nn < c_hi * 32; nn += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + (uint32_t)nn, v);
+                tmem_ld_wait();
+                if (nn + 32 >= c_hi * 32) {                  // last TMEM read of this stage by this warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                }
+                if (row_ok) tall_epilogue_chunk(a, v, row, n0 + nn, inv_keep);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * G_NT);
+    }
+}
+
+static int g_gemm_variant = 1;      // 1: persistent kernel (default), 0: one CTA per tile (kept for A/B measurements)
+extern "C" int asme_b200_tc_gemm_tune(int knob, int value) {
+    ASME_REQUIRE(knob == 0 && (value == 0 || value == 1), "tc_gemm_tune: knob 0 (tall-kernel variant) takes 0 or 1");
+    g_gemm_variant = value;
+    return ASME_OK;
 }
 
 extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
@@ -272,9 +433,36 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     a.p_drop = p_drop; a.seed = seed; a.site = site; a.post_site = post_site; a.residual = residual; a.out_f32 = out_f32;
     a.out_bf16 = (__nv_bfloat16*)out_bf16; a.pre_act_bf16 = (__nv_bfloat16*)pre_act_bf16; a.ld_bf16 = ld_bf16;
     const int kch = K / 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    // weight tile resident (kch x 16 KB) + ring of activation K-chunks; two CTAs per SM whenever they fit (<= ~110 KB each)
+    const size_t fixed = 1024 + (size_t)kch * G_NT * 128 + sizeof(GemmPBars);
+    int pstages = fixed + 2 * (size_t)G_BM * 128 <= 110 * 1024 ? (int)((110 * 1024 - fixed) / ((size_t)G_BM * 128)) : 0;
+    int per_sm = 2;
+    if (pstages < 2) {
+        pstages = fixed + 2 * (size_t)G_BM * 128 <= 220 * 1024 ? (int)((220 * 1024 - fixed) / ((size_t)G_BM * 128)) : 0;
+        per_sm = 1;
+    }
+    if (pstages > GP_MAX_STAGES) pstages = GP_MAX_STAGES;
+    if (g_gemm_variant == 1 && pstages >= 2) {      // (a weight tile too large for shared memory falls back to the per-tile kernel)
+        const int stages = pstages;
+        const size_t smem_p = fixed + (size_t)stages * G_BM * 128;
+        const int n_tiles = ceil_div(N, G_NT), m_tiles = ceil_div(M, G_BM);
+        int gx = (ASME_NUM_SMS * per_sm) / n_tiles;
+        if (gx < 1) gx = 1;
+        if (gx > m_tiles) gx = m_tiles;
+        const dim3 pgrid(gx, n_tiles);
+        if (b_is_kn) {
+            { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_persist_kernel<true>); if (_rc) return _rc; }
+            tc_gemm_persist_kernel<true><<<pgrid, G_TALL_THREADS, smem_p, st>>>(tmA, tmB, a, stages);
+        } else {
+            { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_persist_kernel<false>); if (_rc) return _rc; }
+            tc_gemm_persist_kernel<false><<<pgrid, G_TALL_THREADS, smem_p, st>>>(tmA, tmB, a, stages);
+        }
+        ASME_LAUNCH_OK();
+        return ASME_OK;
+    }
     const int stages = kch < G_STAGES ? kch : G_STAGES;
     const size_t smem = 1024 + (size_t)stages * ((size_t)G_BM * 128 + G_NT * 128) + sizeof(GemmBars);
-    cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid(ceil_div(M, G_BM), ceil_div(N, G_NT));
     if (b_is_kn) {
         { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_tall_kernel<true>); if (_rc) return _rc; }

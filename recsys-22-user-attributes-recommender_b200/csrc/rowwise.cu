@@ -716,6 +716,10 @@ __global__ void fill_kernel(float* x, long long n, float v) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;
 }
+__global__ void fill4_kernel(float4* x, long long n4, float v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) x[i] = make_float4(v, v, v, v);
+}
 // ---- device-resident step state (CUDA-graph replays): {seed, adam step, learning rate} ----------------------------------------
 struct asme_step_state_t { unsigned long long seed; double lr; long long adam_step; };
 __global__ void step_state_advance_kernel(asme_step_state_t* s) { s->seed += 1ull; s->adam_step += 1; }
@@ -731,12 +735,18 @@ __device__ __forceinline__ void adam_update(float* __restrict__ p, const float* 
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                 long long n, const asme_step_state_t* __restrict__ st, float b1, float b2, float omb1, float omb2,
                                 float eps, float wd, double b1d, double b2d) {
+    // the two bias-correction scalars are double-precision pow / sqrt: one thread per block computes them (they used to be
+    // evaluated by every thread, which made this the slowest "memory-bound" kernel of the step)
+    __shared__ float sc[2];
+    if (threadIdx.x == 0) {
+        const double step = (double)st->adam_step;
+        sc[0] = (float)(1.0 / sqrt(1.0 - pow(b2d, step)));       // same double-precision scalars the host computes
+        sc[1] = (float)(st->lr / (1.0 - pow(b1d, step)));        // for asme_b200_adam_step
+    }
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double step = (double)st->adam_step;
-    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(b2d, step)));       // same double-precision scalars the host computes
-    const float lr_over_bc1 = (float)(st->lr / (1.0 - pow(b1d, step)));         // for asme_b200_adam_step
-    adam_update(p, g, m, v, i, lr_over_bc1, b1, b2, omb1, omb2, eps, wd, inv_sqrt_bc2);
+    adam_update(p, g, m, v, i, sc[1], b1, b2, omb1, omb2, eps, wd, sc[0]);
 }
 extern "C" int asme_b200_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, const void* state,
                                        double beta1, double beta2, double eps, double weight_decay, asme_stream_t stream) {
@@ -751,6 +761,11 @@ extern "C" int asme_b200_adam_step_dev(float* param, const float* grad, float* m
 
 extern "C" int asme_b200_fill(float* x, long long n, float value, asme_stream_t stream) {
     if (n == 0) return ASME_OK;
+    if (((uintptr_t)x & 15) == 0 && n % 4 == 0) {
+        fill4_kernel<<<ceil_div(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x), n / 4, value);
+        ASME_LAUNCH_OK();
+        return ASME_OK;
+    }
     fill_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, value);
     ASME_LAUNCH_OK();
     return ASME_OK;
