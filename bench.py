@@ -323,6 +323,9 @@ def main():
     ap.add_argument("--no-eval", action="store_true", help="skip the secondary C5 full-catalog evaluation measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
     ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying its CUDA graph")
+    ap.add_argument("--profile-region", action="store_true",
+                    help="profiling aid (ncu --profile-from-start off): after warm-up bracket ONE launch-by-launch training step and ONE "
+                         "evaluation step in cudaProfilerStart/Stop, print no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -384,6 +387,18 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.profile_region:
+        for i in range(3):
+            train_step(dev_batches[i % NB], i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        train_step(dev_batches[3 % NB], 3)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        bench_eval_c5(device, pk, steps=1, warmup=2, world=world, rank=rank, profile=True)
+        print(json.dumps({"profile_region": "1 training step (C2) + 1 evaluation step (C5), launch by launch"}))
+        return
 
     # The step is ~90 launches; issued from Python the host is the bottleneck, so the product path replays the step's CUDA graph
     # (asme_b200.graphs.GraphedTrainStep: one graph per batch signature, seed / Adam step / lr in device memory).
@@ -543,7 +558,7 @@ def main():
     finish()
 
 
-def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0):
+def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False):
     """secondary measurement: full-catalog scoring + top-k + Recall/NDCG@10 on a 1M-item catalog (C5).  With N ranks the
     catalog is vocab-sharded (asme_b200.sharded): every rank encodes its own 1024 users and scores all N*1024 users against
     its V/N slice; per-shard top-k lists and target scores are merged over NCCL (weak scaling: users per GPU fixed)."""
@@ -577,6 +592,12 @@ def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if profile:
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):

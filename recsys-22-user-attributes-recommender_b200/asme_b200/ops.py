@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import EmbedDesc, GemmEpilogue
 
-# dropout "sites": every dropout application in the model has its own Philox stream
+# dropout "sites": every dropout application in the model has its own counter-based stream (common.cuh: dropout_bits4)
 SITE_EMBED_A, SITE_EMBED_B = 1, 2
 SITE_LAYER_BASE = 16          # + 8 * layer + {0: attn probs, 1: attn out, 2: ffn inner, 3: ffn out, 4: block end}
 

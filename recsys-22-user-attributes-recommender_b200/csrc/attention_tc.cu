@@ -14,7 +14,7 @@
 // Per (head, 128-query tile):  S = Q K^T (K-major operands, the head's 32-byte K-steps inside the 128-byte rows)
 //   -> softmax in registers (two passes over TMEM: max, then exp / sum / dropout), P -> shared memory (bf16, K-major)
 //   -> O = P V (V consumed as an MN-major operand: no transposed copy) -> O / rowsum -> ctx (bf16).
-// Row max / row sum-exp and the Philox dropout stream use the conventions of the fp32 SIMT kernels (attention_simt.cu),
+// Row max / row sum-exp use the conventions of the fp32 SIMT kernels (attention_simt.cu),
 // so forward and backward kernels of either flavour can be mixed and compared.
 #include "common.cuh"
 #include "tc_common.cuh"

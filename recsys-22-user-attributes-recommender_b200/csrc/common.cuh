@@ -113,24 +113,23 @@ __device__ __forceinline__ float gelu_erf_grad_fast(float x) {
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
-// Philox4x32-7 counter-based generator: dropout masks are a pure function of
-// (seed, site, element index) so the backward pass recomputes them instead of storing them.
-__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                            uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += W0;
-        k1 += W1;
-    }
-    return make_uint4(c0, c1, c2, c3);
+// Counter-based dropout generator: the mask is a pure function of (seed, site, element index), so the backward pass recomputes
+// it instead of storing it, and every kernel that touches a site (fused GEMM epilogues, the row-wise kernels, fp32 and
+// tensor-core flavours alike) sees the same stream.  Four elements share two 32-bit hashes (lowbias32 finaliser, one 16-bit
+// keep decision per element): ~28 instructions per four elements.  (The first version ran Philox4x32-7, ~83 instructions per
+// four elements, which made the dropout the largest single item of the FFN GEMM epilogues.)
+__device__ __forceinline__ uint32_t asme_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+    return x;
 }
+// two words = four 16-bit uniform lanes for elements 4*idx4 .. 4*idx4+3 of `site`
+__device__ __forceinline__ uint2 dropout_bits4(uint64_t seed, uint32_t site, uint64_t idx4) {
+    const uint32_t key = asme_mix32((uint32_t)seed ^ (site * 0x9E3779B9u)) ^ (uint32_t)(seed >> 32);
+    const uint32_t a = asme_mix32(((uint32_t)idx4 ^ key) + (uint32_t)(idx4 >> 32) * 0x85EBCA6Bu);
+    const uint32_t b = asme_mix32(a + 0x9E3779B9u);
+    return make_uint2(a, b);
+}
+__device__ __forceinline__ uint32_t dropout_thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
 // A dropout seed argument with bit 63 set is a DEVICE POINTER (low 48 bits) to the seed: a training step captured in a CUDA
 // graph re-reads the seed that a tiny "advance" kernel bumps at the start of every replay (asme_b200_step_state_advance),
 // so the by-value launch arguments baked into the graph never change.  Real seeds always have bit 63 clear.
@@ -141,12 +140,20 @@ __device__ __forceinline__ uint64_t asme_seed(uint64_t s) {
 
 // keep-probability scale for element `idx` of dropout site `site`: 0 if dropped, 1/(1-p) if kept
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
-    const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0u, (uint32_t)seed,
-                               (uint32_t)(seed >> 32));
+    const uint2 r = dropout_bits4(seed, site, idx >> 2);
     const uint32_t lane = (uint32_t)idx & 3u;
-    const uint32_t bits = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
-    const float u = (float)(bits >> 8) * (1.0f / 16777216.0f);   // [0,1)
-    return u < p ? 0.0f : inv_keep;
+    const uint32_t w = (lane & 2u) ? r.y : r.x;
+    const uint32_t u = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
+    return u < dropout_thr16(p) ? 0.0f : inv_keep;
+}
+// the same for four consecutive elements starting at element 4*idx4
+__device__ __forceinline__ void dropout_scales4(uint64_t seed, uint32_t site, uint64_t idx4, float p, float inv_keep, float (&s)[4]) {
+    const uint2 r = dropout_bits4(seed, site, idx4);
+    const uint32_t thr = dropout_thr16(p);
+    s[0] = (r.x & 0xffffu) < thr ? 0.f : inv_keep;
+    s[1] = (r.x >> 16) < thr ? 0.f : inv_keep;
+    s[2] = (r.y & 0xffffu) < thr ? 0.f : inv_keep;
+    s[3] = (r.y >> 16) < thr ? 0.f : inv_keep;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -5,7 +5,7 @@
 // Two kernel shapes, both fed by 128-byte-swizzled TMA boxes of 64 bf16 columns:
 //   "tall"   C[M,N] = A[M,K] x op(B)   M = tokens (large), N, K <= 256.      forward (B = W, K-major) and dX (B = W, MN-major).
 //            One CTA per 128 rows: whole A tile + whole weight in shared memory, one accumulator (N TMEM columns), fused
-//            epilogue (bias, GELU, gelu' multiply, Philox dropout, residual) writing fp32 and / or bf16 rows.
+//            epilogue (bias, GELU, gelu' multiply, counter-based dropout, residual) writing fp32 and / or bf16 rows.
 //            Several CTAs are resident per SM, so loads, MMAs and epilogues of different tiles overlap.
 //   "wgrad"  dW[N,K] = dY[M,N]^T x X[M,K]   contraction over the tokens.  Both operands are MN-major views of row-major
 //            activations; split over token ranges, 4-stage TMA ring, fp32 partials reduced deterministically.
@@ -63,11 +63,7 @@ struct __align__(8) GemmBars {
 
 // four dropout scales for elements idx4*4 .. idx4*4+3 of a site (same stream as dropout_scale in common.cuh)
 __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx4, float p, float inv_keep, float (&s)[4]) {
-    const uint4 r = philox4x32((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-    s[0] = ((float)(r.x >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    s[1] = ((float)(r.y >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    s[2] = ((float)(r.z >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    s[3] = ((float)(r.w >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+    dropout_scales4(seed, site, idx4, p, inv_keep, s);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

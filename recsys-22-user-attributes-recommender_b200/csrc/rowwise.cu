@@ -43,16 +43,11 @@ int asme_ensure_max_smem(const void* kernel) {
 
 #define LN_EPS 1e-5f
 
-// dropout scales for 4 consecutive elements starting at idx (idx % 4 == 0): one Philox call
+// dropout scales for 4 consecutive elements starting at idx (idx % 4 == 0): one generator call
 __device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
-    const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), site, 0u, (uint32_t)seed,
-                               (uint32_t)(seed >> 32));
-    float4 s;
-    s.x = ((float)(r.x >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    s.y = ((float)(r.y >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    s.z = ((float)(r.z >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    s.w = ((float)(r.w >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
-    return s;
+    float s[4];
+    dropout_scales4(seed, site, idx >> 2, p, inv_keep, s);
+    return make_float4(s[0], s[1], s[2], s[3]);
 }
 
 template <int LANES, int CH>

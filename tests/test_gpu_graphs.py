@@ -1,5 +1,5 @@
 """A training step replayed from its CUDA graph (asme_b200.graphs.GraphedTrainStep: seed / Adam step / lr in device memory)
-must be the launch-by-launch step: same kernels, same order, same Philox / hash dropout streams -> identical losses and
+must be the launch-by-launch step: same kernels, same order, same dropout streams -> identical losses and
 weights, bit for bit."""
 import pytest
 import torch

@@ -1,6 +1,6 @@
 """Parity of the tensor-core attention kernels against the fp32 SIMT kernels (themselves pinned to the oracle's
 restatement of Attention.forward, transformer_layers.py:145-155, in test_gpu_kernels.py) on the same bf16-rounded q/k/v,
-with identical Philox dropout masks.  Tolerance: the probabilities are rounded to bf16 before the second MMA and the
+with identical dropout masks.  Tolerance: the probabilities are rounded to bf16 before the second MMA and the
 context is stored as bf16, i.e. 2^-8 relative per element -> 1e-2 of the output scale element-wise, 3e-3 in norm."""
 import pytest
 import torch

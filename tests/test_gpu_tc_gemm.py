@@ -82,7 +82,7 @@ def test_tc_gemm_epilogue_matches_oracle(ops):
     torch.testing.assert_close(got.double(), (dy.double() @ w2.double()) * grad, rtol=1e-5, atol=1e-5)
 
 
-def test_tc_gemm_dropout_uses_the_shared_philox_stream(ops):
+def test_tc_gemm_dropout_uses_the_shared_stream(ops):
     """the fused epilogue dropout must produce exactly the mask of the stand-alone dropout kernel (same seed / site /
     element index), because the backward pass re-creates masks instead of storing them"""
     gen = torch.Generator(device="cuda").manual_seed(2)

@@ -1,6 +1,11 @@
 #!/bin/bash
-# One gpurun call: plain bench run, then the ncu launch list of the same command, then a full capture of the tensor-core kernels.
-python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/plain_bench.log 2>&1 || exit 1
-timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 1100 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc|tc_gemm_tall|tc_wgrad|score_tc|ce_bwd_tc" -s 420 -c 36 -o gpurun_out/prof_step_r1b python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+# One gpurun call: plain run, then the ncu launch list of ONE training step + ONE evaluation step (bench.py --profile-region
+# brackets them in cudaProfilerStart/Stop), then a full capture of the hot kernels of the same region.
+# Keep the captures small: gpurun brings back at most 64 MiB, and every profiled launch costs GPU-seconds.
+TAG=${1:-r1c}
+CMD="python bench.py --profile-region --no-cpu"
+$CMD > gpurun_out/plain_profile_region.log 2>&1 || exit 1
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+timeout 500 ncu --profile-from-start off --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section Occupancy --section SchedulerStats --clock-control none -k regex:"attn_tc|tc_gemm_persist|tc_wgrad|score_tc_kernel|ce_bwd_tc|layernorm|embed_|embgrad|dropout_cast|adam" -c 90 -o gpurun_out/prof_step_${TAG} $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
+ls -la gpurun_out/
