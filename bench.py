@@ -175,7 +175,7 @@ def run_reference(args):
                       "note": "CPU port (oracle/asme_oracle.py) of the reference's PyTorch path; the Python reference cannot travel to the GPU box"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -314,6 +314,18 @@ def summarise_kernels(records, steps, pk):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +343,13 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its version
+    # banner there) are sent to stderr for the whole run, the result line goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -397,7 +416,7 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         bench_eval_c5(device, pk, steps=1, warmup=2, world=world, rank=rank, profile=True)
-        print(json.dumps({"profile_region": "1 training step (C2) + 1 evaluation step (C5), launch by launch"}))
+        emit({"profile_region": "1 training step (C2) + 1 evaluation step (C5), launch by launch"})
         return
 
     # The step is ~90 launches; issued from Python the host is the bottleneck, so the product path replays the step's CUDA graph
@@ -554,7 +573,7 @@ def main():
            "roofline": roofline, "cpu_baseline": cpu,
            "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()} for row in table[:30]],
            "kernel_ms_per_step": kernel_ms_per_step, "eval": eval_info}
-    print(json.dumps(out))
+    emit(out)
     finish()
 
 

@@ -85,25 +85,44 @@ __global__ void __launch_bounds__(128) embgrad_chunk_kernel(const int* __restric
     Acc acc;
     acc.zero();
     int run_start = 0;
-    for (int r = 0; r < CHUNK; ++r) {
-        const int k = __shfl_sync(0xffffffffu, key, r);
-        if (k >= V) break;   // sorted: only skipped entries follow
-        const int v = __shfl_sync(0xffffffffu, val, r);
-        acc.add_row(d_rows + (size_t)v * H, H, lane);
-        const int k_next = r + 1 < CHUNK ? __shfl_sync(0xffffffffu, key, r + 1) : next_key;
-        if (k_next != k) {
-            const bool started_before = run_start == 0 && prev_key == k;
-            if (started_before) { acc.store(head + (size_t)c * H, H, lane); fl |= 1; }
-            else acc.add_to(d_table + (size_t)k * H, H, lane);
-            acc.zero();
-            run_start = r + 1;
-        } else if (r + 1 == CHUNK) {   // run continues into the next chunk
-            const bool started_before = run_start == 0 && prev_key == k;
-            if (started_before) { acc.store(head + (size_t)c * H, H, lane); fl |= 3; }
-            else {
-                acc.store(tail + (size_t)c * H, H, lane);
-                fl |= 4;
-                if (lane == 0) tail_key[c] = k;
+    // rows are fetched eight at a time before any of them is consumed: the chunk used to pay one dependent L2 latency per entry
+    const bool narrow = H <= 128;              // one float4 per lane covers the row
+    bool done = false;
+    for (int rb = 0; rb < CHUNK && !done; rb += 8) {
+        float4 buf[8];
+        if (narrow) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int v = __shfl_sync(0xffffffffu, val, rb + j);
+                buf[j] = lane * 4 < H ? ldg4(d_rows + (size_t)v * H + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = rb + j;
+            const int k = __shfl_sync(0xffffffffu, key, r);
+            if (k >= V) { done = true; break; }   // sorted: only skipped entries follow (warp-uniform)
+            if (narrow) {
+                add4(acc.v[0], buf[j]);
+            } else {
+                const int v = __shfl_sync(0xffffffffu, val, r);
+                acc.add_row(d_rows + (size_t)v * H, H, lane);
+            }
+            const int k_next = r + 1 < CHUNK ? __shfl_sync(0xffffffffu, key, r + 1) : next_key;
+            if (k_next != k) {
+                const bool started_before = run_start == 0 && prev_key == k;
+                if (started_before) { acc.store(head + (size_t)c * H, H, lane); fl |= 1; }
+                else acc.add_to(d_table + (size_t)k * H, H, lane);
+                acc.zero();
+                run_start = r + 1;
+            } else if (r + 1 == CHUNK) {   // run continues into the next chunk
+                const bool started_before = run_start == 0 && prev_key == k;
+                if (started_before) { acc.store(head + (size_t)c * H, H, lane); fl |= 3; }
+                else {
+                    acc.store(tail + (size_t)c * H, H, lane);
+                    fl |= 4;
+                    if (lane == 0) tail_key[c] = k;
+                }
             }
         }
     }
@@ -144,7 +163,24 @@ __global__ void __launch_bounds__(CARRY_WARPS * 32) embgrad_carry_kernel(const f
     Acc acc;
     acc.zero();
     if (warp == 0) acc.add_row(tail + (size_t)c * H, H, lane);
-    for (int i = warp; i < len; i += CARRY_WARPS) acc.add_row(head + (size_t)(c + 1 + i) * H, H, lane);
+    {   // four independent partial sums per warp keep four row loads in flight; combined in a fixed order
+        Acc a1, a2, a3;
+        a1.zero(); a2.zero(); a3.zero();
+        int i = warp;
+        for (; i + 3 * CARRY_WARPS < len; i += 4 * CARRY_WARPS) {
+            acc.add_row(head + (size_t)(c + 1 + i) * H, H, lane);
+            a1.add_row(head + (size_t)(c + 1 + i + CARRY_WARPS) * H, H, lane);
+            a2.add_row(head + (size_t)(c + 1 + i + 2 * CARRY_WARPS) * H, H, lane);
+            a3.add_row(head + (size_t)(c + 1 + i + 3 * CARRY_WARPS) * H, H, lane);
+        }
+        for (; i < len; i += CARRY_WARPS) acc.add_row(head + (size_t)(c + 1 + i) * H, H, lane);
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            add4(a2.v[q], a3.v[q]);
+            add4(a1.v[q], a2.v[q]);
+            add4(acc.v[q], a1.v[q]);
+        }
+    }
     acc.store(carry_smem + (size_t)warp * H, H, lane);
     __syncthreads();
     if (warp == 0) {

@@ -604,12 +604,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
     }
 }
 
-// out[i] (+)= sum over splits of partial[split][i]: 32 float4 columns x 8 split groups per block, fixed summation order
+// out[i] (+)= sum over splits of partial[split][i]: 32 float4 columns x 8 split groups per block, fixed summation order.
+// Two reductions in one launch: blocks [0, blocks0) reduce (partial, n, out), the remaining ones (partial2, n2, out2) -- the
+// weight gradient and its bias gradient.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, long long n,
-                                                           float* __restrict__ out, int accumulate) {
+                                                           float* __restrict__ out, int blocks0, const float* __restrict__ partial2,
+                                                           long long n2, float* __restrict__ out2, int accumulate) {
     __shared__ float4 red[8][32];
     const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-    const long long i = ((long long)blockIdx.x * 32 + tx) * 4;
+    int blk = blockIdx.x;
+    if (blk >= blocks0) {          // block-uniform
+        blk -= blocks0;
+        partial = partial2; n = n2; out = out2;
+    }
+    const long long i = ((long long)blk * 32 + tx) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n) {
         float4 s1 = s;
@@ -670,11 +678,8 @@ extern "C" int asme_b200_tc_wgrad(const void* dY, const void* X, int M, int N, i
     tc_wgrad_kernel<<<dim3(splits, ceil_div(N, 128), ceil_div(K, 256)), G_THREADS, smem, st>>>(tmY, tmX, a);
     ASME_LAUNCH_OK();
     const long long n = (long long)N * K;
-    wgrad_reduce_kernel<<<ceil_div(n / 4, 32), 256, 0, st>>>(a.partial, splits, n, dW, accumulate);
+    const int blocks0 = (int)ceil_div(n / 4, 32), blocks1 = dbias ? ceil_div(N / 4, 32) : 0;
+    wgrad_reduce_kernel<<<blocks0 + blocks1, 256, 0, st>>>(a.partial, splits, n, dW, blocks0, a.partial_bias, (long long)N, dbias, accumulate);
     ASME_LAUNCH_OK();
-    if (dbias) {
-        wgrad_reduce_kernel<<<ceil_div(N / 4, 32), 256, 0, st>>>(a.partial_bias, splits, N, dbias, accumulate);
-        ASME_LAUNCH_OK();
-    }
     return ASME_OK;
 }
