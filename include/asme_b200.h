@@ -297,6 +297,14 @@ int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_i
                       const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
                       unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16, void* pre_act_bf16,
                       asme_stream_t stream);
+/* the same with a fused LayerNorm of the fp32 output rows (transformer_layers.py:120-130: the rows are the next sublayer's
+ * LayerNorm input): ln_out (M,N) bf16 = LN(out_f32; ln_gamma, ln_beta), ln_stats (2,M) = row mean / rstd or NULL.
+ * Needs out_f32 and N <= 128 (one column tile owns whole rows). */
+int asme_b200_tc_gemm_ln(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
+                         const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
+                         unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
+                         void* pre_act_bf16, const float* ln_gamma, const float* ln_beta, void* ln_out, float* ln_stats,
+                         asme_stream_t stream);
 /* diagnostic: knob 0 selects the tall kernel (1 = persistent CTAs with a resident weight tile, default; 0 = one CTA per tile) */
 int asme_b200_tc_gemm_tune(int knob, int value);
 /* dW (N,K) fp32 (+)= dY(M,N)^T X(M,K), dbias (N) (+)= colsum(dY); dY, X bf16; token contraction split over the SMs with a

@@ -120,12 +120,16 @@ class EncoderEngine:
         p = cfg.dropout if train else 0.0
         pa = cfg.attention_dropout if train else 0.0
         B, S = saved.B, saved.S
+        y1_next = st1_next = None      # LayerNorm of the next layer's input, produced by this layer's last GEMM epilogue
         for l in range(cfg.layers):
             pre = f"{self.blocks}.{l}"
             ls = LayerSaved()
             ls.x = x
-            ls.y1, _, ls.st1 = ops.layernorm_fwd_bf16(x, self._w(f"{pre}.input_sublayer.norm.weight"),
-                                                      self._w(f"{pre}.input_sublayer.norm.bias"), save_stats=train)
+            if y1_next is not None:
+                ls.y1, ls.st1 = y1_next, st1_next
+            else:
+                ls.y1, _, ls.st1 = ops.layernorm_fwd_bf16(x, self._w(f"{pre}.input_sublayer.norm.weight"),
+                                                          self._w(f"{pre}.input_sublayer.norm.bias"), save_stats=train)
             wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
             bqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,))
             ls.attn_tc = S <= 256 and (H // cfg.heads) in (16, 32, 64)
@@ -141,18 +145,25 @@ class EncoderEngine:
             if select_rows is not None and l == cfg.layers - 1 and not train:
                 ls.ctx16 = ls.ctx16.index_select(0, select_rows)      # row selection (index plumbing, no arithmetic)
                 x = x.index_select(0, select_rows)
-            ls.x2 = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
-                                bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,
-                                site=self._site(l, 1), residual=x)["f32"]
-            ls.y2, _, ls.st2 = ops.layernorm_fwd_bf16(ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"),
-                                                      self._w(f"{pre}.output_sublayer.norm.bias"), save_stats=train)
+            # output projection + residual, with the output sublayer's LayerNorm fused into the epilogue (H <= 128)
+            r = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
+                            bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,
+                            site=self._site(l, 1), residual=x,
+                            ln=(self._w(f"{pre}.output_sublayer.norm.weight"), self._w(f"{pre}.output_sublayer.norm.bias")), ln_stats=train)
+            ls.x2, ls.y2, ls.st2 = r["f32"], r["ln16"], r["ln_st"]
             r = ops.tc_gemm(ls.y2, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), bias=self._w(f"{pre}.feed_forward.w_1.bias"),
                             act=ACT_GELU, p_drop=p, seed=saved.seed, site=self._site(l, 2), out_f32=False, out_bf16=True,
                             pre_act=train)
             ls.a, ls.z = r["bf16"], r["pre"]
-            x = ops.tc_gemm(ls.a, m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), bias=self._w(f"{pre}.feed_forward.w_2.bias"),
+            nxt = None
+            if l + 1 < cfg.layers:          # the next layer's input LayerNorm rides in this GEMM's epilogue
+                npre = f"{self.blocks}.{l + 1}"
+                nxt = (self._w(f"{npre}.input_sublayer.norm.weight"), self._w(f"{npre}.input_sublayer.norm.bias"))
+            r = ops.tc_gemm(ls.a, m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), bias=self._w(f"{pre}.feed_forward.w_2.bias"),
                             p_drop=p, seed=saved.seed, site=self._site(l, 3), residual=ls.x2,
-                            post_site=self._site(l, 4) if p > 0 else 0)["f32"]
+                            post_site=self._site(l, 4) if p > 0 else 0, ln=nxt, ln_stats=train)
+            x = r["f32"]
+            y1_next, st1_next = (r["ln16"], r["ln_st"]) if nxt is not None else (None, None)
             if train:
                 saved.layers.append(ls)
         return x

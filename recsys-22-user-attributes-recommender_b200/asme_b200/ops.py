@@ -398,6 +398,9 @@ def _bf16(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+FUSE_LAYERNORM = False     # tc_gemm(ln=...): fuse the LayerNorm into the GEMM epilogue.  Measured: no gain (1.135 vs 1.123 ms per C2 step, 1.99 vs 1.97 ms per C5 step: the epilogue is latency-bound and the separate LayerNorm runs near the HBM roofline) -> off, kept as an option
+
+
 def tc_score_topk(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, target=None, target_score_in=None, v0: int = 0,
                   capture_target: bool = True):
     """hb (R,Kp) / wb (Vloc,Kp) bf16.  returns dict(topk_val, topk_idx, target_score, n_greater, n_tie_lower)
@@ -458,9 +461,11 @@ def tc_score_ce_bwd(hb, wb, bias, target, lse, scale: float, H: int, dW: Optiona
 
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, act: int = 0, gelu_grad_of=None,
             p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out_f32: bool = True, out_bf16: bool = False,
-            pre_act: bool = False, post_site: int = 0, bf16_into: Optional[torch.Tensor] = None):
+            pre_act: bool = False, post_site: int = 0, bf16_into: Optional[torch.Tensor] = None, ln=None, ln_stats: bool = False):
     """tensor-core dense layer; a (M,K) bf16, b (N,K) [or (K,N) when b_is_kn] bf16.
-    returns dict(f32=..., bf16=..., pre=...) with the requested outputs"""
+    returns dict(f32=..., bf16=..., pre=...) with the requested outputs.  ``ln=(gamma, beta)``: additionally
+    ``ln16`` = LayerNorm(f32 output) as bf16 and, with ``ln_stats``, ``ln_st`` (2,M) -- fused into the epilogue when one column
+    tile owns whole rows (N <= 128), a separate LayerNorm launch otherwise."""
     a, b = _bf16(a, "a"), _bf16(b, "b")
     M, K = a.shape
     N = b.shape[1] if b_is_kn else b.shape[0]
@@ -469,11 +474,21 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, 
     c16 = bf16_into if bf16_into is not None else (torch.empty(M, N, dtype=torch.bfloat16, device=dev) if out_bf16 else None)
     ld16 = c16.stride(0) if c16 is not None else 0
     pre = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if pre_act else None
+    fuse_ln = ln is not None and out_f32 and N <= 128 and FUSE_LAYERNORM
     if _lib.timing is not None:
-        _lib.note = f"M={M},N={N},K={K},kn={int(b_is_kn)},res={int(residual is not None)},f32={int(out_f32)},bf16={int(c16 is not None)},pre={int(pre_act)},aux={int(gelu_grad_of is not None)}"
-    _lib.call("asme_b200_tc_gemm", _p(a), _p(b), M, N, K, 1 if b_is_kn else 0, _p(bias), int(act), _p(gelu_grad_of), float(p_drop),
-              int(seed), int(site), int(post_site), _p(residual), _p(c32), _p(c16), int(ld16), _p(pre), _stream())
-    return dict(f32=c32, bf16=c16, pre=pre)
+        _lib.note = f"M={M},N={N},K={K},kn={int(b_is_kn)},res={int(residual is not None)},f32={int(out_f32)},bf16={int(c16 is not None)},pre={int(pre_act)},aux={int(gelu_grad_of is not None)}" + (",ln=1" if fuse_ln else "")
+    common = (_p(a), _p(b), M, N, K, 1 if b_is_kn else 0, _p(bias), int(act), _p(gelu_grad_of), float(p_drop),
+              int(seed), int(site), int(post_site), _p(residual), _p(c32), _p(c16), int(ld16), _p(pre))
+    out = dict(f32=c32, bf16=c16, pre=pre)
+    if fuse_ln:
+        out["ln16"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        out["ln_st"] = torch.empty(2, M, dtype=torch.float32, device=dev) if ln_stats else None
+        _lib.call("asme_b200_tc_gemm_ln", *common, _p(_f32(ln[0])), _p(_f32(ln[1])), _p(out["ln16"]), _p(out["ln_st"]), _stream())
+        return out
+    _lib.call("asme_b200_tc_gemm", *common, _stream())
+    if ln is not None:
+        out["ln16"], _, out["ln_st"] = layernorm_fwd_bf16(c32, ln[0], ln[1], save_stats=ln_stats)
+    return out
 
 
 def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True):

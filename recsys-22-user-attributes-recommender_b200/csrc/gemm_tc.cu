@@ -50,6 +50,13 @@ struct TcGemmArgs {
     __nv_bfloat16* out_bf16;           // (M,N) or NULL
     __nv_bfloat16* pre_act_bf16;       // (M,N) or NULL: value before the activation
     int ld_bf16;                       // row stride of out_bf16 (>= N), lets QKV land in a wider buffer
+    // fused LayerNorm of the fp32 output rows (persistent kernel, N <= 128 = one column tile): ln_out = LN(out_f32) as bf16,
+    // ln_stats (2, M) = row mean / rstd for the backward pass.  The rows are the NEXT sublayer's LayerNorm input, so the
+    // stand-alone LayerNorm launch (one more read and write of the activations) disappears.
+    const float* ln_gamma;             // (N) or NULL
+    const float* ln_beta;
+    __nv_bfloat16* ln_out;             // (M,N)
+    float* ln_stats;                   // (2,M) or NULL
 };
 
 #define G_STAGES 2               // K ring depth: the MMAs of a 64-wide chunk take ~100 cycles, two slots keep TMA ahead; a small
@@ -73,7 +80,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // epilogue of one 32-column chunk of one output row (shared by both tall kernels): bias, pre-activation copy, GELU, gelu'
 // multiply, dropout, residual, block-end dropout, fp32 / bf16 stores
-__device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (&v)[32], const int row, const int nc, const float inv_keep) {
+template <bool LN = false>
+__device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (&v)[32], const int row, const int nc, const float inv_keep,
+                                                    float& ln_s, float& ln_s2) {
     const size_t o = (size_t)row * a.N + nc;
     if (a.bias) {
 #pragma unroll
@@ -135,6 +144,13 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
 #pragma unroll
         for (int c = 0; c < 32; c += 4)
             *reinterpret_cast<float4*>(a.out_f32 + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+    if (LN) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            ln_s += v[c];
+            ln_s2 = fmaf(v[c], v[c], ln_s2);
+        }
     }
     if (a.out_bf16) {
         __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + nc;
@@ -241,7 +257,8 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
             tmem_ld32(lane_addr + (uint32_t)nn, v);
             tmem_ld_wait();
             if (!row_ok) continue;
-            tall_epilogue_chunk(a, v, row, n0 + nn, inv_keep);
+            float unused_s = 0.f, unused_s2 = 0.f;
+            tall_epilogue_chunk<false>(a, v, row, n0 + nn, inv_keep, unused_s, unused_s2);
         }
     }
     tc_fence_before();
@@ -267,9 +284,10 @@ struct __align__(8) GemmPBars {
     uint64_t tfull[2];
     uint64_t tempty[2];
     uint32_t tmem_base;
+    float ln_part[2][2][G_BM];         // fused LayerNorm: [warpgroup][sum | sum of squares][row of the tile]
 };
 
-template <bool B_MN>
+template <bool B_MN, bool LN>
 __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
                                                                      int stages) {
@@ -378,8 +396,15 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const _
             if (c_lo == c_hi) {                              // a warpgroup without columns (NT = 32) still hands the stage back
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&bars->tempty[as]);
+                if (LN) {                                    // ... and takes part in the statistics exchange with zeros
+                    bars->ln_part[wg][0][q * 32 + lane] = 0.f;
+                    bars->ln_part[wg][1][q * 32 + lane] = 0.f;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                }
                 continue;
             }
+            float ln_s = 0.f, ln_s2 = 0.f;
             for (int nn = c_lo * 32; nn < c_hi * 32; nn += 32) {
                 float v[32];
                 tmem_ld32(lane_addr + (uint32_t)nn, v);
@@ -389,7 +414,39 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const _
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tempty[as]);
                 }
-                if (row_ok) tall_epilogue_chunk(a, v, row, n0 + nn, inv_keep);
+                if (row_ok) tall_epilogue_chunk<LN>(a, v, row, n0 + nn, inv_keep, ln_s, ln_s2);
+            }
+            if (LN) {
+                // row statistics: the two warpgroups hold disjoint column ranges of the same rows -> exchange the partial sums,
+                // then every thread normalises the columns it wrote (re-read from L1 / L2: its own stores of a moment ago)
+                const int rt = q * 32 + lane;
+                bars->ln_part[wg][0][rt] = ln_s;
+                bars->ln_part[wg][1][rt] = ln_s2;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float inv_n = 1.0f / (float)a.N;
+                const float mean = (ln_s + bars->ln_part[wg ^ 1][0][rt]) * inv_n;
+                const float var = fmaxf((ln_s2 + bars->ln_part[wg ^ 1][1][rt]) * inv_n - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+                asm volatile("bar.sync 2, 256;" ::: "memory");       // ln_part may be overwritten by the next tile
+                if (row_ok) {
+                    if (wg == 0 && a.ln_stats) { a.ln_stats[row] = mean; a.ln_stats[(size_t)a.M + row] = rstd; }
+                    for (int nn = c_lo * 32; nn < c_hi * 32; nn += 32) {
+                        const float* xr = a.out_f32 + (size_t)row * a.N + nn;
+                        __nv_bfloat16* yr = a.ln_out + (size_t)row * a.N + nn;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            const float4 x0 = *reinterpret_cast<const float4*>(xr + c), x1 = *reinterpret_cast<const float4*>(xr + c + 4);
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma + nn + c)), g1 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma + nn + c + 4));
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.ln_beta + nn + c)), b1 = __ldg(reinterpret_cast<const float4*>(a.ln_beta + nn + c + 4));
+                            uint4 w;
+                            w.x = pack_bf16(fmaf((x0.x - mean) * rstd, g0.x, b0.x), fmaf((x0.y - mean) * rstd, g0.y, b0.y));
+                            w.y = pack_bf16(fmaf((x0.z - mean) * rstd, g0.z, b0.z), fmaf((x0.w - mean) * rstd, g0.w, b0.w));
+                            w.z = pack_bf16(fmaf((x1.x - mean) * rstd, g1.x, b1.x), fmaf((x1.y - mean) * rstd, g1.y, b1.y));
+                            w.w = pack_bf16(fmaf((x1.z - mean) * rstd, g1.z, b1.z), fmaf((x1.w - mean) * rstd, g1.w, b1.w));
+                            *reinterpret_cast<uint4*>(yr + c) = w;
+                        }
+                    }
+                }
             }
         }
     }
@@ -408,14 +465,17 @@ extern "C" int asme_b200_tc_gemm_tune(int knob, int value) {
     return ASME_OK;
 }
 
-extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
-                                 const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
-                                 unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
-                                 void* pre_act_bf16, asme_stream_t stream) {
+static int tc_gemm_impl(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
+                        const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
+                        unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
+                        void* pre_act_bf16, const float* ln_gamma, const float* ln_beta, void* ln_out, float* ln_stats,
+                        asme_stream_t stream) {
     ASME_REQUIRE(A && B && (out_f32 || out_bf16), "tc_gemm: null argument");
     ASME_REQUIRE(M >= 0 && N >= 32 && N % 32 == 0, "tc_gemm: N=%d unsupported (multiple of 32)", N);
     ASME_REQUIRE(K >= 64 && K % 64 == 0, "tc_gemm: K=%d unsupported (multiple of 64)", K);
     ASME_REQUIRE(!out_bf16 || (ld_bf16 >= N && ld_bf16 % 8 == 0), "tc_gemm: ld_bf16=%d", ld_bf16);
+    const bool ln = ln_gamma != nullptr;
+    ASME_REQUIRE(!ln || (ln_beta && ln_out && out_f32 && N <= G_NT), "tc_gemm_ln: needs beta, ln_out, out_f32 and N <= %d (one column tile)", G_NT);
     if (M == 0) return ASME_OK;
     CUtensorMap tmA, tmB;
     int rc = asme_tc_make_tmap_bf16(&tmA, A, M, K, K, G_BM);
@@ -428,6 +488,7 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act; a.gelu_grad_of = (const __nv_bfloat16*)gelu_grad_of;
     a.p_drop = p_drop; a.seed = seed; a.site = site; a.post_site = post_site; a.residual = residual; a.out_f32 = out_f32;
     a.out_bf16 = (__nv_bfloat16*)out_bf16; a.pre_act_bf16 = (__nv_bfloat16*)pre_act_bf16; a.ld_bf16 = ld_bf16;
+    a.ln_gamma = ln_gamma; a.ln_beta = ln_beta; a.ln_out = (__nv_bfloat16*)ln_out; a.ln_stats = ln_stats;
     const int kch = K / 64;
     cudaStream_t st = (cudaStream_t)stream;
     // weight tile resident (kch x 16 KB) + ring of activation K-chunks; two CTAs per SM whenever they fit (<= ~110 KB each)
@@ -439,7 +500,8 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
         per_sm = 1;
     }
     if (pstages > GP_MAX_STAGES) pstages = GP_MAX_STAGES;
-    if (g_gemm_variant == 1 && pstages >= 2) {      // (a weight tile too large for shared memory falls back to the per-tile kernel)
+    ASME_REQUIRE(!ln || pstages >= 2, "tc_gemm_ln: K=%d does not fit the persistent kernel", K);
+    if ((g_gemm_variant == 1 || ln) && pstages >= 2) {      // (a weight tile too large for shared memory falls back to the per-tile kernel)
         const int stages = pstages;
         const size_t smem_p = fixed + (size_t)stages * G_BM * 128;
         const int n_tiles = ceil_div(N, G_NT), m_tiles = ceil_div(M, G_BM);
@@ -447,13 +509,14 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
         if (gx < 1) gx = 1;
         if (gx > m_tiles) gx = m_tiles;
         const dim3 pgrid(gx, n_tiles);
-        if (b_is_kn) {
-            { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_persist_kernel<true>); if (_rc) return _rc; }
-            tc_gemm_persist_kernel<true><<<pgrid, G_TALL_THREADS, smem_p, st>>>(tmA, tmB, a, stages);
-        } else {
-            { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_persist_kernel<false>); if (_rc) return _rc; }
-            tc_gemm_persist_kernel<false><<<pgrid, G_TALL_THREADS, smem_p, st>>>(tmA, tmB, a, stages);
+#define LAUNCH_PERSIST(BMN, LNF)                                                                                              \
+        {                                                                                                                     \
+            { const int _rc = asme_ensure_max_smem((const void*)tc_gemm_persist_kernel<BMN, LNF>); if (_rc) return _rc; }     \
+            tc_gemm_persist_kernel<BMN, LNF><<<pgrid, G_TALL_THREADS, smem_p, st>>>(tmA, tmB, a, stages);                     \
         }
+        if (b_is_kn) { if (ln) LAUNCH_PERSIST(true, true) else LAUNCH_PERSIST(true, false) }
+        else { if (ln) LAUNCH_PERSIST(false, true) else LAUNCH_PERSIST(false, false) }
+#undef LAUNCH_PERSIST
         ASME_LAUNCH_OK();
         return ASME_OK;
     }
@@ -469,6 +532,25 @@ extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int
     }
     ASME_LAUNCH_OK();
     return ASME_OK;
+}
+
+extern "C" int asme_b200_tc_gemm(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
+                                 const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
+                                 unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
+                                 void* pre_act_bf16, asme_stream_t stream) {
+    return tc_gemm_impl(A, B, M, N, K, b_is_kn, bias, act, gelu_grad_of, p_drop, seed, site, post_site, residual, out_f32, out_bf16,
+                        ld_bf16, pre_act_bf16, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+// the same with a fused LayerNorm of the fp32 output rows: ln_out (M,N) bf16 = LN(out_f32; gamma, beta), ln_stats (2,M) or NULL
+extern "C" int asme_b200_tc_gemm_ln(const void* A, const void* B, int M, int N, int K, int b_is_kn, const float* bias, int act,
+                                    const void* gelu_grad_of, float p_drop, unsigned long long seed, unsigned int site,
+                                    unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
+                                    void* pre_act_bf16, const float* ln_gamma, const float* ln_beta, void* ln_out, float* ln_stats,
+                                    asme_stream_t stream) {
+    ASME_REQUIRE(ln_gamma && ln_beta && ln_out, "tc_gemm_ln: null LayerNorm argument");
+    return tc_gemm_impl(A, B, M, N, K, b_is_kn, bias, act, gelu_grad_of, p_drop, seed, site, post_site, residual, out_f32, out_bf16,
+                        ld_bf16, pre_act_bf16, ln_gamma, ln_beta, ln_out, ln_stats, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -94,3 +94,51 @@ def test_tc_gemm_dropout_uses_the_shared_stream(ops):
     assert torch.equal(dropped, want)
     keep = (want != 0).float().mean().item()
     assert abs(keep - 0.75 * (plain != 0).float().mean().item()) < 0.02
+
+
+@pytest.fixture(params=[1, 0], ids=["persistent", "per_tile"])
+def gemm_variant(request, ops):
+    """both tall kernels: persistent CTAs with a resident weight tile (default) and one CTA per tile"""
+    ops._lib.call("asme_b200_tc_gemm_tune", 0, request.param)
+    yield request.param
+    ops._lib.call("asme_b200_tc_gemm_tune", 0, 1)
+
+
+@pytest.mark.parametrize("M,N,K", [(100, 192, 64), (51200, 64, 256), (300, 384, 128), (200, 128, 512), (1, 64, 64)])
+def test_tc_gemm_variants_agree(ops, gemm_variant, M, N, K):
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a, w, bias = ints(gen, M, K), ints(gen, N, K), ints(gen, N)
+    out = ops.tc_gemm(a.bfloat16(), w.bfloat16(), bias=bias)
+    assert torch.equal(out["f32"].double(), a.double() @ w.double().t() + bias.double())
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 64, 64), (51200, 64, 256), (257, 128, 512), (130, 32, 64), (1000, 128, 192)])
+def test_tc_gemm_fused_layernorm(ops, M, N, K):
+    """LayerNorm fused into the epilogue (transformer_layers.py:120-130, the next sublayer's norm) against the oracle's
+    LayerNorm of the very same fp32 rows, and against the stand-alone LayerNorm kernel"""
+    gen = torch.Generator(device="cuda").manual_seed(M * 3 + N + K)
+    a = (torch.randn(M, K, generator=gen, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=gen, device="cuda") * 0.2).bfloat16()
+    bias = torch.randn(N, generator=gen, device="cuda")
+    res = torch.randn(M, N, generator=gen, device="cuda") * 2 + 0.5
+    gamma = torch.randn(N, generator=gen, device="cuda") * 0.3 + 1.0
+    beta = torch.randn(N, generator=gen, device="cuda") * 0.2
+    old = ops.FUSE_LAYERNORM
+    try:
+        ops.FUSE_LAYERNORM = True
+        fused = ops.tc_gemm(a, w, bias=bias, residual=res, ln=(gamma, beta), ln_stats=True)
+        ops.FUSE_LAYERNORM = False
+        split = ops.tc_gemm(a, w, bias=bias, residual=res, ln=(gamma, beta), ln_stats=True)
+    finally:
+        ops.FUSE_LAYERNORM = old
+    assert torch.equal(fused["f32"], split["f32"])
+    want = O.layer_norm(fused["f32"].double().cpu(), gamma.double().cpu(), beta.double().cpu())
+    torch.testing.assert_close(fused["ln16"].double().cpu(), want, rtol=1e-2, atol=1e-2)             # bf16 output
+    x = fused["f32"].double()
+    torch.testing.assert_close(fused["ln_st"][0].double(), x.mean(dim=1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(fused["ln_st"][1].double(), 1.0 / torch.sqrt(x.var(dim=1, unbiased=False) + 1e-5), rtol=2e-5, atol=0)
+    # the two implementations round to the same bf16 value almost everywhere; where they differ it is by one bf16 ulp
+    diff = (fused["ln16"].float() - split["ln16"].float()).abs()
+    assert float(diff.max()) <= 2.0 ** -7 * float(split["ln16"].float().abs().max())
+    assert float((diff > 0).float().mean()) < 0.02
+    torch.testing.assert_close(fused["ln_st"], split["ln_st"], rtol=2e-5, atol=1e-6)
