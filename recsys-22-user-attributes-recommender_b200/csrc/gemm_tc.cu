@@ -78,12 +78,72 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// epilogue of one 32-column chunk of one output row (shared by both tall kernels): bias, pre-activation copy, GELU, gelu'
-// multiply, dropout, residual, block-end dropout, fp32 / bf16 stores
+// ---- coalesced epilogue traffic -------------------------------------------------------------------------------------------
+// A TMEM lane is an output row, so each epilogue thread owns a row and would touch memory in 16-byte pieces that are a whole
+// row apart from its neighbours' -- 32 different cache lines per warp instruction.  With a warp-private 2 KB staging tile
+// (32 rows x 64 bytes, 16-byte units XOR-swizzled) the warp moves 64-byte row pieces instead: lanes 4r..4r+3 handle row r of
+// eight rows per instruction, i.e. whole sectors, 4x fewer L1 wavefronts.  stage == NULL: per-thread accesses (per-tile kernel).
+struct WarpTile {
+    uint8_t* stage;      // 2 KB, private to the warp, or NULL
+    int lane;
+    int rows_valid;      // rows [0, rows_valid) of the warp's 32 rows exist
+};
+__device__ __forceinline__ uint32_t wt_off(int r, int u) { return (uint32_t)(r * 64 + ((u ^ ((r >> 1) & 3)) << 4)); }
+// every lane stores its own row's 64 bytes (`mine`) to gbase + lane * pitch
+__device__ __forceinline__ void tile_store64(const WarpTile& t, const uint4 (&mine)[4], uint8_t* gbase, size_t pitch) {
+    if (t.stage == nullptr) {
+        if (t.lane < t.rows_valid) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(gbase + (size_t)t.lane * pitch + u * 16) = mine[u];
+        }
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(t.stage + wt_off(t.lane, u)) = mine[u];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = j * 8 + t.lane / 4, u = t.lane % 4;
+        const uint4 w = *reinterpret_cast<const uint4*>(t.stage + wt_off(r, u));
+        if (r < t.rows_valid) *reinterpret_cast<uint4*>(gbase + (size_t)r * pitch + u * 16) = w;
+    }
+    __syncwarp();
+}
+// every lane receives its own row's 64 bytes from gbase + lane * pitch (zeros for rows that do not exist)
+__device__ __forceinline__ void tile_load64(const WarpTile& t, uint4 (&mine)[4], const uint8_t* gbase, size_t pitch) {
+    if (t.stage == nullptr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            mine[u] = t.lane < t.rows_valid ? __ldg(reinterpret_cast<const uint4*>(gbase + (size_t)t.lane * pitch + u * 16)) : make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = j * 8 + t.lane / 4, u = t.lane % 4;
+        const uint4 w = r < t.rows_valid ? __ldg(reinterpret_cast<const uint4*>(gbase + (size_t)r * pitch + u * 16)) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(t.stage + wt_off(r, u)) = w;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mine[u] = *reinterpret_cast<const uint4*>(t.stage + wt_off(t.lane, u));
+    __syncwarp();
+}
+__device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint4 (&w)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        w[u].x = pack_bf16(v[8 * u], v[8 * u + 1]); w[u].y = pack_bf16(v[8 * u + 2], v[8 * u + 3]);
+        w[u].z = pack_bf16(v[8 * u + 4], v[8 * u + 5]); w[u].w = pack_bf16(v[8 * u + 6], v[8 * u + 7]);
+    }
+}
+
+// epilogue of one 32-column chunk of the 32 output rows of a warp (shared by both tall kernels; ALL lanes call it): bias,
+// pre-activation copy, GELU, gelu' multiply, dropout, residual, block-end dropout, fp32 / bf16 stores.
+// `row` = this lane's row (row0 + lane, may be >= M), nc = first column of the chunk.
 template <bool LN = false>
 __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (&v)[32], const int row, const int nc, const float inv_keep,
-                                                    float& ln_s, float& ln_s2) {
-    const size_t o = (size_t)row * a.N + nc;
+                                                    float& ln_s, float& ln_s2, const WarpTile& t) {
+    const size_t o = (size_t)row * a.N + nc;                       // element index of v[0] (dropout stream index)
+    const size_t o0 = (size_t)(row - t.lane) * a.N + nc;           // the same for the warp's first row
     if (a.bias) {
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
@@ -92,28 +152,25 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
         }
     }
     if (a.pre_act_bf16) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-            uint4 w;
-            w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
-            w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
-            *reinterpret_cast<uint4*>(a.pre_act_bf16 + o + c) = w;
-        }
+        uint4 w[4];
+        pack32_bf16(v, w);
+        tile_store64(t, w, reinterpret_cast<uint8_t*>(a.pre_act_bf16 + o0), (size_t)a.N * 2);
     }
     if (a.act == ASME_ACT_GELU) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] = gelu_erf_fast(v[c]);
     }
     if (a.gelu_grad_of) {
+        uint4 w[4];
+        tile_load64(t, w, reinterpret_cast<const uint8_t*>(a.gelu_grad_of + o0), (size_t)a.N * 2);
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-            const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.gelu_grad_of + o + c));
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
-                v[c + 2 * e] *= gelu_erf_grad_fast(__low2float(z2));
-                v[c + 2 * e + 1] *= gelu_erf_grad_fast(__high2float(z2));
+                v[8 * u + 2 * e] *= gelu_erf_grad_fast(__low2float(z2));
+                v[8 * u + 2 * e + 1] *= gelu_erf_grad_fast(__high2float(z2));
             }
         }
     }
@@ -127,9 +184,14 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
     }
     if (a.residual) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o + c));
-            v[c] += r.x; v[c + 1] += r.y; v[c + 2] += r.z; v[c + 3] += r.w;
+        for (int h = 0; h < 2; ++h) {                              // two 16-column halves of 64 bytes per row
+            uint4 w[4];
+            tile_load64(t, w, reinterpret_cast<const uint8_t*>(a.residual + o0 + 16 * h), (size_t)a.N * 4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[16 * h + 4 * u] += __uint_as_float(w[u].x); v[16 * h + 4 * u + 1] += __uint_as_float(w[u].y);
+                v[16 * h + 4 * u + 2] += __uint_as_float(w[u].z); v[16 * h + 4 * u + 3] += __uint_as_float(w[u].w);
+            }
         }
     }
     if (a.p_drop > 0.f && a.post_site) {
@@ -142,8 +204,14 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
     }
     if (a.out_f32) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-            *reinterpret_cast<float4*>(a.out_f32 + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int h = 0; h < 2; ++h) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                w[u] = make_uint4(__float_as_uint(v[16 * h + 4 * u]), __float_as_uint(v[16 * h + 4 * u + 1]),
+                                  __float_as_uint(v[16 * h + 4 * u + 2]), __float_as_uint(v[16 * h + 4 * u + 3]));
+            tile_store64(t, w, reinterpret_cast<uint8_t*>(a.out_f32 + o0 + 16 * h), (size_t)a.N * 4);
+        }
     }
     if (LN) {
 #pragma unroll
@@ -153,14 +221,9 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
         }
     }
     if (a.out_bf16) {
-        __nv_bfloat16* dst = a.out_bf16 + (size_t)row * a.ld_bf16 + nc;
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-            uint4 w;
-            w.x = pack_bf16(v[c], v[c + 1]); w.y = pack_bf16(v[c + 2], v[c + 3]);
-            w.z = pack_bf16(v[c + 4], v[c + 5]); w.w = pack_bf16(v[c + 6], v[c + 7]);
-            *reinterpret_cast<uint4*>(dst + c) = w;
-        }
+        uint4 w[4];
+        pack32_bf16(v, w);
+        tile_store64(t, w, reinterpret_cast<uint8_t*>(a.out_bf16 + (size_t)(row - t.lane) * a.ld_bf16 + nc), (size_t)a.ld_bf16 * 2);
     }
 }
 
@@ -256,9 +319,9 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
             float v[32];
             tmem_ld32(lane_addr + (uint32_t)nn, v);
             tmem_ld_wait();
-            if (!row_ok) continue;
             float unused_s = 0.f, unused_s2 = 0.f;
-            tall_epilogue_chunk<false>(a, v, row, n0 + nn, inv_keep, unused_s, unused_s2);
+            const WarpTile wt{nullptr, lane, a.M - (row - lane)};
+            tall_epilogue_chunk<false>(a, v, row, n0 + nn, inv_keep, unused_s, unused_s2, wt);
         }
     }
     tc_fence_before();
@@ -288,7 +351,7 @@ struct __align__(8) GemmPBars {
 };
 
 template <bool B_MN, bool LN>
-__global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(G_TALL_THREADS, 2) tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
                                                                      int stages) {
     extern __shared__ uint8_t smem_raw[];
@@ -302,7 +365,8 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const _
     const size_t b_slot = (size_t)G_NT * 128;
     uint8_t* sB = smem;                                   // [kch][b_slot]: the weight tile, resident for the whole launch
     uint8_t* sA = sB + (size_t)kch * b_slot;              // [stages][a_bytes]
-    GemmPBars* bars = reinterpret_cast<GemmPBars*>(sA + (size_t)stages * a_bytes);
+    uint8_t* stage_base = sA + (size_t)stages * a_bytes;       // [8 epilogue warps][2 KB] staging tiles of the coalesced epilogue
+    GemmPBars* bars = reinterpret_cast<GemmPBars*>(stage_base + 8 * 2048);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int m_tiles = (a.M + G_BM - 1) / G_BM;
 
@@ -405,6 +469,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const _
                 continue;
             }
             float ln_s = 0.f, ln_s2 = 0.f;
+            const WarpTile wt{stage_base + (size_t)(warp - 4) * 2048, lane, a.M - (row - lane)};
             for (int nn = c_lo * 32; nn < c_hi * 32; nn += 32) {
                 float v[32];
                 tmem_ld32(lane_addr + (uint32_t)nn, v);
@@ -414,7 +479,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_persist_kernel(const _
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tempty[as]);
                 }
-                if (row_ok) tall_epilogue_chunk<LN>(a, v, row, n0 + nn, inv_keep, ln_s, ln_s2);
+                tall_epilogue_chunk<LN>(a, v, row, n0 + nn, inv_keep, ln_s, ln_s2, wt);
             }
             if (LN) {
                 // row statistics: the two warpgroups hold disjoint column ranges of the same rows -> exchange the partial sums,
@@ -492,7 +557,7 @@ static int tc_gemm_impl(const void* A, const void* B, int M, int N, int K, int b
     const int kch = K / 64;
     cudaStream_t st = (cudaStream_t)stream;
     // weight tile resident (kch x 16 KB) + ring of activation K-chunks; two CTAs per SM whenever they fit (<= ~110 KB each)
-    const size_t fixed = 1024 + (size_t)kch * G_NT * 128 + sizeof(GemmPBars);
+    const size_t fixed = 1024 + (size_t)kch * G_NT * 128 + 8 * 2048 + sizeof(GemmPBars);
     int pstages = fixed + 2 * (size_t)G_BM * 128 <= 110 * 1024 ? (int)((110 * 1024 - fixed) / ((size_t)G_BM * 128)) : 0;
     int per_sm = 2;
     if (pstages < 2) {

@@ -129,6 +129,59 @@ def test_kebert4rec_c3_shape_bf16_vs_oracle():
     check_grads(_grads(model), {k: v.grad for k, v in leaves.items()})
 
 
+def test_ubert4rec_bf16_vs_oracle():
+    """user-attribute model on the tensor-core path: 51 positions (user token + 50 items), causal encoder, H=64, through the
+    drop-in training module (targets get the pad column) and the fused evaluation with the module's MASK rows"""
+    from asme_b200.models import UBERT4RecModel
+    from asme_b200.modules import UBERTMaskedTrainingModule
+    torch.manual_seed(0)
+    V, S, H, B = 5003, 50, 64, 48
+    kw = dict(additional_attributes={"category": {"embedding_type": "content_embedding"}},
+              user_attributes={"user_id": {"embedding_type": "user_embedding"}, "gender": {"embedding_type": "content_embedding"}},
+              attribute_vocab_sizes={"category": 40, "user_id": 900, "gender": 6})
+    model = UBERT4RecModel(H, 2, 2, V, S, 0.0, segment_embedding=True, initializer_range=0.05, **kw).cuda().train()
+    assert model.engine.use_tc()
+    w = _cpu_weights(model)
+    gen = torch.Generator().manual_seed(4321)
+    seq, target, _ = _random_batch(gen, B, S, V)
+    cat = torch.randint(3, 40, (B, S), generator=gen)
+    cat[seq == 0] = 0
+    uid = torch.randint(3, 900, (B, 1), generator=gen).repeat(1, S)
+    gender = torch.randint(3, 6, (B, 1), generator=gen).repeat(1, S)
+    attrs = {"user_id": uid, "gender": gender, "category": cat}
+    module = UBERTMaskedTrainingModule(model, num_warmup_steps=0)
+    batch = {"item": seq.cuda(), "item.target": target.cuda(), **{k: v.cuda() for k, v in attrs.items()}}
+    out = module.training_step(batch, 0)
+    out["loss"].backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    logits = O.ubert4rec_logits(leaves, seq, attrs, 2, 2, additional=("category",), user=("user_id", "gender"))
+    tgt1 = torch.cat([torch.zeros(B, 1, dtype=target.dtype), target], dim=1)
+    ref = O.cross_entropy_ignore_pad(logits, tgt1)
+    ref.backward()
+    assert rel(out["loss"], ref.detach()) < LOSS_RTOL
+    check_grads(_grads(model), {k: v.grad for k, v in leaves.items()})
+    # evaluation: one MASK per row, scored at position (1 + MASK position) of the 51
+    model.eval()
+    ev = seq.clone()
+    lengths = ev.ne(0).sum(-1)
+    for i in range(B):
+        n = min(int(lengths[i]), S - 1)
+        ev[i, n] = 1
+        ev[i, n + 1:] = 0
+    ev[ev.eq(1).cumsum(-1) > 1] = 3          # cloze masks left in the sequence: keep exactly one MASK (the appended one is last)
+    first_mask = ev.eq(1).int().argmax(-1)
+    et = torch.randint(3, V, (B,), generator=gen)
+    c2 = cat.clone()
+    c2[ev == 0] = 0
+    eattrs = {"user_id": uid, "gender": gender, "category": c2}
+    res = model.evaluate_rank(ev.cuda(), ev.cuda().ne(0), {k: v.cuda() for k, v in eattrs.items()}, et.cuda(), k=10,
+                              rows=module._mask_rows(ev.cuda()))
+    with torch.no_grad():
+        full = O.ubert4rec_logits(w, ev, eattrs, 2, 2, additional=("category",), user=("user_id", "gender"))
+    rows = full[torch.arange(B), first_mask + 1]
+    check_eval(res, rows.numpy(), et.numpy(), 10)
+
+
 def test_sasrec_neg_c4_shape_bf16_vs_oracle():
     from asme_b200.models import SASRecModel
     torch.manual_seed(0)
