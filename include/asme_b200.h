@@ -322,6 +322,11 @@ int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int 
                           float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
                           uint32_t* keep_bits /* (B*heads*S, 8) dropout keep bits for the backward pass, or NULL */,
                           asme_stream_t stream);
+/* evaluation of selected positions (the last encoder layer only needs the hidden state of one position per sequence): only the
+ * 128-query tile that holds flat row only_row[b] (= b*S + position) of sequence b is computed; the other rows of ctx are left
+ * untouched.  Rows that are computed are bit-identical to asme_b200_tc_attn_fwd. */
+int asme_b200_tc_attn_fwd_rows(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                               const int64_t* only_row, void* ctx, asme_stream_t stream);
 /* d_qkv (B*S, 3H) bf16 from d_ctx (B*S, H) bf16; scores and dP are recomputed in tensor memory, transposed quantities come
  * from transposed MMAs; needs the forward's ctx, stats and (when p_drop > 0) keep_bits */
 int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,

@@ -109,7 +109,8 @@ class EncoderEngine:
         return getattr(self.m, "precision", "fp32") == "bf16" and cfg.hidden % 64 == 0 and cfg.intermediate % 64 == 0
 
     # ---------------------------------------------------------------- encoder blocks, tensor-core path
-    def _blocks_forward_tc(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _blocks_forward_tc(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None,
+                           one_per_sequence: bool = False) -> torch.Tensor:
         """``select_rows`` (evaluation only): flat indices of the positions whose hidden state is needed.  Every layer but the
         last runs on all tokens; in the last layer only K and V depend on the other positions, so everything after the attention
         (output projection, LayerNorm, feed-forward: ~half of the layer) runs on the selected rows alone.  The selected rows are
@@ -133,10 +134,15 @@ class EncoderEngine:
             wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
             bqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,))
             ls.attn_tc = S <= 256 and (H // cfg.heads) in (16, 32, 64)
+            last_selected = select_rows is not None and l == cfg.layers - 1 and not train
             if ls.attn_tc:      # tcgen05 attention straight on the bf16 QKV projection
                 ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv, out_f32=False, out_bf16=True)["bf16"]
-                ls.ctx16, ls.ast, ls.keep = ops.tc_attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa,
-                                                            saved.seed, self._site(l, 0), save_stats=train)
+                if last_selected and one_per_sequence and select_rows.numel() == B:
+                    # one position per sequence: only the query tile that holds it is computed (the rows read below are bit-identical)
+                    ls.ctx16 = ops.tc_attn_fwd_rows(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, select_rows)
+                else:
+                    ls.ctx16, ls.ast, ls.keep = ops.tc_attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa,
+                                                                saved.seed, self._site(l, 0), save_stats=train)
             else:               # long sequences / odd head sizes: fp32 SIMT attention between tensor-core GEMMs
                 ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv)["f32"]
                 ls.ctx, ls.ast = ops.attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa, saved.seed,
@@ -213,10 +219,11 @@ class EncoderEngine:
         return dx
 
     # ---------------------------------------------------------------- encoder blocks, strict fp32 path
-    def blocks_forward(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def blocks_forward(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None,
+                       one_per_sequence: bool = False) -> torch.Tensor:
         if self.use_tc():
             saved.extra["tc"] = True
-            return self._blocks_forward_tc(x, saved, select_rows)
+            return self._blocks_forward_tc(x, saved, select_rows, one_per_sequence)
         if select_rows is not None:
             raise RuntimeError("row-selective encoding is implemented by the tensor-core path only")
         cfg, m = self.cfg, self.m

@@ -217,7 +217,7 @@ class TransformerRecommenderModel(ArenaModule):
         return (int(self._seed) << 32) + self._step_counter
 
     def encode_rows(self, seq: torch.Tensor, padding_mask: Optional[torch.Tensor], attrs: Dict[str, torch.Tensor],
-                    rows: torch.Tensor) -> torch.Tensor:
+                    rows: torch.Tensor, one_per_sequence: bool = False) -> torch.Tensor:
         """evaluation: hidden states of the selected positions only, (len(rows), H).  Identical to ``encode(...)[rows]``; on the
         tensor-core path the last encoder layer skips the output projection / feed-forward of every other position."""
         if self.engine.use_tc() and not self.postfusion:
@@ -227,7 +227,7 @@ class TransformerRecommenderModel(ArenaModule):
             S += self.user_prefix
             saved = Saved(B=B, S=S, seed=0, training=False, key_valid=self._key_valid(padding_mask, seq))
             x, _ = ops.embed_fwd(self._embed_spec(seq, attrs, False, 0), B, S)
-            return self.engine.blocks_forward(x, saved, select_rows=rows)
+            return self.engine.blocks_forward(x, saved, select_rows=rows, one_per_sequence=one_per_sequence)
         hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
         return ops.gather_rows(hidden, rows)
 
@@ -429,11 +429,14 @@ class TransformerRecommenderModel(ArenaModule):
     @torch.no_grad()
     def evaluate_rank(self, seq, padding_mask, attrs, target, k: int = 10, rows: Optional[torch.Tensor] = None,
                       select: str = "mask", mask_id: int = MASK_TOKEN_ID, with_loss: bool = False, pad_id: int = PAD_TOKEN_ID,
-                      full_rank: bool = True):
-        """returns dict(topk_val (B,k), topk_idx (B,k) int32, rank (B) int32 1-based, target_score (B)[, loss])"""
+                      full_rank: bool = True, rows_one_per_sequence: bool = False):
+        """returns dict(topk_val (B,k), topk_idx (B,k) int32, rank (B) int32 1-based, target_score (B)[, loss]).
+        ``rows_one_per_sequence``: the caller guarantees rows[b] is a position of sequence b (as the built-in selectors
+        produce them) -- the last encoder layer then computes only the attention query tile that holds it."""
         if rows is None:
             rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
-        h_rows = self.encode_rows(seq, padding_mask, attrs, rows)
+            rows_one_per_sequence = True
+        h_rows = self.encode_rows(seq, padding_mask, attrs, rows, one_per_sequence=rows_one_per_sequence)
         m_rows, _ = self.modify(h_rows)
         if self.precision == "bf16":
             wb, folded = self.projection_operands_folded()
@@ -463,9 +466,10 @@ def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, 
     per-shard top-k lists / target scores are merged with three NCCL calls.  Returns the rows of this rank's users."""
     import torch.distributed as dist
     from . import sharded
+    one = rows is None
     if rows is None:
         rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
-    m_rows, _ = self.modify(self.encode_rows(seq, padding_mask, attrs, rows))
+    m_rows, _ = self.modify(self.encode_rows(seq, padding_mask, attrs, rows, one_per_sequence=one))
     G = dist.get_world_size(group) if dist.is_initialized() else 1
     g = dist.get_rank(group) if dist.is_initialized() else 0
     wb, folded = self.projection_operands_folded()          # bias (if any) rides in two extra K columns of the table

@@ -378,7 +378,7 @@ class UBERTMaskedTrainingModule(MaskedTrainingModule):
         if not self.fused_eval or targets.dim() != 1:
             prediction = self._get_prediction_for_masked_item(batch, batch_idx)
             return build_eval_step_return_dict(seq, prediction, targets)
-        out = self.model.evaluate_rank(seq, pm, meta, targets, k=self._eval_k(), rows=self._mask_rows(seq),
+        out = self.model.evaluate_rank(seq, pm, meta, targets, k=self._eval_k(), rows=self._mask_rows(seq), rows_one_per_sequence=True,
                                        with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id,
                                        full_rank=self._full_rank())
         if self.eval_loss:
@@ -435,7 +435,7 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
             logits = self(batch, batch_idx)
             return build_eval_step_return_dict(seq, self._extract_target_logits(seq, logits), target)
         out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), target, k=self._eval_k(),
-                                       rows=self._target_rows(seq, pm), with_loss=self.eval_loss,
+                                       rows=self._target_rows(seq, pm), rows_one_per_sequence=True, with_loss=self.eval_loss,
                                        pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)

@@ -52,6 +52,8 @@ struct AttnTcArgs {
     __nv_bfloat16* ctx;          // (B*S, H)
     float* stats;                // (2, B*heads*S) or NULL
     uint32_t* keep_bits;         // (B*heads*S, 8) or NULL: bit j of word w of row (b,h,q) = key 32w+j survived the dropout
+    const int64_t* only_row;     // (B) or NULL: evaluation of selected positions -- only the 128-query tile that holds flat row
+                                 // only_row[b] (= b*S + position) is computed, the other rows of ctx are left untouched
 };
 
 struct __align__(8) AttnBars {
@@ -115,7 +117,9 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
     const int b = blockIdx.x, slice = blockIdx.y;
     const int S = a.S, d = a.d;
     const int hps = 64 / d;                   // heads per 64-column slice
-    const int n_qt = (S + 127) / 128;
+    const int n_qt_all = (S + 127) / 128;
+    const int qt_only = a.only_row ? (int)((a.only_row[b] - (long long)b * S) / 128) : -1;     // CTA-uniform
+    const int n_qt = qt_only >= 0 ? 1 : n_qt_all;   // query tiles this CTA visits; unit u -> (head u / n_qt, tile qt_of(u))
     const int NS = (S + 15) / 16 * 16;        // score columns computed by the first MMA
     const int units = hps * n_qt;
 
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             mbar_wait(&sh->loaded, 0);
             tc_fence_after();
             auto issue_s = [&](int u) {
-                const int hh = u / n_qt, qt = u % n_qt;
+                const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
                 const uint64_t qd = smem_desc_sw128(smem_u32(sQ + (size_t)qt * 128 * 128));
                 const uint64_t kd = smem_desc_sw128(smem_u32(sK));
                 for (int ks = 0; ks < ks_qk; ++ks)
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
                                                              // that a fully masked row's max is EXACTLY -1e9 (no cancellation error)
         const uint32_t thr16 = (uint32_t)(a.p_drop * 65536.0f + 0.5f);
         for (int u = 0; u < units; ++u) {
-            const int hh = u / n_qt, qt = u % n_qt;
+            const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
             const int head = slice * hps + hh;
             const int qi = qt * 128 + r;                     // query position in the sequence
             const bool q_ok = qi < S;
@@ -333,9 +337,23 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
     }
 }
 
+static int tc_attn_fwd_impl(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                            float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
+                            uint32_t* keep_bits, const int64_t* only_row, asme_stream_t stream);
 extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                                      float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
                                      uint32_t* keep_bits, asme_stream_t stream) {
+    return tc_attn_fwd_impl(qkv, key_valid, B, S, heads, d, causal, p_drop, seed, site, ctx, stats, keep_bits, nullptr, stream);
+}
+// evaluation of selected positions: only the query tile that holds flat row only_row[b] of every sequence b is computed
+extern "C" int asme_b200_tc_attn_fwd_rows(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                                          const int64_t* only_row, void* ctx, asme_stream_t stream) {
+    ASME_REQUIRE(only_row, "tc_attn_fwd_rows: null row list");
+    return tc_attn_fwd_impl(qkv, key_valid, B, S, heads, d, causal, 0.f, 0ull, 0u, ctx, nullptr, nullptr, only_row, stream);
+}
+static int tc_attn_fwd_impl(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                            float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
+                            uint32_t* keep_bits, const int64_t* only_row, asme_stream_t stream) {
     ASME_REQUIRE(qkv && ctx, "tc_attn_fwd: null argument");
     ASME_REQUIRE(S >= 1 && S <= AT_MAXS, "tc_attn_fwd: S=%d unsupported (1..%d)", S, AT_MAXS);
     ASME_REQUIRE(d == 16 || d == 32 || d == 64, "tc_attn_fwd: head dim %d unsupported (16, 32, 64)", d);
@@ -349,7 +367,7 @@ extern "C" int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, 
     AttnTcArgs a{};
     a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
     a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-    a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits;
+    a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits; a.only_row = only_row;
     const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnFwdShared);
     { const int _rc = asme_ensure_max_smem((const void*)attn_tc_fwd_kernel); if (_rc) return _rc; }
     attn_tc_fwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tm, a);

@@ -236,8 +236,8 @@ def test_encode_rows_equals_full_encode_on_selected_rows():
     from asme_b200 import ops
     from asme_b200.models import BERT4RecModel, SASRecModel, mask_position_rows, last_position_rows
     torch.manual_seed(0)
-    for cls, kw in ((BERT4RecModel, {}), (SASRecModel, {"mode": "full"})):
-        V, S, H, B = 997, 70, 128, 37
+    for cls, kw, S in ((BERT4RecModel, {}, 70), (SASRecModel, {"mode": "full"}, 70), (BERT4RecModel, {}, 200), (SASRecModel, {"mode": "full"}, 131)):
+        V, H, B = 997, 128, 37
         model = cls(H, 2, 2, V, S, 0.1, **kw).cuda().eval()
         seq, _, lengths = _random_batch(torch.Generator().manual_seed(2), B, S, V, p_mask=0.0)
         seq = seq.cuda()
@@ -246,3 +246,6 @@ def test_encode_rows_equals_full_encode_on_selected_rows():
         full, _ = model.encode(seq, seq.ne(0), {}, training=False)
         sel = model.encode_rows(seq, seq.ne(0), {}, rows)
         assert torch.equal(sel, ops.gather_rows(full, rows))
+        # one position per sequence: the last layer's attention computes only the query tile that holds it
+        sel1 = model.encode_rows(seq, seq.ne(0), {}, rows, one_per_sequence=True)
+        assert torch.equal(sel1, sel)
