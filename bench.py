@@ -259,7 +259,7 @@ def algorithmic_cost(name, note):
     return 0, 0
 
 
-NCU_NAMES = {"tc_attn_bwd": "attn_tc_bwd_kernel", "tc_attn_fwd": "attn_tc_fwd_kernel", "tc_gemm": "tc_gemm_tall_kernel",
+NCU_NAMES = {"tc_attn_bwd": "attn_tc_bwd1_kernel", "tc_attn_fwd": "attn_tc_fwd_kernel", "tc_gemm": "tc_gemm_persist_kernel",
              "tc_wgrad": "tc_wgrad_kernel", "tc_score_topk": "score_tc_kernel", "tc_score_ce_bwd": "ce_bwd_tc_kernel",
              "tc_score_ce_partial": "score_tc_kernel"}
 
@@ -284,7 +284,7 @@ def ncu_traffic(kernel):
                 try:
                     return {"bytes_per_launch": mb(r["dram__bytes_read.sum"]) + mb(r["dram__bytes_write.sum"]), "source": os.path.basename(path)}
                 except Exception:
-                    return None
+                    continue          # this capture has no DRAM counters for the kernel: try the next record / older capture
     return None
 
 

@@ -131,6 +131,11 @@ size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H);
 int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
                             const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
                             asme_stream_t stream);
+/* the same, also emitting what the next stage of the backward pass consumes (replaces an asme_b200_dropout_cast launch):
+ * dx (fp32) = (LayerNorm gradient + d_residual) * mask(site_a), dx_bf16 (M,H) = bf16(dx * mask(site_b)); site 0 = no mask */
+int asme_b200_layernorm_bwd_drop(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
+                                 const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop,
+                                 uint64_t seed, uint32_t site_a, uint32_t site_b, void* dx_bf16, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K7/K9/K10/K11/K12  dense layers: C = epilogue(A x op(B)), fp32 SIMT path (strict 1e-5 parity mode)

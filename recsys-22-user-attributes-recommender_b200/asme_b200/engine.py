@@ -180,11 +180,14 @@ class EncoderEngine:
         p, pa = cfg.dropout, cfg.attention_dropout
         B, S = saved.B, saved.S
         g = m._arena.ensure_grad()
+        pending = None      # (dx3, dy16) of the layer below, already produced by the LayerNorm backward above it
         for l in reversed(range(cfg.layers)):
             pre = f"{self.blocks}.{l}"
             ls = saved.layers[l]
             # ---- feed forward: out = drop4(x2 + drop3(W2 a + b2)), a = drop2(gelu(z)), z = W1 y2 + b1
-            if p > 0:
+            if pending is not None:
+                dx3, dy16 = pending
+            elif p > 0:
                 dx3, dy16 = ops.dropout_cast(dx, p, saved.seed, self._site(l, 4), self._site(l, 3), want_f32=True)
             else:
                 dx3, dy16 = dx, ops.cast_bf16(dx, ld_out=H)
@@ -194,9 +197,9 @@ class EncoderEngine:
             ops.tc_wgrad(dz16, ls.y2, self._w(f"{pre}.feed_forward.w_1.weight", True), self._w(f"{pre}.feed_forward.w_1.bias", True))
             dy2 = ops.tc_gemm(dz16, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), b_is_kn=True)["f32"]
             dgb2 = m.weights_span(f"{pre}.output_sublayer.norm.weight", f"{pre}.output_sublayer.norm.bias", (2, H), g)
-            dx2 = ops.layernorm_bwd(dy2, ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"), ls.st2, dgb2, d_residual=dx3)
-            # ---- attention: x2 = x + drop1(ctx Wo^T + bo)
-            _, do16 = ops.dropout_cast(dx2, p, saved.seed, 0, self._site(l, 1), want_f32=False)
+            # ---- attention: x2 = x + drop1(ctx Wo^T + bo); the LayerNorm backward also emits do16 = bf16(dx2 * mask1)
+            dx2, do16 = ops.layernorm_bwd_drop(dy2, ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"), ls.st2, dgb2, dx3,
+                                               p, saved.seed, 0, self._site(l, 1))
             ops.tc_wgrad(do16, ls.ctx16, self._w(f"{pre}.attention.output_linear.weight", True),
                          self._w(f"{pre}.attention.output_linear.bias", True))
             if ls.attn_tc:
@@ -215,7 +218,12 @@ class EncoderEngine:
             ops.tc_wgrad(dqkv16, ls.y1, dwqkv, dbqkv)
             dy1 = ops.tc_gemm(dqkv16, wqkv, b_is_kn=True)["f32"]
             dgb1 = m.weights_span(f"{pre}.input_sublayer.norm.weight", f"{pre}.input_sublayer.norm.bias", (2, H), g)
-            dx = ops.layernorm_bwd(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, d_residual=dx2)
+            if l > 0:       # the gradient entering the layer below: its two dropped copies come out of this LayerNorm backward
+                dx, dy16n = ops.layernorm_bwd_drop(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, dx2,
+                                                   p, saved.seed, self._site(l - 1, 4), self._site(l - 1, 3))
+                pending = (dx, dy16n)
+            else:
+                dx = ops.layernorm_bwd(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, d_residual=dx2)
         return dx
 
     # ---------------------------------------------------------------- encoder blocks, strict fp32 path

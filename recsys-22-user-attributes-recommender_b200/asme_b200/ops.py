@@ -231,6 +231,22 @@ def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[t
     return dx
 
 
+def layernorm_bwd_drop(dy, x, gamma, stats, dgb: torch.Tensor, d_residual, p: float, seed: int, site_a: int, site_b: int):
+    """LayerNorm backward fused with the dropout_cast of the next backward stage:
+    returns (dx = (d_residual + LN'(dy)) * mask_a as fp32, bf16(dx * mask_b)); site 0 = no mask"""
+    dy, x = _f32(dy), _f32(x)
+    M, H = x.shape
+    dx = torch.empty_like(x)
+    dx16 = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
+    ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
+    ws = workspace(ws_bytes, x.device)
+    if _lib.timing is not None:
+        _lib.note = f"M={M},H={H},res={int(d_residual is not None)},drop=1"
+    _lib.call("asme_b200_layernorm_bwd_drop", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
+              _p(ws), ws.numel(), float(p), int(seed), int(site_a), int(site_b), _p(dx16), _stream())
+    return dx, dx16
+
+
 # ------------------------------------------------------------------------------------------------
 # dense layers
 # ------------------------------------------------------------------------------------------------

@@ -344,8 +344,11 @@ template <int LANES, int CH>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ stats,
                                                             int M, int H, const float* __restrict__ d_residual,
-                                                            float* __restrict__ dx, float* __restrict__ partials) {
+                                                            float* __restrict__ dx, float* __restrict__ partials,
+                                                            float p_drop, uint64_t seed, uint32_t site_a, uint32_t site_b,
+                                                            __nv_bfloat16* __restrict__ dx16) {
     extern __shared__ float smem[];
+    const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     const int lane = threadIdx.x % LANES;
     const int groups_per_block = blockDim.x / LANES;
     const int group_in_block = threadIdx.x / LANES;
@@ -364,7 +367,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         g.load(dy + r * H, lane);
         ln_backward<LANES, CH>(g, xhat, gamma, lane, H, rstd, dg, db);
         if (d_residual) g.add(d_residual + r * H, lane);
+        // what the next stage of the backward pass consumes, produced here instead of by a separate dropout_cast launch:
+        // dx (fp32) = gradient * mask_a, dx16 = bf16(dx * mask_b)   (site 0 = no mask)
+        if (p_drop > 0.f && site_a) apply_dropout<LANES, CH>(g, asme_seed(seed), site_a, r, H, lane, p_drop, inv_keep);
         g.store(dx + r * H, lane);
+        if (dx16) {
+            if (p_drop > 0.f && site_b) apply_dropout<LANES, CH>(g, asme_seed(seed), site_b, r, H, lane, p_drop, inv_keep);
+            g.store_bf16(dx16 + r * H, lane);
+        }
     }
     float* out = partials + (size_t)blockIdx.x * 2 * H;
     block_reduce_rows<LANES, CH>(dg, smem, out, H, group_in_block, groups_per_block, lane);
@@ -599,9 +609,27 @@ extern "C" size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H) {
     return (size_t)ASME_NUM_SMS * 4 * 2 * H * sizeof(float);
 }
 
+static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
+                              const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop, uint64_t seed,
+                              uint32_t site_a, uint32_t site_b, void* dx_bf16, asme_stream_t stream);
 extern "C" int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M,
                                        int H, const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
                                        asme_stream_t stream) {
+    return layernorm_bwd_impl(dy, x, gamma, stats, M, H, d_residual, dx, dgb, ws, ws_bytes, 0.f, 0ull, 0u, 0u, nullptr, stream);
+}
+// LayerNorm backward that also emits what the next backward stage consumes (replaces a dropout_cast launch):
+// dx (fp32) = (LN gradient + d_residual) * mask(site_a),  dx_bf16 = bf16(dx * mask(site_b));  site 0 = no mask
+extern "C" int asme_b200_layernorm_bwd_drop(const float* dy, const float* x, const float* gamma, const float* stats, int M,
+                                            int H, const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
+                                            float p_drop, uint64_t seed, uint32_t site_a, uint32_t site_b, void* dx_bf16,
+                                            asme_stream_t stream) {
+    ASME_REQUIRE(dx_bf16, "layernorm_bwd_drop: null bf16 output");
+    ASME_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "layernorm_bwd_drop: p=%f out of range", p_drop);
+    return layernorm_bwd_impl(dy, x, gamma, stats, M, H, d_residual, dx, dgb, ws, ws_bytes, p_drop, seed, site_a, site_b, dx_bf16, stream);
+}
+static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
+                              const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop, uint64_t seed,
+                              uint32_t site_a, uint32_t site_b, void* dx_bf16, asme_stream_t stream) {
     ASME_REQUIRE(dy && x && gamma && stats && dx && dgb, "layernorm_bwd: null argument");
     if (M == 0) return ASME_OK;
     const int lanes = lanes_for(H);
@@ -615,7 +643,8 @@ extern "C" int asme_b200_layernorm_bwd(const float* dy, const float* x, const fl
     const size_t smem = (size_t)groups * H * sizeof(float);
 #define CALL(L, C)                                                                                                 \
     layernorm_bwd_kernel<L, C><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, x, gamma, stats, M, H, d_residual, dx, \
-                                                                          partials)
+                                                                          partials, p_drop, seed, site_a, site_b,   \
+                                                                          (__nv_bfloat16*)dx_bf16)
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
