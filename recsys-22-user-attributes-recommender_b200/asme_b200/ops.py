@@ -6,6 +6,7 @@ tensors.  No arithmetic happens in torch on this path and there is no fallback -
 missing library raises.
 """
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -414,7 +415,7 @@ def _bf16(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
-FUSE_LAYERNORM = False     # tc_gemm(ln=...): fuse the LayerNorm into the GEMM epilogue.  Measured: no gain (1.135 vs 1.123 ms per C2 step, 1.99 vs 1.97 ms per C5 step: the epilogue is latency-bound and the separate LayerNorm runs near the HBM roofline) -> off, kept as an option
+FUSE_LAYERNORM = os.environ.get("ASME_B200_FUSE_LN", "0") == "1"     # tc_gemm(ln=...): fuse the LayerNorm into the GEMM epilogue.  Measured: no gain (1.135 vs 1.123 ms per C2 step, 1.99 vs 1.97 ms per C5 step: the epilogue is latency-bound and the separate LayerNorm runs near the HBM roofline) -> off, kept as an option
 
 
 def tc_score_topk(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, target=None, target_score_in=None, v0: int = 0,

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <type_traits>
+#include <string.h>
 
 #include <limits.h>
 
@@ -31,7 +32,18 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 
+static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols,
+                          CUtensorMapSwizzle swz);
 int asme_tc_make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    return make_tmap_bf16(map, base, rows, cols, ld, box_rows, CHUNK_K, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+// 16-column boxes with the 32-byte swizzle: the K tail of operands whose padded width is 64 k + 16 (bias folded into the
+// contraction) -- a quarter of the bytes of a 64-column box
+static int make_tmap_bf16_tail16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    return make_tmap_bf16(map, base, rows, cols, ld, box_rows, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+}
+static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols,
+                          CUtensorMapSwizzle swz) {
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -46,10 +58,10 @@ int asme_tc_make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, l
     ASME_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box_rows=%d", box_rows);
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)CHUNK_K, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         asme_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box_rows=%d)", (int)r, rows, cols,
@@ -146,6 +158,7 @@ enum { EPI_TOPK = 0, EPI_CE = 1, EPI_PROBE = 2 };   // EPI_PROBE: diagnostic, ep
 struct ScoreTcArgs {
     int R, Vloc, v0, k, kch, stages;
     int last_ksteps;             // K-steps (of 16 columns) in the last 64-wide chunk: 4, or fewer when Kp % 64 != 0 (bias columns)
+    int tail16;                  // 1: the last chunk is ONE K-step staged as a 16-column box with the 32-byte swizzle (tmAt / tmBt)
     int n_tiles, tiles_per_split;
     int tile_lo, tile_hi;        // this launch sweeps tiles [split*tps + tile_lo, min(n_tiles, split*tps + tile_hi)) of every split
     int part0;                   // first partial-result slot written by this launch
@@ -247,6 +260,16 @@ __device__ __forceinline__ float max8(const float* v) {
     return fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
 }
 
+// K-major operand chunk of 16 columns staged with the 32-byte swizzle: rows of 32 bytes, 8-row groups 256 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                              // layout type: SWIZZLE_32B
+    return d;
+}
+
 // KC = capacity of the per-thread top-k list (0: no top-k); the first a.k (<= KC) entries are reported
 // PAIR: the CTA and its cluster neighbour (the next row tile) form a cta_group::2 pair -- one M=256 MMA per K-step issued by the
 // even CTA, each CTA staging its own 128 rows of A and its own 128 of the tile's 256 table rows, so that shared memory
@@ -254,7 +277,9 @@ __device__ __forceinline__ float max8(const float* v) {
 // writes 64 KB and reads 96 KB of operands in the 1024 cycles the MMAs need).
 template <int EPI, int KC, bool COUNT, int WGS, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB, const ScoreTcArgs a) {
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmAt,
+                                                                  const __grid_constant__ CUtensorMap tmBt, const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u)   /* pointer arithmetic on the __shared__ array keeps the address space: LDS/STS, not generic LD/ST */;
     const int kch = a.kch, stages = a.stages;
@@ -311,9 +336,11 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             // pair: the leader's barriers count the bytes of both CTAs
-            if (leader) mbar_arrive_expect_tx(&bars->a_full, (PAIR ? 2u : 1u) * (uint32_t)kch * A_CHUNK_BYTES);
+            const uint32_t a_tail_bytes = a.tail16 ? (uint32_t)BM * 32u : (uint32_t)A_CHUNK_BYTES;
+            if (leader) mbar_arrive_expect_tx(&bars->a_full, (PAIR ? 2u : 1u) * ((uint32_t)(kch - 1) * A_CHUNK_BYTES + a_tail_bytes));
             for (int c = 0; c < kch; ++c) {
                 if (PAIR) tma_load_2d_pair(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
+                else if (a.tail16 && c == kch - 1) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmAt, &bars->a_full, c * CHUNK_K, m0);
                 else tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmA, &bars->a_full, c * CHUNK_K, m0);
             }
             int s = 0;                                    // ring slot and its phase, advanced without integer division
@@ -321,8 +348,10 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             for (int t = t0; t < t1; ++t) {
                 for (int c = 0; c < kch; ++c) {
                     mbar_wait(&bars->empty[s], ph ^ 1u);
-                    if (leader) mbar_arrive_expect_tx(&bars->full[s], (uint32_t)B_CHUNK_BYTES);
+                    const bool tail = a.tail16 && c == kch - 1;
+                    if (leader) mbar_arrive_expect_tx(&bars->full[s], tail ? (uint32_t)BN * 32u : (uint32_t)B_CHUNK_BYTES);
                     if (PAIR) tma_load_2d_pair(sB + (size_t)s * B_SLOT_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN + (int)rank * (BN / 2));
+                    else if (tail) tma_load_2d(sB + (size_t)s * B_SLOT_BYTES, &tmBt, &bars->full[s], c * CHUNK_K, t * BN);
                     else tma_load_2d(sB + (size_t)s * B_SLOT_BYTES, &tmB, &bars->full[s], c * CHUNK_K, t * BN);
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
@@ -356,6 +385,10 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                     if (PAIR) {
                         for (int k4 = 0; k4 < ksteps; ++k4) umma_bf16_pair(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, (uint32_t)((c | k4) != 0));
                         umma_commit_pair(&bars->empty[s]);
+                    } else if (a.tail16 && c == kch - 1) {
+                        umma_bf16(d_tmem, smem_desc_sw32(smem_u32(sA + (size_t)c * A_CHUNK_BYTES)),
+                                  smem_desc_sw32(smem_u32(sB + (size_t)s * B_SLOT_BYTES)), idesc, (uint32_t)(c != 0));
+                        umma_commit(&bars->empty[s]);
                     } else {
                         if (ksteps == 4) {
                             umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)(c != 0));
@@ -755,8 +788,9 @@ __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 struct ScorePlan {
-    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps, wgs, pair, grid_x;
+    int m_tiles, n_tiles, splits, tiles_per_split, parts, kch, stages, last_ksteps, wgs, pair, grid_x, tail16;
     size_t smem;
+    CUtensorMap tmAt, tmBt;      // 16-column / 32-byte-swizzle maps of the K tail (tail16 only)
 };
 
 // Tuning knobs (diagnostics; defaults are what the product path uses).  Results do not depend on them.
@@ -767,6 +801,7 @@ static float g_thr_floor = -INFINITY;
 static int g_pair = 0;             // 1: CTA pairs (cta_group::2) whenever there are at least two row tiles; 0: single CTAs.  Measured:
                                    // no gain (the single-CTA pipeline already runs at the power-capped tensor peak, it is not shared-
                                    // memory bound) and the pair couples the two epilogues' jitter -> off by default, kept as a knob
+static int g_tail16 = 1;           // stage a 16-column K tail (Kp = 64 k + 16: folded bias) as a 32-byte-swizzled quarter-size box
 static int g_pdl = 0;              // programmatic dependent launch between the launches of one top-k call
 int g_pdl_merge = 0;            // measured: slower (early-scheduled dependents take SM resources from the sweep) -> off, kept as a knob
 
@@ -778,6 +813,7 @@ extern "C" int asme_b200_tc_score_tune(int knob, int value) {
         case 3: ASME_REQUIRE(value == 2 || value == 4, "tc_score_tune: epilogue warpgroups must be 2 or 4"); g_epi_wgs_other = value; break;
         case 4: g_pair = value ? 1 : 0; break;
         case 5: g_pdl = g_pdl_merge = value ? 1 : 0; break;
+        case 6: g_tail16 = value ? 1 : 0; break;
         default: ASME_REQUIRE(false, "tc_score_tune: unknown knob %d", knob);
     }
     return ASME_OK;
@@ -788,10 +824,12 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
     ASME_REQUIRE(Kp >= 16 && Kp <= 272 && Kp % 16 == 0, "tc score: padded hidden size %d unsupported (multiple of 16, <= 272)", Kp);
     p->kch = ceil_div(Kp, CHUNK_K);
     p->last_ksteps = (Kp % CHUNK_K) ? (Kp % CHUNK_K) / UMMA_K : CHUNK_K / UMMA_K;
+    p->tail16 = 0;
     p->m_tiles = ceil_div(R, BM);
     p->n_tiles = ceil_div(Vloc, BN);
     p->pair = (g_pair && p->m_tiles >= 2) ? 1 : 0;
     p->grid_x = p->pair ? (p->m_tiles + 1) / 2 * 2 : p->m_tiles;      // an odd last row tile is paired with an empty one
+    p->tail16 = (g_tail16 && !p->pair && Kp % CHUNK_K == 16 && Kp > 16) ? 1 : 0;
     int splits = ASME_NUM_SMS / p->grid_x;
     if (splits < 1) splits = 1;
     if (splits > p->n_tiles) splits = p->n_tiles;
@@ -829,6 +867,17 @@ static int tc_set_smem(K kernel, size_t bytes) {
     return ASME_OK;
 }
 
+static int make_tail_maps(ScorePlan* p, const void* Hb, int R, const void* Wb, int Vloc, int Kp) {
+    if (!p->tail16) {
+        memset(&p->tmAt, 0, sizeof(CUtensorMap));
+        memset(&p->tmBt, 0, sizeof(CUtensorMap));
+        return ASME_OK;
+    }
+    int rc = make_tmap_bf16_tail16(&p->tmAt, Hb, R, Kp, Kp, BM);
+    if (rc) return rc;
+    return make_tmap_bf16_tail16(&p->tmBt, Wb, Vloc, Kp, Kp, BN);
+}
+
 template <int EPI, int KC, bool COUNT, int WGS, bool PAIR>
 static int launch_score_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreTcArgs& a, const ScorePlan& p, cudaStream_t st,
                             bool pdl) {
@@ -849,7 +898,7 @@ static int launch_score_one(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
-    ASME_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, a));
+    ASME_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p.tmAt, p.tmBt, a));
     asme_count_launch();
     return ASME_OK;
 }
@@ -908,10 +957,12 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     if (rc) return rc;
     rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, p.pair ? BN / 2 : BN);
     if (rc) return rc;
+    rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
+    if (rc) return rc;
     const int n_sample = topk ? sample_tiles(p) : 0;
     const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
     a.bias = bias; a.target = target; a.target_score = target_score_in; a.thr_floor = g_thr_floor;
     a.pv = (float*)ws;
@@ -958,8 +1009,10 @@ extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, 
     if (rc) return rc;
     rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, p.pair ? BN / 2 : BN);
     if (rc) return rc;
+    rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
+    if (rc) return rc;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.k = read_tmem ? 1 : 0;
+    a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.k = read_tmem ? 1 : 0;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_lo = 0; a.tile_hi = p.tiles_per_split;
     return launch_score<EPI_PROBE, 0, false>(tmA, tmB, a, p, (cudaStream_t)stream);
 }
@@ -989,8 +1042,10 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     if (rc) return rc;
     rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, p.pair ? BN / 2 : BN);
     if (rc) return rc;
+    rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
+    if (rc) return rc;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
     a.bias = bias; a.target = target; a.target_score = nullptr; a.thr_floor = -INFINITY;
     a.pv = (float*)ws;
