@@ -83,6 +83,12 @@ typedef struct {
     const int64_t* user_ids[ASME_MAX_ATTR];  /* (B) each */
     const float* user_table[ASME_MAX_ATTR];  /* (Vu,H) */
     const float* seg_table;
+    /* forward only: the first encoder block's input LayerNorm (transformer_layers.py:120-130) applied to the output rows in the
+     * same pass: next_out (T,H) bf16 = LN(out; next_gamma, next_beta), next_stats (2,T) = row mean / rstd or NULL */
+    const float* next_gamma;                 /* (H) or NULL */
+    const float* next_beta;
+    void* next_out;
+    float* next_stats;
 } asme_embed_desc;
 
 int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* out /*T,H*/,

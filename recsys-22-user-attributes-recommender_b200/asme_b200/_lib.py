@@ -28,6 +28,7 @@ class EmbedDesc(Structure):
         ("p_drop", c_float), ("seed", c_uint64), ("site_a", c_uint32), ("site_b", c_uint32),
         ("n_user", c_int), ("user_ids", c_void_p * ASME_MAX_ATTR), ("user_table", c_void_p * ASME_MAX_ATTR),
         ("seg_table", c_void_p),
+        ("next_gamma", c_void_p), ("next_beta", c_void_p), ("next_out", c_void_p), ("next_stats", c_void_p),
     ]
 
 

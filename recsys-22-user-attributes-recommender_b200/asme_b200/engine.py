@@ -109,8 +109,16 @@ class EncoderEngine:
         return getattr(self.m, "precision", "fp32") == "bf16" and cfg.hidden % 64 == 0 and cfg.intermediate % 64 == 0
 
     # ---------------------------------------------------------------- encoder blocks, tensor-core path
+    def first_norm(self):
+        """(gamma, beta) of the first block's input LayerNorm when the tensor-core path runs: the embedding kernel applies it
+        in the same pass (``blocks_forward(first_ln=...)``); None on the fp32 path"""
+        if not self.use_tc() or self.cfg.layers == 0:
+            return None
+        pre = f"{self.blocks}.0"
+        return self._w(f"{pre}.input_sublayer.norm.weight"), self._w(f"{pre}.input_sublayer.norm.bias")
+
     def _blocks_forward_tc(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None,
-                           one_per_sequence: bool = False) -> torch.Tensor:
+                           one_per_sequence: bool = False, first_ln=None) -> torch.Tensor:
         """``select_rows`` (evaluation only): flat indices of the positions whose hidden state is needed.  Every layer but the
         last runs on all tokens; in the last layer only K and V depend on the other positions, so everything after the attention
         (output projection, LayerNorm, feed-forward: ~half of the layer) runs on the selected rows alone.  The selected rows are
@@ -121,7 +129,9 @@ class EncoderEngine:
         p = cfg.dropout if train else 0.0
         pa = cfg.attention_dropout if train else 0.0
         B, S = saved.B, saved.S
-        y1_next = st1_next = None      # LayerNorm of the next layer's input, produced by this layer's last GEMM epilogue
+        # LayerNorm of the coming layer's input when it was already produced upstream (by the embedding kernel for layer 0, by the
+        # previous layer's last GEMM epilogue when that fusion is on)
+        y1_next, st1_next = first_ln if first_ln is not None else (None, None)
         for l in range(cfg.layers):
             pre = f"{self.blocks}.{l}"
             ls = LayerSaved()
@@ -228,10 +238,10 @@ class EncoderEngine:
 
     # ---------------------------------------------------------------- encoder blocks, strict fp32 path
     def blocks_forward(self, x: torch.Tensor, saved: Saved, select_rows: Optional[torch.Tensor] = None,
-                       one_per_sequence: bool = False) -> torch.Tensor:
+                       one_per_sequence: bool = False, first_ln=None) -> torch.Tensor:
         if self.use_tc():
             saved.extra["tc"] = True
-            return self._blocks_forward_tc(x, saved, select_rows, one_per_sequence)
+            return self._blocks_forward_tc(x, saved, select_rows, one_per_sequence, first_ln)
         if select_rows is not None:
             raise RuntimeError("row-selective encoding is implemented by the tensor-core path only")
         cfg, m = self.cfg, self.m

@@ -226,8 +226,8 @@ class TransformerRecommenderModel(ArenaModule):
             B, S = seq.shape
             S += self.user_prefix
             saved = Saved(B=B, S=S, seed=0, training=False, key_valid=self._key_valid(padding_mask, seq))
-            x, _ = ops.embed_fwd(self._embed_spec(seq, attrs, False, 0), B, S)
-            return self.engine.blocks_forward(x, saved, select_rows=rows, one_per_sequence=one_per_sequence)
+            x, _, y16, st = ops.embed_fwd(self._embed_spec(seq, attrs, False, 0), B, S, next_ln=self.engine.first_norm())
+            return self.engine.blocks_forward(x, saved, select_rows=rows, one_per_sequence=one_per_sequence, first_ln=(y16, st))
         hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
         return ops.gather_rows(hidden, rows)
 
@@ -250,8 +250,13 @@ class TransformerRecommenderModel(ArenaModule):
         saved.extra["attrs"] = attrs
         spec = self._embed_spec(seq, attrs, training, saved.seed)
         saved.embed_spec = spec
-        x, saved.embed_stats = ops.embed_fwd(spec, B, S, save_stats=training)
-        x = self.engine.blocks_forward(x, saved)
+        nxt = self.engine.first_norm()
+        if nxt is not None:      # tensor-core path: the first block's input LayerNorm is computed by the embedding kernel
+            x, saved.embed_stats, y16, st = ops.embed_fwd(spec, B, S, save_stats=training, next_ln=nxt, next_stats=training)
+            x = self.engine.blocks_forward(x, saved, first_ln=(y16, st))
+        else:
+            x, saved.embed_stats = ops.embed_fwd(spec, B, S, save_stats=training)
+            x = self.engine.blocks_forward(x, saved)
         if self.postfusion:
             if self.user_prefix:
                 raise NotImplementedError("post-fusion attributes together with user attributes")

@@ -117,16 +117,27 @@ class EmbedSpec:
         return d
 
 
-def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False):
-    """S counts the user position when ``spec.users`` is not empty (item ids are then (B, S-1))."""
+def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False, next_ln=None, next_stats: bool = False):
+    """S counts the user position when ``spec.users`` is not empty (item ids are then (B, S-1)).
+    ``next_ln=(gamma, beta)``: also returns (y16, st) = the following LayerNorm of the output rows as bf16 and, with
+    ``next_stats``, its (2,T) row statistics -- the first encoder block's input norm, computed in the same pass."""
     H = spec.item_table.shape[1]
     T = B * S
     out = torch.empty(T, H, dtype=torch.float32, device=spec.item_table.device)
     stats = torch.empty(4, T, dtype=torch.float32, device=out.device) if save_stats else None
     d = spec.desc()
+    y16 = st = None
+    if next_ln is not None:
+        g, b = _f32(next_ln[0]), _f32(next_ln[1])
+        y16 = torch.empty(T, H, dtype=torch.bfloat16, device=out.device)
+        st = torch.empty(2, T, dtype=torch.float32, device=out.device) if next_stats else None
+        d.next_gamma, d.next_beta, d.next_out = g.data_ptr(), b.data_ptr(), y16.data_ptr()
+        d.next_stats = None if st is None else st.data_ptr()
     if _lib.timing is not None:
         _lib.note = f"T={T},H={H},tables={1 + (spec.pos_table is not None) + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)},ids={1 + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)}"
     _lib.call("asme_b200_embed_fwd", ctypes.byref(d), T, S, H, _p(out), _p(stats), _stream())
+    if next_ln is not None:
+        return out, stats, y16, st
     return out, stats
 
 

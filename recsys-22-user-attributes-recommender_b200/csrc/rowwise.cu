@@ -241,6 +241,14 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d,
             if (d.p_drop > 0.f) apply_dropout<LANES, CH>(x, asme_seed(d.seed), d.site_b, t, H, lane, d.p_drop, inv_keep);
         }
         if (ok) x.store(out + t * H, lane);
+        if (d.next_gamma) {      // the first encoder block's input LayerNorm rides along: y16 = LN(x) as bf16 (+ row statistics)
+            float mean, rstd;
+            ln_forward<LANES, CH>(x, y, d.next_gamma, d.next_beta, lane, H, mean, rstd);
+            if (ok) {
+                if (d.next_stats && lane == 0) { d.next_stats[t] = mean; d.next_stats[(size_t)T + t] = rstd; }
+                y.store_bf16(reinterpret_cast<__nv_bfloat16*>(d.next_out) + t * H, lane);
+            }
+        }
     }
 }
 
