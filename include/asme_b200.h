@@ -381,6 +381,23 @@ int asme_b200_step_state_advance(void* state, asme_stream_t stream);
 int asme_b200_adam_step_dev(float* param, const float* grad, float* m, float* v, long long n, const void* state, double beta1,
                             double beta2, double eps, double weight_decay, asme_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input pipeline on the GPU.  Ids are int64 (B,S), right-padded with pad_id, as the reference's collate
+ * delivers them (data/collate.py:42-110).  Streams are counter-based (seed, sequence, position): same distribution and
+ * invariants as the reference's processors, not the same draws (those come from Python's global generator).
+ *   cloze_mask      data/datasets/processors/cloze_mask.py:50-92: with probability only_last_prob only the last item of a sequence is
+ *                   masked; otherwise every item is selected with probability mask_prob and then replaced by the MASK id (80 %), a
+ *                   uniform random id in [0, vocab-2] (10 %; Tensor.random_ excludes its upper end) or kept (10 %); target = original item at selected positions, pad_id
+ *                   elsewhere.  Feature 0 is the item sequence; further sequence features are masked at the same positions.
+ *   pos_neg_sample  data/datasets/processors/pos_neg_sampler.py:41-114: x = seq[:-1], pos = seq[1:], neg = uniform over the
+ *                   vocabulary minus the n_special lowest ids minus the tokens of the sequence (with replacement); outputs (B,S-1).
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_cloze_mask(int B, int S, int n_feat, const int64_t* const* in, int64_t* const* out, const int64_t* mask_id,
+                         const int64_t* vocab, int64_t* target, int64_t pad_id, float mask_prob, float only_last_prob,
+                         uint64_t seed, asme_stream_t stream);
+int asme_b200_pos_neg_sample(const int64_t* seq, int B, int S, int64_t V, int n_special, int64_t pad_id, uint64_t seed,
+                             int64_t* x, int64_t* pos, int64_t* neg, asme_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

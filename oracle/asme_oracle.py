@@ -376,6 +376,53 @@ def usasrec_full_logits(w: Weights, seq, attrs, heads, layers, additional=(), us
 
 
 # --------------------------------------------------------------------------------------------
+# 8f row 2  input pipeline                           data/datasets/processors/cloze_mask.py:50-92
+#                                                    data/datasets/processors/pos_neg_sampler.py:41-114
+# Per-sample restatements that draw from torch's global CPU generator exactly as the reference does
+# (data/datasets/processors/utils.py:29-50), so the reference's own seeded golden vectors pin them.
+# --------------------------------------------------------------------------------------------
+def _random_uniform() -> float:
+    return torch.empty((), dtype=torch.float, device="cpu").uniform_(0.0, 1.0).item()
+
+
+def _random_int(start: int, end: int) -> int:
+    """utils.py:41-50 -- documented as inclusive, but Tensor.random_(from, to) excludes `to`"""
+    return torch.empty((), dtype=torch.int, device="cpu").random_(start, end).item()
+
+
+def cloze_mask_sequence(sequence: Sequence[int], mask_prob: float, only_last_item_mask_prob: float, vocab_size: int,
+                        mask_id: int = MASK_ID, pad_id: int = PAD_ID) -> Tuple[List[int], List[int]]:
+    """(masked sequence, target) of ONE un-padded item sequence, cloze_mask.py:50-92"""
+    seq = list(sequence)
+    target = list(sequence)
+    if _random_uniform() <= only_last_item_mask_prob:
+        last = len(seq) - 1
+        seq[last] = mask_id
+        target[:last] = [pad_id] * last
+        return seq, target
+    for index in range(len(seq)):
+        prob = _random_uniform()
+        if prob < mask_prob:
+            prob = prob / mask_prob
+            if prob < 0.8:
+                seq[index] = mask_id
+            elif prob < 0.9:
+                seq[index] = _random_int(0, vocab_size - 1)
+        else:
+            target[index] = pad_id
+    return seq, target
+
+
+def pos_neg_sequence(sequence: Sequence[int], vocab_size: int, special_ids: Sequence[int] = (PAD_ID, MASK_ID, 2)):
+    """(x, pos, neg) of ONE un-padded item sequence, pos_neg_sampler.py:41-63, :86-101"""
+    weights = torch.ones([vocab_size])
+    weights[list(special_ids)] = 0.0
+    weights[list(set(sequence))] = 0.0
+    neg = torch.multinomial(weights, num_samples=len(sequence) - 1, replacement=True).tolist()
+    return list(sequence[:-1]), list(sequence[1:]), neg
+
+
+# --------------------------------------------------------------------------------------------
 # a15-a18  ranking metrics (integer / index work: numpy)
 #          metrics/container/metrics_sampler.py:45-71, metrics/common.py:4-175, metrics/mrr.py:21-37
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,133 @@
+"""GPU input pipeline against the oracle's restatements of the reference processors
+(data/datasets/processors/cloze_mask.py:50-92, pos_neg_sampler.py:41-114): same invariants on every sample, same distribution over
+many samples (the reference's draws come from torch's global generator and cannot be reproduced on the device)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import asme_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(gen, B, S, V, min_len=2):
+    seq = torch.randint(3, V, (B, S), generator=gen)
+    lengths = torch.randint(min_len, S + 1, (B,), generator=gen)
+    seq[torch.arange(S).unsqueeze(0) >= lengths.unsqueeze(1)] = 0
+    return seq, lengths
+
+
+def test_cloze_mask_invariants_and_distribution():
+    from asme_b200 import input_pipeline as ip
+    gen = torch.Generator().manual_seed(0)
+    B, S, V, VC, p, p_last = 4096, 60, 500, 40, 0.3, 0.15
+    seq, lengths = make_batch(gen, B, S, V)
+    cat = torch.randint(3, VC, (B, S), generator=gen)
+    cat[seq == 0] = 0
+    batch = {"item": seq.cuda(), "cat": cat.cuda()}
+    out = ip.cloze_mask(batch, {"item": V, "cat": VC}, p, p_last, seed=7, masking_targets=["item", "cat"])
+    x, c, t = out["item"].cpu(), out["cat"].cpu(), out["item.target"].cpu()
+    valid = seq != 0
+    sel = t != 0
+    # invariants of cloze_mask.py:50-92 on every sample
+    assert not (sel & ~valid).any()                                   # padding is never selected
+    assert torch.equal(t[sel], seq[sel])                               # the target is the original item
+    assert torch.equal(x[~sel], seq[~sel]) and torch.equal(c[~sel], cat[~sel])          # nothing else changes
+    masked = sel & (x == 1) & (c == 1)                                 # all masking targets are masked at the same positions
+    # (a random replacement may hit the MASK id in one feature only: 1 / (V - 1) of the 10 % branch)
+    assert float(((sel & (x == 1)) ^ (sel & (c == 1))).float().sum()) < 0.01 * float(masked.float().sum())
+    rnd_x, rnd_c = sel & (x != seq) & (x != 1), sel & (c != cat) & (c != 1)
+    assert int(x[rnd_x].max()) <= V - 2 and int(c[rnd_c].max()) <= VC - 2   # random ids come from [0, len - 2]
+    # sequences in "last item only" mode: exactly one selected position, the last real one, and it is a MASK
+    n_sel = sel.sum(1)
+    last_only = (n_sel == 1) & sel[torch.arange(B), lengths - 1] & (x[torch.arange(B), lengths - 1] == 1)
+    # distribution against the oracle's per-sample restatement (torch CPU generator) on the same sequences
+    torch.manual_seed(123)
+    o_sel = o_mask = o_keep = o_valid = o_last = 0
+    for b in range(1024):
+        n = int(lengths[b])
+        s_o, t_o = O.cloze_mask_sequence(seq[b, :n].tolist(), p, p_last, V)
+        sel_o = [v != 0 for v in t_o]
+        one_last = sum(sel_o) == 1 and sel_o[-1] and s_o[-1] == 1
+        o_last += one_last
+        if not one_last:
+            o_sel += sum(sel_o)
+            o_valid += n
+            o_mask += sum(1 for v, f in zip(s_o, sel_o) if f and v == 1)
+            o_keep += sum(1 for v, w, f in zip(s_o, seq[b, :n].tolist(), sel_o) if f and v == w)
+    normal = ~last_only
+    g_valid = int(valid[normal].sum())
+    g_sel = int(sel[normal].sum())
+    g_mask = int(masked[normal].sum())
+    g_keep = int((sel & (x == seq))[normal].sum())
+    assert abs(float(last_only.float().mean()) - o_last / 1024) < 0.04          # ~ p_last (+ the single-selection coincidences)
+    assert abs(g_sel / g_valid - o_sel / o_valid) < 0.02                         # ~ mask_prob
+    assert abs(g_mask / g_sel - o_mask / o_sel) < 0.02                           # ~ 0.8
+    assert abs(g_keep / g_sel - o_keep / o_sel) < 0.02                           # ~ 0.1 (+ random ids that hit the original)
+    assert abs(g_sel / g_valid - p) < 0.01 and abs(g_mask / g_sel - 0.8) < 0.01
+    # pure function of the seed
+    again = ip.cloze_mask(batch, {"item": V, "cat": VC}, p, p_last, seed=7, masking_targets=["item", "cat"])
+    assert torch.equal(again["item"], out["item"]) and torch.equal(again["item.target"], out["item.target"])
+    other = ip.cloze_mask(batch, {"item": V, "cat": VC}, p, p_last, seed=8, masking_targets=["item", "cat"])
+    assert not torch.equal(other["item"], out["item"])
+
+
+def test_cloze_mask_last_item_only_matches_reference_golden_vector():
+    """tests/test_cloze_mask.py:9-21 of the reference: probability 1 of masking only the last item"""
+    from asme_b200 import input_pipeline as ip
+    seq = torch.tensor([[5, 8, 9, 7, 3, 4, 0, 0], [3, 0, 0, 0, 0, 0, 0, 0]])
+    out = ip.cloze_mask({"item": seq.cuda()}, {"item": 13}, 1.0, 1.0, seed=1)
+    assert out["item"].cpu().tolist() == [[5, 8, 9, 7, 3, 1, 0, 0], [1, 0, 0, 0, 0, 0, 0, 0]]
+    assert out["item.target"].cpu().tolist() == [[0, 0, 0, 0, 0, 4, 0, 0], [3, 0, 0, 0, 0, 0, 0, 0]]
+
+
+def test_pos_neg_sample_invariants_and_distribution():
+    from asme_b200 import input_pipeline as ip
+    gen = torch.Generator().manual_seed(1)
+    B, S1, V = 2048, 51, 300
+    seq, lengths = make_batch(gen, B, S1, V)
+    out = ip.pos_neg_sample({"item": seq.cuda()}, V, seed=3)
+    x, pos, neg = out["item"].cpu(), out["positive_samples"].cpu(), out["negative_samples"].cpu()
+    S = S1 - 1
+    inside = torch.arange(S).unsqueeze(0) < (lengths - 1).unsqueeze(1)
+    # pos_neg_sampler.py:96-101: x = seq[:-1], pos = seq[1:], padded to the batch shape
+    assert torch.equal(x[inside], seq[:, :-1][inside]) and torch.equal(pos[inside], seq[:, 1:][inside])
+    assert (x[~inside] == 0).all() and (pos[~inside] == 0).all() and (neg[~inside] == 0).all()
+    # :44-54: negatives are never special tokens and never a token of their own sequence
+    assert int(neg[inside].min()) >= 3 and int(neg[inside].max()) < V
+    clash = (neg.unsqueeze(2) == seq.unsqueeze(1)).any(dim=2) & inside
+    assert not clash.any()
+    # uniform over the allowed ids: compare the histogram with the oracle's multinomial on the same sequences
+    torch.manual_seed(5)
+    ref = []
+    for b in range(512):
+        n = int(lengths[b])
+        ref += O.pos_neg_sequence(seq[b, :n].tolist(), V)[2]
+    g = neg[:512][inside[:512]].numpy()
+    hist_g = np.bincount(g, minlength=V) / len(g)
+    hist_o = np.bincount(np.array(ref), minlength=V) / len(ref)
+    assert len(g) == len(ref)
+    assert np.abs(hist_g - hist_o).max() < 0.004 and abs(g.mean() - np.mean(ref)) < 3.0
+    assert torch.equal(ip.pos_neg_sample({"item": seq.cuda()}, V, seed=3)["negative_samples"].cpu(), neg)
+
+
+def test_pipeline_feeds_the_training_modules():
+    """GPU cloze masking -> MaskedTrainingModule.training_step; GPU negative sampling -> SequenceNextItemPredictionTrainingModule"""
+    from asme_b200 import input_pipeline as ip
+    from asme_b200.models import BERT4RecModel, SASRecModel
+    from asme_b200.modules import MaskedTrainingModule, SequenceNextItemPredictionTrainingModule
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(2)
+    V, S, B = 400, 32, 64
+    seq, _ = make_batch(gen, B, S, V)
+    batch = ip.cloze_mask({"item": seq.cuda()}, {"item": V}, 0.2, 0.1, seed=11)
+    module = MaskedTrainingModule(BERT4RecModel(64, 2, 1, V, S, 0.1).cuda().train(), num_warmup_steps=0)
+    loss = module.training_step(batch, 0)["loss"]
+    loss.backward()
+    assert torch.isfinite(loss) and 4.0 < float(loss) < 8.0
+    seq1, _ = make_batch(gen, B, S + 1, V)
+    nb = ip.pos_neg_sample({"item": seq1.cuda()}, V, seed=12)
+    module = SequenceNextItemPredictionTrainingModule(SASRecModel(64, 2, 1, V, S, 0.1, mode="neg_sampling").cuda().train())
+    loss = module.training_step(nb, 0)["loss"]
+    loss.backward()
+    assert torch.isfinite(loss)

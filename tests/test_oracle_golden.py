@@ -185,3 +185,24 @@ def test_attention_fully_masked_rows_are_uniform():
     out = O.multi_head_attention(x, w, "a", heads, O.attention_mask(pm, b, s, True))
     v = x @ w["a.linear_layers.2.weight"].t() + w["a.linear_layers.2.bias"]
     torch.testing.assert_close(out, v.mean(dim=1, keepdim=True).expand(-1, s, -1), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# input pipeline: the oracle's per-sample restatements draw from torch's global generator in the
+# reference's order, so the reference's own seeded golden vectors pin them exactly
+# ------------------------------------------------------------------------------------------------------------
+def test_cloze_mask_golden_vectors_of_the_reference():
+    """/root/reference/tests/test_cloze_mask.py:9-37 (seed_everything(42), example vocabulary of 13 tokens)"""
+    torch.manual_seed(42)
+    seq, tgt = O.cloze_mask_sequence([5, 8, 9, 7, 3, 4], 1.0, 1.0, 13)
+    assert seq == [5, 8, 9, 7, 3, 1] and tgt == [0, 0, 0, 0, 0, 4]
+    torch.manual_seed(42)
+    seq, tgt = O.cloze_mask_sequence([5, 8, 9, 7, 3, 4, 12, 10, 11, 3], 0.5, 0.1, 13)
+    assert seq == [5, 1, 9, 1, 3, 1, 12, 10, 1, 3] and tgt == [0, 8, 0, 7, 0, 4, 0, 0, 11, 0]
+
+
+def test_pos_neg_sampler_golden_vector_of_the_reference():
+    """/root/reference/tests/test_pos_neg.py:9-24"""
+    torch.manual_seed(42)
+    x, pos, neg = O.pos_neg_sequence([5, 8, 9, 7, 3, 4], 13)
+    assert x == [5, 8, 9, 7, 3] and pos == [8, 9, 7, 3, 4] and neg == [6, 6, 6, 6, 11]
