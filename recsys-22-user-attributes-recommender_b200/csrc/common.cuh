@@ -90,9 +90,14 @@ __device__ __forceinline__ float exp2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {      // one MUFU.RCP (__frcp_rn is a Newton step plus a slow-path call)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // returns erf(|x|) given e = exp(-x*x)
 __device__ __forceinline__ float erf_abs_fast(float ax, float e) {
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));       // argument >= 1: no denormal / overflow cases
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
