@@ -398,6 +398,12 @@ int asme_b200_cloze_mask(int B, int S, int n_feat, const int64_t* const* in, int
 int asme_b200_pos_neg_sample(const int64_t* seq, int B, int S, int64_t V, int n_special, int64_t pad_id, uint64_t seed,
                              int64_t* x, int64_t* pos, int64_t* neg, asme_stream_t stream);
 
+/* Negatives for sampled ranking metrics (metrics/container/metrics_sampler.py:140-204): for every user n_samples DISTINCT items drawn
+ * from the item weights (cdf = cumulative sum of the weights, float64, (V)) with the user's target and all items of the input
+ * sequence (B,S) excluded.  *failed is set to 1 when a user has fewer than n_samples admissible items. */
+int asme_b200_weighted_negatives(const double* cdf, int V, const int64_t* input_seq, int S, const int64_t* targets, int B,
+                                 int n_samples, uint64_t seed, int64_t* out, int* failed, asme_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

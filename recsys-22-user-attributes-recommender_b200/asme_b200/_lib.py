@@ -91,6 +91,7 @@ _PROTOTYPES = {
     "asme_b200_tc_attn_tune": (c_int, [c_int, c_int]),
     "asme_b200_tc_gemm_tune": (c_int, [c_int, c_int]),
     "asme_b200_cloze_mask": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int64, c_float, c_float, c_uint64, P]),
+    "asme_b200_weighted_negatives": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_uint64, P, P, P]),
     "asme_b200_pos_neg_sample": (c_int, [P, c_int, c_int, c_int64, c_int, c_int64, c_uint64, P, P, P, P]),
     "asme_b200_tc_score_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),

@@ -175,8 +175,16 @@ class FusedPredictions:
     target rank and the top-k list, produced inside the scoring kernel (the logits never reached HBM)."""
 
     def __init__(self, rank: torch.Tensor, topk_idx: torch.Tensor, topk_val: torch.Tensor, target_score: torch.Tensor,
-                 num_items: int):
+                 num_items: int, scorer=None):
         self.rank, self.topk_idx, self.topk_val, self.target_score, self.num_items = rank, topk_idx, topk_val, target_score, num_items
+        # scorer(items (N,I) int64) -> (N,I) fp32 scores of chosen items for the same rows: what the item-subset samplers gather
+        self.scorer = scorer
+
+    def gather(self, dim: int, items: torch.Tensor) -> torch.Tensor:
+        """``predictions.gather(1, items)`` of the dense tensor this object stands for"""
+        if dim != 1 or self.scorer is None:
+            raise RuntimeError("asme_b200: this evaluation step carries no item scorer (sampled / fixed-subset metrics need one)")
+        return self.scorer(items)
 
     def size(self):
         return torch.Size([self.rank.shape[0], self.num_items])
@@ -201,6 +209,58 @@ class AllItemsSampler:
 
     def suffix_metric_name(self) -> str:
         return ""
+
+
+class FixedItemsSampler:
+    """metrics_sampler.py:74-107 -- only the configured items are candidates (single-target recommendation)"""
+
+    def __init__(self, fixed_items: List[int]):
+        self.fixed_items = list(fixed_items)
+
+    def sample(self, input_seq, targets, predictions, mask=None) -> MetricsSample:
+        if targets.dim() != 1:
+            raise NotImplementedError("basket targets are outside the B200 hot path")
+        items = torch.tensor(self.fixed_items, dtype=torch.int64, device=targets.device).unsqueeze(0).repeat(targets.shape[0], 1)
+        sampled = predictions.gather(1, items)
+        positive = items.eq(targets.unsqueeze(1)).to(dtype=sampled.dtype)
+        return MetricsSample(sampled, positive, None)
+
+    def suffix_metric_name(self) -> str:
+        return "_fixed"
+
+
+class NegativeMetricsSampler:
+    """metrics_sampler.py:140-204 -- the target plus ``sample_size`` negatives drawn (without replacement) from the item weights,
+    never the target nor an item of the input sequence.  The draw runs on the GPU (csrc/pipeline.cu) from the library's
+    counter-based generator: same distribution, not the same draws as torch.multinomial."""
+
+    def __init__(self, weights: List[float], sample_size: int, metrics_suffix: str, seed: int = 0):
+        self.weights = weights
+        self.sample_size = int(sample_size)
+        self.metrics_suffix = metrics_suffix
+        self.seed = int(seed)
+        self._calls = 0
+        self._cdf = None
+
+    def _cdf_on(self, device):
+        if self._cdf is None or self._cdf.device != device:
+            self._cdf = torch.cumsum(torch.as_tensor(self.weights, dtype=torch.float64), 0).to(device)
+        return self._cdf
+
+    def sample(self, input_seq, targets, predictions, mask=None) -> MetricsSample:
+        if targets.dim() != 1 or input_seq.dim() != 2:
+            raise NotImplementedError("basket inputs / targets are outside the B200 hot path")
+        self._calls += 1
+        negatives, failed = ops.weighted_negatives(self._cdf_on(targets.device), input_seq, targets, self.sample_size,
+                                                   (self.seed << 32) + self._calls)
+        items = torch.cat([targets.unsqueeze(1), negatives], dim=1)
+        sampled = predictions.gather(1, items)
+        positive = items.eq(targets.unsqueeze(1)).to(dtype=sampled.dtype)
+        self.last_failed = failed          # device flag: a user had fewer admissible items than sample_size (torch.multinomial raises)
+        return MetricsSample(sampled, positive, torch.ones_like(items))
+
+    def suffix_metric_name(self) -> str:
+        return self.metrics_suffix
 
 
 class MetricsContainer(nn.Module):

@@ -443,6 +443,12 @@ class TransformerRecommenderModel(ArenaModule):
             rows_one_per_sequence = True
         h_rows = self.encode_rows(seq, padding_mask, attrs, rows, one_per_sequence=rows_one_per_sequence)
         m_rows, _ = self.modify(h_rows)
+        out = self._evaluate_rows(m_rows, target, k, with_loss, pad_id, full_rank)
+        # scores of chosen items for the same rows (fp32): item-subset samplers gather these instead of dense logits
+        out["scorer"] = lambda items, rows_=m_rows: ops.score_items(rows_, *self.projection_operands(), items)
+        return out
+
+    def _evaluate_rows(self, m_rows, target, k, with_loss, pad_id, full_rank):
         if self.precision == "bf16":
             wb, folded = self.projection_operands_folded()
             b = None

@@ -198,7 +198,8 @@ class MaskedTrainingModule(_ModuleBase):
                                        pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_TEST_LOSS if is_test else LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
-        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
+                                scorer=out.get("scorer"))
         return build_eval_step_return_dict(seq, pred, targets)
 
     def validation_step(self, batch, batch_idx):
@@ -268,7 +269,8 @@ class NextItemPredictionTrainingModule(_ModuleBase):
                                        full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
-        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
+                                scorer=out.get("scorer"))
         return build_eval_step_return_dict(seq, pred, target)
 
     def test_step(self, batch, batch_idx):
@@ -320,7 +322,8 @@ class SequenceNextItemPredictionTrainingModule(_ModuleBase):
             return build_eval_step_return_dict(seq, self.predict_step(batch, batch_idx), targets)
         out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), targets, k=self._eval_k(),
                                        select="last", full_rank=self._full_rank())
-        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
+                                scorer=out.get("scorer"))
         return build_eval_step_return_dict(seq, pred, targets)
 
     def test_step(self, batch, batch_idx):
@@ -383,7 +386,8 @@ class UBERTMaskedTrainingModule(MaskedTrainingModule):
                                        full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_TEST_LOSS if is_test else LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
-        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
+                                scorer=out.get("scorer"))
         return build_eval_step_return_dict(seq, pred, targets)
 
 
@@ -439,7 +443,8 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
                                        pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
-        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
+                                scorer=out.get("scorer"))
         return build_eval_step_return_dict(seq, pred, target)
 
 

@@ -367,6 +367,27 @@ def score_targets(h: torch.Tensor, w: torch.Tensor, bias, target: torch.Tensor, 
     return out
 
 
+def score_items(h: torch.Tensor, w: torch.Tensor, bias, items: torch.Tensor) -> torch.Tensor:
+    """scores of chosen catalog items: out[n, i] = h[n] . w[items[n, i]] (+ bias[items[n, i]]), fp32 -- what a sampled metric needs
+    instead of dense (N,V) logits (metrics/container/metrics_sampler.py:74-204 gather them from the dense tensor)"""
+    items = _i64(items)
+    N, I = items.shape
+    rows = torch.arange(N, device=h.device, dtype=torch.int64).repeat_interleave(I)
+    return score_targets(gather_rows(_f32(h), rows), w, bias, items.reshape(-1)).view(N, I)
+
+
+def weighted_negatives(cdf: torch.Tensor, input_seq: torch.Tensor, targets: torch.Tensor, n_samples: int, seed: int) -> torch.Tensor:
+    """(N, n_samples) distinct item ids per user drawn from the item weights (``cdf`` = float64 cumulative sum), never the user's
+    target nor an item of the input sequence"""
+    input_seq, targets = _i64(input_seq), _i64(targets)
+    N, S = input_seq.shape
+    out = torch.empty(N, n_samples, dtype=torch.int64, device=input_seq.device)
+    failed = torch.zeros(1, dtype=torch.int32, device=input_seq.device)
+    _lib.call("asme_b200_weighted_negatives", _p(cdf), cdf.numel(), _p(input_seq), S, _p(targets), N, int(n_samples), int(seed), _p(out),
+              _p(failed), _stream())
+    return out, failed
+
+
 def score_topk_rank(h, w, bias, k: int, target=None, target_score=None, v0: int = 0):
     """returns (topk_val (R,k), topk_idx (R,k) int32, n_greater (R) int32, n_tie_lower (R) int32)"""
     h, w = _f32(h), _f32(w)

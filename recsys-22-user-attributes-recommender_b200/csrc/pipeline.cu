@@ -141,3 +141,75 @@ extern "C" int asme_b200_pos_neg_sample(const int64_t* seq, int B, int S1, int64
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Negative sampling for sampled ranking metrics (metrics/container/metrics_sampler.py:140-204): per user n_samples distinct items
+// drawn from the item weights (popularity) with the user's target and every item of the input sequence excluded -- sequential
+// draws without replacement from the renormalised weights == rejection sampling of an i.i.d. candidate stream (candidates that are
+// excluded or already drawn are skipped).  One warp per user: 32 candidates per round by inversion of the cumulative weights
+// (binary search), accepted in lane order.
+// ---------------------------------------------------------------------------------------------------------------------------
+#define NEG_MAX_SAMPLES 512
+__global__ void weighted_negatives_kernel(const double* __restrict__ cdf, int V, const int64_t* __restrict__ input_seq, int S,
+                                          const int64_t* __restrict__ targets, int B, int n_samples, uint64_t seed_arg,
+                                          int64_t* __restrict__ out, int* __restrict__ failed) {
+    extern __shared__ int64_t neg_sh[];                 // per warp: [S input items][1 target][n_samples accepted]
+    const int wib = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.x * (blockDim.x / 32) + wib;
+    if (b >= B) return;
+    int64_t* mine = neg_sh + (size_t)wib * (S + 1 + n_samples);
+    const uint64_t seed = asme_seed(seed_arg);
+    for (int s = lane; s < S; s += 32) mine[s] = input_seq[(size_t)b * S + s];
+    if (lane == 0) mine[S] = targets[b];
+    __syncwarp();
+    const double total = cdf[V - 1];
+    int n_acc = 0;
+    for (uint32_t round = 0; n_acc < n_samples && round < 4096u; ++round) {
+        // candidate of this lane: inversion of the cumulative weights
+        const uint32_t r0 = pipe_bits(seed, 21u, (uint32_t)b, round * 32u + (uint32_t)lane, 0u);
+        const uint32_t r1 = pipe_bits(seed, 22u, (uint32_t)b, round * 32u + (uint32_t)lane, 0u);
+        const double u = ((double)r0 * 4294967296.0 + (double)r1) * (1.0 / 18446744073709551616.0) * total;
+        int lo = 0, hi = V - 1;                         // first index with cdf[i] > u
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+        }
+        const int64_t cand = lo;
+        bool bad = false;
+        for (int j = 0; j < S + 1 + n_acc; ++j) bad |= mine[j] == cand;
+        // accept in lane order; a lane's candidate is also rejected when an earlier lane of this round drew the same item
+        for (int l = 0; l < 32 && n_acc < n_samples; ++l) {
+            const int64_t c = __shfl_sync(0xffffffffu, cand, l);
+            const bool c_bad = __shfl_sync(0xffffffffu, (int)bad, l) != 0;
+            bool dup = false;
+            if (!c_bad) {
+                // compare with what was accepted earlier in THIS round (positions >= the count at the start of the round are new)
+                for (int j = S + 1 + lane; j < S + 1 + n_acc; j += 32) dup |= mine[j] == c;
+                dup = __any_sync(0xffffffffu, dup);
+            }
+            if (!c_bad && !dup) {
+                if (lane == 0) mine[S + 1 + n_acc] = c;
+                ++n_acc;
+                __syncwarp();
+            }
+        }
+    }
+    if (n_acc < n_samples && lane == 0) atomicExch(failed, 1);
+    for (int j = lane; j < n_samples; j += 32) out[(size_t)b * n_samples + j] = j < n_acc ? mine[S + 1 + j] : 0;
+}
+
+extern "C" int asme_b200_weighted_negatives(const double* cdf, int V, const int64_t* input_seq, int S, const int64_t* targets, int B,
+                                            int n_samples, uint64_t seed, int64_t* out, int* failed, asme_stream_t stream) {
+    ASME_REQUIRE(cdf && input_seq && targets && out && failed, "weighted_negatives: null argument");
+    ASME_REQUIRE(n_samples >= 1 && n_samples <= NEG_MAX_SAMPLES, "weighted_negatives: n_samples=%d (1..%d)", n_samples, NEG_MAX_SAMPLES);
+    ASME_REQUIRE(V >= 1 && S >= 0, "weighted_negatives: bad shape");
+    if (B == 0) return ASME_OK;
+    const int warps = 4;
+    const size_t smem = (size_t)warps * (S + 1 + n_samples) * sizeof(int64_t);
+    ASME_REQUIRE(smem <= 200 * 1024, "weighted_negatives: S=%d with %d samples needs too much shared memory", S, n_samples);
+    { const int _rc = asme_ensure_max_smem((const void*)weighted_negatives_kernel); if (_rc) return _rc; }
+    weighted_negatives_kernel<<<ceil_div(B, warps), warps * 32, smem, (cudaStream_t)stream>>>(cdf, V, input_seq, S, targets, B, n_samples,
+                                                                                           seed, out, failed);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}

@@ -131,3 +131,83 @@ def test_pipeline_feeds_the_training_modules():
     loss = module.training_step(nb, 0)["loss"]
     loss.backward()
     assert torch.isfinite(loss)
+
+
+def test_weighted_negatives_invariants_and_distribution():
+    """metrics_sampler.py:140-204: negatives follow the item weights, are distinct, never the target, never an input item"""
+    from asme_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    V, B, S, n = 60, 4000, 6, 10
+    weights = torch.rand(V, generator=gen) + 0.05
+    weights[[0, 1, 2, 7]] = 0.0                                     # special tokens and one unpopular item: never drawn
+    seq = torch.tensor([[5, 9, 11, 0, 0, 0]]).repeat(B, 1)          # every user has the same history and target ...
+    tgt = torch.full((B,), 13)
+    cdf = torch.cumsum(weights.double(), 0).cuda()
+    neg, failed = ops.weighted_negatives(cdf, seq.cuda(), tgt.cuda(), n, seed=5)
+    neg = neg.cpu()
+    assert int(failed.item()) == 0
+    assert (neg.sort(dim=1).values.diff(dim=1) != 0).all()          # distinct within a user
+    banned = torch.tensor([0, 1, 2, 7, 5, 9, 11, 13])
+    assert not torch.isin(neg, banned).any()
+    # ... so the inclusion frequencies can be compared with torch.multinomial (without replacement) on the same renormalised weights
+    w = weights.clone()
+    w[[5, 9, 11, 13, 0]] = 0.0
+    torch.manual_seed(1)
+    ref = torch.multinomial(w.unsqueeze(0).repeat(B, 1), n)
+    f_g = np.bincount(neg.reshape(-1).numpy(), minlength=V) / B
+    f_o = np.bincount(ref.reshape(-1).numpy(), minlength=V) / B
+    assert np.abs(f_g - f_o).max() < 0.035                          # inclusion probabilities are O(0.2): ~4 sigma at B = 4000
+    # the FIRST draw alone follows the renormalised weights exactly
+    first = np.bincount(neg[:, 0].numpy(), minlength=V) / B
+    assert np.abs(first - (w / w.sum()).numpy()).max() < 0.015
+    # too few admissible items: the flag is raised instead of torch.multinomial's exception
+    few = torch.zeros(V)
+    few[[20, 21, 22]] = 1.0
+    _, failed = ops.weighted_negatives(torch.cumsum(few.double(), 0).cuda(), seq[:4].cuda(), tgt[:4].cuda(), 5, seed=1)
+    assert int(failed.item()) == 1
+
+
+def test_sampled_and_fixed_subset_metrics_from_fused_predictions():
+    """FixedItemsSampler / NegativeMetricsSampler on the fused evaluation output (no dense logits): identical to the oracle's
+    metrics on the dense logits gathered at the same items"""
+    from asme_b200.data import InputSequence
+    from asme_b200.metrics import (FixedItemsSampler, FusedPredictions, NegativeMetricsSampler, NormalizedDiscountedCumulativeGainMetric,
+                                   RankingMetricsContainer, RecallMetric)
+    from asme_b200.models import BERT4RecModel, mask_position_rows
+    from asme_b200 import models
+    old = models.DEFAULT_PRECISION
+    models.set_default_precision("fp32")
+    try:
+        torch.manual_seed(0)
+        gen = torch.Generator().manual_seed(4)
+        V, S, B = 300, 20, 64
+        model = BERT4RecModel(32, 2, 1, V, S, 0.0, initializer_range=0.3).cuda().eval()
+        seq, lengths = make_batch(gen, B, S, V)
+        seq[torch.arange(B), lengths - 1] = 1
+        tgt = torch.randint(3, V, (B,), generator=gen)
+        seq_d, tgt_d = seq.cuda(), tgt.cuda()
+        out = model.evaluate_rank(seq_d, seq_d.ne(0), {}, tgt_d, k=10)
+        pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], V, scorer=out["scorer"])
+        dense = model(InputSequence(seq_d, seq_d.ne(0), {})).reshape(B * S, V)[mask_position_rows(seq_d, 1)].cpu()
+        fixed = list(range(3, 120, 2))
+        cont = RankingMetricsContainer([RecallMetric(5), NormalizedDiscountedCumulativeGainMetric(5)], FixedItemsSampler(fixed))
+        got = cont.update(seq_d, tgt_d, pred)
+        items = torch.tensor(fixed).unsqueeze(0).repeat(B, 1)
+        sub = dense.gather(1, items).numpy()
+        pos = items.eq(tgt.unsqueeze(1)).numpy()
+        assert abs(float(got["recall@5_fixed"]) - O.recall_at_k(sub, pos, 5).mean()) < 1e-6
+        assert abs(float(got["NDCG@5_fixed"]) - O.ndcg_at_k(sub, pos, 5).mean()) < 1e-6
+        sampler = NegativeMetricsSampler([0.0, 0.0, 0.0] + [1.0] * (V - 3), 50, "_sampled(50)", seed=9)
+        cont = RankingMetricsContainer([RecallMetric(5), NormalizedDiscountedCumulativeGainMetric(5)], sampler)
+        sample = sampler.sample(seq_d, tgt_d, pred)
+        assert tuple(sample.sampled_predictions.shape) == (B, 51)
+        sampler._calls -= 1                                             # the container's call below repeats exactly this draw
+        got = cont.update(seq_d, tgt_d, pred)
+        sp = sample.sampled_predictions.cpu().numpy()
+        pm = sample.positive_item_mask.cpu().numpy()
+        assert abs(float(got["recall@5_sampled(50)"]) - O.recall_at_k(sp, pm, 5).mean()) < 1e-6
+        assert abs(float(got["NDCG@5_sampled(50)"]) - O.ndcg_at_k(sp, pm, 5).mean()) < 1e-6
+        # the gathered scores are the dense logits at those items
+        np.testing.assert_allclose(sub, pred.gather(1, items.cuda()).cpu().numpy(), rtol=1e-5, atol=1e-5)
+    finally:
+        models.set_default_precision(old)

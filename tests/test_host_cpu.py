@@ -149,3 +149,14 @@ def test_user_models_expose_user_keys_and_extra_position():
     with pytest.raises(NotImplementedError):
         UBERT4RecModel(16, 2, 1, 50, 12, 0.0, user_attributes={"uid": {"embedding_type": "user_linear_upscale"}},
                        attribute_vocab_sizes={"uid": 5})
+
+
+def test_fixed_items_sampler_on_dense_predictions():
+    """metrics_sampler.py:74-107 -- the sampler works on dense (N,I) predictions without a GPU (pure index plumbing)"""
+    from asme_b200.metrics import FixedItemsSampler
+    pred = torch.arange(24, dtype=torch.float32).view(3, 8)
+    targets = torch.tensor([2, 5, 7])
+    s = FixedItemsSampler([1, 2, 5]).sample(None, targets, pred)
+    assert s.sampled_predictions.tolist() == [[1.0, 2.0, 5.0], [9.0, 10.0, 13.0], [17.0, 18.0, 21.0]]
+    assert s.positive_item_mask.tolist() == [[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, 0.0]]
+    assert FixedItemsSampler([1]).suffix_metric_name() == "_fixed"
