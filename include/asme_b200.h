@@ -344,7 +344,8 @@ int asme_b200_tc_attn_fwd_rows(const void* qkv, const uint8_t* key_valid, int B,
 int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                           float p_drop, const void* ctx, const void* d_ctx, const float* stats,
                           const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream);
-/* diagnostic: knob 0 selects the backward kernel (1 = single sweep, default; 0 = two sweeps); results agree to rounding */
+/* diagnostic: knob 0 selects the backward kernel (1 = single sweep, default; 0 = two sweeps), knob 1 the epilogue warpgroups of the
+ * single-sweep kernel (2 or 4); results agree to rounding */
 int asme_b200_tc_attn_tune(int knob, int value);
 
 /* ------------------------------------------------------------------------------------------

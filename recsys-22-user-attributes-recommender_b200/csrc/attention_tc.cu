@@ -685,7 +685,10 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
 // Loop order: key tile ct outer, query tile rt inner, so dK / dV accumulate over the inner loop and every query tile keeps
 // its own dQ accumulator: tensor memory = 2 x 128 (T1, T2) + (2 + n_t) x d <= 512 columns.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __grid_constant__ CUtensorMap tmQKV,
+// WGS epilogue warpgroups (2 or 4), each owning 128 / WGS columns of a sub-tile: the element-wise stage is latency-bound (23 % issue
+// utilisation with two warpgroups), more resident warps hide it
+template <int WGS>
+__global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                      const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
         tma_prefetch_desc(&tmDO);
         mbar_init(&sh->loaded, 1);
         mbar_init(&sh->t_full, 1);
-        mbar_init(&sh->x_full, 256);
+        mbar_init(&sh->x_full, 128 * WGS);
         mbar_init(&sh->acc_done, 1);
         fence_barrier_init();
     }
@@ -785,7 +788,8 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
         const int wg = (warp - 4) / 4;
         const int q4 = warp % 4;
         const int r = q4 * 32 + lane;
-        const int et = threadIdx.x - 128;
+        const int et = threadIdx.x - 128;                    // 0 .. 128*WGS-1 among the epilogue threads
+        constexpr int C16_PER_WG = 8 / WGS;                  // 16-column chunks of a sub-tile per warpgroup
         const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
         const float cs = a.scale * LOG2E;
         if (warp == 4) {
@@ -802,8 +806,8 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
         for (int hh = 0; hh < hps; ++hh) {
             const int head = slice * hps + hh;
             const long long bh = (long long)b * a.heads + head;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int q = et; q < S; q += 256) {
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");
+            for (int q = et; q < S; q += 128 * WGS) {
                 const __nv_bfloat16* o = a.ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
                 const __nv_bfloat16* go = a.d_ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
                 float D = 0.f;
@@ -827,7 +831,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
                     reinterpret_cast<uint4*>(sh->keep + q * 8)[1] = kb[1];
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");
             for (int i = 0; i < subs_per_head; ++i, ++g) {
                 const int ct = i / n_t, rt = i % n_t;
                 const int row = rt * 128 + r;                  // query of this thread
@@ -839,13 +843,8 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
                 float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
                 if (row_ok) rc = sh->qc[row];
                 const bool warp_rows_plain = warp_row0 + 31 < S;
-                uint32_t keep_w0 = 0xffffffffu, keep_w1 = 0xffffffffu;
-                if (a.keep_bits && row_ok) {
-                    keep_w0 = sh->keep[row * 8 + ct * 4 + wg * 2];
-                    keep_w1 = sh->keep[row * 8 + ct * 4 + wg * 2 + 1];
-                }
 #pragma unroll 1
-                for (int c16 = wg * 4; c16 < wg * 4 + 4; ++c16) {
+                for (int c16 = wg * C16_PER_WG; c16 < (wg + 1) * C16_PER_WG; ++c16) {
                     const int col0 = ct * 128 + c16 * 16;                  // first key of the chunk
                     if (c16 * 16 >= ((ncols + 31) / 32) * 32) break;
                     const uint32_t kv16 = (sh->kvb[col0 >> 5] >> (col0 & 31)) & 0xffffu;
@@ -864,7 +863,9 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
                     tmem_ld16(tm_t2 + lane_addr + (uint32_t)(c16 * 16), t2);
                     tmem_ld_wait();
                     float pd[16], ds[16];
-                    const uint32_t kp16 = ((((c16 >> 1) & 1) ? keep_w1 : keep_w0) >> ((c16 & 1) * 16)) & 0xffffu;
+                    uint32_t keep_w = 0xffffffffu;                      // keep bits of this row for the 32 keys around the chunk
+                    if (a.keep_bits && row_ok) keep_w = sh->keep[row * 8 + ct * 4 + (c16 >> 1)];
+                    const uint32_t kp16 = (keep_w >> ((c16 & 1) * 16)) & 0xffffu;
                     const bool plain = warp_rows_plain && kv16 == 0xffffu && (!a.causal || col0 + 15 <= warp_row0);
                     if (plain) {
 #pragma unroll
@@ -906,15 +907,14 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
                 if (store_kv || store_q) {
                     mbar_wait(&sh->acc_done, (uint32_t)g & 1u);
                     tc_fence_after();
-                    const int dcols = d >= 32 ? d / 2 : d;
-                    if (d >= 32 || wg == 0) {
-                        const int cbeg = d >= 32 ? wg * dcols : 0;
+                    // the head's d output columns are stored in 16-column pieces dealt round-robin to the warpgroups
+                    {
                         // which: 0 = dQ (row = query rt*128 + r), 1 = dK, 2 = dV (row = key ct*128 + r)
                         for (int which = store_q ? 0 : 1; which < (store_kv ? 3 : 1); ++which) {
                             const uint32_t tm = which == 0 ? tm_dq0 + (uint32_t)(rt * d) : (which == 1 ? tm_dk : tm_dv);
                             const int out_row = which == 0 ? row : ct * 128 + r;
                             const int colbase = which * a.H + slice * 64 + hh * d;
-                            for (int c0 = cbeg; c0 < cbeg + dcols; c0 += 16) {
+                            for (int c0 = wg * 16; c0 < d; c0 += WGS * 16) {
                                 float o[16];
                                 tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
                                 tmem_ld_wait();
@@ -943,9 +943,17 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd1_kernel(const __gr
 }
 
 static int g_attn_bwd_variant = 1;      // 1: single sweep (default), 0: the two-sweep kernel (kept for A/B measurements)
+static int g_attn_bwd_wgs = 4;          // epilogue warpgroups of the single-sweep kernel: 2 or 4 (4: 3-6 % faster, bit-identical)
 extern "C" int asme_b200_tc_attn_tune(int knob, int value) {
-    ASME_REQUIRE(knob == 0 && (value == 0 || value == 1), "tc_attn_tune: knob 0 (backward variant) takes 0 or 1");
-    g_attn_bwd_variant = value;
+    if (knob == 0) {
+        ASME_REQUIRE(value == 0 || value == 1, "tc_attn_tune: knob 0 (backward variant) takes 0 or 1");
+        g_attn_bwd_variant = value;
+    } else if (knob == 1) {
+        ASME_REQUIRE(value == 2 || value == 4, "tc_attn_tune: knob 1 (epilogue warpgroups of the single-sweep backward) takes 2 or 4");
+        g_attn_bwd_wgs = value;
+    } else {
+        ASME_REQUIRE(false, "tc_attn_tune: unknown knob %d", knob);
+    }
     return ASME_OK;
 }
 
@@ -972,8 +980,13 @@ extern "C" int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, 
     a.keep_bits = p_drop > 0.f ? keep_bits : nullptr; a.d_qkv = (__nv_bfloat16*)d_qkv;
     const size_t smem = 1024 + 6 * 32768 + sizeof(AttnBwdShared);
     if (g_attn_bwd_variant == 1) {
-        { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd1_kernel); if (_rc) return _rc; }
-        attn_tc_bwd1_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+        if (g_attn_bwd_wgs == 4) {
+            { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd1_kernel<4>); if (_rc) return _rc; }
+            attn_tc_bwd1_kernel<4><<<dim3(B, H / 64), 128 + 128 * 4, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+        } else {
+            { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd1_kernel<2>); if (_rc) return _rc; }
+            attn_tc_bwd1_kernel<2><<<dim3(B, H / 64), 128 + 128 * 2, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);
+        }
     } else {
         { const int _rc = asme_ensure_max_smem((const void*)attn_tc_bwd_kernel); if (_rc) return _rc; }
         attn_tc_bwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmD, a);

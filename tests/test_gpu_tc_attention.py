@@ -105,12 +105,14 @@ def test_tc_attn_fwd_no_mask_and_fully_masked_rows(ops):
     torch.testing.assert_close(got.float().view(B, S, H)[b, 0], uniform, rtol=2e-2, atol=2e-2)
 
 
-@pytest.fixture(params=[1, 0], ids=["single_sweep", "two_sweeps"])
+@pytest.fixture(params=[(1, 4), (1, 2), (0, 2)], ids=["single_sweep_4wg", "single_sweep_2wg", "two_sweeps"])
 def bwd_variant(request, ops):
-    """both tensor-core backward kernels: the single-sweep one (default) and the older two-sweep one"""
-    ops._lib.call("asme_b200_tc_attn_tune", 0, request.param)
+    """the tensor-core backward kernels: single sweep with four (default) or two epilogue warpgroups, and the older two-sweep one"""
+    ops._lib.call("asme_b200_tc_attn_tune", 0, request.param[0])
+    ops._lib.call("asme_b200_tc_attn_tune", 1, request.param[1])
     yield request.param
     ops._lib.call("asme_b200_tc_attn_tune", 0, 1)
+    ops._lib.call("asme_b200_tc_attn_tune", 1, 4)
 
 
 @pytest.mark.parametrize("B,S,heads,d", CASES)

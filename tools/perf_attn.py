@@ -17,10 +17,14 @@ def run(B, S, H, heads, causal, p):
     res = dict(B=B, S=S, H=H, heads=heads, causal=causal, p=p)
     res["fwd_ms"] = round(timeit(lambda: ops.tc_attn_fwd(qkv, kv, B, S, heads, causal, p, 1234, 7, True), iters=20), 4)
     outs = {}
-    for variant in (0, 1):
+    for variant, wgs in ((0, 2), (1, 2), (1, 4)):
         ops._lib.call("asme_b200_tc_attn_tune", 0, variant)
-        outs[variant] = ops.tc_attn_bwd(qkv, kv, B, S, heads, causal, ctx, dctx, st, keep, p).float()
-        res[f"bwd{variant}_ms"] = round(timeit(lambda: ops.tc_attn_bwd(qkv, kv, B, S, heads, causal, ctx, dctx, st, keep, p), iters=20), 4)
+        ops._lib.call("asme_b200_tc_attn_tune", 1, wgs)
+        key = variant if wgs == 2 else "1w4"
+        outs[key] = ops.tc_attn_bwd(qkv, kv, B, S, heads, causal, ctx, dctx, st, keep, p).float()
+        res[f"bwd{key}_ms"] = round(timeit(lambda: ops.tc_attn_bwd(qkv, kv, B, S, heads, causal, ctx, dctx, st, keep, p), iters=20), 4)
+    res["w4_equal"] = bool(torch.equal(outs[1], outs["1w4"]))
+    ops._lib.call("asme_b200_tc_attn_tune", 1, 4)
     diff = (outs[0] - outs[1]).abs().max().item()
     res["max_abs_diff"], res["max_abs"] = diff, outs[0].abs().max().item()
     ops._lib.call("asme_b200_tc_attn_tune", 0, 1)
