@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
         tma_prefetch_desc(&tmQKV);
         mbar_init(&sh->loaded, 1);
         mbar_init(&sh->s_full, 1);
-        mbar_init(&sh->p_full, 256);
+        mbar_init(&sh->p_full, 8);                     // one arrival per epilogue warp
         mbar_init(&sh->o_full, 1);
         fence_barrier_init();
     }
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             sh->xl[wg][r] = l;
             fence_proxy_async_smem();                         // make the generic-proxy P writes visible to the tensor core
             tc_fence_before();
-            mbar_arrive(&sh->p_full);
+            mbar_arrive_warp(&sh->p_full);
             // ---- O = P V done: normalise and store (each warpgroup half of the head's columns)
             mbar_wait(&sh->o_full, (uint32_t)u & 1u);
             tc_fence_after();
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
         tma_prefetch_desc(&tmDO);
         mbar_init(&sh->loaded, 1);
         mbar_init(&sh->t_full, 1);
-        mbar_init(&sh->x_full, 128 * WGS);
+        mbar_init(&sh->x_full, 4 * WGS);               // one arrival per epilogue warp
         mbar_init(&sh->acc_done, 1);
         fence_barrier_init();
     }
@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
-                mbar_arrive(&sh->x_full);
+                mbar_arrive_warp(&sh->x_full);
                 const bool store_kv = rt == n_t - 1, store_q = ct == n_t - 1;
                 if (store_kv || store_q) {
                     mbar_wait(&sh->acc_done, (uint32_t)g & 1u);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
         tma_prefetch_desc(&tmCol);
         mbar_init(&sh->row_full, 1);
         mbar_init(&sh->t_full, 1);
-        mbar_init(&sh->x_full, 256);
+        mbar_init(&sh->x_full, 8);                     // one arrival per epilogue warp
         mbar_init(&sh->acc_done, 1);
         for (int s = 0; s < stages; ++s) {
             mbar_init(&sh->full[s], 1);
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&sh->x_full);
+            mbar_arrive_warp(&sh->x_full);
         }
         // ---- accumulators -> partial outputs (each warpgroup half of the Kp columns)
         float* out = a.partial + (size_t)split * n_rows_total * a.H;

@@ -50,6 +50,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival for a whole (converged) warp: every lane has already issued its own proxy / tcgen05 fences, __syncwarp orders the
+// lanes' shared-memory writes before lane 0's releasing arrive.  512 per-thread arrivals on one barrier serialise in the
+// shared-memory atomic unit; 16 per-warp ones do not.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
