@@ -234,7 +234,7 @@ def algorithmic_cost(name, note):
         return 4 * (3 + g("res")) * M * H, 16 * M * H
     if name == "asme_b200_embed_fwd":
         T, H, nt = g("T"), g("H"), g("tables")
-        return nt * T * H * 4 + g("ids") * T * 8 + T * H * 4, 8 * T * H
+        return nt * T * H * 4 + g("ids") * T * 8 + T * H * 4 + g("next") * T * H * 2, 8 * T * H
     if name == "asme_b200_embed_bwd":
         T, H, nt = g("T"), g("H"), g("tables")
         return (nt + 2) * T * H * 4 + g("ids") * T * 8, 16 * T * H

@@ -134,7 +134,7 @@ def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False, next_ln
         d.next_gamma, d.next_beta, d.next_out = g.data_ptr(), b.data_ptr(), y16.data_ptr()
         d.next_stats = None if st is None else st.data_ptr()
     if _lib.timing is not None:
-        _lib.note = f"T={T},H={H},tables={1 + (spec.pos_table is not None) + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)},ids={1 + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)}"
+        _lib.note = f"T={T},H={H},tables={1 + (spec.pos_table is not None) + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)},ids={1 + len(spec.attrs) + sum(b[0].shape[-1] for b in spec.bags)},next={int(next_ln is not None)}"
     _lib.call("asme_b200_embed_fwd", ctypes.byref(d), T, S, H, _p(out), _p(stats), _stream())
     if next_ln is not None:
         return out, stats, y16, st

@@ -185,8 +185,8 @@ __device__ __forceinline__ void embed_gather_attrs(Row<LANES, CH>& x, const asme
 // TOK tokens per lane group: all ids, then all item rows are requested before anything is consumed, so every group keeps
 // TOK independent 128-bit gathers in flight (a random 256-512 B row per token is latency-bound otherwise).  A block covers
 // TOK * groups consecutive tokens; token j of group g is base + j * groups + g, so stores stay coalesced across groups.
-template <int LANES, int CH, int TOK>
-__global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d, int T, int S, int H, float* __restrict__ out,
+template <int LANES, int CH, int TOK, bool PRE>
+__global__ void __launch_bounds__(256, (!PRE && CH == 1) ? 5 : 1) embed_fwd_kernel(const asme_embed_desc d, int T, int S, int H, float* __restrict__ out,
                                                         float* __restrict__ stats) {
     const int lane = threadIdx.x % LANES;
     const int groups = blockDim.x / LANES;
@@ -194,17 +194,25 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d,
     const float inv_keep = d.p_drop > 0.f ? 1.0f / (1.0f - d.p_drop) : 1.0f;
     // user prefix (UBERT4Rec / UserSASRec): position 0 of every sequence is the sum of the user-attribute embeddings and the
     // items follow at positions 1..S-1, i.e. output row (b, s) reads item token b*(S-1) + s-1.  pre = 0: plain layout.
-    const int pre = d.n_user > 0 ? 1 : 0;
+    // PRE is a template parameter: the plain layout keeps the short id -> row address chain (and its register count)
+    constexpr int pre = PRE ? 1 : 0;
     const float* first[TOK];
+    int bs[TOK], sps[TOK];
     Row<LANES, CH> xs[TOK];
 #pragma unroll
     for (int j = 0; j < TOK; ++j) {
         const long long tj = base + (long long)j * groups;
         const long long t = tj < T ? tj : 0;
-        const long long b = t / S;
-        const int sp = (int)(t - b * S);
-        if (pre && sp == 0) first[j] = d.user_table[0] + __ldg(d.user_ids[0] + b) * H;
-        else first[j] = d.item_table + __ldg(d.item_ids + (pre ? b * (S - 1) + sp - 1 : t)) * H;
+        if (PRE) {
+            // token index -> (sequence, position) in 32-bit arithmetic (T is an int; a 64-bit division costs more than the gather)
+            const unsigned b = (unsigned)t / (unsigned)S;
+            const int sp = (int)((unsigned)t - b * (unsigned)S);
+            bs[j] = (int)b; sps[j] = sp;
+            if (sp == 0) first[j] = d.user_table[0] + __ldg(d.user_ids[0] + b) * H;
+            else first[j] = d.item_table + __ldg(d.item_ids + (long long)b * (S - 1) + sp - 1) * H;
+        } else {
+            first[j] = d.item_table + __ldg(d.item_ids + t) * H;
+        }
     }
 #pragma unroll
     for (int j = 0; j < TOK; ++j) xs[j].load(first[j], lane);
@@ -214,10 +222,10 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const asme_embed_desc d,
         const long long tj = base + (long long)j * groups;
         const bool ok = tj < T;
         const long long t = ok ? tj : 0;
-        const long long b = t / S;
-        const int sp = (int)(t - b * S);
-        const bool is_user = pre && sp == 0;                  // uniform inside the lane group
-        const long long src = pre ? b * (S - 1) + sp - 1 : t;  // item token feeding this row (unused for the user row)
+        const long long b = PRE ? bs[j] : 0;
+        const int sp = PRE ? sps[j] : (d.pos_table ? (int)((unsigned)t % (unsigned)S) : 0);
+        const bool is_user = PRE && sp == 0;                  // uniform inside the lane group
+        const long long src = PRE ? b * (S - 1) + sp - 1 : t;  // item token feeding this row (unused for the user row)
         Row<LANES, CH> x = xs[j], y;
         if (is_user) {
             for (int u = 1; u < d.n_user; ++u) x.add(d.user_table[u] + __ldg(d.user_ids[u] + b) * H, lane);
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const asme_embed_desc d,
     for (long long t = (long long)blockIdx.x * groups_per_block + group_in_block; t < T;
          t += (long long)gridDim.x * groups_per_block) {
         Row<LANES, CH> x, xhat1, xhat2, g;
-        const long long b = t / S;
+        const long long b = (unsigned)t / (unsigned)S;       // 32-bit: T is an int
         const int sp = (int)(t - b * S);
         const bool is_user = pre && sp == 0;
         const long long src = pre ? b * (S - 1) + sp - 1 : t;
@@ -532,14 +540,22 @@ extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H
     const int groups = 256 / lanes;
     // tokens per lane group: as many as still leave >= 4 blocks per SM
     const int tok = ceil_div(T, groups * 4) >= ASME_NUM_SMS * 4 ? 4 : (ceil_div(T, groups * 2) >= ASME_NUM_SMS * 4 ? 2 : 1);
-#define CALL(L, C)                                                                                                             \
-    {                                                                                                                          \
-        if (tok == 4) embed_fwd_kernel<L, C, 4><<<ceil_div(T, groups * 4), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats);      \
-        else if (tok == 2) embed_fwd_kernel<L, C, 2><<<ceil_div(T, groups * 2), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats); \
-        else embed_fwd_kernel<L, C, 1><<<ceil_div(T, groups), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats);                   \
+#define LAUNCH_TOK(L, C, K, P) embed_fwd_kernel<L, C, K, P><<<ceil_div(T, groups * K), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats)
+#define CALL(L, C)                                                                       \
+    {                                                                                    \
+        if (d->n_user > 0) {                                                             \
+            if (tok == 4) LAUNCH_TOK(L, C, 4, true);                                     \
+            else if (tok == 2) LAUNCH_TOK(L, C, 2, true);                                \
+            else LAUNCH_TOK(L, C, 1, true);                                              \
+        } else {                                                                         \
+            if (tok == 4) LAUNCH_TOK(L, C, 4, false);                                    \
+            else if (tok == 2) LAUNCH_TOK(L, C, 2, false);                               \
+            else LAUNCH_TOK(L, C, 1, false);                                             \
+        }                                                                                \
     }
     DISPATCH_H(H, CALL)
 #undef CALL
+#undef LAUNCH_TOK
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

@@ -10,7 +10,7 @@ from tools.perf_score import timeit
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
 
-def run(B, S, V, H, pos, ln, p):
+def run(B, S, V, H, pos, ln, p, nxt=False):
     g = torch.Generator(device="cuda").manual_seed(0)
     table = torch.randn(V, H, device="cuda", generator=g)
     P = torch.randn(S, H, device="cuda", generator=g) if pos else None
@@ -20,12 +20,12 @@ def run(B, S, V, H, pos, ln, p):
     it = [0]
 
     def step():
-        ops.embed_fwd(specs[it[0] % 4], B, S)
+        ops.embed_fwd(specs[it[0] % 4], B, S, next_ln=(gam, bet) if nxt else None)
         it[0] += 1
     ms = timeit(step, iters=20)
     T = B * S
-    nbytes = T * ((1 + int(pos)) * H * 4 + 8 + H * 4)
-    print(json.dumps(dict(T=T, V=V, H=H, pos=pos, ln=ln, p=p, ms=round(ms, 4), gbs=round(nbytes / ms / 1e6, 1),
+    nbytes = T * ((1 + int(pos)) * H * 4 + 8 + H * 4 + (H * 2 if nxt else 0))
+    print(json.dumps(dict(T=T, V=V, H=H, pos=pos, ln=ln, p=p, next_ln=nxt, ms=round(ms, 4), gbs=round(nbytes / ms / 1e6, 1),
                           frac=round(nbytes / ms / 1e6 / PEAK, 3))), flush=True)
 
 
@@ -33,3 +33,4 @@ if __name__ == "__main__":
     for (B, S, V, H) in [(1024, 200, 1_000_003, 128), (4096, 200, 1_000_003, 128), (256, 200, 3709, 64), (4096, 50, 13047, 64)]:
         for pos, ln, p in [(False, False, 0.0), (False, True, 0.0), (True, True, 0.0), (False, True, 0.2)]:
             run(B, S, V, H, pos, ln, p)
+        run(B, S, V, H, True, True, 0.0, nxt=True)
