@@ -232,6 +232,9 @@ def algorithmic_cost(name, note):
     if name in ("asme_b200_layernorm_bwd",):
         M, H = g("M"), g("H")
         return 4 * (3 + g("res")) * M * H, 16 * M * H
+    if name == "asme_b200_attn_row_fwd":     # K and V rows of every token once (bf16), one query / context row per sequence
+        T, H, S = g("T"), g("H"), g("S")
+        return 2 * T * H * 2 + T + 2 * (T // max(S, 1)) * H * 2, 4 * T * H
     if name == "asme_b200_embed_fwd":
         T, H, nt = g("T"), g("H"), g("tables")
         return nt * T * H * 4 + g("ids") * T * 8 + T * H * 4 + g("next") * T * H * 2, 8 * T * H

@@ -339,6 +339,12 @@ int asme_b200_tc_attn_fwd(const void* qkv, const uint8_t* key_valid, int B, int 
  * untouched.  Rows that are computed are bit-identical to asme_b200_tc_attn_fwd. */
 int asme_b200_tc_attn_fwd_rows(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                                const int64_t* only_row, void* ctx, asme_stream_t stream);
+/* one query position per sequence as two matrix-vector products (HBM-bound, fp32 arithmetic on the bf16 q/k/v): ctx_rows (B, H)
+ * bf16, row b = attention output of flat row only_row[b] (= b*S + position) -- Attention.forward (transformer_layers.py:145-155)
+ * restricted to the rows the last encoder layer needs (models/.../evaluation reads one position per sequence).  d: power of
+ * two 8..256, H/8 must divide 256. */
+int asme_b200_attn_row_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                           const int64_t* only_row, void* ctx_rows, asme_stream_t stream);
 /* d_qkv (B*S, 3H) bf16 from d_ctx (B*S, H) bf16; scores and dP are recomputed in tensor memory, transposed quantities come
  * from transposed MMAs; needs the forward's ctx, stats and (when p_drop > 0) keep_bits */
 int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,

@@ -104,6 +104,7 @@ _PROTOTYPES = {
     "asme_b200_tc_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "asme_b200_tc_attn_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P, P]),
     "asme_b200_tc_attn_fwd_rows": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "asme_b200_attn_row_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "asme_b200_tc_attn_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
     "asme_b200_posneg_bce_fwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),
     "asme_b200_posneg_bce_bwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, c_float, P, P, P, P]),

@@ -122,7 +122,9 @@ class EncoderEngine:
         """``select_rows`` (evaluation only): flat indices of the positions whose hidden state is needed.  Every layer but the
         last runs on all tokens; in the last layer only K and V depend on the other positions, so everything after the attention
         (output projection, LayerNorm, feed-forward: ~half of the layer) runs on the selected rows alone.  The selected rows are
-        bit-identical to the full computation; returns (len(select_rows), H)."""
+        bit-identical to the full computation; with ``one_per_sequence`` the last attention is the fp32 matrix-vector kernel
+        (asme_b200_attn_row_fwd) instead of the tensor-core tile, i.e. equal up to the bf16 rounding of the probabilities.
+        Returns (len(select_rows), H)."""
         cfg, m = self.cfg, self.m
         H = cfg.hidden
         train = saved.training
@@ -145,10 +147,14 @@ class EncoderEngine:
             bqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,))
             ls.attn_tc = S <= 256 and (H // cfg.heads) in (16, 32, 64)
             last_selected = select_rows is not None and l == cfg.layers - 1 and not train
+            ctx_rows = None
             if ls.attn_tc:      # tcgen05 attention straight on the bf16 QKV projection
                 ls.qkv = ops.tc_gemm(ls.y1, wqkv, bias=bqkv, out_f32=False, out_bf16=True)["bf16"]
-                if last_selected and one_per_sequence and select_rows.numel() == B:
-                    # one position per sequence: only the query tile that holds it is computed (the rows read below are bit-identical)
+                if last_selected and one_per_sequence and select_rows.numel() == B and 256 % (H // 8) == 0:
+                    # one position per sequence: two matrix-vector products per head (HBM-bound), straight into (B, H) rows
+                    ctx_rows = ops.attn_row_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, select_rows)
+                elif last_selected and one_per_sequence and select_rows.numel() == B:
+                    # hidden sizes the row kernel's thread layout does not cover: only the query tile holding the row is computed
                     ls.ctx16 = ops.tc_attn_fwd_rows(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, select_rows)
                 else:
                     ls.ctx16, ls.ast, ls.keep = ops.tc_attn_fwd(ls.qkv, saved.key_valid, B, S, cfg.heads, not cfg.bidirectional, pa,
@@ -159,7 +165,8 @@ class EncoderEngine:
                                               self._site(l, 0), save_stats=train)
                 ls.ctx16 = ops.cast_bf16(ls.ctx, ld_out=H)
             if select_rows is not None and l == cfg.layers - 1 and not train:
-                ls.ctx16 = ls.ctx16.index_select(0, select_rows)      # row selection (index plumbing, no arithmetic)
+                # row selection (index plumbing, no arithmetic)
+                ls.ctx16 = ctx_rows if ctx_rows is not None else ls.ctx16.index_select(0, select_rows)
                 x = x.index_select(0, select_rows)
             # output projection + residual, with the output sublayer's LayerNorm fused into the epilogue (H <= 128)
             r = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),

@@ -584,6 +584,20 @@ def tc_attn_fwd_rows(qkv16: torch.Tensor, key_valid: Optional[torch.Tensor], B: 
     return ctx
 
 
+def attn_row_fwd(qkv16: torch.Tensor, key_valid: Optional[torch.Tensor], B: int, S: int, heads: int, causal: bool,
+                 only_row: torch.Tensor) -> torch.Tensor:
+    """evaluation of one position per sequence: (B, H) bf16 attention output of flat rows ``only_row`` (two matrix-vector
+    products per head over the sequence's K / V rows; fp32 arithmetic)"""
+    qkv16 = _bf16(qkv16, "qkv")
+    H = qkv16.shape[1] // 3
+    out = torch.empty(B, H, dtype=torch.bfloat16, device=qkv16.device)
+    if _lib.timing is not None:
+        _lib.note = f"T={B * S},H={H},S={S},heads={heads}"
+    _lib.call("asme_b200_attn_row_fwd", _p(qkv16), _p(_u8(key_valid)), B, S, heads, H // heads, 1 if causal else 0,
+              _p(_i64(only_row)), _p(out), _stream())
+    return out
+
+
 def tc_attn_bwd(qkv16, key_valid, B, S, heads, causal, ctx16, d_ctx16, stats, keep_bits, p_drop=0.0):
     """d_qkv (B*S, 3H) bf16"""
     qkv16, ctx16, d_ctx16 = _bf16(qkv16, "qkv"), _bf16(ctx16, "ctx"), _bf16(d_ctx16, "d_ctx")

@@ -7,6 +7,7 @@
 // of the whole sequence are staged once in shared memory (row stride d+1 -> conflict-free for the
 // lane-owns-a-row access pattern).  Each warp processes 4 owner rows at a time.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 #define ATT_WARPS 4
 #define ATT_RQ 4                         // rows per warp pass
@@ -421,6 +422,141 @@ extern "C" int asme_b200_attn_bwd(const float* qkv, const uint8_t* key_valid, in
     }
     DISPATCH_KPL(S, CALL)
 #undef CALL
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One query position per sequence (evaluation, last encoder layer): the attention of row only_row[b] is two matrix-vector
+// products over that sequence's K and V rows -- HBM-bound (every K/V byte is read once, 128 bits per thread, coalesced), no
+// tensor-core tile to fill.  Same semantics as Attention.forward (transformer_layers.py:145-155): -1e9 fill, softmax over all
+// S keys (a row without any valid key attends uniformly), fp32 arithmetic on the bf16 q/k/v, context rounded to bf16.
+// Thread layout: thread = (8-column slice of the H-wide row, row group); both phases walk rows group, group + G, ...
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8_bf16(const uint4 u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(256) attn_row_kernel(const __nv_bfloat16* __restrict__ qkv, const uint8_t* __restrict__ key_valid,
+                                                       int S, int heads, int d, int causal, const int64_t* __restrict__ only_row,
+                                                       __nv_bfloat16* __restrict__ ctx_rows) {
+    extern __shared__ float row_smem[];
+    const int H = heads * d;
+    float* score = row_smem;                       // heads * S (scores, then unnormalised probabilities)
+    float* red = score + heads * S;                // G * H partial contexts
+    float* inv_l = red + 256 * 8;                  // heads
+    const int b = blockIdx.x;
+    const int slices = H / 8;                      // threads per row
+    const int G = 256 / slices;                    // row groups
+    const int c8 = threadIdx.x % slices, g = threadIdx.x / slices;
+    const int per_head = d / 8;                    // consecutive threads that share a head (power of two <= 32)
+    const int h = c8 / per_head;
+    long long sq = only_row[b] - (long long)b * S;
+    sq = sq < 0 ? 0 : (sq >= S ? S - 1 : sq);
+    const __nv_bfloat16* base = qkv + (size_t)b * S * 3 * H;
+    float q[8];
+    unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(base + (size_t)sq * 3 * H + c8 * 8)), q);
+    const float scale = rsqrtf((float)d);
+    // ---- scores: partial dot over this thread's 8 columns, reduced over the head's per_head threads
+    for (int j0 = 0; j0 < S; j0 += 4 * G) {        // four independent 128-bit loads in flight per thread
+        uint4 kr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * G + g;
+            kr[u] = j < S ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)j * 3 * H + H + c8 * 8)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * G + g;
+            float k[8];
+            unpack8_bf16(kr[u], k);
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part = fmaf(q[i], k[i], part);
+            for (int o = per_head >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (j < S && (c8 % per_head) == 0) {
+                const bool ok = (!key_valid || key_valid[(size_t)b * S + j]) && (!causal || j <= sq);
+                score[h * S + j] = ok ? part * scale : -1e9f;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- softmax statistics: one warp per head
+    for (int hh = threadIdx.x / 32; hh < heads; hh += 8) {
+        const int lane = threadIdx.x % 32;
+        float m = -INFINITY;
+        for (int j = lane; j < S; j += 32) m = fmaxf(m, score[hh * S + j]);
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float l = 0.f;
+        for (int j = lane; j < S; j += 32) {
+            const float p = expf(score[hh * S + j] - m);
+            score[hh * S + j] = p;
+            l += p;
+        }
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        if (lane == 0) inv_l[hh] = 1.0f / l;
+    }
+    __syncthreads();
+    // ---- context: sum_j p_j v_j over this thread's rows, then across the row groups
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j0 = g; j0 < S; j0 += 4 * G) {
+        uint4 vr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * G;
+            vr[u] = j < S ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)j * 3 * H + 2 * H + c8 * 8)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * G;
+            float v[8];
+            unpack8_bf16(vr[u], v);
+            const float p = j < S ? score[h * S + j] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, v[i], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(size_t)g * H + c8 * 8 + i] = acc[i];
+    __syncthreads();
+    if (g == 0) {
+        const float il = inv_l[h];
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int gg = 0; gg < G; ++gg) {           // fixed order: deterministic
+                a0 += red[(size_t)gg * H + c8 * 8 + i];
+                a1 += red[(size_t)gg * H + c8 * 8 + i + 1];
+            }
+            __nv_bfloat162 pk = __floats2bfloat162_rn(a0 * il, a1 * il);
+            w[i / 2] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        *reinterpret_cast<uint4*>(ctx_rows + (size_t)b * H + c8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+extern "C" int asme_b200_attn_row_fwd(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
+                                      const int64_t* only_row, void* ctx_rows, asme_stream_t stream) {
+    ASME_REQUIRE(qkv && only_row && ctx_rows, "attn_row_fwd: null argument");
+    ASME_REQUIRE(B >= 0 && S > 0 && heads > 0, "attn_row_fwd: bad shape B=%d S=%d heads=%d", B, S, heads);
+    ASME_REQUIRE(d % 8 == 0 && d >= 8 && d <= 256 && (d & (d - 1)) == 0, "attn_row_fwd: head size d=%d (supported: 8..256, power of two)", d);
+    const int H = heads * d;
+    ASME_REQUIRE(H <= 2048 && 256 % (H / 8) == 0, "attn_row_fwd: hidden size H=%d (H/8 must divide 256)", H);
+    const size_t smem = ((size_t)heads * S + 256 * 8 + heads) * sizeof(float);
+    ASME_REQUIRE(smem <= 200 * 1024, "attn_row_fwd: heads*S=%d does not fit shared memory", heads * S);
+    if (B == 0) return ASME_OK;
+    int rc = set_smem(attn_row_kernel, smem);
+    if (rc) return rc;
+    attn_row_kernel<<<B, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, key_valid, S, heads, d, causal, only_row,
+                                                           (__nv_bfloat16*)ctx_rows);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

@@ -246,6 +246,8 @@ def test_encode_rows_equals_full_encode_on_selected_rows():
         full, _ = model.encode(seq, seq.ne(0), {}, training=False)
         sel = model.encode_rows(seq, seq.ne(0), {}, rows)
         assert torch.equal(sel, ops.gather_rows(full, rows))
-        # one position per sequence: the last layer's attention computes only the query tile that holds it
+        # one position per sequence: the last layer's attention is the fp32 matrix-vector kernel; the tensor-core tile rounds the
+        # probabilities to bf16 (2^-9 relative) before P V, so the rows agree to that rounding, not bit for bit
         sel1 = model.encode_rows(seq, seq.ne(0), {}, rows, one_per_sequence=True)
-        assert torch.equal(sel1, sel)
+        assert float((sel1 - sel).norm() / sel.norm()) < 3e-3
+        torch.testing.assert_close(sel1, sel, rtol=2e-2, atol=2e-2 * float(sel.abs().max()))

@@ -157,3 +157,39 @@ def test_tc_attn_bwd_fully_masked_rows(ops, bwd_variant):
     ctx, st, keep = ops.tc_attn_fwd(qkv, valid, B, S, heads, True, save_stats=True)
     got = ops.tc_attn_bwd(qkv, valid, B, S, heads, True, ctx, d_ctx, st, keep)
     assert norm_err(got, want) < 1.5e-2
+
+
+@pytest.mark.parametrize("B,S,heads,d", CASES + [(3, 300, 8, 16), (2, 64, 1, 128), (4, 200, 2, 8)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attn_row_fwd_matches_reference_arithmetic(ops, B, S, heads, d, causal):
+    """one query position per sequence (asme_b200_attn_row_fwd): fp32 restatement of Attention.forward on the same bf16 q/k/v,
+    left padding so some query rows see no valid key (uniform attention, quirk Q4); output rounded to bf16 -> 2^-8 relative"""
+    gen = torch.Generator(device="cuda").manual_seed(B * 31 + S + heads + d)
+    for pad, use_mask in (("right", True), ("left", True), ("right", False)):
+        qkv, valid = make(gen, B, S, heads, d, pad=pad)
+        kv = valid if use_mask else None
+        pos = torch.randint(0, S, (B,), generator=gen, device="cuda")
+        pos[0] = 0
+        rows = torch.arange(B, device="cuda") * S + pos
+        got = ops.attn_row_fwd(qkv, kv, B, S, heads, causal, rows)
+        want = torch_attention(qkv, kv, B, S, heads, causal).index_select(0, rows)
+        assert got.shape == (B, heads * d) and got.dtype == torch.bfloat16
+        torch.testing.assert_close(got.float(), want, rtol=1e-2, atol=1e-2 * float(want.abs().max()))
+        assert norm_err(got, want) < 3e-3
+        assert torch.equal(got, ops.attn_row_fwd(qkv, kv, B, S, heads, causal, rows))          # deterministic
+
+
+def test_attn_row_fwd_rejects_unsupported_head_size(ops):
+    qkv = torch.zeros(4, 3 * 24, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="head size"):
+        ops.attn_row_fwd(qkv, None, 1, 4, 2, False, torch.zeros(1, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("B,S,heads,d", [(3, 200, 2, 32), (2, 256, 3, 64), (4, 70, 4, 16)])
+def test_tc_attn_fwd_rows_is_bit_identical_on_the_selected_rows(ops, B, S, heads, d):
+    gen = torch.Generator(device="cuda").manual_seed(S + d)
+    qkv, valid = make(gen, B, S, heads, d)
+    rows = torch.arange(B, device="cuda") * S + torch.randint(0, S, (B,), generator=gen, device="cuda")
+    full, _, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, True)
+    part = ops.tc_attn_fwd_rows(qkv, valid, B, S, heads, True, rows)
+    assert torch.equal(part.index_select(0, rows), full.index_select(0, rows))
