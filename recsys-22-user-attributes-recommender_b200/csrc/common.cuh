@@ -82,9 +82,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // Tensor-core (bf16 policy) epilogues: the GELU evaluations are what the FFN GEMM epilogues spend their issue slots on (erff is
-// ~25 instructions, erff + expf ~45).  Abramowitz & Stegun 7.1.26, |erf error| <= 1.5e-7 in exact arithmetic (~3e-7 here), which
-// is far below the bf16 rounding of the values these epilogues store; one MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe instructions,
-// and the gradient shares the exponential.  The fp32 strict-parity path keeps erff / expf.
+// ~25 instructions, erff + expf ~45; an Abramowitz & Stegun 7.1.26 erf with MUFU.EX2 / MUFU.RCP was 17).  These epilogues store
+// bf16 (2^-9 relative), so the erf form x * Phi(x) is evaluated as x * sigmoid(2u), u = x (a + b x^2 + c x^4): the classic
+// tanh form with one more term, coefficients from a minimax fit against 0.5 x (1 + erf(x / sqrt 2)) on [-8, 8]:
+// |error| <= 2.6e-5 absolute for every x (1/60 of a bf16 ulp at 1), derivative within 1.1e-4.  Seven instructions:
+// x^2 (clamped at 64, beyond which the sigmoid is saturated and the quartic would turn around), two FMAs for
+// w = -2 log2(e) (a + b x^2 + c x^4), x w, MUFU.EX2, 1 + e, MUFU.RCP, x * r.  Used where the epilogue stores bf16 only; an epilogue that also
+// writes an fp32 copy uses the A&S erf below (3e-7), and the fp32 strict-parity path keeps erff / expf.
 __device__ __forceinline__ float exp2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -95,27 +99,46 @@ __device__ __forceinline__ float rcp_approx(float x) {      // one MUFU.RCP (__f
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// returns erf(|x|) given e = exp(-x*x)
-__device__ __forceinline__ float erf_abs_fast(float ax, float e) {
-    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));       // argument >= 1: no denormal / overflow cases
+// erf form for the epilogues that also hand out an fp32 copy: Abramowitz & Stegun 7.1.26, |erf error| <= 3e-7 (17 instructions)
+__device__ __forceinline__ float erf_abs_as(float ax, float e) {   // erf(|x|) given e = exp(-x*x)
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
     return fmaf(-p * t, e, 1.0f);
 }
-__device__ __forceinline__ float gelu_erf_fast(float x) {
+__device__ __forceinline__ float gelu_erf_as(float x) {
     const float ax = fabsf(x) * 0.70710678118654752440f;
-    const float e = exp2_approx(-ax * ax * 1.4426950408889634f);
-    const float y = erf_abs_fast(ax, e);                       // erf(|x| / sqrt 2)
+    const float y = erf_abs_as(ax, exp2_approx(-ax * ax * 1.4426950408889634f));
     return 0.5f * x * (1.0f + copysignf(y, x));
 }
-__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+__device__ __forceinline__ float gelu_erf_grad_as(float x) {
     const float ax = fabsf(x) * 0.70710678118654752440f;
     const float e = exp2_approx(-ax * ax * 1.4426950408889634f);   // exp(-x^2 / 2)
-    const float y = erf_abs_fast(ax, e);
-    const float cdf = 0.5f * (1.0f + copysignf(y, x));
+    const float cdf = 0.5f * (1.0f + copysignf(erf_abs_as(ax, e), x));
     return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+#define GELU_FIT_A 7.97507884e-01f
+#define GELU_FIT_B 3.70056460e-02f
+#define GELU_FIT_C -3.51516788e-04f
+#define GELU_M2LOG2E -2.8853900817779268f               // -2 log2(e)
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float x2 = fminf(x * x, 64.0f);
+    float w = fmaf(x2, GELU_M2LOG2E * GELU_FIT_C, GELU_M2LOG2E * GELU_FIT_B);
+    w = fmaf(x2, w, GELU_M2LOG2E * GELU_FIT_A);
+    const float e = exp2_approx(x * w);                  // exp(-2u); +inf for very negative x -> rcp -> 0 -> -0
+    return x * rcp_approx(1.0f + e);
+}
+// d/dx [x sigmoid(v)], v = 2u: sigmoid + x sigmoid (1 - sigmoid) v', v' = 2 (a + 3 b x^2 + 5 c x^4)
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+    const float x2 = fminf(x * x, 64.0f);
+    float w = fmaf(x2, GELU_M2LOG2E * GELU_FIT_C, GELU_M2LOG2E * GELU_FIT_B);
+    w = fmaf(x2, w, GELU_M2LOG2E * GELU_FIT_A);
+    const float sg = rcp_approx(1.0f + exp2_approx(x * w));
+    float dv = fmaf(x2, 10.0f * GELU_FIT_C, 6.0f * GELU_FIT_B);
+    dv = fmaf(x2, dv, 2.0f * GELU_FIT_A);
+    return fmaf(x * sg * (1.0f - sg), dv, sg);
 }
 
 // Counter-based dropout generator: the mask is a pure function of (seed, site, element index), so the backward pass recomputes

@@ -157,8 +157,13 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
         tile_store64(t, w, reinterpret_cast<uint8_t*>(a.pre_act_bf16 + o0), (size_t)a.N * 2);
     }
     if (a.act == ASME_ACT_GELU) {
+        if (a.out_f32) {                 // an fp32 copy leaves the kernel: erf to 3e-7
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = gelu_erf_fast(v[c]);
+            for (int c = 0; c < 32; ++c) v[c] = gelu_erf_as(v[c]);
+        } else {                         // bf16 only: the 7-instruction form (2.6e-5 absolute, far inside the bf16 rounding)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = gelu_erf_fast(v[c]);
+        }
     }
     if (a.gelu_grad_of) {
         uint4 w[4];
@@ -169,8 +174,9 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
-                v[8 * u + 2 * e] *= gelu_erf_grad_fast(__low2float(z2));
-                v[8 * u + 2 * e + 1] *= gelu_erf_grad_fast(__high2float(z2));
+                const float z0 = __low2float(z2), z1 = __high2float(z2);
+                v[8 * u + 2 * e] *= a.out_f32 ? gelu_erf_grad_as(z0) : gelu_erf_grad_fast(z0);
+                v[8 * u + 2 * e + 1] *= a.out_f32 ? gelu_erf_grad_as(z1) : gelu_erf_grad_fast(z1);
             }
         }
     }

@@ -80,6 +80,13 @@ def test_tc_gemm_epilogue_matches_oracle(ops):
     zd = zz.double()
     grad = 0.5 * (1 + torch.erf(zd / math.sqrt(2))) + zd * torch.exp(-0.5 * zd * zd) / math.sqrt(2 * math.pi)
     torch.testing.assert_close(got.double(), (dy.double() @ w2.double()) * grad, rtol=1e-5, atol=1e-5)
+    # bf16-only outputs (what the encoder's feed-forward uses) take the 7-instruction GELU: x sigmoid(2u) with a fitted quintic u,
+    # |error| <= 2.6e-5 absolute against the erf form (1.1e-4 for the derivative) before the bf16 rounding of the store
+    out16 = ops.tc_gemm(a, w, bias=bias, act=1, out_f32=False, out_bf16=True)["bf16"]
+    torch.testing.assert_close(out16.double(), O.gelu_erf(z), rtol=2 ** -8, atol=4e-5)
+    got16 = ops.tc_gemm(dy, w2, b_is_kn=True, gelu_grad_of=zz, out_f32=False, out_bf16=True)["bf16"]
+    base = dy.double() @ w2.double()
+    torch.testing.assert_close(got16.double(), base * grad, rtol=2 ** -8, atol=2e-4 * float(base.abs().max()))
 
 
 def test_tc_gemm_dropout_uses_the_shared_stream(ops):
