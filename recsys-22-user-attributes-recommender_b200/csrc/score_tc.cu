@@ -158,6 +158,7 @@ enum { EPI_TOPK = 0, EPI_CE = 1, EPI_PROBE = 2 };   // EPI_PROBE: diagnostic, ep
 struct ScoreTcArgs {
     int R, Vloc, v0, k, kch, stages;
     int last_ksteps;             // K-steps (of 16 columns) in the last 64-wide chunk: 4, or fewer when Kp % 64 != 0 (bias columns)
+    int pend_cap;                // FIFO entries per epilogue thread (drained when more than pend_cap - 8 are pending)
     int tail16;                  // 1: the last chunk is ONE K-step staged as a 16-column box with the 32-byte swizzle (tmAt / tmBt)
     int n_tiles, tiles_per_split;
     int tile_lo, tile_hi;        // this launch sweeps tiles [split*tps + tile_lo, min(n_tiles, split*tps + tile_hi)) of every split
@@ -227,7 +228,7 @@ __device__ __forceinline__ void tie_insert(float (&lv)[KC], int (&li)[KC], float
 // (8 bytes into a per-thread shared-memory FIFO) where they are found and INSERTED later in batches: the warp drains all
 // its FIFOs together when any of them may overflow and once at the end, so the serial insertion code runs with many
 // lanes active.  FIFO order == stream order == ascending item id, so ties still resolve to the lowest id.
-#define PEND_CAP 16             // FIFO entries per epilogue thread; drained when more than PEND_CAP - 8 are pending
+#define PEND_CAP_MAX 16         // FIFO entries per epilogue thread (run-time a.pend_cap <= this); drained when more than pend_cap - 8 are pending
 template <int KC>
 __device__ __forceinline__ void pend_drain(float (&lv)[KC], int (&li)[KC], float& thr, float thr0, int& cnt, const uint2* pend,
                                            int stride) {
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                         const float mc = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
                         if (__any_sync(0xffffffffu, mc > thr)) {      // rare once the thresholds have converged
                             if (a.sample_mode) {      // warp-uniform
-                                if (__any_sync(0xffffffffu, cnt > PEND_CAP - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
+                                if (__any_sync(0xffffffffu, cnt > a.pend_cap - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
                                 if (mc > thr) {
                                     pend[(size_t)cnt * (WGS * 128)] = make_uint2(__float_as_uint(mc), (uint32_t)(a.v0 + col0));
                                     ++cnt;
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                             } else
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                if (__any_sync(0xffffffffu, cnt > PEND_CAP - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
+                                if (__any_sync(0xffffffffu, cnt > a.pend_cap - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
                                 if (m8[j] > thr) {
 #pragma unroll
                                     for (int c = 0; c < 8; ++c) {
@@ -802,6 +803,8 @@ static int g_pair = 0;             // 1: CTA pairs (cta_group::2) whenever there
                                    // no gain (the single-CTA pipeline already runs at the power-capped tensor peak, it is not shared-
                                    // memory bound) and the pair couples the two epilogues' jitter -> off by default, kept as a knob
 static int g_tail16 = 1;           // stage a 16-column K tail (Kp = 64 k + 16: folded bias) as a 32-byte-swizzled quarter-size box
+static int g_pend_cap = 12;        // candidate FIFO depth per epilogue thread: 8 bytes x 512 threads per entry come out of the B ring's
+                                   // shared memory -- 12 instead of 16 buys the ring a fourth slot at Kp = 144 (three K chunks per tile)
 static int g_pdl = 0;              // programmatic dependent launch between the launches of one top-k call
 int g_pdl_merge = 0;            // measured: slower (early-scheduled dependents take SM resources from the sweep) -> off, kept as a knob
 
@@ -814,6 +817,7 @@ extern "C" int asme_b200_tc_score_tune(int knob, int value) {
         case 4: g_pair = value ? 1 : 0; break;
         case 5: g_pdl = g_pdl_merge = value ? 1 : 0; break;
         case 6: g_tail16 = value ? 1 : 0; break;
+        case 7: ASME_REQUIRE(value >= 8 && value <= PEND_CAP_MAX, "tc_score_tune: FIFO depth must be 8..16"); g_pend_cap = value; break;
         default: ASME_REQUIRE(false, "tc_score_tune: unknown knob %d", knob);
     }
     return ASME_OK;
@@ -838,7 +842,7 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
     p->wgs = topk ? g_epi_wgs : g_epi_wgs_other;
     p->parts = p->splits;      // the warpgroups of a CTA fold their results before writing
     const size_t fixed = 1024 + (size_t)p->kch * A_CHUNK_BYTES + ((sizeof(ScoreTcBarriers) + 15) & ~(size_t)15) +
-                         (topk ? (size_t)p->wgs * 128 * PEND_CAP * sizeof(uint2) : 0);
+                         (topk ? (size_t)p->wgs * 128 * g_pend_cap * sizeof(uint2) : 0);
     const size_t stage = (size_t)B_CHUNK_BYTES / (p->pair ? 2 : 1);
     const size_t budget = 227 * 1024;
     ASME_REQUIRE(fixed + 2 * stage <= budget, "tc score: shared memory budget exceeded (Kp=%d)", Kp);
@@ -962,7 +966,7 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     const int n_sample = topk ? sample_tiles(p) : 0;
     const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = k; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
     a.bias = bias; a.target = target; a.target_score = target_score_in; a.thr_floor = g_thr_floor;
     a.pv = (float*)ws;
@@ -1012,7 +1016,7 @@ extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, 
     rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
     if (rc) return rc;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.k = read_tmem ? 1 : 0;
+    a.R = R; a.Vloc = Vloc; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap; a.k = read_tmem ? 1 : 0;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_lo = 0; a.tile_hi = p.tiles_per_split;
     return launch_score<EPI_PROBE, 0, false>(tmA, tmB, a, p, (cudaStream_t)stream);
 }
@@ -1045,7 +1049,7 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
     if (rc) return rc;
     ScoreTcArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = 0; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split;
     a.bias = bias; a.target = target; a.target_score = nullptr; a.thr_floor = -INFINITY;
     a.pv = (float*)ws;
