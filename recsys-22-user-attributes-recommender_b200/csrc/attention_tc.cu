@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             const uint32_t idesc_o = at_idesc(128, d, 0, 1);
             const int ks_qk = d / 16;                        // K-steps of Q K^T
             const int ks_pv = (S + 15) / 16;                 // K-steps of P V
-            mbar_wait(&sh->loaded, 0);
+            mbar_wait_lean(&sh->loaded, 0);
             tc_fence_after();
             auto issue_s = [&](int u) {
                 const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             issue_s(0);
             for (int u = 0; u < units; ++u) {
                 const int hh = u / n_qt;
-                mbar_wait(&sh->p_full, (uint32_t)u & 1u);
+                mbar_wait_lean(&sh->p_full, (uint32_t)u & 1u);
                 tc_fence_after();
                 for (int ks = 0; ks < ks_pv; ++ks) {
                     const uint64_t pd = smem_desc_advance(smem_desc_sw128(smem_u32(sP + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             const bool q_ok = qi < S;
             const long long bh = (long long)b * a.heads + head;
             const int q_warp_min = qt * 128 + q4 * 32;       // smallest query index of this warp (causal fast-path test)
-            mbar_wait(&sh->s_full, (uint32_t)u & 1u);
+            mbar_wait_lean(&sh->s_full, (uint32_t)u & 1u);
             tc_fence_after();
             // ---- pass 1: partial row maximum over this warpgroup's key columns
             float m = -INFINITY;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
             tc_fence_before();
             mbar_arrive_warp(&sh->p_full);
             // ---- O = P V done: normalise and store (each warpgroup half of the head's columns)
-            mbar_wait(&sh->o_full, (uint32_t)u & 1u);
+            mbar_wait_lean(&sh->o_full, (uint32_t)u & 1u);
             tc_fence_after();
             asm volatile("bar.sync 2, 256;" ::: "memory");   // both partial sums are in shared memory
             l += sh->xl[wg ^ 1][r];
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            mbar_wait(&sh->loaded, 0);
+            mbar_wait_lean(&sh->loaded, 0);
             tc_fence_after();
             const int ks_d = d / 16;
             // sub-tile i of a head: sweep = i / (n_t*n_t), rt = row tile, ct = column tile
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
                     const int ncols = min(128, S - ct * 128);
                     const int ks_c = (ncols + 15) / 16;
                     const uint32_t idesc_acc = at_idesc(128, d, 0, 1);
-                    mbar_wait(&sh->x_full, (uint32_t)g & 1u);
+                    mbar_wait_lean(&sh->x_full, (uint32_t)g & 1u);
                     tc_fence_after();
                     const uint32_t acc_on = ct != 0;          // first column tile of a row tile overwrites the accumulators
                     const uint32_t coff = (uint32_t)(hh * d * 2);
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
                 const bool row_ok = row < S;
                 const int ncols = min(128, S - ct * 128);
                 const int warp_row0 = rt * 128 + q4 * 32;      // first row of this warp
-                mbar_wait(&sh->t_full, (uint32_t)g & 1u);
+                mbar_wait_lean(&sh->t_full, (uint32_t)g & 1u);
                 tc_fence_after();
                 float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
                 if (sweep == 0 && row_ok) rc = sh->qc[row];
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
                 if (ct == n_t - 1) {
                     // all column tiles of this row tile accumulated: store dQ (sweep A) or dK, dV (sweep B); each warpgroup
                     // stores half of the head's columns (d = 16: warpgroup 0 stores everything)
-                    mbar_wait(&sh->acc_done, (uint32_t)g & 1u);
+                    mbar_wait_lean(&sh->acc_done, (uint32_t)g & 1u);
                     tc_fence_after();
                     const int n_out = sweep == 0 ? 1 : 2;
                     const int dcols = d >= 32 ? d / 2 : d;
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            mbar_wait(&sh->loaded, 0);
+            mbar_wait_lean(&sh->loaded, 0);
             tc_fence_after();
             const int ks_d = d / 16;
             auto issue_t = [&](int hh, int i) {
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                     const int ct = i / n_t, rt = i % n_t;
                     const int ks_c = (min(128, S - ct * 128) + 15) / 16;      // K-steps over the keys of the tile
                     const int ks_r = (min(128, S - rt * 128) + 15) / 16;      // K-steps over the queries of the tile
-                    mbar_wait(&sh->x_full, (uint32_t)g & 1u);
+                    mbar_wait_lean(&sh->x_full, (uint32_t)g & 1u);
                     tc_fence_after();
                     const uint32_t tm_dq = tm_dq0 + (uint32_t)(rt * d);
                     for (int ks = 0; ks < ks_c; ++ks) {       // dQ[rt] += dS K[ct]
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                 const bool row_ok = row < S;
                 const int ncols = min(128, S - ct * 128);
                 const int warp_row0 = rt * 128 + q4 * 32;
-                mbar_wait(&sh->t_full, (uint32_t)g & 1u);
+                mbar_wait_lean(&sh->t_full, (uint32_t)g & 1u);
                 tc_fence_after();
                 float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
                 if (row_ok) rc = sh->qc[row];
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                 mbar_arrive_warp(&sh->x_full);
                 const bool store_kv = rt == n_t - 1, store_q = ct == n_t - 1;
                 if (store_kv || store_q) {
-                    mbar_wait(&sh->acc_done, (uint32_t)g & 1u);
+                    mbar_wait_lean(&sh->acc_done, (uint32_t)g & 1u);
                     tc_fence_after();
                     // the head's d output columns are stored in 16-column pieces dealt round-robin to the warpgroups
                     {

@@ -139,7 +139,8 @@ __device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint4 (&w)[4])
 // epilogue of one 32-column chunk of the 32 output rows of a warp (shared by both tall kernels; ALL lanes call it): bias,
 // pre-activation copy, GELU, gelu' multiply, dropout, residual, block-end dropout, fp32 / bf16 stores.
 // `row` = this lane's row (row0 + lane, may be >= M), nc = first column of the chunk.
-template <bool LN = false>
+// FAST: the cheap GELU forms (the caller passes it when no fp32 copy of the result leaves the kernel)
+template <bool LN = false, bool FAST = false>
 __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (&v)[32], const int row, const int nc, const float inv_keep,
                                                     float& ln_s, float& ln_s2, const WarpTile& t) {
     const size_t o = (size_t)row * a.N + nc;                       // element index of v[0] (dropout stream index)
@@ -157,12 +158,12 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
         tile_store64(t, w, reinterpret_cast<uint8_t*>(a.pre_act_bf16 + o0), (size_t)a.N * 2);
     }
     if (a.act == ASME_ACT_GELU) {
-        if (a.out_f32) {                 // an fp32 copy leaves the kernel: erf to 3e-7
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = gelu_erf_as(v[c]);
-        } else {                         // bf16 only: the 7-instruction form (2.6e-5 absolute, far inside the bf16 rounding)
+        if (FAST) {                      // bf16 only: the 7-instruction form (2.6e-5 absolute, far inside the bf16 rounding)
 #pragma unroll
             for (int c = 0; c < 32; ++c) v[c] = gelu_erf_fast(v[c]);
+        } else {                         // an fp32 copy leaves the kernel: erf to 3e-7
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = gelu_erf_as(v[c]);
         }
     }
     if (a.gelu_grad_of) {
@@ -175,8 +176,8 @@ __device__ __forceinline__ void tall_epilogue_chunk(const TcGemmArgs& a, float (
             for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
                 const float z0 = __low2float(z2), z1 = __high2float(z2);
-                v[8 * u + 2 * e] *= a.out_f32 ? gelu_erf_grad_as(z0) : gelu_erf_grad_fast(z0);
-                v[8 * u + 2 * e + 1] *= a.out_f32 ? gelu_erf_grad_as(z1) : gelu_erf_grad_fast(z1);
+                v[8 * u + 2 * e] *= FAST ? gelu_erf_grad_fast(z0) : gelu_erf_grad_as(z0);
+                v[8 * u + 2 * e + 1] *= FAST ? gelu_erf_grad_fast(z1) : gelu_erf_grad_as(z1);
             }
         }
     }
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
             for (int c = 0; c < kch; ++c) {
                 const int s = c % stages;
                 const uint32_t ph = (uint32_t)(c / stages) & 1u;
-                mbar_wait(&bars->empty[s], ph ^ 1u);
+                mbar_wait_lean(&bars->empty[s], ph ^ 1u);
                 uint8_t* sA = smem + (size_t)s * slot;
                 uint8_t* sB = sA + a_bytes;
                 mbar_arrive_expect_tx(&bars->full[s], (uint32_t)(a_bytes + b_bytes));
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
             for (int c = 0; c < kch; ++c) {
                 const int s = c % stages;
                 const uint32_t ph = (uint32_t)(c / stages) & 1u;
-                mbar_wait(&bars->full[s], ph);
+                mbar_wait_lean(&bars->full[s], ph);
                 tc_fence_after();
                 uint8_t* sA = smem + (size_t)s * slot;
                 uint8_t* sB = sA + a_bytes;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
         const float inv_keep = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
         const int n_chunks = NT / 32;
         const int c_lo = wg == 0 ? 0 : (n_chunks + 1) / 2, c_hi = wg == 0 ? (n_chunks + 1) / 2 : n_chunks;
-        mbar_wait(&bars->done, 0);
+        mbar_wait_lean(&bars->done, 0);
         tc_fence_after();
         for (int nn = c_lo * 32; nn < c_hi * 32; nn += 32) {
             float v[32];
@@ -327,7 +328,8 @@ __global__ void __launch_bounds__(G_TALL_THREADS) tc_gemm_tall_kernel(const __gr
             tmem_ld_wait();
             float unused_s = 0.f, unused_s2 = 0.f;
             const WarpTile wt{nullptr, lane, a.M - (row - lane)};
-            tall_epilogue_chunk<false>(a, v, row, n0 + nn, inv_keep, unused_s, unused_s2, wt);
+            if (a.out_f32) tall_epilogue_chunk<false, false>(a, v, row, n0 + nn, inv_keep, unused_s, unused_s2, wt);
+            else tall_epilogue_chunk<false, true>(a, v, row, n0 + nn, inv_keep, unused_s, unused_s2, wt);
         }
     }
     tc_fence_before();
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS, 2) tc_gemm_persist_kernel(cons
             uint32_t ph = 0;
             for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
                 for (int c = 0; c < kch; ++c) {
-                    mbar_wait(&bars->empty[s], ph ^ 1u);
+                    mbar_wait_lean(&bars->empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&bars->full[s], (uint32_t)a_bytes);
                     tma_load_2d(sA + (size_t)s * a_bytes, &tmA, &bars->full[s], c * CHUNK_K, mt * G_BM);
                     if (++s == stages) { s = 0; ph ^= 1u; }
@@ -421,17 +423,17 @@ __global__ void __launch_bounds__(G_TALL_THREADS, 2) tc_gemm_persist_kernel(cons
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = idesc_major(G_BM, NT, 0, B_MN ? 1 : 0);
-            mbar_wait(&bars->b_full, 0);
+            mbar_wait_lean(&bars->b_full, 0);
             tc_fence_after();
             int s = 0, i = 0;
             uint32_t ph = 0;
             for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++i) {
                 const int as = i & 1;
-                mbar_wait(&bars->tempty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                mbar_wait_lean(&bars->tempty[as], ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * G_NT);
                 for (int c = 0; c < kch; ++c) {
-                    mbar_wait(&bars->full[s], ph);
+                    mbar_wait_lean(&bars->full[s], ph);
                     tc_fence_after();
                     const uint8_t* pa = sA + (size_t)s * a_bytes;
                     const uint8_t* pb = sB + (size_t)c * b_slot;
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS, 2) tc_gemm_persist_kernel(cons
         const int wg = (warp - 4) / 4;                       // both warpgroups own all 128 rows, each half of the 32-column chunks
         const int q = warp % 4;
         const float inv_keep = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f;
+        const bool fast_act = a.out_f32 == nullptr;          // bf16-only results: cheap GELU forms (two specialised epilogue bodies)
         const int n_chunks = NT / 32;
         const int c_lo = wg == 0 ? 0 : (n_chunks + 1) / 2, c_hi = wg == 0 ? (n_chunks + 1) / 2 : n_chunks;
         int i = 0;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(G_TALL_THREADS, 2) tc_gemm_persist_kernel(cons
             const int row = mt * G_BM + q * 32 + lane;
             const bool row_ok = row < a.M;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G_NT);
-            mbar_wait(&bars->tfull[as], (uint32_t)(i >> 1) & 1u);
+            mbar_wait_lean(&bars->tfull[as], (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             if (c_lo == c_hi) {                              // a warpgroup without columns (NT = 32) still hands the stage back
                 tc_fence_before();
@@ -485,7 +488,8 @@ __global__ void __launch_bounds__(G_TALL_THREADS, 2) tc_gemm_persist_kernel(cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->tempty[as]);
                 }
-                tall_epilogue_chunk<LN>(a, v, row, n0 + nn, inv_keep, ln_s, ln_s2, wt);
+                if (fast_act) tall_epilogue_chunk<LN, true>(a, v, row, n0 + nn, inv_keep, ln_s, ln_s2, wt);
+                else tall_epilogue_chunk<LN, false>(a, v, row, n0 + nn, inv_keep, ln_s, ln_s2, wt);
             }
             if (LN) {
                 // row statistics: the two warpgroups hold disjoint column ranges of the same rows -> exchange the partial sums,
@@ -692,7 +696,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
             for (int sl = s0; sl < s1; ++sl, ++i) {
                 const int s = i % W_STAGES;
                 const uint32_t ph = (uint32_t)(i / W_STAGES) & 1u;
-                mbar_wait(&bars->empty[s], ph ^ 1u);
+                mbar_wait_lean(&bars->empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&bars->full[s], (uint32_t)((2 + nb_x) * blk));
                 uint8_t* base = smem + (size_t)s * stage_bytes;
                 // dY columns beyond N are out of bounds of the tensor map: zero-filled, the extra output rows are not stored
@@ -709,7 +713,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
             for (int sl = s0; sl < s1; ++sl, ++i) {
                 const int s = i % W_STAGES;
                 const uint32_t ph = (uint32_t)(i / W_STAGES) & 1u;
-                mbar_wait(&bars->full[s], ph);
+                mbar_wait_lean(&bars->full[s], ph);
                 tc_fence_after();
                 uint8_t* base = smem + (size_t)s * stage_bytes;
 #pragma unroll
@@ -728,7 +732,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_wgrad_kernel(const __grid_con
     } else if (warp >= 4) {
         const int q = warp % 4;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        mbar_wait(&bars->done, 0);
+        mbar_wait_lean(&bars->done, 0);
         tc_fence_after();
         float* out = a.partial + (size_t)split * a.N * a.K;
         const int n = nrow0 + q * 32 + lane;               // output row (= dY column)

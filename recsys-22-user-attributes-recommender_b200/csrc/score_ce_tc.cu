@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
             for (int ct = ct0; ct < ct1; ++ct, ++i) {
                 const int s = i % stages;
                 const uint32_t ph = (uint32_t)(i / stages) & 1u;
-                mbar_wait(&sh->empty[s], ph ^ 1u);
+                mbar_wait_lean(&sh->empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&sh->full[s], (uint32_t)kch * CE_CHUNK_BYTES);
                 for (int c = 0; c < kch; ++c)
                     tma_load_2d(sCol + ((size_t)s * kch + c) * CE_CHUNK_BYTES, &tmCol, &sh->full[s], c * CHUNK_K, ct * CE_TILE);
@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
         if (lane == 0) {
             const uint32_t idesc_t = ce_idesc(CE_TILE, CE_TILE, 0, 0);
             const uint32_t idesc_acc = ce_idesc(CE_TILE, a.Kp, 0, 1);
-            mbar_wait(&sh->row_full, 0);
+            mbar_wait_lean(&sh->row_full, 0);
             tc_fence_after();
             auto issue_t = [&](int i) {
                 const int s = i % stages;
                 const uint32_t ph = (uint32_t)(i / stages) & 1u;
-                mbar_wait(&sh->full[s], ph);
+                mbar_wait_lean(&sh->full[s], ph);
                 tc_fence_after();
                 for (int c = 0; c < kch; ++c) {
                     const uint64_t ad = smem_desc_sw128(smem_u32(sRow + (size_t)c * CE_CHUNK_BYTES));
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
             if (n > 0) issue_t(0);
             for (int i = 0; i < n; ++i) {
                 const int s = i % stages;
-                mbar_wait(&sh->x_full, (uint32_t)i & 1u);
+                mbar_wait_lean(&sh->x_full, (uint32_t)i & 1u);
                 tc_fence_after();
                 // acc[128 x Kp] += G[128 x 128 columns] . ColTile[128 columns x Kp]   (column tile consumed MN-major)
 #pragma unroll
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            mbar_wait(&sh->t_full, (uint32_t)i & 1u);
+            mbar_wait_lean(&sh->t_full, (uint32_t)i & 1u);
             tc_fence_after();
 #pragma unroll 1
             for (int c16 = wg * 4; c16 < wg * 4 + 4; ++c16) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
         // ---- accumulators -> partial outputs (each warpgroup half of the Kp columns)
         float* out = a.partial + (size_t)split * n_rows_total * a.H;
         if (n > 0) {
-            mbar_wait(&sh->acc_done, 0);
+            mbar_wait_lean(&sh->acc_done, 0);
             tc_fence_after();
         }
         const int half = a.Kp / 2;
