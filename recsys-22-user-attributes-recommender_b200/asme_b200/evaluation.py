@@ -1,0 +1,155 @@
+"""Batch evaluators of the ``predict`` command (asme/core/evaluation/evaluation.py) on the fused evaluation output.
+
+The reference evaluators receive the dense ``(N, I)`` logits of a batch and run ``softmax`` + a full ``sort`` over the
+catalog to keep ``num_predictions`` items (evaluation.py:176-178, :222-224).  Here ``logits`` may also be a
+:class:`asme_b200.metrics.FusedPredictions` carrying the top-n list and the row log-sum-exp straight from the scoring
+sweeps (``model.recommend`` / ``module.predict_topn``): the softmax score of a listed item is ``exp(logit - lse)`` and the
+list is already ordered best-first (ties -> lowest item id, where ``torch.sort`` leaves the order of ties open).
+Same class names, constructor arguments, headers and return shapes as the reference; dense tensors still work (CPU
+included) and follow the reference arithmetic literally.
+"""
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from .metrics import FusedPredictions
+
+ITEM_SEQ_ENTRY_NAME = "item"                 # asme/data/datasets/__init__.py
+TARGET_ENTRY_NAME = "item.target"
+SAMPLE_IDS = "sample_ids"
+SESSION_IDENTIFIER = "session_identifier"
+
+
+def _vocab_lookup(item_tokenizer) -> np.ndarray:
+    """id -> token array (evaluation.py:48-52)"""
+    tokens = np.asarray(item_tokenizer.vocabulary.tokens())
+    ids = np.asarray(item_tokenizer.vocabulary.ids())
+    lookup = np.empty(max(ids) + 1, dtype=tokens.dtype)
+    lookup[ids] = tokens
+    return lookup
+
+
+def top_predictions(logits, num_predictions: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(softmax scores, item ids) of the ``num_predictions`` best items per sample, best first, as numpy arrays"""
+    if isinstance(logits, FusedPredictions):
+        if logits.topk_idx is None or logits.topk_idx.shape[1] < num_predictions:
+            have = 0 if logits.topk_idx is None else logits.topk_idx.shape[1]
+            raise RuntimeError(f"asme_b200: the fused prediction holds {have} items per sample, {num_predictions} requested")
+        if logits.lse is None:
+            raise RuntimeError("asme_b200: this fused prediction carries no log-sum-exp (use model.recommend / module.predict_topn)")
+        val = logits.topk_val[:, :num_predictions].float()
+        scores = torch.exp(val - logits.lse.float().unsqueeze(1))
+        return scores.cpu().numpy(), logits.topk_idx[:, :num_predictions].to(torch.int64).cpu().numpy()
+    softmax = torch.softmax(logits, dim=-1)
+    scores, indices = torch.sort(softmax, dim=-1, descending=True)
+    return scores[:, :num_predictions].cpu().numpy(), indices[:, :num_predictions].cpu().numpy()
+
+
+class BatchEvaluator:
+    """evaluation.py:12-40"""
+
+    def evaluate(self, batch_index: int, batch: Dict[str, Any], logits) -> List[Any]:
+        raise NotImplementedError
+
+    def get_header(self) -> List[str]:
+        return self.header
+
+    def eval_samplewise(self) -> bool:
+        raise NotImplementedError
+
+
+class LogInputEvaluator(BatchEvaluator):
+    """the input sequence as tokens, special tokens removed (evaluation.py:43-75)"""
+
+    def __init__(self, item_tokenizer):
+        self.item_tokenizer = item_tokenizer
+        self.header = ["input"]
+        self.vocab_lookup = _vocab_lookup(item_tokenizer)
+        self.special_tokens = np.asarray(item_tokenizer.get_special_token_ids())
+
+    def eval_samplewise(self) -> bool:
+        return True
+
+    def evaluate(self, batch_index, batch, logits) -> List[Any]:
+        ids = batch[ITEM_SEQ_ENTRY_NAME]
+        input_ids = np.asarray(ids.cpu() if isinstance(ids, torch.Tensor) else ids)
+        tokens = self.vocab_lookup[input_ids]
+        keep = np.isin(input_ids, self.special_tokens, invert=True)
+        return [tokens[i][keep[i]].tolist() for i in range(tokens.shape[0])]
+
+
+class ExtractSampleIdEvaluator(BatchEvaluator):
+    """sample id, ``<id>_<pos>`` when the batch carries sequence positions (evaluation.py:78-118)"""
+
+    def __init__(self, use_session_id: bool = False):
+        self.header = ["SID"]
+        self.use_session_id = use_session_id
+
+    def eval_samplewise(self) -> bool:
+        return True
+
+    def evaluate(self, batch_index, batch, logits) -> List[Any]:
+        sample_ids = batch[SESSION_IDENTIFIER] if self.use_session_id else batch[SAMPLE_IDS].tolist()
+        positions = batch["pos"].tolist() if "pos" in batch else None
+        n = logits.size()[0] if isinstance(logits, FusedPredictions) else logits.shape[0]
+        return [sample_ids[i] if positions is None else f"{sample_ids[i]}_{positions[i]}" for i in range(n)]
+
+
+class TrueTargetEvaluator(BatchEvaluator):
+    """the true target as a one-element token list (evaluation.py:121-146)"""
+
+    def __init__(self, item_tokenizer):
+        self.header = ["target"]
+        self.item_tokenizer = item_tokenizer
+        self.vocab_lookup = _vocab_lookup(item_tokenizer)
+
+    def eval_samplewise(self) -> bool:
+        return True
+
+    def evaluate(self, batch_index, batch, logits) -> List[Any]:
+        targets = batch[TARGET_ENTRY_NAME].cpu().numpy()
+        return [[t] for t in self.vocab_lookup[targets].tolist()]
+
+
+class _TopNEvaluator(BatchEvaluator):
+    def __init__(self, item_tokenizer, num_predictions: int, selected_items=None):
+        self.item_tokenizer = item_tokenizer
+        self.num_predictions = num_predictions
+        self.selected_items = selected_items
+        self.filter_items = np.asarray(self.selected_items)
+
+    def eval_samplewise(self) -> bool:
+        return False
+
+    def _filtered(self, values: np.ndarray, indices: np.ndarray) -> List[Any]:
+        """the reference filters AFTER cutting to num_predictions: fewer than num_predictions entries may remain"""
+        if self.selected_items is None:
+            return values.tolist()
+        keep = np.isin(indices, self.filter_items)
+        return [values[i][keep[i]].tolist() for i in range(values.shape[0])]
+
+
+class ExtractScoresEvaluator(_TopNEvaluator):
+    """softmax scores of the recommended items (evaluation.py:149-189)"""
+
+    def __init__(self, item_tokenizer, num_predictions: int, selected_items=None):
+        super().__init__(item_tokenizer, num_predictions, selected_items)
+        self.header = ["score"]
+
+    def evaluate(self, batch_index, batch, logits) -> List[Any]:
+        scores, indices = top_predictions(logits, self.num_predictions)
+        return self._filtered(scores, indices)
+
+
+class ExtractRecommendationEvaluator(_TopNEvaluator):
+    """the recommended items as tokens (evaluation.py:192-236)"""
+
+    def __init__(self, item_tokenizer, num_predictions: int, selected_items=None):
+        super().__init__(item_tokenizer, num_predictions, selected_items)
+        self.header = ["recommendation"]
+        self.vocab_lookup = _vocab_lookup(item_tokenizer)
+
+    def evaluate(self, batch_index, batch, logits) -> List[Any]:
+        _, indices = top_predictions(logits, self.num_predictions)
+        return self._filtered(self.vocab_lookup[indices], indices)

@@ -175,8 +175,10 @@ class FusedPredictions:
     target rank and the top-k list, produced inside the scoring kernel (the logits never reached HBM)."""
 
     def __init__(self, rank: torch.Tensor, topk_idx: torch.Tensor, topk_val: torch.Tensor, target_score: torch.Tensor,
-                 num_items: int, scorer=None):
+                 num_items: int, scorer=None, lse: Optional[torch.Tensor] = None):
         self.rank, self.topk_idx, self.topk_val, self.target_score, self.num_items = rank, topk_idx, topk_val, target_score, num_items
+        # log-sum-exp of every row over the whole catalog (predict: softmax score of a listed item = exp(topk_val - lse))
+        self.lse = lse
         # scorer(items (N,I) int64) -> (N,I) fp32 scores of chosen items for the same rows: what the item-subset samplers gather
         self.scorer = scorer
 
@@ -187,7 +189,8 @@ class FusedPredictions:
         return self.scorer(items)
 
     def size(self):
-        return torch.Size([self.rank.shape[0], self.num_items])
+        n = self.rank.shape[0] if self.rank is not None else self.topk_idx.shape[0]
+        return torch.Size([n, self.num_items])
 
 
 class MetricsSample:

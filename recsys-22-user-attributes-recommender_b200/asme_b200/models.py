@@ -448,6 +448,35 @@ class TransformerRecommenderModel(ArenaModule):
         out["scorer"] = lambda items, rows_=m_rows: ops.score_items(rows_, *self.projection_operands(), items)
         return out
 
+    @torch.no_grad()
+    def recommend(self, seq, padding_mask, attrs, n: int, rows: Optional[torch.Tensor] = None, select: str = "mask",
+                  mask_id: int = MASK_TOKEN_ID, rows_one_per_sequence: bool = False):
+        """top-``n`` recommendation of the ``predict`` command without dense logits: dict(topk_idx (B,n) int32 best first,
+        ties -> lowest id; topk_val (B,n) logits; lse (B) log-sum-exp over the whole catalog), i.e. everything
+        ``softmax(logits).sort(descending=True)[:, :n]`` (evaluation/evaluation.py:176-178, :222-224) yields: the softmax score
+        of an item is ``exp(logit - lse)``.  Two sweeps over the catalog (top-n, max / sum-exp); n <= 32."""
+        if rows is None:
+            rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
+            rows_one_per_sequence = True
+        m_rows, _ = self.modify(self.encode_rows(seq, padding_mask, attrs, rows, one_per_sequence=rows_one_per_sequence))
+        return self._recommend_rows(m_rows, n)
+
+    def _recommend_rows(self, m_rows, n: int):
+        if not 1 <= n <= 32:
+            raise ValueError(f"asme_b200: the fused top-n list holds 1..32 entries, got {n}")
+        zero = torch.zeros(m_rows.shape[0], dtype=torch.int64, device=m_rows.device)
+        if self.precision == "bf16":
+            wb, folded = self.projection_operands_folded()
+            hb = ops.cast_bf16_ext(m_rows) if folded else ops.cast_bf16(m_rows, ld_out=wb.shape[1])
+            o = ops.tc_score_topk(hb, wb, None, n)
+            rmax, rsum, _ = ops.tc_score_ce_partial(hb, wb, None, zero)
+        else:
+            w, b = self.projection_operands()
+            val, idx, _, _ = ops.score_topk_rank(m_rows, w, b, n, zero, ops.score_targets(m_rows, w, b, zero))
+            o = dict(topk_val=val, topk_idx=idx)
+            rmax, rsum, _ = ops.score_ce_partial(m_rows, w, b, zero)
+        return dict(topk_idx=o["topk_idx"], topk_val=o["topk_val"], lse=rmax + torch.log(rsum))
+
     def _evaluate_rows(self, m_rows, target, k, with_loss, pad_id, full_rank):
         if self.precision == "bf16":
             wb, folded = self.projection_operands_folded()

@@ -136,6 +136,22 @@ class _ModuleBase(nn.Module):
     def test_epoch_end(self, outputs=None):
         return self._eval_epoch_end(outputs)
 
+    # ---- predict command on the fused path (evaluation/evaluation.py's evaluators consume the result, asme_b200/evaluation.py)
+    def _prediction_rows(self, seq, padding_mask):
+        """flat rows whose hidden state predicts the next item; None = the last real position of every sequence"""
+        return None
+
+    @torch.no_grad()
+    def predict_topn(self, batch, num_predictions: int) -> FusedPredictions:
+        """what ``predict_step`` + ``softmax`` + ``sort`` + ``[:, :num_predictions]`` deliver, without the (N, I) logits: the
+        top-n list (best first) and the row log-sum-exp, straight from the scoring sweeps"""
+        seq = batch[ITEM_SEQ_ENTRY_NAME]
+        pm = get_padding_mask(seq, self.item_tokenizer.pad_token_id)
+        rows = self._prediction_rows(seq, pm)
+        out = self.model.recommend(seq, pm, get_additional_meta_data(self.model, batch), num_predictions, rows=rows, select="last",
+                                   rows_one_per_sequence=rows is not None)
+        return FusedPredictions(None, out["topk_idx"], out["topk_val"], None, self.model.item_vocab_size, lse=out["lse"])
+
     def _eval_k(self) -> int:
         return min(32, max(self.metrics.max_k(), 1)) if hasattr(self.metrics, "max_k") else 10
 
@@ -182,6 +198,10 @@ class MaskedTrainingModule(_ModuleBase):
         loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
         self.log(LOG_KEY_TRAINING_LOSS, loss, prog_bar=False)
         return {"loss": loss}
+
+    def _prediction_rows(self, seq, padding_mask):
+        from .models import mask_position_rows
+        return mask_position_rows(seq, self.item_tokenizer.mask_token_id)
 
     def _get_prediction_for_masked_item(self, batch, batch_idx):
         seq = batch[ITEM_SEQ_ENTRY_NAME]
@@ -370,6 +390,9 @@ class UBERTMaskedTrainingModule(MaskedTrainingModule):
         pos = (seq == self.item_tokenizer.mask_token_id).to(torch.int32).argmax(dim=1).to(torch.int64)
         return torch.arange(B, device=seq.device, dtype=torch.int64) * (S + shift) + pos + shift
 
+    def _prediction_rows(self, seq, padding_mask):
+        return self._mask_rows(seq)
+
     def _get_prediction_for_masked_item(self, batch, batch_idx):
         seq = batch[ITEM_SEQ_ENTRY_NAME]
         logits = self(batch, batch_idx)
@@ -426,6 +449,9 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
         last = pm.sum(dim=-1).to(torch.int64) - 1
         last = torch.where(last < 0, last + S1, last)            # advanced indexing wraps -1 around
         return torch.arange(B, device=seq.device, dtype=torch.int64) * S1 + last
+
+    def _prediction_rows(self, seq, padding_mask):
+        return self._target_rows(seq, padding_mask)
 
     def _extract_target_logits(self, input_seq, logits):
         pm = get_padding_mask(input_seq, self.item_tokenizer.pad_token_id)

@@ -251,3 +251,43 @@ def test_encode_rows_equals_full_encode_on_selected_rows():
         sel1 = model.encode_rows(seq, seq.ne(0), {}, rows, one_per_sequence=True)
         assert float((sel1 - sel).norm() / sel.norm()) < 3e-3
         torch.testing.assert_close(sel1, sel, rtol=2e-2, atol=2e-2 * float(sel.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_predict_topn_matches_softmax_sort_of_the_dense_logits(precision):
+    """`predict` on the fused path (module.predict_topn -> asme_b200.evaluation evaluators) against the reference arithmetic
+    (softmax + sort of predict_step's dense logits, evaluation/evaluation.py:176-178): same items in the same order wherever
+    the dense scores are separated by more than the precision policy's noise, softmax scores within the policy's tolerance"""
+    from asme_b200.models import BERT4RecModel, SASRecModel
+    from asme_b200.modules import MaskedTrainingModule, NextItemPredictionTrainingModule
+    from asme_b200.evaluation import top_predictions
+    torch.manual_seed(1)
+    V, S, H, B, n = 1203, 24, 64, 33, 20
+
+    class Tok:
+        pad_token_id, mask_token_id = 0, 1
+
+    for cls, mod_cls, kw in ((BERT4RecModel, MaskedTrainingModule, {"initializer_range": 0.2}),
+                             (SASRecModel, NextItemPredictionTrainingModule, {"mode": "full"})):
+        model = cls(H, 2, 2, V, S, 0.1, **kw)
+        model.precision = precision
+        module = mod_cls(model, item_tokenizer=Tok()).cuda().eval()
+        seq, _, lengths = _random_batch(torch.Generator().manual_seed(7), B, S, V, p_mask=0.0)
+        if cls is BERT4RecModel:
+            seq[torch.arange(B), lengths - 1] = 1
+        batch = {"item": seq.cuda()}
+        fused = module.predict_topn(batch, n)
+        dense = module.predict_step(batch, 0).float()
+        assert dense.shape == (B, V) and fused.topk_idx.shape == (B, n)
+        got_s, got_i = top_predictions(fused, n)
+        want_s, want_i = top_predictions(dense, n)
+        tol = 2e-2 if precision == "bf16" else 1e-4
+        np.testing.assert_allclose(got_s, want_s, rtol=tol, atol=tol * float(want_s.max()))
+        # every listed item carries (up to the tolerance) the dense score of that item; the order may only differ inside near-ties
+        probs = torch.softmax(dense, dim=-1).cpu().numpy()
+        np.testing.assert_allclose(got_s, np.take_along_axis(probs, got_i, axis=1), rtol=tol, atol=tol * float(want_s.max()))
+        if precision == "fp32":
+            assert (got_i == want_i).mean() > 0.99
+        assert (np.diff(got_s, axis=1) <= 1e-7).all()                      # best first
+    with pytest.raises(ValueError, match="1..32"):
+        module.predict_topn(batch, 40)

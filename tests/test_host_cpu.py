@@ -160,3 +160,62 @@ def test_fixed_items_sampler_on_dense_predictions():
     assert s.sampled_predictions.tolist() == [[1.0, 2.0, 5.0], [9.0, 10.0, 13.0], [17.0, 18.0, 21.0]]
     assert s.positive_item_mask.tolist() == [[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, 0.0]]
     assert FixedItemsSampler([1]).suffix_metric_name() == "_fixed"
+
+
+class _Vocab:
+    def __init__(self, n):
+        self._tokens = ["<PAD>", "<MASK>", "<UNK>"] + [f"item_{i}" for i in range(3, n)]
+
+    def tokens(self):
+        return list(self._tokens)
+
+    def ids(self):
+        return list(range(len(self._tokens)))
+
+
+class _Tok:
+    def __init__(self, n):
+        self.vocabulary = _Vocab(n)
+
+    def get_special_token_ids(self):
+        return [0, 1, 2]
+
+
+def test_predict_evaluators_dense_and_fused_agree():
+    """evaluation/evaluation.py:43-236 -- headers, sample-wise flags and outputs; the fused input (top-n list + log-sum-exp) gives
+    the same recommendations and softmax scores as softmax + sort on the dense logits (the reference arithmetic)"""
+    from asme_b200 import evaluation as E
+    from asme_b200.metrics import FusedPredictions
+    gen = torch.Generator().manual_seed(3)
+    N, V, n = 6, 40, 5
+    logits = torch.randn(N, V, generator=gen) * 2
+    tok = _Tok(V)
+    batch = {"item": torch.tensor([[5, 7, 1, 0], [9, 1, 0, 0], [3, 4, 6, 1], [8, 1, 0, 0], [11, 12, 1, 0], [2, 30, 1, 0]]),
+             "item.target": torch.tensor([4, 8, 15, 16, 23, 39]), "sample_ids": torch.arange(10, 16), "pos": torch.arange(6)}
+    val, idx = torch.topk(logits, n, dim=1)
+    fused = FusedPredictions(None, idx.to(torch.int32), val, None, V, lse=torch.logsumexp(logits, dim=1))
+    assert fused.size() == torch.Size([N, V])
+    rec, sc = E.ExtractRecommendationEvaluator(tok, n), E.ExtractScoresEvaluator(tok, n)
+    assert rec.get_header() == ["recommendation"] and sc.get_header() == ["score"] and not rec.eval_samplewise()
+    want_scores, want_idx = torch.sort(torch.softmax(logits, dim=-1), dim=-1, descending=True)
+    want_rec = [[tok.vocabulary.tokens()[j] for j in row[:n].tolist()] for row in want_idx]
+    assert rec.evaluate(0, batch, logits) == want_rec and rec.evaluate(0, batch, fused) == want_rec
+    np.testing.assert_allclose(np.asarray(sc.evaluate(0, batch, logits)), want_scores[:, :n].numpy(), rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(sc.evaluate(0, batch, fused)), want_scores[:, :n].numpy(), rtol=1e-5)
+    # selected items filter what is left AFTER the cut to n predictions (:181-185): rows may become shorter than n
+    selected = want_idx[0, :2].tolist() + want_idx[1, 3:9].tolist()
+    recf = E.ExtractRecommendationEvaluator(tok, n, selected_items=selected)
+    got_dense, got_fused = recf.evaluate(0, batch, logits), recf.evaluate(0, batch, fused)
+    assert got_dense == got_fused and got_dense[0][:2] == want_rec[0][:2]
+    assert all(len(r) <= n for r in got_dense)
+    scf = E.ExtractScoresEvaluator(tok, n, selected_items=selected)
+    assert [len(r) for r in scf.evaluate(0, batch, fused)] == [len(r) for r in got_dense]
+    # the bookkeeping evaluators
+    assert E.LogInputEvaluator(tok).evaluate(0, batch, fused)[0] == ["item_5", "item_7"]
+    assert E.TrueTargetEvaluator(tok).evaluate(0, batch, fused)[2] == ["item_15"]
+    assert E.ExtractSampleIdEvaluator().evaluate(0, batch, fused) == [f"{10 + i}_{i}" for i in range(N)]
+    assert E.ExtractSampleIdEvaluator().evaluate(0, {"sample_ids": torch.arange(6)}, logits) == list(range(6))
+    with pytest.raises(RuntimeError, match="holds 5 items"):
+        E.ExtractScoresEvaluator(tok, 8).evaluate(0, batch, fused)
+    with pytest.raises(RuntimeError, match="log-sum-exp"):
+        E.ExtractScoresEvaluator(tok, 3).evaluate(0, batch, FusedPredictions(None, idx.to(torch.int32), val, None, V))
