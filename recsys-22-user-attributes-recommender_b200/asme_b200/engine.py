@@ -15,8 +15,13 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+import os
+
 from . import ops
 from ._lib import ACT_GELU, ACT_NONE
+
+# weight gradients of the tensor-core backward on a second stream (ASME_B200_SIDE_WGRAD=0 keeps everything on one stream)
+SIDE_STREAM_WGRAD = os.environ.get("ASME_B200_SIDE_WGRAD", "1") == "1"
 
 BLOCKS = "_sequence_representation_layer.transformer_layer.transformer_blocks"
 MODIFIER = "_sequence_representation_modifier_layer"
@@ -93,6 +98,49 @@ class EncoderEngine:
         self.m = module        # ArenaModule: weight(path[, buf]) / weights_span(...)
         self.cfg = cfg
         self.blocks = getattr(module, "blocks_path", BLOCKS)
+        self._side = None          # second stream for the weight gradients of the tensor-core backward
+        self._side_keep = []       # their operands stay referenced until the streams have joined
+
+    # The weight gradients (dW = dY^T X, dbias) are leaves of the backward pass: nothing downstream reads them before the
+    # optimizer.  They run on a second stream -- in a captured step they become a parallel branch of the graph -- and fill the
+    # SMs the latency-bound dX chain leaves idle.  Same kernels, same order of additions: results are bit-identical.
+    def _wgrad(self, dy16, x16, dw, db):
+        if not SIDE_STREAM_WGRAD:
+            return ops.tc_wgrad(dy16, x16, dw, db)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dy16.device)
+        self._side.wait_stream(torch.cuda.current_stream())          # the operands were produced on the main stream
+        with torch.cuda.stream(self._side):
+            ops.tc_wgrad(dy16, x16, dw, db, slot=1)
+        self._side_keep.append((dy16, x16))                          # no reuse of their memory before the join
+
+    def run_on_side(self, fn, keep, table_grad: bool = False) -> bool:
+        """other leaves of the backward pass (the catalog-gradient sweep of the CE backward).  ``table_grad``: the work adds into the
+        item table's gradient, which the embedding backward on the main stream also does -- :meth:`wait_table_grad` orders them."""
+        if not SIDE_STREAM_WGRAD:
+            return False
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=torch.cuda.current_device())
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            fn()
+            if table_grad:
+                self._table_event = torch.cuda.Event()
+                self._table_event.record(self._side)
+        self._side_keep.append(keep)
+        return True
+
+    def wait_table_grad(self):
+        ev = getattr(self, "_table_event", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._table_event = None
+
+    def join_side_stream(self):
+        if self._side_keep:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_keep.clear()
+        self._table_event = None
 
     # ---------------------------------------------------------------- helpers
     def _w(self, path, grad=False):
@@ -208,16 +256,16 @@ class EncoderEngine:
                 dx3, dy16 = ops.dropout_cast(dx, p, saved.seed, self._site(l, 4), self._site(l, 3), want_f32=True)
             else:
                 dx3, dy16 = dx, ops.cast_bf16(dx, ld_out=H)
-            ops.tc_wgrad(dy16, ls.a, self._w(f"{pre}.feed_forward.w_2.weight", True), self._w(f"{pre}.feed_forward.w_2.bias", True))
+            self._wgrad(dy16, ls.a, self._w(f"{pre}.feed_forward.w_2.weight", True), self._w(f"{pre}.feed_forward.w_2.bias", True))
             dz16 = ops.tc_gemm(dy16, m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), b_is_kn=True, gelu_grad_of=ls.z, p_drop=p,
                                seed=saved.seed, site=self._site(l, 2), out_f32=False, out_bf16=True)["bf16"]
-            ops.tc_wgrad(dz16, ls.y2, self._w(f"{pre}.feed_forward.w_1.weight", True), self._w(f"{pre}.feed_forward.w_1.bias", True))
+            self._wgrad(dz16, ls.y2, self._w(f"{pre}.feed_forward.w_1.weight", True), self._w(f"{pre}.feed_forward.w_1.bias", True))
             dy2 = ops.tc_gemm(dz16, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), b_is_kn=True)["f32"]
             dgb2 = m.weights_span(f"{pre}.output_sublayer.norm.weight", f"{pre}.output_sublayer.norm.bias", (2, H), g)
             # ---- attention: x2 = x + drop1(ctx Wo^T + bo); the LayerNorm backward also emits do16 = bf16(dx2 * mask1)
             dx2, do16 = ops.layernorm_bwd_drop(dy2, ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"), ls.st2, dgb2, dx3,
                                                p, saved.seed, 0, self._site(l, 1))
-            ops.tc_wgrad(do16, ls.ctx16, self._w(f"{pre}.attention.output_linear.weight", True),
+            self._wgrad(do16, ls.ctx16, self._w(f"{pre}.attention.output_linear.weight", True),
                          self._w(f"{pre}.attention.output_linear.bias", True))
             if ls.attn_tc:
                 dctx16 = ops.tc_gemm(do16, m.weight_bf16(f"{pre}.attention.output_linear.weight"), b_is_kn=True, out_f32=False,
@@ -232,7 +280,7 @@ class EncoderEngine:
             wqkv = m.weights_span_bf16(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H))
             dwqkv = m.weights_span(f"{pre}.attention.linear_layers.0.weight", f"{pre}.attention.linear_layers.2.weight", (3 * H, H), g)
             dbqkv = m.weights_span(f"{pre}.attention.linear_layers.0.bias", f"{pre}.attention.linear_layers.2.bias", (3 * H,), g)
-            ops.tc_wgrad(dqkv16, ls.y1, dwqkv, dbqkv)
+            self._wgrad(dqkv16, ls.y1, dwqkv, dbqkv)
             dy1 = ops.tc_gemm(dqkv16, wqkv, b_is_kn=True)["f32"]
             dgb1 = m.weights_span(f"{pre}.input_sublayer.norm.weight", f"{pre}.input_sublayer.norm.bias", (2, H), g)
             if l > 0:       # the gradient entering the layer below: its two dropped copies come out of this LayerNorm backward

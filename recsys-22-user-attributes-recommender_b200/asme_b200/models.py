@@ -157,6 +157,7 @@ class TransformerRecommenderModel(ArenaModule):
                              self.cfg.dropout if training else 0.0, seed, users=users, seg_table=seg)
 
     def _embed_backward(self, saved: Saved, d_x: torch.Tensor):
+        self.engine.wait_table_grad()           # a catalog gradient still running on the second stream adds into the same table
         spec: ops.EmbedSpec = saved.embed_spec
         B, S, H = saved.B, saved.S, self.cfg.hidden
         g = self._arena.ensure_grad()
@@ -280,6 +281,7 @@ class TransformerRecommenderModel(ArenaModule):
             self._attr_backward(saved.extra["attrs"], self.postfusion, _POST_ATTR, d_ctx, saved.B * saved.S)
         d_x = self.engine.blocks_backward(d_hidden, saved)
         self._embed_backward(saved, d_x)
+        self.engine.join_side_stream()          # the weight gradients issued on the second stream are complete from here on
 
     # ---- projection -------------------------------------------------------------------------------
     def projection_operands(self, grad: bool = False):
@@ -390,7 +392,12 @@ class TransformerRecommenderModel(ArenaModule):
         dw, db = self.projection_operands(grad=True)
         if ctx["hb"] is not None:
             wb, b = self.projection_operands_bf16()
-            d_m = ops.tc_score_ce_bwd(ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], self.cfg.hidden, dw, db)
+            args = (ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], self.cfg.hidden)
+            # the catalog-gradient sweep (dW, dbias) is a leaf: second stream, next to the whole encoder backward
+            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1), keep=args, table_grad=True):
+                d_m = ops.tc_score_ce_bwd(*args, None, None)
+            else:
+                d_m = ops.tc_score_ce_bwd(*args, dw, db)
         else:
             w, b = self.projection_operands()
             d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], dw, db)

@@ -493,14 +493,14 @@ def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: in
 
 
 def tc_score_ce_bwd(hb, wb, bias, target, lse, scale: float, H: int, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
-                    v0: int = 0, need_dh: bool = True) -> Optional[torch.Tensor]:
+                    v0: int = 0, need_dh: bool = True, slot: int = 0) -> Optional[torch.Tensor]:
     """tensor-core backward of scoring + CE: returns dH (R,H) fp32; accumulates into dW (Vloc,H) / dbias (Vloc)"""
     hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
     R, Kp = hb.shape
     Vloc = wb.shape[0]
     dh = torch.empty(R, H, dtype=torch.float32, device=hb.device) if need_dh else None
     ws_bytes = _lib.query("asme_b200_tc_score_ce_bwd_workspace_bytes", R, H, Kp, Vloc)
-    ws = workspace(ws_bytes, hb.device)
+    ws = workspace(ws_bytes, hb.device, slot)
     if _lib.timing is not None:
         _lib.note = f"R={R},V={Vloc},H={Kp}"
     _lib.call("asme_b200_tc_score_ce_bwd", _p(hb), R, H, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
@@ -540,13 +540,15 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, 
     return out
 
 
-def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True):
-    """dw (N,K) fp32 (+)= dy(M,N)^T x(M,K); dbias (N) (+)= colsum(dy); dy, x bf16"""
+def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True,
+             slot: int = 0):
+    """dw (N,K) fp32 (+)= dy(M,N)^T x(M,K); dbias (N) (+)= colsum(dy); dy, x bf16.  ``slot``: scratch buffer to use (calls issued
+    on different streams must not share one)"""
     dy, x = _bf16(dy, "dy"), _bf16(x, "x")
     M, N = dy.shape
     K = x.shape[1]
     ws_bytes = _lib.query("asme_b200_tc_wgrad_workspace_bytes", M, N, K)
-    ws = workspace(ws_bytes, x.device)
+    ws = workspace(ws_bytes, x.device, slot)
     if _lib.timing is not None:
         _lib.note = f"M={M},N={N},K={K}"
     _lib.call("asme_b200_tc_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws), ws.numel(), _stream())
