@@ -109,6 +109,12 @@ int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H, const flo
 size_t asme_b200_embgrad_workspace_bytes(int T, int H);
 int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int row_divisor, int H, float* d_table,
                                     int V, int64_t skip_id, void* ws, size_t ws_bytes, asme_stream_t stream);
+/* the two phases of the call above, separately: the sort depends on the ids only (not on any gradient), so a training step can run
+ * it early / on another stream; the reduce consumes the sorted pairs the sort left in the SAME workspace. */
+int asme_b200_embgrad_sort(const int64_t* ids, int T, int row_divisor, int H, int V, int64_t skip_id, void* ws, size_t ws_bytes,
+                           asme_stream_t stream);
+int asme_b200_embgrad_reduce_sorted(int T, const float* d_rows, int H, float* d_table, int V, void* ws, size_t ws_bytes,
+                                    asme_stream_t stream);
 /* d_pos[s,:] += sum_b d_rows[b*S+s,:]   (positions are generated, t mod S; transformer_layers.py:68) */
 int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H, float* d_pos, asme_stream_t stream);
 /* the same for sequences that are seq_stride_rows rows apart (user prefix: d_rows points at position 1 of sequence 0) */

@@ -51,6 +51,8 @@ _PROTOTYPES = {
     "asme_b200_embed_bwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "asme_b200_embgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_embgrad_sorted_reduce": (c_int, [P, c_int, P, c_int, c_int, P, c_int, c_int64, P, c_size_t, P]),
+    "asme_b200_embgrad_sort": (c_int, [P, c_int, c_int, c_int, c_int, c_int64, P, c_size_t, P]),
+    "asme_b200_embgrad_reduce_sorted": (c_int, [c_int, P, c_int, P, c_int, P, c_size_t, P]),
     "asme_b200_posgrad_reduce": (c_int, [P, c_int, c_int, c_int, P, P]),
     "asme_b200_posgrad_reduce_strided": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "asme_b200_colsum_accumulate": (c_int, [P, c_int, c_int, P, P, c_size_t, P]),

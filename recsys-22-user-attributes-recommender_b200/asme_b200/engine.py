@@ -114,21 +114,22 @@ class EncoderEngine:
             ops.tc_wgrad(dy16, x16, dw, db, slot=1)
         self._side_keep.append((dy16, x16))                          # no reuse of their memory before the join
 
-    def run_on_side(self, fn, keep, table_grad: bool = False) -> bool:
+    def run_on_side(self, fn, keep, table_grad: bool = False):
         """other leaves of the backward pass (the catalog-gradient sweep of the CE backward).  ``table_grad``: the work adds into the
         item table's gradient, which the embedding backward on the main stream also does -- :meth:`wait_table_grad` orders them."""
         if not SIDE_STREAM_WGRAD:
-            return False
+            return None         # caller runs the work in line; otherwise the event that marks its completion
         if self._side is None:
             self._side = torch.cuda.Stream(device=torch.cuda.current_device())
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             fn()
-            if table_grad:
-                self._table_event = torch.cuda.Event()
-                self._table_event.record(self._side)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        if table_grad:
+            self._table_event = done
         self._side_keep.append(keep)
-        return True
+        return done
 
     def wait_table_grad(self):
         ev = getattr(self, "_table_event", None)

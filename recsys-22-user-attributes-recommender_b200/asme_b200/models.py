@@ -167,7 +167,13 @@ class TransformerRecommenderModel(ArenaModule):
             dln = g[off:off + 4 * H].view(4, H)
         d_item, d_attr = ops.embed_bwd(spec, B, S, d_x, saved.embed_stats, dln)
         if not self.user_attrs:
-            ops.embgrad_sorted_reduce(spec.item_ids, d_item, self.weight(self.item_table_path, g))
+            pre, ev = saved.extra.pop("sorted_items", (None, None))
+            if pre is None:
+                ops.embgrad_sorted_reduce(spec.item_ids, d_item, self.weight(self.item_table_path, g))
+            else:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                pre.reduce(d_item, self.weight(self.item_table_path, g))
             if self.pos_table_path is not None:
                 ops.posgrad_reduce(d_item, B, S, self.weight(self.pos_table_path, g))
             self._attr_backward(saved.extra["attrs"], self.prefusion, self.pre_attr_prefix, d_attr, B * S)
@@ -279,6 +285,12 @@ class TransformerRecommenderModel(ArenaModule):
                 d_ctx = ops.binary(d_hidden, x, "multiply")
                 d_hidden = ops.binary(d_hidden, ctx, "multiply")
             self._attr_backward(saved.extra["attrs"], self.postfusion, _POST_ATTR, d_ctx, saved.B * saved.S)
+        # the sort of the (item id, token) pairs needs no gradient: second stream, long before the embedding backward consumes it
+        if not self.user_attrs and d_hidden.is_cuda:
+            spec = saved.embed_spec
+            pre = ops.SortedIds(spec.item_ids, self.cfg.hidden, self.weight(self.item_table_path).shape[0])
+            ev = self.engine.run_on_side(pre.sort, keep=(pre,))
+            saved.extra["sorted_items"] = (pre, ev) if ev is not None else (pre.sort(), None)
         d_x = self.engine.blocks_backward(d_hidden, saved)
         self._embed_backward(saved, d_x)
         self.engine.join_side_stream()          # the weight gradients issued on the second stream are complete from here on
@@ -394,7 +406,8 @@ class TransformerRecommenderModel(ArenaModule):
             wb, b = self.projection_operands_bf16()
             args = (ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], self.cfg.hidden)
             # the catalog-gradient sweep (dW, dbias) is a leaf: second stream, next to the whole encoder backward
-            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1), keep=args, table_grad=True):
+            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1), keep=args,
+                                       table_grad=True) is not None:
                 d_m = ops.tc_score_ce_bwd(*args, None, None)
             else:
                 d_m = ops.tc_score_ce_bwd(*args, dw, db)

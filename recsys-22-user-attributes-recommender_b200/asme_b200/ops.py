@@ -173,6 +173,30 @@ def embgrad_sorted_reduce(ids: torch.Tensor, d_rows: torch.Tensor, d_table: torc
               _p(ws), ws.numel(), _stream())
 
 
+class SortedIds:
+    """phase 1 of the embedding-table gradient: the (id, token) pairs of one id tensor sorted by id, in a scratch buffer of its own"""
+
+    def __init__(self, ids: torch.Tensor, H: int, V: int, skip_id: int = -1, row_divisor: int = 1):
+        self.ids = _i64(ids).reshape(-1)
+        self.T, self.H, self.V = self.ids.numel(), H, V
+        self.skip_id, self.row_divisor = skip_id, int(row_divisor)
+        self.ws = torch.empty(max(_lib.query("asme_b200_embgrad_workspace_bytes", self.T, H), 256), dtype=torch.uint8, device=ids.device)
+
+    def sort(self):
+        """launches phase 1 on the current stream (may differ from the stream the object was created on)"""
+        _lib.call("asme_b200_embgrad_sort", _p(self.ids), self.T, self.row_divisor, self.H, self.V, self.skip_id, _p(self.ws),
+                  self.ws.numel(), _stream())
+        return self
+
+    def reduce(self, d_rows: torch.Tensor, d_table: torch.Tensor):
+        """phase 2: d_table[id] += the rows of d_rows that carry that id (same result as embgrad_sorted_reduce)"""
+        d_rows = _f32(d_rows)
+        assert d_table.shape == (self.V, self.H)
+        if _lib.timing is not None:
+            _lib.note = f"T={self.T},H={self.H}"
+        _lib.call("asme_b200_embgrad_reduce_sorted", self.T, _p(d_rows), self.H, _p(d_table), self.V, _p(self.ws), self.ws.numel(), _stream())
+
+
 def posgrad_reduce(d_rows: torch.Tensor, B: int, S: int, d_pos: torch.Tensor, prefix: int = 0):
     """d_pos[s] += sum_b d_rows[b, prefix + s]; d_rows is (B*(S+prefix), H)"""
     d_rows = _f32(d_rows)

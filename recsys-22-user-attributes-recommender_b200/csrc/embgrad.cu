@@ -205,11 +205,37 @@ extern "C" size_t asme_b200_embgrad_workspace_bytes(int T, int H) {
            2 * align256(chunks * sizeof(int));
 }
 
-extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int row_divisor, int H,
-                                               float* d_table, int V, int64_t skip_id, void* ws, size_t ws_bytes,
-                                               asme_stream_t stream) {
+struct EmbgradLayout {
+    int *keys_in, *vals_in, *keys_out, *vals_out;
+    void* temp;
+    size_t temp_bytes;
+    float *head, *tail;
+    int *tail_key, *flags;
+    int chunks;
+};
+static EmbgradLayout embgrad_layout(void* ws, int T, int H) {
+    EmbgradLayout L;
+    L.chunks = ceil_div(T, CHUNK);
+    char* p = (char*)ws;
+    L.keys_in = (int*)p;  p += align256((size_t)T * sizeof(int));
+    L.vals_in = (int*)p;  p += align256((size_t)T * sizeof(int));
+    L.keys_out = (int*)p; p += align256((size_t)T * sizeof(int));
+    L.vals_out = (int*)p; p += align256((size_t)T * sizeof(int));
+    L.temp_bytes = cub_temp_bytes(T);
+    L.temp = p;           p += align256(L.temp_bytes);
+    L.head = (float*)p;   p += align256((size_t)L.chunks * H * sizeof(float));
+    L.tail = (float*)p;   p += align256((size_t)L.chunks * H * sizeof(float));
+    L.tail_key = (int*)p; p += align256((size_t)L.chunks * sizeof(int));
+    L.flags = (int*)p;
+    return L;
+}
+
+// Phase 1: (id, token) pairs sorted by id into the workspace.  Depends on the ids only, not on any gradient -- a training step
+// can run it at the start of the backward pass on a second stream (asme_b200/models.py) and keep the workspace until phase 2.
+extern "C" int asme_b200_embgrad_sort(const int64_t* ids, int T, int row_divisor, int H, int V, int64_t skip_id, void* ws,
+                                      size_t ws_bytes, asme_stream_t stream) {
     ASME_REQUIRE(row_divisor >= 1, "embgrad: row_divisor=%d", row_divisor);
-    ASME_REQUIRE(ids && d_rows && d_table, "embgrad: null argument");
+    ASME_REQUIRE(ids, "embgrad: null argument");
     ASME_REQUIRE(H % 4 == 0 && H >= 4 && H <= 512, "embgrad: H=%d unsupported (4..512, multiple of 4)", H);
     ASME_REQUIRE(V >= 1, "embgrad: V=%d", V);
     if (T == 0) return ASME_OK;
@@ -218,29 +244,42 @@ extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const 
         return ASME_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunks = ceil_div(T, CHUNK);
-    char* p = (char*)ws;
-    int* keys_in = (int*)p;  p += align256((size_t)T * sizeof(int));
-    int* vals_in = (int*)p;  p += align256((size_t)T * sizeof(int));
-    int* keys_out = (int*)p; p += align256((size_t)T * sizeof(int));
-    int* vals_out = (int*)p; p += align256((size_t)T * sizeof(int));
-    size_t temp_bytes = cub_temp_bytes(T);
-    void* temp = p;          p += align256(temp_bytes);
-    float* head = (float*)p; p += align256((size_t)chunks * H * sizeof(float));
-    float* tail = (float*)p; p += align256((size_t)chunks * H * sizeof(float));
-    int* tail_key = (int*)p; p += align256((size_t)chunks * sizeof(int));
-    int* flags = (int*)p;
-
-    embgrad_keys_kernel<<<ceil_div(T, 256), 256, 0, st>>>(ids, T, V, skip_id, row_divisor, keys_in, vals_in);
+    const EmbgradLayout L = embgrad_layout(ws, T, H);
+    embgrad_keys_kernel<<<ceil_div(T, 256), 256, 0, st>>>(ids, T, V, skip_id, row_divisor, L.keys_in, L.vals_in);
     ASME_LAUNCH_OK();
     int bits = 1;
     while ((1LL << bits) <= (long long)V) ++bits;   // keys are in [0, V]
-    ASME_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, T, 0, bits, st));
-    embgrad_chunk_kernel<<<ceil_div(chunks, 4), 128, 0, st>>>(keys_out, vals_out, T, V, d_rows, H, d_table, head, tail, tail_key,
-                                                              flags, chunks);
+    size_t temp_bytes = L.temp_bytes;
+    ASME_CUDA_OK(cub::DeviceRadixSort::SortPairs(L.temp, temp_bytes, L.keys_in, L.keys_out, L.vals_in, L.vals_out, T, 0, bits, st));
+    return ASME_OK;
+}
+
+// Phase 2: segmented sums of d_rows over the sorted pairs phase 1 left in the workspace; d_table[id] += ...
+extern "C" int asme_b200_embgrad_reduce_sorted(int T, const float* d_rows, int H, float* d_table, int V, void* ws, size_t ws_bytes,
+                                               asme_stream_t stream) {
+    ASME_REQUIRE(d_rows && d_table, "embgrad: null argument");
+    ASME_REQUIRE(H % 4 == 0 && H >= 4 && H <= 512, "embgrad: H=%d unsupported (4..512, multiple of 4)", H);
+    if (T == 0) return ASME_OK;
+    if (ws_bytes < asme_b200_embgrad_workspace_bytes(T, H)) {
+        asme_set_error("embgrad: workspace too small");
+        return ASME_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const EmbgradLayout L = embgrad_layout(ws, T, H);
+    embgrad_chunk_kernel<<<ceil_div(L.chunks, 4), 128, 0, st>>>(L.keys_out, L.vals_out, T, V, d_rows, H, d_table, L.head, L.tail,
+                                                                L.tail_key, L.flags, L.chunks);
     ASME_LAUNCH_OK();
-    embgrad_carry_kernel<<<chunks, CARRY_WARPS * 32, (size_t)CARRY_WARPS * H * sizeof(float), st>>>(head, tail, tail_key, flags, chunks, H,
-                                                                                                   d_table);
+    embgrad_carry_kernel<<<L.chunks, CARRY_WARPS * 32, (size_t)CARRY_WARPS * H * sizeof(float), st>>>(L.head, L.tail, L.tail_key, L.flags,
+                                                                                                     L.chunks, H, d_table);
     ASME_LAUNCH_OK();
     return ASME_OK;
+}
+
+extern "C" int asme_b200_embgrad_sorted_reduce(const int64_t* ids, int T, const float* d_rows, int row_divisor, int H,
+                                               float* d_table, int V, int64_t skip_id, void* ws, size_t ws_bytes,
+                                               asme_stream_t stream) {
+    ASME_REQUIRE(ids && d_rows && d_table, "embgrad: null argument");
+    int rc = asme_b200_embgrad_sort(ids, T, row_divisor, H, V, skip_id, ws, ws_bytes, stream);
+    if (rc) return rc;
+    return asme_b200_embgrad_reduce_sorted(T, d_rows, H, d_table, V, ws, ws_bytes, stream);
 }

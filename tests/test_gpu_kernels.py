@@ -389,6 +389,19 @@ def test_embgrad_sorted_reduce(ops, T, V, H):
     got0 = torch.zeros(V, H, device="cuda")
     ops.embgrad_sorted_reduce(dev(ids), dev(rows), got0, skip_id=0)
     close(got0, want0, rtol=1e-4, atol=1e-3, msg="embgrad skip")
+    # the two phases separately (sort early / on another stream, reduce when the gradient rows exist): bit-identical to the one call
+    pre = ops.SortedIds(dev(ids), H, V)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        pre.sort()
+    torch.cuda.current_stream().wait_stream(side)
+    split = torch.ones(V, H, device="cuda")
+    pre.reduce(dev(rows), split)
+    assert torch.equal(split, got)
+    split0 = torch.zeros(V, H, device="cuda")
+    ops.SortedIds(dev(ids), H, V, skip_id=0).sort().reduce(dev(rows), split0)
+    assert torch.equal(split0, got0)
 
 
 def test_adam_matches_oracle(ops):
