@@ -527,7 +527,7 @@ def main():
     # ---- (4) secondary: C5 full-catalog evaluation ------------------------------------------------------------------
     eval_info = None
     if not args.no_eval:
-        eval_info = bench_eval_c5(device, pk, world=world, rank=rank)
+        eval_info = bench_eval_c5(device, pk, world=world, rank=rank, graph=not args.no_graph)
 
     def finish():
         # CUDA graphs that captured NCCL collectives keep communicator resources alive and ncclCommDestroy can then block for ever:
@@ -580,7 +580,7 @@ def main():
     finish()
 
 
-def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False):
+def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False, graph=True):
     """secondary measurement: full-catalog scoring + top-k + Recall/NDCG@10 on a 1M-item catalog (C5).  With N ranks the
     catalog is vocab-sharded (asme_b200.sharded): every rank encodes its own 1024 users and scores all N*1024 users against
     its V/N slice; per-shard top-k lists and target scores are merged over NCCL (weak scaling: users per GPU fixed)."""
@@ -602,11 +602,28 @@ def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False)
     seq_d, target_d = seq.to(device), target.to(device)
     from asme_b200.metrics import FusedPredictions
 
-    def step():
+    full_rank = metrics.needs_full_rank()
+
+    def model_step(b):
         if world > 1:
-            out = model.evaluate_rank_sharded(seq_d, seq_d.ne(0), {}, target_d, k=cfg["k"], full_rank=metrics.needs_full_rank())
-        else:
-            out = model.evaluate_rank(seq_d, seq_d.ne(0), {}, target_d, k=cfg["k"], full_rank=metrics.needs_full_rank())
+            return model.evaluate_rank_sharded(b["seq"], b["seq"].ne(0), {}, b["target"], k=cfg["k"], full_rank=full_rank)
+        return model.evaluate_rank(b["seq"], b["seq"].ne(0), {}, b["target"], k=cfg["k"], full_rank=full_rank)
+
+    # ~40 launches per step: issued from Python the host is as slow as the GPU, so the single-GPU step replays a CUDA graph of the
+    # model part (asme_b200.graphs.GraphedEvalStep); the metric accumulation stays outside (it rebinds its state tensors)
+    graphed = None
+    if graph and world == 1 and not profile:
+        from asme_b200.graphs import GraphedEvalStep
+        try:
+            graphed = GraphedEvalStep(model_step)
+            graphed({"seq": seq_d, "target": target_d})
+        except Exception as e:
+            print(f"[bench] evaluation graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graphed = None
+
+    def step(eager=False):
+        batch = {"seq": seq_d, "target": target_d}
+        out = model_step(batch) if (graphed is None or eager) else graphed(batch)
         return metrics.update(seq_d, target_d, FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], V))
 
     for _ in range(warmup):
@@ -634,7 +651,7 @@ def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     _lib.timing = []
-    step()
+    step(eager=True)
     torch.cuda.synchronize()
     rec = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
@@ -643,6 +660,7 @@ def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False)
     metrics.sync()
     res = metrics.compute()
     return {"metric": "eval_users_per_sec", "value": world * B / (ms / 1e3), "unit": "users/s", "ms_per_step": ms, "n_gpus": world,
+            "launch": "CUDA graph replay of the model part of the step" if graphed is not None else "launch by launch",
             "scaling": "weak", "sharding": "single GPU" if world == 1 else f"catalog rows sharded over {world} ranks (NCCL: all-gather hidden rows, all-reduce target scores, all-gather top-k lists)",
             "config": {"workload": "C5 full-catalog scoring + top-k eval, synthetic 1M-item catalog", "items": V, "hidden": cfg["H"],
                        "seq_len": S, "users_per_step_per_gpu": B, "k": cfg["k"], "dtype": model.precision},

@@ -88,3 +88,42 @@ class GraphedTrainStep:
         if self.scheduler is not None:
             self.scheduler.step()
         return loss
+
+
+class GraphedEvalStep:
+    """captures ``fn(batch) -> dict of tensors`` (e.g. ``model.evaluate_rank`` of one batch: embedding, encoder, catalog sweeps,
+    merges -- ~40 launches that the host cannot issue as fast as the GPU retires them) once per batch signature and replays it.
+    ``fn`` must not synchronise with the host.  Non-tensor entries of the result are dropped; the returned tensors are the
+    graph's static outputs: consume them (e.g. ``metrics.update``) before the next replay of the same signature."""
+
+    def __init__(self, fn: Callable[[Dict[str, torch.Tensor]], Dict[str, Any]], warmup_iters: int = 2):
+        self.fn, self.warmup_iters = fn, warmup_iters
+        self.graphs: Dict[Any, Any] = {}
+
+    def _capture(self, key, batch):
+        static = {k: v.clone() for k, v in batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup_iters):
+                self.fn(static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            out = self.fn(static)
+        out = {k: v for k, v in out.items() if torch.is_tensor(v)}
+        self.graphs[key] = (graph, static, out)
+        return self.graphs[key]
+
+    def __call__(self, batch: Dict[str, torch.Tensor], key=None) -> Dict[str, torch.Tensor]:
+        if key is None:
+            key = tuple((k, tuple(v.shape)) for k, v in sorted(batch.items()))
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, batch)
+        graph, static, out = entry
+        for k, v in batch.items():
+            if static[k].data_ptr() != v.data_ptr():
+                static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return out

@@ -68,3 +68,33 @@ def test_graph_replay_takes_new_inputs_and_learning_rate():
     opt.param_groups[0]["lr"] = 0.0                       # the host-side schedule is written into the device state before each replay
     step(batch)
     assert all(torch.equal(a, b) for a, b in zip(before, module.model.parameters()))
+
+
+def test_graphed_eval_step_equals_eager():
+    """GraphedEvalStep replays model.evaluate_rank: same top-k, ranks and target scores as the launch-by-launch step, for new
+    inputs copied into the captured buffers"""
+    from asme_b200.graphs import GraphedEvalStep
+    from asme_b200.models import BERT4RecModel
+    torch.manual_seed(0)
+    V, S, H, B = 5003, 40, 64, 96
+    model = BERT4RecModel(H, 2, 2, V, S, 0.1, initializer_range=0.2).cuda().eval()
+
+    def batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        seq = torch.randint(3, V, (B, S), generator=g)
+        lengths = torch.randint(2, S, (B,), generator=g)
+        seq = torch.where(torch.arange(S).unsqueeze(0) < lengths.unsqueeze(1), seq, torch.zeros_like(seq))
+        seq[torch.arange(B), lengths] = 1
+        return {"seq": seq.cuda(), "target": torch.randint(3, V, (B,), generator=g).cuda()}
+
+    def fn(b):
+        return model.evaluate_rank(b["seq"], b["seq"].ne(0), {}, b["target"], k=10, full_rank=True)
+
+    graphed = GraphedEvalStep(fn)
+    for seed in (1, 2, 3):
+        b = batch(seed)
+        got = {k: v.clone() for k, v in graphed(b).items()}
+        want = fn(b)
+        assert len(graphed.graphs) == 1
+        for k in ("topk_idx", "topk_val", "rank", "target_score"):
+            assert torch.equal(got[k], want[k]), k
