@@ -609,10 +609,11 @@ def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False,
             return model.evaluate_rank_sharded(b["seq"], b["seq"].ne(0), {}, b["target"], k=cfg["k"], full_rank=full_rank)
         return model.evaluate_rank(b["seq"], b["seq"].ne(0), {}, b["target"], k=cfg["k"], full_rank=full_rank)
 
-    # ~40 launches per step: issued from Python the host is as slow as the GPU, so the single-GPU step replays a CUDA graph of the
-    # model part (asme_b200.graphs.GraphedEvalStep); the metric accumulation stays outside (it rebinds its state tensors)
+    # ~40 launches per step: issued from Python the host is as slow as the GPU, so the step replays a CUDA graph of the model part
+    # (asme_b200.graphs.GraphedEvalStep; with N ranks the NCCL exchanges of the sharded merge are captured with it, like the
+    # gradient all-reduce of the training graph); the metric accumulation stays outside (it rebinds its state tensors)
     graphed = None
-    if graph and world == 1 and not profile:
+    if graph and not profile:
         from asme_b200.graphs import GraphedEvalStep
         try:
             graphed = GraphedEvalStep(model_step)
