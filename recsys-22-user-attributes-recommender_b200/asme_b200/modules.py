@@ -96,6 +96,7 @@ class _ModuleBase(nn.Module):
         super().__init__()
         self.logged: Dict[str, Any] = {}
         self.fused_eval = True        # eval steps return FusedPredictions (rank + top-k) instead of dense (N,V) logits
+        self.eval_graph = False       # replay the model part of a fused evaluation step from a CUDA graph (all-item metrics only)
         self.eval_loss = True         # also log val_loss / test_loss (one extra fused CE pass over the selected rows)
         self.use_fused_adam = True
 
@@ -135,6 +136,26 @@ class _ModuleBase(nn.Module):
 
     def test_epoch_end(self, outputs=None):
         return self._eval_epoch_end(outputs)
+
+    # ---- fused evaluation, optionally replayed from a CUDA graph
+    def _rank(self, seq, pm, meta, targets, rows_fn=None, **kw):
+        """``model.evaluate_rank`` for the evaluation hooks.  With ``self.eval_graph = True`` the model part of the step (~40
+        launches, host-bound when issued from Python) is captured once per batch signature and replayed
+        (:class:`asme_b200.graphs.GraphedEvalStep`); the result then carries no item scorer, i.e. only all-item metrics."""
+        def run(b):
+            meta_b = {k[5:]: v for k, v in b.items() if k.startswith("meta.")}
+            rows = rows_fn(b["seq"], b["pm"]) if rows_fn is not None else None
+            extra = dict(rows=rows, rows_one_per_sequence=True) if rows is not None else {}
+            return self.model.evaluate_rank(b["seq"], b["pm"], meta_b, b["target"], **extra, **kw)
+        batch = {"seq": seq, "pm": pm, "target": targets, **{f"meta.{k}": v for k, v in meta.items()}}
+        if not getattr(self, "eval_graph", False) or not seq.is_cuda:
+            return run(batch)
+        from .graphs import GraphedEvalStep
+        graphs = self.__dict__.setdefault("_eval_graphs", {})
+        key = tuple(sorted((k, str(v)) for k, v in kw.items()))
+        if key not in graphs:
+            graphs[key] = GraphedEvalStep(run)
+        return dict(graphs[key](batch))
 
     # ---- predict command on the fused path (evaluation/evaluation.py's evaluators consume the result, asme_b200/evaluation.py)
     def _prediction_rows(self, seq, padding_mask):
@@ -213,9 +234,9 @@ class MaskedTrainingModule(_ModuleBase):
         if not self.fused_eval or targets.dim() != 1:
             prediction = self._get_prediction_for_masked_item(batch, batch_idx)
             return build_eval_step_return_dict(seq, prediction, targets)
-        out = self.model.evaluate_rank(seq, pm, meta, targets, k=self._eval_k(), select="mask",
-                                       mask_id=self.item_tokenizer.mask_token_id, with_loss=self.eval_loss,
-                                       pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
+        out = self._rank(seq, pm, meta, targets, k=self._eval_k(), select="mask",
+                         mask_id=self.item_tokenizer.mask_token_id, with_loss=self.eval_loss,
+                         pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_TEST_LOSS if is_test else LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
@@ -284,9 +305,9 @@ class NextItemPredictionTrainingModule(_ModuleBase):
         if not self.fused_eval or target.dim() != 1:
             logits = self(batch, batch_idx)
             return build_eval_step_return_dict(seq, self._extract_target_logits(seq, logits), target)
-        out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), target, k=self._eval_k(),
-                                       select="last", with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id,
-                                       full_rank=self._full_rank())
+        out = self._rank(seq, pm, get_additional_meta_data(self.model, batch), target, k=self._eval_k(),
+                         select="last", with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id,
+                         full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
@@ -340,8 +361,8 @@ class SequenceNextItemPredictionTrainingModule(_ModuleBase):
         pm = get_padding_mask(seq, self.item_tokenizer.pad_token_id)
         if not self.fused_eval or targets.dim() != 1:
             return build_eval_step_return_dict(seq, self.predict_step(batch, batch_idx), targets)
-        out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), targets, k=self._eval_k(),
-                                       select="last", full_rank=self._full_rank())
+        out = self._rank(seq, pm, get_additional_meta_data(self.model, batch), targets, k=self._eval_k(),
+                         select="last", full_rank=self._full_rank())
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
                                 scorer=out.get("scorer"))
         return build_eval_step_return_dict(seq, pred, targets)
@@ -404,9 +425,8 @@ class UBERTMaskedTrainingModule(MaskedTrainingModule):
         if not self.fused_eval or targets.dim() != 1:
             prediction = self._get_prediction_for_masked_item(batch, batch_idx)
             return build_eval_step_return_dict(seq, prediction, targets)
-        out = self.model.evaluate_rank(seq, pm, meta, targets, k=self._eval_k(), rows=self._mask_rows(seq), rows_one_per_sequence=True,
-                                       with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id,
-                                       full_rank=self._full_rank())
+        out = self._rank(seq, pm, meta, targets, rows_fn=lambda s_, p_: self._mask_rows(s_), k=self._eval_k(),
+                         with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_TEST_LOSS if is_test else LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
@@ -464,9 +484,8 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
         if not self.fused_eval or target.dim() != 1:
             logits = self(batch, batch_idx)
             return build_eval_step_return_dict(seq, self._extract_target_logits(seq, logits), target)
-        out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), target, k=self._eval_k(),
-                                       rows=self._target_rows(seq, pm), rows_one_per_sequence=True, with_loss=self.eval_loss,
-                                       pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
+        out = self._rank(seq, pm, get_additional_meta_data(self.model, batch), target, rows_fn=self._target_rows, k=self._eval_k(),
+                         with_loss=self.eval_loss, pad_id=self.item_tokenizer.pad_token_id, full_rank=self._full_rank())
         if self.eval_loss:
             self.log(LOG_KEY_VALIDATION_LOSS, out["loss"], prog_bar=True)
         pred = FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,

@@ -98,3 +98,44 @@ def test_graphed_eval_step_equals_eager():
         assert len(graphed.graphs) == 1
         for k in ("topk_idx", "topk_val", "rank", "target_score"):
             assert torch.equal(got[k], want[k]), k
+
+
+def test_module_eval_graph_option_gives_the_same_metrics():
+    """module.eval_graph = True: validation_step replays the captured model part; step values and epoch metrics are equal to the
+    launch-by-launch hooks"""
+    from asme_b200.metrics import build_metrics
+    from asme_b200.models import BERT4RecModel, SASRecModel
+    from asme_b200.modules import MaskedTrainingModule, NextItemPredictionTrainingModule
+    torch.manual_seed(0)
+    V, S, H, B = 2003, 30, 64, 64
+
+    class Tok:
+        pad_token_id, mask_token_id = 0, 1
+
+    def batches(masked):
+        out = []
+        for seed in (1, 2, 3):
+            g = torch.Generator().manual_seed(seed)
+            seq = torch.randint(3, V, (B, S), generator=g)
+            lengths = torch.randint(2, S, (B,), generator=g)
+            seq = torch.where(torch.arange(S).unsqueeze(0) < lengths.unsqueeze(1), seq, torch.zeros_like(seq))
+            if masked:
+                seq[torch.arange(B), lengths] = 1
+            out.append({"item": seq.cuda(), "item.target": torch.randint(3, V, (B,), generator=g).cuda()})
+        return out
+
+    for cls, mod_cls, kw, masked in ((BERT4RecModel, MaskedTrainingModule, {"initializer_range": 0.2}, True),
+                                     (SASRecModel, NextItemPredictionTrainingModule, {"mode": "full"}, False)):
+        model = cls(H, 2, 2, V, S, 0.1, **kw)
+        results = []
+        for use_graph in (False, True):
+            module = mod_cls(model, item_tokenizer=Tok(), metrics=build_metrics({"recall": [1, 10], "ndcg": [10], "mrr": [10], "rank": []})).cuda().eval()
+            module.eval_graph = use_graph
+            steps = [module.validation_step_end(module.validation_step(b, i)) for i, b in enumerate(batches(masked))]
+            results.append((steps, module.validation_epoch_end(None)))
+            if use_graph:
+                assert len(module._eval_graphs) == 1
+        (s0, e0), (s1, e1) = results
+        for a, b in zip(s0, s1):
+            assert set(a) == set(b) and all(torch.equal(a[k].float().cpu(), b[k].float().cpu()) for k in a)
+        assert all(torch.equal(e0[k].cpu(), e1[k].cpu()) for k in e0)
