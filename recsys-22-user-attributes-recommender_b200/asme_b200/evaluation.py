@@ -8,7 +8,9 @@ list is already ordered best-first (ties -> lowest item id, where ``torch.sort``
 Same class names, constructor arguments, headers and return shapes as the reference; dense tensors still work (CPU
 included) and follow the reference arithmetic literally.
 """
-from typing import Any, Dict, List, Tuple
+import csv
+import itertools
+from typing import IO, Any, Dict, List, Tuple
 
 import numpy as np
 import torch
@@ -153,3 +155,70 @@ class ExtractRecommendationEvaluator(_TopNEvaluator):
     def evaluate(self, batch_index, batch, logits) -> List[Any]:
         _, indices = top_predictions(logits, self.num_predictions)
         return self._filtered(self.vocab_lookup[indices], indices)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the writers of the predict command (asme/core/writer/prediction/batch_prediction_writer.py): one batch at a time into a CSV
+# file.  ``logits`` is whatever the evaluators accept (dense tensor or FusedPredictions; both have ``.shape[0]``).
+# ---------------------------------------------------------------------------------------------------------------
+class BatchEvaluationWriter:
+    def __init__(self, evaluators: List[BatchEvaluator]):
+        self.evaluators = evaluators
+
+    def init_file(self, file_handle: IO[str]):
+        self.file_handle = file_handle
+        self.csv_writer = csv.writer(file_handle)
+        self.csv_writer.writerow(itertools.chain.from_iterable(self.headers))
+
+    def _results(self, batch_index, batch, logits):
+        return [(e.evaluate(batch_index, batch, logits), e.eval_samplewise(), e.get_header()) for e in self.evaluators]
+
+    def write_evaluation(self, batch_index, batch, logits):
+        raise NotImplementedError
+
+
+def _append(row: List[Any], value, header: List[str]) -> None:
+    if len(header) > 1:
+        row.extend(value)
+    else:
+        row.append(value)
+
+
+class CSVMultiLineWriter(BatchEvaluationWriter):
+    """one line per (sample, recommendation position), the position in a leading ``order`` column (:33-77).  Like the reference,
+    the number of lines per sample is the length of the list-valued evaluators' output for the batch's SECOND sample
+    (``eval[1]``, :62) -- all samples have num_predictions entries unless a selected-items filter shortened some."""
+
+    def __init__(self, evaluators: List[BatchEvaluator]):
+        super().__init__(evaluators)
+        self.headers = [["order"]] + [e.get_header() for e in evaluators]
+
+    def write_evaluation(self, batch_index, batch, logits):
+        results = self._results(batch_index, batch, logits)
+        rows = []
+        for sample in range(logits.shape[0]):
+            num_rows = [len(values[1]) for values, samplewise, _ in results if not samplewise]
+            for i in range(num_rows[0]):
+                row = [str(i + 1)]
+                for values, samplewise, header in results:
+                    _append(row, values[sample] if samplewise else values[sample][i], header)
+                rows.append(row)
+        self.csv_writer.writerows(rows)
+
+
+class CSVSingleLineWriter(BatchEvaluationWriter):
+    """one line per sample, list-valued outputs written as lists (:79-117)"""
+
+    def __init__(self, evaluators: List[BatchEvaluator]):
+        super().__init__(evaluators)
+        self.headers = [e.get_header() for e in evaluators]
+
+    def write_evaluation(self, batch_index, batch, logits):
+        results = self._results(batch_index, batch, logits)
+        rows = []
+        for sample in range(logits.shape[0]):
+            row: List[Any] = []
+            for values, _, header in results:
+                _append(row, values[sample], header)
+            rows.append(row)
+        self.csv_writer.writerows(rows)

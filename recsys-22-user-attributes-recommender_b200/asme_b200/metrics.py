@@ -192,6 +192,11 @@ class FusedPredictions:
         n = self.rank.shape[0] if self.rank is not None else self.topk_idx.shape[0]
         return torch.Size([n, self.num_items])
 
+    @property
+    def shape(self):
+        """(N, I) of the dense tensor this object stands for -- the reference's prediction writers read ``logits.shape[0]``"""
+        return self.size()
+
 
 class MetricsSample:
     def __init__(self, sampled_predictions, positive_item_mask, metric_mask):

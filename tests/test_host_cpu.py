@@ -219,3 +219,47 @@ def test_predict_evaluators_dense_and_fused_agree():
         E.ExtractScoresEvaluator(tok, 8).evaluate(0, batch, fused)
     with pytest.raises(RuntimeError, match="log-sum-exp"):
         E.ExtractScoresEvaluator(tok, 3).evaluate(0, batch, FusedPredictions(None, idx.to(torch.int32), val, None, V))
+
+
+def test_predict_writers_reproduce_the_reference_csv(golden_dir):
+    """asme/core/writer/prediction/batch_prediction_writer.py: CSV text of the UNMODIFIED reference evaluators + writers on seeded
+    logits (tests/golden/make_predict_golden.py).  Dense input: identical text.  Fused input (top-n list + log-sum-exp): identical
+    except for the last bits of the softmax scores."""
+    import csv
+    import io
+    import json
+    from asme_b200 import evaluation as E
+    from asme_b200.metrics import FusedPredictions
+    with open(os.path.join(golden_dir, "predict_small.json")) as f:
+        g = json.load(f)
+
+    class Tok(_Tok):
+        def __init__(self, tokens):
+            self.vocabulary = _Vocab(0)
+            self.vocabulary._tokens = list(tokens)
+
+    tok = Tok(g["tokens"])
+    n = g["num_predictions"]
+    logits = torch.tensor(g["logits"])
+    batch = {k: torch.tensor(v) for k, v in g["batch"].items()}
+    val, idx = torch.topk(logits, n, dim=1)
+    fused = FusedPredictions(None, idx.to(torch.int32), val, None, logits.shape[1], lse=torch.logsumexp(logits, dim=1))
+    assert fused.shape[0] == logits.shape[0]
+
+    def run(writer_cls, preds):
+        evaluators = [E.ExtractSampleIdEvaluator(), E.LogInputEvaluator(tok), E.TrueTargetEvaluator(tok),
+                      E.ExtractRecommendationEvaluator(tok, n), E.ExtractScoresEvaluator(tok, n)]
+        out = io.StringIO()
+        w = writer_cls(evaluators)
+        w.init_file(out)
+        w.write_evaluation(0, batch, preds)
+        return out.getvalue()
+
+    for name, cls in (("multi_line", E.CSVMultiLineWriter), ("single_line", E.CSVSingleLineWriter)):
+        assert run(cls, logits) == g[name]
+        got, want = list(csv.reader(io.StringIO(run(cls, fused)))), list(csv.reader(io.StringIO(g[name])))
+        assert len(got) == len(want) and got[0] == want[0]
+        for a, b in zip(got[1:], want[1:]):
+            assert a[:-1] == b[:-1]
+            fa, fb = np.asarray(json.loads(a[-1]), dtype=np.float64), np.asarray(json.loads(b[-1]), dtype=np.float64)
+            np.testing.assert_allclose(fa, fb, rtol=1e-5)
