@@ -228,6 +228,19 @@ def test_tc_topk_c5_shape_properties(ops):
     assert torch.equal(pos[in_list].int(), rank[in_list])
     dense_rank = (dense > ts[sub].unsqueeze(1)).sum(dim=1) + 1
     assert ((dense_rank - rank[sub]).abs() <= 2).all()
+    # predict path at full size: the log-sum-exp of the second sweep turns list entries into softmax scores (asme_b200.evaluation)
+    rmax, rsum, _ = ops.tc_score_ce_partial(hb, wb, b, target)
+    lse = rmax + torch.log(rsum)
+    assert (lse >= val[:, 0]).all()                                            # lse >= max logit
+    p = torch.exp(val - lse.unsqueeze(1))
+    assert (p.sum(dim=1) <= 1.0 + 1e-5).all() and (p > 0).all()
+    torch.testing.assert_close(lse[sub], torch.logsumexp(dense.double(), dim=1).float(), rtol=1e-5, atol=1e-4)
+    # the candidate-FIFO depth (ring slots vs FIFO entries) must not change any result
+    for depth in (8, 16):
+        ops._lib.call("asme_b200_tc_score_tune", 7, depth)
+        again = ops.tc_score_topk(hb, wb, b, k, target=target)
+        assert torch.equal(again["topk_idx"], out["topk_idx"]) and torch.equal(again["topk_val"], val)
+    ops._lib.call("asme_b200_tc_score_tune", 7, 12)
 
 
 @pytest.mark.parametrize("R,V,H", [(1, 13, 64), (300, 3709, 64), (130, 12104, 64), (100, 1031, 100), (64, 30000, 128), (5253, 3709, 64),
