@@ -157,6 +157,50 @@ class ExtractRecommendationEvaluator(_TopNEvaluator):
         return self._filtered(self.vocab_lookup[indices], indices)
 
 
+class PerSampleMetricsEvaluator(BatchEvaluator):
+    """the module's metrics per sample (evaluation.py:239-287): switches every metric of ``module.metrics`` to per-sample
+    storage on first use, feeds it this batch and returns one row of metric values per sample.  Fused input: the values are
+    closed forms of the target's exact rank (``FusedPredictions.rank``, from ``module.predict_topn(batch, n, with_rank=True)``);
+    a selected-items filter changes the candidate set and therefore needs the dense logits."""
+
+    def __init__(self, item_tokenizer, selected_items, module):
+        self.item_tokenizer = item_tokenizer
+        self.selected_items = selected_items
+        self.module = module
+        self.header = module.metrics.get_metric_names()
+        self.samplewise_metrics_set = False
+
+    def eval_samplewise(self) -> bool:
+        return True
+
+    def evaluate(self, batch_index, batch, logits) -> List[Any]:
+        from .metrics import MetricStorageMode
+        container = self.module.metrics
+        if not self.samplewise_metrics_set:          # only here, so that training is not affected (:268-273)
+            for metric in container.get_metrics():
+                metric.set_metrics_storage_mode(MetricStorageMode.PER_SAMPLE)
+            self.samplewise_metrics_set = True
+        metrics = [m for m in container.get_metrics() if m._storage_mode == MetricStorageMode.PER_SAMPLE]
+        if isinstance(logits, FusedPredictions):
+            if self.selected_items:
+                raise RuntimeError("asme_b200: per-sample metrics over selected items need the dense logits (module.predict_step)")
+            if logits.rank is None:
+                raise RuntimeError("asme_b200: this fused prediction carries no target rank (module.predict_topn(..., with_rank=True))")
+            for metric in metrics:
+                metric.update_from_ranks(logits.rank)
+        else:
+            targets = batch[TARGET_ENTRY_NAME].to(logits.device)
+            item_mask = torch.nn.functional.one_hot(targets, logits.size()[1])
+            if self.selected_items:
+                chosen = torch.tensor(self.selected_items, dtype=torch.int32, device=logits.device)
+                logits = torch.index_select(logits, 1, chosen)
+                item_mask = torch.index_select(item_mask, 1, chosen)
+            for metric in metrics:
+                metric.update(logits, item_mask)
+        values = [m.raw_metric_values()[batch_index].cpu().numpy() for m in metrics]
+        return np.asarray(values).T.tolist()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the writers of the predict command (asme/core/writer/prediction/batch_prediction_writer.py): one batch at a time into a CSV
 # file.  ``logits`` is whatever the evaluators accept (dense tensor or FusedPredictions; both have ``.shape[0]``).

@@ -505,7 +505,8 @@ class TransformerRecommenderModel(ArenaModule):
             out = score_rows_tc(hb, wb, b, target, k, full_rank)
             if with_loss:
                 rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, target)
-                nll = rmax + torch.log(rsum) - tl
+                out["lse"] = rmax + torch.log(rsum)
+                nll = out["lse"] - tl
                 keep = target.ne(pad_id)
                 out["loss"] = (nll * keep).sum() / keep.sum()
             return out
@@ -513,7 +514,8 @@ class TransformerRecommenderModel(ArenaModule):
         out = score_rows(m_rows, w, b, target, k)
         if with_loss:      # nn.CrossEntropyLoss(ignore_index=pad) on the selected rows (masked_training_module.py:150)
             rmax, rsum, _tl = ops.score_ce_partial(m_rows, w, b, target)
-            nll = rmax + torch.log(rsum) - out["target_score"]
+            out["lse"] = rmax + torch.log(rsum)
+            nll = out["lse"] - out["target_score"]
             keep = target.ne(pad_id)
             out["loss"] = (nll * keep).sum() / keep.sum()
         return out

@@ -163,12 +163,20 @@ class _ModuleBase(nn.Module):
         return None
 
     @torch.no_grad()
-    def predict_topn(self, batch, num_predictions: int) -> FusedPredictions:
+    def predict_topn(self, batch, num_predictions: int, with_rank: bool = False) -> FusedPredictions:
         """what ``predict_step`` + ``softmax`` + ``sort`` + ``[:, :num_predictions]`` deliver, without the (N, I) logits: the
-        top-n list (best first) and the row log-sum-exp, straight from the scoring sweeps"""
+        top-n list (best first) and the row log-sum-exp, straight from the scoring sweeps.  ``with_rank`` (the batch must carry
+        single targets): also the exact rank and score of every target, which is what per-sample metrics are computed from."""
         seq = batch[ITEM_SEQ_ENTRY_NAME]
         pm = get_padding_mask(seq, self.item_tokenizer.pad_token_id)
         rows = self._prediction_rows(seq, pm)
+        if with_rank:
+            extra = dict(rows=rows, rows_one_per_sequence=True) if rows is not None else dict(select="last")
+            out = self.model.evaluate_rank(seq, pm, get_additional_meta_data(self.model, batch), batch[TARGET_ENTRY_NAME],
+                                           k=num_predictions, with_loss=True, pad_id=self.item_tokenizer.pad_token_id, full_rank=True,
+                                           **extra)
+            return FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], self.model.item_vocab_size,
+                                    lse=out["lse"])
         out = self.model.recommend(seq, pm, get_additional_meta_data(self.model, batch), num_predictions, rows=rows, select="last",
                                    rows_one_per_sequence=rows is not None)
         return FusedPredictions(None, out["topk_idx"], out["topk_val"], None, self.model.item_vocab_size, lse=out["lse"])

@@ -291,3 +291,34 @@ def test_predict_topn_matches_softmax_sort_of_the_dense_logits(precision):
         assert (np.diff(got_s, axis=1) <= 1e-7).all()                      # best first
     with pytest.raises(ValueError, match="1..32"):
         module.predict_topn(batch, 40)
+
+
+def test_per_sample_metrics_evaluator_fused_equals_dense():
+    """PerSampleMetricsEvaluator: module.predict_topn(batch, n, with_rank=True) (exact target rank from the counting sweep) gives the
+    per-sample metric values of the reference arithmetic on predict_step's dense logits (fp32 policy: identical ranks)"""
+    from asme_b200.models import BERT4RecModel
+    from asme_b200.modules import MaskedTrainingModule
+    from asme_b200.metrics import build_metrics
+    from asme_b200.evaluation import PerSampleMetricsEvaluator, top_predictions
+    torch.manual_seed(3)
+    V, S, H, B, n = 903, 20, 64, 40, 10
+
+    class Tok:
+        pad_token_id, mask_token_id = 0, 1
+
+    model = BERT4RecModel(H, 2, 2, V, S, 0.1, initializer_range=0.2)
+    model.precision = "fp32"
+    names = {"recall": [1, 10], "ndcg": [10], "mrr": [10], "rank": []}
+    seq, _, lengths = _random_batch(torch.Generator().manual_seed(9), B, S, V, p_mask=0.0)
+    seq[torch.arange(B), lengths - 1] = 1
+    batch = {"item": seq.cuda(), "item.target": torch.randint(3, V, (B,), generator=torch.Generator().manual_seed(4)).cuda()}
+    rows = []
+    for fused in (True, False):
+        module = MaskedTrainingModule(model, item_tokenizer=Tok(), metrics=build_metrics(names)).cuda().eval()
+        ev = PerSampleMetricsEvaluator(None, None, module)
+        preds = module.predict_topn(batch, n, with_rank=True) if fused else module.predict_step(batch, 0).float()
+        rows.append(np.asarray(ev.evaluate(0, batch, preds)))
+        if fused:
+            assert preds.rank is not None and preds.lse is not None and top_predictions(preds, n)[0].shape == (B, n)
+    assert rows[0].shape == (B, 5)
+    np.testing.assert_allclose(rows[0], rows[1], rtol=1e-6, atol=1e-7)

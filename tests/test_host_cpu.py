@@ -263,3 +263,31 @@ def test_predict_writers_reproduce_the_reference_csv(golden_dir):
             assert a[:-1] == b[:-1]
             fa, fb = np.asarray(json.loads(a[-1]), dtype=np.float64), np.asarray(json.loads(b[-1]), dtype=np.float64)
             np.testing.assert_allclose(fa, fb, rtol=1e-5)
+
+
+def test_per_sample_metrics_evaluator_on_fused_ranks():
+    """evaluation.py:239-287 on the fused input: per-sample metric values are closed forms of the target's exact rank"""
+    from types import SimpleNamespace
+    from asme_b200 import evaluation as E
+    from asme_b200.metrics import FusedPredictions, build_metrics
+    gen = torch.Generator().manual_seed(5)
+    N, V = 7, 50
+    module = SimpleNamespace(metrics=build_metrics({"recall": [1, 5], "ndcg": [5], "mrr": [5], "rank": []}))
+    ev = E.PerSampleMetricsEvaluator(_Tok(V), None, module)
+    assert ev.eval_samplewise() and ev.get_header() == module.metrics.get_metric_names()
+    names = ev.get_header()
+    for batch_index in range(2):                      # raw_metric_values()[batch_index]: one entry per evaluated batch
+        logits = torch.randn(N, V, generator=gen)
+        targets = torch.randint(3, V, (N,), generator=gen)
+        rank = (logits > logits.gather(1, targets.unsqueeze(1))).sum(dim=1) + 1
+        fused = FusedPredictions(rank.to(torch.int32), None, None, None, V)
+        rows = np.asarray(ev.evaluate(batch_index, {"item.target": targets}, fused))
+        assert rows.shape == (N, len(names))
+        r = rank.numpy().astype(np.float64)
+        want = {"recall@1": r <= 1, "recall@5": r <= 5, "NDCG@5": (r <= 5) / np.log2(r + 1), "MRR@5": (r <= 5) / r, "rank": r}
+        for j, name in enumerate(names):
+            np.testing.assert_allclose(rows[:, j], np.asarray(want[name], dtype=np.float64), rtol=1e-6, err_msg=name)
+    with pytest.raises(RuntimeError, match="no target rank"):
+        ev.evaluate(2, {}, FusedPredictions(None, torch.zeros(N, 3, dtype=torch.int32), torch.zeros(N, 3), None, V))
+    with pytest.raises(RuntimeError, match="selected items"):
+        E.PerSampleMetricsEvaluator(_Tok(V), [3, 4], module).evaluate(0, {}, fused)
