@@ -266,3 +266,54 @@ class CSVSingleLineWriter(BatchEvaluationWriter):
                 _append(row, values[sample], header)
             rows.append(row)
         self.csv_writer.writerows(rows)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the result writers of the evaluate command (asme/core/writer/results/results_writer.py): the metric dictionary of
+# ``metrics.compute()`` (0-dim tensors here) as JSON {"recommender_id", "metrics"} or as "metric name,value" CSV lines
+# ---------------------------------------------------------------------------------------------------------------
+def _plain(metrics: Dict[str, Any]) -> Dict[str, float]:
+    return {name: (float(value) if isinstance(value, torch.Tensor) else value) for name, value in metrics.items()}
+
+
+class ResultWriter:
+    def __init__(self, file_handle: IO[str]):
+        self.file_handle = file_handle
+
+    def write_overall_results(self, recommender_name: str, metrics: Dict[str, Any]):
+        raise NotImplementedError
+
+
+class JSONResultWriter(ResultWriter):
+    def write_overall_results(self, recommender_name: str, metrics: Dict[str, Any]):
+        import json
+        json.dump({"recommender_id": recommender_name, "metrics": _plain(metrics)}, self.file_handle)
+
+
+class CSVResultWriter(ResultWriter):
+    HEADER = ["metric name", "value"]
+
+    def __init__(self, file_handle: IO[str]):
+        super().__init__(file_handle)
+        self.csv_writer = csv.writer(file_handle)
+        self.csv_writer.writerow(self.HEADER)
+
+    def write_overall_results(self, recommender_name: str, metrics: Dict[str, Any]):
+        self.csv_writer.writerows([[name, value] for name, value in _plain(metrics).items()] + [["recommender_id", recommender_name]])
+
+
+SUPPORTED_RESULT_WRITERS = {".csv": CSVResultWriter, ".json": JSONResultWriter}
+
+
+def check_file_format_supported(output_file) -> bool:
+    import pathlib
+    return pathlib.Path(output_file).suffix in SUPPORTED_RESULT_WRITERS
+
+
+def build_result_writer(file_handle: IO[str]) -> ResultWriter:
+    """writer chosen by the extension of the file behind ``file_handle`` (.json / .csv)"""
+    import pathlib
+    suffix = pathlib.Path(file_handle.name).suffix
+    if suffix not in SUPPORTED_RESULT_WRITERS:
+        raise KeyError(f"{suffix} is not a supported format to write predictions to file")
+    return SUPPORTED_RESULT_WRITERS[suffix](file_handle)

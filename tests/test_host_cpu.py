@@ -291,3 +291,21 @@ def test_per_sample_metrics_evaluator_on_fused_ranks():
         ev.evaluate(2, {}, FusedPredictions(None, torch.zeros(N, 3, dtype=torch.int32), torch.zeros(N, 3), None, V))
     with pytest.raises(RuntimeError, match="selected items"):
         E.PerSampleMetricsEvaluator(_Tok(V), [3, 4], module).evaluate(0, {}, fused)
+
+
+def test_result_writers(tmp_path):
+    """writer/results/results_writer.py: JSON object / CSV lines of the overall metrics, chosen by file extension"""
+    import json
+    from asme_b200 import evaluation as E
+    metrics = {"recall@10": torch.tensor(0.25), "NDCG@10": torch.tensor(0.125), "MRR": 0.5}
+    with open(tmp_path / "r.json", "w") as f:
+        E.build_result_writer(f).write_overall_results("MaskedTrainingModule", metrics)
+    assert json.loads((tmp_path / "r.json").read_text()) == {"recommender_id": "MaskedTrainingModule",
+                                                            "metrics": {"recall@10": 0.25, "NDCG@10": 0.125, "MRR": 0.5}}
+    with open(tmp_path / "r.csv", "w", newline="") as f:
+        E.build_result_writer(f).write_overall_results("MaskedTrainingModule", metrics)
+    assert (tmp_path / "r.csv").read_text().splitlines() == ["metric name,value", "recall@10,0.25", "NDCG@10,0.125", "MRR,0.5",
+                                                             "recommender_id,MaskedTrainingModule"]
+    assert E.check_file_format_supported("x.json") and not E.check_file_format_supported("x.txt")
+    with open(tmp_path / "r.txt", "w") as f, pytest.raises(KeyError, match="not a supported format"):
+        E.build_result_writer(f)
