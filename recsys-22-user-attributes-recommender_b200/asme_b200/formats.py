@@ -168,11 +168,12 @@ class TokenisedSessions:
 
     def batch(self, session_ids: Iterable[int], positions: Optional[Iterable[int]] = None, max_seq_length: int = 200,
               pad_id: int = 0, extract_target: bool = True, dynamic_padding: bool = False,
-              pin: bool = False) -> Dict[str, torch.Tensor]:
+              pin: bool = False, entry_name: str = ITEM_SEQ_ENTRY_NAME) -> Dict[str, torch.Tensor]:
         """One collated batch: ``item`` (N, S) int64 right-padded, ``item.target`` (N) (with ``extract_target``), ``length``,
         ``sample_ids`` and, when ``positions`` are given (a position-index slice), ``pos``.  Per sample the reference computes
         ``seq = session[:pos + 1]``; ``target = seq[-1]``, ``item = seq[:-1]``; ``item = item[-S:]`` + right padding;
-        ``length`` is the length BEFORE the cut to S (collate.py:82), as the reference reports it."""
+        ``length`` is the length BEFORE the cut to S (collate.py:82), as the reference reports it.  ``entry_name``: key of the
+        sequence (a store of another CSV column, e.g. an item attribute, collates under its own name and ``<name>.target``)."""
         sid = np.asarray(list(session_ids) if not isinstance(session_ids, np.ndarray) else session_ids, dtype=np.int64)
         if sid.size and (sid.min() < 0 or sid.max() >= len(self)):
             raise Exception(f"{int(sid.max() if sid.max() >= len(self) else sid.min())} is not a valid index in [0, {len(self)}]")
@@ -193,10 +194,10 @@ class TokenisedSessions:
         valid = cols < kept[:, None]
         src = np.where(valid, first[:, None] + cols, 0)
         item = np.where(valid, np.asarray(self.tokens)[src.reshape(-1)].reshape(src.shape), pad_id).astype(np.int64)
-        out = {ITEM_SEQ_ENTRY_NAME: torch.from_numpy(item), "length": torch.from_numpy(n_in.astype(np.int64)),
+        out = {entry_name: torch.from_numpy(item), "length": torch.from_numpy(n_in.astype(np.int64)),
                SAMPLE_IDS: torch.from_numpy(sid)}
         if extract_target:
-            out[TARGET_ENTRY_NAME] = torch.from_numpy(np.asarray(self.tokens)[start + n_seq - 1].astype(np.int64))
+            out[entry_name + ".target"] = torch.from_numpy(np.asarray(self.tokens)[start + n_seq - 1].astype(np.int64))
         if pos is not None:
             out["pos"] = torch.from_numpy(pos)
         if pin and torch.cuda.is_available():
