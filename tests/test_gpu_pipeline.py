@@ -211,3 +211,57 @@ def test_sampled_and_fixed_subset_metrics_from_fused_predictions():
         np.testing.assert_allclose(sub, pred.gather(1, items.cuda()).cpu().numpy(), rtol=1e-5, atol=1e-5)
     finally:
         models.set_default_precision(old)
+
+
+def test_files_to_predictions_csv_end_to_end(golden_dir):
+    """either side of the hot path in one go: the reference's data files (session CSV + session index + position index + vocabulary)
+    -> pre-tokenised store -> collated batch -> GPU -> SASRec next-item top-n on the fused path -> the predict evaluators -> CSV text"""
+    import csv
+    import io
+    import os
+    from asme_b200 import evaluation as E
+    from asme_b200 import formats as F
+    from asme_b200.models import SASRecModel
+    from asme_b200.modules import NextItemPredictionTrainingModule
+    d = os.path.join(golden_dir, "formats")
+    vocab = F.read_vocabulary(os.path.join(d, "sessions.vocabulary.item_id.txt"))
+    store = F.TokenisedSessions.from_csv(os.path.join(d, "sessions.csv"), F.read_session_index(os.path.join(d, "sessions.session.idx")), vocab)
+    positions = F.read_position_index(os.path.join(d, "sessions.nextitem.idx"))
+    S, n = 12, 5
+    batch = {k: v.cuda() for k, v in store.batch(positions[:48, 0], positions[:48, 1], max_seq_length=S).items()}
+
+    class Vocab:
+        def tokens(self):
+            return list(vocab)
+
+        def ids(self):
+            return list(vocab.values())
+
+    class Tok:
+        pad_token_id, mask_token_id, vocabulary = 0, 1, Vocab()
+
+        def get_special_token_ids(self):
+            return [0, 1, 2]
+
+    torch.manual_seed(0)
+    module = NextItemPredictionTrainingModule(SASRecModel(64, 2, 1, len(vocab), S, 0.1, mode="full"), item_tokenizer=Tok()).cuda().eval()
+    preds = module.predict_topn(batch, n, with_rank=True)
+    writer = E.CSVSingleLineWriter([E.ExtractSampleIdEvaluator(), E.LogInputEvaluator(Tok()), E.TrueTargetEvaluator(Tok()),
+                                    E.ExtractRecommendationEvaluator(Tok(), n), E.ExtractScoresEvaluator(Tok(), n)])
+    out = io.StringIO()
+    writer.init_file(out)
+    writer.write_evaluation(0, batch, preds)
+    rows = list(csv.reader(io.StringIO(out.getvalue())))
+    assert rows[0] == ["SID", "input", "target", "recommendation", "score"] and len(rows) == 49
+    assert rows[1][0] == f"{int(positions[0, 0])}_{int(positions[0, 1])}"
+    # the written recommendations are the tokens of the fused top-n ids, best first, and agree with the dense logits' ordering
+    dense = module.predict_step(batch, 0).float()
+    want = torch.topk(dense, n, dim=1).indices.cpu().numpy()
+    tokens = list(vocab)
+    agree = 0
+    for i, row in enumerate(rows[1:]):
+        rec = eval(row[3])
+        assert len(rec) == n and all(t in vocab for t in rec)
+        agree += rec == [tokens[j] for j in want[i]]
+    assert agree >= 44                                   # bf16 near-ties may swap neighbours in a few rows
+    assert ((preds.rank >= 1) & (preds.rank <= len(vocab))).all()
