@@ -203,3 +203,30 @@ class TokenisedSessions:
         if pin and torch.cuda.is_available():
             out = {k: v.pin_memory() for k, v in out.items()}
         return out
+
+
+def epoch_batches(n_entries: int, batch_size: int, shuffle: bool = True, seed: int = 0, epoch: int = 0, world: int = 1, rank: int = 0,
+                  drop_last: bool = False) -> List[np.ndarray]:
+    """Entry indices of one epoch for this rank, cut into batches -- the order ``torch.utils.data.DistributedSampler`` (what
+    Lightning's ``ddp`` puts in front of the reference's datasets) + a ``DataLoader(batch_size=...)`` produce: a permutation
+    seeded with ``seed + epoch``, padded to a multiple of ``world`` by wrapping around (or truncated with ``drop_last``), rank r
+    takes entries r, r + world, ...  Feed the batches to ``TokenisedSessions.batch(positions[idx, 0], positions[idx, 1], ...)``."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        order = torch.randperm(n_entries, generator=g).numpy()
+    else:
+        order = np.arange(n_entries)
+    if drop_last and n_entries % world != 0:
+        total = (n_entries // world) * world
+        order = order[:total]
+    else:
+        total = -(-n_entries // world) * world
+        pad = total - order.size
+        if pad > 0:
+            reps = -(-pad // max(order.size, 1))
+            order = np.concatenate([order, np.tile(order, reps)[:pad]])
+    mine = order[rank:total:world]
+    return [mine[i:i + batch_size] for i in range(0, mine.size, batch_size)]
