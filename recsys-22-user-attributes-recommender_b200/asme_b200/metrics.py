@@ -378,3 +378,47 @@ def build_metrics(spec: Dict[str, List[int]], sampler=None) -> AggregateMetricsC
         else:
             metrics += [cls(k) for k in ks]
     return AggregateMetricsContainer([RankingMetricsContainer(metrics, sampler or AllItemsSampler())])
+
+
+# ------------------------------------------------------------------------------------------------
+# containers built by the reference's own factories
+# ------------------------------------------------------------------------------------------------
+_CLASS_TO_ID = {"RecallMetric": "recall", "NormalizedDiscountedCumulativeGainMetric": "ndcg", "DiscountedCumulativeGainMetric": "dcg",
+                "MRRMetric": "mrr", "PrecisionMetric": "precision", "F1Metric": "f1", "MRRFullMetric": "mrr_full", "Rank": "rank"}
+
+
+def _adopt_sampler(sampler):
+    kind = type(sampler).__name__
+    if kind == "AllItemsSampler":
+        return AllItemsSampler()
+    if kind == "FixedItemsSampler":
+        return FixedItemsSampler(sampler.fixed_items)
+    if kind == "NegativeMetricsSampler":
+        return NegativeMetricsSampler(sampler.weights, sampler.sample_size, sampler.metrics_suffix)
+    raise NotImplementedError(f"asme_b200: metrics sampler {kind} has no B200 counterpart")
+
+
+def adopt_metrics(container):
+    """The ASME module factory builds the ``metrics`` argument with the reference's OWN ``MetricsContainerFactory``
+    (init/factories/modules/modules.py:88, init/factories/metrics/metrics_container.py:31-33): an
+    ``AggregateMetricsContainer`` of ``RankingMetricsContainer(metrics, sampler)`` whose metrics sort dense (N,I) logits.  The
+    B200 evaluation step has no dense logits, so such a container is re-expressed -- same metric names, k values, sampler
+    parameters and name suffixes -- with the classes of this module.  Containers of this module pass through unchanged."""
+    if container is None or isinstance(container, MetricsContainer):
+        return container
+    groups = getattr(container, "containers", None)
+    if groups is None:
+        groups = [container]
+    adopted = []
+    for group in groups:
+        metrics = []
+        for metric in group.metrics:
+            metric_id = _CLASS_TO_ID.get(type(metric).__name__)
+            if metric_id is None:
+                raise NotImplementedError(f"asme_b200: metric {type(metric).__name__} has no B200 counterpart")
+            cls = METRIC_REGISTRY[metric_id]
+            mode = getattr(getattr(metric, "_storage_mode", None), "name", "SUM")
+            kwargs = dict(storage_mode=MetricStorageMode[mode])
+            metrics.append(cls(**kwargs) if metric_id in ("mrr_full", "rank") else cls(int(metric._k), **kwargs))
+        adopted.append(RankingMetricsContainer(metrics, _adopt_sampler(group.sampler)))
+    return AggregateMetricsContainer(adopted)

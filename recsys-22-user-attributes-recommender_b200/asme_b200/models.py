@@ -21,6 +21,7 @@ from torch import nn
 from . import ops
 from .arena import ArenaModule
 from .data import InputSequence
+from .inject import resolve_tokenizers, resolve_vocab_size
 from .engine import BLOCKS, MODIFIER, EncoderConfig, EncoderEngine, Saved, block_param_specs, modifier_param_specs
 
 PAD_TOKEN_ID = 0
@@ -668,6 +669,7 @@ class BERT4RecModel(TransformerRecommenderModel):
                  initializer_range: float = 0.02, transformer_intermediate_size: int = None,
                  transformer_attention_dropout: float = None):
         super().__init__()
+        item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
             raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
         H, V = transformer_hidden_size, item_vocab_size
@@ -707,6 +709,7 @@ class KeBERT4RecModel(TransformerRecommenderModel):
                  transformer_intermediate_size: Optional[int] = None, transformer_attention_dropout: Optional[float] = None,
                  attribute_vocab_sizes: Dict[str, int] = None):
         super().__init__()
+        item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
             raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
         H, V = transformer_hidden_size, item_vocab_size
@@ -720,7 +723,7 @@ class KeBERT4RecModel(TransformerRecommenderModel):
         specs += block_param_specs(cfg) + modifier_param_specs(H)
         specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
         self._setup(cfg, V, max_seq_length, specs, prefusion_attributes, postfusion_attributes,
-                    additional_attributes_tokenizer, attribute_vocab_sizes, postfusion_merge_function)
+                    resolve_tokenizers(additional_attributes_tokenizer), attribute_vocab_sizes, postfusion_merge_function)
         _init_normal(self, initializer_range)
 
 
@@ -743,6 +746,7 @@ class SASRecModel(TransformerRecommenderModel):
                  transformer_attention_dropout: float = None, mode: str = "neg_sampling",
                  attribute_vocab_sizes: Dict[str, int] = None):
         super().__init__()
+        item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
             raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
         H, V = transformer_hidden_size, item_vocab_size
@@ -761,7 +765,7 @@ class SASRecModel(TransformerRecommenderModel):
         else:
             raise Exception(f"{mode} is an unknown projection mode. Choose either <full> or <neg_sampling>.")
         self._setup(cfg, V, max_seq_length, specs, prefusion_attributes, postfusion_attributes,
-                    additional_attributes_tokenizer, attribute_vocab_sizes, postfusion_merge_function)
+                    resolve_tokenizers(additional_attributes_tokenizer), attribute_vocab_sizes, postfusion_merge_function)
         if mode == "neg_sampling":      # SASRecProjectionComponent holds the TransformerEmbedding again (components.py:16-19)
             base = f"{_EMB}.item_embedding_layer"
             for sub in ("item_embedding.embedding.weight", "position_embedding.weight", "embedding_norm.weight",
@@ -804,6 +808,7 @@ class UBERT4RecModel(TransformerRecommenderModel):
                  transformer_intermediate_size: Optional[int] = None, transformer_attention_dropout: Optional[float] = None,
                  attribute_vocab_sizes: Dict[str, int] = None):
         super().__init__()
+        item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
             raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
         H, V = transformer_hidden_size, item_vocab_size
@@ -818,7 +823,7 @@ class UBERT4RecModel(TransformerRecommenderModel):
         specs += [("_ghost_ln1+", (2 * H,)), (self.ln2_paths[0] + "+", (H,)), (self.ln2_paths[1], (H,))]
         specs += block_param_specs(cfg, self.blocks_path) + modifier_param_specs(H)
         specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
-        toks, sizes = _tokenizer_sizes(additional_tokenizers, attribute_vocab_sizes)
+        toks, sizes = _tokenizer_sizes(resolve_tokenizers(additional_tokenizers), attribute_vocab_sizes)
         # rows of the segment table as the reference counts them (components.py:75-90): one for the item attributes as a
         # whole plus one per user attribute; rows 0 (user) and 1 (items) are the ones ever read
         seg_rows = ((1 if additional_attributes else 0) + len(user_attributes or {})) if segment_embedding else 0
@@ -852,6 +857,7 @@ class UserSASRecModel(TransformerRecommenderModel):
                  transformer_attention_dropout: float = None, mode: str = "neg_sampling", positional_embedding: bool = True,
                  replace_first_item: bool = False, attribute_vocab_sizes: Dict[str, int] = None):
         super().__init__()
+        item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
             raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
         if replace_first_item:
@@ -873,7 +879,7 @@ class UserSASRecModel(TransformerRecommenderModel):
                   (self.ln2_paths[0] + "+", (H,)), (self.ln2_paths[1], (H,))]
         specs += block_param_specs(cfg, self.blocks_path)
         specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
-        toks, sizes = _tokenizer_sizes(additional_tokenizers, attribute_vocab_sizes)
+        toks, sizes = _tokenizer_sizes(resolve_tokenizers(additional_tokenizers), attribute_vocab_sizes)
         seg_rows = ((1 if additional_attributes else 0) + len(user_attributes or {})) if segment_embedding else 0
         if segment_embedding and (not user_attributes or seg_rows < 2):
             raise NotImplementedError("segment_embedding needs user attributes and at least two segment rows")

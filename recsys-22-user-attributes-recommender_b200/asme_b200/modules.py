@@ -18,7 +18,8 @@ from torch import nn
 
 from . import ops
 from .data import InputSequence
-from .metrics import FusedPredictions, MetricsContainer
+from .inject import resolve_tokenizer
+from .metrics import FusedPredictions, MetricsContainer, adopt_metrics
 from .models import MASK_TOKEN_ID, PAD_TOKEN_ID, TransformerRecommenderModel, last_position_rows, mask_position_rows, score_rows
 
 ITEM_SEQ_ENTRY_NAME = "item"                 # asme/data/datasets/__init__.py
@@ -89,7 +90,24 @@ class _TokenIds:
         self.pad_token_id, self.mask_token_id = pad_token_id, mask_token_id
 
 
-class _ModuleBase(nn.Module):
+def _item_tokenizer(given):
+    """``@inject(item_tokenizer=InjectTokenizer("item"))`` (modules/masked_training_module.py:28,
+    next_item_prediction_training_module.py:34, sequence_next_item_prediction_training_module.py:34): the ASME factory passes None
+    and the tokenizer comes from the build context; outside a container the default special-token ids are used"""
+    tok = resolve_tokenizer("item", given)
+    return tok if tok is not None else _TokenIds()
+
+
+try:        # inside an ASME process the modules ARE LightningModules (pl.Trainer type-checks what it is given); without
+    import pytorch_lightning as _pl          # Lightning (this image) asme_b200.trainer.Trainer drives the same hooks
+    _LightningBase = _pl.LightningModule
+    if not (isinstance(_LightningBase, type) and issubclass(_LightningBase, nn.Module)):
+        _LightningBase = nn.Module
+except Exception:
+    _LightningBase = nn.Module
+
+
+class _ModuleBase(_LightningBase):
     """MetricsTrait + the slice of the LightningModule protocol the runner uses."""
 
     def __init__(self):
@@ -102,6 +120,8 @@ class _ModuleBase(nn.Module):
 
     def log(self, name, value, *args, **kwargs):
         self.logged[name] = value
+        if _LightningBase is not nn.Module and (getattr(self, "_trainer", None) or self.__dict__.get("trainer")) is not None:
+            super().log(name, value, *args, **kwargs)          # attached to a pl.Trainer: loggers, checkpoint monitors, early stopping
 
     def save_hyperparameters(self, *args, **kwargs):
         pass
@@ -185,8 +205,12 @@ class _ModuleBase(nn.Module):
         return min(32, max(self.metrics.max_k(), 1)) if hasattr(self.metrics, "max_k") else 10
 
     def _full_rank(self) -> bool:
+        """the exact target rank (a second, count-only sweep) is needed by ``rank`` / full ``MRR`` -- and by every metric whose k
+        exceeds the 32 entries the fused list holds: without it a miss would be ranked 33 and counted as a hit @50"""
         fn = getattr(self.metrics, "needs_full_rank", None)
-        return True if fn is None else bool(fn())
+        if fn is None or bool(fn()):
+            return True
+        return hasattr(self.metrics, "max_k") and self.metrics.max_k() > 32
 
     def _adam(self, weight_decay: float):
         if self.use_fused_adam:
@@ -207,8 +231,8 @@ class MaskedTrainingModule(_ModuleBase):
         self.learning_rate, self.beta_1, self.beta_2 = learning_rate, beta_1, beta_2
         self.weight_decay = weight_decay          # accepted and ignored, exactly like the reference (:165-168)
         self.num_warmup_steps = num_warmup_steps
-        self.item_tokenizer = item_tokenizer if item_tokenizer is not None else _TokenIds()
-        self.metrics = metrics
+        self.item_tokenizer = _item_tokenizer(item_tokenizer)
+        self.metrics = adopt_metrics(metrics)
 
     def _input(self, batch):
         seq = batch[ITEM_SEQ_ENTRY_NAME]
@@ -278,8 +302,8 @@ class NextItemPredictionTrainingModule(_ModuleBase):
         super().__init__()
         self.model = model
         self.learning_rate, self.beta_1, self.beta_2, self.weight_decay = learning_rate, beta_1, beta_2, weight_decay
-        self.item_tokenizer = item_tokenizer if item_tokenizer is not None else _TokenIds()
-        self.metrics = metrics
+        self.item_tokenizer = _item_tokenizer(item_tokenizer)
+        self.metrics = adopt_metrics(metrics)
         self.loss_function = loss_function     # CE with ignore_index=pad is fused into the scoring kernel
 
     def forward(self, batch, batch_idx=None):
@@ -343,8 +367,8 @@ class SequenceNextItemPredictionTrainingModule(_ModuleBase):
         super().__init__()
         self.model = model
         self.learning_rate, self.beta_1, self.beta_2, self.weight_decay = learning_rate, beta_1, beta_2, weight_decay
-        self.item_tokenizer = item_tokenizer if item_tokenizer is not None else _TokenIds()
-        self.metrics = metrics
+        self.item_tokenizer = _item_tokenizer(item_tokenizer)
+        self.metrics = adopt_metrics(metrics)
         self.loss_function = loss_function     # SASRecBinaryCrossEntropyLoss is fused into the pos/neg kernel
 
     def training_step(self, batch, batch_idx):

@@ -35,7 +35,6 @@ def register(verbose: bool = False) -> bool:
         if verbose:
             print(f"[asme_b200] ASME registry not available ({type(e).__name__}: {e}); nothing registered")
         return False
-    extra = {"sasrec-cross": {"mode": "full"}}
     for key, (module_cls, model_cls) in REGISTRATIONS.items():
         register_module(key, ModuleConfig(GenericModuleFactory, module_cls, {"model_cls": model_cls}), overwrite=True)
     return True

@@ -1,0 +1,91 @@
+"""C1 (BASELINE.json configs[0]): SASRec (``configs-new/sasrec-cross``) on the reference's ``tests/example_dataset``.
+
+``tests/golden/make_c1_golden.py`` ran the UNMODIFIED reference runner (``create_container`` -> module / dataloaders, hook loop) for
+three epochs and recorded the initial weights, every batch it saw, every training / validation loss and every step / epoch metric.
+Here the same batches go through the drop-in ``NextItemPredictionTrainingModule`` (strict fp32 policy) on the GPU: training_step
+-> loss.backward() -> Adam, validation_step -> validation_step_end -> validation_epoch_end.  Bar: losses within 1e-5 relative at
+the start (the trajectories of two fp32 implementations drift apart slowly; the last epoch is held to 1e-4), ranking metrics of
+every step and epoch IDENTICAL."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir):
+    z = np.load(os.path.join(golden_dir, "c1_sasrec_cross_example.npz"))
+    summary = json.loads(bytes(z["summary_json"]).decode())
+    return z, summary
+
+
+def _build(z, summary, use_fused_adam):
+    from asme_b200 import models
+    from asme_b200.metrics import build_metrics
+    from asme_b200.models import SASRecModel
+    from asme_b200.modules import NextItemPredictionTrainingModule
+    models.set_default_precision("fp32")
+    m = summary["model"]
+    model = SASRecModel(m["transformer_hidden_size"], m["num_transformer_heads"], m["num_transformer_layers"], summary["tokenizer"]["len"],
+                        m["max_seq_length"], m["transformer_dropout"], mode=m["mode"])
+    spec = {name.lower(): ks for name, ks in summary["metrics"]["full"]["metrics"].items()}
+    hp = summary["module"]
+    module = NextItemPredictionTrainingModule(model, metrics=build_metrics(spec), learning_rate=hp["learning_rate"], beta_1=hp["beta_1"],
+                                              beta_2=hp["beta_2"], weight_decay=hp["weight_decay"])
+    module.use_fused_adam = use_fused_adam
+    weights = {k[len("w::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+    own = set(module.state_dict().keys())
+    missing = [k for k in weights if k not in own]
+    assert not missing, f"reference state-dict keys the drop-in module does not have: {missing}"
+    module.load_state_dict(weights, strict=False)
+    return module.cuda()
+
+
+@pytest.mark.parametrize("use_fused_adam", [True, False])
+def test_c1_replay_matches_the_reference_run(golden_dir, use_fused_adam):
+    from asme_b200 import models
+    old = models.DEFAULT_PRECISION
+    try:
+        z, summary = _load(golden_dir)
+        module = _build(z, summary, use_fused_adam)
+        optimizer = module.configure_optimizers()
+        for epoch, rec in enumerate(summary["epochs"]):
+            module.train()
+            tol = 1e-5 if epoch == 0 else 1e-4
+            for i, want in enumerate(rec["train_loss"]):
+                batch = {"item": torch.from_numpy(z[f"train::{epoch}::{i}::item"]).cuda(),
+                         "item.target": torch.from_numpy(z[f"train::{epoch}::{i}::target"]).cuda()}
+                optimizer.zero_grad()
+                loss = module.training_step(batch, i)["loss"]
+                loss.backward()
+                optimizer.step()
+                assert float(loss) == pytest.approx(want, rel=tol, abs=tol), f"training loss, epoch {epoch} step {i}"
+            module.eval()
+            with torch.no_grad():
+                for i, want in enumerate(rec["val_step"]):
+                    batch = {"item": torch.from_numpy(z[f"val::{epoch}::{i}::item"]).cuda(),
+                             "item.target": torch.from_numpy(z[f"val::{epoch}::{i}::target"]).cuda()}
+                    out = module.validation_step(batch, i)
+                    assert float(module.logged["val_loss"]) == pytest.approx(rec["val_loss"][i], rel=10 * tol, abs=10 * tol)
+                    got = module.validation_step_end(out)
+                    assert {k: float(v) for k, v in got.items()} == pytest.approx(want, abs=1e-7), f"step metrics, epoch {epoch} step {i}"
+                got = module.validation_epoch_end(None)
+            assert {k: float(v) for k, v in got.items()} == pytest.approx(rec["val_epoch"], abs=1e-7), f"epoch metrics, epoch {epoch}"
+        with torch.no_grad():
+            for i, want in enumerate(summary["test_step"]):
+                batch = {"item": torch.from_numpy(z[f"test::{i}::item"]).cuda(), "item.target": torch.from_numpy(z[f"test::{i}::target"]).cuda()}
+                got = module.test_step_end(module.test_step(batch, i))
+                assert {k: float(v) for k, v in got.items()} == pytest.approx(want, abs=1e-7)
+            got = module.test_epoch_end(None)
+        assert {k: float(v) for k, v in got.items()} == pytest.approx(summary["test_epoch"], abs=1e-7)
+        # the weights after three epochs of Adam
+        final = {k[len("final::"):]: z[k] for k in z.files if k.startswith("final::")}
+        sd = module.state_dict()
+        for name, want in final.items():
+            if name in sd and sd[name].dtype.is_floating_point:
+                np.testing.assert_allclose(sd[name].cpu().numpy(), want, rtol=2e-3, atol=2e-4, err_msg=name)
+    finally:
+        models.set_default_precision(old)
