@@ -62,7 +62,7 @@ def test_c1_replay_matches_the_reference_run(golden_dir, use_fused_adam):
                 loss = module.training_step(batch, i)["loss"]
                 loss.backward()
                 optimizer.step()
-                assert float(loss) == pytest.approx(want, rel=tol, abs=tol), f"training loss, epoch {epoch} step {i}"
+                assert float(loss.detach()) == pytest.approx(want, rel=tol, abs=tol), f"training loss, epoch {epoch} step {i}"
             module.eval()
             with torch.no_grad():
                 for i, want in enumerate(rec["val_step"]):
@@ -84,8 +84,17 @@ def test_c1_replay_matches_the_reference_run(golden_dir, use_fused_adam):
         # the weights after three epochs of Adam
         final = {k[len("final::"):]: z[k] for k in z.files if k.startswith("final::")}
         sd = module.state_dict()
+        bad = []
         for name, want in final.items():
-            if name in sd and sd[name].dtype.is_floating_point:
-                np.testing.assert_allclose(sd[name].cpu().numpy(), want, rtol=2e-3, atol=2e-4, err_msg=name)
+            if name not in sd or not sd[name].dtype.is_floating_point:
+                continue
+            # the key bias shifts every score of a query by the same amount, softmax cancels it: its true gradient is 0, what
+            # reaches Adam is rounding noise, and Adam normalises noise to steps of +-lr -- not comparable between implementations
+            if name.endswith("attention.linear_layers.1.bias"):
+                continue
+            got = sd[name].cpu().numpy()
+            if not np.allclose(got, want, rtol=2e-3, atol=2e-4):
+                bad.append((name, float(np.abs(got - want).max())))
+        assert not bad, f"weights after {len(summary['epochs'])} epochs differ: {bad}"
     finally:
         models.set_default_precision(old)
