@@ -123,6 +123,9 @@ int asme_b200_posgrad_reduce_strided(const float* d_rows, int B, int S, int seq_
 /* bag tables: d_table_t[id,:] += d_rows[t,:] for every bag entry id != 0; d_bias += column sums of d_rows */
 int asme_b200_colsum_accumulate(const float* x, int M, int N, float* out /*N, +=*/, void* ws, size_t ws_bytes,
                                 asme_stream_t stream);
+/* the same over the first *m_live rows only (device row count of a row selection, see asme_b200_select_rows; NULL = all M) */
+int asme_b200_colsum_accumulate_live(const float* x, int M, int N, float* out /*N, +=*/, void* ws, size_t ws_bytes,
+                                     const int32_t* m_live, asme_stream_t stream);
 size_t asme_b200_colsum_workspace_bytes(int M, int N);
 
 /* ------------------------------------------------------------------------------------------
@@ -131,7 +134,8 @@ size_t asme_b200_colsum_workspace_bytes(int M, int N);
  *           (models/common/components/representation_modifier/ffn_modifier.py:18-26)
  * ------------------------------------------------------------------------------------------ */
 int asme_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int H, float* y,
-                            float* stats /* (2,M) mean,rstd or NULL */, asme_stream_t stream);
+                            float* stats /* (2,M) mean,rstd or NULL */, const int32_t* n_live /* device row count or NULL */,
+                            asme_stream_t stream);
 /* LayerNorm whose output feeds a tensor-core GEMM: bf16 copy of y (y_f32 optional) */
 int asme_b200_layernorm_fwd_bf16(const float* x, const float* gamma, const float* beta, int M, int H, float* y_f32 /*NULL ok*/,
                                  void* y_bf16, float* stats, asme_stream_t stream);
@@ -142,7 +146,7 @@ int asme_b200_dropout_cast(const float* x, long long n, float p, uint64_t seed, 
 size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H);
 int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
                             const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
-                            asme_stream_t stream);
+                            const int32_t* n_live /* device row count or NULL */, asme_stream_t stream);
 /* the same, also emitting what the next stage of the backward pass consumes (replaces an asme_b200_dropout_cast launch):
  * dx (fp32) = (LayerNorm gradient + d_residual) * mask(site_a), dx_bf16 (M,H) = bf16(dx * mask(site_b)); site 0 = no mask */
 int asme_b200_layernorm_bwd_drop(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
@@ -169,6 +173,7 @@ typedef struct {
     uint64_t seed;
     uint32_t site;
     const float* residual;         /* (M,N) or NULL */
+    const int32_t* m_live;         /* device count of live rows of A / C (row selections, asme_b200_select_rows) or NULL = all M */
 } asme_gemm_epilogue;
 
 int asme_b200_gemm(const float* A, const float* B, float* C, int M, int N, int K, int trans_b,
@@ -177,13 +182,16 @@ int asme_b200_gemm(const float* A, const float* B, float* C, int M, int N, int K
  * deterministic second-stage reduction. accumulate = 0 overwrites. */
 size_t asme_b200_gemm_wgrad_workspace_bytes(int M, int N, int K);
 int asme_b200_gemm_wgrad(const float* dY, const float* X, int M, int N, int K, float* dW, float* dbias /*NULL ok*/,
-                         int accumulate, void* ws, size_t ws_bytes, asme_stream_t stream);
+                         int accumulate, void* ws, size_t ws_bytes, const int32_t* m_live /* device row count or NULL */,
+                         asme_stream_t stream);
 
 /* elementwise dropout with the same (seed, site, index) masks the fused epilogues use */
 int asme_b200_dropout(const float* x, float* y, long long n, float p, uint64_t seed, uint32_t site,
                       asme_stream_t stream);
 /* dz = dy * gelu'(z) (exact erf GELU, ffn_modifier.py:20) */
-int asme_b200_gelu_bwd(const float* dy, const float* z, float* dz, long long n, asme_stream_t stream);
+/* n_live != NULL: only the first *n_live rows of row_width elements */
+int asme_b200_gelu_bwd(const float* dy, const float* z, float* dz, long long n, int row_width, const int32_t* n_live,
+                       asme_stream_t stream);
 /* y = a (*|+) b : post-fusion merge (kebert4rec/components.py:110-113); op 0 = add, 1 = multiply */
 int asme_b200_binary(const float* a, const float* b, float* y, long long n, int op, asme_stream_t stream);
 
@@ -242,19 +250,24 @@ int asme_b200_dense_ranking(const float* pred, const int64_t* pos_mask, const in
  * (masked_training_module.py:107-111, losses/sasrec/sas_rec_losses.py:16-32).
  * partial: per row (max, sumexp, target logit) over the slice [v0, v0+Vloc) -- shards combine with
  * all-reduce(MAX)/(SUM).  loss_sum += sum_r (max_r + log(sumexp_r) - target_logit_r).
+ * Device row counts: the rows may be a row selection of CAPACITY R whose live count is only known on the device
+ * (asme_b200_select_rows); every entry point below then takes ``n_live`` (NULL = all R rows live), works on the live rows only,
+ * and the mean's 1/n is applied on the device: ce_loss_from_partials writes loss_mean = loss_sum / *n_live, the backward entry
+ * points use scale / *n_live.  One CUDA graph then serves every batch of a shape and the host never waits for the count.
  * ------------------------------------------------------------------------------------------ */
 size_t asme_b200_score_ce_workspace_bytes(int R, int Vloc);
 int asme_b200_score_ce_partial(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
                                const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
-                               void* ws, size_t ws_bytes, asme_stream_t stream);
+                               void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream);
 int asme_b200_ce_loss_from_partials(const float* row_max, const float* row_sumexp, const float* target_logit, int R,
-                                    float* lse /*R*/, float* loss_sum /*1, +=*/, asme_stream_t stream);
+                                    float* lse /*R*/, float* loss_sum /*1, +=*/, const int32_t* n_live,
+                                    float* loss_mean /*1 or NULL: loss_sum / live rows*/, asme_stream_t stream);
 /* backward: dlogit = (softmax - onehot) * scale; dH (R,H) = dlogit W (overwritten; shards all-reduce),
  * dW (Vloc,H) += dlogit^T H, dbias (Vloc) += colsum(dlogit). */
 size_t asme_b200_score_ce_bwd_workspace_bytes(int R, int H, int Vloc);
 int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
                            const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
-                           void* ws, size_t ws_bytes, asme_stream_t stream);
+                           void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 + TMEM + TMA) scoring path, bf16 operands / fp32 accumulation.
@@ -264,7 +277,9 @@ int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const float* W, con
  * zero-padded to a multiple of 16 (<= 272; a multiple of 64 for the CE backward).
  * ------------------------------------------------------------------------------------------ */
 /* y[r, 0..ld_out) = bf16(x[r, 0..cols)) zero padded; ld_out % 4 == 0 */
-int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, asme_stream_t stream);
+/* n_live != NULL: rows past *n_live are written as ZEROS (the result is a tensor-core operand: no stale NaNs) */
+int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, const int32_t* n_live,
+                        asme_stream_t stream);
 /* as above plus two extra columns right after `cols` that fold a per-row bias into the contraction (h.w + b == [h,1,1].[w,b_hi,b_lo]):
  * mode 1 appends (1, 1) (activations), mode 2 appends bf16 hi / lo parts of bias[r] (weights); ld_out >= cols + 2, multiple of 16
  * for the scoring kernels, which then take bias = NULL and Kp = ld_out */
@@ -290,10 +305,12 @@ int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, const void*
 int asme_b200_tc_score_tune(int knob, int value);
 /* cross-entropy partials over the slice: row_max, row_sumexp (natural units, combine across shards as for the fp32
  * entry point) and target_logit (owner shard writes; caller zero-fills) */
-size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc);
+/* n_live / plan_rows: device row count of a row selection and the host's guess of it (0 = R), from which only the split of the
+ * catalog over CTAs is chosen -- a wrong guess costs balance, never correctness; the workspace query takes the same guess */
+size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc, int plan_rows);
 int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
                                   const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
-                                  void* ws, size_t ws_bytes, asme_stream_t stream);
+                                  void* ws, size_t ws_bytes, const int32_t* n_live, int plan_rows, asme_stream_t stream);
 
 /* backward of the fused scoring + cross-entropy layer on the tensor cores: dlogit = (softmax - onehot) * scale is recomputed tile
  * by tile in tensor memory; dH (R,H) fp32 is overwritten, dW (Vloc,H) and dbias (Vloc) are accumulated (+=); any of the three
@@ -301,7 +318,7 @@ int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb,
 size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp, int Vloc);
 int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
                               const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
-                              void* ws, size_t ws_bytes, asme_stream_t stream);
+                              void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core dense layers (tcgen05 + TMEM + TMA), bf16 operands / fp32 accumulation.  Same call sites as asme_b200_gemm.
@@ -375,10 +392,24 @@ int asme_b200_posneg_bce_bwd(const float* Hseq, const float* E, const int64_t* p
                              const float* sums, float dloss, float* dH, float* d_pos_rows, float* d_neg_rows,
                              asme_stream_t stream);
 
-/* rows gather: out[r,:] = x[row_index[r],:]  (K15 row select) and its transpose scatter (rows are distinct) */
-int asme_b200_gather_rows(const float* x, const int64_t* row_index, int R, int H, float* out, asme_stream_t stream);
-int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, int H, float* out /*T,H*/,
+/* rows gather: out[r,:] = x[row_index[r],:]  (K15 row select) and its transpose scatter (rows are distinct); negative indices
+ * and rows past *n_live (device row count or NULL) are skipped */
+int asme_b200_gather_rows(const float* x, const int64_t* row_index, int R, int H, float* out, const int32_t* n_live,
+                          asme_stream_t stream);
+int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, int H, float* out /*T,H*/, const int32_t* n_live,
                            asme_stream_t stream);
+/* Row selection ON THE DEVICE: rows[] = the flat positions t (ascending) with target[t] != ignore_id -- the rows
+ * nn.CrossEntropyLoss(ignore_index=pad) sees (modules/masked_training_module.py:93-111, losses/sasrec/sas_rec_losses.py:16-32) --
+ * row_targets[] = their targets, n_rows[0] = how many.  rows / row_targets have capacity T; slots past n_rows carry -1 / ignore_id.
+ * Replaces torch.nonzero + index_select (a host synchronisation per batch, and a different launch geometry per batch). */
+size_t asme_b200_select_rows_workspace_bytes(long long T);
+int asme_b200_select_rows(const int64_t* target, long long T, int64_t ignore_id, int64_t* rows, int64_t* row_targets,
+                          int32_t* n_rows, void* ws, size_t ws_bytes, asme_stream_t stream);
+/* Gradient clipping by global L2 norm over the flat gradient arena: grad *= min(1, max_norm / (||grad|| + 1e-6))
+ * (pl.Trainer(gradient_clip_val=...) -> torch.nn.utils.clip_grad_norm_); norm_out (1) optional; deterministic reduction */
+size_t asme_b200_clip_grad_norm_workspace_bytes(void);
+int asme_b200_clip_grad_norm(float* grad, long long n, float max_norm, float* norm_out, void* ws, size_t ws_bytes,
+                             asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K22  fused Adam over the flat parameter arena (torch.optim.Adam semantics: L2 decay added to the gradient;

@@ -36,7 +36,7 @@ class GemmEpilogue(Structure):
     """mirror of ``asme_gemm_epilogue``"""
     _fields_ = [
         ("bias", c_void_p), ("pre_act", c_void_p), ("act", c_int), ("mul_gelu_grad_of", c_void_p),
-        ("p_drop", c_float), ("seed", c_uint64), ("site", c_uint32), ("residual", c_void_p),
+        ("p_drop", c_float), ("seed", c_uint64), ("site", c_uint32), ("residual", c_void_p), ("m_live", c_void_p),
     ]
 
 
@@ -56,19 +56,20 @@ _PROTOTYPES = {
     "asme_b200_posgrad_reduce": (c_int, [P, c_int, c_int, c_int, P, P]),
     "asme_b200_posgrad_reduce_strided": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "asme_b200_colsum_accumulate": (c_int, [P, c_int, c_int, P, P, c_size_t, P]),
+    "asme_b200_colsum_accumulate_live": (c_int, [P, c_int, c_int, P, P, c_size_t, P, P]),
     "asme_b200_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "asme_b200_layernorm_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P]),
+    "asme_b200_layernorm_fwd": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "asme_b200_layernorm_fwd_bf16": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "asme_b200_dropout_cast": (c_int, [P, c_longlong, c_float, c_uint64, c_uint32, c_uint32, P, P, P]),
     "asme_b200_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "asme_b200_layernorm_bwd": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "asme_b200_layernorm_bwd": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, P, P]),
     "asme_b200_layernorm_bwd_drop": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, c_float, c_uint64, c_uint32, c_uint32, P, P]),
     "asme_b200_gemm": (c_int, [P, P, P, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), P]),
     "asme_b200_gemm_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "asme_b200_gemm_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
+    "asme_b200_gemm_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P, P]),
     "asme_b200_dropout": (c_int, [P, P, c_longlong, c_float, c_uint64, c_uint32, P]),
     "asme_b200_binary": (c_int, [P, P, P, c_longlong, c_int, P]),
-    "asme_b200_gelu_bwd": (c_int, [P, P, P, c_longlong, P]),
+    "asme_b200_gelu_bwd": (c_int, [P, P, P, c_longlong, c_int, P, P]),
     "asme_b200_attn_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P]),
     "asme_b200_attn_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P, P, P,
                                    c_size_t, P]),
@@ -80,12 +81,12 @@ _PROTOTYPES = {
     "asme_b200_ranking_metrics": (c_int, [P, c_int, P, c_int, P, P]),
     "asme_b200_dense_ranking": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "asme_b200_score_ce_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "asme_b200_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
-    "asme_b200_ce_loss_from_partials": (c_int, [P, P, P, c_int, P, P, P]),
+    "asme_b200_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
+    "asme_b200_ce_loss_from_partials": (c_int, [P, P, P, c_int, P, P, P, P, P]),
     "asme_b200_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "asme_b200_score_ce_bwd": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P]),
+    "asme_b200_score_ce_bwd": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P, P]),
     "asme_b200_cast_bf16_ext": (c_int, [P, P, P, c_longlong, c_int, c_int, c_int, c_int, P]),
-    "asme_b200_cast_bf16": (c_int, [P, P, c_longlong, c_int, c_int, c_int, P]),
+    "asme_b200_cast_bf16": (c_int, [P, P, c_longlong, c_int, c_int, c_int, P, P]),
     "asme_b200_tc_score_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "asme_b200_tc_score_topk": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, P, c_size_t, P]),
     "asme_b200_tc_score_pipeline_probe": (c_int, [P, c_int, c_int, P, c_int, c_int, P]),
@@ -95,10 +96,10 @@ _PROTOTYPES = {
     "asme_b200_cloze_mask": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int64, c_float, c_float, c_uint64, P]),
     "asme_b200_weighted_negatives": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_uint64, P, P, P]),
     "asme_b200_pos_neg_sample": (c_int, [P, c_int, c_int, c_int64, c_int, c_int64, c_uint64, P, P, P, P]),
-    "asme_b200_tc_score_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "asme_b200_tc_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_tc_score_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "asme_b200_tc_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P, c_int, P]),
     "asme_b200_tc_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "asme_b200_tc_score_ce_bwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P]),
+    "asme_b200_tc_score_ce_bwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P, P]),
     "asme_b200_tc_gemm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P, P]),
     "asme_b200_tc_gemm_ln": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P,
                                      P, P, P, P, P]),
@@ -110,8 +111,12 @@ _PROTOTYPES = {
     "asme_b200_tc_attn_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
     "asme_b200_posneg_bce_fwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),
     "asme_b200_posneg_bce_bwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, c_float, P, P, P, P]),
-    "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P]),
-    "asme_b200_scatter_rows": (c_int, [P, P, c_int, c_int, P, P]),
+    "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P, P]),
+    "asme_b200_scatter_rows": (c_int, [P, P, c_int, c_int, P, P, P]),
+    "asme_b200_select_rows_workspace_bytes": (c_size_t, [c_longlong]),
+    "asme_b200_select_rows": (c_int, [P, c_longlong, c_int64, P, P, P, P, c_size_t, P]),
+    "asme_b200_clip_grad_norm_workspace_bytes": (c_size_t, []),
+    "asme_b200_clip_grad_norm": (c_int, [P, c_longlong, c_float, P, P, c_size_t, P]),
     "asme_b200_adam_step": (c_int, [P, P, P, P, c_longlong, c_double, c_double, c_double, c_double, c_double, c_int, P]),
     "asme_b200_step_state_advance": (c_int, [P, P]),
     "asme_b200_adam_step_dev": (c_int, [P, P, P, P, c_longlong, P, c_double, c_double, c_double, c_double, P]),

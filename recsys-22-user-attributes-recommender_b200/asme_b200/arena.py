@@ -37,6 +37,7 @@ class ParamArena:
         self.exp_avg = None
         self.exp_avg_sq = None
         self.version = 0            # bumped by everything that rewrites the weights behind torch's back (fused Adam, repack)
+        self.generation = 0         # bumped when the flat buffer itself is re-created (captured CUDA graphs hold its address)
         self.flat_bf16 = None       # bf16 shadow of ``flat`` for the tensor-core kernels (same layout, same views)
         self._bf16_stamp = None
 
@@ -141,16 +142,21 @@ class ArenaModule(nn.Module):
             yield path, mod._parameters[parts[-1]]
 
     def _repack(self, device=None):
+        """re-create the flat buffer on ``device`` from the current parameter values and re-point every parameter at it.  The
+        gradient buffer and the Adam moments have the same layout and simply move along (a validation pass or a ``.to()`` must
+        not reset the optimizer); captured CUDA graphs hold the old addresses, so ``generation`` tells them to re-capture."""
         params = list(self._named_arena_params())
         device = device if device is not None else params[0][1].device
         new_flat = torch.zeros(self._arena.numel, dtype=torch.float32, device=device)
         old_flat = self._arena.flat
         self._arena.flat = new_flat
         self._arena.bump()
+        self._arena.generation = getattr(self._arena, "generation", 0) + 1
         self._arena.flat_bf16 = None
-        self._arena.grad = None
-        self._arena.exp_avg = None
-        self._arena.exp_avg_sq = None
+        for attr in ("grad", "exp_avg", "exp_avg_sq"):
+            t = getattr(self._arena, attr)
+            if t is not None and t.device != new_flat.device:
+                setattr(self._arena, attr, t.to(new_flat.device))
         with torch.no_grad():
             for path, p in params:
                 v = self._arena.view(self._spec_name(path))
@@ -164,7 +170,9 @@ class ArenaModule(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         params = list(self._named_arena_params())
-        if params:
+        # ``.to()`` / ``.cuda()`` onto the device the arena already lives on leaves every parameter where it is: nothing to do
+        # (re-packing would hand out a new buffer -- and used to drop the Adam moments -- on every validation pass)
+        if params and not (self.arena_is_intact() and all(p.dtype == torch.float32 for _, p in params)):
             self._repack(params[0][1].device)
         return out
 

@@ -373,22 +373,24 @@ class EncoderEngine:
         return dx
 
     # ---------------------------------------------------------------- FFN modifier  LN(GELU(Wx+b))  (K11)
-    def modifier_forward(self, x: torch.Tensor, save: bool):
+    def modifier_forward(self, x: torch.Tensor, save: bool, n_live=None):
+        """``n_live``: device count of live rows when ``x`` is a capacity-sized row selection (models.loss_ce)"""
         w, b = self._w(f"{MODIFIER}.transform.0.weight"), self._w(f"{MODIFIER}.transform.0.bias")
         if save:
-            a, z = ops.gemm(x, w, bias=b, act=ACT_GELU, pre_act_out=True)
+            a, z = ops.gemm(x, w, bias=b, act=ACT_GELU, pre_act_out=True, m_live=n_live)
         else:
-            a, z = ops.gemm(x, w, bias=b, act=ACT_GELU), None
+            a, z = ops.gemm(x, w, bias=b, act=ACT_GELU, m_live=n_live), None
         y, st = ops.layernorm_fwd(a, self._w(f"{MODIFIER}.transform.2.weight"), self._w(f"{MODIFIER}.transform.2.bias"),
-                                  save_stats=save)
+                                  save_stats=save, n_live=n_live)
         return y, (x, z, a, st)
 
-    def modifier_backward(self, dy: torch.Tensor, saved) -> torch.Tensor:
+    def modifier_backward(self, dy: torch.Tensor, saved, n_live=None) -> torch.Tensor:
         x, z, a, st = saved
         H = self.cfg.hidden
         g = self.m._arena.ensure_grad()
         dgb = self.m.weights_span(f"{MODIFIER}.transform.2.weight", f"{MODIFIER}.transform.2.bias", (2, H), g)
-        da = ops.layernorm_bwd(dy, a, self._w(f"{MODIFIER}.transform.2.weight"), st, dgb)
-        dz = ops.gelu_backward(da, z)
-        ops.gemm_wgrad(dz, x, self._w(f"{MODIFIER}.transform.0.weight", True), self._w(f"{MODIFIER}.transform.0.bias", True))
-        return ops.gemm(dz, self._w(f"{MODIFIER}.transform.0.weight"), trans_b=False)
+        da = ops.layernorm_bwd(dy, a, self._w(f"{MODIFIER}.transform.2.weight"), st, dgb, n_live=n_live)
+        dz = ops.gelu_backward(da, z, n_live=n_live)
+        ops.gemm_wgrad(dz, x, self._w(f"{MODIFIER}.transform.0.weight", True), self._w(f"{MODIFIER}.transform.0.bias", True),
+                       m_live=n_live)
+        return ops.gemm(dz, self._w(f"{MODIFIER}.transform.0.weight"), trans_b=False, m_live=n_live)

@@ -1,8 +1,10 @@
 """Whole-step CUDA graphs.  A training step of the C2-C4 shapes is ~90 kernel launches of 5-300 us each; issued one by one
 from Python the host needs ~2.7 ms per step while the kernels need ~2 ms, i.e. the GPU idles.  ``GraphedTrainStep`` captures
-zero_grad -> training_step -> backward -> fused Adam for one batch signature into a CUDA graph and replays it; everything
-that changes from step to step lives in device memory (:class:`StepState`): the dropout seed and the Adam step count are
-bumped by the first node of the graph, the learning rate is written by the host before each replay.
+zero_grad -> training_step -> backward -> fused Adam for one batch SHAPE into a CUDA graph and replays it; everything
+that changes from step to step lives in device memory: the dropout seed and the Adam step count (:class:`StepState`, bumped
+by the first node of the graph), the learning rate (written by the host before each replay) and the number of positions that
+carry a target (``ops.select_rows``: the selected-rows path has capacity-sized buffers and a device-side row count).  One
+graph therefore serves every batch of a ``(B, S)`` -- cloze masking draws a different number of targets for every batch.
 
 The captured step is exactly the eager step (same kernels, same order, same arithmetic); eager mode stays the default and the
 reference API (training_step / loss.backward() / optimizer.step()) is unchanged."""
@@ -58,33 +60,53 @@ class GraphedTrainStep:
         return out["loss"].detach()
 
     def _capture(self, key, batch):
-        static = {k: v.clone() for k, v in batch.items()}
+        dev = self.state.tensor.device
+        static = {k: (v.to(dev, copy=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        arena = self.model._arena
+        arena.ensure_grad()
+        arena.ensure_moments()
+        # the warm-up iterations are REAL steps (they grow workspaces and allocator pools and fetch driver entry points): weights,
+        # moments, step state and host counters are put back afterwards, so that the batch that triggers a capture is trained on
+        # exactly once -- by the first replay
+        snapshot = (arena.flat.clone(), arena.exp_avg.clone(), arena.exp_avg_sq.clone(), self.state.tensor.clone(),
+                    self.optimizer._steps, self.model._step_counter)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(self.warmup_iters):       # grows workspaces / allocator pools, fetches driver entry points
+            for _ in range(self.warmup_iters):
                 self._eager(static)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = self._eager(static)
-        self.graphs[key] = (graph, static, loss)
+        arena.flat.copy_(snapshot[0])
+        arena.exp_avg.copy_(snapshot[1])
+        arena.exp_avg_sq.copy_(snapshot[2])
+        self.state.tensor.copy_(snapshot[3])
+        self.optimizer._steps, self.model._step_counter = snapshot[4], snapshot[5]
+        arena.bump()
+        self.graphs[key] = (graph, static, loss, arena.generation)
         return self.graphs[key]
 
     def __call__(self, batch: Dict[str, torch.Tensor], key=None) -> torch.Tensor:
         """batch tensors are copied into the graph's static inputs (device-to-device or pinned host-to-device); returns the
         loss tensor of the replayed step (static: read it before the next replay of the same graph)"""
+        batch = {k: v for k, v in batch.items() if torch.is_tensor(v)}
         if key is None:
-            key = tuple((k, tuple(v.shape)) for k, v in sorted(batch.items()))
+            key = tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(batch.items()))
         entry = self.graphs.get(key)
+        if entry is not None and entry[3] != self.model._arena.generation:
+            entry = None            # the parameter arena was re-created (a real device move): the graph points at freed memory
         if entry is None:
             entry = self._capture(key, batch)
-        graph, static, loss = entry
+        graph, static, loss, _ = entry
         for k, v in batch.items():
             if static[k].data_ptr() != v.data_ptr():
                 static[k].copy_(v, non_blocking=True)
         self.state.set_lr(self.optimizer.param_groups[0]["lr"])
         graph.replay()
+        self.optimizer._steps += 1
+        self.model._step_counter += 1
         if self.scheduler is not None:
             self.scheduler.step()
         return loss

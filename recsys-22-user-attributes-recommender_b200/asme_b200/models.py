@@ -333,14 +333,14 @@ class TransformerRecommenderModel(ArenaModule):
             self._wb_folded = (stamp, ops.cast_bf16_ext(w, b))
         return self._wb_folded[1], True
 
-    def modify(self, rows: torch.Tensor, save: bool = False):
+    def modify(self, rows: torch.Tensor, save: bool = False, n_live=None):
         if self.modifier_kind == "ffn":
-            return self.engine.modifier_forward(rows, save)
+            return self.engine.modifier_forward(rows, save, n_live)
         return rows, None
 
-    def modify_backward(self, d_rows: torch.Tensor, saved_mod):
+    def modify_backward(self, d_rows: torch.Tensor, saved_mod, n_live=None):
         if self.modifier_kind == "ffn":
-            return self.engine.modifier_backward(d_rows, saved_mod)
+            return self.engine.modifier_backward(d_rows, saved_mod, n_live)
         return d_rows
 
     # ---- reference-compatible forward (inference; materialises the logits the reference returns) --------
@@ -371,53 +371,63 @@ class TransformerRecommenderModel(ArenaModule):
         return all_scores if pos is None else torch.gather(all_scores, 1, pos)
 
     # ---- fused training: scoring + cross entropy --------------------------------------------------------
-    def loss_ce(self, seq, padding_mask, attrs, target, pad_id: int = PAD_TOKEN_ID, rows: Optional[torch.Tensor] = None):
+    def loss_ce(self, seq, padding_mask, attrs, target, pad_id: int = PAD_TOKEN_ID):
         """Cross entropy over the positions with target != pad (== nn.CrossEntropyLoss(ignore_index=pad) over all
-        B*S rows, masked_training_module.py:107-111), without materialising logits.  Returns (loss, ctx)."""
+        B*S rows, masked_training_module.py:107-111), without materialising logits.  Returns (loss, ctx).
+
+        The positions are selected ON THE DEVICE (``ops.select_rows``): every buffer of the selected-rows path has the capacity
+        B*S, the number of live rows stays in device memory and every kernel of the path reads it there.  Launch geometry and
+        buffer sizes therefore depend on (B, S) only -- one CUDA graph serves every batch of a shape -- and the host never
+        waits for the count (``torch.nonzero`` would)."""
         hidden, saved = self.encode(seq, padding_mask, attrs, training=self.training)
-        flat_t = target.reshape(-1)
-        if rows is None:
-            rows = torch.nonzero(flat_t != pad_id).reshape(-1)          # index plumbing (one host sync for the count)
-        row_targets = flat_t.index_select(0, rows)
-        h_rows = ops.gather_rows(hidden, rows)
-        m_rows, saved_mod = self.modify(h_rows, save=self.training)
+        rows, row_targets, n_dev = ops.select_rows(target, pad_id)
+        plan_rows = self._plan_rows(n_dev)
+        h_rows = ops.gather_rows(hidden, rows, n_dev)
+        m_rows, saved_mod = self.modify(h_rows, save=self.training, n_live=n_dev)
         use_tc = self.precision == "bf16"
         if use_tc:      # tcgen05 scoring + CE partials on bf16 operands; the backward recomputes the same tiles
             wb, b = self.projection_operands_bf16()
-            hb = ops.cast_bf16(m_rows, ld_out=wb.shape[1])
-            rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, row_targets)
+            hb = ops.cast_bf16(m_rows, ld_out=wb.shape[1], n_live=n_dev)
+            rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, row_targets, n_live=n_dev, plan_rows=plan_rows)
         else:
             hb = None
             w, b = self.projection_operands()
-            rmax, rsum, tl = ops.score_ce_partial(m_rows, w, b, row_targets)
-        loss_sum = torch.zeros(1, dtype=torch.float32, device=seq.device)
-        lse = ops.ce_loss_from_partials(rmax, rsum, tl, loss_sum)
-        n_rows = int(rows.numel())
-        loss = loss_sum[0] / n_rows if n_rows > 0 else loss_sum[0] * float("nan")
-        ctx = dict(saved=saved, rows=rows, row_targets=row_targets, m_rows=m_rows, hb=hb, saved_mod=saved_mod, lse=lse, n_rows=n_rows,
+            rmax, rsum, tl = ops.score_ce_partial(m_rows, w, b, row_targets, n_live=n_dev)
+        loss_acc = torch.zeros(2, dtype=torch.float32, device=seq.device)          # [sum, mean]
+        lse = ops.ce_loss_from_partials(rmax, rsum, tl, loss_acc[0:1], n_dev, loss_acc[1:2])
+        loss = loss_acc[1]                      # NaN when no position has a target, like the mean over an empty set in torch
+        ctx = dict(saved=saved, rows=rows, row_targets=row_targets, m_rows=m_rows, hb=hb, saved_mod=saved_mod, lse=lse, n_dev=n_dev,
                    T=hidden.shape[0])
         return loss, ctx
 
+    def _plan_rows(self, n_dev: torch.Tensor) -> int:
+        """how many selected rows to PLAN the catalog sweeps for (their split over CTAs; never their result).  Read back once, on
+        the first training step of the model -- the one host synchronisation of this path, outside any graph capture -- and kept:
+        cloze masking and sequence lengths make the count vary by a few percent from batch to batch, not by factors."""
+        hint = getattr(self, "_rows_hint", None)
+        if hint is None and n_dev.is_cuda and not torch.cuda.is_current_stream_capturing():
+            hint = self._rows_hint = max(int(n_dev.item()), 1)
+        return hint or 0
+
     def loss_ce_backward(self, ctx, dloss: float = 1.0):
-        if ctx["n_rows"] == 0:
-            return
         g = self._prepare_grads()
         dw, db = self.projection_operands(grad=True)
+        n_dev = ctx["n_dev"]
         if ctx["hb"] is not None:
             wb, b = self.projection_operands_bf16()
-            args = (ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], self.cfg.hidden)
+            args = (ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss, self.cfg.hidden)      # the kernels divide by the live count
             # the catalog-gradient sweep (dW, dbias) is a leaf: second stream, next to the whole encoder backward
-            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1), keep=args,
+            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1, n_live=n_dev), keep=args,
                                        table_grad=True) is not None:
-                d_m = ops.tc_score_ce_bwd(*args, None, None)
+                d_m = ops.tc_score_ce_bwd(*args, None, None, n_live=n_dev)
             else:
-                d_m = ops.tc_score_ce_bwd(*args, dw, db)
+                d_m = ops.tc_score_ce_bwd(*args, dw, db, n_live=n_dev)
         else:
             w, b = self.projection_operands()
-            d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss / ctx["n_rows"], dw, db)
-        d_h = self.modify_backward(d_m, ctx["saved_mod"])
+            d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss, dw, db, n_live=n_dev)
+        d_h = self.modify_backward(d_m, ctx["saved_mod"], n_live=n_dev)
         d_hidden = torch.zeros(ctx["T"], self.cfg.hidden, dtype=torch.float32, device=d_h.device)
-        ops.scatter_rows(d_h, ctx["rows"], d_hidden)
+        ops.scatter_rows(d_h, ctx["rows"], d_hidden, n_dev)
         self.encode_backward(d_hidden, ctx["saved"])
         self.attach_grads()
 

@@ -247,7 +247,7 @@ class MaskedTrainingModule(_ModuleBase):
         target = batch[TARGET_ENTRY_NAME]
         if target.dim() > 2:
             raise NotImplementedError("basket targets are outside the B200 hot path")
-        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id, rows=batch.get("_target_rows"))
+        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id)
         loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
         self.log(LOG_KEY_TRAINING_LOSS, loss, prog_bar=False)
         return {"loss": loss}
@@ -321,7 +321,7 @@ class NextItemPredictionTrainingModule(_ModuleBase):
             full = torch.zeros_like(seq).reshape(-1)
             full[rows] = target
             target = full.view_as(seq)
-        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id, rows=batch.get("_target_rows"))
+        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id)
         loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
         self.log(LOG_KEY_TRAINING_LOSS, loss)
         return {"loss": loss}
@@ -431,7 +431,7 @@ class UBERTMaskedTrainingModule(MaskedTrainingModule):
             raise NotImplementedError("basket targets are outside the B200 hot path")
         if self.user_key_len > 0:
             target = _prepend_pad_column(target, self.item_tokenizer.pad_token_id)
-        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id, rows=batch.get("_target_rows"))
+        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id)
         loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
         self.log(LOG_KEY_TRAINING_LOSS, loss, prog_bar=False)
         return {"loss": loss}
@@ -490,7 +490,7 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
         if self.user_key_len > 0:
             target = _prepend_pad_column(target, self.item_tokenizer.pad_token_id)
         meta = get_additional_meta_data(self.model, batch)
-        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id, rows=batch.get("_target_rows"))
+        loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id)
         loss = fused_loss(self.model, loss, lambda: self.model.loss_ce_backward(ctx))
         self.log(LOG_KEY_TRAINING_LOSS, loss)
         return {"loss": loss}

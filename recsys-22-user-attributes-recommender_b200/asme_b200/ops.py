@@ -19,6 +19,7 @@ SITE_EMBED_A, SITE_EMBED_B = 1, 2
 SITE_LAYER_BASE = 16          # + 8 * layer + {0: attn probs, 1: attn out, 2: ffn inner, 3: ffn out, 4: block end}
 
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+_retired: List[torch.Tensor] = []      # outgrown scratch buffers: captured CUDA graphs may still hold their addresses
 
 
 def _stream():
@@ -60,8 +61,10 @@ def workspace(nbytes: int, device: torch.device, slot: int = 0) -> torch.Tensor:
     key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
+        if buf is not None:
+            _retired.append(buf)       # never freed: a graph captured earlier replays kernels that point into it.  Sizes at least
+        buf = torch.empty(max(int(nbytes), 1 << 20, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf         # double, so the retired buffers together stay smaller than the live one
     return buf
 
 
@@ -218,14 +221,16 @@ def colsum_accumulate(x: torch.Tensor, out: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
-def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save_stats: bool = False):
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save_stats: bool = False, n_live=None):
+    """``n_live`` (here and below): int32 device scalar = how many leading rows are live when ``x`` is a capacity-sized row
+    selection (:func:`select_rows`); the other rows are left untouched"""
     x = _f32(x)
     M, H = x.shape
     y = torch.empty_like(x)
     stats = torch.empty(2, M, dtype=torch.float32, device=x.device) if save_stats else None
     if _lib.timing is not None:
         _lib.note = f"M={M},H={H}"
-    _lib.call("asme_b200_layernorm_fwd", _p(x), _p(gamma), _p(beta), M, H, _p(y), _p(stats), _stream())
+    _lib.call("asme_b200_layernorm_fwd", _p(x), _p(gamma), _p(beta), M, H, _p(y), _p(stats), _p(n_live), _stream())
     return y, stats
 
 
@@ -253,7 +258,7 @@ def dropout_cast(x: torch.Tensor, p: float, seed: int, site_a: int, site_b: int,
     return y32, y16
 
 
-def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[torch.Tensor] = None):
+def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[torch.Tensor] = None, n_live=None):
     """dx = d_residual + LN'(dy); accumulates (dgamma, dbeta) into dgb (2,H)."""
     dy, x = _f32(dy), _f32(x)
     M, H = x.shape
@@ -263,7 +268,7 @@ def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[t
     if _lib.timing is not None:
         _lib.note = f"M={M},H={H},res={int(d_residual is not None)}"
     _lib.call("asme_b200_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
-              _p(ws), ws.numel(), _stream())
+              _p(ws), ws.numel(), _p(n_live), _stream())
     return dx
 
 
@@ -287,7 +292,7 @@ def layernorm_bwd_drop(dy, x, gamma, stats, dgb: torch.Tensor, d_residual, p: fl
 # dense layers
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, trans_b: bool = True, bias=None, act: int = 0, pre_act_out: bool = False,
-         mul_gelu_grad_of=None, p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out=None):
+         mul_gelu_grad_of=None, p_drop: float = 0.0, seed: int = 0, site: int = 0, residual=None, out=None, m_live=None):
     """C = epilogue(A @ B^T) (trans_b) or epilogue(A @ B).  Returns C or (C, pre_act)."""
     a, b = _f32(a, "A"), _f32(b, "B")
     M, K = a.shape
@@ -302,13 +307,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_b: bool = True, bias=None, act:
     epi.mul_gelu_grad_of = None if mul_gelu_grad_of is None else mul_gelu_grad_of.data_ptr()
     epi.p_drop, epi.seed, epi.site = float(p_drop), int(seed), int(site)
     epi.residual = None if residual is None else residual.data_ptr()
+    epi.m_live = None if m_live is None else m_live.data_ptr()
     if _lib.timing is not None:
         _lib.note = f"M={M},N={N},K={K},tb={int(trans_b)},res={int(residual is not None)},pre={int(pre is not None)},aux={int(mul_gelu_grad_of is not None)}"
     _lib.call("asme_b200_gemm", _p(a), _p(b), _p(c), M, N, K, 1 if trans_b else 0, ctypes.byref(epi), _stream())
     return (c, pre) if pre_act_out else c
 
 
-def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True):
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True,
+               m_live=None):
     """dW (+)= dY^T X, dbias (+)= colsum(dY)."""
     dy, x = _f32(dy), _f32(x)
     M, N = dy.shape
@@ -318,7 +325,7 @@ def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optio
     if _lib.timing is not None:
         _lib.note = f"M={M},N={N},K={K}"
     _lib.call("asme_b200_gemm_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws),
-              ws.numel(), _stream())
+              ws.numel(), _p(m_live), _stream())
 
 
 def dropout(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
@@ -330,12 +337,12 @@ def dropout(x: torch.Tensor, p: float, seed: int, site: int) -> torch.Tensor:
     return y
 
 
-def gelu_backward(dy: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+def gelu_backward(dy: torch.Tensor, z: torch.Tensor, n_live=None) -> torch.Tensor:
     dy, z = _f32(dy), _f32(z)
     dz = torch.empty_like(dy)
     if _lib.timing is not None:
         _lib.note = f"n={dy.numel()}"
-    _lib.call("asme_b200_gelu_bwd", _p(dy), _p(z), _p(dz), dy.numel(), _stream())
+    _lib.call("asme_b200_gelu_bwd", _p(dy), _p(z), _p(dz), dy.numel(), dy.shape[-1], _p(n_live), _stream())
     return dz
 
 
@@ -440,15 +447,15 @@ def padded_k(H: int) -> int:
     return (H + 63) // 64 * 64
 
 
-def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None) -> torch.Tensor:
-    """(rows, cols) fp32 -> (rows, ld_out) bf16, round-to-nearest-even, zero padded"""
+def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None, n_live=None) -> torch.Tensor:
+    """(rows, cols) fp32 -> (rows, ld_out) bf16, round-to-nearest-even, zero padded; rows past ``n_live`` become zeros"""
     x = _f32(x)
     rows, cols = x.shape
     ld_out = padded_k(cols) if ld_out is None else ld_out
     y = torch.empty(rows, ld_out, dtype=torch.bfloat16, device=x.device)
     if _lib.timing is not None:
         _lib.note = f"rows={rows},cols={cols},ld={ld_out}"
-    _lib.call("asme_b200_cast_bf16", _p(x), _p(y), rows, cols, cols, ld_out, _stream())
+    _lib.call("asme_b200_cast_bf16", _p(x), _p(y), rows, cols, cols, ld_out, _p(n_live), _stream())
     return y
 
 
@@ -498,8 +505,9 @@ def tc_score_topk(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, target=None,
     return dict(topk_val=val, topk_idx=idx, target_score=ts_out, n_greater=ng, n_tie_lower=nt)
 
 
-def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: int = 0):
-    """per row (max, sumexp, target logit) over the catalog slice [v0, v0+Vloc), tensor-core path"""
+def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: int = 0, n_live=None, plan_rows: int = 0):
+    """per row (max, sumexp, target logit) over the catalog slice [v0, v0+Vloc), tensor-core path.  ``plan_rows``: the host's guess
+    of ``n_live`` (0 = all rows) -- only the split of the catalog over CTAs is chosen from it"""
     hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
     R, Kp = hb.shape
     Vloc = wb.shape[0]
@@ -507,18 +515,20 @@ def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: in
     rmax = torch.empty(R, dtype=torch.float32, device=dev)
     rsum = torch.empty_like(rmax)
     tl = torch.zeros_like(rmax)
-    ws_bytes = _lib.query("asme_b200_tc_score_ce_workspace_bytes", R, Kp, Vloc)
+    plan_rows = int(plan_rows) if n_live is not None else 0
+    ws_bytes = _lib.query("asme_b200_tc_score_ce_workspace_bytes", R, Kp, Vloc, plan_rows)
     ws = workspace(ws_bytes, dev)
     if _lib.timing is not None:
         _lib.note = f"R={R},V={Vloc},H={Kp}"
     _lib.call("asme_b200_tc_score_ce_partial", _p(hb), R, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
-              _p(tl), _p(ws), ws.numel(), _stream())
+              _p(tl), _p(ws), ws.numel(), _p(n_live), plan_rows, _stream())
     return rmax, rsum, tl
 
 
 def tc_score_ce_bwd(hb, wb, bias, target, lse, scale: float, H: int, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
-                    v0: int = 0, need_dh: bool = True, slot: int = 0) -> Optional[torch.Tensor]:
-    """tensor-core backward of scoring + CE: returns dH (R,H) fp32; accumulates into dW (Vloc,H) / dbias (Vloc)"""
+                    v0: int = 0, need_dh: bool = True, slot: int = 0, n_live=None) -> Optional[torch.Tensor]:
+    """tensor-core backward of scoring + CE: returns dH (R,H) fp32; accumulates into dW (Vloc,H) / dbias (Vloc).  With ``n_live``
+    the kernels use ``scale / n_live`` (the mean over the live rows) and leave the other rows of dH untouched"""
     hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
     R, Kp = hb.shape
     Vloc = wb.shape[0]
@@ -528,7 +538,7 @@ def tc_score_ce_bwd(hb, wb, bias, target, lse, scale: float, H: int, dW: Optiona
     if _lib.timing is not None:
         _lib.note = f"R={R},V={Vloc},H={Kp}"
     _lib.call("asme_b200_tc_score_ce_bwd", _p(hb), R, H, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
-              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _stream())
+              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _p(n_live), _stream())
     return dh
 
 
@@ -665,7 +675,7 @@ def dense_ranking(pred: torch.Tensor, pos_mask: torch.Tensor, metric_mask: Optio
     return out
 
 
-def score_ce_partial(h, w, bias, target, v0: int = 0):
+def score_ce_partial(h, w, bias, target, v0: int = 0, n_live=None):
     """returns (row_max, row_sumexp, target_logit) over the slice [v0, v0+Vloc)"""
     h, w = _f32(h), _f32(w)
     R, H = h.shape
@@ -679,18 +689,20 @@ def score_ce_partial(h, w, bias, target, v0: int = 0):
     if _lib.timing is not None:
         _lib.note = f"R={R},V={Vloc},H={H}"
     _lib.call("asme_b200_score_ce_partial", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
-              _p(tl), _p(ws), ws.numel(), _stream())
+              _p(tl), _p(ws), ws.numel(), _p(n_live), _stream())
     return rmax, rsum, tl
 
 
-def ce_loss_from_partials(rmax, rsum, tl, loss_sum: torch.Tensor):
+def ce_loss_from_partials(rmax, rsum, tl, loss_sum: torch.Tensor, n_live=None, loss_mean: Optional[torch.Tensor] = None):
+    """lse (R); loss_sum += sum of the rows' negative log-likelihoods; ``loss_mean`` (1) = loss_sum / number of (live) rows"""
     lse = torch.empty_like(rmax)
-    _lib.call("asme_b200_ce_loss_from_partials", _p(rmax), _p(rsum), _p(tl), rmax.numel(), _p(lse), _p(loss_sum), _stream())
+    _lib.call("asme_b200_ce_loss_from_partials", _p(rmax), _p(rsum), _p(tl), rmax.numel(), _p(lse), _p(loss_sum), _p(n_live),
+              _p(loss_mean), _stream())
     return lse
 
 
 def score_ce_bwd(h, w, bias, target, lse, scale: float, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
-                 need_dh: bool = True, v0: int = 0):
+                 need_dh: bool = True, v0: int = 0, n_live=None):
     h, w = _f32(h), _f32(w)
     R, H = h.shape
     Vloc = w.shape[0]
@@ -700,7 +712,7 @@ def score_ce_bwd(h, w, bias, target, lse, scale: float, dW: Optional[torch.Tenso
     if _lib.timing is not None:
         _lib.note = f"R={R},V={Vloc},H={H}"
     _lib.call("asme_b200_score_ce_bwd", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
-              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _stream())
+              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _p(n_live), _stream())
     return dh
 
 
@@ -725,17 +737,37 @@ def posneg_bce_bwd(h, table, pos, neg, mask, pl, nl, sums, dloss: float = 1.0):
     return dh, dpos, dneg
 
 
-def gather_rows(x: torch.Tensor, row_index: torch.Tensor) -> torch.Tensor:
+def gather_rows(x: torch.Tensor, row_index: torch.Tensor, n_live=None) -> torch.Tensor:
     x = _f32(x)
     R, H = row_index.numel(), x.shape[1]
     out = torch.empty(R, H, dtype=torch.float32, device=x.device)
-    _lib.call("asme_b200_gather_rows", _p(x), _p(_i64(row_index)), R, H, _p(out), _stream())
+    _lib.call("asme_b200_gather_rows", _p(x), _p(_i64(row_index)), R, H, _p(out), _p(n_live), _stream())
     return out
 
 
-def scatter_rows(rows: torch.Tensor, row_index: torch.Tensor, out: torch.Tensor):
+def scatter_rows(rows: torch.Tensor, row_index: torch.Tensor, out: torch.Tensor, n_live=None):
     rows = _f32(rows)
-    _lib.call("asme_b200_scatter_rows", _p(rows), _p(_i64(row_index)), rows.shape[0], rows.shape[1], _p(out), _stream())
+    _lib.call("asme_b200_scatter_rows", _p(rows), _p(_i64(row_index)), rows.shape[0], rows.shape[1], _p(out), _p(n_live), _stream())
+
+
+def select_rows(target: torch.Tensor, ignore_id: int):
+    """(rows, row_targets, n_rows): the flat positions whose target is not ``ignore_id`` (ascending), their targets, and their
+    number as an int32 DEVICE scalar.  rows / row_targets have the capacity ``target.numel()``; slots past ``n_rows`` carry
+    -1 / ``ignore_id``.  No host synchronisation (``torch.nonzero`` needs one to size its result)."""
+    target = _i64(target).reshape(-1)
+    T = target.numel()
+    rows = torch.empty(T, dtype=torch.int64, device=target.device)
+    row_targets = torch.empty(T, dtype=torch.int64, device=target.device)
+    n_rows = torch.empty(1, dtype=torch.int32, device=target.device)
+    ws = workspace(_lib.query("asme_b200_select_rows_workspace_bytes", T), target.device)
+    _lib.call("asme_b200_select_rows", _p(target), T, int(ignore_id), _p(rows), _p(row_targets), _p(n_rows), _p(ws), ws.numel(), _stream())
+    return rows, row_targets, n_rows
+
+
+def clip_grad_norm(grad: torch.Tensor, max_norm: float, norm_out: Optional[torch.Tensor] = None):
+    """grad *= min(1, max_norm / (||grad||_2 + 1e-6)) over the flat gradient arena (torch.nn.utils.clip_grad_norm_)"""
+    ws = workspace(max(_lib.query("asme_b200_clip_grad_norm_workspace_bytes"), 256), grad.device, slot=2)
+    _lib.call("asme_b200_clip_grad_norm", _p(grad), grad.numel(), float(max_norm), _p(norm_out), _p(ws), ws.numel(), _stream())
 
 
 def adam_step(param, grad, m, v, lr, beta1, beta2, eps, weight_decay, step):

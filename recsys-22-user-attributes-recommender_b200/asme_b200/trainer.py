@@ -21,6 +21,7 @@ class Trainer:
         self.max_epochs, self.max_steps = max_epochs, max_steps
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.log_every_n_steps = log_every_n_steps
+        self.gradient_clip_val = float(gradient_clip_val) if gradient_clip_val else None     # pl.Trainer: clip by global L2 norm
         self.process_group = process_group
         self.global_step = 0
         self.history: List[Dict[str, float]] = []
@@ -38,8 +39,22 @@ class Trainer:
         g.div_(world)
 
     # ---- loops ----------------------------------------------------------------------------------------------------
+    def _broadcast_parameters(self, module):
+        """data parallel: every replica starts from rank 0's weights (what DDP does at construction), whatever the seeding"""
+        if self._world() > 1:
+            arena = module.model._arena
+            dist.broadcast(arena.flat, src=dist.get_global_rank(self.process_group, 0) if self.process_group is not None else 0,
+                           group=self.process_group)
+            arena.bump()
+
+    def _clip(self, module):
+        if self.gradient_clip_val is not None:
+            from . import ops
+            ops.clip_grad_norm(module.model._arena.ensure_grad(), self.gradient_clip_val)
+
     def fit(self, module, train_dataloaders: Iterable, val_dataloaders: Optional[Iterable] = None):
         module.to(self.device)
+        self._broadcast_parameters(module)
         opt = module.configure_optimizers()
         schedulers = []
         if isinstance(opt, tuple):
@@ -59,6 +74,7 @@ class Trainer:
                 loss = out["loss"] if isinstance(out, dict) else out
                 loss.backward()
                 self._allreduce_grads(module)
+                self._clip(module)
                 optimizer.step()
                 for s in schedulers:
                     s.step()
@@ -75,7 +91,8 @@ class Trainer:
 
     @torch.no_grad()
     def _eval_loop(self, module, loader, step, step_end, epoch_end) -> Dict[str, float]:
-        module.to(self.device)
+        if next(module.parameters()).device != self.device:
+            module.to(self.device)
         module.eval()
         for batch_idx, batch in enumerate(loader):
             batch = _to_device(batch, self.device)

@@ -47,6 +47,16 @@ __host__ __device__ static inline int ceil_div(long long a, long long b) { retur
 // ---------------------------------------------------------------------------------------------
 #define ASME_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+// Device-side row counts.  Buffers of a row selection (asme_b200_select_rows) are allocated for the CAPACITY (every position
+// could be selected); how many rows are live is only known on the device.  Kernels on that path take the capacity as their row
+// count plus ``n_live`` (device pointer, may be NULL = all rows live) and touch the live rows only: one CUDA graph serves
+// every batch of a shape, whatever its number of selected rows, and the host never waits for the count.
+__device__ __forceinline__ int asme_live_rows(int capacity, const int32_t* __restrict__ n_live) {
+    if (n_live == nullptr) return capacity;
+    const int n = __ldg(n_live);
+    return n < capacity ? n : capacity;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -48,12 +48,14 @@ __device__ __forceinline__ float apply_epilogue(float v, long long m, int n, int
 template <bool TRANS_B>
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                    float* __restrict__ C, int M, int N, int K, EpilogueArgs epi,
-                                                   bool a_vec, bool b_vec) {
+                                                   bool a_vec, bool b_vec, const int32_t* __restrict__ m_live) {
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    M = asme_live_rows(M, m_live);
+    if (m0 >= M) return;
 
     // loader coordinates
     const int a_row = tid / 4, a_k = (tid % 4) * 4;          // A tile: 64 rows x 16 k
@@ -129,8 +131,8 @@ extern "C" int asme_b200_gemm(const float* A, const float* B, float* C, int M, i
     const bool a_vec = (K % 4 == 0) && aligned16(A);
     const bool b_vec = trans_b ? ((K % 4 == 0) && aligned16(B)) : ((N % 4 == 0) && aligned16(B));
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-    if (trans_b) gemm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, e, a_vec, b_vec);
-    else gemm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, e, a_vec, b_vec);
+    if (trans_b) gemm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, e, a_vec, b_vec, epi ? epi->m_live : nullptr);
+    else gemm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, e, a_vec, b_vec, epi ? epi->m_live : nullptr);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -141,12 +143,13 @@ extern "C" int asme_b200_gemm(const float* A, const float* B, float* C, int M, i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, int M, int N,
                                                     int K, int rows_per_split, float* __restrict__ partial, bool y_vec,
-                                                    bool x_vec) {
+                                                    bool x_vec, const int32_t* __restrict__ m_live) {
     __shared__ __align__(16) float Ys[BK][BM + PAD];
     __shared__ __align__(16) float Xs[BK][BN + PAD];
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int n0 = blockIdx.x * BM, k0 = blockIdx.y * BN;
+    M = asme_live_rows(M, m_live);
     const int m_begin = blockIdx.z * rows_per_split;
     const int m_end = min(M, m_begin + rows_per_split);
     const int l_row = tid / 16, l_col = (tid % 16) * 4;
@@ -222,8 +225,10 @@ extern "C" size_t asme_b200_gemm_wgrad_workspace_bytes(int M, int N, int K) {
     return a > b ? a : b;
 }
 
+extern "C" int asme_b200_colsum_accumulate_live(const float* x, int M, int N, float* out, void* ws, size_t ws_bytes,
+                                                const int32_t* m_live, asme_stream_t stream);
 extern "C" int asme_b200_gemm_wgrad(const float* dY, const float* X, int M, int N, int K, float* dW, float* dbias,
-                                    int accumulate, void* ws, size_t ws_bytes, asme_stream_t stream) {
+                                    int accumulate, void* ws, size_t ws_bytes, const int32_t* m_live, asme_stream_t stream) {
     ASME_REQUIRE(dY && X && dW, "gemm_wgrad: null argument");
     ASME_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_wgrad: bad shape M=%d N=%d K=%d", M, N, K);
     cudaStream_t st = (cudaStream_t)stream;
@@ -244,14 +249,14 @@ extern "C" int asme_b200_gemm_wgrad(const float* dY, const float* X, int M, int 
     const bool y_vec = (N % 4 == 0) && aligned16(dY);
     const bool x_vec = (K % 4 == 0) && aligned16(X);
     dim3 grid(ceil_div(N, BM), ceil_div(K, BN), splits);
-    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, M, N, K, rows_per_split, (float*)ws, y_vec, x_vec);
+    wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, M, N, K, rows_per_split, (float*)ws, y_vec, x_vec, m_live);
     ASME_LAUNCH_OK();
     const long long n = (long long)N * K;
     split_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)ws, splits, n, dW, accumulate);
     ASME_LAUNCH_OK();
     if (dbias) {
         if (!accumulate) ASME_CUDA_OK(cudaMemsetAsync(dbias, 0, (size_t)N * sizeof(float), st));
-        return asme_b200_colsum_accumulate(dY, M, N, dbias, ws, ws_bytes, stream);
+        return asme_b200_colsum_accumulate_live(dY, M, N, dbias, ws, ws_bytes, m_live, stream);
     }
     return ASME_OK;
 }

@@ -26,7 +26,7 @@ extern "C" const char* asme_b200_last_error(void) { return g_last_error; }
 static std::atomic<long long> g_launches{0};
 void asme_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long asme_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-extern "C" int asme_b200_abi_version(void) { return 1; }
+extern "C" int asme_b200_abi_version(void) { return 2; }
 
 #include <mutex>
 int asme_ensure_max_smem(const void* kernel) {
@@ -343,10 +343,10 @@ template <int LANES, int CH>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int M, int H,
                                                             float* __restrict__ y, float* __restrict__ stats,
-                                                            __nv_bfloat16* __restrict__ y16) {
+                                                            __nv_bfloat16* __restrict__ y16, const int32_t* __restrict__ n_live) {
     const int lane = threadIdx.x % LANES;
     const long long r = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
-    if (r >= M) return;
+    if (r >= asme_live_rows(M, n_live)) return;
     Row<LANES, CH> xr, yr;
     xr.load(x + r * H, lane);
     float mean, rstd;
@@ -362,9 +362,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             int M, int H, const float* __restrict__ d_residual,
                                                             float* __restrict__ dx, float* __restrict__ partials,
                                                             float p_drop, uint64_t seed, uint32_t site_a, uint32_t site_b,
-                                                            __nv_bfloat16* __restrict__ dx16) {
+                                                            __nv_bfloat16* __restrict__ dx16, const int32_t* __restrict__ n_live) {
     extern __shared__ float smem[];
     const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    const int M_stats = M;                       // the statistics were saved with the capacity as their row stride
+    M = asme_live_rows(M, n_live);
     const int lane = threadIdx.x % LANES;
     const int groups_per_block = blockDim.x / LANES;
     const int group_in_block = threadIdx.x / LANES;
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
          r += (long long)gridDim.x * groups_per_block) {
         Row<LANES, CH> xhat, g;
         xhat.load(x + r * H, lane);
-        const float mean = stats[r], rstd = stats[(size_t)M + r];
+        const float mean = stats[r], rstd = stats[(size_t)M_stats + r];
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             xhat.v[c].x = (xhat.v[c].x - mean) * rstd; xhat.v[c].y = (xhat.v[c].y - mean) * rstd;
@@ -401,9 +403,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // column sums: out[n] (+)= sum_m x[m,n]. stage 1: one block per chunk of rows; stage 2: over chunks.
 // ---------------------------------------------------------------------------------------------
 #define COLSUM_ROWS 128
-__global__ void colsum_stage1_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ partial) {
+__global__ void colsum_stage1_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ partial,
+                                     const int32_t* __restrict__ m_live) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    M = asme_live_rows(M, m_live);               // chunks past the live rows write zeros
     const int m0 = blockIdx.y * COLSUM_ROWS;
     const int m1 = min(M, m0 + COLSUM_ROWS);
     float s = 0.f;
@@ -440,8 +444,8 @@ __global__ void __launch_bounds__(1024) colsum_stage2_kernel(const float* __rest
 }
 
 static int launch_colsum(const float* x, int M, int N, float* out, int accumulate, void* ws, size_t ws_bytes,
-                         cudaStream_t stream) {
-    if (M <= COLSUM_ROWS) {   // small: single stage
+                         cudaStream_t stream, const int32_t* m_live = nullptr) {
+    if (M <= COLSUM_ROWS && m_live == nullptr) {   // small: single stage
         colsum_stage2_kernel<<<ceil_div(N, 32), 1024, 0, stream>>>(x, M, N, out, accumulate);
         ASME_LAUNCH_OK();
         return ASME_OK;
@@ -452,7 +456,7 @@ static int launch_colsum(const float* x, int M, int N, float* out, int accumulat
         return ASME_ERR_WORKSPACE;
     }
     float* partial = (float*)ws;
-    colsum_stage1_kernel<<<dim3(ceil_div(N, 128), chunks), 128, 0, stream>>>(x, M, N, partial);
+    colsum_stage1_kernel<<<dim3(ceil_div(N, 128), chunks), 128, 0, stream>>>(x, M, N, partial, m_live);
     ASME_LAUNCH_OK();
     colsum_stage2_kernel<<<ceil_div(N, 32), 1024, 0, stream>>>(partial, chunks, N, out, accumulate);
     ASME_LAUNCH_OK();
@@ -467,6 +471,13 @@ extern "C" int asme_b200_colsum_accumulate(const float* x, int M, int N, float* 
     ASME_REQUIRE(M >= 0 && N > 0, "colsum: bad shape M=%d N=%d", M, N);
     if (M == 0) return ASME_OK;
     return launch_colsum(x, M, N, out, 1, ws, ws_bytes, (cudaStream_t)stream);
+}
+// the same over the live rows of a capacity-sized buffer (device count, may be NULL)
+extern "C" int asme_b200_colsum_accumulate_live(const float* x, int M, int N, float* out, void* ws, size_t ws_bytes,
+                                                const int32_t* m_live, asme_stream_t stream) {
+    ASME_REQUIRE(M >= 0 && N > 0, "colsum: bad shape M=%d N=%d", M, N);
+    if (M == 0) return ASME_OK;
+    return launch_colsum(x, M, N, out, 1, ws, ws_bytes, (cudaStream_t)stream, m_live);
 }
 
 // d_pos[s,:] += sum_b d_rows[b*S+s,:]
@@ -600,12 +611,12 @@ extern "C" int asme_b200_embed_bwd(const asme_embed_desc* d, int T, int S, int H
 }
 
 extern "C" int asme_b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int H, float* y,
-                                       float* stats, asme_stream_t stream) {
+                                       float* stats, const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null argument");
     if (M == 0) return ASME_OK;
     const int lanes = lanes_for(H);
     const int groups = 256 / lanes;
-#define CALL(L, C) layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y, stats, nullptr)
+#define CALL(L, C) layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y, stats, nullptr, n_live)
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
@@ -621,7 +632,7 @@ extern "C" int asme_b200_layernorm_fwd_bf16(const float* x, const float* gamma, 
     const int groups = 256 / lanes;
 #define CALL(L, C)                                                                                                     \
     layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y_f32, stats, \
-                                                                                      (__nv_bfloat16*)y_bf16)
+                                                                                      (__nv_bfloat16*)y_bf16, nullptr)
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
@@ -635,11 +646,11 @@ extern "C" size_t asme_b200_layernorm_bwd_workspace_bytes(int M, int H) {
 
 static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
                               const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop, uint64_t seed,
-                              uint32_t site_a, uint32_t site_b, void* dx_bf16, asme_stream_t stream);
+                              uint32_t site_a, uint32_t site_b, void* dx_bf16, const int32_t* n_live, asme_stream_t stream);
 extern "C" int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int M,
                                        int H, const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes,
-                                       asme_stream_t stream) {
-    return layernorm_bwd_impl(dy, x, gamma, stats, M, H, d_residual, dx, dgb, ws, ws_bytes, 0.f, 0ull, 0u, 0u, nullptr, stream);
+                                       const int32_t* n_live, asme_stream_t stream) {
+    return layernorm_bwd_impl(dy, x, gamma, stats, M, H, d_residual, dx, dgb, ws, ws_bytes, 0.f, 0ull, 0u, 0u, nullptr, n_live, stream);
 }
 // LayerNorm backward that also emits what the next backward stage consumes (replaces a dropout_cast launch):
 // dx (fp32) = (LN gradient + d_residual) * mask(site_a),  dx_bf16 = bf16(dx * mask(site_b));  site 0 = no mask
@@ -649,11 +660,11 @@ extern "C" int asme_b200_layernorm_bwd_drop(const float* dy, const float* x, con
                                             asme_stream_t stream) {
     ASME_REQUIRE(dx_bf16, "layernorm_bwd_drop: null bf16 output");
     ASME_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "layernorm_bwd_drop: p=%f out of range", p_drop);
-    return layernorm_bwd_impl(dy, x, gamma, stats, M, H, d_residual, dx, dgb, ws, ws_bytes, p_drop, seed, site_a, site_b, dx_bf16, stream);
+    return layernorm_bwd_impl(dy, x, gamma, stats, M, H, d_residual, dx, dgb, ws, ws_bytes, p_drop, seed, site_a, site_b, dx_bf16, nullptr, stream);
 }
 static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
                               const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop, uint64_t seed,
-                              uint32_t site_a, uint32_t site_b, void* dx_bf16, asme_stream_t stream) {
+                              uint32_t site_a, uint32_t site_b, void* dx_bf16, const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(dy && x && gamma && stats && dx && dgb, "layernorm_bwd: null argument");
     if (M == 0) return ASME_OK;
     const int lanes = lanes_for(H);
@@ -668,7 +679,7 @@ static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamm
 #define CALL(L, C)                                                                                                 \
     layernorm_bwd_kernel<L, C><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, x, gamma, stats, M, H, d_residual, dx, \
                                                                           partials, p_drop, seed, site_a, site_b,   \
-                                                                          (__nv_bfloat16*)dx_bf16)
+                                                                          (__nv_bfloat16*)dx_bf16, n_live)
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
@@ -748,14 +759,179 @@ extern "C" int asme_b200_binary(const float* a, const float* b, float* y, long l
     return ASME_OK;
 }
 
-__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, float* __restrict__ dz, long long n) {
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, float* __restrict__ dz, long long n,
+                                int row_width, const int32_t* __restrict__ n_live) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_live != nullptr) n = min(n, (long long)__ldg(n_live) * row_width);
     if (i < n) dz[i] = dy[i] * gelu_erf_grad(z[i]);
 }
-extern "C" int asme_b200_gelu_bwd(const float* dy, const float* z, float* dz, long long n, asme_stream_t stream) {
+extern "C" int asme_b200_gelu_bwd(const float* dy, const float* z, float* dz, long long n, int row_width, const int32_t* n_live,
+                                  asme_stream_t stream) {
     ASME_REQUIRE(dy && z && dz, "gelu_bwd: null argument");
+    ASME_REQUIRE(!n_live || row_width > 0, "gelu_bwd: a live-row count needs the row width");
     if (n == 0) return ASME_OK;
-    gelu_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, z, dz, n);
+    gelu_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, z, dz, n, row_width, n_live);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row selection on the device: rows[] = ascending flat indices t with target[t] != ignore_id (the positions the cross entropy
+// sees, nn.CrossEntropyLoss(ignore_index=pad): modules/masked_training_module.py:93-111), row_targets[] = their targets,
+// n_rows[0] = how many.  Slots past n_rows carry -1 / ignore_id.  Two launches: per-block counts, then every block sums the
+// counts of the blocks before it (a few hundred integers) and writes its own matches in order -- deterministic, no atomics,
+// no host round trip (torch.nonzero synchronises to size its result).
+// ---------------------------------------------------------------------------------------------
+#define SEL_THREADS 256
+#define SEL_PER_THREAD 8
+#define SEL_BLOCK (SEL_THREADS * SEL_PER_THREAD)
+__global__ void __launch_bounds__(SEL_THREADS) select_count_kernel(const int64_t* __restrict__ target, long long T, int64_t ignore_id,
+                                                                   int32_t* __restrict__ block_counts) {
+    __shared__ int warp_counts[SEL_THREADS / 32];
+    const long long base = (long long)blockIdx.x * SEL_BLOCK + (long long)threadIdx.x * SEL_PER_THREAD;
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < SEL_PER_THREAD; ++e)
+        if (base + e < T && target[base + e] != ignore_id) ++c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (threadIdx.x % 32 == 0) warp_counts[threadIdx.x / 32] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) s += warp_counts[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(SEL_THREADS) select_write_kernel(const int64_t* __restrict__ target, long long T, int64_t ignore_id,
+                                                                   const int32_t* __restrict__ block_counts, int64_t* __restrict__ rows,
+                                                                   int64_t* __restrict__ row_targets, int32_t* __restrict__ n_rows) {
+    __shared__ int warp_sums[SEL_THREADS / 32];
+    __shared__ int block_offset, total;
+    // offset of this block = matches of all blocks before it; block 0 also publishes the total
+    int before = 0, all = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += SEL_THREADS) {
+        const int c = block_counts[b];
+        all += c;
+        if (b < (int)blockIdx.x) before += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+    if (threadIdx.x % 32 == 0) { warp_sums[threadIdx.x / 32] = before; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) s += warp_sums[w];
+        block_offset = s;
+    }
+    __syncthreads();
+    if (threadIdx.x % 32 == 0) warp_sums[threadIdx.x / 32] = all;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) s += warp_sums[w];
+        total = s;
+        if (blockIdx.x == 0) n_rows[0] = s;
+    }
+    __syncthreads();
+    // matches of this thread's SEL_PER_THREAD consecutive positions, exclusive scan over the block
+    const long long base = (long long)blockIdx.x * SEL_BLOCK + (long long)threadIdx.x * SEL_PER_THREAD;
+    int64_t tg[SEL_PER_THREAD];
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < SEL_PER_THREAD; ++e) {
+        tg[e] = base + e < T ? target[base + e] : ignore_id;
+        if (tg[e] != ignore_id) ++c;
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)(threadIdx.x % 32) >= o) incl += v;
+    }
+    __syncthreads();
+    if (threadIdx.x % 32 == 31) warp_sums[threadIdx.x / 32] = incl;
+    __syncthreads();
+    int warp_before = 0;
+    for (int w = 0; w < (int)(threadIdx.x / 32); ++w) warp_before += warp_sums[w];
+    int slot = block_offset + warp_before + incl - c;
+#pragma unroll
+    for (int e = 0; e < SEL_PER_THREAD; ++e)
+        if (tg[e] != ignore_id) { rows[slot] = base + e; row_targets[slot] = tg[e]; ++slot; }
+    // the unused tail of the capacity: -1 / ignore_id (every block clears its share)
+    for (long long i = (long long)total + (long long)blockIdx.x * SEL_THREADS + threadIdx.x; i < T; i += (long long)gridDim.x * SEL_THREADS) {
+        rows[i] = -1;
+        row_targets[i] = ignore_id;
+    }
+}
+extern "C" size_t asme_b200_select_rows_workspace_bytes(long long T) { return (size_t)ceil_div(T < 1 ? 1 : T, SEL_BLOCK) * sizeof(int32_t); }
+extern "C" int asme_b200_select_rows(const int64_t* target, long long T, int64_t ignore_id, int64_t* rows, int64_t* row_targets,
+                                     int32_t* n_rows, void* ws, size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(target && rows && row_targets && n_rows, "select_rows: null argument");
+    ASME_REQUIRE(T >= 0 && T < (1ll << 31), "select_rows: T=%lld out of range", T);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 0) {
+        ASME_CUDA_OK(cudaMemsetAsync(n_rows, 0, sizeof(int32_t), st));
+        return ASME_OK;
+    }
+    const int blocks = ceil_div(T, SEL_BLOCK);
+    if (ws_bytes < (size_t)blocks * sizeof(int32_t)) {
+        asme_set_error("select_rows: workspace too small");
+        return ASME_ERR_WORKSPACE;
+    }
+    select_count_kernel<<<blocks, SEL_THREADS, 0, st>>>(target, T, ignore_id, (int32_t*)ws);
+    ASME_LAUNCH_OK();
+    select_write_kernel<<<blocks, SEL_THREADS, 0, st>>>(target, T, ignore_id, (const int32_t*)ws, rows, row_targets, n_rows);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient clipping by global L2 norm over the flat gradient arena (pl.Trainer(gradient_clip_val=c) = torch clip_grad_norm_:
+// g *= min(1, c / (||g|| + 1e-6))).  Fixed-order two-stage sum of squares (double), then one scaling pass.
+// ---------------------------------------------------------------------------------------------
+#define CLIP_BLOCKS (ASME_NUM_SMS * 2)
+__global__ void __launch_bounds__(256) sumsq_stage1_kernel(const float* __restrict__ g, long long n, double* __restrict__ partial) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const double v = (double)g[i];
+        acc += v * v;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) clip_scale_kernel(float* __restrict__ g, long long n, const double* __restrict__ partial, int parts,
+                                                         float max_norm, float* __restrict__ norm_out) {
+    __shared__ float coef_s;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int p = 0; p < parts; ++p) s += partial[p];
+        const float norm = (float)sqrt(s);
+        const float coef = max_norm / (norm + 1e-6f);
+        coef_s = coef < 1.0f ? coef : 1.0f;
+        if (norm_out && blockIdx.x == 0) norm_out[0] = norm;
+    }
+    __syncthreads();
+    const float coef = coef_s;
+    if (coef >= 1.0f) return;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) g[i] *= coef;
+}
+extern "C" size_t asme_b200_clip_grad_norm_workspace_bytes(void) { return (size_t)CLIP_BLOCKS * sizeof(double); }
+extern "C" int asme_b200_clip_grad_norm(float* grad, long long n, float max_norm, float* norm_out, void* ws, size_t ws_bytes,
+                                        asme_stream_t stream) {
+    ASME_REQUIRE(grad && max_norm > 0.f, "clip_grad_norm: null gradient or max_norm <= 0");
+    ASME_REQUIRE(ws && ws_bytes >= asme_b200_clip_grad_norm_workspace_bytes() && ((uintptr_t)ws & 7) == 0, "clip_grad_norm: workspace too small or misaligned");
+    if (n == 0) return ASME_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    sumsq_stage1_kernel<<<CLIP_BLOCKS, 256, 0, st>>>(grad, n, (double*)ws);
+    ASME_LAUNCH_OK();
+    clip_scale_kernel<<<CLIP_BLOCKS, 256, 0, st>>>(grad, n, (const double*)ws, CLIP_BLOCKS, max_norm, norm_out);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -820,27 +996,28 @@ extern "C" int asme_b200_fill(float* x, long long n, float value, asme_stream_t 
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, int R, int H4,
-                                   float* __restrict__ out, int scatter) {
+                                   float* __restrict__ out, int scatter, const int32_t* __restrict__ n_live) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)R * H4) return;
+    if (i >= (long long)asme_live_rows(R, n_live) * H4) return;
     const long long r = i / H4, c = i % H4;
     const long long src = idx[r];
+    if (src < 0) return;                          // slots past the live rows of a row selection carry -1
     if (!scatter) reinterpret_cast<float4*>(out)[r * H4 + c] = __ldg(reinterpret_cast<const float4*>(x) + src * H4 + c);
     else reinterpret_cast<float4*>(out)[src * H4 + c] = __ldg(reinterpret_cast<const float4*>(x) + r * H4 + c);
 }
 extern "C" int asme_b200_gather_rows(const float* x, const int64_t* row_index, int R, int H, float* out,
-                                     asme_stream_t stream) {
+                                     const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(H % 4 == 0, "gather_rows: H=%d must be a multiple of 4", H);
     if (R == 0) return ASME_OK;
-    gather_rows_kernel<<<ceil_div((long long)R * H / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, row_index, R, H / 4, out, 0);
+    gather_rows_kernel<<<ceil_div((long long)R * H / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, row_index, R, H / 4, out, 0, n_live);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
 extern "C" int asme_b200_scatter_rows(const float* rows, const int64_t* row_index, int R, int H, float* out,
-                                      asme_stream_t stream) {
+                                      const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(H % 4 == 0, "scatter_rows: H=%d must be a multiple of 4", H);
     if (R == 0) return ASME_OK;
-    gather_rows_kernel<<<ceil_div((long long)R * H / 4, 256), 256, 0, (cudaStream_t)stream>>>(rows, row_index, R, H / 4, out, 1);
+    gather_rows_kernel<<<ceil_div((long long)R * H / 4, 256), 256, 0, (cudaStream_t)stream>>>(rows, row_index, R, H / 4, out, 1, n_live);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

@@ -57,6 +57,7 @@ struct CeBwdArgs {
     float scale;
     float* partial;             // MODE_DH: [splits][R][H]   MODE_DW: [splits][Vloc][H]
     float* partial_bias;        // MODE_DW: [splits][Vloc] or NULL
+    const int32_t* n_live;      // device count of live hidden rows (row selections of capacity R) or NULL; then scale /= n_live
 };
 struct __align__(16) CeShared {
     float col_lse[CE_TILE];     // MODE_DW: lse of the 128 hidden rows of the current column tile (log2 units)
@@ -79,10 +80,23 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int row0 = blockIdx.x * CE_TILE;
     const int split = blockIdx.y;
-    const int ct0 = split * a.col_tiles_per_split;
-    const int ct1 = min(a.n_col_tiles, ct0 + a.col_tiles_per_split);
-    const int n_rows_total = MODE == MODE_DH ? a.R : a.Vloc;     // extent of the row dimension
-    const int n_cols_total = MODE == MODE_DH ? a.Vloc : a.R;     // extent of the streamed dimension
+    // hidden rows that are live: the capacity a.R, or the device count of a row selection (the mean's 1/n then comes from it too)
+    int R_live = a.R;
+    float scale = a.scale;
+    if (a.n_live != nullptr) {
+        R_live = asme_live_rows(a.R, a.n_live);
+        scale = scale / (float)R_live;
+        if (MODE == MODE_DH && row0 >= R_live) return;          // whole CTA, before any barrier / TMEM allocation
+    }
+    // MODE_DH streams a contiguous range of item tiles.  MODE_DW streams the hidden-row tiles ROUND ROBIN over the splits: the
+    // live rows of a capacity-sized selection are then spread over all of them, whatever their number
+    const int n_stream_tiles = MODE == MODE_DH ? a.n_col_tiles : ceil_div(R_live, CE_TILE);
+    const int ct0 = MODE == MODE_DH ? split * a.col_tiles_per_split : split;
+    const int ct_step = MODE == MODE_DH ? 1 : (int)gridDim.y;
+    const int n_mine = MODE == MODE_DH ? max(0, min(n_stream_tiles, ct0 + a.col_tiles_per_split) - ct0)
+                                       : (split < n_stream_tiles ? (n_stream_tiles - split + ct_step - 1) / ct_step : 0);
+    const int n_rows_total = MODE == MODE_DH ? R_live : a.Vloc;  // extent of the row dimension
+    const int n_rows_layout = MODE == MODE_DH ? a.R : a.Vloc;    // row stride of the partial buffers (capacity)
     uint32_t tmem_cols = 256;
     while ((int)tmem_cols < CE_TILE + a.Kp) tmem_cols <<= 1;
 
@@ -109,8 +123,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
         if (lane == 0) {
             mbar_arrive_expect_tx(&sh->row_full, (uint32_t)kch * CE_CHUNK_BYTES);
             for (int c = 0; c < kch; ++c) tma_load_2d(sRow + (size_t)c * CE_CHUNK_BYTES, &tmRow, &sh->row_full, c * CHUNK_K, row0);
-            int i = 0;
-            for (int ct = ct0; ct < ct1; ++ct, ++i) {
+            for (int i = 0; i < n_mine; ++i) {
+                const int ct = ct0 + i * ct_step;
                 const int s = i % stages;
                 const uint32_t ph = (uint32_t)(i / stages) & 1u;
                 mbar_wait_lean(&sh->empty[s], ph ^ 1u);
@@ -139,7 +153,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
                 }
                 umma_commit(&sh->t_full);
             };
-            const int n = ct1 - ct0;
+            const int n = n_mine;
             if (n > 0) issue_t(0);
             for (int i = 0; i < n; ++i) {
                 const int s = i % stages;
@@ -177,11 +191,11 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
         } else {
             if (row_ok && a.bias) row_bias = a.bias[row];
         }
-        const float sc2 = a.scale;
+        const float sc2 = scale;
         float bias_sum = 0.f;
-        const int n = ct1 - ct0;
+        const int n = n_mine;
         for (int i = 0; i < n; ++i) {
-            const int col_base = (ct0 + i) * CE_TILE;
+            const int col_base = (ct0 + i * ct_step) * CE_TILE;
             if (MODE == MODE_DW) {
                 // lse / target of the 128 hidden rows forming this tile's columns
                 asm volatile("bar.sync 1, 256;" ::: "memory");       // previous tile's constants no longer in use
@@ -189,7 +203,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
                     const int hr = col_base + et;
                     float l2 = 0.f;
                     int tg = -1;
-                    if (hr < a.R) {
+                    if (hr < R_live) {
                         l2 = a.lse[hr] * CE_LOG2E;
                         const long long t = a.target[hr] - (long long)a.v0;
                         tg = (t >= 0 && t < (long long)a.Vloc) ? (int)t : -1;
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
                         const int cc = c16 * 16 + c;                       // column inside the tile
                         const float p = ce_exp2(fmaf(t[c] + row_bias, CE_LOG2E, -sh->col_lse[cc]));
                         const float gg = (p - (sh->col_tgt[cc] == row ? 1.f : 0.f)) * sc2;
-                        g[c] = (row_ok && col0 + c < a.R) ? gg : 0.f;
+                        g[c] = (row_ok && col0 + c < R_live) ? gg : 0.f;
                         bias_sum += g[c];
                     }
                 }
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_bwd_tc_kernel(const __grid_c
             mbar_arrive_warp(&sh->x_full);
         }
         // ---- accumulators -> partial outputs (each warpgroup half of the Kp columns)
-        float* out = a.partial + (size_t)split * n_rows_total * a.H;
+        float* out = a.partial + (size_t)split * n_rows_layout * a.H;
         if (n > 0) {
             mbar_wait_lean(&sh->acc_done, 0);
             tc_fence_after();
@@ -350,7 +364,7 @@ extern "C" size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp
 
 extern "C" int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
                                          const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
-                                         void* ws, size_t ws_bytes, asme_stream_t stream) {
+                                         void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(Hb && Wb && target && lse, "tc_score_ce_bwd: null argument");
     ASME_REQUIRE(Kp >= 64 && Kp <= 256 && Kp % 64 == 0 && H <= Kp && H % 4 == 0, "tc_score_ce_bwd: H=%d Kp=%d unsupported", H, Kp);
     ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_ce_bwd: bias must be 16-byte aligned");
@@ -363,7 +377,7 @@ extern "C" int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, c
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     CeBwdArgs a{};
-    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.H = H; a.Kp = Kp; a.bias = bias; a.target = target; a.lse = lse; a.scale = scale;
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.H = H; a.Kp = Kp; a.bias = bias; a.target = target; a.lse = lse; a.scale = scale; a.n_live = n_live;
     a.partial = (float*)ws;
     if (dH) {
         CePlan p;

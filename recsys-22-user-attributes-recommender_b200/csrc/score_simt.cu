@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(const float* __res
                                                               const float* __restrict__ W, const float* __restrict__ bias, int v0,
                                                               int Vloc, const int64_t* __restrict__ target, int tiles_per_split,
                                                               float* __restrict__ pm, float* __restrict__ ps,
-                                                              float* __restrict__ ptl) {
+                                                              float* __restrict__ ptl, const int32_t* __restrict__ n_live) {
     extern __shared__ __align__(16) float smem[];
     const int ld = H + 4;
     float* hs = smem;
@@ -360,6 +360,9 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(const float* __res
     float* tile = Ws + TS * ld;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16, warp = tid / 32, lane = tid % 32;
     const int m0 = blockIdx.x * TS;
+    const int R_cap = R;                          // partial buffers are laid out for the capacity
+    R = asme_live_rows(R, n_live);
+    if (m0 >= R) return;
     const int split = blockIdx.y;
     const int tile_begin = split * tiles_per_split;
     const int tile_end = min(ceil_div(Vloc, TS), tile_begin + tiles_per_split);
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(const float* __res
         for (int r = 0; r < ROWS_PER_WARP; ++r) {
             const int row = m0 + warp * ROWS_PER_WARP + r;
             if (row >= R) break;
-            const size_t o = (size_t)split * R + row;
+            const size_t o = (size_t)split * R_cap + row;
             pm[o] = mx[r]; ps[o] = sm[r]; ptl[o] = tl[r];
         }
     }
@@ -408,9 +411,9 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_kernel(const float* __res
 
 __global__ void ce_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps, const float* __restrict__ ptl,
                                   int splits, int R, float* __restrict__ row_max, float* __restrict__ row_sumexp,
-                                  float* __restrict__ target_logit) {
+                                  float* __restrict__ target_logit, const int32_t* __restrict__ n_live) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
+    if (r >= asme_live_rows(R, n_live)) return;
     float m = -INFINITY;
     for (int s = 0; s < splits; ++s) m = fmaxf(m, pm[(size_t)s * R + r]);
     float sum = 0.f, tl = 0.f;
@@ -428,7 +431,7 @@ extern "C" size_t asme_b200_score_ce_workspace_bytes(int R, int Vloc) {
 
 extern "C" int asme_b200_score_ce_partial(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
                                           const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
-                                          void* ws, size_t ws_bytes, asme_stream_t stream) {
+                                          void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(Hrows && W && target && row_max && row_sumexp && target_logit, "score_ce_partial: null argument");
     int rc = check_score(R, H, Vloc);
     if (rc) return rc;
@@ -447,19 +450,22 @@ extern "C" int asme_b200_score_ce_partial(const float* Hrows, int R, int H, cons
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     score_ce_kernel<<<dim3(ceil_div(R, TS), splits), SC_THREADS, smem, st>>>(Hrows, R, H, W, bias, v0, Vloc, target,
-                                                                             tiles_per_split, pm, ps, ptl);
+                                                                             tiles_per_split, pm, ps, ptl, n_live);
     ASME_LAUNCH_OK();
-    ce_combine_kernel<<<ceil_div(R, 128), 128, 0, st>>>(pm, ps, ptl, splits, R, row_max, row_sumexp, target_logit);
+    ce_combine_kernel<<<ceil_div(R, 128), 128, 0, st>>>(pm, ps, ptl, splits, R, row_max, row_sumexp, target_logit, n_live);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
 
 // lse[r] = max + log(sumexp); loss_sum += sum_r (lse[r] - target_logit[r])   (single block: deterministic)
+// with a device row count: only the live rows, and loss_mean[0] = loss_sum / n_live (0 live rows -> NaN, as the mean over an
+// empty set is in nn.CrossEntropyLoss)
 __global__ void ce_loss_kernel(const float* __restrict__ row_max, const float* __restrict__ row_sumexp,
                                const float* __restrict__ target_logit, int R, float* __restrict__ lse,
-                               float* __restrict__ loss_sum) {
+                               float* __restrict__ loss_sum, const int32_t* __restrict__ n_live, float* __restrict__ loss_mean) {
     __shared__ float red[1024];
     float acc = 0.f;
+    R = asme_live_rows(R, n_live);
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         const float l = row_max[r] + logf(row_sumexp[r]);
         lse[r] = l;
@@ -471,13 +477,18 @@ __global__ void ce_loss_kernel(const float* __restrict__ row_max, const float* _
         if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) loss_sum[0] += red[0];
+    if (threadIdx.x == 0) {
+        const float total = loss_sum[0] + red[0];
+        loss_sum[0] = total;
+        if (loss_mean) loss_mean[0] = total / (float)R;
+    }
 }
 extern "C" int asme_b200_ce_loss_from_partials(const float* row_max, const float* row_sumexp, const float* target_logit, int R,
-                                               float* lse, float* loss_sum, asme_stream_t stream) {
+                                               float* lse, float* loss_sum, const int32_t* n_live, float* loss_mean,
+                                               asme_stream_t stream) {
     ASME_REQUIRE(row_max && row_sumexp && target_logit && lse && loss_sum, "ce_loss: null argument");
-    if (R == 0) return ASME_OK;
-    ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_max, row_sumexp, target_logit, R, lse, loss_sum);
+    if (R == 0 && !loss_mean) return ASME_OK;
+    ce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_max, row_sumexp, target_logit, R, lse, loss_sum, n_live, loss_mean);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_bwd_kernel(const float* _
                                                                   int v0, int Vloc, const int64_t* __restrict__ target,
                                                                   const float* __restrict__ lse, float scale, int mode,
                                                                   int tiles_per_split, float* __restrict__ out,
-                                                                  float* __restrict__ out_bias) {
+                                                                  float* __restrict__ out_bias, const int32_t* __restrict__ n_live) {
     extern __shared__ __align__(16) float smem[];
     const int ld = H + 4;
     float* hs = smem;
@@ -502,9 +513,18 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_bwd_kernel(const float* _
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int split = blockIdx.y;
     const int own0 = blockIdx.x * TS;    // first owned row (mode 0) / item (mode 1)
+    const int R_cap = R;                 // partial buffers are laid out for the capacity
+    if (n_live != nullptr) {             // row selection: the live count and the mean's 1/n come from the device
+        R = asme_live_rows(R, n_live);
+        scale = scale / (float)R;
+        if (mode == 0 && own0 >= R) return;
+    }
     const int n_other = mode == 0 ? Vloc : R;
-    const int tile_begin = split * tiles_per_split;
-    const int tile_end = min(ceil_div(n_other, TS), tile_begin + tiles_per_split);
+    // mode 0 streams a contiguous range of item tiles; mode 1 streams hidden-row tiles round robin over the splits, so that the
+    // live rows of a capacity-sized selection are spread over all of them
+    const int tile_begin = mode == 0 ? split * tiles_per_split : split;
+    const int tile_end = mode == 0 ? min(ceil_div(n_other, TS), tile_begin + tiles_per_split) : ceil_div(n_other, TS);
+    const int tile_step = mode == 0 ? 1 : (int)gridDim.y;
 
     float4 acc2[4][NC];
 #pragma unroll
@@ -515,7 +535,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_bwd_kernel(const float* _
 
     if (mode == 0) stage_tile(Hrows, R, own0, H, hs, ld);
     else stage_tile(W, Vloc, own0, H, Ws, ld);
-    for (int t = tile_begin; t < tile_end; ++t) {
+    for (int t = tile_begin; t < tile_end; t += tile_step) {
         const int oth0 = t * TS;
         const int m0 = mode == 0 ? own0 : oth0;
         const int n0 = mode == 0 ? oth0 : own0;
@@ -589,7 +609,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_ce_bwd_kernel(const float* _
         }
     }
     const int n_own = mode == 0 ? R : Vloc;
-    float* o = out + (size_t)split * n_own * H;
+    float* o = out + (size_t)split * (mode == 0 ? R_cap : Vloc) * H;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = own0 + ty * 4 + i;
@@ -627,7 +647,7 @@ extern "C" size_t asme_b200_score_ce_bwd_workspace_bytes(int R, int H, int Vloc)
 
 extern "C" int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
                                       const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
-                                      void* ws, size_t ws_bytes, asme_stream_t stream) {
+                                      void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(Hrows && W && target && lse, "score_ce_bwd: null argument");
     int rc = check_score(R, H, Vloc);
     if (rc) return rc;
@@ -645,7 +665,7 @@ extern "C" int asme_b200_score_ce_bwd(const float* Hrows, int R, int H, const fl
         rc = set_smem(score_ce_bwd_kernel<NC>, smem);                                                                       \
         if (rc) return rc;                                                                                                  \
         score_ce_bwd_kernel<NC><<<GRID, SC_THREADS, smem, st>>>(Hrows, R, H, W, bias, v0, Vloc, target, lse, scale, MODE, TPS, \
-                                                                OUT, OUTB);                                                 \
+                                                                OUT, OUTB, n_live);                                         \
     }
 #define LAUNCH_NC(MODE, GRID, TPS, OUT, OUTB)                          \
     switch (nc) {                                                      \

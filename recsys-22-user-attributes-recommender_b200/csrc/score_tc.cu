@@ -75,7 +75,7 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, lo
 // fp32 -> bf16 operand preparation (round to nearest even), zero padded to ld_out columns
 // ------------------------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int cols, int ld_in,
-                                 int ld_out) {
+                                 int ld_out, const int32_t* __restrict__ n_live) {
     const int per_row = ld_out / 4;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * per_row) return;
@@ -83,7 +83,10 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     const int c = (int)(i % per_row) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* src = x + r * ld_in + c;
-    if (c + 3 < cols && (ld_in % 4) == 0) v = ldg4(src);
+    // rows past the live count are written as zeros (not skipped): the result is a TMA / MMA operand, and stale bits there could
+    // be NaNs that a masked-out (x 0) product would still propagate
+    if (n_live != nullptr && r >= (long long)__ldg(n_live)) { /* zeros */ }
+    else if (c + 3 < cols && (ld_in % 4) == 0) v = ldg4(src);
     else {
         if (c + 0 < cols) v.x = src[0];
         if (c + 1 < cols) v.y = src[1];
@@ -129,13 +132,14 @@ extern "C" int asme_b200_cast_bf16_ext(const float* x, const float* bias, void* 
     return ASME_OK;
 }
 
-extern "C" int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, asme_stream_t stream) {
+extern "C" int asme_b200_cast_bf16(const float* x, void* y, long long rows, int cols, int ld_in, int ld_out, const int32_t* n_live,
+                                   asme_stream_t stream) {
     ASME_REQUIRE(x && y, "cast_bf16: null argument");
     ASME_REQUIRE(cols >= 1 && ld_in >= cols && ld_out >= cols && ld_out % 4 == 0, "cast_bf16: cols=%d ld_in=%d ld_out=%d", cols, ld_in,
                  ld_out);
     if (rows == 0) return ASME_OK;
     const long long n = rows * (ld_out / 4);
-    cast_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, rows, cols, ld_in, ld_out);
+    cast_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, rows, cols, ld_in, ld_out, n_live);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
@@ -177,6 +181,7 @@ struct ScoreTcArgs {
     int* pt;                     // partial #tie-lower    [parts][R]
     float* ps;                   // CE: partial sum-exp   [parts][R]
     float* captured;             // [R]: score of the target column as computed by this kernel (owner writes)
+    const int32_t* n_live;       // device count of live rows (row selections of capacity R) or NULL: row tiles past it exit at once
 };
 
 struct __align__(8) ScoreTcBarriers {
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
     const int split = blockIdx.y;
     const int t0 = min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
     const int t1 = min(a.n_tiles, split * a.tiles_per_split + a.tile_hi);
+    if (a.n_live != nullptr && m0 >= __ldg(a.n_live)) return;      // whole CTA, before any barrier / TMEM allocation (never with PAIR)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -771,9 +777,9 @@ static int launch_merge(const float* pv, const int* pi, const int* pg, const int
 
 // CE partials: (max in log2 units, sum of exp2) per part -> natural-log row max and sum-exp
 __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps, int parts, int R,
-                                   float* __restrict__ row_max, float* __restrict__ row_sumexp) {
+                                   float* __restrict__ row_max, float* __restrict__ row_sumexp, const int32_t* __restrict__ n_live) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
+    if (r >= asme_live_rows(R, n_live)) return;
     float m = -INFINITY;
     for (int p = 0; p < parts; ++p) m = fmaxf(m, pm[(size_t)p * R + r]);
     float s = 0.f;
@@ -823,7 +829,9 @@ extern "C" int asme_b200_tc_score_tune(int knob, int value) {
     return ASME_OK;
 }
 
-static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
+// ``plan_rows`` (0 = R): how many of the R rows are expected to be live (row selections pass their capacity as R and the count on
+// the device); only the split of the catalog over CTAs is chosen from it -- a wrong guess costs balance, never correctness.
+static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false, int plan_rows = 0) {
     ASME_REQUIRE(R >= 1 && Vloc >= 1, "tc score: bad shape R=%d Vloc=%d", R, Vloc);
     ASME_REQUIRE(Kp >= 16 && Kp <= 272 && Kp % 16 == 0, "tc score: padded hidden size %d unsupported (multiple of 16, <= 272)", Kp);
     p->kch = ceil_div(Kp, CHUNK_K);
@@ -834,7 +842,8 @@ static int make_plan(int R, int Kp, int Vloc, ScorePlan* p, bool topk = false) {
     p->pair = (g_pair && p->m_tiles >= 2) ? 1 : 0;
     p->grid_x = p->pair ? (p->m_tiles + 1) / 2 * 2 : p->m_tiles;      // an odd last row tile is paired with an empty one
     p->tail16 = (g_tail16 && !p->pair && Kp % CHUNK_K == 16 && Kp > 16) ? 1 : 0;
-    int splits = ASME_NUM_SMS / p->grid_x;
+    const int fill_x = (plan_rows > 0 && plan_rows < R) ? ceil_div(plan_rows, BM) : p->grid_x;
+    int splits = ASME_NUM_SMS / fill_x;
     if (splits < 1) splits = 1;
     if (splits > p->n_tiles) splits = p->n_tiles;
     p->tiles_per_split = ceil_div(p->n_tiles, splits);
@@ -1021,21 +1030,22 @@ extern "C" int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, 
     return launch_score<EPI_PROBE, 0, false>(tmA, tmB, a, p, (cudaStream_t)stream);
 }
 
-extern "C" size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc) {
+extern "C" size_t asme_b200_tc_score_ce_workspace_bytes(int R, int Kp, int Vloc, int plan_rows) {
     ScorePlan p;
-    if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p)) return 0;
+    if (make_plan(R < 1 ? 1 : R, Kp, Vloc, &p, false, plan_rows)) return 0;
     return (size_t)(p.splits + 1) * MAX_EPI_WGS * (R < 1 ? 1 : R) * 8;
 }
 
 extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
                                              const int64_t* target, float* row_max, float* row_sumexp, float* target_logit,
-                                             void* ws, size_t ws_bytes, asme_stream_t stream) {
+                                             void* ws, size_t ws_bytes, const int32_t* n_live, int plan_rows, asme_stream_t stream) {
     ASME_REQUIRE(Hb && Wb && target && row_max && row_sumexp && target_logit, "tc_score_ce_partial: null argument");
     ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_ce_partial: bias must be 16-byte aligned");
     if (R == 0) return ASME_OK;
     ScorePlan p;
-    int rc = make_plan(R, Kp, Vloc, &p);
+    int rc = make_plan(R, Kp, Vloc, &p, false, n_live ? plan_rows : 0);
     if (rc) return rc;
+    ASME_REQUIRE(!(n_live && p.pair), "tc_score_ce_partial: a device row count cannot be combined with CTA pairs");
     const size_t need = (size_t)p.splits * MAX_EPI_WGS * R * 8;
     if (ws_bytes < need) {
         asme_set_error("tc_score_ce_partial: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -1056,10 +1066,11 @@ extern "C" int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, cons
     a.ps = a.pv + (size_t)p.parts * R;
     a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
     a.captured = target_logit;      // the caller zero-fills: only the shard that owns the target column writes
+    a.n_live = n_live;
     cudaStream_t st = (cudaStream_t)stream;
     rc = launch_score<EPI_CE, 0, false>(tmA, tmB, a, p, st);
     if (rc) return rc;
-    tc_ce_merge_kernel<<<ceil_div(R, 128), 128, 0, st>>>(a.pv, a.ps, p.parts, R, row_max, row_sumexp);
+    tc_ce_merge_kernel<<<ceil_div(R, 128), 128, 0, st>>>(a.pv, a.ps, p.parts, R, row_max, row_sumexp, n_live);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

@@ -436,3 +436,93 @@ def test_errors_are_loud(ops):
         ops.layernorm_fwd(torch.randn(4, 24, device="cuda"), torch.ones(24, device="cuda"), torch.zeros(24, device="cuda"))
     with pytest.raises(RuntimeError):
         ops.layernorm_fwd(torch.randn(4, 64), torch.ones(64), torch.zeros(64))     # CPU tensors: no CPU path
+
+
+# ---- device-side row selection and live-row counts ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,density", [(1, 1.0), (7, 0.5), (2048, 0.2), (2049, 0.0), (51200, 0.2), (300000, 0.9)])
+def test_select_rows_matches_nonzero(T, density):
+    from asme_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    target = torch.where(torch.rand(T, generator=g) < density, torch.randint(1, 1000, (T,), generator=g), torch.zeros(T, dtype=torch.int64))
+    rows, row_targets, n = ops.select_rows(target.cuda(), 0)
+    want = torch.nonzero(target).reshape(-1)
+    k = int(n.item())
+    assert k == want.numel()
+    assert torch.equal(rows[:k].cpu(), want) and torch.equal(row_targets[:k].cpu(), target[want])
+    assert bool((rows[k:] == -1).all()) and bool((row_targets[k:] == 0).all())
+
+
+def test_clip_grad_norm_matches_torch():
+    from asme_b200 import ops
+    g = torch.randn(100003, generator=torch.Generator().manual_seed(0)).cuda() * 3
+    for max_norm in (1.0, 1e6):
+        mine = g.clone()
+        norm = torch.zeros(1, device="cuda")
+        ops.clip_grad_norm(mine, max_norm, norm)
+        ref = torch.nn.Parameter(g.clone())
+        ref.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref], max_norm)
+        torch.testing.assert_close(norm[0], total, rtol=1e-6, atol=0)
+        torch.testing.assert_close(mine, ref.grad, rtol=1e-6, atol=0)
+
+
+def test_live_row_counts_leave_the_other_rows_alone():
+    """row-path kernels with a device count: live rows equal the plain call on exactly those rows, the rest is untouched"""
+    from asme_b200 import ops
+    torch.manual_seed(0)
+    cap, live, H = 300, 77, 64
+    n = torch.tensor([live], dtype=torch.int32, device="cuda")
+    x = torch.randn(cap, H, device="cuda")
+    gamma, beta = torch.randn(H, device="cuda"), torch.randn(H, device="cuda")
+    w, b = torch.randn(H, H, device="cuda"), torch.randn(H, device="cuda")
+    y, _ = ops.layernorm_fwd(x, gamma, beta, n_live=n)
+    y_ref, _ = ops.layernorm_fwd(x[:live].contiguous(), gamma, beta)
+    assert torch.equal(y[:live], y_ref)
+    c = torch.full((cap, H), 7.0, device="cuda")
+    ops.gemm(x, w, bias=b, out=c, m_live=n)
+    assert torch.equal(c[:live], ops.gemm(x[:live].contiguous(), w, bias=b)) and bool((c[live:] == 7.0).all())
+    z16 = ops.cast_bf16(x, ld_out=H, n_live=n)
+    assert torch.equal(z16[:live], ops.cast_bf16(x[:live].contiguous(), ld_out=H)) and bool((z16[live:] == 0).all())
+    idx = torch.randperm(1000, device="cuda")[:cap]
+    idx[live:] = -1
+    src = torch.randn(1000, H, device="cuda")
+    out = ops.gather_rows(src, idx, n)
+    assert torch.equal(out[:live], src[idx[:live]])
+    dst = torch.zeros(1000, H, device="cuda")
+    ops.scatter_rows(x, idx, dst, n)
+    want = torch.zeros(1000, H, device="cuda")
+    want[idx[:live]] = x[:live]
+    assert torch.equal(dst, want)
+    dw, db = torch.zeros(H, H, device="cuda"), torch.zeros(H, device="cuda")
+    dy = torch.randn(cap, H, device="cuda")
+    ops.gemm_wgrad(dy, x, dw, db, m_live=n)
+    torch.testing.assert_close(dw, dy[:live].t() @ x[:live], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(db, dy[:live].sum(0), rtol=1e-4, atol=1e-4)
+    dz = ops.gelu_backward(dy, x, n_live=n)
+    assert torch.equal(dz[:live], ops.gelu_backward(dy[:live].contiguous(), x[:live].contiguous()))
+
+
+@pytest.mark.parametrize("cap,live,V,H", [(300, 100, 3709, 64), (200, 1, 61, 16), (130, 130, 1000, 128)])
+def test_score_ce_with_device_row_count(ops, cap, live, V, H):
+    """fp32 scoring + CE on a capacity-sized row selection: live rows as the call on exactly those rows; mean and 1/n on the device"""
+    gen = torch.Generator().manual_seed(cap + V)
+    h = torch.randn(cap, H, generator=gen)
+    h[live:] = float("nan")
+    w = torch.randn(V, H, generator=gen) * 0.2
+    bias = torch.randn(V, generator=gen) * 0.2
+    target = torch.randint(1, V, (cap,), generator=gen)
+    target[live:] = 0
+    n = torch.tensor([live], dtype=torch.int32, device="cuda")
+    rmax, rsum, tl = ops.score_ce_partial(dev(h), dev(w), dev(bias), dev(target), n_live=n)
+    acc = torch.zeros(2, device="cuda")
+    lse = ops.ce_loss_from_partials(rmax, rsum, tl, acc[0:1], n, acc[1:2])
+    hl = h[:live].clone().requires_grad_(True)
+    wl, bl = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(hl @ wl.t() + bl, target[:live])
+    loss.backward()
+    close(acc[1], loss, rtol=1e-5, atol=1e-5, msg="mean loss")
+    dW, db = torch.zeros(V, H, device="cuda"), torch.zeros(V, device="cuda")
+    dh = ops.score_ce_bwd(dev(h), dev(w), dev(bias), dev(target), lse, 1.0, dW, db, n_live=n)
+    close(dh[:live], hl.grad, rtol=1e-4, atol=1e-6, msg="dH")
+    close(dW, wl.grad, rtol=1e-4, atol=1e-6, msg="dW")
+    close(db, bl.grad, rtol=1e-4, atol=1e-6, msg="dbias")

@@ -324,3 +324,43 @@ def test_tc_topk_bias_folded_into_the_contraction_exact(ops, R, V, H, k):
     got = ops.tc_score_topk(hb, wb2, None, k, target=target.cuda())["target_score"].cpu()
     want = torch.from_numpy(ref_logits(h, w, None).float().numpy())[torch.arange(R), target] + bias[target]
     torch.testing.assert_close(got, want, rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("cap,live,V,H,plan", [(1000, 300, 3709, 64, 300), (1000, 1, 700, 64, 0), (640, 640, 1031, 128, 100), (2000, 129, 5003, 64, 2000)])
+def test_tc_ce_with_device_row_count(ops, cap, live, V, H, plan):
+    """row selections: the buffers have a capacity, the live count is in device memory.  Forward partials and the loss of the live
+    rows equal the call on exactly those rows bit for bit (rows are independent in the sweep); the backward divides by the count on
+    the device and matches autograd of the mean over the live rows; dead rows hold NaNs on purpose and must not leak."""
+    gen = torch.Generator(device="cuda").manual_seed(cap + live)
+    h = torch.randn(cap, H, generator=gen, device="cuda")
+    h[live:] = float("nan")
+    w = torch.randn(V, H, generator=gen, device="cuda") * 0.2
+    b = torch.randn(V, generator=gen, device="cuda") * 0.1
+    target = torch.randint(1, V, (cap,), generator=gen, device="cuda")
+    target[live:] = 0
+    n = torch.tensor([live], dtype=torch.int32, device="cuda")
+    wb = ops.cast_bf16(w)
+    hb = ops.cast_bf16(h, n_live=n)
+    assert bool((hb[live:] == 0).all())
+    rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, target, n_live=n, plan_rows=plan)
+    hb_x = ops.cast_bf16(h[:live].contiguous())
+    rmax_x, rsum_x, tl_x = ops.tc_score_ce_partial(hb_x, wb, b, target[:live].contiguous())
+    # the split of the catalog over CTAs follows the planned row count, and with it the order in which the partial sums meet
+    assert torch.equal(rmax[:live], rmax_x) and torch.equal(tl[:live], tl_x)
+    torch.testing.assert_close(rsum[:live], rsum_x, rtol=2e-6, atol=0)
+    acc = torch.zeros(2, device="cuda")
+    lse = ops.ce_loss_from_partials(rmax, rsum, tl, acc[0:1], n, acc[1:2])
+    acc_x = torch.zeros(1, device="cuda")
+    lse_x = ops.ce_loss_from_partials(rmax_x, rsum_x, tl_x, acc_x)
+    torch.testing.assert_close(lse[:live], lse_x, rtol=1e-6, atol=1e-6)
+    assert float(acc[1]) == pytest.approx(float(acc_x[0]) / live, rel=1e-5)
+    dW, db = torch.zeros(V, H, device="cuda"), torch.zeros(V, device="cuda")
+    dh = ops.tc_score_ce_bwd(hb, wb, b, target, lse, 1.0, H, dW, db, n_live=n)
+    hd = hb_x[:, :H].double().requires_grad_(True)
+    wd = wb[:, :H].double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    torch.nn.functional.cross_entropy(hd @ wd.t() + bd, target[:live]).backward()
+    for name, got, want in (("dH", dh[:live], hd.grad), ("dW", dW, wd.grad), ("dbias", db, bd.grad)):
+        assert bool(torch.isfinite(got).all()), name
+        err = float((got.double() - want).norm() / want.norm())
+        assert err < 6e-3, f"{name}: relative norm error {err:.5f}"

@@ -19,7 +19,7 @@ module.train()
 (optimizer,), _ = module.configure_optimizers()
 gen = torch.Generator().manual_seed(1)
 inp, target, rows = bench.make_cloze_batch(gen, 64, cfg["S"], cfg["V"], 0.2, 20)
-batch = {"item": inp.to(dev), "item.target": target.to(dev), "_target_rows": rows.to(dev)}
+batch = {"item": inp.to(dev), "item.target": target.to(dev)}
 
 
 def attempt(name, fn, mode="global"):
@@ -55,11 +55,11 @@ ids = torch.randint(0, 3709, (12800,), device=dev)
 tab = torch.zeros(3709, 64, device=dev)
 attempt("embgrad", lambda: ops.embgrad_sorted_reduce(ids, x, tab))
 attempt("layernorm_bwd", lambda: ops.layernorm_bwd(x, x, torch.ones(64, device=dev), torch.ones(2, x.shape[0], device=dev), torch.zeros(2, 64, device=dev)))
-attempt("forward loss_ce", lambda: model.loss_ce(batch["item"], batch["item"].ne(0), {}, batch["item.target"], rows=batch["_target_rows"]))
+attempt("forward loss_ce", lambda: model.loss_ce(batch["item"], batch["item"].ne(0), {}, batch["item.target"]))
 
 
 def fwd_bwd():
-    loss, ctx = model.loss_ce(batch["item"], batch["item"].ne(0), {}, batch["item.target"], rows=batch["_target_rows"])
+    loss, ctx = model.loss_ce(batch["item"], batch["item"].ne(0), {}, batch["item.target"])
     model.loss_ce_backward(ctx)
 
 
