@@ -296,6 +296,40 @@ int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void* Wb, const
                             const int64_t* target, const float* target_score_in, int k, float* topk_val,
                             int32_t* topk_idx, float* target_score_out, int32_t* n_greater, int32_t* n_tie_lower,
                             void* ws, size_t ws_bytes, asme_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * EXACT top-k on the tensor-core path (metrics/common.py:18-27 sorts the fp32 logits).  The bf16 sweep above is the candidate
+ * generator (KC > k best items by bf16-operand score); asme_b200_topk_rescore re-scores the candidates from the fp32 hidden rows
+ * and the fp32 table slice [v0, v0+V) with the arithmetic of the fp32 path (sequential fmaf chain, + bias: bit-identical to
+ * asme_b200_score_topk_rank / asme_b200_score_targets), orders them (score desc, id asc) and CERTIFIES each row: with
+ * E = ||h-h~|| max||w_v|| + ||h~|| max||w_v-w~_v|| + 2^-15 max|b_v| + 2^-16 ||h|| max||w_v|| (h~, w~ the bf16 operands) bounding
+ * |exact - bf16| for every item, no item outside the list can
+ * enter the top k when (bf16 score of anything outside the list) + E < (exact k-th best candidate score).  Rows that cannot be certified get
+ * row_flag = 1 (n_flagged counts them) and are re-run exactly by asme_b200_score_topk_flagged -- all decided on the device.
+ *   norm_bound (3) = {max_v ||w_v||_2, max_v |b_v|, max_v ||w_v - bf16(w_v)||_2} from asme_b200_table_norm_bound (cache it until
+ *   the weights change)
+ *   target (R) optional: target_score (R) = exact score, written by the slice that owns the target's row (caller zero-fills);
+ *   rank (R) = 1-based position of the target among the exact top k, k+1 when it is not among them
+ * ------------------------------------------------------------------------------------------ */
+int asme_b200_table_norm_bound(const float* W, int V, int H, const float* bias /*NULL ok*/, float* out3, asme_stream_t stream);
+/* candidates for the exact top-k: cand_val / cand_idx (R,k_out) = the k_out best by bf16 score among what the sweep's lists kept,
+ * bound (R) = upper bound of the bf16 score of every item in NONE of the row's lists (-inf: the list is the true bf16 top k_out) */
+size_t asme_b200_tc_score_candidates_workspace_bytes(int R, int Kp, int Vloc, int k, int k_out);
+int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                                  const int64_t* target /*NULL ok*/, int k, int k_out, float* cand_val, int32_t* cand_idx, float* bound,
+                                  float* target_score_out /*NULL ok: bf16 score of the target, owner shard writes*/, void* ws,
+                                  size_t ws_bytes, asme_stream_t stream);
+int asme_b200_topk_rescore(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int V,
+                           const int32_t* cand_idx /*R,KC global ids, -1 = empty*/, const float* cand_val /*R,KC bf16-sweep scores*/,
+                           const float* cand_bound /*R or NULL*/, int KC, int k, const float* norm_bound, const int64_t* target /*NULL ok*/, float* topk_val /*R,k*/,
+                           int32_t* topk_idx /*R,k*/, float* target_score /*NULL ok*/, int32_t* rank /*NULL ok*/,
+                           int32_t* row_flag /*R*/, int32_t* n_flagged /*1*/, asme_stream_t stream);
+/* the exact fp32 sweep (asme_b200_score_topk_rank) restricted to the rows with row_flag != 0: only row tiles holding a flagged row
+ * run, only flagged rows of topk_val / topk_idx / rank (= exact FULL rank, needs target + target_score) are overwritten */
+size_t asme_b200_score_topk_flagged_workspace_bytes(int R, int Vloc);
+int asme_b200_score_topk_flagged(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                                 const int64_t* target, const float* target_score, int k, const int32_t* row_flag,
+                                 float* topk_val, int32_t* topk_idx, int32_t* rank /*NULL ok*/, void* ws, size_t ws_bytes,
+                                 asme_stream_t stream);
 /* diagnostic: the same sweep with an empty epilogue -- the ceiling of the TMA -> tcgen05.mma -> TMEM pipeline for this shape */
 int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, const void* Wb, int Vloc, int read_tmem /* also read (and
     discard) every accumulator: TMEM read throughput */, asme_stream_t stream);

@@ -111,6 +111,12 @@ _PROTOTYPES = {
     "asme_b200_tc_attn_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, P, P]),
     "asme_b200_posneg_bce_fwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, P]),
     "asme_b200_posneg_bce_bwd": (c_int, [P, P, P, P, P, c_int, c_int, P, P, P, c_float, P, P, P, P]),
+    "asme_b200_table_norm_bound": (c_int, [P, c_int, c_int, P, P, P]),
+    "asme_b200_topk_rescore": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P, P]),
+    "asme_b200_tc_score_candidates_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "asme_b200_tc_score_candidates": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_score_topk_flagged_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_score_topk_flagged": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P, P]),
     "asme_b200_scatter_rows": (c_int, [P, P, c_int, c_int, P, P, P]),
     "asme_b200_select_rows_workspace_bytes": (c_size_t, [c_longlong]),

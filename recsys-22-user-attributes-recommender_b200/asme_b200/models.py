@@ -32,6 +32,9 @@ MASK_TOKEN_ID = 1
 #           LayerNorm, softmax statistics, losses and optimizer state stay fp32 (north_star tolerance 1e-3)
 #   "fp32": strict-parity SIMT path (1e-5)
 DEFAULT_PRECISION = os.environ.get("ASME_B200_PRECISION", "bf16")
+# Exact top-k lists under the bf16 policy: the bf16 sweep only proposes candidates, which are re-scored from the fp32 table and
+# certified (csrc/rescore.cu) -- lists, target positions and @k metrics are then those of the fp32 path for the same hidden rows.
+EXACT_TOPK = os.environ.get("ASME_B200_EXACT_TOPK", "1") == "1"
 
 
 def set_default_precision(precision: str) -> None:
@@ -112,6 +115,7 @@ class TransformerRecommenderModel(ArenaModule):
         self._init_arena(list(specs) + attr_specs + [("_ghost_zero_row", (H,))])
         self.engine = EncoderEngine(self, cfg)
         self.precision = DEFAULT_PRECISION
+        self.exact_topk = EXACT_TOPK
         self._wb_cache = None
         self._seed = 0
         self._step_counter = 0
@@ -333,6 +337,15 @@ class TransformerRecommenderModel(ArenaModule):
             self._wb_folded = (stamp, ops.cast_bf16_ext(w, b))
         return self._wb_folded[1], True
 
+    def projection_norm_bound(self):
+        """(2): max row norm of the catalog table and max |bias| (ops.table_norm_bound), cached until the weights change"""
+        w, b = self.projection_operands()
+        stamp = (self._arena.version, self._arena.flat._version, w.data_ptr())
+        cache = getattr(self, "_norm_bound", None)
+        if cache is None or cache[0] != stamp:
+            self._norm_bound = (stamp, ops.table_norm_bound(w, b))
+        return self._norm_bound[1]
+
     def modify(self, rows: torch.Tensor, save: bool = False, n_live=None):
         if self.modifier_kind == "ffn":
             return self.engine.modifier_forward(rows, save, n_live)
@@ -499,7 +512,10 @@ class TransformerRecommenderModel(ArenaModule):
         if self.precision == "bf16":
             wb, folded = self.projection_operands_folded()
             hb = ops.cast_bf16_ext(m_rows) if folded else ops.cast_bf16(m_rows, ld_out=wb.shape[1])
-            o = ops.tc_score_topk(hb, wb, None, n)
+            if self.exact_topk:
+                o = score_rows_tc_exact(m_rows, hb, wb, *self.projection_operands(), self.projection_norm_bound(), None, n, False)
+            else:
+                o = ops.tc_score_topk(hb, wb, None, n)
             rmax, rsum, _ = ops.tc_score_ce_partial(hb, wb, None, zero)
         else:
             w, b = self.projection_operands()
@@ -513,7 +529,10 @@ class TransformerRecommenderModel(ArenaModule):
             wb, folded = self.projection_operands_folded()
             b = None
             hb = ops.cast_bf16_ext(m_rows) if folded else ops.cast_bf16(m_rows, ld_out=wb.shape[1])
-            out = score_rows_tc(hb, wb, b, target, k, full_rank)
+            if self.exact_topk:
+                out = score_rows_tc_exact(m_rows, hb, wb, *self.projection_operands(), self.projection_norm_bound(), target, k, full_rank)
+            else:
+                out = score_rows_tc(hb, wb, b, target, k, full_rank)
             if with_loss:
                 rmax, rsum, tl = ops.tc_score_ce_partial(hb, wb, b, target)
                 out["lse"] = rmax + torch.log(rsum)
@@ -575,6 +594,27 @@ def score_rows_tc(hb, wb, b, target, k, full_rank: bool = True):
         hit = o["topk_idx"].eq(target.to(torch.int32).unsqueeze(1))
         pos = hit.to(torch.int32).argmax(dim=1).to(torch.int32)
         out["rank"] = torch.where(hit.any(dim=1), pos + 1, torch.full_like(pos, k + 1))
+    return out
+
+
+def score_rows_tc_exact(m_rows, hb, wb, w32, b32, norm_bound, target, k, full_rank: bool = False):
+    """exact top-k on the tensor-core path: bf16 sweep -> candidates + what the sweep may have dropped (``ops.tc_score_candidates``)
+    -> fp32 re-score + order + certificate (``ops.topk_rescore``) -> exact fp32 sweep for the rows the certificate could not
+    cover (``ops.score_topk_flagged``; normally none).  ``topk_idx`` / ``topk_val`` / ``target_score`` and the target's position
+    among the top k are bit-identical to the fp32 path's for the same hidden rows; with ``full_rank`` a target OUTSIDE the top k
+    gets the rank of the bf16 count sweep."""
+    want_full = full_rank and target is not None
+    o = ops.tc_score_candidates(hb, wb, None, k, 64, target=target if want_full else None)
+    r = ops.topk_rescore(m_rows, w32, b32, o["cand_idx"], o["cand_val"], k, norm_bound, target, cand_bound=o["bound"])
+    rank = r["rank"]
+    out = dict(topk_val=r["topk_val"], topk_idx=r["topk_idx"], target_score=r["target_score"], n_uncertified=r["n_flagged"])
+    if want_full:
+        c = ops.tc_score_topk(hb, wb, None, 0, target=target, target_score_in=o["target_score"], capture_target=False)
+        out["n_greater"], out["n_tie_lower"] = c["n_greater"], c["n_tie_lower"]
+        full = (c["n_greater"] + c["n_tie_lower"] + 1).to(torch.int32)
+        rank = torch.where(rank <= k, rank, torch.clamp(full, min=k + 1))
+    ops.score_topk_flagged(m_rows, w32, b32, target, r["target_score"], k, r["row_flag"], r["topk_val"], r["topk_idx"], rank)
+    out["rank"] = rank
     return out
 
 

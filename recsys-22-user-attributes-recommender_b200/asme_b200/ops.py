@@ -648,6 +648,73 @@ def tc_attn_bwd(qkv16, key_valid, B, S, heads, causal, ctx16, d_ctx16, stats, ke
     return d_qkv
 
 
+def table_norm_bound(w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """(3) fp32: max row L2 norm of the catalog table, max |bias|, max row norm of (table - bf16(table)) -- the constants of the
+    exact top-k certificate"""
+    w = _f32(w, "table")
+    out = torch.empty(3, dtype=torch.float32, device=w.device)
+    _lib.call("asme_b200_table_norm_bound", _p(w), w.shape[0], w.shape[1], _p(bias), _p(out), _stream())
+    return out
+
+
+def tc_score_candidates(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, k_out: int = 64, target=None, v0: int = 0):
+    """candidates for an exact top-``k``: dict(cand_val, cand_idx (R,k_out) best first by bf16 score, bound (R) = upper bound of the bf16
+    score of every item in none of the sweep's lists, target_score (R) bf16 score of the target or None)"""
+    hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
+    R, Kp = hb.shape
+    Vloc = wb.shape[0]
+    dev = hb.device
+    k_out = max(k, min(int(k_out), 64))
+    val = torch.empty(R, k_out, dtype=torch.float32, device=dev)
+    idx = torch.empty(R, k_out, dtype=torch.int32, device=dev)
+    bound = torch.empty(R, dtype=torch.float32, device=dev)
+    tgt = None if target is None else _i64(target)
+    ts = torch.zeros(R, dtype=torch.float32, device=dev) if tgt is not None else None
+    ws = workspace(_lib.query("asme_b200_tc_score_candidates_workspace_bytes", R, Kp, Vloc, k, k_out), dev)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={Vloc},H={Kp},k={k},kout={k_out}"
+    _lib.call("asme_b200_tc_score_candidates", _p(hb), R, Kp, _p(wb), _p(bias), v0, Vloc, _p(tgt), k, k_out, _p(val), _p(idx), _p(bound),
+              _p(ts), _p(ws), ws.numel(), _stream())
+    return dict(cand_val=val, cand_idx=idx, bound=bound, target_score=ts)
+
+
+def topk_rescore(h: torch.Tensor, w: torch.Tensor, bias, cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int,
+                 norm_bound: torch.Tensor, target=None, v0: int = 0, want_rank: bool = True, cand_bound=None):
+    """exact top-k from the bf16 sweep's candidates: re-score in fp32 (the fp32 path's arithmetic), order (score desc, id asc),
+    certify.  returns dict(topk_val (R,k), topk_idx (R,k), target_score (R) or None, rank (R) or None [position among the exact top
+    k, k+1 otherwise], row_flag (R) int32 [1 = not certified: run :func:`score_topk_flagged`], n_flagged (1) int32)"""
+    h, w = _f32(h, "hidden rows"), _f32(w, "table")
+    R, H = h.shape
+    KC = cand_idx.shape[1]
+    dev = h.device
+    val = torch.empty(R, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(R, k, dtype=torch.int32, device=dev)
+    tgt = None if target is None else _i64(target)
+    ts = torch.zeros(R, dtype=torch.float32, device=dev) if tgt is not None else None
+    rank = torch.empty(R, dtype=torch.int32, device=dev) if (tgt is not None and want_rank) else None
+    flag = torch.empty(R, dtype=torch.int32, device=dev)
+    n_flagged = torch.empty(1, dtype=torch.int32, device=dev)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},H={H},KC={KC},k={k}"
+    _lib.call("asme_b200_topk_rescore", _p(h), R, H, _p(w), _p(bias), v0, w.shape[0], _p(cand_idx.contiguous()), _p(_f32(cand_val)),
+              _p(cand_bound), KC, k,
+              _p(norm_bound), _p(tgt), _p(val), _p(idx), _p(ts), _p(rank), _p(flag), _p(n_flagged), _stream())
+    return dict(topk_val=val, topk_idx=idx, target_score=ts, rank=rank, row_flag=flag, n_flagged=n_flagged)
+
+
+def score_topk_flagged(h, w, bias, target, target_score, k: int, row_flag, topk_val, topk_idx, rank=None, v0: int = 0):
+    """the exact fp32 sweep for the rows with ``row_flag != 0`` only; overwrites their rows of topk_val / topk_idx (/ rank = exact
+    full rank).  With no flagged row this is a few microseconds of empty CTAs -- decided on the device, no host round trip."""
+    h, w = _f32(h), _f32(w)
+    R, H = h.shape
+    ws = workspace(_lib.query("asme_b200_score_topk_flagged_workspace_bytes", R, w.shape[0]), h.device)
+    tgt = None if target is None else _i64(target)
+    if _lib.timing is not None:
+        _lib.note = f"R={R},V={w.shape[0]},H={H},k={k},flagged=1"
+    _lib.call("asme_b200_score_topk_flagged", _p(h), R, H, _p(w), _p(bias), v0, w.shape[0], _p(tgt), _p(target_score), k, _p(row_flag),
+              _p(topk_val), _p(topk_idx), _p(rank), _p(ws), ws.numel(), _stream())
+
+
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor, k: int):
     """vals/idx: (G,R,k) partial lists -> merged (R,k)"""
     vals, idx = _f32(vals), idx.contiguous()

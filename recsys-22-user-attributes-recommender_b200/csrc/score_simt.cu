@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_topk_kernel(const float* __r
                                                                 const float* __restrict__ target_score, int k,
                                                                 int tiles_per_split, float* __restrict__ pv,
                                                                 int* __restrict__ pi, int* __restrict__ pg,
-                                                                int* __restrict__ pt) {
+                                                                int* __restrict__ pt, const int32_t* __restrict__ row_flag) {
     extern __shared__ __align__(16) float smem[];
     const int ld = H + 4;
     float* hs = smem;
@@ -162,6 +162,10 @@ __global__ void __launch_bounds__(SC_THREADS) score_topk_kernel(const float* __r
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16, warp = tid / 32, lane = tid % 32;
     const int m0 = blockIdx.x * TS;
     const int split = blockIdx.y;
+    if (row_flag != nullptr) {       // only row tiles that hold a flagged row are swept (exact re-run of uncertified rows)
+        const int any = __syncthreads_or(tid < TS && m0 + tid < R && row_flag[m0 + tid] != 0);
+        if (!any) return;
+    }
     const int tile_begin = split * tiles_per_split;
     const int tile_end = min(ceil_div(Vloc, TS), tile_begin + tiles_per_split);
 
@@ -224,10 +228,12 @@ __global__ void __launch_bounds__(SC_THREADS) score_topk_kernel(const float* __r
 // merge `parts` sorted 32-wide (or k-wide) lists per row; one warp per row
 __global__ void topk_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, const int* __restrict__ pg,
                                   const int* __restrict__ pt, int parts, int R, int width, int k, float* __restrict__ out_v,
-                                  int32_t* __restrict__ out_i, int32_t* __restrict__ out_g, int32_t* __restrict__ out_t) {
+                                  int32_t* __restrict__ out_i, int32_t* __restrict__ out_g, int32_t* __restrict__ out_t,
+                                  const int32_t* __restrict__ row_flag = nullptr, int32_t* __restrict__ rank_out = nullptr) {
     const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (row >= R) return;
+    if (row_flag != nullptr && row_flag[row] == 0) return;      // rows that were not re-run keep what they hold
     float lv = -INFINITY, thr_v = -INFINITY;
     int li = INT_MAX, thr_i = INT_MAX;
     int g = 0, t = 0;
@@ -244,7 +250,10 @@ __global__ void topk_merge_kernel(const float* __restrict__ pv, const int* __res
         out_v[(size_t)row * k + lane] = lv;
         out_i[(size_t)row * k + lane] = li == INT_MAX ? -1 : li;
     }
-    if (pg && lane == 0) { out_g[row] = g; out_t[row] = t; }
+    if (pg && lane == 0) {
+        if (out_g) { out_g[row] = g; out_t[row] = t; }
+        if (rank_out) rank_out[row] = g + t + 1;
+    }
 }
 
 extern "C" size_t asme_b200_score_topk_workspace_bytes(int R, int Vloc, int k) {
@@ -253,22 +262,50 @@ extern "C" size_t asme_b200_score_topk_workspace_bytes(int R, int Vloc, int k) {
     return splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int));
 }
 
+static int score_topk_impl(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                           const int64_t* target, const float* target_score, int k, float* topk_val,
+                           int32_t* topk_idx, int32_t* n_greater, int32_t* n_tie_lower, void* ws,
+                           size_t ws_bytes, const int32_t* row_flag, int32_t* rank_out, asme_stream_t stream);
 extern "C" int asme_b200_score_topk_rank(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
                                          const int64_t* target, const float* target_score, int k, float* topk_val,
                                          int32_t* topk_idx, int32_t* n_greater, int32_t* n_tie_lower, void* ws,
                                          size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(target == nullptr || (n_greater && n_tie_lower), "score_topk_rank: rank outputs missing");
+    return score_topk_impl(Hrows, R, H, W, bias, v0, Vloc, target, target_score, k, topk_val, topk_idx, n_greater, n_tie_lower, ws, ws_bytes,
+                           nullptr, nullptr, stream);
+}
+// The exact sweep for the rows a certificate could not cover (asme_b200_topk_rescore: row_flag != 0): only row tiles holding a
+// flagged row run, only flagged rows are written -- topk_val / topk_idx (and rank = exact full rank, when given) of the others
+// keep what they hold.  Everything is decided on the device: with no flagged row the launch is a few microseconds of empty CTAs.
+extern "C" size_t asme_b200_score_topk_flagged_workspace_bytes(int R, int Vloc) {
+    const size_t splits = ceil_div(Vloc, TS) < ASME_NUM_SMS ? ceil_div(Vloc, TS) : ASME_NUM_SMS;
+    return splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int));
+}
+extern "C" int asme_b200_score_topk_flagged(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                                            const int64_t* target, const float* target_score, int k, const int32_t* row_flag,
+                                            float* topk_val, int32_t* topk_idx, int32_t* rank, void* ws, size_t ws_bytes,
+                                            asme_stream_t stream) {
+    ASME_REQUIRE(row_flag, "score_topk_flagged: null row_flag");
+    ASME_REQUIRE(!rank || target, "score_topk_flagged: a rank needs the target");
+    return score_topk_impl(Hrows, R, H, W, bias, v0, Vloc, target, target_score, k, topk_val, topk_idx, nullptr, nullptr, ws, ws_bytes,
+                           row_flag, rank, stream);
+}
+static int score_topk_impl(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
+                           const int64_t* target, const float* target_score, int k, float* topk_val,
+                           int32_t* topk_idx, int32_t* n_greater, int32_t* n_tie_lower, void* ws,
+                           size_t ws_bytes, const int32_t* row_flag, int32_t* rank_out, asme_stream_t stream) {
     ASME_REQUIRE(Hrows && W && topk_val && topk_idx, "score_topk_rank: null argument");
     ASME_REQUIRE(k >= 1 && k <= 32, "score_topk_rank: k=%d unsupported (1..32)", k);
     ASME_REQUIRE((target == nullptr) == (target_score == nullptr), "score_topk_rank: target and target_score go together");
-    ASME_REQUIRE(target == nullptr || (n_greater && n_tie_lower), "score_topk_rank: rank outputs missing");
     int rc = check_score(R, H, Vloc);
     if (rc) return rc;
     if (R == 0) return ASME_OK;
-    if (ws_bytes < asme_b200_score_topk_workspace_bytes(R, Vloc, k)) {
+    // few row tiles are expected to be live in the flagged variant: split the catalog over the whole machine for each of them
+    const int splits = row_flag ? (ceil_div(Vloc, TS) < ASME_NUM_SMS ? ceil_div(Vloc, TS) : ASME_NUM_SMS) : item_splits(R, Vloc);
+    if (ws_bytes < (size_t)splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int))) {
         asme_set_error("score_topk_rank: workspace too small");
         return ASME_ERR_WORKSPACE;
     }
-    const int splits = item_splits(R, Vloc);
     const int tiles_per_split = ceil_div(ceil_div(Vloc, TS), splits);
     float* pv = (float*)ws;
     int* pi = (int*)(pv + (size_t)splits * R * 32);
@@ -279,10 +316,10 @@ extern "C" int asme_b200_score_topk_rank(const float* Hrows, int R, int H, const
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     score_topk_kernel<<<dim3(ceil_div(R, TS), splits), SC_THREADS, smem, st>>>(Hrows, R, H, W, bias, v0, Vloc, target,
-                                                                               target_score, k, tiles_per_split, pv, pi, pg, pt);
+                                                                               target_score, k, tiles_per_split, pv, pi, pg, pt, row_flag);
     ASME_LAUNCH_OK();
     topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(pv, pi, target ? pg : nullptr, pt, splits, R, 32, k, topk_val, topk_idx,
-                                                      n_greater, n_tie_lower);
+                                                      n_greater, n_tie_lower, row_flag, rank_out);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }

@@ -182,6 +182,8 @@ struct ScoreTcArgs {
     float* ps;                   // CE: partial sum-exp   [parts][R]
     float* captured;             // [R]: score of the target column as computed by this kernel (owner writes)
     const int32_t* n_live;       // device count of live rows (row selections of capacity R) or NULL: row tiles past it exit at once
+    int tile_step;               // 0 / 1: a split sweeps a contiguous range of tiles; S > 1: split s sweeps tiles s, s+S, s+2S, ... (round
+                                 // robin: whatever order the catalog is in, every split sees an even share of the best items)
 };
 
 struct __align__(8) ScoreTcBarriers {
@@ -305,8 +307,9 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int m0 = blockIdx.x * BM;
     const int split = blockIdx.y;
-    const int t0 = min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
-    const int t1 = min(a.n_tiles, split * a.tiles_per_split + a.tile_hi);
+    const int tstep = a.tile_step > 1 ? a.tile_step : 1;
+    const int t0 = tstep > 1 ? min(a.n_tiles, split + a.tile_lo * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
+    const int t1 = tstep > 1 ? min(a.n_tiles, split + a.tile_hi * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_hi);
     if (a.n_live != nullptr && m0 >= __ldg(a.n_live)) return;      // whole CTA, before any barrier / TMEM allocation (never with PAIR)
 
     if (warp == 0 && lane == 0) {
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
             int s = 0;                                    // ring slot and its phase, advanced without integer division
             uint32_t ph = 0;
-            for (int t = t0; t < t1; ++t) {
+            for (int t = t0; t < t1; t += tstep) {
                 for (int c = 0; c < kch; ++c) {
                     mbar_wait(&bars->empty[s], ph ^ 1u);
                     const bool tail = a.tail16 && c == kch - 1;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             const uint64_t bdesc0 = smem_desc_sw128(smem_u32(sB));
             int i = 0, s = 0;
             uint32_t ph = 0;
-            for (int t = t0; t < t1; ++t, ++i) {
+            for (int t = t0; t < t1; t += tstep, ++i) {
                 const int as = i & 1;
                 const uint32_t aph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bars->tempty[as], aph ^ 1u);
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         float run_m = -INFINITY, run_s = 0.f;     // CE: running max (in log2 units) and sum of exp2
 
         int i = 0;
-        for (int t = t0; t < t1; ++t, ++i) {
+        for (int t = t0; t < t1; t += tstep, ++i) {
             const int as = i & 1;
             const uint32_t aph = (uint32_t)(i >> 1) & 1u;
             mbar_wait_lean(&bars->tfull[as], aph);
@@ -775,6 +778,84 @@ static int launch_merge(const float* pv, const int* pi, const int* pg, const int
     return ASME_OK;
 }
 
+// Candidate merge (exact top-k, csrc/rescore.cu): the union of the per-part lists is merged into the k_out best by bf16 score, and
+// ``bound[row]`` = an upper bound of the bf16 score of EVERY item that is in none of the row's part lists.  Such an item was dropped
+// by a sorted list that was full (its score is <= that list's last entry; the last entry of a list only grows), or it never passed
+// the sample threshold: bound = max(last entry of every full part list, last entry of a full lane list that folded several parts,
+// threshold).  Entries cut by the k_out limit are bounded by the k_out-th output itself (the caller adds that).
+template <int KC>
+__global__ void __launch_bounds__(128) tc_cand_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, int parts, int R, int k,
+                                                            int k_out, const float* __restrict__ thr_init, int thr_stride, int thr_col,
+                                                            float* __restrict__ out_v, int32_t* __restrict__ out_i,
+                                                            float* __restrict__ bound) {
+    const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= R) return;
+    constexpr int KL = KC;
+    float lv[KL];
+    int li[KL];
+#pragma unroll
+    for (int p = 0; p < KL; ++p) { lv[p] = -INFINITY; li[p] = INT_MAX; }
+    float tau = -INFINITY;
+    int folded = 0;
+    for (int p = lane; p < parts; p += 32, ++folded) {
+        const size_t o = ((size_t)p * R + row) * k;
+        float cv[KL];
+        int ci[KL];
+#pragma unroll
+        for (int j = 0; j < KL; ++j) {
+            cv[j] = j < k ? __ldg(pv + o + j) : -INFINITY;
+            ci[j] = j < k ? __ldg(pi + o + j) : INT_MAX;
+        }
+#pragma unroll
+        for (int j = 0; j < KL; ++j)
+            if (j == k - 1 && ci[j] != INT_MAX) tau = fmaxf(tau, cv[j]);          // a full part list: whatever it dropped is <= its tail
+#pragma unroll
+        for (int j = 0; j < KL; ++j) {
+            if (ci[j] == INT_MAX || !tc_better(cv[j], ci[j], lv[KL - 1], li[KL - 1])) break;
+            tie_insert<KL>(lv, li, cv[j], ci[j]);
+        }
+    }
+    if (folded > 1 && li[KL - 1] != INT_MAX) tau = fmaxf(tau, lv[KL - 1]);        // entries this lane's fold pushed out
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) tau = fmaxf(tau, __shfl_xor_sync(0xffffffffu, tau, s));
+    if (thr_init != nullptr) tau = fmaxf(tau, thr_init[(size_t)row * thr_stride + thr_col]);
+    for (int r = 0; r < k_out; ++r) {
+        float bv = lv[0];
+        int bi = li[0];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, bv, s);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, s);
+            if (tc_better(v2, i2, bv, bi)) { bv = v2; bi = i2; }
+        }
+        if (bi != INT_MAX && li[0] == bi) {
+#pragma unroll
+            for (int p = 0; p < KL - 1; ++p) { lv[p] = lv[p + 1]; li[p] = li[p + 1]; }
+            lv[KL - 1] = -INFINITY;
+            li[KL - 1] = INT_MAX;
+        }
+        if (lane == 0) {
+            out_v[(size_t)row * k_out + r] = bv;
+            out_i[(size_t)row * k_out + r] = bi == INT_MAX ? -1 : bi;
+        }
+    }
+    if (lane == 0) bound[row] = tau;
+}
+// classic candidate path: (R, kc) lists -> (R, k_out) rows with empty tail slots; bound = -inf (the list is the true bf16 top kc)
+__global__ void spread_candidates_kernel(const float* __restrict__ src_v, const int32_t* __restrict__ src_i, int R, int kc, int k_out,
+                                         float* __restrict__ dst_v, int32_t* __restrict__ dst_i, float* __restrict__ bound) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * k_out) return;
+    const int r = (int)(i / k_out), c = (int)(i % k_out);
+    if (src_v != dst_v) {
+        dst_v[i] = c < kc ? src_v[(size_t)r * kc + c] : -INFINITY;
+        dst_i[i] = c < kc ? src_i[(size_t)r * kc + c] : -1;
+    }
+    // a full kc-entry list cut the catalog: everything outside it scores at most its last entry; a shorter list holds everything
+    if (c == 0) bound[r] = (kc < k_out && src_i[(size_t)r * kc + kc - 1] >= 0) ? src_v[(size_t)r * kc + kc - 1] : -INFINITY;
+}
+
 // CE partials: (max in log2 units, sum of exp2) per part -> natural-log row max and sum-exp
 __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __restrict__ ps, int parts, int R,
                                    float* __restrict__ row_max, float* __restrict__ row_sumexp, const int32_t* __restrict__ n_live) {
@@ -1008,6 +1089,118 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
     if (rc) return rc;
     return launch_merge(topk ? a.pv : nullptr, a.pi, count ? a.pg : nullptr, a.pt, total_parts, R, k, topk_val, topk_idx, n_greater,
                         n_tie_lower, st);
+}
+
+// Candidate generation for the exact top-k (csrc/rescore.cu).  With >= 4 catalog splits the sweep keeps its cheap k-entry thread
+// lists (the 20- / 32-entry lists need the two-warpgroup epilogue and cost up to 2x) and the k_out candidates come from the UNION of
+// the splits' lists: tiles are dealt round robin, so every split sees an even share of the best items however the catalog is ordered,
+// and ``bound`` tells the certificate what the lists may have dropped.  With fewer splits (very many rows) the thread lists hold
+// k_out entries themselves and the merged list is the true bf16 top-k_out (bound = -inf).
+// Union mode needs enough parts that no single part holds k of the row's best ~2k items (the certificate fails for a row where one
+// does): with P parts dealt round robin that happens with probability ~ P C(2k, k) P^-k -- 1e-7 per row at P = 16, k = 10.  So the
+// catalog is cut into at least CAND_MIN_PARTS splits even when fewer would fill the machine (more CTAs than SMs run in waves; every
+// CTA still sweeps many tiles), and catalogs of fewer tiles than that take the classic path with k_out-entry thread lists.
+#define CAND_MIN_PARTS 16
+static int cand_list_len(int k) { return k <= 2 ? 5 : 10; }      // thread-list entries in union mode: at least 2k spare-ish, 5 or 10
+static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* use_union) {
+    int rc = make_plan(R, Kp, Vloc, p, true);
+    if (rc) return rc;
+    *use_union = k <= 10 && !p->pair && p->n_tiles >= CAND_MIN_PARTS;
+    if (*use_union && p->splits < CAND_MIN_PARTS) {
+        p->tiles_per_split = ceil_div(p->n_tiles, CAND_MIN_PARTS);
+        p->splits = ceil_div(p->n_tiles, p->tiles_per_split);
+        p->parts = p->splits;
+    }
+    return ASME_OK;
+}
+extern "C" size_t asme_b200_tc_score_candidates_workspace_bytes(int R, int Kp, int Vloc, int k, int k_out) {
+    const int kk = k > k_out ? k : k_out;
+    if (R < 1) R = 1;
+    ScorePlan p;
+    bool use_union = false;
+    if (make_cand_plan(R, Kp, Vloc, k, &p, &use_union)) return 0;
+    const size_t classic = asme_b200_tc_score_topk_workspace_bytes(R, Kp, Vloc, 32) + (size_t)R * 32 * 8;
+    const size_t uni = (size_t)2 * (p.splits + 1) * MAX_EPI_WGS * R * ((size_t)kk * 8 + 8) + (size_t)R * kk * 8;
+    return classic > uni ? classic : uni;
+}
+extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+                                             const int64_t* target, int k, int k_out, float* cand_val, int32_t* cand_idx, float* bound,
+                                             float* target_score_out, void* ws, size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(Hb && Wb && cand_val && cand_idx && bound, "tc_score_candidates: null argument");
+    ASME_REQUIRE(k >= 1 && k <= 32 && k <= k_out && k_out <= 64, "tc_score_candidates: k=%d k_out=%d unsupported (1 <= k <= 32, k <= k_out <= 64)", k, k_out);
+    ASME_REQUIRE(!target_score_out || target, "tc_score_candidates: target_score_out needs target");
+    ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_candidates: bias must be 16-byte aligned");
+    if (R == 0) return ASME_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    ScorePlan p;
+    bool use_union = false;
+    int rc = make_cand_plan(R, Kp, Vloc, k, &p, &use_union);
+    if (rc) return rc;
+    const int kl = cand_list_len(k);          // entries of the sweep's lists (>= k)
+    if (!use_union) {          // classic: the true bf16 top 32 (the longest thread lists); unused candidate slots stay empty
+        const int kc = k_out < 32 ? k_out : 32;
+        float* tmp_v = cand_val;
+        int32_t* tmp_i = cand_idx;
+        if (kc != k_out) {     // the sweep writes (R, kc) rows: stage them behind the sweep's own scratch and spread them out afterwards
+            const size_t off = asme_b200_tc_score_topk_workspace_bytes(R, Kp, Vloc, 32);
+            ASME_REQUIRE(ws_bytes >= off + (size_t)R * kc * 8, "tc_score_candidates: workspace too small");
+            tmp_v = (float*)((uint8_t*)ws + off);
+            tmp_i = (int32_t*)(tmp_v + (size_t)R * kc);
+        }
+        rc = asme_b200_tc_score_topk(Hb, R, Kp, Wb, bias, v0, Vloc, target, nullptr, kc, tmp_v, tmp_i, target_score_out, nullptr,
+                                     nullptr, ws, ws_bytes, stream);
+        if (rc) return rc;
+        spread_candidates_kernel<<<ceil_div((long long)R * k_out, 256), 256, 0, st>>>(tmp_v, tmp_i, R, kc, k_out, cand_val, cand_idx, bound);
+        ASME_LAUNCH_OK();
+        return ASME_OK;
+    }
+    ASME_REQUIRE(ws_bytes >= asme_b200_tc_score_candidates_workspace_bytes(R, Kp, Vloc, k, k_out), "tc_score_candidates: workspace too small");
+    CUtensorMap tmA, tmB;
+    rc = asme_tc_make_tmap_bf16(&tmA, Hb, R, Kp, Kp, BM);
+    if (rc) return rc;
+    rc = asme_tc_make_tmap_bf16(&tmB, Wb, Vloc, Kp, Kp, BN);
+    if (rc) return rc;
+    rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
+    if (rc) return rc;
+    const int n_sample = sample_tiles(p);
+    const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
+    ScoreTcArgs a{};
+    a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = kl; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap;
+    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_step = p.splits;
+    a.bias = bias; a.target = target; a.target_score = nullptr; a.thr_floor = g_thr_floor;
+    a.pv = (float*)ws;
+    a.pi = (int*)(a.pv + (size_t)total_parts * R * kl);
+    a.pg = a.pi + (size_t)total_parts * R * kl;
+    a.pt = a.pg + (size_t)total_parts * R;
+    float* thr_v = (float*)(a.pt + (size_t)total_parts * R);
+    int32_t* thr_i = (int32_t*)(thr_v + (size_t)R * kl);
+    a.ps = nullptr;
+    const float* thr_init = nullptr;
+    const float* fpv = a.pv;
+    const int* fpi = a.pi;
+    if (n_sample > 0) {
+        a.tile_lo = 0; a.tile_hi = n_sample; a.part0 = 0; a.thr_init = nullptr; a.sample_mode = 1; a.captured = nullptr;
+        rc = launch_topk(tmA, tmB, a, p, true, false, st);
+        if (rc) return rc;
+        rc = launch_merge(a.pv, a.pi, nullptr, nullptr, p.parts, R, kl, thr_v, thr_i, nullptr, nullptr, st);
+        if (rc) return rc;
+        a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = p.parts; a.sample_mode = 0;
+        a.thr_init = thr_v; a.thr_stride = kl; a.thr_col = kl - 1;
+        thr_init = thr_v;
+        fpv = a.pv + (size_t)p.parts * R * kl;
+        fpi = a.pi + (size_t)p.parts * R * kl;
+    } else {
+        a.tile_lo = 0; a.tile_hi = p.tiles_per_split; a.part0 = 0; a.thr_init = nullptr;
+    }
+    a.captured = target_score_out;
+    rc = launch_topk(tmA, tmB, a, p, true, false, st);
+    if (rc) return rc;
+#define CAND_MERGE(KC) tc_cand_merge_kernel<KC><<<ceil_div(R, 4), 128, 0, st>>>(fpv, fpi, p.parts, R, kl, k_out, thr_init, kl, kl - 1, cand_val, cand_idx, bound)
+    if (kl == 5) CAND_MERGE(5);
+    else CAND_MERGE(10);
+#undef CAND_MERGE
+    ASME_LAUNCH_OK();
+    return ASME_OK;
 }
 
 // diagnostic: the scoring sweep with an empty epilogue (upper bound of what the TMA -> MMA -> TMEM pipeline sustains)
