@@ -262,6 +262,11 @@ int asme_b200_score_ce_partial(const float* Hrows, int R, int H, const float* W,
 int asme_b200_ce_loss_from_partials(const float* row_max, const float* row_sumexp, const float* target_logit, int R,
                                     float* lse /*R*/, float* loss_sum /*1, +=*/, const int32_t* n_live,
                                     float* loss_mean /*1 or NULL: loss_sum / live rows*/, asme_stream_t stream);
+/* vocab-sharded scoring: merge of the shards' softmax statistics -- pm / ps (G,R) per-shard row maxima / sum-exps -> those of the
+ * whole catalog; and a shard's sum-exp re-expressed against the all-reduced row maximum (row_sumexp * exp(row_max - global_max)) */
+int asme_b200_ce_combine(const float* pm, const float* ps, int G, int R, float* row_max, float* row_sumexp, asme_stream_t stream);
+int asme_b200_ce_rescale(const float* row_sumexp, const float* row_max, const float* global_max, int R, float* out,
+                         asme_stream_t stream);
 /* backward: dlogit = (softmax - onehot) * scale; dH (R,H) = dlogit W (overwritten; shards all-reduce),
  * dW (Vloc,H) += dlogit^T H, dbias (Vloc) += colsum(dlogit). */
 size_t asme_b200_score_ce_bwd_workspace_bytes(int R, int H, int Vloc);

@@ -82,6 +82,8 @@ _PROTOTYPES = {
     "asme_b200_dense_ranking": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "asme_b200_score_ce_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
+    "asme_b200_ce_combine": (c_int, [P, P, c_int, c_int, P, P, P]),
+    "asme_b200_ce_rescale": (c_int, [P, P, P, c_int, P, P]),
     "asme_b200_ce_loss_from_partials": (c_int, [P, P, P, c_int, P, P, P, P, P]),
     "asme_b200_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_score_ce_bwd": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P, P]),

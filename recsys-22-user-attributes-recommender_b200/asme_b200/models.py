@@ -552,13 +552,15 @@ class TransformerRecommenderModel(ArenaModule):
 
 
 def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, rows: Optional[torch.Tensor] = None,
-                           select: str = "mask", mask_id: int = MASK_TOKEN_ID, full_rank: bool = False, group=None):
-    """vocab-sharded variant of :meth:`evaluate_rank` (asme_b200.sharded): this rank encodes ITS users, all ranks exchange the
-    selected hidden rows, every rank scores all users against its own slice of the catalog on the tensor cores, and the
-    per-shard top-k lists / target scores are merged with three NCCL calls.  Returns the rows of this rank's users."""
+                           select: str = "mask", mask_id: int = MASK_TOKEN_ID, full_rank: bool = False, group=None,
+                           with_loss: bool = False, pad_id: int = PAD_TOKEN_ID, rows_one_per_sequence: bool = False):
+    """vocab-sharded variant of :meth:`evaluate_rank` (asme_b200.sharded): this rank encodes ITS users, one all-gather hands every
+    rank all selected hidden rows, every rank scores all users against its own slice of the catalog on the tensor cores (exact
+    lists, csrc/rescore.cu), one all-to-all brings every rank the slices' results for its own users.  Same keys as
+    :meth:`evaluate_rank` incl. ``loss`` / ``lse`` (``with_loss``: the softmax statistics of the slices are merged too)."""
     import torch.distributed as dist
     from . import sharded
-    one = rows is None
+    one = rows is None or rows_one_per_sequence
     if rows is None:
         rows = mask_position_rows(seq, mask_id) if select == "mask" else last_position_rows(seq, padding_mask)
     m_rows, _ = self.modify(self.encode_rows(seq, padding_mask, attrs, rows, one_per_sequence=one))
@@ -566,8 +568,16 @@ def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, 
     g = dist.get_rank(group) if dist.is_initialized() else 0
     wb, folded = self.projection_operands_folded()          # bias (if any) rides in two extra K columns of the table
     v0, v1 = sharded.shard_range(wb.shape[0], G, g)
-    return sharded.sharded_topk_rank(m_rows, target, k, sharded.tc_local_scorer(wb[v0:v1], None, v0, folded), sharded.tc_merge,
-                                     full_rank=full_rank, group=group)
+    exact = None
+    if self.exact_topk:
+        w32, b32 = self.projection_operands()
+        stamp = (self._arena.version, self._arena.flat._version, w32.data_ptr(), v0, v1)
+        cache = getattr(self, "_shard_norm_bound", None)
+        if cache is None or cache[0] != stamp:
+            self._shard_norm_bound = (stamp, ops.table_norm_bound(w32[v0:v1], None if b32 is None else b32[v0:v1]))
+        exact = (w32[v0:v1], None if b32 is None else b32[v0:v1], self._shard_norm_bound[1])
+    return sharded.sharded_topk_rank(m_rows, target, k, sharded.tc_local_scorer(wb[v0:v1], None, v0, folded, exact=exact), sharded.tc_merge,
+                                     full_rank=full_rank, group=group, with_loss=with_loss, pad_id=pad_id, combine_ce=sharded.tc_combine_ce)
 
 
 TransformerRecommenderModel.evaluate_rank_sharded = torch.no_grad()(_evaluate_rank_sharded)

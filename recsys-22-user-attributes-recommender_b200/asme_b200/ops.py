@@ -768,6 +768,23 @@ def ce_loss_from_partials(rmax, rsum, tl, loss_sum: torch.Tensor, n_live=None, l
     return lse
 
 
+def ce_combine(rmax: torch.Tensor, rsum: torch.Tensor):
+    """(G,R) per-shard row maxima / sum-exps -> (R) maxima / sum-exps over the whole catalog"""
+    rmax, rsum = _f32(rmax), _f32(rsum)
+    G, R = rmax.shape
+    m = torch.empty(R, dtype=torch.float32, device=rmax.device)
+    s = torch.empty_like(m)
+    _lib.call("asme_b200_ce_combine", _p(rmax), _p(rsum), G, R, _p(m), _p(s), _stream())
+    return m, s
+
+
+def ce_rescale(rsum: torch.Tensor, rmax: torch.Tensor, gmax: torch.Tensor) -> torch.Tensor:
+    """rsum * exp(rmax - gmax): a shard's sum-exp against the all-reduced row maximum"""
+    out = torch.empty_like(rsum)
+    _lib.call("asme_b200_ce_rescale", _p(_f32(rsum)), _p(_f32(rmax)), _p(_f32(gmax)), rsum.numel(), _p(out), _stream())
+    return out
+
+
 def score_ce_bwd(h, w, bias, target, lse, scale: float, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
                  need_dh: bool = True, v0: int = 0, n_live=None):
     h, w = _f32(h), _f32(w)

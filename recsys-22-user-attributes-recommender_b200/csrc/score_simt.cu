@@ -457,9 +457,37 @@ __global__ void ce_combine_kernel(const float* __restrict__ pm, const float* __r
     for (int s = 0; s < splits; ++s) {
         const float ms = pm[(size_t)s * R + r];
         if (ms > -INFINITY) sum += ps[(size_t)s * R + r] * expf(ms - m);
-        tl += ptl[(size_t)s * R + r];
+        if (ptl) tl += ptl[(size_t)s * R + r];
     }
-    row_max[r] = m; row_sumexp[r] = sum; target_logit[r] = tl;
+    row_max[r] = m; row_sumexp[r] = sum;
+    if (target_logit) target_logit[r] = tl;
+}
+
+// merge of per-shard softmax statistics (vocab-sharded scoring): pm / ps (G, R) row maxima and sum-exps over each shard's catalog slice
+// -> the row maximum and sum-exp over the whole catalog.  The same arithmetic that merges the item splits of one sweep.
+extern "C" int asme_b200_ce_combine(const float* pm, const float* ps, int G, int R, float* row_max, float* row_sumexp,
+                                    asme_stream_t stream) {
+    ASME_REQUIRE(pm && ps && row_max && row_sumexp && G >= 1, "ce_combine: bad argument");
+    if (R == 0) return ASME_OK;
+    ce_combine_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(pm, ps, nullptr, G, R, row_max, row_sumexp, nullptr, nullptr);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+// out[r] = row_sumexp[r] * exp(row_max[r] - global_max[r]): a shard's sum-exp re-expressed against the all-reduced row maximum
+__global__ void ce_rescale_kernel(const float* __restrict__ rsum, const float* __restrict__ rmax, const float* __restrict__ gmax, int R,
+                                  float* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float m = rmax[r];
+    out[r] = m > -INFINITY ? rsum[r] * expf(m - gmax[r]) : 0.f;
+}
+extern "C" int asme_b200_ce_rescale(const float* row_sumexp, const float* row_max, const float* global_max, int R, float* out,
+                                    asme_stream_t stream) {
+    ASME_REQUIRE(row_sumexp && row_max && global_max && out, "ce_rescale: null argument");
+    if (R == 0) return ASME_OK;
+    ce_rescale_kernel<<<ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(row_sumexp, row_max, global_max, R, out);
+    ASME_LAUNCH_OK();
+    return ASME_OK;
 }
 
 extern "C" size_t asme_b200_score_ce_workspace_bytes(int R, int Vloc) {

@@ -26,7 +26,7 @@ def _free_port():
 def _oracle_scorer(w_shard, b_shard, v0):
     from oracle import asme_oracle as O
 
-    def score(hidden_all, target_all, k, target_score_in):
+    def score(hidden_all, target_all, k, target_score_in, want_ce=False):
         logits = (hidden_all.double() @ w_shard.double().t() + b_shard.double()).float().numpy()
         B, Vloc = logits.shape
         t = target_all.numpy() - v0
@@ -48,6 +48,10 @@ def _oracle_scorer(w_shard, b_shard, v0):
             cols = np.arange(Vloc)[None, :] + v0
             out["n_greater"] = torch.from_numpy((logits > st).sum(1).astype(np.int32))
             out["n_tie_lower"] = torch.from_numpy(((logits == st) & (cols < target_all.numpy()[:, None])).sum(1).astype(np.int32))
+        if want_ce:
+            lt = torch.from_numpy(logits)
+            out["rmax"] = lt.max(dim=1).values
+            out["rsum"] = torch.exp(lt - out["rmax"].unsqueeze(1)).sum(dim=1)
         return out
 
     return score
@@ -68,13 +72,33 @@ def _worker(rank, world, port, V, H, B_local, k, seed, result_path):
     out = sharded.sharded_topk_rank(h_all[sl], t_all[sl], k, _oracle_scorer(w[v0:v1], b[v0:v1], v0), sharded.merge_topk_host,
                                     full_rank=True)
     lite = sharded.sharded_topk_rank(h_all[sl], t_all[sl], k, _oracle_scorer(w[v0:v1], b[v0:v1], v0), sharded.merge_topk_host,
-                                     full_rank=False)
+                                     full_rank=False, with_loss=True, pad_id=0)
+    # vocab-sharded cross entropy of a training step: every rank scores the SAME rows against its slice
+    def partial():
+        logits = torch.from_numpy((h_all.double() @ w[v0:v1].double().t() + b[v0:v1].double()).float().numpy())
+        rmax = logits.max(dim=1).values
+        rsum = torch.exp(logits - rmax.unsqueeze(1)).sum(dim=1)
+        t = t_all - v0
+        own = (t >= 0) & (t < v1 - v0)
+        tl = torch.where(own, logits[torch.arange(len(t)), t.clamp(0, v1 - v0 - 1)], torch.zeros(len(t)))
+        return rmax, rsum, tl
+    ce = sharded.sharded_ce(partial, t_all, pad_id=0)
+
+    def backward(lse):          # dH of this slice for dlogit = (softmax - onehot) / n_rows
+        logits = h_all.double() @ w[v0:v1].double().t() + b[v0:v1].double()
+        p = torch.exp(logits - lse.double().unsqueeze(1))
+        t = t_all - v0
+        own = (t >= 0) & (t < v1 - v0)
+        p[torch.arange(len(t))[own], t[own]] -= 1.0
+        p = p * t_all.ne(0).double().unsqueeze(1) / float(ce["n_rows"])
+        return (p @ w[v0:v1].double()).float()
+    dh = sharded.sharded_ce_backward(backward, ce["lse"])
     metrics = build_metrics({"recall": [1, 5], "ndcg": [5], "mrr": [5]})
     for c in metrics.containers:
         for m in c.metrics:
             m.update_from_ranks(out["rank"])
     metrics.sync()
-    torch.save(dict(out=out, lite=lite, metrics={k_: float(v) for k_, v in metrics.compute().items()}, h=h_all, t=t_all, w=w, b=b),
+    torch.save(dict(out=out, lite=lite, ce={k_: v for k_, v in ce.items()}, dh=dh, metrics={k_: float(v) for k_, v in metrics.compute().items()}, h=h_all, t=t_all, w=w, b=b),
                f"{result_path}.{rank}")
     dist.destroy_process_group()
 
@@ -98,6 +122,21 @@ def test_sharded_topk_rank_two_ranks_gloo(tmp_path, V, k):
     np.testing.assert_array_equal(got_ts, logits[np.arange(len(t)), t.numpy()])
     lite_rank = np.concatenate([r["lite"]["rank"].numpy() for r in res])
     np.testing.assert_array_equal(lite_rank, np.minimum(want_rank, k + 1))
+    # validation loss of every rank's own users from the merged softmax statistics == CrossEntropyLoss(ignore_index=0) on the full logits
+    lt, tt = torch.from_numpy(logits), t
+    for r, part in enumerate(res):
+        sl = slice(r * B_local, (r + 1) * B_local)
+        want_loss = torch.nn.functional.cross_entropy(lt[sl], tt[sl], ignore_index=0)
+        assert abs(float(part["lite"]["loss"]) - float(want_loss)) < 1e-4 * max(1.0, abs(float(want_loss)))
+        torch.testing.assert_close(part["lite"]["lse"], torch.logsumexp(lt[sl], dim=1), rtol=1e-5, atol=1e-5)
+    # vocab-sharded training cross entropy: loss and lse identical on every rank and equal to the unsharded values; dH all-reduced
+    hd = h.clone().double().requires_grad_(True)
+    full_loss = torch.nn.functional.cross_entropy(hd @ w.double().t() + b.double(), tt, ignore_index=0)
+    full_loss.backward()
+    for part in res:
+        assert abs(float(part["ce"]["loss"]) - float(full_loss)) < 1e-5 * max(1.0, abs(float(full_loss)))
+        torch.testing.assert_close(part["ce"]["lse"], torch.logsumexp(lt, dim=1), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(part["dh"].double(), hd.grad, rtol=1e-4, atol=1e-6)
     # metric states all-reduced over the ranks == metrics of the whole batch
     want = {name: v / len(want_rank) for name, v in O.metrics_from_rank(want_rank, [1, 5]).items()}     # sums -> means
     for r in res:
