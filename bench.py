@@ -3,20 +3,24 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Workload (BASELINE.json configs[1], "C2"): BERT4Rec cloze TRAINING step at the ML-1M shape -- 3,706 items (+3
-special tokens, V=3709), max_seq_len 200, hidden 64, 2 layers, 2 heads, batch 256 per GPU, dropout 0.2, Adam
-(beta 0.99/0.998) with warm-up schedule: forward + fused scoring/cross-entropy + backward + optimizer step.
-Synthetic data of that shape (uniform ids, lengths U[20,200], right padded, 20 % cloze masks), random-init weights.
+BASELINE.json's metric has two halves, both measured here:
+
+  train (C2, the headline ``value``): BERT4Rec cloze TRAINING step at the ML-1M shape -- 3,706 items (+3 special tokens, V=3709),
+      max_seq_len 200, hidden 64, 2 layers, 2 heads, batch 256 per GPU, dropout 0.2, Adam (0.99/0.998) with warm-up schedule:
+      forward + fused scoring/cross-entropy + backward + optimizer step.  64 DISTINCT synthetic batches (uniform ids, lengths
+      U[20,200], right padded), cloze-masked on the GPU by the input pipeline (every batch has its own number of masked positions);
+      ONE CUDA graph serves all of them.
+  eval  (C5, the ``eval`` object -- last key of the line): full-catalog scoring + exact top-10 + Recall/NDCG@10 on a synthetic
+      1M-item catalog, hidden 128, seq 200, 1024 users per GPU per step; with N GPUs the catalog is vocab-sharded.
 
 One JSON line on stdout (rank 0):
-  value      train seqs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        the same metric through the public module API (MaskedTrainingModule.training_step -> loss.backward() ->
-             optimizer.step()) with HOST (pinned) input buffers: H2D copy of the step's inputs and D2H read of the loss
-             inside the timed region
-  roofline   dominant kernel of the step: algorithmic bytes (or flops) per launch / CUDA-event launch duration
-  cpu_baseline  the CPU oracle (a port of the reference's PyTorch path) timed on this box's host cores, bounded sample
-  eval       secondary: full-catalog evaluation users/s (Recall/NDCG@10) on the synthetic 1M-item catalog (C5)
---impl reference times the CPU oracle port with all host threads on the same workload (bounded sample per step).
+  value / ms_per_step   train seqs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e                   the same through the public module API with HOST (pinned) inputs: H2D copy of the step's item sequences,
+                        GPU cloze masking, the step, D2H read of the loss -- all inside the timed region
+  roofline              dominant kernel of the step: algorithmic bytes (or flops) per launch / CUDA-event launch duration
+  cpu_baseline          the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, full C2 batch
+  eval                  {value users/s, e2e, roofline (scoring sweep, flops on H=128), cpu_baseline (B=64), recall@10, checks}
+The per-kernel tables go to stderr.  --impl reference times the CPU oracle port with all host threads on the same workloads.
 """
 import argparse
 import json
@@ -27,7 +31,6 @@ import sys
 import threading
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,10 +39,11 @@ for _p in (ROOT, PKG_DIR):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-C2 = dict(V=3709, S=200, H=64, L=2, heads=2, B=256, dropout=0.2, mask_prob=0.2, min_len=20)
-C5 = dict(V=1_000_003, S=200, H=128, L=2, heads=2, B=1024, k=10)
+C2 = dict(V=3709, S=200, H=64, L=2, heads=2, B=256, dropout=0.2, mask_prob=0.2, only_last_prob=0.1, min_len=20)
+C5 = dict(V=1_000_003, S=200, H=128, L=2, heads=2, B=1024, k=10, B_cpu=64)
 METRIC = "train_seqs_per_sec"
 UNIT = "seqs/s"
+N_BATCHES = 64
 
 
 def peaks():
@@ -52,24 +56,36 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def workload_config(world):
+    """the workload -- identical for this arm and the reference arm; how each arm runs it is in its ``implementation`` key"""
+    cfg = C2
+    return {"workload": "C2 BERT4Rec cloze training, ML-1M shape", "items": cfg["V"], "seq_len": cfg["S"], "hidden": cfg["H"],
+            "layers": cfg["L"], "heads": cfg["heads"], "batch_per_gpu": cfg["B"], "global_batch": cfg["B"] * world, "dropout": cfg["dropout"],
+            "optimizer": "Adam(0.99,0.998), LambdaLR warm-up", "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "inputs larger than L2: each step streams ~0.9 GB of activations (> 126 MB L2); distinct batches rotate"}
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # synthetic data (seeded as SURVEY.md 8d: manual_seed(1234 + config index))
 # ----------------------------------------------------------------------------------------------------------------
-def make_cloze_batch(gen, B, S, V, mask_prob, min_len):
+def make_sessions(gen, B, S, V, min_len):
+    """right-padded item sequences as the reference's collate delivers them (before any masking)"""
     seq = torch.randint(3, V, (B, S), generator=gen)
     lengths = torch.randint(min_len, S + 1, (B,), generator=gen)
-    pos = torch.arange(S).unsqueeze(0)
-    valid = pos < lengths.unsqueeze(1)
-    seq = torch.where(valid, seq, torch.zeros_like(seq))
-    masked = (torch.rand(B, S, generator=gen) < mask_prob) & valid
-    only_last = torch.rand(B, generator=gen) < 0.1            # 10 % of the rows: only the last item is masked
+    return torch.where(torch.arange(S).unsqueeze(0) < lengths.unsqueeze(1), seq, torch.zeros_like(seq))
+
+
+def cloze_host(gen, seq, mask_prob, only_last_prob):
+    """CPU cloze masking of one batch for the oracle arms (same distribution as the GPU input pipeline)"""
+    valid = seq.ne(0)
+    lengths = valid.sum(1)
+    B = seq.shape[0]
+    masked = (torch.rand(seq.shape, generator=gen) < mask_prob) & valid
     last = torch.zeros_like(masked)
     last[torch.arange(B), lengths - 1] = True
+    only_last = torch.rand(B, generator=gen) < only_last_prob
     masked = torch.where(only_last.unsqueeze(1), last, masked | (last & ~masked.any(dim=1, keepdim=True)))
-    target = torch.where(masked, seq, torch.zeros_like(seq))
-    inp = torch.where(masked, torch.ones_like(seq), seq)
-    rows = torch.nonzero(target.reshape(-1) != 0).reshape(-1)
-    return inp, target, rows
+    return torch.where(masked, torch.ones_like(seq), seq), torch.where(masked, seq, torch.zeros_like(seq))
 
 
 class ClockSampler:
@@ -118,7 +134,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU oracle step (cpu_baseline and --impl reference)
+# CPU oracle steps (cpu_baseline and --impl reference): the oracle is the checker / the reported baseline, never the product
 # ----------------------------------------------------------------------------------------------------------------
 def oracle_train_setup(cfg, B_cpu, seed=0):
     from oracle import asme_oracle as O
@@ -130,10 +146,12 @@ def oracle_train_setup(cfg, B_cpu, seed=0):
     m = [torch.zeros_like(w[n]) for n in names]
     v = [torch.zeros_like(w[n]) for n in names]
     gen = torch.Generator().manual_seed(1234 + 1)
-    inp, target, _ = make_cloze_batch(gen, B_cpu, cfg["S"], cfg["V"], cfg["mask_prob"], cfg["min_len"])
+    batches = [cloze_host(gen, make_sessions(gen, B_cpu, cfg["S"], cfg["V"], cfg["min_len"]), cfg["mask_prob"], cfg["only_last_prob"])
+               for _ in range(4)]
     state = dict(step=0)
 
     def step():
+        inp, target = batches[state["step"] % len(batches)]
         O.DROPOUT_P = cfg["dropout"]
         for n in names:
             w[n].grad = None
@@ -143,14 +161,48 @@ def oracle_train_setup(cfg, B_cpu, seed=0):
         with torch.no_grad():
             O.adam_step([w[n] for n in names], [w[n].grad for n in names], m, v, state["step"], 1e-3, 0.99, 0.998, 1e-8, 0.0)
         O.DROPOUT_P = 0.0
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
 
-def time_oracle(cfg, B_cpu, steps, warmup):
+def oracle_eval_setup(cfg, B_cpu, seed=0):
+    """full-catalog evaluation as the reference runs it, restricted to what a CPU can hold: encoder on B_cpu users, MASK-row select,
+    modifier, projection of the SELECTED rows onto the catalog (the reference projects every position: (B,S,V) = 51 GB at this
+    shape -- the port is given the cheaper form), then the reference's metric path: one full argsort per metric (common.py:18-27)"""
+    from oracle import asme_oracle as O
+    from asme_b200.models import BERT4RecModel
+    torch.manual_seed(seed)
+    model = BERT4RecModel(cfg["H"], cfg["heads"], cfg["L"], cfg["V"], cfg["S"], 0.0)
+    w = {k: v.detach().clone() for k, v in model.state_dict().items() if k != "_projection_layer.embedding.weight"}
+    gen = torch.Generator().manual_seed(1234 + 4)
+    seq = make_sessions(gen, B_cpu, cfg["S"] - 1, cfg["V"], 20)
+    seq = torch.cat([seq, torch.zeros(B_cpu, 1, dtype=seq.dtype)], dim=1)
+    seq[torch.arange(B_cpu), seq.ne(0).sum(1)] = 1
+    target = torch.randint(3, cfg["V"], (B_cpu,), generator=gen)
+    table, bias = w["_sequence_embedding_layer.item_embedding.embedding.weight"], w["_projection_layer.output_bias"]
+
+    def step():
+        with torch.no_grad():
+            hidden = O.bert4rec_hidden(w, seq, cfg["heads"], cfg["L"])
+            rows = O.ffn_modifier(O.select_masked_rows(hidden, seq), w)
+            logits = O.project(rows, table, bias)
+            out = {}
+            for name in ("recall", "ndcg"):                       # one sort per metric instance, as RankingMetric does
+                order = torch.argsort(logits, dim=1, descending=True, stable=True)[:, :cfg["k"]]
+                hit = order.eq(target.unsqueeze(1))
+                if name == "recall":
+                    out[name] = hit.any(1).float().mean()
+                else:
+                    pos = hit.float().argmax(1)
+                    out[name] = (hit.any(1).float() / torch.log2(pos.float() + 2.0)).mean()
+        return float(out["recall"])
+
+    return step
+
+
+def time_cpu(step, units, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
-    step = oracle_train_setup(cfg, B_cpu)
     for _ in range(warmup):
         step()
     times = []
@@ -158,23 +210,32 @@ def time_oracle(cfg, B_cpu, steps, warmup):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-    return B_cpu / statistics.median(times), statistics.median(times), torch.get_num_threads()
+    med = statistics.median(times)
+    return units / med, med, torch.get_num_threads()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B_cpu = 16
-    value, t_step, cores = time_oracle(C2, B_cpu, max(1, args.steps), max(1, min(args.warmup, 2)))
-    sample = f"{B_cpu} of the {C2['B']} sequences of one C2 batch per step (same shapes, dropout 0.2, fwd+CE+bwd+Adam)"
+    steps = max(5, min(args.steps, 30))
+    warmup = max(2, min(args.warmup, 5))
+    value, t_step, cores = time_cpu(oracle_train_setup(C2, C2["B"]), C2["B"], steps, warmup)
+    sample = (f"the full C2 batch ({C2['B']} sequences, 4 distinct cloze batches rotating) per step, median of {steps} steps after {warmup} warm-up "
+              f"({t_step:.2f} s/step): oracle/asme_oracle.py port of the reference's PyTorch path, dropout 0.2, fwd + CE + bwd + Adam")
+    ev = None
+    if not args.no_eval:
+        ev_v, ev_t, _ = time_cpu(oracle_eval_setup(C5, C5["B_cpu"]), C5["B_cpu"], 5, 2)
+        ev = {"metric": "eval_users_per_sec", "value": ev_v, "unit": "users/s", "ms_per_step": ev_t * 1e3, "users_per_step": C5["B_cpu"],
+              "note": "B=64 users per step (SURVEY 8d): encoder + MASK-row select + projection of the selected rows onto 1M items + one "
+                      "full argsort per metric"}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "C2 BERT4Rec cloze training, ML-1M shape (V=3709, S=200, H=64, L=2, heads=2, B=256/GPU, dropout 0.2, Adam)",
-                      "note": "CPU port (oracle/asme_oracle.py) of the reference's PyTorch path; the Python reference cannot travel to the GPU box"},
+           "dtype": "f32", "data": "synthetic", "config": workload_config(max(1, args.gpus)),
+           "implementation": {"precision": "fp32 (torch CPU ops)", "launch": "oracle/asme_oracle.py on the host cores", "distinct_batches": 4},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "timed_steps": steps, "eval": ev}
     emit(out)
 
 
@@ -182,7 +243,7 @@ def run_reference(args):
 # roofline model: algorithmic bytes / flops per launch of each C-ABI entry point, from the shapes noted by ops.py
 # ----------------------------------------------------------------------------------------------------------------
 def algorithmic_cost(name, note):
-    """returns (bytes, flops) per call for the entry points that matter; shapes come from ``note``."""
+    """returns (bytes, flops) per call; shapes come from ``note``.  DESIGN.md section 4 states the per-unit figures."""
     f = dict(kv.split("=") for kv in note.split(",") if "=" in kv) if note else {}
     g = lambda k: int(f.get(k, 0))
     if name == "asme_b200_gemm":
@@ -192,7 +253,7 @@ def algorithmic_cost(name, note):
     if name == "asme_b200_gemm_wgrad":
         M, N, K = g("M"), g("N"), g("K")
         return 4 * (M * N + M * K + N * K), 2 * M * N * K
-    if name == "asme_b200_tc_gemm":
+    if name in ("asme_b200_tc_gemm", "asme_b200_tc_gemm_ln"):
         M, N, K = g("M"), g("N"), g("K")
         b = 2 * (M * K + N * K) + M * N * (4 * g("f32") + 2 * g("bf16") + 2 * g("pre") + 2 * g("aux") + 4 * g("res"))
         return b, 2 * M * N * K
@@ -211,8 +272,10 @@ def algorithmic_cost(name, note):
     if name == "asme_b200_dropout_cast":
         n = g("n")
         return (4 + 2 + 4 * g("f32")) * n, n
-    if name in ("asme_b200_tc_score_topk",):
-        R, V, H, k = g("R"), g("V"), g("H"), g("k")
+    if name in ("asme_b200_tc_score_topk", "asme_b200_tc_score_candidates"):
+        # flops on the MODEL's hidden size: the bias-folding columns (Kp = H + 16) are this implementation's overhead, not algorithmic work
+        R, V, Kp, k = g("R"), g("V"), g("H"), g("k")
+        H = Kp - 16 if Kp % 64 == 16 else Kp
         return 2 * (R * H + V * H) + 4 * V + R * (k * 8 + 8), 2 * R * V * H
     if name == "asme_b200_tc_score_ce_bwd":
         R, V, H = g("R"), g("V"), g("H")
@@ -221,7 +284,7 @@ def algorithmic_cost(name, note):
         R, V, H = g("R"), g("V"), g("H")
         return 2 * (R * H + V * H) + 4 * V + 12 * R, 2 * R * V * H
     if name == "asme_b200_attn_fwd":
-        T, H, S, heads = g("T"), g("H"), g("S"), g("heads")
+        T, H, S = g("T"), g("H"), g("S")
         return 4 * 4 * T * H, 4 * T * S * H
     if name == "asme_b200_attn_bwd":
         T, H, S = g("T"), g("H"), g("S")
@@ -229,9 +292,12 @@ def algorithmic_cost(name, note):
     if name in ("asme_b200_layernorm_fwd", "asme_b200_layernorm_fwd_bf16"):
         M, H = g("M"), g("H")
         return 4 * 2 * M * H, 8 * M * H
-    if name in ("asme_b200_layernorm_bwd",):
+    if name == "asme_b200_layernorm_bwd":
         M, H = g("M"), g("H")
         return 4 * (3 + g("res")) * M * H, 16 * M * H
+    if name == "asme_b200_layernorm_bwd_drop":      # reads dy, x (+ residual), writes dx fp32 and its dropped bf16 copy
+        M, H = g("M"), g("H")
+        return (4 * (3 + g("res")) + 2) * M * H, 20 * M * H
     if name == "asme_b200_attn_row_fwd":     # K and V rows of every token once (bf16), one query / context row per sequence
         T, H, S = g("T"), g("H"), g("S")
         return 2 * T * H * 2 + T + 2 * (T // max(S, 1)) * H * 2, 4 * T * H
@@ -247,24 +313,50 @@ def algorithmic_cost(name, note):
     if name == "asme_b200_score_ce_bwd":
         R, V, H = g("R"), g("V"), g("H")
         return 4 * (2 * R * H + 2 * V * H + 2 * V), 8 * R * V * H
-    if name == "asme_b200_score_topk_rank":
+    if name in ("asme_b200_score_topk_rank", "asme_b200_score_topk_flagged"):
         R, V, H, k = g("R"), g("V"), g("H"), g("k")
+        if g("flagged"):
+            return R * (k * 8 + 8), 0          # nothing flagged: the launch only reads the flags
         return 4 * (R * H + V * H + V) + R * (k * 8 + 8), 2 * R * V * H
+    if name == "asme_b200_topk_rescore":     # candidate rows of the fp32 table + the hidden row, per user
+        R, H, KC = g("R"), g("H"), g("KC")
+        return R * (KC * (H * 4 + 8) + H * 4), 2 * R * KC * H
     if name == "asme_b200_embgrad_sorted_reduce":
         T, H = g("T"), g("H")
         return T * H * 4 * 2 + T * 8, T * H
+    if name == "asme_b200_embgrad_sort":          # (id, token) keys: read ids, radix sort passes over 8-byte pairs
+        T = g("T")
+        return T * 8 + 4 * T * 8 * 2, T
+    if name == "asme_b200_embgrad_reduce_sorted":  # gradient rows read once, one row written per distinct id (<= T)
+        T, H = g("T"), g("H")
+        return T * H * 4 * 2 + T * 8, T * H
+    if name in ("asme_b200_gather_rows", "asme_b200_scatter_rows"):
+        R, H = g("R"), g("H")
+        return R * (2 * H * 4 + 8), 0
+    if name == "asme_b200_select_rows":
+        T = g("T")
+        return T * 8 * 2 + T * 16, T
+    if name == "asme_b200_fill":
+        return 4 * g("n"), 0
+    if name == "asme_b200_ce_loss_from_partials":
+        return 4 * 4 * g("R"), 4 * g("R")
+    if name in ("asme_b200_posgrad_reduce", "asme_b200_posgrad_reduce_strided"):
+        B, S, H = g("B"), g("S"), g("H")
+        return 4 * (B * S * H + S * H), B * S * H
+    if name == "asme_b200_colsum_accumulate":
+        return 4 * g("M") * g("N"), g("M") * g("N")
     if name in ("asme_b200_dropout", "asme_b200_gelu_bwd", "asme_b200_binary"):
         n = g("n")
         return 4 * 2 * n, n
-    if name == "asme_b200_adam_step":
+    if name in ("asme_b200_adam_step", "asme_b200_adam_step_dev"):
         n = g("n")
         return 4 * 7 * n, 12 * n
     return 0, 0
 
 
 NCU_NAMES = {"tc_attn_bwd": "attn_tc_bwd1_kernel", "tc_attn_fwd": "attn_tc_fwd_kernel", "tc_gemm": "tc_gemm_persist_kernel",
-             "tc_wgrad": "tc_wgrad_kernel", "tc_score_topk": "score_tc_kernel", "tc_score_ce_bwd": "ce_bwd_tc_kernel",
-             "tc_score_ce_partial": "score_tc_kernel"}
+             "tc_wgrad": "tc_wgrad_kernel", "tc_score_topk": "score_tc_kernel", "tc_score_candidates": "score_tc_kernel",
+             "tc_score_ce_bwd": "ce_bwd_tc_kernel", "tc_score_ce_partial": "score_tc_kernel"}
 
 
 def ncu_traffic(kernel):
@@ -292,11 +384,10 @@ def ncu_traffic(kernel):
 
 
 def summarise_kernels(records, steps, pk):
-    """records: (name, note, ms). Returns per-entry-point table (sorted by share) and the roofline of the top one."""
+    """records: (name, note, ms). Returns per-entry-point table (sorted by share) and the kernel time per step."""
     groups = {}
     for name, note, ms in records:
-        key = (name, note)
-        gsum = groups.setdefault(key, [0.0, 0])
+        gsum = groups.setdefault((name, note), [0.0, 0])
         gsum[0] += ms
         gsum[1] += 1
     total = sum(v[0] for v in groups.values())
@@ -316,6 +407,14 @@ def summarise_kernels(records, steps, pk):
     return table, total / steps
 
 
+def roofline_of(row, pk):
+    traffic = ncu_traffic(row["kernel"]) or {}
+    return {"kernel": row["kernel"], "shape": row["shape"], "bound": row["bound"], "achieved": row["achieved"], "peak": row["peak"],
+            "unit": row["unit"], "frac": row["frac"], "traffic": traffic.get("bytes_per_launch"), "traffic_source": traffic.get("source"),
+            "avg_launch_ms": row["avg_ms"], "share_of_step": row["share"], "peak_source": pk["source"],
+            "algorithmic_bytes_per_launch": row["algorithmic_bytes"], "algorithmic_flops_per_launch": row["algorithmic_flops"]}
+
+
 # ----------------------------------------------------------------------------------------------------------------
 _RESULT_FD = None
 
@@ -329,15 +428,20 @@ def emit(obj):
         os.write(_RESULT_FD, line)
 
 
+def log_table(title, table):
+    rows = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()} for row in table]
+    print(f"[bench kernels] {title}: " + json.dumps(rows), file=sys.stderr)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-eval", action="store_true", help="skip the secondary C5 full-catalog evaluation measurement")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
-    ap.add_argument("--no-graph", action="store_true", help="issue the step launch by launch instead of replaying its CUDA graph")
+    ap.add_argument("--no-eval", action="store_true", help="skip the C5 full-catalog evaluation half")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
+    ap.add_argument("--no-graph", action="store_true", help="issue the steps launch by launch instead of replaying their CUDA graphs")
     ap.add_argument("--profile-region", action="store_true",
                     help="profiling aid (ncu --profile-from-start off): after warm-up bracket ONE launch-by-launch training step and ONE "
                          "evaluation step in cudaProfilerStart/Stop, print no bench line")
@@ -365,7 +469,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    from asme_b200 import _lib, ops
+    from asme_b200 import _lib, input_pipeline
     from asme_b200.metrics import build_metrics
     from asme_b200.models import BERT4RecModel
     from asme_b200.modules import MaskedTrainingModule
@@ -380,15 +484,18 @@ def main():
     (optimizer,), (sched,) = module.configure_optimizers()
     scheduler = sched["scheduler"]
 
-    # distinct synthetic batches per rank (data parallel: every rank owns its own sequences)
-    NB = 4
+    # 64 distinct batches per rank (data parallel: every rank owns its own sequences).  Host side: the unmasked item sequences in
+    # pinned memory, as the session store delivers them; device side: cloze-masked by the GPU input pipeline (csrc/pipeline.cu) --
+    # every batch draws its own number of masked positions
     gen = torch.Generator().manual_seed(1234 + 1 + 1000 * rank)
-    host_batches, dev_batches = [], []
-    for _ in range(NB):
-        inp, target, rows = make_cloze_batch(gen, cfg["B"], cfg["S"], cfg["V"], cfg["mask_prob"], cfg["min_len"])
-        hb = {"item": inp.pin_memory(), "item.target": target.pin_memory(), "_target_rows": rows.pin_memory()}
-        host_batches.append(hb)
-        dev_batches.append({k: v.to(device) for k, v in hb.items()})
+    host_items = [make_sessions(gen, cfg["B"], cfg["S"], cfg["V"], cfg["min_len"]).pin_memory() for _ in range(N_BATCHES)]
+
+    def cloze(items_dev, j):
+        return input_pipeline.cloze_mask({"item": items_dev}, {"item": cfg["V"]}, cfg["mask_prob"], cfg["only_last_prob"],
+                                         seed=(rank << 20) + j)
+
+    dev_batches = [cloze(h.to(device), j) for j, h in enumerate(host_items)]
+    target_counts = sorted({int((b["item.target"] != 0).sum()) for b in dev_batches})
 
     def allreduce_grads():
         if world > 1:
@@ -412,25 +519,24 @@ def main():
 
     if args.profile_region:
         for i in range(3):
-            train_step(dev_batches[i % NB], i)
+            train_step(dev_batches[i], i)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        train_step(dev_batches[3 % NB], 3)
+        train_step(dev_batches[3], 3)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        bench_eval_c5(device, pk, steps=1, warmup=2, world=world, rank=rank, profile=True)
+        bench_eval_c5(args, device, pk, world=world, rank=rank, profile=True)
         emit({"profile_region": "1 training step (C2) + 1 evaluation step (C5), launch by launch"})
         return
 
     # The step is ~90 launches; issued from Python the host is the bottleneck, so the product path replays the step's CUDA graph
-    # (asme_b200.graphs.GraphedTrainStep: one graph per batch signature, seed / Adam step / lr in device memory).
+    # (asme_b200.graphs.GraphedTrainStep).  ONE graph per batch shape: the positions that carry a target are selected on the device.
     graphed = None
     if not args.no_graph:
         from asme_b200.graphs import GraphedTrainStep
         try:
             graphed = GraphedTrainStep(module, optimizer, scheduler, grad_hook=allreduce_grads if world > 1 else None)
-            for j in range(NB):
-                graphed(dev_batches[j], key=j)
+            graphed(dev_batches[0])
             torch.cuda.synchronize()
         except Exception as e:      # e.g. a collective that cannot be captured: fall back to launch-by-launch
             print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
@@ -439,9 +545,7 @@ def main():
             optimizer.step_state = None
 
     def run_step(batch, i):
-        if graphed is not None:
-            return graphed(batch, key=i % NB)
-        return train_step(batch, i)
+        return graphed(batch) if graphed is not None else train_step(batch, i)
 
     def timed(fn, steps):
         barrier()
@@ -464,33 +568,29 @@ def main():
     if rank == 0:
         clocks.start()
 
-    # ---- (1) device-resident throughput -------------------------------------------------------------------------
+    # ---- (1) device-resident throughput: a different batch every step --------------------------------------------------------------
     for i in range(args.warmup):
-        run_step(dev_batches[i % NB], i)
-    launches0 = _lib.kernel_launches()
-    ms, win1 = timed(lambda i: run_step(dev_batches[i % NB], i), args.steps)
-    launches = _lib.kernel_launches() - launches0
-    launches_per_step_eager = None
+        run_step(dev_batches[i % N_BATCHES], i)
+    ms, win1 = timed(lambda i: run_step(dev_batches[(args.warmup + i) % N_BATCHES], i), args.steps)
     value = args.steps * cfg["B"] * world / (ms / 1e3)
 
-    # ---- (2) end to end through the public module API with HOST buffers ------------------------------------------
-    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    # ---- (2) end to end through the public API with HOST buffers ---------------------------------------------------------------------
+    h2d = host_items[0].numel() * host_items[0].element_size()
+    staged = torch.empty_like(dev_batches[0]["item"])
 
     def e2e_step(i):
-        hb = host_batches[i % NB]
-        if graphed is not None:
-            loss = graphed(hb, key=i % NB)                                      # H2D of this step's inputs into the graph's static buffers
-        else:
-            batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
-            loss = train_step(batch, i)
-        return float(loss)                                                      # D2H read of the step's result
+        j = (args.warmup + i) % N_BATCHES
+        staged.copy_(host_items[j], non_blocking=True)                    # H2D of this step's item sequences (pinned)
+        batch = cloze(staged, N_BATCHES + i)                              # input pipeline on the GPU: fresh masks every step
+        return float(run_step(batch, i))                                  # the step; D2H read of its loss
 
     for i in range(3):
         e2e_step(i)
     ms_e2e, win2 = timed(e2e_step, args.steps)
     e2e_value = args.steps * cfg["B"] * world / (ms_e2e / 1e3)
+    graphs_captured = len(graphed.graphs) if graphed is not None else 0
 
-    # ---- (3) per-kernel CUDA-event timing of the same step (roofline of the dominant kernel) -----------------------
+    # ---- (3) per-kernel CUDA-event timing of the same step (roofline of the dominant kernel) -----------------------------------------
     prof_steps = min(5, args.steps)
     if graphed is not None:          # the per-kernel pass (and the launch count) runs the same step launch by launch
         module.model._step_state = None
@@ -499,13 +599,13 @@ def main():
     barrier()
     l0 = _lib.kernel_launches()
     for i in range(prof_steps):
-        train_step(dev_batches[i % NB], i)
-    if graphed is not None:
-        launches = (_lib.kernel_launches() - l0) * args.steps // prof_steps   # kernels of this library per step x timed steps (graph replays launch the same nodes)
+        train_step(dev_batches[i % N_BATCHES], i)
+    launches = (_lib.kernel_launches() - l0) * args.steps // prof_steps   # kernels of this library per step x timed steps (graph replays launch the same nodes)
     torch.cuda.synchronize()
     records = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
     table, kernel_ms_per_step = summarise_kernels(records, prof_steps, pk)
+    unaccounted = sum(r["share"] for r in table if r["algorithmic_bytes"] == 0 and r["algorithmic_flops"] == 0)
     # the timed regions last tens of milliseconds -- shorter than nvidia-smi's sampling period -- so the same step keeps
     # running (untimed) until enough clock samples were taken under exactly this load
     probe = None
@@ -514,7 +614,7 @@ def main():
         i = 0
         while clocks.count_in([win1, win2, (t_probe0, time.time())]) < 8 and time.time() - t_probe0 < 4.0:
             optimizer.zero_grad()                      # forward + backward only: no collective, weights stay in sync across ranks
-            module.training_step(dev_batches[i % NB], i)["loss"].backward()
+            module.training_step(dev_batches[i % N_BATCHES], i)["loss"].backward()
             i += 1
             if i % 20 == 0:
                 torch.cuda.synchronize()
@@ -524,10 +624,11 @@ def main():
         dist.barrier()
     clocks.stop()
 
-    # ---- (4) secondary: C5 full-catalog evaluation ------------------------------------------------------------------
+    # ---- (4) the evaluation half: C5 full-catalog scoring + exact top-k + Recall/NDCG ------------------------------------------------
     eval_info = None
     if not args.no_eval:
-        eval_info = bench_eval_c5(device, pk, world=world, rank=rank, graph=not args.no_graph)
+        del dev_batches
+        eval_info = bench_eval_c5(args, device, pk, world=world, rank=rank, graph=not args.no_graph)
 
     def finish():
         # CUDA graphs that captured NCCL collectives keep communicator resources alive and ncclCommDestroy can then block for ever:
@@ -542,133 +643,177 @@ def main():
         finish()
         return
 
-    top = table[0] if table else None
-    roofline = None
-    if top:
-        roofline = {"kernel": top["kernel"], "shape": top["shape"], "bound": top["bound"], "achieved": top["achieved"],
-                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                    "traffic": (ncu_traffic(top["kernel"]) or {}).get("bytes_per_launch"),
-                    "traffic_source": (ncu_traffic(top["kernel"]) or {}).get("source"),
-                    "avg_launch_ms": top["avg_ms"], "share_of_step": top["share"], "peak_source": pk["source"],
-                    "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "algorithmic_flops_per_launch": top["algorithmic_flops"]}
+    roofline = roofline_of(table[0], pk) if table else None
+    log_table("C2 training step", table[:40])
     cpu = None
     if not args.no_cpu and world == 1:
-        B_cpu = 16
-        v_cpu, t_cpu, cores = time_oracle(cfg, B_cpu, steps=3, warmup=1)
+        v_cpu, t_cpu, cores = time_cpu(oracle_train_setup(cfg, cfg["B"]), cfg["B"], steps=5, warmup=2)
         cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{B_cpu} sequences of one C2 batch per step, median of 3 steps after 1 warm-up ({t_cpu:.2f} s/step); "
+               "sample": f"the full C2 batch ({cfg['B']} sequences) per step, median of 5 steps after 2 warm-up ({t_cpu:.2f} s/step); "
                          f"oracle/asme_oracle.py port of the reference path, dropout 0.2, fwd+CE+bwd+Adam"}
+    launch = ("CUDA graph replay of the whole step: ONE graph for every batch of the shape (target rows selected on the device)"
+              if graphed is not None else "launch by launch")
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "bf16" if model.precision == "bf16" else "f32",
-           "data": "synthetic",
-           "config": {"workload": "C2 BERT4Rec cloze training, ML-1M shape", "items": cfg["V"], "seq_len": cfg["S"], "hidden": cfg["H"],
-                      "layers": cfg["L"], "heads": cfg["heads"], "batch_per_gpu": cfg["B"], "global_batch": cfg["B"] * world,
-                      "dropout": cfg["dropout"], "optimizer": "Adam(0.99,0.998) fused, LambdaLR warm-up",
-                      "precision": f"{model.precision}: tcgen05 GEMMs/attention/scoring with bf16 operands, fp32 accumulation, residual stream, LayerNorm, loss and Adam state",
-                      "parallelism": f"dp{world}" if world > 1 else "single",
-                      "launch": "CUDA graph replay of the whole step (one graph per batch signature)" if graphed is not None else "launch by launch",
-                      "l2": "inputs larger than L2: each step streams ~0.9 GB of activations (> 126 MB L2), 4 distinct batches rotate"},
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+           "dtype": "bf16" if model.precision == "bf16" else "f32", "data": "synthetic",
+           "config": workload_config(world),
+           "implementation": {"precision": f"{model.precision}: tcgen05 GEMMs/attention/scoring with bf16 operands, fp32 accumulation, residual "
+                                           f"stream, LayerNorm, loss and Adam state", "launch": launch, "distinct_batches": N_BATCHES},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                   "path": "pinned host item sequences -> H2D -> GPU cloze masking -> MaskedTrainingModule step (graph replay) -> loss D2H"},
            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+           "graphs_captured": graphs_captured, "distinct_target_counts": len(target_counts),
+           "target_count_range": [target_counts[0], target_counts[-1]],
            "clocks": dict(clocks.summary([win1, win2] + ([probe] if probe else [])),
                           window="timed regions + an untimed continuation of the same step until 8 samples (nvidia-smi -lms 50)"),
-           "roofline": roofline, "cpu_baseline": cpu,
-           "kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()} for row in table[:30]],
-           "kernel_ms_per_step": kernel_ms_per_step, "eval": eval_info}
+           "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms_per_step,
+           "kernel_time_without_cost_model": unaccounted,
+           "kernels_top5": [{k: (round(r[k], 4) if isinstance(r[k], float) else r[k]) for k in ("kernel", "avg_ms", "share", "bound", "frac")}
+                            for r in table[:5]],
+           "eval": eval_info}
     emit(out)
     finish()
 
 
-def bench_eval_c5(device, pk, steps=5, warmup=2, world=1, rank=0, profile=False, graph=True):
-    """secondary measurement: full-catalog scoring + top-k + Recall/NDCG@10 on a 1M-item catalog (C5).  With N ranks the
-    catalog is vocab-sharded (asme_b200.sharded): every rank encodes its own 1024 users and scores all N*1024 users against
-    its V/N slice; per-shard top-k lists and target scores are merged over NCCL (weak scaling: users per GPU fixed)."""
+def bench_eval_c5(args, device, pk, world=1, rank=0, profile=False, graph=True):
+    """the evaluation half of the metric: full-catalog scoring + EXACT top-10 + Recall/NDCG@10 on a 1M-item catalog (C5), through
+    ``MaskedTrainingModule.validation_step`` / ``validation_step_end``.  With N ranks the catalog is vocab-sharded
+    (asme_b200.sharded): every rank encodes its own 1024 users and scores all N*1024 users against its V/N slice (weak scaling)."""
     import torch.distributed as dist
     from asme_b200 import _lib
     from asme_b200.metrics import build_metrics
     from asme_b200.models import BERT4RecModel
+    from asme_b200.modules import MaskedTrainingModule
     cfg = C5
     torch.manual_seed(0)
-    model = BERT4RecModel(cfg["H"], cfg["heads"], cfg["L"], cfg["V"], cfg["S"], 0.0).to(device).eval()
-    metrics = build_metrics({"recall": [10], "ndcg": [10]})
+    model = BERT4RecModel(cfg["H"], cfg["heads"], cfg["L"], cfg["V"], cfg["S"], 0.0)
+    module = MaskedTrainingModule(model, metrics=build_metrics({"recall": [10], "ndcg": [10]})).to(device).eval()
+    module.eval_loss = False
+    module.shard_catalog = world > 1
+    module.eval_graph = bool(graph and not profile)
     gen = torch.Generator().manual_seed(1234 + 4 + 1000 * rank)
-    B, S, V = cfg["B"], cfg["S"], cfg["V"]
-    seq = torch.randint(3, V, (B, S), generator=gen)
-    lengths = torch.randint(20, S, (B,), generator=gen)
-    seq = torch.where(torch.arange(S).unsqueeze(0) < lengths.unsqueeze(1), seq, torch.zeros_like(seq))
-    seq[torch.arange(B), lengths] = 1                      # one MASK appended per user
-    target = torch.randint(3, V, (B,), generator=gen)
-    seq_d, target_d = seq.to(device), target.to(device)
-    from asme_b200.metrics import FusedPredictions
+    B, S, V, k = cfg["B"], cfg["S"], cfg["V"], cfg["k"]
+    seq = make_sessions(gen, B, S - 1, V, 20)
+    seq = torch.cat([seq, torch.zeros(B, 1, dtype=seq.dtype)], dim=1)
+    seq[torch.arange(B), seq.ne(0).sum(1)] = 1                       # one MASK appended per user
+    free = torch.randint(3, V, (B,), generator=gen)
+    seq_d = seq.to(device)
+    # targets: for every second user an item of the user's OWN top 20 (so that Recall@10 is not trivially zero on random weights)
+    with torch.no_grad():
+        first = model.evaluate_rank(seq_d, seq_d.ne(0), {}, free.to(device), k=20)
+    col = torch.randint(0, 20, (B,), generator=gen).to(device)
+    planted = first["topk_idx"].gather(1, col.unsqueeze(1)).squeeze(1).to(torch.int64)
+    target_d = torch.where(torch.arange(B, device=device) % 2 == 0, planted, free.to(device))
+    host = {"item": seq.pin_memory(), "item.target": target_d.cpu().pin_memory()}
+    dev = {"item": seq_d, "item.target": target_d}
+    staged = {k_: torch.empty_like(v) for k_, v in dev.items()}
 
-    full_rank = metrics.needs_full_rank()
+    def step(batch):
+        with torch.no_grad():
+            return module.validation_step_end(module.validation_step(batch, 0))
 
-    def model_step(b):
+    def e2e_step():
+        for k_ in staged:
+            staged[k_].copy_(host[k_], non_blocking=True)               # H2D of this step's users (pinned)
+        values = step(staged)
+        return float(values["recall@10"]), float(values["NDCG@10"])     # D2H of the step's metric values
+
+    def barrier():
         if world > 1:
-            return model.evaluate_rank_sharded(b["seq"], b["seq"].ne(0), {}, b["target"], k=cfg["k"], full_rank=full_rank)
-        return model.evaluate_rank(b["seq"], b["seq"].ne(0), {}, b["target"], k=cfg["k"], full_rank=full_rank)
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    # ~40 launches per step: issued from Python the host is as slow as the GPU, so the step replays a CUDA graph of the model part
-    # (asme_b200.graphs.GraphedEvalStep; with N ranks the NCCL exchanges of the sharded merge are captured with it, like the
-    # gradient all-reduce of the training graph); the metric accumulation stays outside (it rebinds its state tensors)
-    graphed = None
-    if graph and not profile:
-        from asme_b200.graphs import GraphedEvalStep
-        try:
-            graphed = GraphedEvalStep(model_step)
-            graphed({"seq": seq_d, "target": target_d})
-        except Exception as e:
-            print(f"[bench] evaluation graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-            graphed = None
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
-    def step(eager=False):
-        batch = {"seq": seq_d, "target": target_d}
-        out = model_step(batch) if (graphed is None or eager) else graphed(batch)
-        return metrics.update(seq_d, target_d, FusedPredictions(out["rank"], out["topk_idx"], out["topk_val"], out["target_score"], V))
-
+    steps, warmup = max(5, min(args.steps, 20)), max(3, min(args.warmup, 5))
     for _ in range(warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        step(dev)
+    barrier()
     if profile:
         torch.cuda.profiler.start()
-        step()
+        step(dev)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        step()
+        step(dev)
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        recall_step, ndcg_step = e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / steps)
+    module.metrics.sync() if world > 1 else None
+    res = module.validation_epoch_end(None)
+
+    # ---- checks, outside the timed regions -----------------------------------------------------------------------------------------
+    checks = {}
+    with torch.no_grad():
+        mine = model.evaluate_rank(seq_d, seq_d.ne(0), {}, target_d, k=k, full_rank=False)
+        if world > 1:       # the sharded result of this rank's users equals its own unsharded evaluation
+            sh = model.evaluate_rank_sharded(seq_d, seq_d.ne(0), {}, target_d, k=k, full_rank=False)
+            checks["sharded_equals_unsharded"] = bool(torch.equal(sh["topk_idx"], mine["topk_idx"]) and torch.equal(sh["rank"], mine["rank"])
+                                                      and torch.equal(sh["topk_val"], mine["topk_val"]))
+        # dense cross-check on a row subset: float64 logits of the fp32 operands -> stable sort -> Recall@10
+        from asme_b200.models import mask_position_rows
+        n_chk = 64
+        m_rows, _ = model.modify(model.encode_rows(seq_d, seq_d.ne(0), {}, mask_position_rows(seq_d, 1), one_per_sequence=True))
+        w32, b32 = model.projection_operands()
+        logits = m_rows[:n_chk].double() @ w32.double().t() + b32.double()
+        order = torch.argsort(logits, dim=1, descending=True, stable=True)[:, :k]
+        checks["dense_rows"] = n_chk
+        checks["topk_equals_dense_fp64"] = bool(torch.equal(order.to(torch.int32), mine["topk_idx"][:n_chk]))
+        hit = order.eq(target_d[:n_chk].unsqueeze(1)).any(1)
+        checks["recall_equals_dense"] = bool(torch.equal(hit, mine["rank"][:n_chk] <= k))
+        checks["uncertified_rows"] = int(mine["n_uncertified"]) if "n_uncertified" in mine else None
+    # ---- per-kernel pass of one launch-by-launch step -----------------------------------------------------------------------------
+    module.eval_graph = False
     _lib.timing = []
-    step(eager=True)
+    step(dev)
     torch.cuda.synchronize()
     rec = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
-    table, _ = summarise_kernels(rec, 1, pk)
-    score = next((r for r in table if r["kernel"] in ("tc_score_topk", "score_topk_rank")), None)
-    metrics.sync()
-    res = metrics.compute()
-    return {"metric": "eval_users_per_sec", "value": world * B / (ms / 1e3), "unit": "users/s", "ms_per_step": ms, "n_gpus": world,
-            "launch": "CUDA graph replay of the model part of the step" if graphed is not None else "launch by launch",
-            "scaling": "weak", "sharding": "single GPU" if world == 1 else f"catalog rows sharded over {world} ranks (NCCL: all-gather hidden rows, all-reduce target scores, all-gather top-k lists)",
-            "config": {"workload": "C5 full-catalog scoring + top-k eval, synthetic 1M-item catalog", "items": V, "hidden": cfg["H"],
-                       "seq_len": S, "users_per_step_per_gpu": B, "k": cfg["k"], "dtype": model.precision},
-            "recall@10": float(res["recall@10"]), "NDCG@10": float(res["NDCG@10"]),
-            "scoring_kernel": None if score is None else {k: score[k] for k in ("avg_ms", "bound", "achieved", "peak", "unit", "frac", "share")},
-            "kernels": [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in row.items() if k in ("kernel", "shape", "launches_per_step", "avg_ms", "share", "bound", "frac")}
-                        for row in table[:14]]}
+    table, kernel_ms = summarise_kernels(rec, 1, pk)
+    score = next((r for r in table if r["kernel"] in ("tc_score_candidates", "tc_score_topk", "score_topk_rank")), None)
+    if rank == 0:
+        log_table("C5 evaluation step", table[:30])
+    if rank != 0:
+        return None
+    cpu = None
+    if not args.no_cpu and world == 1:
+        v_cpu, t_cpu, cores = time_cpu(oracle_eval_setup(cfg, cfg["B_cpu"]), cfg["B_cpu"], steps=5, warmup=2)
+        cpu = {"value": v_cpu, "unit": "users/s", "cores": cores, "kind": "port",
+               "sample": f"{cfg['B_cpu']} users per step (SURVEY 8d), median of 5 after 2 warm-up ({t_cpu:.2f} s/step): encoder, MASK-row select, "
+                         f"projection of the selected rows onto the 1M catalog, one full argsort per metric"}
+    roof = None
+    if score is not None:
+        roof = roofline_of(score, pk)
+        roof["note"] = ("whole candidates call (threshold pass + merge + main sweep + merge); flops = 2 * users * items * 128 (the model's hidden "
+                        "size; the kernel contracts Kp = 144 columns: bias folded into the table)")
+    return {"metric": "eval_users_per_sec", "value": world * B / (ms / 1e3), "unit": "users/s", "ms_per_step": ms, "n_gpus": world, "steps": steps,
+            "scaling": "weak", "users_per_step_per_gpu": B, "items": V, "hidden": cfg["H"], "seq_len": S, "k": k,
+            "launch": "graph replay of the model part" if module.__dict__.get("_eval_graphs") else "launch by launch",
+            "sharding": "single GPU" if world == 1 else f"catalog rows over {world} ranks: 1 all-gather (hidden rows+targets), 1 all-to-all (lists of own users)",
+            "exact_topk": bool(model.exact_topk), "recall@10": float(res["recall@10"]), "NDCG@10": float(res["NDCG@10"]),
+            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "users/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": 8,
+                    "path": "pinned host (item, item.target) -> H2D -> MaskedTrainingModule.validation_step + step_end -> metric values D2H"},
+            "roofline": roof, "cpu_baseline": cpu, "checks": checks, "kernel_ms_per_step": kernel_ms,
+            "kernels_top5": [{k_: (round(r[k_], 4) if isinstance(r[k_], float) else r[k_]) for k_ in ("kernel", "avg_ms", "share", "bound", "frac")}
+                             for r in table[:5]]}
 
 
 if __name__ == "__main__":

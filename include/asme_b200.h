@@ -354,10 +354,10 @@ int asme_b200_tc_score_ce_partial(const void* Hb, int R, int Kp, const void* Wb,
 /* backward of the fused scoring + cross-entropy layer on the tensor cores: dlogit = (softmax - onehot) * scale is recomputed tile
  * by tile in tensor memory; dH (R,H) fp32 is overwritten, dW (Vloc,H) and dbias (Vloc) are accumulated (+=); any of the three
  * may be NULL (dbias needs dW).  lse = row_max + log(row_sumexp) over the WHOLE catalog (shards combine first). */
-size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp, int Vloc);
+size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp, int Vloc, int plan_rows /* as for the forward; 0 = R */);
 int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
                               const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
-                              void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream);
+                              void* ws, size_t ws_bytes, const int32_t* n_live, int plan_rows, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core dense layers (tcgen05 + TMEM + TMA), bf16 operands / fp32 accumulation.  Same call sites as asme_b200_gemm.

@@ -100,8 +100,8 @@ _PROTOTYPES = {
     "asme_b200_pos_neg_sample": (c_int, [P, c_int, c_int, c_int64, c_int, c_int64, c_uint64, P, P, P, P]),
     "asme_b200_tc_score_ce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "asme_b200_tc_score_ce_partial": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P, c_size_t, P, c_int, P]),
-    "asme_b200_tc_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "asme_b200_tc_score_ce_bwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P, P]),
+    "asme_b200_tc_score_ce_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "asme_b200_tc_score_ce_bwd": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_float, P, P, P, P, c_size_t, P, c_int, P]),
     "asme_b200_tc_gemm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P, P]),
     "asme_b200_tc_gemm_ln": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P,
                                      P, P, P, P, P]),

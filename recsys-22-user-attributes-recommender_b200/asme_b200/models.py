@@ -395,6 +395,7 @@ class TransformerRecommenderModel(ArenaModule):
         hidden, saved = self.encode(seq, padding_mask, attrs, training=self.training)
         rows, row_targets, n_dev = ops.select_rows(target, pad_id)
         plan_rows = self._plan_rows(n_dev)
+        ops.live_rows_hint = plan_rows
         h_rows = ops.gather_rows(hidden, rows, n_dev)
         m_rows, saved_mod = self.modify(h_rows, save=self.training, n_live=n_dev)
         use_tc = self.precision == "bf16"
@@ -410,7 +411,7 @@ class TransformerRecommenderModel(ArenaModule):
         lse = ops.ce_loss_from_partials(rmax, rsum, tl, loss_acc[0:1], n_dev, loss_acc[1:2])
         loss = loss_acc[1]                      # NaN when no position has a target, like the mean over an empty set in torch
         ctx = dict(saved=saved, rows=rows, row_targets=row_targets, m_rows=m_rows, hb=hb, saved_mod=saved_mod, lse=lse, n_dev=n_dev,
-                   T=hidden.shape[0])
+                   T=hidden.shape[0], plan_rows=plan_rows)
         return loss, ctx
 
     def _plan_rows(self, n_dev: torch.Tensor) -> int:
@@ -430,11 +431,12 @@ class TransformerRecommenderModel(ArenaModule):
             wb, b = self.projection_operands_bf16()
             args = (ctx["hb"], wb, b, ctx["row_targets"], ctx["lse"], dloss, self.cfg.hidden)      # the kernels divide by the live count
             # the catalog-gradient sweep (dW, dbias) is a leaf: second stream, next to the whole encoder backward
-            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1, n_live=n_dev), keep=args,
-                                       table_grad=True) is not None:
-                d_m = ops.tc_score_ce_bwd(*args, None, None, n_live=n_dev)
+            plan = ctx["plan_rows"]
+            if self.engine.run_on_side(lambda: ops.tc_score_ce_bwd(*args, dw, db, need_dh=False, slot=1, n_live=n_dev, plan_rows=plan),
+                                       keep=args, table_grad=True) is not None:
+                d_m = ops.tc_score_ce_bwd(*args, None, None, n_live=n_dev, plan_rows=plan)
             else:
-                d_m = ops.tc_score_ce_bwd(*args, dw, db, n_live=n_dev)
+                d_m = ops.tc_score_ce_bwd(*args, dw, db, n_live=n_dev, plan_rows=plan)
         else:
             w, b = self.projection_operands()
             d_m = ops.score_ce_bwd(ctx["m_rows"], w, b, ctx["row_targets"], ctx["lse"], dloss, dw, db, n_live=n_dev)

@@ -166,6 +166,8 @@ class _ModuleBase(_LightningBase):
             meta_b = {k[5:]: v for k, v in b.items() if k.startswith("meta.")}
             rows = rows_fn(b["seq"], b["pm"]) if rows_fn is not None else None
             extra = dict(rows=rows, rows_one_per_sequence=True) if rows is not None else {}
+            if self._catalog_is_sharded():
+                return self.model.evaluate_rank_sharded(b["seq"], b["pm"], meta_b, b["target"], **extra, **kw)
             return self.model.evaluate_rank(b["seq"], b["pm"], meta_b, b["target"], **extra, **kw)
         batch = {"seq": seq, "pm": pm, "target": targets, **{f"meta.{k}": v for k, v in meta.items()}}
         if not getattr(self, "eval_graph", False) or not seq.is_cuda:
@@ -176,6 +178,12 @@ class _ModuleBase(_LightningBase):
         if key not in graphs:
             graphs[key] = GraphedEvalStep(run)
         return dict(graphs[key](batch))
+
+    def _catalog_is_sharded(self) -> bool:
+        """``module.shard_catalog = True`` under torch.distributed: every rank evaluates its own users, the catalog sweep is
+        vocab-sharded over the ranks (asme_b200.sharded; the result carries no item scorer, i.e. all-item metrics only)"""
+        import torch.distributed as dist
+        return bool(getattr(self, "shard_catalog", False)) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     # ---- predict command on the fused path (evaluation/evaluation.py's evaluators consume the result, asme_b200/evaluation.py)
     def _prediction_rows(self, seq, padding_mask):

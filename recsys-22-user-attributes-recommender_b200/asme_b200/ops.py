@@ -18,6 +18,14 @@ from ._lib import EmbedDesc, GemmEpilogue
 SITE_EMBED_A, SITE_EMBED_B = 1, 2
 SITE_LAYER_BASE = 16          # + 8 * layer + {0: attn probs, 1: attn out, 2: ffn inner, 3: ffn out, 4: block end}
 
+live_rows_hint = 0       # rows the caller expects to be live in capacity-sized row selections: only used to annotate timed calls
+
+
+def _note_rows(R: int, n_live) -> int:
+    """row count for the timing annotation (bench.py's cost model): the live rows, not the capacity, when a device count is given"""
+    return live_rows_hint if (n_live is not None and 0 < live_rows_hint < R) else R
+
+
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 _retired: List[torch.Tensor] = []      # outgrown scratch buffers: captured CUDA graphs may still hold their addresses
 
@@ -187,6 +195,8 @@ class SortedIds:
 
     def sort(self):
         """launches phase 1 on the current stream (may differ from the stream the object was created on)"""
+        if _lib.timing is not None:
+            _lib.note = f"T={self.T},H={self.H}"
         _lib.call("asme_b200_embgrad_sort", _p(self.ids), self.T, self.row_divisor, self.H, self.V, self.skip_id, _p(self.ws),
                   self.ws.numel(), _stream())
         return self
@@ -204,6 +214,8 @@ def posgrad_reduce(d_rows: torch.Tensor, B: int, S: int, d_pos: torch.Tensor, pr
     """d_pos[s] += sum_b d_rows[b, prefix + s]; d_rows is (B*(S+prefix), H)"""
     d_rows = _f32(d_rows)
     H = d_rows.shape[-1]
+    if _lib.timing is not None:
+        _lib.note = f"B={B},S={S},H={H}"
     if prefix == 0:
         _lib.call("asme_b200_posgrad_reduce", _p(d_rows), B, S, H, _p(d_pos), _stream())
     else:
@@ -215,6 +227,8 @@ def colsum_accumulate(x: torch.Tensor, out: torch.Tensor):
     M, N = x.shape
     ws_bytes = _lib.query("asme_b200_colsum_workspace_bytes", M, N)
     ws = workspace(ws_bytes, x.device)
+    if _lib.timing is not None:
+        _lib.note = f"M={M},N={N}"
     _lib.call("asme_b200_colsum_accumulate", _p(x), M, N, _p(out), _p(ws), ws.numel(), _stream())
 
 
@@ -229,7 +243,7 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, save
     y = torch.empty_like(x)
     stats = torch.empty(2, M, dtype=torch.float32, device=x.device) if save_stats else None
     if _lib.timing is not None:
-        _lib.note = f"M={M},H={H}"
+        _lib.note = f"M={_note_rows(M, n_live)},H={H}"
     _lib.call("asme_b200_layernorm_fwd", _p(x), _p(gamma), _p(beta), M, H, _p(y), _p(stats), _p(n_live), _stream())
     return y, stats
 
@@ -266,7 +280,7 @@ def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[t
     ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
     ws = workspace(ws_bytes, x.device)
     if _lib.timing is not None:
-        _lib.note = f"M={M},H={H},res={int(d_residual is not None)}"
+        _lib.note = f"M={_note_rows(M, n_live)},H={H},res={int(d_residual is not None)}"
     _lib.call("asme_b200_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
               _p(ws), ws.numel(), _p(n_live), _stream())
     return dx
@@ -309,7 +323,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_b: bool = True, bias=None, act:
     epi.residual = None if residual is None else residual.data_ptr()
     epi.m_live = None if m_live is None else m_live.data_ptr()
     if _lib.timing is not None:
-        _lib.note = f"M={M},N={N},K={K},tb={int(trans_b)},res={int(residual is not None)},pre={int(pre is not None)},aux={int(mul_gelu_grad_of is not None)}"
+        _lib.note = f"M={_note_rows(M, m_live)},N={N},K={K},tb={int(trans_b)},res={int(residual is not None)},pre={int(pre is not None)},aux={int(mul_gelu_grad_of is not None)}"
     _lib.call("asme_b200_gemm", _p(a), _p(b), _p(c), M, N, K, 1 if trans_b else 0, ctypes.byref(epi), _stream())
     return (c, pre) if pre_act_out else c
 
@@ -323,7 +337,7 @@ def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optio
     ws_bytes = _lib.query("asme_b200_gemm_wgrad_workspace_bytes", M, N, K)
     ws = workspace(ws_bytes, x.device)
     if _lib.timing is not None:
-        _lib.note = f"M={M},N={N},K={K}"
+        _lib.note = f"M={_note_rows(M, m_live)},N={N},K={K}"
     _lib.call("asme_b200_gemm_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws),
               ws.numel(), _p(m_live), _stream())
 
@@ -341,7 +355,7 @@ def gelu_backward(dy: torch.Tensor, z: torch.Tensor, n_live=None) -> torch.Tenso
     dy, z = _f32(dy), _f32(z)
     dz = torch.empty_like(dy)
     if _lib.timing is not None:
-        _lib.note = f"n={dy.numel()}"
+        _lib.note = f"n={_note_rows(dy.shape[0], n_live) * dy.shape[-1]}"
     _lib.call("asme_b200_gelu_bwd", _p(dy), _p(z), _p(dz), dy.numel(), dy.shape[-1], _p(n_live), _stream())
     return dz
 
@@ -454,7 +468,7 @@ def cast_bf16(x: torch.Tensor, ld_out: Optional[int] = None, n_live=None) -> tor
     ld_out = padded_k(cols) if ld_out is None else ld_out
     y = torch.empty(rows, ld_out, dtype=torch.bfloat16, device=x.device)
     if _lib.timing is not None:
-        _lib.note = f"rows={rows},cols={cols},ld={ld_out}"
+        _lib.note = f"rows={_note_rows(rows, n_live)},cols={cols},ld={ld_out}"
     _lib.call("asme_b200_cast_bf16", _p(x), _p(y), rows, cols, cols, ld_out, _p(n_live), _stream())
     return y
 
@@ -519,26 +533,27 @@ def tc_score_ce_partial(hb: torch.Tensor, wb: torch.Tensor, bias, target, v0: in
     ws_bytes = _lib.query("asme_b200_tc_score_ce_workspace_bytes", R, Kp, Vloc, plan_rows)
     ws = workspace(ws_bytes, dev)
     if _lib.timing is not None:
-        _lib.note = f"R={R},V={Vloc},H={Kp}"
+        _lib.note = f"R={_note_rows(R, n_live)},V={Vloc},H={Kp}"
     _lib.call("asme_b200_tc_score_ce_partial", _p(hb), R, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
               _p(tl), _p(ws), ws.numel(), _p(n_live), plan_rows, _stream())
     return rmax, rsum, tl
 
 
 def tc_score_ce_bwd(hb, wb, bias, target, lse, scale: float, H: int, dW: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
-                    v0: int = 0, need_dh: bool = True, slot: int = 0, n_live=None) -> Optional[torch.Tensor]:
+                    v0: int = 0, need_dh: bool = True, slot: int = 0, n_live=None, plan_rows: int = 0) -> Optional[torch.Tensor]:
     """tensor-core backward of scoring + CE: returns dH (R,H) fp32; accumulates into dW (Vloc,H) / dbias (Vloc).  With ``n_live``
     the kernels use ``scale / n_live`` (the mean over the live rows) and leave the other rows of dH untouched"""
     hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
     R, Kp = hb.shape
     Vloc = wb.shape[0]
     dh = torch.empty(R, H, dtype=torch.float32, device=hb.device) if need_dh else None
-    ws_bytes = _lib.query("asme_b200_tc_score_ce_bwd_workspace_bytes", R, H, Kp, Vloc)
+    plan_rows = int(plan_rows) if n_live is not None else 0
+    ws_bytes = _lib.query("asme_b200_tc_score_ce_bwd_workspace_bytes", R, H, Kp, Vloc, plan_rows)
     ws = workspace(ws_bytes, hb.device, slot)
     if _lib.timing is not None:
-        _lib.note = f"R={R},V={Vloc},H={Kp}"
+        _lib.note = f"R={_note_rows(R, n_live)},V={Vloc},H={Kp}"
     _lib.call("asme_b200_tc_score_ce_bwd", _p(hb), R, H, Kp, _p(wb), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
-              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _p(n_live), _stream())
+              _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _p(n_live), plan_rows, _stream())
     return dh
 
 
@@ -754,7 +769,7 @@ def score_ce_partial(h, w, bias, target, v0: int = 0, n_live=None):
     ws_bytes = _lib.query("asme_b200_score_ce_workspace_bytes", R, Vloc)
     ws = workspace(ws_bytes, dev)
     if _lib.timing is not None:
-        _lib.note = f"R={R},V={Vloc},H={H}"
+        _lib.note = f"R={_note_rows(R, n_live)},V={Vloc},H={H}"
     _lib.call("asme_b200_score_ce_partial", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(rmax), _p(rsum),
               _p(tl), _p(ws), ws.numel(), _p(n_live), _stream())
     return rmax, rsum, tl
@@ -763,6 +778,8 @@ def score_ce_partial(h, w, bias, target, v0: int = 0, n_live=None):
 def ce_loss_from_partials(rmax, rsum, tl, loss_sum: torch.Tensor, n_live=None, loss_mean: Optional[torch.Tensor] = None):
     """lse (R); loss_sum += sum of the rows' negative log-likelihoods; ``loss_mean`` (1) = loss_sum / number of (live) rows"""
     lse = torch.empty_like(rmax)
+    if _lib.timing is not None:
+        _lib.note = f"R={_note_rows(rmax.numel(), n_live)}"
     _lib.call("asme_b200_ce_loss_from_partials", _p(rmax), _p(rsum), _p(tl), rmax.numel(), _p(lse), _p(loss_sum), _p(n_live),
               _p(loss_mean), _stream())
     return lse
@@ -794,7 +811,7 @@ def score_ce_bwd(h, w, bias, target, lse, scale: float, dW: Optional[torch.Tenso
     ws_bytes = _lib.query("asme_b200_score_ce_bwd_workspace_bytes", R, H, Vloc)
     ws = workspace(ws_bytes, h.device)
     if _lib.timing is not None:
-        _lib.note = f"R={R},V={Vloc},H={H}"
+        _lib.note = f"R={_note_rows(R, n_live)},V={Vloc},H={H}"
     _lib.call("asme_b200_score_ce_bwd", _p(h), R, H, _p(w), _p(bias), v0, Vloc, _p(_i64(target)), _p(lse), float(scale),
               _p(dh), _p(dW), _p(dbias), _p(ws), ws.numel(), _p(n_live), _stream())
     return dh
@@ -825,12 +842,16 @@ def gather_rows(x: torch.Tensor, row_index: torch.Tensor, n_live=None) -> torch.
     x = _f32(x)
     R, H = row_index.numel(), x.shape[1]
     out = torch.empty(R, H, dtype=torch.float32, device=x.device)
+    if _lib.timing is not None:
+        _lib.note = f"R={_note_rows(R, n_live)},H={H}"
     _lib.call("asme_b200_gather_rows", _p(x), _p(_i64(row_index)), R, H, _p(out), _p(n_live), _stream())
     return out
 
 
 def scatter_rows(rows: torch.Tensor, row_index: torch.Tensor, out: torch.Tensor, n_live=None):
     rows = _f32(rows)
+    if _lib.timing is not None:
+        _lib.note = f"R={_note_rows(rows.shape[0], n_live)},H={rows.shape[1]}"
     _lib.call("asme_b200_scatter_rows", _p(rows), _p(_i64(row_index)), rows.shape[0], rows.shape[1], _p(out), _p(n_live), _stream())
 
 
@@ -844,6 +865,8 @@ def select_rows(target: torch.Tensor, ignore_id: int):
     row_targets = torch.empty(T, dtype=torch.int64, device=target.device)
     n_rows = torch.empty(1, dtype=torch.int32, device=target.device)
     ws = workspace(_lib.query("asme_b200_select_rows_workspace_bytes", T), target.device)
+    if _lib.timing is not None:
+        _lib.note = f"T={T}"
     _lib.call("asme_b200_select_rows", _p(target), T, int(ignore_id), _p(rows), _p(row_targets), _p(n_rows), _p(ws), ws.numel(), _stream())
     return rows, row_targets, n_rows
 
@@ -873,4 +896,6 @@ def adam_step_dev(param, grad, m, v, state: torch.Tensor, beta1, beta2, eps, wei
 
 
 def fill(x: torch.Tensor, value: float):
+    if _lib.timing is not None:
+        _lib.note = f"n={x.numel()}"
     _lib.call("asme_b200_fill", _p(x), x.numel(), float(value), _stream())

@@ -334,11 +334,14 @@ struct CePlan {
     int row_tiles, col_tiles, splits, tiles_per_split, kch, stages;
     size_t smem;
 };
-static int ce_plan(int n_rows, int n_cols, int Kp, CePlan* p) {
+// ``plan_rows`` (0 = n_rows): how many of the rows are expected to be live (row selections pass their capacity and the count on the
+// device); only the split of the streamed dimension over CTAs is chosen from it
+static int ce_plan(int n_rows, int n_cols, int Kp, CePlan* p, int plan_rows = 0) {
     p->kch = Kp / CHUNK_K;
     p->row_tiles = ceil_div(n_rows, CE_TILE);
     p->col_tiles = ceil_div(n_cols, CE_TILE);
-    int splits = ASME_NUM_SMS / p->row_tiles;
+    const int fill_tiles = (plan_rows > 0 && plan_rows < n_rows) ? ceil_div(plan_rows, CE_TILE) : p->row_tiles;
+    int splits = ASME_NUM_SMS / fill_tiles;
     if (splits < 1) splits = 1;
     if (splits > p->col_tiles) splits = p->col_tiles;
     p->tiles_per_split = ceil_div(p->col_tiles, splits);
@@ -353,10 +356,10 @@ static int ce_plan(int n_rows, int n_cols, int Kp, CePlan* p) {
     return ASME_OK;
 }
 
-extern "C" size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp, int Vloc) {
+extern "C" size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp, int Vloc, int plan_rows) {
     CePlan a, b;
     if (R < 1) R = 1;
-    if (ce_plan(R, Vloc, Kp, &a) || ce_plan(Vloc, R, Kp, &b)) return 0;
+    if (ce_plan(R, Vloc, Kp, &a, plan_rows) || ce_plan(Vloc, R, Kp, &b)) return 0;
     const size_t wa = (size_t)a.splits * R * H;
     const size_t wb = (size_t)b.splits * ((size_t)Vloc * H + Vloc);
     return (wa > wb ? wa : wb) * sizeof(float);
@@ -364,12 +367,13 @@ extern "C" size_t asme_b200_tc_score_ce_bwd_workspace_bytes(int R, int H, int Kp
 
 extern "C" int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
                                          const int64_t* target, const float* lse, float scale, float* dH, float* dW, float* dbias,
-                                         void* ws, size_t ws_bytes, const int32_t* n_live, asme_stream_t stream) {
+                                         void* ws, size_t ws_bytes, const int32_t* n_live, int plan_rows, asme_stream_t stream) {
     ASME_REQUIRE(Hb && Wb && target && lse, "tc_score_ce_bwd: null argument");
+    if (!n_live) plan_rows = 0;
     ASME_REQUIRE(Kp >= 64 && Kp <= 256 && Kp % 64 == 0 && H <= Kp && H % 4 == 0, "tc_score_ce_bwd: H=%d Kp=%d unsupported", H, Kp);
     ASME_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "tc_score_ce_bwd: bias must be 16-byte aligned");
     if (R == 0) return ASME_OK;
-    ASME_REQUIRE(ws_bytes >= asme_b200_tc_score_ce_bwd_workspace_bytes(R, H, Kp, Vloc), "tc_score_ce_bwd: workspace too small");
+    ASME_REQUIRE(ws_bytes >= asme_b200_tc_score_ce_bwd_workspace_bytes(R, H, Kp, Vloc, plan_rows), "tc_score_ce_bwd: workspace too small");
     CUtensorMap tmH, tmW;
     int rc = asme_tc_make_tmap_bf16(&tmH, Hb, R, Kp, Kp, CE_TILE);
     if (rc) return rc;
@@ -381,7 +385,7 @@ extern "C" int asme_b200_tc_score_ce_bwd(const void* Hb, int R, int H, int Kp, c
     a.partial = (float*)ws;
     if (dH) {
         CePlan p;
-        rc = ce_plan(R, Vloc, Kp, &p);
+        rc = ce_plan(R, Vloc, Kp, &p, plan_rows);
         if (rc) return rc;
         a.kch = p.kch; a.stages = p.stages; a.n_row_tiles = p.row_tiles; a.n_col_tiles = p.col_tiles; a.col_tiles_per_split = p.tiles_per_split;
         a.partial_bias = nullptr;
