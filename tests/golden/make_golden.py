@@ -282,6 +282,104 @@ def user_fixtures():
     print("usasrec full loss", float(loss))
 
 
+def postfusion_fixtures():
+    """post-fusion attributes: the attribute embeddings are merged into the ENCODED sequence, by ``add`` or
+    ``multiply``, before the modifier transform (KeBERT4Rec, models/kebert4rec/components.py:97-116) or instead of it (SASRec,
+    models/sasrec/components.py:88-106)."""
+    from asme.core.models.kebert4rec.kebert4rec_model import KeBERT4RecModel
+    from asme.core.models.sasrec.sasrec_model import SASRecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    V, S, H, L, heads, B, VA, VT, A = 59, 8, 16, 1, 2, 5, 11, 17, 3
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V), "category": ref_shims.make_tokenizer(VA, "c"),
+                                     "tags": ref_shims.make_tokenizer(VT, "t")})
+    for merge in ("add", "multiply"):
+        gen = torch.Generator().manual_seed(606 + len(merge))
+        # ---- KeBERT4Rec: one pre-fused and two post-fused attributes (a table and an id-bag Linear)
+        model = KeBERT4RecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                                max_seq_length=S, transformer_dropout=0.0,
+                                prefusion_attributes={"category": {"embedding_type": "content_embedding"}},
+                                postfusion_attributes={"category": {"embedding_type": "content_embedding"},
+                                                       "tags": {"embedding_type": "linear_upscale"}},
+                                postfusion_merge_function=merge)
+        randomize(model, gen)
+        seq, lengths = make_sequences(gen, B, S, V)
+        inp, tgt = cloze(seq, lengths, gen)
+        cat = torch.randint(3, VA, (B, S), generator=gen)
+        tags = torch.randint(0, VT, (B, S, A), generator=gen)
+        cat[inp == 0] = 0
+        cat[inp == 1] = 1
+        tags[inp == 0] = 0
+        logits = model(InputSequence(inp, inp.ne(0), {"category": cat, "tags": tags}))
+        loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, V), tgt.view(-1))
+        loss.backward()
+        data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": inp, "target": tgt, "category": cat, "tags": tags,
+                "logits": logits, "loss": loss}
+        data.update(weights_of(model))
+        data.update(grads_of(model))
+        np.savez_compressed(os.path.join(HERE, f"kebert4rec_postfusion_{merge}.npz"), **to_np(data))
+        print(f"kebert4rec postfusion {merge} loss", float(loss))
+        # ---- SASRec (mode="full"): identity modifier with one post-fused table
+        model = SASRecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L,
+                            max_seq_length=S, transformer_dropout=0.0, mode="full",
+                            postfusion_attributes={"category": {"embedding_type": "content_embedding"}},
+                            postfusion_merge_function=merge)
+        randomize(model, gen)
+        tgt = torch.zeros_like(seq)
+        for i in range(B):
+            n = int(lengths[i])
+            tgt[i, :n] = torch.randint(3, V, (n,), generator=gen)
+        c = torch.randint(3, VA, (B, S), generator=gen)
+        c[seq == 0] = 0
+        logits = model(InputSequence(seq, seq.ne(0), {"category": c}))
+        loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.reshape(-1, V), tgt.reshape(-1))
+        loss.backward()
+        data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": seq, "target": tgt, "category": c, "logits": logits, "loss": loss}
+        data.update(weights_of(model))
+        data.update(grads_of(model))
+        np.savez_compressed(os.path.join(HERE, f"sasrec_postfusion_{merge}.npz"), **to_np(data))
+        print(f"sasrec postfusion {merge} loss", float(loss))
+
+
+def init_stats_fixture():
+    """row a19: per-parameter statistics of the reference's initialisers (models/bert4rec/bert4rec_model.py:59-68 N(0, range) applied
+    AFTER models/transformer/transformer_encoder_model.py:63-73 xavier-normal; layers.py:134-136 U(+-1/sqrt(V)) for ``output_bias``)
+    for every model family at a shape large enough for a statistical comparison."""
+    from asme.core.models.bert4rec.bert4rec_model import BERT4RecModel
+    from asme.core.models.kebert4rec.kebert4rec_model import KeBERT4RecModel
+    from asme.core.models.sasrec.sasrec_model import SASRecModel
+    from asme.core.models.ubert4rec.ubert4rec_model import UBERT4RecModel
+    from asme.core.models.user_sasrec.user_sasrec_model import UserSASRecModel
+    V, S, H, L, heads, VA, VT, VU = 2003, 32, 64, 1, 2, 301, 157, 211
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V), "category": ref_shims.make_tokenizer(VA, "c"),
+                                     "tags": ref_shims.make_tokenizer(VT, "t"), "user_id": ref_shims.make_tokenizer(VU, "u")})
+    toks = {"tokenizers.user_id": ref_shims.make_tokenizer(VU, "u"), "tokenizers.category": ref_shims.make_tokenizer(VA, "c")}
+    kw = dict(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L, max_seq_length=S, transformer_dropout=0.1)
+    pre = {"category": {"embedding_type": "content_embedding"}, "tags": {"embedding_type": "linear_upscale"}}
+    ukw = dict(item_vocab_size=V, additional_tokenizers=toks, additional_attributes={"category": {"embedding_type": "content_embedding"}},
+               user_attributes={"user_id": {"embedding_type": "user_embedding"}}, **kw)
+    torch.manual_seed(7)
+    models = {
+        "bert4rec": BERT4RecModel(**kw),
+        "bert4rec_range_0.1": BERT4RecModel(initializer_range=0.1, **kw),
+        "kebert4rec": KeBERT4RecModel(prefusion_attributes=pre, postfusion_attributes={"category": {"embedding_type": "content_embedding"}}, **kw),
+        "sasrec_full": SASRecModel(mode="full", **kw),
+        "sasrec_neg": SASRecModel(mode="neg_sampling", **kw),
+        "ubert4rec": UBERT4RecModel(positional_embedding=True, segment_embedding=True, **ukw),
+        "usasrec_full": UserSASRecModel(segment_embedding=False, mode="full", **ukw),
+    }
+    out = {"shape": dict(V=V, S=S, H=H, L=L, heads=heads, VA=VA, VT=VT, VU=VU), "models": {}}
+    for name, model in models.items():
+        stats = {}
+        for pname, p in model.named_parameters():
+            x = p.detach().double()
+            stats[pname] = {"shape": list(p.shape), "mean": float(x.mean()), "std": float(x.std(unbiased=False)), "min": float(x.min()),
+                            "max": float(x.max())}
+        out["models"][name] = stats
+    with open(os.path.join(HERE, "init_stats.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("init stats:", {k: len(v) for k, v in out["models"].items()})
+
+
 def metrics_fixture():
     """Reference metric classes on random scores; ties are made deterministic by patching
     torch.argsort to a stable sort inside the reference call (the reference's own argsort is
@@ -334,7 +432,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1:]
     steps = {"metric_vectors": export_metric_vectors, "bert4rec": bert4rec_fixture, "kebert4rec": kebert4rec_fixture,
-             "sasrec": sasrec_fixtures, "user": user_fixtures, "metrics": metrics_fixture}
+             "sasrec": sasrec_fixtures, "user": user_fixtures, "postfusion": postfusion_fixtures, "init": init_stats_fixture, "metrics": metrics_fixture}
     for name, fn in steps.items():
         if not only or name in only:
             fn()

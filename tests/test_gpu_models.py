@@ -101,6 +101,27 @@ def test_sasrec_full_vs_reference_fixture(golden_dir):
     assert np.array_equal(out["rank"].cpu().numpy(), O.target_rank(z["eval_logits"], et.numpy()))
 
 
+@pytest.mark.parametrize("name", ["kebert4rec_postfusion_add.npz", "kebert4rec_postfusion_multiply.npz", "sasrec_postfusion_add.npz",
+                                  "sasrec_postfusion_multiply.npz"])
+def test_postfusion_attributes_vs_reference_fixture(golden_dir, name):
+    """row a9: attribute embeddings merged into the encoded sequence (add / multiply) before (KeBERT4Rec) or instead of (SASRec) the
+    modifier transform -- logits, loss and every gradient (incl. the post-fused tables and the id-bag Linear) vs the unmodified
+    reference (models/kebert4rec/components.py:97-116, models/sasrec/components.py:88-106)"""
+    from asme_b200.data import InputSequence
+    z, w, model = build_from_fixture(golden_dir, name)
+    model.load_state_dict(w)
+    model = model.cuda().train()
+    inp, tgt = torch.from_numpy(z["input"]).cuda(), torch.from_numpy(z["target"]).cuda()
+    attrs = {k: torch.from_numpy(z[k]).cuda() for k in ("category", "tags") if k in z.files}
+    close(model(InputSequence(inp, inp.ne(0), attrs)), z["logits"], msg="logits")
+    loss, ctx = model.loss_ce(inp, inp.ne(0), attrs, tgt)
+    close(loss, z["loss"], msg="loss")
+    model.loss_ce_backward(ctx)
+    _check_grads(model, z)
+    post = [n for n, p in model.named_parameters() if "postfusion_attribute_embeddings" in n and p.grad is not None]
+    assert post and all(float(dict(model.named_parameters())[n].grad.abs().sum()) > 0 for n in post)
+
+
 def test_sasrec_neg_vs_reference_fixture(golden_dir):
     from asme_b200.data import InputSequence
     z, w, model = build_from_fixture(golden_dir, "sasrec_neg_small.npz")

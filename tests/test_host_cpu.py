@@ -19,8 +19,22 @@ def build_from_fixture(golden_dir, name):
     z, w = _fixture_weights(golden_dir, name)
     kw = dict(transformer_hidden_size=int(z["H"]), num_transformer_heads=int(z["heads"]), num_transformer_layers=int(z["L"]),
               item_vocab_size=int(z["V"]), max_seq_length=int(z["S"]), transformer_dropout=0.0)
+    post = "_sequence_representation_modifier_layer.postfusion_attribute_embeddings"
     if name.startswith("bert4rec"):
         model = BERT4RecModel(**kw)
+    elif name.startswith("kebert4rec_postfusion") or name.startswith("sasrec_postfusion"):
+        merge = name.split("_")[2].split(".")[0]
+        if name.startswith("kebert4rec"):
+            model = KeBERT4RecModel(prefusion_attributes={"category": {"embedding_type": "content_embedding"}},
+                                    postfusion_attributes={"category": {"embedding_type": "content_embedding"},
+                                                           "tags": {"embedding_type": "linear_upscale"}},
+                                    postfusion_merge_function=merge,
+                                    attribute_vocab_sizes={"category": w[f"{post}.category.weight"].shape[0],
+                                                           "tags": w[f"{post}.tags.linear.weight"].shape[1]}, **kw)
+        else:
+            model = SASRecModel(mode="full", postfusion_attributes={"category": {"embedding_type": "content_embedding"}},
+                                postfusion_merge_function=merge,
+                                attribute_vocab_sizes={"category": w[f"{post}.category.weight"].shape[0]}, **kw)
     elif name.startswith("kebert4rec"):
         model = KeBERT4RecModel(prefusion_attributes={"category": {"embedding_type": "content_embedding"},
                                                       "tags": {"embedding_type": "linear_upscale"}},
@@ -45,7 +59,8 @@ def build_from_fixture(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", ["bert4rec_small.npz", "kebert4rec_small.npz", "sasrec_full_small.npz", "sasrec_neg_small.npz",
-                                  "ubert4rec_small.npz", "usasrec_full_small.npz"])
+                                  "ubert4rec_small.npz", "usasrec_full_small.npz", "kebert4rec_postfusion_add.npz",
+                                  "kebert4rec_postfusion_multiply.npz", "sasrec_postfusion_add.npz", "sasrec_postfusion_multiply.npz"])
 def test_state_dict_is_checkpoint_compatible(golden_dir, name):
     """every key of the reference's state_dict exists with the same shape, and loads strictly"""
     z, w, model = build_from_fixture(golden_dir, name)
@@ -309,3 +324,63 @@ def test_result_writers(tmp_path):
     assert E.check_file_format_supported("x.json") and not E.check_file_format_supported("x.txt")
     with open(tmp_path / "r.txt", "w") as f, pytest.raises(KeyError, match="not a supported format"):
         E.build_result_writer(f)
+
+
+# ---- row a19: initialisers ---------------------------------------------------------------------------------------------------------
+def _init_models():
+    import json
+    from asme_b200.models import UBERT4RecModel, UserSASRecModel
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "init_stats.json")) as f:
+        ref = json.load(f)
+    sh = ref["shape"]
+    kw = dict(transformer_hidden_size=sh["H"], num_transformer_heads=sh["heads"], num_transformer_layers=sh["L"], item_vocab_size=sh["V"],
+              max_seq_length=sh["S"], transformer_dropout=0.1)
+    sizes = {"category": sh["VA"], "tags": sh["VT"], "user_id": sh["VU"]}
+    pre = {"category": {"embedding_type": "content_embedding"}, "tags": {"embedding_type": "linear_upscale"}}
+    ukw = dict(additional_attributes={"category": {"embedding_type": "content_embedding"}},
+               user_attributes={"user_id": {"embedding_type": "user_embedding"}}, attribute_vocab_sizes=sizes, **kw)
+    torch.manual_seed(11)
+    ours = {
+        "bert4rec": BERT4RecModel(**kw),
+        "bert4rec_range_0.1": BERT4RecModel(initializer_range=0.1, **kw),
+        "kebert4rec": KeBERT4RecModel(prefusion_attributes=pre, postfusion_attributes={"category": {"embedding_type": "content_embedding"}},
+                                      attribute_vocab_sizes=sizes, **kw),
+        "sasrec_full": SASRecModel(mode="full", **kw),
+        "sasrec_neg": SASRecModel(mode="neg_sampling", **kw),
+        "ubert4rec": UBERT4RecModel(segment_embedding=True, **ukw),
+        "usasrec_full": UserSASRecModel(mode="full", **ukw),
+    }
+    return ref["models"], ours
+
+
+@pytest.mark.parametrize("name", ["bert4rec", "bert4rec_range_0.1", "kebert4rec", "sasrec_full", "sasrec_neg", "ubert4rec", "usasrec_full"])
+def test_initialisers_match_the_reference_statistics(name):
+    """freshly constructed models: every parameter the reference creates exists with the same shape, constants (LayerNorm 1 / 0, zero
+    biases) are exact, random tensors have the reference initialiser's distribution -- N(0, initializer_range) after
+    normal_initialize_weights (bert4rec_model.py:59-68), xavier-normal for the SASRec family (transformer_encoder_model.py:63-73),
+    U(+-1/sqrt(V)) for ``output_bias`` (layers.py:134-136).  The reference's statistics come from tests/golden/init_stats.json."""
+    import math
+    ref_all, ours_all = _init_models()
+    ref, model = ref_all[name], ours_all[name]
+    params = dict(model.named_parameters())
+    sd = model.state_dict()
+    for pname, st in ref.items():
+        assert pname in sd, f"{name}: missing parameter {pname}"
+        p = sd[pname].detach().double()
+        assert list(p.shape) == st["shape"], pname
+        n = p.numel()
+        if st["std"] == 0.0:                                   # constants: LayerNorm weight 1, every bias 0
+            assert float(p.min()) == float(p.max()) == st["mean"], pname
+            continue
+        std, mean = float(p.std(unbiased=False)), float(p.mean())
+        tol = 4.0 / math.sqrt(2 * n) + 0.01                     # sampling error of a standard deviation (both sides) + slack
+        assert abs(std / st["std"] - 1.0) < 2 * tol, f"{name}.{pname}: std {std} vs reference {st['std']}"
+        assert abs(mean - st["mean"]) < 6 * st["std"] / math.sqrt(n) * 1.5, f"{name}.{pname}: mean {mean} vs {st['mean']}"
+        if pname.endswith("output_bias"):                       # uniform, not normal: hard bounds
+            bound = 1.0 / math.sqrt(n)
+            assert float(p.min()) >= -bound and float(p.max()) <= bound
+            assert abs(std - bound / math.sqrt(3)) < 0.05 * bound
+        else:                                                   # normal: about 0.27 % beyond three standard deviations
+            frac = float((p.abs() > 3 * st["std"]).double().mean())
+            assert frac < 0.01 + 8.0 / n, f"{name}.{pname}: {frac} of the entries beyond 3 sigma"
+    assert params, name
