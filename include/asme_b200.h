@@ -128,6 +128,10 @@ int asme_b200_colsum_accumulate_live(const float* x, int M, int N, float* out /*
                                      const int32_t* m_live, asme_stream_t stream);
 size_t asme_b200_colsum_workspace_bytes(int M, int N);
 
+/* diagnostic: knob 0 = 1 (default): the forward row kernels (embedding gather, LayerNorm) give a row to H/16 lanes with four
+ * 128-bit chunks each; 0: H/4 lanes with one chunk (the first layout, ALU-bound at H = 128).  Results differ only in the summation
+ * order of the LayerNorm statistics. */
+int asme_b200_rowwise_tune(int knob, int value);
 /* ------------------------------------------------------------------------------------------
  * K4/K6/K11  LayerNorm (eps 1e-5, biased variance) forward / backward
  * replaces: nn.LayerNorm in SublayerConnection (transformer_layers.py:120-130) and the FFN modifier
@@ -318,8 +322,14 @@ int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void* Wb, const
 int asme_b200_table_norm_bound(const float* W, int V, int H, const float* bias /*NULL ok*/, float* out3, asme_stream_t stream);
 /* candidates for the exact top-k: cand_val / cand_idx (R,k_out) = the k_out best by bf16 score among what the sweep's lists kept,
  * bound (R) = upper bound of the bf16 score of every item in NONE of the row's lists (-inf: the list is the true bf16 top k_out) */
+/* bias_bounds (ceil(Vloc/32), 2) = {max, min} of bias over every 32-column chunk of the slice (asme_b200_bias_chunk_bounds, cache it
+ * until the weights change): with it the sweep keeps the bias OUT of the contraction (Kp = hidden size instead of hidden + 16 folded
+ * columns, layers.py:138-143) and out of the hot epilogue -- the exact fp32 bias is added only to chunks whose best raw score plus
+ * the chunk's largest bias could pass the row's threshold. */
+int asme_b200_bias_chunk_bounds(const float* bias, int V, float* bounds, asme_stream_t stream);
 size_t asme_b200_tc_score_candidates_workspace_bytes(int R, int Kp, int Vloc, int k, int k_out);
-int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, const float* bias_bounds /*NULL ok*/,
+                                  int v0, int Vloc,
                                   const int64_t* target /*NULL ok*/, int k, int k_out, float* cand_val, int32_t* cand_idx, float* bound,
                                   float* target_score_out /*NULL ok: bf16 score of the target, owner shard writes*/, void* ws,
                                   size_t ws_bytes, asme_stream_t stream);
@@ -379,6 +389,16 @@ int asme_b200_tc_gemm_ln(const void* A, const void* B, int M, int N, int K, int 
                          unsigned int post_site, const float* residual, float* out_f32, void* out_bf16, int ld_bf16,
                          void* pre_act_bf16, const float* ln_gamma, const float* ln_beta, void* ln_out, float* ln_stats,
                          asme_stream_t stream);
+/* Position-wise feed-forward block as ONE kernel (inference; models/common/layers/transformer_layers.py:217-220 + the residual of
+ * SublayerConnection :120-130): out = residual + W2 gelu(W1 Y + b1) + b2, the (M, FF) intermediate stays in shared / tensor memory.
+ * Y (M,H) bf16 = the LayerNorm'ed input, W1 (FF,H) / W2 (H,FF) bf16 (nn.Linear layouts), residual (M,H) fp32; H in {64, 128},
+ * FF % 64 == 0.  out_f32 (M,H) and / or ln_out (M,H) bf16 = LayerNorm(out; ln_gamma, ln_beta) (the next block's input).  The fp32
+ * output equals asme_b200_tc_gemm(act = GELU, bf16 out) followed by asme_b200_tc_gemm(residual) bit for bit. */
+int asme_b200_tc_ffn_fused(const void* Y, const void* W1, const float* b1, const void* W2, const float* b2, const float* residual,
+                           int M, int H, int FF, float* out_f32, const float* ln_gamma, const float* ln_beta, void* ln_out,
+                           asme_stream_t stream);
+/* diagnostic: knob 0 = GELU warpgroups of asme_b200_tc_ffn_fused (0 = automatic, default; 2; 4) */
+int asme_b200_tc_ffn_tune(int knob, int value);
 /* diagnostic: knob 0 selects the tall kernel (1 = persistent CTAs with a resident weight tile, default; 0 = one CTA per tile) */
 int asme_b200_tc_gemm_tune(int knob, int value);
 /* dW (N,K) fp32 (+)= dY(M,N)^T X(M,K), dbias (N) (+)= colsum(dY); dY, X bf16; token contraction split over the SMs with a
@@ -413,7 +433,8 @@ int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int 
                           float p_drop, const void* ctx, const void* d_ctx, const float* stats,
                           const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream);
 /* diagnostic: knob 0 selects the backward kernel (1 = single sweep, default; 0 = two sweeps), knob 1 the epilogue warpgroups of the
- * single-sweep kernel (2 or 4); results agree to rounding */
+ * single-sweep kernel (2 or 4), knob 2 the forward kernel (2 = probabilities in tensor memory as the A operand of the second MMA,
+ * two CTAs per SM, default when the grid fills the machine; 1 = probabilities through shared memory); results agree to rounding */
 int asme_b200_tc_attn_tune(int knob, int value);
 
 /* ------------------------------------------------------------------------------------------

@@ -95,6 +95,8 @@ _PROTOTYPES = {
     "asme_b200_tc_score_tune": (c_int, [c_int, c_int]),
     "asme_b200_tc_attn_tune": (c_int, [c_int, c_int]),
     "asme_b200_tc_gemm_tune": (c_int, [c_int, c_int]),
+    "asme_b200_rowwise_tune": (c_int, [c_int, c_int]),
+    "asme_b200_tc_ffn_tune": (c_int, [c_int, c_int]),
     "asme_b200_cloze_mask": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_int64, c_float, c_float, c_uint64, P]),
     "asme_b200_weighted_negatives": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_uint64, P, P, P]),
     "asme_b200_pos_neg_sample": (c_int, [P, c_int, c_int, c_int64, c_int, c_int64, c_uint64, P, P, P, P]),
@@ -105,6 +107,7 @@ _PROTOTYPES = {
     "asme_b200_tc_gemm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P, P]),
     "asme_b200_tc_gemm_ln": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P,
                                      P, P, P, P, P]),
+    "asme_b200_tc_ffn_fused": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
     "asme_b200_tc_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "asme_b200_tc_attn_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P, P]),
@@ -116,7 +119,8 @@ _PROTOTYPES = {
     "asme_b200_table_norm_bound": (c_int, [P, c_int, c_int, P, P, P]),
     "asme_b200_topk_rescore": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, P, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "asme_b200_tc_score_candidates_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
-    "asme_b200_tc_score_candidates": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_tc_score_candidates": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "asme_b200_bias_chunk_bounds": (c_int, [P, c_int, P, P]),
     "asme_b200_score_topk_flagged_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_score_topk_flagged": (c_int, [P, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     "asme_b200_gather_rows": (c_int, [P, P, c_int, c_int, P, P, P]),

@@ -22,6 +22,10 @@ from ._lib import ACT_GELU, ACT_NONE
 
 # weight gradients of the tensor-core backward on a second stream (ASME_B200_SIDE_WGRAD=0 keeps everything on one stream)
 SIDE_STREAM_WGRAD = os.environ.get("ASME_B200_SIDE_WGRAD", "1") == "1"
+# inference: feed-forward block as one kernel (asme_b200_tc_ffn_fused); ASME_B200_FUSED_FFN=0 keeps the two GEMM launches,
+# ASME_B200_FUSED_FFN_LN=0 keeps the next block's LayerNorm as its own launch (bit-identical bf16 rows to the unfused path)
+FUSED_FFN = os.environ.get("ASME_B200_FUSED_FFN", "1") == "1"
+FUSED_FFN_LN = os.environ.get("ASME_B200_FUSED_FFN_LN", "1") == "1"
 
 BLOCKS = "_sequence_representation_layer.transformer_layer.transformer_blocks"
 MODIFIER = "_sequence_representation_modifier_layer"
@@ -223,14 +227,24 @@ class EncoderEngine:
                             site=self._site(l, 1), residual=x,
                             ln=(self._w(f"{pre}.output_sublayer.norm.weight"), self._w(f"{pre}.output_sublayer.norm.bias")), ln_stats=train)
             ls.x2, ls.y2, ls.st2 = r["f32"], r["ln16"], r["ln_st"]
-            r = ops.tc_gemm(ls.y2, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), bias=self._w(f"{pre}.feed_forward.w_1.bias"),
-                            act=ACT_GELU, p_drop=p, seed=saved.seed, site=self._site(l, 2), out_f32=False, out_bf16=True,
-                            pre_act=train)
-            ls.a, ls.z = r["bf16"], r["pre"]
             nxt = None
             if l + 1 < cfg.layers:          # the next layer's input LayerNorm rides in this GEMM's epilogue
                 npre = f"{self.blocks}.{l + 1}"
                 nxt = (self._w(f"{npre}.input_sublayer.norm.weight"), self._w(f"{npre}.input_sublayer.norm.bias"))
+            if not train and FUSED_FFN and H in (64, 128) and cfg.intermediate % 64 == 0:
+                # inference: the whole feed-forward block (+ the next block's LayerNorm) in one kernel, no (T, 4H) intermediate
+                r = ops.tc_ffn_fused(ls.y2, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), self._w(f"{pre}.feed_forward.w_1.bias"),
+                                     m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), self._w(f"{pre}.feed_forward.w_2.bias"), ls.x2,
+                                     ln=nxt if FUSED_FFN_LN else None)
+                x = r["f32"]
+                if nxt is not None and not FUSED_FFN_LN:
+                    r["ln16"], _, _ = ops.layernorm_fwd_bf16(x, nxt[0], nxt[1], save_stats=False)
+                y1_next, st1_next = (r["ln16"], None) if nxt is not None else (None, None)
+                continue
+            r = ops.tc_gemm(ls.y2, m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), bias=self._w(f"{pre}.feed_forward.w_1.bias"),
+                            act=ACT_GELU, p_drop=p, seed=saved.seed, site=self._site(l, 2), out_f32=False, out_bf16=True,
+                            pre_act=train)
+            ls.a, ls.z = r["bf16"], r["pre"]
             r = ops.tc_gemm(ls.a, m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), bias=self._w(f"{pre}.feed_forward.w_2.bias"),
                             p_drop=p, seed=saved.seed, site=self._site(l, 3), residual=ls.x2,
                             post_site=self._site(l, 4) if p > 0 else 0, ln=nxt, ln_stats=train)

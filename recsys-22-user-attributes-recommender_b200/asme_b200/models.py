@@ -337,6 +337,21 @@ class TransformerRecommenderModel(ArenaModule):
             self._wb_folded = (stamp, ops.cast_bf16_ext(w, b))
         return self._wb_folded[1], True
 
+    def projection_bias_bounds(self, v0: int = 0, v1: Optional[int] = None):
+        """(bias slice as its own 16-byte-aligned tensor, per-32-item {max, min} of it) for the catalog slice [v0, v1) -- what the
+        exact top-k sweep needs to keep the bias out of the contraction (ops.tc_score_candidates(bias_bounds=...)); None without a
+        bias.  Cached until the weights change."""
+        w, b = self.projection_operands()
+        if b is None:
+            return None
+        v1 = b.numel() if v1 is None else v1
+        stamp = (self._arena.version, self._arena.flat._version, b.data_ptr(), v0, v1)
+        cache = getattr(self, "_bias_bounds", None)
+        if cache is None or cache[0] != stamp:
+            bs = b[v0:v1].clone() if (v0 != 0 or v1 != b.numel() or b.data_ptr() % 16) else b
+            self._bias_bounds = (stamp, (bs, ops.bias_chunk_bounds(bs)))
+        return self._bias_bounds[1]
+
     def projection_norm_bound(self):
         """(2): max row norm of the catalog table and max |bias| (ops.table_norm_bound), cached until the weights change"""
         w, b = self.projection_operands()
@@ -528,6 +543,13 @@ class TransformerRecommenderModel(ArenaModule):
 
     def _evaluate_rows(self, m_rows, target, k, with_loss, pad_id, full_rank):
         if self.precision == "bf16":
+            if BIAS_BOUNDS and self.exact_topk and not with_loss and not (full_rank and target is not None):
+                # the usual evaluation call (@k metrics): the catalog table as it lies in the arena's bf16 shadow, K = hidden size, the
+                # bias bounded per chunk (the folded operands below cost a ninth K step per tile and a second copy of the table)
+                wb, _ = self.projection_operands_bf16()
+                hb = ops.cast_bf16(m_rows, ld_out=wb.shape[1])
+                return score_rows_tc_exact(m_rows, hb, wb, *self.projection_operands(), self.projection_norm_bound(), target, k, False,
+                                           bias_bounds=self.projection_bias_bounds())
             wb, folded = self.projection_operands_folded()
             b = None
             hb = ops.cast_bf16_ext(m_rows) if folded else ops.cast_bf16(m_rows, ld_out=wb.shape[1])
@@ -568,7 +590,11 @@ def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, 
     m_rows, _ = self.modify(self.encode_rows(seq, padding_mask, attrs, rows, one_per_sequence=one))
     G = dist.get_world_size(group) if dist.is_initialized() else 1
     g = dist.get_rank(group) if dist.is_initialized() else 0
-    wb, folded = self.projection_operands_folded()          # bias (if any) rides in two extra K columns of the table
+    plain = BIAS_BOUNDS and self.exact_topk and not full_rank and not with_loss and self.precision == "bf16"
+    if plain:       # @k metrics only: the plain table slice, the bias bounded per chunk (see _evaluate_rows)
+        wb, folded = self.projection_operands_bf16()[0], False
+    else:
+        wb, folded = self.projection_operands_folded()          # bias (if any) rides in two extra K columns of the table
     v0, v1 = sharded.shard_range(wb.shape[0], G, g)
     exact = None
     if self.exact_topk:
@@ -578,11 +604,22 @@ def _evaluate_rank_sharded(self, seq, padding_mask, attrs, target, k: int = 10, 
         if cache is None or cache[0] != stamp:
             self._shard_norm_bound = (stamp, ops.table_norm_bound(w32[v0:v1], None if b32 is None else b32[v0:v1]))
         exact = (w32[v0:v1], None if b32 is None else b32[v0:v1], self._shard_norm_bound[1])
-    return sharded.sharded_topk_rank(m_rows, target, k, sharded.tc_local_scorer(wb[v0:v1], None, v0, folded, exact=exact), sharded.tc_merge,
+    bb = self.projection_bias_bounds(v0, v1) if plain else None
+    scorer = sharded.tc_local_scorer(wb[v0:v1], bb[0] if bb is not None else None, v0, folded, exact=exact,
+                                     bias_bounds=bb[1] if bb is not None else None)
+    return sharded.sharded_topk_rank(m_rows, target, k, scorer, sharded.tc_merge,
                                      full_rank=full_rank, group=group, with_loss=with_loss, pad_id=pad_id, combine_ce=sharded.tc_combine_ce)
 
 
 TransformerRecommenderModel.evaluate_rank_sharded = torch.no_grad()(_evaluate_rank_sharded)
+
+
+# ASME_B200_BIAS_BOUNDS=1: the exact top-k sweep runs on the plain (V, H) table with the output bias bounded per 32-item chunk
+# (ops.bias_chunk_bounds) instead of the table with the bias folded into 16 extra K columns.  Same lists (tests/test_gpu_exact_topk.py),
+# but measured SLOWER on the 1024 x 1M x 128 call even for a tiny bias (0.38 vs 0.37 ms; no bias at all: 0.33 ms) and up to 0.54 ms
+# when the bias varies as much as the scores do (every chunk then takes the exact-add path) -> off; the folded operands cost a
+# constant 12 %.
+BIAS_BOUNDS = os.environ.get("ASME_B200_BIAS_BOUNDS", "0") == "1"
 
 
 def score_rows(m_rows, w, b, target, k):
@@ -609,14 +646,19 @@ def score_rows_tc(hb, wb, b, target, k, full_rank: bool = True):
     return out
 
 
-def score_rows_tc_exact(m_rows, hb, wb, w32, b32, norm_bound, target, k, full_rank: bool = False):
+def score_rows_tc_exact(m_rows, hb, wb, w32, b32, norm_bound, target, k, full_rank: bool = False, bias_bounds=None):
     """exact top-k on the tensor-core path: bf16 sweep -> candidates + what the sweep may have dropped (``ops.tc_score_candidates``)
     -> fp32 re-score + order + certificate (``ops.topk_rescore``) -> exact fp32 sweep for the rows the certificate could not
     cover (``ops.score_topk_flagged``; normally none).  ``topk_idx`` / ``topk_val`` / ``target_score`` and the target's position
     among the top k are bit-identical to the fp32 path's for the same hidden rows; with ``full_rank`` a target OUTSIDE the top k
     gets the rank of the bf16 count sweep."""
     want_full = full_rank and target is not None
-    o = ops.tc_score_candidates(hb, wb, None, k, 64, target=target if want_full else None)
+    if bias_bounds is not None:      # plain operands: (aligned bias, its chunk bounds) ride along instead of folded bias columns
+        if want_full:
+            raise ValueError("score_rows_tc_exact: the count sweep of full_rank needs the folded operands")
+        o = ops.tc_score_candidates(hb, wb, bias_bounds[0], k, 64, bias_bounds=bias_bounds[1])
+    else:
+        o = ops.tc_score_candidates(hb, wb, None, k, 64, target=target if want_full else None)
     r = ops.topk_rescore(m_rows, w32, b32, o["cand_idx"], o["cand_val"], k, norm_bound, target, cand_bound=o["bound"])
     rank = r["rank"]
     out = dict(topk_val=r["topk_val"], topk_idx=r["topk_idx"], target_score=r["target_score"], n_uncertified=r["n_flagged"])

@@ -589,6 +589,26 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, b_is_kn: bool = False, bias=None, 
     return out
 
 
+def tc_ffn_fused(y16: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, residual: torch.Tensor,
+                 ln=None, out_f32: bool = True):
+    """feed-forward block in one kernel (inference): out = residual + W2 gelu(W1 y + b1) + b2; y16 (M,H) bf16, w1 (FF,H) / w2 (H,FF)
+    bf16, residual (M,H) fp32.  returns dict(f32=out or None, ln16=LayerNorm(out; *ln) as bf16 or None).  The (M,FF) intermediate
+    never reaches HBM; ``f32`` is bit-identical to the two-GEMM path."""
+    y16, w1, w2 = _bf16(y16, "y"), _bf16(w1, "w1"), _bf16(w2, "w2")
+    M, H = y16.shape
+    FF = w1.shape[0]
+    if tuple(w1.shape) != (FF, H) or tuple(w2.shape) != (H, FF) or tuple(residual.shape) != (M, H):
+        raise ValueError(f"tc_ffn_fused: shapes y{tuple(y16.shape)} w1{tuple(w1.shape)} w2{tuple(w2.shape)} residual{tuple(residual.shape)}")
+    dev = y16.device
+    o32 = torch.empty(M, H, dtype=torch.float32, device=dev) if out_f32 else None
+    ln16 = torch.empty(M, H, dtype=torch.bfloat16, device=dev) if ln is not None else None
+    if _lib.timing is not None:
+        _lib.note = f"M={M},H={H},FF={FF},f32={int(out_f32)},ln={int(ln is not None)}"
+    _lib.call("asme_b200_tc_ffn_fused", _p(y16), _p(w1), _p(_f32(b1)), _p(w2), _p(_f32(b2)), _p(_f32(residual)), M, H, FF, _p(o32),
+              _p(_f32(ln[0])) if ln is not None else None, _p(_f32(ln[1])) if ln is not None else None, _p(ln16), _stream())
+    return dict(f32=o32, ln16=ln16)
+
+
 def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True,
              slot: int = 0):
     """dw (N,K) fp32 (+)= dy(M,N)^T x(M,K); dbias (N) (+)= colsum(dy); dy, x bf16.  ``slot``: scratch buffer to use (calls issued
@@ -672,9 +692,20 @@ def table_norm_bound(w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Ten
     return out
 
 
-def tc_score_candidates(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, k_out: int = 64, target=None, v0: int = 0):
+def bias_chunk_bounds(bias: torch.Tensor) -> torch.Tensor:
+    """(ceil(V/32), 2) fp32: {max, min} of ``bias`` over every 32-item chunk -- lets the top-k sweeps skip the bias add for chunks
+    that cannot reach a row's threshold (``tc_score_candidates(bias_bounds=...)``)"""
+    bias = _f32(bias, "bias")
+    V = bias.numel()
+    out = torch.empty((V + 31) // 32, 2, dtype=torch.float32, device=bias.device)
+    _lib.call("asme_b200_bias_chunk_bounds", _p(bias), V, _p(out), _stream())
+    return out
+
+
+def tc_score_candidates(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, k_out: int = 64, target=None, v0: int = 0, bias_bounds=None):
     """candidates for an exact top-``k``: dict(cand_val, cand_idx (R,k_out) best first by bf16 score, bound (R) = upper bound of the bf16
-    score of every item in none of the sweep's lists, target_score (R) bf16 score of the target or None)"""
+    score of every item in none of the sweep's lists, target_score (R) bf16 score of the target or None).  ``bias`` / ``bias_bounds``
+    (:func:`bias_chunk_bounds` of the same slice): the bias stays out of the contraction and is added per chunk only where needed."""
     hb, wb = _bf16(hb, "hb"), _bf16(wb, "wb")
     R, Kp = hb.shape
     Vloc = wb.shape[0]
@@ -688,7 +719,9 @@ def tc_score_candidates(hb: torch.Tensor, wb: torch.Tensor, bias, k: int, k_out:
     ws = workspace(_lib.query("asme_b200_tc_score_candidates_workspace_bytes", R, Kp, Vloc, k, k_out), dev)
     if _lib.timing is not None:
         _lib.note = f"R={R},V={Vloc},H={Kp},k={k},kout={k_out}"
-    _lib.call("asme_b200_tc_score_candidates", _p(hb), R, Kp, _p(wb), _p(bias), v0, Vloc, _p(tgt), k, k_out, _p(val), _p(idx), _p(bound),
+    if bias_bounds is not None and (bias is None or tuple(bias_bounds.shape) != ((Vloc + 31) // 32, 2)):
+        raise ValueError("tc_score_candidates: bias_bounds must be bias_chunk_bounds(bias) of the same catalog slice")
+    _lib.call("asme_b200_tc_score_candidates", _p(hb), R, Kp, _p(wb), _p(bias), _p(bias_bounds), v0, Vloc, _p(tgt), k, k_out, _p(val), _p(idx), _p(bound),
               _p(ts), _p(ws), ws.numel(), _stream())
     return dict(cand_val=val, cand_idx=idx, bound=bound, target_score=ts)
 

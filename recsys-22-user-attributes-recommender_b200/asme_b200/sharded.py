@@ -178,11 +178,12 @@ def sharded_topk_rank(hidden_local: torch.Tensor, target_local: torch.Tensor, k:
 
 
 def tc_local_scorer(wb_shard: torch.Tensor, bias_shard: Optional[torch.Tensor], v0: int, folded: bool = False,
-                    exact: Optional[Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]] = None):
+                    exact: Optional[Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]] = None, bias_bounds=None):
     """the production per-shard scorer: tcgen05 scoring kernel over the rank's (Vloc, Kp) bf16 slice; ``folded``: the slice
     carries the bias in two extra K columns (models.projection_operands_folded) and the hidden rows get the matching ones.
     ``exact = (w32_shard, b32_shard, norm_bound)``: the slice's lists are made exact (csrc/rescore.cu) before they are exchanged,
-    so the merged lists are the fp32 path's."""
+    so the merged lists are the fp32 path's.  ``bias_bounds`` (ops.bias_chunk_bounds(bias_shard), exact lists without a count sweep
+    only): the slice is the plain (Vloc, H) table and the bias is added per chunk where a score could pass the threshold."""
     from . import ops
 
     def score(hidden_all, target_all, k, target_score_in, want_ce: bool = False):
@@ -194,7 +195,10 @@ def tc_local_scorer(wb_shard: torch.Tensor, bias_shard: Optional[torch.Tensor], 
             out = ops.tc_score_topk(hb, wb_shard, bias_shard, k, target=target_all, v0=v0)
         else:
             w32, b32, nb = exact
-            c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, 64, target=target_all, v0=v0)
+            if bias_bounds is not None:
+                c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, 64, v0=v0, bias_bounds=bias_bounds)
+            else:
+                c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, 64, target=target_all, v0=v0)
             r = ops.topk_rescore(hidden_all, w32, b32, c["cand_idx"], c["cand_val"], k, nb, target_all, v0=v0, want_rank=False,
                                  cand_bound=c["bound"])
             ops.score_topk_flagged(hidden_all, w32, b32, target_all, r["target_score"], k, r["row_flag"], r["topk_val"], r["topk_idx"],

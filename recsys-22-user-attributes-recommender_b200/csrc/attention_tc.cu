@@ -337,6 +337,253 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Forward, second version (default): the probabilities never touch shared memory.  The softmax threads write P as packed bf16 pairs
+// straight back into the tensor-memory columns the scores came from (tcgen05.st; key pair (2j, 2j+1) -> column j) and the second
+// MMA takes its A operand from tensor memory (tcgen05.mma with [a_tmem]).  Without the 64 KB probability tile a CTA needs 96 KB of
+// shared memory and 256 tensor-memory columns -- scores / P in [0, NS), O in [128, 128 + d) over score columns that are consumed by
+// then -- so TWO CTAs share an SM and each other's TMA round trip, MMA and softmax phases overlap: the first version ran one CTA per
+// SM through load -> MMA -> softmax -> MMA -> store strictly in turn (ncu: 36 % issue utilisation, 4 % tensor pipe, 1.73 waves at
+// B = 256).  One softmax warpgroup per CTA: thread = query row over ALL key columns, so row maxima / sums need no exchange and a
+// thread only ever overwrites score columns it has already read (P chunk c lands in columns [16c, 16c+16), inside score chunk c/2).
+// ------------------------------------------------------------------------------------------------------------
+#define ATF2_THREADS 256       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, warps 4-7 softmax / epilogue
+#define ATF2_OCOL 128          // first tensor-memory column of O
+struct __align__(8) AttnFwd2Shared {
+    uint64_t loaded, s_full, p_full, o_full, o_done;
+    uint32_t tmem_base;
+    uint32_t kvb[8];
+};
+
+__global__ void __launch_bounds__(ATF2_THREADS, 2) attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                       // [256 tokens][128 B]   (64 hidden columns of this slice)
+    uint8_t* sK = sQ + 32768;
+    uint8_t* sV = sK + 32768;
+    AttnFwd2Shared* sh = reinterpret_cast<AttnFwd2Shared*>(sV + 32768);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int b = blockIdx.x, slice = blockIdx.y;
+    const int S = a.S, d = a.d;
+    const int hps = 64 / d;                   // heads per 64-column slice
+    const int n_qt_all = (S + 127) / 128;
+    const int qt_only = a.only_row ? (int)((a.only_row[b] - (long long)b * S) / 128) : -1;     // CTA-uniform
+    const int n_qt = qt_only >= 0 ? 1 : n_qt_all;
+    const int NS = (S + 15) / 16 * 16;        // score columns computed by the first MMA
+    const int units = hps * n_qt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_init(&sh->loaded, 1);
+        mbar_init(&sh->s_full, 1);
+        mbar_init(&sh->p_full, 4);                     // one arrival per softmax warp
+        mbar_init(&sh->o_full, 1);
+        mbar_init(&sh->o_done, 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+    const uint32_t tmem_o = tmem_base + ATF2_OCOL;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&sh->loaded, 3 * 32768);
+            tma_load_2d(sQ, &tmQKV, &sh->loaded, slice * 64, b * S);
+            tma_load_2d(sK, &tmQKV, &sh->loaded, a.H + slice * 64, b * S);
+            tma_load_2d(sV, &tmQKV, &sh->loaded, 2 * a.H + slice * 64, b * S);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = at_idesc(128, NS, 0, 0);
+            const uint32_t idesc_o = at_idesc(128, d, 0, 1);
+            const int ks_qk = d / 16;                        // K-steps of Q K^T
+            const int ks_pv = (S + 15) / 16;                 // K-steps of P V
+            mbar_wait_lean(&sh->loaded, 0);
+            tc_fence_after();
+            for (int u = 0; u < units; ++u) {
+                const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
+                if (u > 0) {                                 // the score columns double as P and O of the previous unit
+                    mbar_wait_lean(&sh->o_done, (uint32_t)(u - 1) & 1u);
+                    tc_fence_after();
+                }
+                const uint64_t qd = smem_desc_sw128(smem_u32(sQ + (size_t)qt * 128 * 128));
+                const uint64_t kd = smem_desc_sw128(smem_u32(sK));
+                for (int ks = 0; ks < ks_qk; ++ks)
+                    umma_bf16(tmem_base, smem_desc_advance(qd, (hh * d + ks * 16) * 2), smem_desc_advance(kd, (hh * d + ks * 16) * 2),
+                              idesc_s, (uint32_t)(ks != 0));
+                umma_commit(&sh->s_full);
+                mbar_wait_lean(&sh->p_full, (uint32_t)u & 1u);
+                tc_fence_after();
+                for (int ks = 0; ks < ks_pv; ++ks) {         // A = P from tensor memory: 16 keys = 8 packed columns per K-step
+                    const uint64_t vd = at_desc_mn(smem_u32(sV + (size_t)ks * 2048 + (size_t)hh * d * 2), 0);
+                    umma_bf16_ts(tmem_o, tmem_base + (uint32_t)(ks * 8), vd, idesc_o, (uint32_t)(ks != 0));
+                }
+                umma_commit(&sh->o_full);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q4 = warp % 4;
+        const int r = q4 * 32 + lane;                        // row of the query tile == TMEM lane
+        const uint32_t lane_addr = ((uint32_t)(q4 * 32) << 16);
+        if (warp == 4) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int key = w * 32 + lane;
+                bool ok = key < S;
+                if (ok && a.key_valid) ok = a.key_valid[(size_t)b * S + key] != 0;
+                const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) sh->kvb[w] = bits;
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four softmax warps only
+        const int n_chunks = (NS + 31) / 32;
+        const float cs = a.scale * LOG2E;
+        const uint32_t thr16 = (uint32_t)(a.p_drop * 65536.0f + 0.5f);
+        for (int u = 0; u < units; ++u) {
+            const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
+            const int head = slice * hps + hh;
+            const int qi = qt * 128 + r;                     // query position in the sequence
+            const bool q_ok = qi < S;
+            const long long bh = (long long)b * a.heads + head;
+            const int q_warp_min = qt * 128 + q4 * 32;       // smallest query index of this warp (causal fast-path test)
+            mbar_wait_lean(&sh->s_full, (uint32_t)u & 1u);
+            tc_fence_after();
+            // ---- pass 1: row maximum
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const uint32_t bits = sh->kvb[ch];
+                if (bits == 0u) {            // a chunk of padding keys only (warp-uniform): every score is the mask fill value
+                    if (ch * 32 < S) m = fmaxf(m, MASK_FILL);
+                    continue;
+                }
+                float v[32];
+                if (ch * 32 + 32 <= NS) tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
+                else {                       // NS = 16 (mod 32): the last chunk holds 16 score columns (the rest belongs to nobody)
+                    float v16[16];
+                    tmem_ld16(tmem_base + lane_addr + (uint32_t)(ch * 32), v16);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { v[c] = v16[c]; v[16 + c] = 0.f; }
+                }
+                tmem_ld_wait();
+                const bool plain = bits == 0xffffffffu && (!a.causal || ch * 32 + 31 <= q_warp_min);   // warp-uniform
+                if (plain) {
+                    float mm = v[0];
+#pragma unroll
+                    for (int c = 1; c < 32; ++c) mm = fmaxf(mm, v[c]);
+                    m = fmaxf(m, mm * a.scale);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int key = ch * 32 + c;
+                        const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
+                        float t = ok ? v[c] * a.scale : MASK_FILL;
+                        t = key < S ? t : -INFINITY;
+                        m = fmaxf(m, t);
+                    }
+                }
+            }
+            const float m2 = m * LOG2E;
+            const float e_masked = fast_exp2((MASK_FILL - m) * LOG2E);     // 1 in a fully masked row (uniform attention), else 0
+            // ---- pass 2: exp, row sum, dropout, P -> tensor memory (packed bf16 pairs over the score columns already read)
+            float l = 0.f;
+            uint32_t rowkey = 0;
+            if (a.p_drop > 0.f) rowkey = drop_rowkey(asme_seed(a.seed), a.site, (uint64_t)bh * S + (uint64_t)(q_ok ? qi : 0));
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const uint32_t bits = sh->kvb[ch];
+                const uint32_t p_addr = tmem_base + lane_addr + (uint32_t)(ch * 16);
+                uint32_t w[16];
+                if (bits == 0u && __all_sync(0xffffffffu, e_masked == 0.f)) {      // exact zeros: no exponentials, no dropout stream
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) w[c] = 0u;
+                    tmem_st16(p_addr, w);
+                    continue;
+                }
+                float v[32];
+                if (ch * 32 + 32 <= NS) tmem_ld32(tmem_base + lane_addr + (uint32_t)(ch * 32), v);
+                else {
+                    float v16[16];
+                    tmem_ld16(tmem_base + lane_addr + (uint32_t)(ch * 32), v16);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { v[c] = v16[c]; v[16 + c] = 0.f; }
+                }
+                tmem_ld_wait();
+                const bool plain = bits == 0xffffffffu && (!a.causal || ch * 32 + 31 <= q_warp_min);
+                if (plain) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        v[c] = fast_exp2(fmaf(v[c], cs, -m2));
+                        l += v[c];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int key = ch * 32 + c;
+                        const bool ok = ((bits >> c) & 1u) && (!a.causal || key <= qi);
+                        float e = ok ? fast_exp2(fmaf(v[c], cs, -m2)) : e_masked;
+                        e = key < S ? e : 0.f;
+                        l += e;
+                        v[c] = e;
+                    }
+                }
+                if (a.p_drop > 0.f) {
+                    const uint32_t kb = drop_keep_bits32(rowkey, ch, thr16);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = ((kb >> c) & 1u) ? v[c] * a.inv_keep : 0.f;
+                    if (a.keep_bits && q_ok) a.keep_bits[((size_t)bh * S + qi) * 8 + ch] = kb;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) w[c] = at_pack(v[2 * c], v[2 * c + 1]);
+                if (ch * 32 + 32 <= NS) tmem_st16(p_addr, w);
+                else {                       // 16 keys -> 8 packed columns
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(p_addr), "r"(w[0]),
+                                 "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                 : "memory");
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive_warp(&sh->p_full);
+            // ---- O = P V done: normalise and store
+            mbar_wait_lean(&sh->o_full, (uint32_t)u & 1u);
+            tc_fence_after();
+            const float inv_l = 1.0f / l;
+            if (a.stats && q_ok) {
+                a.stats[bh * S + qi] = m;                                         // natural units, as the SIMT kernels store it
+                a.stats[(long long)a.B * a.heads * S + bh * S + qi] = l;
+            }
+            for (int c0 = 0; c0 < d; c0 += 16) {
+                float o[16];
+                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+                tmem_ld_wait();
+                if (q_ok) {
+                    __nv_bfloat16* dst = a.ctx + ((size_t)b * S + qi) * a.H + slice * 64 + hh * d + c0;
+                    uint4 w0, w1;
+                    w0.x = at_pack(o[0] * inv_l, o[1] * inv_l); w0.y = at_pack(o[2] * inv_l, o[3] * inv_l);
+                    w0.z = at_pack(o[4] * inv_l, o[5] * inv_l); w0.w = at_pack(o[6] * inv_l, o[7] * inv_l);
+                    w1.x = at_pack(o[8] * inv_l, o[9] * inv_l); w1.y = at_pack(o[10] * inv_l, o[11] * inv_l);
+                    w1.z = at_pack(o[12] * inv_l, o[13] * inv_l); w1.w = at_pack(o[14] * inv_l, o[15] * inv_l);
+                    reinterpret_cast<uint4*>(dst)[0] = w0;
+                    reinterpret_cast<uint4*>(dst)[1] = w1;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_warp(&sh->o_done);       // scores of the next unit may overwrite P and O
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+static int g_attn_fwd_variant = 2;      // 2: probabilities in tensor memory, two CTAs per SM (default); 1: the first kernel (A/B)
 static int tc_attn_fwd_impl(const void* qkv, const uint8_t* key_valid, int B, int S, int heads, int d, int causal,
                             float p_drop, unsigned long long seed, unsigned int site, void* ctx, float* stats,
                             uint32_t* keep_bits, const int64_t* only_row, asme_stream_t stream);
@@ -368,6 +615,15 @@ static int tc_attn_fwd_impl(const void* qkv, const uint8_t* key_valid, int B, in
     a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
     a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits; a.only_row = only_row;
+    // second kernel whenever the grid fills the machine: with fewer CTAs than SMs nothing shares an SM and the first kernel's two
+    // softmax warpgroups per CTA are the shorter critical path (64 x 256 x 64: 0.077 vs 0.091 ms; 1024 x 200 x 128: 0.165 vs 0.112 ms)
+    if (g_attn_fwd_variant == 2 && (long long)B * (H / 64) >= ASME_NUM_SMS) {
+        const size_t smem2 = 1024 + 3 * 32768 + sizeof(AttnFwd2Shared);
+        { const int _rc = asme_ensure_max_smem((const void*)attn_tc_fwd2_kernel); if (_rc) return _rc; }
+        attn_tc_fwd2_kernel<<<dim3(B, H / 64), ATF2_THREADS, smem2, (cudaStream_t)stream>>>(tm, a);
+        ASME_LAUNCH_OK();
+        return ASME_OK;
+    }
     const size_t smem = 1024 + 3 * 32768 + 65536 + sizeof(AttnFwdShared);
     { const int _rc = asme_ensure_max_smem((const void*)attn_tc_fwd_kernel); if (_rc) return _rc; }
     attn_tc_fwd_kernel<<<dim3(B, H / 64), ATF_THREADS, smem, (cudaStream_t)stream>>>(tm, a);
@@ -951,6 +1207,9 @@ extern "C" int asme_b200_tc_attn_tune(int knob, int value) {
     } else if (knob == 1) {
         ASME_REQUIRE(value == 2 || value == 4, "tc_attn_tune: knob 1 (epilogue warpgroups of the single-sweep backward) takes 2 or 4");
         g_attn_bwd_wgs = value;
+    } else if (knob == 2) {
+        ASME_REQUIRE(value == 1 || value == 2, "tc_attn_tune: knob 2 (forward kernel) takes 1 or 2");
+        g_attn_fwd_variant = value;
     } else {
         ASME_REQUIRE(false, "tc_attn_tune: unknown knob %d", knob);
     }

@@ -26,7 +26,7 @@ extern "C" const char* asme_b200_last_error(void) { return g_last_error; }
 static std::atomic<long long> g_launches{0};
 void asme_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long asme_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-extern "C" int asme_b200_abi_version(void) { return 2; }
+extern "C" int asme_b200_abi_version(void) { return 3; }
 
 #include <mutex>
 int asme_ensure_max_smem(const void* kernel) {
@@ -87,7 +87,8 @@ struct Row {
 template <int LANES, int CH>
 __device__ __forceinline__ void ln_forward(Row<LANES, CH>& x, Row<LANES, CH>& y, const float* gamma, const float* beta,
                                            int lane, int H, float& mean, float& rstd) {
-    mean = x.sum() / (float)H;
+    const float inv_h = 1.0f / (float)H;      // H is a power of two (DISPATCH_H): v * (1/H) == v / H bit for bit, without the division sequence per row
+    mean = x.sum() * inv_h;
     float sq = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -95,7 +96,7 @@ __device__ __forceinline__ void ln_forward(Row<LANES, CH>& x, Row<LANES, CH>& y,
         sq += (x.v[c].x * x.v[c].x + x.v[c].y * x.v[c].y) + (x.v[c].z * x.v[c].z + x.v[c].w * x.v[c].w);
     }
     sq = group_sum<LANES>(sq);
-    rstd = rsqrtf(sq / (float)H + LN_EPS);
+    rstd = rsqrtf(sq * inv_h + LN_EPS);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         const float4 g = ldg4(gamma + (c * LANES + lane) * 4);
@@ -186,7 +187,7 @@ __device__ __forceinline__ void embed_gather_attrs(Row<LANES, CH>& x, const asme
 // TOK independent 128-bit gathers in flight (a random 256-512 B row per token is latency-bound otherwise).  A block covers
 // TOK * groups consecutive tokens; token j of group g is base + j * groups + g, so stores stay coalesced across groups.
 template <int LANES, int CH, int TOK, bool PRE>
-__global__ void __launch_bounds__(256, (!PRE && CH == 1) ? 5 : 1) embed_fwd_kernel(const asme_embed_desc d, int T, int S, int H, float* __restrict__ out,
+__global__ void __launch_bounds__(256, (!PRE && CH == 1) ? 5 : ((!PRE && TOK == 1) ? 4 : 1)) embed_fwd_kernel(const asme_embed_desc d, int T, int S, int H, float* __restrict__ out,
                                                         float* __restrict__ stats) {
     const int lane = threadIdx.x % LANES;
     const int groups = blockDim.x / LANES;
@@ -537,6 +538,30 @@ extern "C" int asme_b200_posgrad_reduce(const float* d_rows, int B, int S, int H
 
 static int lanes_for(int H) { return H / 4 < 32 ? H / 4 : 32; }
 
+// Forward kernels (embedding gather, LayerNorm): WIDE rows -- a row is owned by H/16 lanes with four 128-bit chunks each instead of
+// H/4 lanes with one.  The per-row work that does not scale with the row (address arithmetic, the two shuffle reductions of the
+// LayerNorm statistics, rsqrt) is paid by a quarter of the threads: the narrow layout issued ~265 warp instructions per token of
+// H = 128 and was ALU-bound at 78 % issue utilisation (ncu, C5 shape), not memory-bound.  Four chunks per lane keep the same four
+// independent 128-bit loads in flight per thread that the narrow kernel gets from four tokens per lane group.
+static int g_row_wide = 1;
+extern "C" int asme_b200_rowwise_tune(int knob, int value) {
+    ASME_REQUIRE(knob == 0 && (value == 0 || value == 1), "rowwise_tune: knob 0 (wide forward rows) takes 0 or 1");
+    g_row_wide = value;
+    return ASME_OK;
+}
+static bool wide_rows(int H) { return g_row_wide && H >= 64; }
+static int lanes_wide(int H) { return H / 16; }
+#define DISPATCH_H_WIDE(H, CALL)                                  \
+    switch (H) {                                                  \
+        case 64: { CALL(4, 4); break; }                           \
+        case 128: { CALL(8, 4); break; }                          \
+        case 256: { CALL(16, 4); break; }                         \
+        case 512: { CALL(32, 4); break; }                         \
+        default:                                                  \
+            asme_set_error("unsupported hidden size H=%d (supported: 16,32,64,128,256,512)", H); \
+            return ASME_ERR_INVALID;                              \
+    }
+
 extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* out, float* stats,
                                    asme_stream_t stream) {
     ASME_REQUIRE(d && out, "embed_fwd: null argument");
@@ -547,10 +572,11 @@ extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H
     ASME_REQUIRE(d->n_user >= 0 && d->n_user <= ASME_MAX_ATTR, "embed_fwd: too many user-attribute tables");
     ASME_REQUIRE(d->n_user == 0 || (S >= 2 && T % S == 0), "embed_fwd: user prefix needs S >= 2 (S counts the user position) and T = B*S");
     if (T == 0) return ASME_OK;
-    const int lanes = lanes_for(H);
+    const bool wide = wide_rows(H);
+    const int lanes = wide ? lanes_wide(H) : lanes_for(H);
     const int groups = 256 / lanes;
-    // tokens per lane group: as many as still leave >= 4 blocks per SM
-    const int tok = ceil_div(T, groups * 4) >= ASME_NUM_SMS * 4 ? 4 : (ceil_div(T, groups * 2) >= ASME_NUM_SMS * 4 ? 2 : 1);
+    // tokens per lane group: as many as still leave >= 4 blocks per SM (wide rows: one -- the four chunks are the loads in flight)
+    const int tok = wide ? 1 : (ceil_div(T, groups * 4) >= ASME_NUM_SMS * 4 ? 4 : (ceil_div(T, groups * 2) >= ASME_NUM_SMS * 4 ? 2 : 1));
 #define LAUNCH_TOK(L, C, K, P) embed_fwd_kernel<L, C, K, P><<<ceil_div(T, groups * K), 256, 0, (cudaStream_t)stream>>>(*d, T, S, H, out, stats)
 #define CALL(L, C)                                                                       \
     {                                                                                    \
@@ -564,7 +590,17 @@ extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H
             else LAUNCH_TOK(L, C, 1, false);                                             \
         }                                                                                \
     }
-    DISPATCH_H(H, CALL)
+    if (wide) {
+#define CALLW(L, C)                                                                      \
+    {                                                                                    \
+        if (d->n_user > 0) LAUNCH_TOK(L, C, 1, true);                                    \
+        else LAUNCH_TOK(L, C, 1, false);                                                 \
+    }
+        DISPATCH_H_WIDE(H, CALLW)
+#undef CALLW
+    } else {
+        DISPATCH_H(H, CALL)
+    }
 #undef CALL
 #undef LAUNCH_TOK
     ASME_LAUNCH_OK();
@@ -614,10 +650,11 @@ extern "C" int asme_b200_layernorm_fwd(const float* x, const float* gamma, const
                                        float* stats, const int32_t* n_live, asme_stream_t stream) {
     ASME_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null argument");
     if (M == 0) return ASME_OK;
-    const int lanes = lanes_for(H);
+    const bool wide = wide_rows(H);
+    const int lanes = wide ? lanes_wide(H) : lanes_for(H);
     const int groups = 256 / lanes;
 #define CALL(L, C) layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y, stats, nullptr, n_live)
-    DISPATCH_H(H, CALL)
+    if (wide) { DISPATCH_H_WIDE(H, CALL) } else { DISPATCH_H(H, CALL) }
 #undef CALL
     ASME_LAUNCH_OK();
     return ASME_OK;
@@ -628,12 +665,13 @@ extern "C" int asme_b200_layernorm_fwd_bf16(const float* x, const float* gamma, 
                                             void* y_bf16, float* stats, asme_stream_t stream) {
     ASME_REQUIRE(x && gamma && beta && y_bf16, "layernorm_fwd_bf16: null argument");
     if (M == 0) return ASME_OK;
-    const int lanes = lanes_for(H);
+    const bool wide = wide_rows(H);
+    const int lanes = wide ? lanes_wide(H) : lanes_for(H);
     const int groups = 256 / lanes;
 #define CALL(L, C)                                                                                                     \
     layernorm_fwd_kernel<L, C><<<ceil_div(M, groups), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, M, H, y_f32, stats, \
                                                                                       (__nv_bfloat16*)y_bf16, nullptr)
-    DISPATCH_H(H, CALL)
+    if (wide) { DISPATCH_H_WIDE(H, CALL) } else { DISPATCH_H(H, CALL) }
 #undef CALL
     ASME_LAUNCH_OK();
     return ASME_OK;

@@ -37,13 +37,31 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, lo
 int asme_tc_make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
     return make_tmap_bf16(map, base, rows, cols, ld, box_rows, CHUNK_K, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+// fp32 row blocks for epilogues that read activations through TMA: box (16 columns x box_rows), 64-byte swizzle
+static int ensure_encoder();
+int asme_tc_make_tmap_f32_16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    { const int rc = ensure_encoder(); if (rc) return rc; }
+    ASME_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 4) % 16 == 0 && cols % 16 == 0, "tensor map (fp32): base / row stride / width must be 16-aligned");
+    ASME_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map (fp32): box_rows=%d", box_rows);
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        asme_set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rows=%lld cols=%lld ld=%lld box_rows=%d)", (int)r, rows, cols, ld, box_rows);
+        return ASME_ERR_CUDA;
+    }
+    return ASME_OK;
+}
 // 16-column boxes with the 32-byte swizzle: the K tail of operands whose padded width is 64 k + 16 (bias folded into the
 // contraction) -- a quarter of the bytes of a 64-column box
 static int make_tmap_bf16_tail16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
     return make_tmap_bf16(map, base, rows, cols, ld, box_rows, 16, CU_TENSOR_MAP_SWIZZLE_32B);
 }
-static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols,
-                          CUtensorMapSwizzle swz) {
+static int ensure_encoder() {
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -54,6 +72,11 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, lo
         }
         g_encode = (PFN_encodeTiled)fn;
     }
+    return ASME_OK;
+}
+static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols,
+                          CUtensorMapSwizzle swz) {
+    { const int rc = ensure_encoder(); if (rc) return rc; }
     ASME_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "tensor map: base / row stride must be 16-byte aligned");
     ASME_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box_rows=%d", box_rows);
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -173,6 +196,9 @@ struct ScoreTcArgs {
                                  //    chunk maximum is a lower bound of the k-th best score: k distinct chunks hold a score >= it)
     float thr_floor;             // diagnostic: -inf normally; +inf makes every list reject everything (cost of the insertion-free sweep)
     const float* bias;
+    const float2* bias_bounds;   // (ceil(Vloc/32)) {max, min} of the bias over every 32-column chunk, or NULL.  With it the top-k sweeps
+                                 // run the bias-free fast path and add the bias only to chunks whose best raw score + max bias could
+                                 // pass the row's threshold (asme_b200_bias_chunk_bounds)
     const int64_t* target;
     const float* target_score;   // count mode: the pivot
     float* pv;                   // top-k partial values  [parts][R][k]      | CE: partial row max    [parts][R]
@@ -456,9 +482,21 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         float run_m = -INFINITY, run_s = 0.f;     // CE: running max (in log2 units) and sum of exp2
 
         int i = 0;
+        // bias bounds of this warp's two chunks of the current / next tile (BOUND tiles, four warpgroups)
+        float2 bb_cur0 = make_float2(0.f, 0.f), bb_cur1 = bb_cur0;
+        const bool use_bb = EPI == EPI_TOPK && TOPK && !COUNT && EPI_COLS == 64 && a.bias_bounds != nullptr;
+        const int bb_last = ((a.Vloc + 31) >> 5) - 1;
+        auto load_bb = [&](int tt, float2& b0, float2& b1) {
+            const int c = (tt * BN + wg * EPI_COLS) >> 5;
+            b0 = __ldg(a.bias_bounds + min(c, bb_last));
+            b1 = __ldg(a.bias_bounds + min(c + 1, bb_last));
+        };
+        if (use_bb && t0 < t1) load_bb(t0, bb_cur0, bb_cur1);
         for (int t = t0; t < t1; t += tstep, ++i) {
             const int as = i & 1;
             const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+            float2 bb_nxt0 = bb_cur0, bb_nxt1 = bb_cur1;
+            if (use_bb && t + tstep < t1) load_bb(t + tstep, bb_nxt0, bb_nxt1);
             mbar_wait_lean(&bars->tfull[as], aph);
             tc_fence_after();
             if (EPI == EPI_PROBE) {          // a.k == 0: no TMEM reads at all (what TMA + MMA + handshakes sustain);
@@ -481,9 +519,18 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
             // PLAIN tiles (all 256 columns valid, no bias vector, no target column of this warp's rows inside) skip the per-chunk
             // bookkeeping: the epilogue warps are issue-bound, every instruction per chunk counts
-            auto chunk = [&](auto plain_c, const int ch) {
-                constexpr bool PLAIN = decltype(plain_c)::value;
+            // MODE 0: general tile; 1: PLAIN; 2: BOUND = a full tile without target column whose bias is only bounded per chunk
+            auto chunk = [&](auto mode_c, const int ch) {
+                constexpr int MODE = decltype(mode_c)::value;
+                constexpr bool PLAIN = MODE != 0;
+                constexpr bool BOUND = MODE == 2;
                 const int col0 = t * BN + wg * EPI_COLS + ch * 32;     // local column of v[0]
+                float2 bb = make_float2(0.f, 0.f);
+                if (BOUND) {      // warp-uniform; the array (V/4 bytes) does not stay in L1 next to 227 KB of shared memory, so the
+                                  // bounds of a tile were requested a whole tile ahead (two chunks per warp with four warpgroups)
+                    if (EPI_COLS == 64) bb = ch == 0 ? bb_cur0 : bb_cur1;
+                    else bb = __ldg(a.bias_bounds + (col0 >> 5));
+                }
                 float v[32];
                 tmem_ld32(lane_addr + (uint32_t)(as * BN + wg * EPI_COLS + ch * 32), v);
                 tmem_ld_wait();
@@ -551,8 +598,21 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
                         float m8[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) m8[j] = max8(v + 8 * j);
-                        const float mc = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                        float mc = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+                        // BOUND: rounding is monotone, so fl(best raw + max bias) >= every biased score of the chunk (main sweep: nothing
+                        // that could pass the threshold is skipped) and fl(best raw + min bias) <= the chunk's best biased score (threshold
+                        // pass: k distinct chunks hold a score >= the k-th best of these lower bounds)
+                        if (BOUND) mc += a.sample_mode ? bb.y : bb.x;
                         if (__any_sync(0xffffffffu, mc > thr)) {      // rare once the thresholds have converged
+                            if (BOUND && !a.sample_mode) {            // now the exact biased scores of this chunk
+#pragma unroll
+                                for (int c = 0; c < 32; c += 4) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + c));
+                                    v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) m8[j] = max8(v + 8 * j);
+                            }
                             if (a.sample_mode) {      // warp-uniform
                                 if (__any_sync(0xffffffffu, cnt > a.pend_cap - 8)) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
                                 if (mc > thr) {
@@ -580,13 +640,18 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             };
             const bool tile_full = (t + 1) * BN <= a.Vloc;
             const bool target_here = a.captured && tgl >= t * BN && tgl < (t + 1) * BN;
-            if (tile_full && !a.bias && !__any_sync(0xffffffffu, target_here)) {
+            const bool clean = tile_full && !__any_sync(0xffffffffu, target_here);
+            if (clean && !a.bias) {
 #pragma unroll 1
-                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::true_type{}, ch);
+                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::integral_constant<int, 1>{}, ch);
+            } else if (EPI == EPI_TOPK && TOPK && !COUNT && clean && a.bias_bounds) {
+#pragma unroll 1
+                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::integral_constant<int, 2>{}, ch);
             } else {
 #pragma unroll 1
-                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::false_type{}, ch);
+                for (int ch = 0; ch < EPI_COLS / 32; ++ch) chunk(std::integral_constant<int, 0>{}, ch);
             }
+            bb_cur0 = bb_nxt0; bb_cur1 = bb_nxt1;
         }
         if (TOPK) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
         // --- fold the warpgroups' results into warpgroup 0 through the table ring (idle: every MMA of this CTA has completed),
@@ -872,6 +937,29 @@ __global__ void tc_ce_merge_kernel(const float* __restrict__ pm, const float* __
     row_sumexp[r] = s;
 }
 
+// {max, min} of the bias over every 32-column chunk [32 c, 32 c + 32) of the (local) catalog slice: one warp per chunk
+__global__ void __launch_bounds__(256) bias_chunk_bounds_kernel(const float* __restrict__ bias, int V, float2* __restrict__ bounds) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+    if (c * 32 >= V) return;
+    const int j = c * 32 + lane;
+    const float b = j < V ? __ldg(bias + j) : __ldg(bias + c * 32);
+    float hi = b, lo = b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    if (lane == 0) bounds[c] = make_float2(hi, lo);
+}
+extern "C" int asme_b200_bias_chunk_bounds(const float* bias, int V, float* bounds, asme_stream_t stream) {
+    ASME_REQUIRE(bias && bounds && V >= 1, "bias_chunk_bounds: bad argument");
+    ASME_REQUIRE(((uintptr_t)bounds & 7) == 0, "bias_chunk_bounds: bounds must be 8-byte aligned");
+    const int chunks = ceil_div(V, 32);
+    bias_chunk_bounds_kernel<<<ceil_div(chunks, 8), 256, 0, (cudaStream_t)stream>>>(bias, V, reinterpret_cast<float2*>(bounds));
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
@@ -1123,9 +1211,11 @@ extern "C" size_t asme_b200_tc_score_candidates_workspace_bytes(int R, int Kp, i
     const size_t uni = (size_t)2 * (p.splits + 1) * MAX_EPI_WGS * R * ((size_t)kk * 8 + 8) + (size_t)R * kk * 8;
     return classic > uni ? classic : uni;
 }
-extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, int v0, int Vloc,
+extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, const float* bias_bounds,
+                                             int v0, int Vloc,
                                              const int64_t* target, int k, int k_out, float* cand_val, int32_t* cand_idx, float* bound,
                                              float* target_score_out, void* ws, size_t ws_bytes, asme_stream_t stream) {
+    ASME_REQUIRE(!bias_bounds || (bias && ((uintptr_t)bias_bounds & 7) == 0), "tc_score_candidates: bias_bounds needs the bias and 8-byte alignment");
     ASME_REQUIRE(Hb && Wb && cand_val && cand_idx && bound, "tc_score_candidates: null argument");
     ASME_REQUIRE(k >= 1 && k <= 32 && k <= k_out && k_out <= 64, "tc_score_candidates: k=%d k_out=%d unsupported (1 <= k <= 32, k <= k_out <= 64)", k, k_out);
     ASME_REQUIRE(!target_score_out || target, "tc_score_candidates: target_score_out needs target");
@@ -1167,7 +1257,7 @@ extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, cons
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = kl; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap;
     a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_step = p.splits;
-    a.bias = bias; a.target = target; a.target_score = nullptr; a.thr_floor = g_thr_floor;
+    a.bias = bias; a.bias_bounds = reinterpret_cast<const float2*>(bias_bounds); a.target = target; a.target_score = nullptr; a.thr_floor = g_thr_floor;
     a.pv = (float*)ws;
     a.pi = (int*)(a.pv + (size_t)total_parts * R * kl);
     a.pg = a.pi + (size_t)total_parts * R * kl;

@@ -274,3 +274,5 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int unit16) {
 // Encode a 2-D bf16 tensor map: global (rows x cols) row-major with row stride `ld` elements, box (CHUNK_K x box_rows),
 // 128-byte swizzle, zero fill out of bounds. Returns 0 on success.
 int asme_tc_make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// the same for fp32 row blocks: box (16 columns x box_rows), 64-byte swizzle (16-byte unit u of row r lands at unit u ^ ((r >> 1) & 3))
+int asme_tc_make_tmap_f32_16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);

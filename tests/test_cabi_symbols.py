@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.asme_b200_abi_version() == 2
+    assert lib.asme_b200_abi_version() == 3
     # an invalid call fails loudly with a message, without touching the GPU
     rc = lib.asme_b200_layernorm_fwd(None, None, None, 4, 64, None, None, None, None)
     assert rc != 0

@@ -156,3 +156,28 @@ def test_model_evaluation_is_exact_on_the_benchmark_shapes(name, V, S, H, B):
     target = torch.where(torch.arange(B, device="cuda") % 2 == 0, planted, free)
     out = _oracle_check(model, seq, target)
     assert int((out["rank"] <= 10).sum()) > B // 8
+
+
+@pytest.mark.parametrize("R,V,H,k,sigma_b", [(64, 3709, 64, 10, 0.1), (128, 100003, 128, 10, 0.001), (128, 100003, 128, 10, 0.3), (33, 20011, 128, 5, 0.05),
+                                            (200, 30000, 64, 1, 0.1)])
+def test_exact_topk_with_the_bias_bounded_per_chunk(R, V, H, k, sigma_b):
+    """layers.py:138-143 (h E^T + output_bias): the sweep on the plain (V, H) table with the bias only BOUNDED per 32-item chunk
+    (ops.bias_chunk_bounds; exact add where a chunk could pass the threshold) returns the lists of the strict fp32 sweep, for a bias
+    far below and one as large as the spread of the scores (every chunk then takes the exact path)."""
+    from asme_b200 import models, ops
+    g = torch.Generator(device="cuda").manual_seed(R + V + k + 1)
+    h = torch.randn(R, H, generator=g, device="cuda")
+    w = torch.randn(V, H, generator=g, device="cuda") * 0.02
+    b = torch.randn(V, generator=g, device="cuda") * sigma_b
+    target = torch.randint(0, V, (R,), generator=g, device="cuda")
+    bb = ops.bias_chunk_bounds(b)
+    bref = b.view(-1)[: V // 32 * 32].view(-1, 32)
+    assert torch.equal(bb[: V // 32, 0], bref.max(1).values) and torch.equal(bb[: V // 32, 1], bref.min(1).values)
+    wb = ops.cast_bf16(w)
+    hb = ops.cast_bf16(h, ld_out=wb.shape[1])
+    out = models.score_rows_tc_exact(h, hb, wb, w, b, ops.table_norm_bound(w, b), target, k, False, bias_bounds=(b, bb))
+    val, idx, rank, ts = _fp32_sweep(ops, h, w, b, k, target)
+    assert torch.equal(out["topk_idx"], idx)
+    assert torch.equal(out["topk_val"], val)
+    assert torch.equal(out["target_score"], ts)
+    assert torch.equal(torch.clamp(out["rank"], max=k + 1), torch.clamp(rank, max=k + 1).to(torch.int32))

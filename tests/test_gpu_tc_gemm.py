@@ -149,3 +149,57 @@ def test_tc_gemm_fused_layernorm(ops, M, N, K):
     assert float(diff.max()) <= 2.0 ** -7 * float(split["ln16"].float().abs().max())
     assert float((diff > 0).float().mean()) < 0.02
     torch.testing.assert_close(fused["ln_st"], split["ln_st"], rtol=2e-5, atol=1e-6)
+
+
+# ---- feed-forward block as one kernel (asme_b200_tc_ffn_fused, evaluation path) ----------------------------------------------
+FFN_SHAPES = [(1, 64, 256), (300, 128, 512), (1000, 64, 256), (1024, 128, 512), (148 * 128 * 2 + 77, 128, 512), (148 * 128 + 130, 64, 128),
+              (700, 128, 192)]
+
+
+@pytest.mark.parametrize("M,H,FF", FFN_SHAPES)
+def test_tc_ffn_fused_equals_two_gemms(ops, M, H, FF):
+    """out = x + W2 gelu(W1 y + b1) + b2 (transformer_layers.py:217-220, :120-130): the fused kernel against the two tensor-core
+    GEMM launches it replaces -- bit for bit on the fp32 rows -- and its fused LayerNorm against the stand-alone LayerNorm kernel on
+    the same rows (one bf16 ulp: the row statistics are summed in a different order)."""
+    from asme_b200._lib import ACT_GELU
+    gen = torch.Generator(device="cuda").manual_seed(M + H + FF)
+    y = (torch.randn(M, H, generator=gen, device="cuda")).bfloat16()
+    x = torch.randn(M, H, generator=gen, device="cuda")
+    w1 = (torch.randn(FF, H, generator=gen, device="cuda") * 0.1).bfloat16()
+    w2 = (torch.randn(H, FF, generator=gen, device="cuda") * 0.1).bfloat16()
+    b1 = torch.randn(FF, generator=gen, device="cuda") * 0.1
+    b2 = torch.randn(H, generator=gen, device="cuda") * 0.1
+    g = 1.0 + 0.1 * torch.randn(H, generator=gen, device="cuda")
+    b = 0.1 * torch.randn(H, generator=gen, device="cuda")
+    a16 = ops.tc_gemm(y, w1, bias=b1, act=ACT_GELU, out_f32=False, out_bf16=True)["bf16"]
+    want = ops.tc_gemm(a16, w2, bias=b2, residual=x)["f32"]
+    want_ln, _, _ = ops.layernorm_fwd_bf16(want, g, b)
+    got = ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=(g, b))
+    torch.cuda.synchronize()
+    assert torch.equal(got["f32"], want)
+    d = (got["ln16"].float() - want_ln.float()).abs()
+    ulp = want_ln.float().abs().clamp_min(2.0 ** -6) * 2.0 ** -7
+    assert bool((d <= ulp).all()), float((d / ulp).max())
+    assert float((d > 0).float().mean()) < 0.01
+    # the oracle's arithmetic on the same bf16 operands (float64): gelu = 0.5 z (1 + erf(z / sqrt 2))
+    z = y.double() @ w1.double().t() + b1.double()
+    a = (0.5 * z * (1.0 + torch.erf(z / math.sqrt(2.0)))).float().bfloat16().double()
+    ref = x.double() + a @ w2.double().t() + b2.double()
+    assert float((got["f32"].double() - ref).abs().max()) < 2e-2 * float(ref.abs().max())
+    only = ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=None)
+    assert only["ln16"] is None and torch.equal(only["f32"], want)
+    ln_only = ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=(g, b), out_f32=False)
+    assert ln_only["f32"] is None and torch.equal(ln_only["ln16"], got["ln16"])
+
+
+def test_tc_ffn_fused_integer_exact(ops):
+    """small-integer operands and a zero first-layer bias keep z in {integers}: with gelu(0) = 0 and W1 = 0 the block reduces to
+    out = x + b2 exactly; with identity-like W1 rows it pins the chunk order of the second contraction"""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    M, H, FF = 260, 128, 512
+    y = ints(gen, M, H).bfloat16()
+    x = ints(gen, M, H)
+    w2 = ints(gen, H, FF).bfloat16()
+    b2 = ints(gen, H)
+    out = ops.tc_ffn_fused(y, torch.zeros(FF, H, device="cuda").bfloat16(), torch.zeros(FF, device="cuda"), w2, b2, x)["f32"]
+    assert torch.equal(out, x + b2)

@@ -29,7 +29,29 @@ def run(B, S, V, H, pos, ln, p, nxt=False):
                           frac=round(nbytes / ms / 1e6 / PEAK, 3))), flush=True)
 
 
+def run_ln(M, H):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xs = [torch.randn(M, H, device="cuda", generator=g) for _ in range(3)]
+    gam, bet = torch.ones(H, device="cuda"), torch.zeros(H, device="cuda")
+    it = [0]
+
+    def step():
+        ops.layernorm_fwd_bf16(xs[it[0] % 3], gam, bet)
+        it[0] += 1
+    ms = timeit(step, iters=20)
+    nbytes = M * H * 6
+    print(json.dumps(dict(kernel="layernorm_fwd_bf16", M=M, H=H, ms=round(ms, 4), gbs=round(nbytes / ms / 1e6, 1),
+                          frac=round(nbytes / ms / 1e6 / PEAK, 3))), flush=True)
+
+
 if __name__ == "__main__":
+    wide = int(os.environ.get("ROW_WIDE", "1"))
+    ops._lib.call("asme_b200_rowwise_tune", 0, wide)
+    print(json.dumps(dict(wide_rows=wide)), flush=True)
+    run(1024, 200, 1_000_003, 128, False, True, 0.0, nxt=True)      # the C5 evaluation step's call (BERT4Rec: no positions)
+    run(256, 200, 3709, 64, False, True, 0.2, nxt=True)             # the C2 training step's call
+    run_ln(204800, 128)
+    run_ln(51200, 64)
     for (B, S, V, H) in [(1024, 200, 1_000_003, 128), (4096, 200, 1_000_003, 128), (256, 200, 3709, 64), (4096, 50, 13047, 64)]:
         for pos, ln, p in [(False, False, 0.0), (False, True, 0.0), (True, True, 0.0), (False, True, 0.2)]:
             run(B, S, V, H, pos, ln, p)

@@ -48,3 +48,25 @@ print(f"bf16-only call:   {timed(lambda: models.score_rows_tc(hb, wb, None, targ
 print(f"table norm bound: {timed(lambda: ops.table_norm_bound(w, b)):.4f} ms")
 flag = r["row_flag"].clone(); flag[::97] = 1
 print(f"flagged pass ({int(flag.sum())} rows flagged): {timed(lambda: ops.score_topk_flagged(h, w, b, target, r['target_score'], 10, flag, r['topk_val'], r['topk_idx'], r['rank']), 3):.4f} ms")
+
+# ---- bias kept out of the contraction: plain (V, H) table + per-chunk bias bounds (K = 128 instead of 144) -------------------------
+wp = ops.cast_bf16(w)
+hp = ops.cast_bf16(h, ld_out=H)
+bbs = ops.bias_chunk_bounds(b)
+print(f"candidate sweep, plain table + bias bounds: {timed(lambda: ops.tc_score_candidates(hp, wp, b, 10, 64, bias_bounds=bbs)):.4f} ms")
+print(f"candidate sweep, plain table, bias added in every chunk: {timed(lambda: ops.tc_score_candidates(hp, wp, b, 10, 64)):.4f} ms")
+print(f"candidate sweep, plain table, no bias at all: {timed(lambda: ops.tc_score_candidates(hp, wp, None, 10, 64)):.4f} ms")
+o2 = ops.tc_score_candidates(hp, wp, b, 10, 64, bias_bounds=bbs)
+r2 = ops.topk_rescore(h, w, b, o2["cand_idx"], o2["cand_val"], 10, nb, target, cand_bound=o2["bound"])
+print("uncertified rows (bounds path):", int(r2["n_flagged"]), "| lists equal the folded path's:", bool(torch.equal(r2["topk_idx"], r["topk_idx"])),
+      bool(torch.equal(r2["topk_val"], r["topk_val"])))
+print(f"whole exact call, bounds path: {timed(lambda: models.score_rows_tc_exact(h, hp, wp, w, b, nb, target, 10, bias_bounds=(b, bbs))):.4f} ms")
+bl = torch.randn(V, generator=g, device="cuda") * 0.5          # a bias as large as the scores' spread (popularity-like)
+bbl = ops.bias_chunk_bounds(bl)
+nbl = ops.table_norm_bound(w, bl)
+print(f"candidate sweep, bounds path, LARGE bias (sigma 0.5): {timed(lambda: ops.tc_score_candidates(hp, wp, bl, 10, 64, bias_bounds=bbl)):.4f} ms")
+o3 = ops.tc_score_candidates(hp, wp, bl, 10, 64, bias_bounds=bbl)
+r3 = ops.topk_rescore(h, w, bl, o3["cand_idx"], o3["cand_val"], 10, nbl, target, cand_bound=o3["bound"])
+dense = (h[:64].double() @ w.double().t() + bl.double())
+want = torch.sort(dense, dim=1, descending=True, stable=True).indices[:, :10]
+print("large bias: uncertified rows", int(r3["n_flagged"]), "| top-10 of the first 64 rows equals dense fp64:", bool(torch.equal(want.int(), r3["topk_idx"][:64])))

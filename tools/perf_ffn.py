@@ -1,0 +1,45 @@
+"""Feed-forward block of the evaluation path: the fused kernel (asme_b200_tc_ffn_fused) against the two GEMM launches + the
+stand-alone LayerNorm it replaces (CUDA events, warm, inputs larger than L2 at the C5 shape)."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "recsys-22-user-attributes-recommender_b200")]
+import torch
+from asme_b200 import ops
+from tools.perf_score import timeit
+
+
+def run(M, H, FF):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    y = torch.randn(M, H, device="cuda", generator=g).bfloat16()
+    x = torch.randn(M, H, device="cuda", generator=g)
+    w1 = (torch.randn(FF, H, device="cuda", generator=g) * 0.1).bfloat16()
+    w2 = (torch.randn(H, FF, device="cuda", generator=g) * 0.1).bfloat16()
+    b1 = torch.randn(FF, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(H, device="cuda", generator=g) * 0.1
+    gm, bt = torch.ones(H, device="cuda"), torch.zeros(H, device="cuda")
+
+    def unfused():
+        a = ops.tc_gemm(y, w1, bias=b1, act=1, out_f32=False, out_bf16=True)["bf16"]
+        o = ops.tc_gemm(a, w2, bias=b2, residual=x)["f32"]
+        return o, ops.layernorm_fwd_bf16(o, gm, bt)[0]
+
+    o_ref, ln_ref = unfused()
+    r = ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=(gm, bt))
+    res = dict(M=M, H=H, FF=FF, equal_f32=bool(torch.equal(r["f32"], o_ref)),
+               ln_max_diff=float((r["ln16"].float() - ln_ref.float()).abs().max()))
+    res["unfused_ms"] = round(timeit(unfused, iters=20), 4)
+    for gw in (2, 4):
+        ops._lib.call("asme_b200_tc_ffn_tune", 0, gw)
+        res[f"gw{gw}_ln_ms"] = round(timeit(lambda: ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=(gm, bt)), iters=20), 4)
+        res[f"gw{gw}_ms"] = round(timeit(lambda: ops.tc_ffn_fused(y, w1, b1, w2, b2, x), iters=20), 4)
+        res[f"gw{gw}_equal"] = bool(torch.equal(ops.tc_ffn_fused(y, w1, b1, w2, b2, x)["f32"], o_ref))
+    res["fused_ln_ms"] = round(timeit(lambda: ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=(gm, bt)), iters=20), 4)
+    res["fused_ms"] = round(timeit(lambda: ops.tc_ffn_fused(y, w1, b1, w2, b2, x), iters=20), 4)
+    res["fused_tflops"] = round(4.0 * M * H * FF / res["fused_ms"] / 1e9, 1)
+    res["fused_ln_gbs"] = round(M * H * (2 + 4 + 4 + 2) / res["fused_ln_ms"] / 1e6, 1)
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    for cfg in [(204800, 128, 512), (51200, 64, 256), (1024, 128, 512), (819200, 128, 512)]:
+        run(*cfg)
