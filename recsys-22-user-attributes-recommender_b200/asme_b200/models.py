@@ -85,15 +85,22 @@ class TransformerRecommenderModel(ArenaModule):
         self.prefusion: List[Tuple[str, str, int]] = []      # (name, type, vocab)
         self.postfusion: List[Tuple[str, str, int]] = []
         attr_specs = []
-        # user attributes (UBERT4Rec / UserSASRec): plain tables whose sum becomes an extra token at position 0
-        self.user_attrs: List[Tuple[str, int]] = []
+        # user attributes (UBERT4Rec / UserSASRec): their sum becomes the token at position 0.  Tables (``user_embedding`` /
+        # ``content_embedding``: one id per user) or ``user_linear_upscale`` (models/ubert4rec/components.py:12-44: Linear over the
+        # multi-hot of a LIST of ids, id 0 included -- unlike the item-side LinearUpscaler nothing is zeroed)
+        self.user_attrs: List[Tuple[str, int, str]] = []
         for name, info in (user_attributes or {}).items():
             kind = info["embedding_type"]
-            if kind not in ("user_embedding", "content_embedding"):
-                raise NotImplementedError(f"user attribute embedding type {kind!r}: only table look-ups are on the B200 path")
             vu = _attr_vocab_size(name, tokenizers, attr_sizes)
-            self.user_attrs.append((name, vu))
-            attr_specs.append((f"{_USER_ATTR}.{name}.weight", (vu, H)))
+            if kind in ("user_embedding", "content_embedding"):
+                attr_specs.append((f"{_USER_ATTR}.{name}.weight", (vu, H)))
+            elif kind == "user_linear_upscale":
+                attr_specs.append((f"{_USER_ATTR}.{name}.linear.weight", (vu, H), "T"))   # stored transposed (Vu,H)
+                attr_specs.append((f"{_USER_ATTR}.{name}.linear.bias", (H,)))
+            else:
+                raise NotImplementedError(f"user attribute embedding type {kind!r} (user_embedding, content_embedding and "
+                                          "user_linear_upscale are built)")
+            self.user_attrs.append((name, vu, kind))
         self.segment_rows = int(segment_rows)
         if self.segment_rows:
             attr_specs.append((_SEGMENT, (self.segment_rows, H)))
@@ -109,7 +116,7 @@ class TransformerRecommenderModel(ArenaModule):
                     attr_specs.append((f"{prefix}.{name}.linear.bias", (H,)))
                 else:
                     raise KeyError(f"{kind} invalid attribute embedding type")
-        self.additional_userdata_keys = [n for n, _ in self.user_attrs]
+        self.additional_userdata_keys = [n for n, _, _ in self.user_attrs]
         self.additional_metadata_keys = self.additional_userdata_keys + [n for n, _, _ in self.prefusion] + \
             [n for n, _, _ in self.postfusion]
         self._init_arena(list(specs) + attr_specs + [("_ghost_zero_row", (H,))])
@@ -128,10 +135,23 @@ class TransformerRecommenderModel(ArenaModule):
     def optional_metadata_keys(self) -> List[str]:
         return self.additional_userdata_keys
 
+    replace_first_item: bool = False           # the user token takes the place of the first item instead of being prepended
+
     @property
     def user_prefix(self) -> int:
-        """1 when a user token is prepended to every sequence (hidden states then have S+1 positions)"""
-        return 1 if self.user_attrs else 0
+        """1 when a user token is prepended to every sequence (hidden states then have S+1 positions); with
+        ``replace_first_item`` (models/ubert4rec/components.py:117-121) the token overwrites position 0 and the length stays S"""
+        return 1 if (self.user_attrs and not self.replace_first_item) else 0
+
+    def _item_side(self, seq: torch.Tensor, attrs: Dict[str, torch.Tensor]):
+        """what the embedding kernels see as the item sequence: with ``replace_first_item`` positions 1..S-1 (the embedding of
+        item 0, its position and its attributes are computed by the reference and then thrown away)"""
+        if not (self.user_attrs and self.replace_first_item):
+            return seq, attrs
+        sliced = dict(attrs)
+        for name, _k, _v in self.prefusion:
+            sliced[name] = attrs[name][:, 1:].contiguous()
+        return seq[:, 1:].contiguous(), sliced
 
     # ---- embedding ------------------------------------------------------------------------------
     def _attr_operands(self, attrs: Dict[str, torch.Tensor], which, prefix, T):
@@ -147,19 +167,36 @@ class TransformerRecommenderModel(ArenaModule):
         return singles, bags
 
     def _embed_spec(self, seq: torch.Tensor, attrs, training: bool, seed: int) -> ops.EmbedSpec:
+        """``seq`` / ``attrs``: the item side (:meth:`_item_side`)"""
         B, S = seq.shape
         singles, bags = self._attr_operands(attrs, self.prefusion, self.pre_attr_prefix, B * S)
-        # only column 0 of a user feature is read (models/ubert4rec/components.py:112-113)
-        users = [(attrs[name][:, 0].contiguous() if attrs[name].dim() > 1 else attrs[name], self.weight(f"{_USER_ATTR}.{name}.weight"))
-                 for name, _vu in self.user_attrs]
+        # only column 0 of a user feature is read (models/ubert4rec/components.py:112-113).  A user_linear_upscale attribute with a
+        # list of A ids per user becomes A gathers from the transposed Linear weight plus one from its bias (a one-row table)
+        users, user_paths = [], []
+        for name, _vu, kind in self.user_attrs:
+            first = attrs[name][:, 0] if attrs[name].dim() > 1 else attrs[name]
+            if kind == "user_linear_upscale":
+                ids = first.reshape(B, -1)
+                for a in range(ids.shape[1]):
+                    users.append((ids[:, a].contiguous(), self.weight(f"{_USER_ATTR}.{name}.linear.weight")))
+                    user_paths.append((f"{_USER_ATTR}.{name}.linear.weight", False))
+                users.append((torch.zeros(B, dtype=torch.int64, device=seq.device), self.weight(f"{_USER_ATTR}.{name}.linear.bias").view(1, -1)))
+                user_paths.append((f"{_USER_ATTR}.{name}.linear.bias", True))
+            else:
+                users.append((first.contiguous(), self.weight(f"{_USER_ATTR}.{name}.weight")))
+                user_paths.append((f"{_USER_ATTR}.{name}.weight", False))
         seg = self.weight(_SEGMENT) if self.segment_rows else None
         ln1 = None if self.ln1_paths is None else (self.weight(self.ln1_paths[0]), self.weight(self.ln1_paths[1]))
         ln2 = None if self.ln2_paths is None else (self.weight(self.ln2_paths[0]), self.weight(self.ln2_paths[1]))
         pos = None if self.pos_table_path is None else self.weight(self.pos_table_path)
+        if pos is not None and self.user_attrs and self.replace_first_item:
+            pos = pos[1:]                       # item s of the sliced sequence sits at position s + 1 of the original one
         if pos is not None and S > pos.shape[0]:
             raise RuntimeError(f"sequence length {S} exceeds max_seq_length {pos.shape[0]}")
-        return ops.EmbedSpec(seq.reshape(-1), self.weight(self.item_table_path), pos, singles, bags, ln1, ln2,
+        spec = ops.EmbedSpec(seq.reshape(-1), self.weight(self.item_table_path), pos, singles, bags, ln1, ln2,
                              self.cfg.dropout if training else 0.0, seed, users=users, seg_table=seg)
+        spec.user_paths = user_paths
+        return spec
 
     def _embed_backward(self, saved: Saved, d_x: torch.Tensor):
         self.engine.wait_table_grad()           # a catalog gradient still running on the second stream adds into the same table
@@ -195,14 +232,16 @@ class TransformerRecommenderModel(ArenaModule):
 
         ops.embgrad_sorted_reduce(with_user_column(spec.item_ids, -1).reshape(-1), d_item, self.weight(self.item_table_path, g))
         if self.pos_table_path is not None:
-            ops.posgrad_reduce(d_item, B, Si, self.weight(self.pos_table_path, g), prefix=1)
+            dpos = self.weight(self.pos_table_path, g)
+            ops.posgrad_reduce(d_item, B, Si, dpos[1:] if self.replace_first_item else dpos, prefix=1)
         attrs = saved.extra["attrs"]
         shifted = {name: with_user_column(attrs[name], -1) for name, _k, _v in self.prefusion}
         self._attr_backward(shifted, self.prefusion, self.pre_attr_prefix, d_attr, B * S)
         user_rows = torch.arange(B, device=dev, dtype=torch.int64) * S
         d_user = ops.gather_rows(d_attr, user_rows)
-        for (ids, _tab), (name, _vu) in zip(spec.users, self.user_attrs):
-            ops.embgrad_sorted_reduce(ids, d_user, self.weight(f"{_USER_ATTR}.{name}.weight", g))
+        for (ids, _tab), (path, is_bias) in zip(spec.users, spec.user_paths):
+            dst = self.weight(path, g)
+            ops.embgrad_sorted_reduce(ids, d_user, dst.view(1, -1) if is_bias else dst)
         if self.segment_rows:
             seg_ids = torch.ones(B, S, dtype=torch.int64, device=dev)
             seg_ids[:, 0] = 0
@@ -238,7 +277,7 @@ class TransformerRecommenderModel(ArenaModule):
             B, S = seq.shape
             S += self.user_prefix
             saved = Saved(B=B, S=S, seed=0, training=False, key_valid=self._key_valid(padding_mask, seq))
-            x, _, y16, st = ops.embed_fwd(self._embed_spec(seq, attrs, False, 0), B, S, next_ln=self.engine.first_norm())
+            x, _, y16, st = ops.embed_fwd(self._embed_spec(*self._item_side(seq, attrs), False, 0), B, S, next_ln=self.engine.first_norm())
             return self.engine.blocks_forward(x, saved, select_rows=rows, one_per_sequence=one_per_sequence, first_ln=(y16, st))
         hidden, _ = self.encode(seq, padding_mask, attrs, training=False)
         return ops.gather_rows(hidden, rows)
@@ -259,8 +298,9 @@ class TransformerRecommenderModel(ArenaModule):
         S += self.user_prefix          # hidden states cover the prepended user token as well
         saved = Saved(B=B, S=S, seed=self._next_seed() if training else 0, training=training,
                       key_valid=self._key_valid(padding_mask, seq))
+        item_seq, attrs = self._item_side(seq, attrs)
         saved.extra["attrs"] = attrs
-        spec = self._embed_spec(seq, attrs, training, saved.seed)
+        spec = self._embed_spec(item_seq, attrs, training, saved.seed)
         saved.embed_spec = spec
         nxt = self.engine.first_norm()
         if nxt is not None:      # tensor-core path: the first block's input LayerNorm is computed by the embedding kernel
@@ -964,11 +1004,20 @@ class UserSASRecModel(TransformerRecommenderModel):
         item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
             raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
-        if replace_first_item:
-            raise NotImplementedError("replace_first_item=True is not on the B200 path")
-        if mode != "full":
-            raise NotImplementedError("UserSASRecModel: only mode='full' is on the B200 path (the sampled projection of the "
-                                      "reference, user_sasrec/components.py, is a next row)")
+        if mode not in ("full", "neg_sampling"):
+            raise Exception(f"{mode} is an unknown projection mode. Choose either <full> or <neg_sampling>.")
+        if replace_first_item and segment_embedding and user_attributes:
+            # components.py:123-128 builds S+1 segment ids for the S positions that are left: the reference fails on the shapes
+            raise ValueError("replace_first_item=True cannot be combined with segment_embedding (the reference adds (N,S+1) segment "
+                             "embeddings to (N,S) positions)")
+        self.replace_first_item = bool(replace_first_item)
+        if mode == "neg_sampling":
+            # user_sasrec/components.py:10-60 == SASRecProjectionComponent: products with the positive / negative item embeddings
+            # over the S positions of the item sequence -- only runnable when the encoder output has S positions too
+            if user_attributes and not replace_first_item:
+                raise ValueError("UserSASRecModel(mode='neg_sampling') multiplies (N,S,H) item embeddings with the (N,S+1,H) encoder "
+                                 "output when a user token is PREPENDED (the reference fails on the shapes): use replace_first_item=True")
+            self.projection_kind = "sasrec_neg"
         H, V = transformer_hidden_size, item_vocab_size
         if user_attributes:
             max_seq_length += 1
@@ -982,11 +1031,19 @@ class UserSASRecModel(TransformerRecommenderModel):
         specs += [(self.ln1_paths[0] + "+", (H,)), (self.ln1_paths[1] + "+", (H,)),
                   (self.ln2_paths[0] + "+", (H,)), (self.ln2_paths[1], (H,))]
         specs += block_param_specs(cfg, self.blocks_path)
-        specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
+        if mode == "full":
+            specs += [("_projection_layer.linear.weight", (V, H)), ("_projection_layer.linear.bias", (V,))]
         toks, sizes = _tokenizer_sizes(resolve_tokenizers(additional_tokenizers), attribute_vocab_sizes)
         seg_rows = ((1 if additional_attributes else 0) + len(user_attributes or {})) if segment_embedding else 0
         if segment_embedding and (not user_attributes or seg_rows < 2):
             raise NotImplementedError("segment_embedding needs user attributes and at least two segment rows")
         self._setup(cfg, V, max_seq_length, specs, additional_attributes, None, toks, sizes, "add",
                     user_attributes=user_attributes, segment_rows=seg_rows)
+        if mode == "neg_sampling":      # UserSASRecProjectionComponent holds the TransformerEmbedding again (components.py:12-14)
+            base = f"{_EMB}.item_embedding_layer"
+            subs = ["item_embedding.embedding.weight", "embedding_norm.weight", "embedding_norm.bias"]
+            if positional_embedding:
+                subs.append("position_embedding.weight")
+            for sub in subs:
+                _alias(self, f"_projection_layer.embedding.{sub}", _get_param(self, f"{base}.{sub}"))
         _init_xavier(self)

@@ -484,10 +484,13 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
                  learning_rate: float = 0.001, beta_1: float = 0.99, beta_2: float = 0.998, weight_decay: float = 0,
                  loss_function=None, first_item: bool = False):
         super().__init__(model, item_tokenizer, metrics, learning_rate, beta_1, beta_2, weight_decay, loss_function)
-        if first_item:
-            raise NotImplementedError("first_item=True (replace_first_item models) is not on the B200 path")
         self.user_key_len = len(model.optional_metadata_keys())
-        self.first_item = first_item
+        # first_item (user_next_item_prediction_training_module.py:57-60): the logits are used as they come -- for models whose
+        # user token REPLACES the first item (replace_first_item) the S outputs line up with the S targets
+        self.first_item = bool(first_item)
+        if self.first_item != bool(getattr(model, "replace_first_item", False)) and self.user_key_len > 0:
+            raise ValueError("first_item must be set exactly when the model replaces the first item (otherwise the reference compares "
+                             "S logit rows with S+1 / S-1 targets)")
 
     def training_step(self, batch, batch_idx):
         seq = batch[ITEM_SEQ_ENTRY_NAME]
@@ -495,7 +498,7 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
         target = batch[TARGET_ENTRY_NAME]
         if target.dim() != 2:
             raise NotImplementedError("UserNextItemPredictionTrainingModule: per-position targets (N,S) expected")
-        if self.user_key_len > 0:
+        if self.user_key_len > 0 and not self.first_item:
             target = _prepend_pad_column(target, self.item_tokenizer.pad_token_id)
         meta = get_additional_meta_data(self.model, batch)
         loss, ctx = self.model.loss_ce(seq, pm, meta, target, self.item_tokenizer.pad_token_id)
@@ -505,7 +508,7 @@ class UserNextItemPredictionTrainingModule(NextItemPredictionTrainingModule):
 
     def _target_rows(self, seq: torch.Tensor, pm: torch.Tensor) -> torch.Tensor:
         B, S = seq.shape
-        S1 = S + (1 if self.user_key_len > 0 else 0)
+        S1 = S + self.model.user_prefix                          # positions of the encoder output
         last = pm.sum(dim=-1).to(torch.int64) - 1
         last = torch.where(last < 0, last + S1, last)            # advanced indexing wraps -1 around
         return torch.arange(B, device=seq.device, dtype=torch.int64) * S1 + last

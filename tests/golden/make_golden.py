@@ -282,6 +282,71 @@ def user_fixtures():
     print("usasrec full loss", float(loss))
 
 
+def user_fixtures_first_item():
+    """UserSASRec whose user token REPLACES the first item (replace_first_item=True, the example configs'
+    local_usersasrec_config_first_item.jsonnet), with a user_linear_upscale user attribute (a LIST of ids per user,
+    models/ubert4rec/components.py:12-44), in both projection modes: "full" (Linear over the catalog, the module's first_item=True
+    loss over all S positions) and "neg_sampling" (user_sasrec/components.py:10-60) -- SURVEY.md 8f row 1 leftovers."""
+    from asme.core.models.user_sasrec.user_sasrec_model import UserSASRecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    from asme.core.losses.sasrec.sas_rec_losses import SASRecBinaryCrossEntropyLoss
+    gen = torch.Generator().manual_seed(606)
+    V, S, H, L, heads, B, VU, VG, VC, A = 59, 9, 16, 2, 2, 7, 11, 7, 13, 3
+    toks = {"tokenizers.user_id": ref_shims.make_tokenizer(VU, "u"), "tokenizers.gender": ref_shims.make_tokenizer(VG, "g"),
+            "tokenizers.category": ref_shims.make_tokenizer(VC, "c")}
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V), "user_id": toks["tokenizers.user_id"],
+                                     "gender": toks["tokenizers.gender"], "category": toks["tokenizers.category"]})
+    user_attributes = {"user_id": {"embedding_type": "user_linear_upscale"}, "gender": {"embedding_type": "content_embedding"}}
+    additional = {"category": {"embedding_type": "content_embedding"}}
+    seq, lengths = make_sequences(gen, B, S, V, min_len=2)
+    # a list-valued user feature: (B, S, A) ids, 0-padded lists, the same list at every step; only step 0 is read
+    uid = torch.randint(1, VU, (B, 1, A), generator=gen)
+    uid[torch.rand(B, 1, A, generator=gen) < 0.3] = 0
+    uid = uid.repeat(1, S, 1)
+    gender = torch.randint(3, VG, (B, 1), generator=gen).repeat(1, S)
+    cat = torch.randint(3, VC, (B, S), generator=gen)
+    cat[seq == 0] = 0
+    attrs = {"user_id": uid, "gender": gender, "category": cat}
+    tgt = torch.zeros_like(seq)
+    for i in range(B):
+        n = int(lengths[i])
+        tgt[i, :n] = torch.randint(3, V, (n,), generator=gen)
+    common = dict(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L, item_vocab_size=V,
+                  additional_tokenizers=toks, max_seq_length=S, transformer_dropout=0.0, additional_attributes=additional,
+                  user_attributes=user_attributes, segment_embedding=False, replace_first_item=True)
+    base = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": seq, "target": tgt, "user_id": uid, "gender": gender, "category": cat}
+    # ---- mode="full": first_item=True keeps all S logit rows (user_next_item_prediction_training_module.py:57-60)
+    model = UserSASRecModel(mode="full", **common)
+    randomize(model, gen)
+    logits = model(InputSequence(seq, seq.ne(0), attrs))                        # (B, S, V)
+    assert tuple(logits.shape) == (B, S, V)
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.reshape(-1, V), tgt.reshape(-1))
+    loss.backward()
+    last = logits.detach()[torch.arange(B), seq.ne(0).sum(-1) - 1]             # :124-135
+    data = dict(base, logits=logits, loss=loss, eval_logits=last)
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "usasrec_first_item_full.npz"), **to_np(data))
+    print("usasrec first-item full loss", float(loss))
+    # ---- mode="neg_sampling"
+    model = UserSASRecModel(mode="neg_sampling", **common)
+    randomize(model, gen)
+    pos = tgt.clone()
+    neg = torch.randint(3, V, (B, S), generator=gen)
+    neg[seq == 0] = 0
+    pl, nl = model(InputSequence(seq, seq.ne(0), dict(attrs, positive_samples=pos, negative_samples=neg)))
+    loss = SASRecBinaryCrossEntropyLoss()(pl, nl, seq.ne(0))
+    loss.backward()
+    items = torch.randint(0, V, (B, 12), generator=gen)
+    with torch.no_grad():
+        ev = model(InputSequence(seq, seq.ne(0), dict(attrs, positive_samples=items)))         # (B, 12)
+    data = dict(base, positive=pos, negative=neg, pos_logits=pl, neg_logits=nl, loss=loss, eval_items=items, eval_logits=ev)
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "usasrec_first_item_neg.npz"), **to_np(data))
+    print("usasrec first-item neg loss", float(loss))
+
+
 def postfusion_fixtures():
     """post-fusion attributes: the attribute embeddings are merged into the ENCODED sequence, by ``add`` or
     ``multiply``, before the modifier transform (KeBERT4Rec, models/kebert4rec/components.py:97-116) or instead of it (SASRec,
@@ -432,7 +497,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1:]
     steps = {"metric_vectors": export_metric_vectors, "bert4rec": bert4rec_fixture, "kebert4rec": kebert4rec_fixture,
-             "sasrec": sasrec_fixtures, "user": user_fixtures, "postfusion": postfusion_fixtures, "init": init_stats_fixture, "metrics": metrics_fixture}
+             "sasrec": sasrec_fixtures, "user": user_fixtures, "user_first_item": user_fixtures_first_item, "postfusion": postfusion_fixtures, "init": init_stats_fixture, "metrics": metrics_fixture}
     for name, fn in steps.items():
         if not only or name in only:
             fn()

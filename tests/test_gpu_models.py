@@ -200,6 +200,62 @@ def test_usasrec_full_vs_reference_fixture(golden_dir):
     assert np.array_equal(res["rank"].cpu().numpy(), O.target_rank(z["eval_logits"], et.numpy()))
 
 
+def test_usasrec_first_item_full_vs_reference_fixture(golden_dir):
+    """UserSASRec with replace_first_item=True (the user token overwrites position 0, models/ubert4rec/components.py:117-121) and a
+    ``user_linear_upscale`` user attribute (:12-44: Linear over the multi-hot of a list of ids, id 0 included); the module's
+    ``first_item=True`` keeps all S logit rows (user_next_item_prediction_training_module.py:57-60).  Logits, loss, every gradient
+    (incl. the transposed Linear of the id list and its bias) and the evaluation rows vs the unmodified reference."""
+    from asme_b200.data import InputSequence
+    from asme_b200.modules import UserNextItemPredictionTrainingModule
+    z, w, model = build_from_fixture(golden_dir, "usasrec_first_item_full.npz")
+    model.load_state_dict(w)
+    model = model.cuda().train()
+    inp, tgt = torch.from_numpy(z["input"]).cuda(), torch.from_numpy(z["target"]).cuda()
+    attrs = _user_attrs(z)
+    logits = model(InputSequence(inp, inp.ne(0), attrs))
+    assert tuple(logits.shape) == tuple(z["logits"].shape)          # S positions, not S + 1
+    close(logits, z["logits"], msg="logits")
+    with pytest.raises(ValueError):
+        UserNextItemPredictionTrainingModule(model, first_item=False)
+    module = UserNextItemPredictionTrainingModule(model, first_item=True)
+    out = module.training_step({"item": inp, "item.target": tgt, **attrs}, 0)
+    close(out["loss"], z["loss"], rtol=1e-5, atol=1e-5, msg="loss")
+    out["loss"].backward()
+    _check_grads(model, z)
+    model.eval()
+    close(module.predict_step({"item": inp, **attrs}, 0), z["eval_logits"], msg="eval rows")
+    et = torch.randint(3, int(z["V"]), (inp.shape[0],), generator=torch.Generator().manual_seed(0))
+    res = model.evaluate_rank(inp, inp.ne(0), attrs, et.cuda(), k=5, rows=module._target_rows(inp, inp.ne(0)))
+    assert np.array_equal(res["rank"].cpu().numpy(), O.target_rank(z["eval_logits"], et.numpy()))
+    assert np.array_equal(res["topk_idx"].cpu().numpy(), O.topk_ids(z["eval_logits"], 5))
+
+
+def test_usasrec_first_item_neg_sampling_vs_reference_fixture(golden_dir):
+    """UserSASRecModel(mode="neg_sampling") -- the reference's default mode: products with the positive / negative item embeddings
+    (models/user_sasrec/components.py:10-60), BCE loss, item-subset scores at the last position"""
+    from asme_b200.data import InputSequence
+    z, w, model = build_from_fixture(golden_dir, "usasrec_first_item_neg.npz")
+    model.load_state_dict(w)
+    model = model.cuda().train()
+    inp = torch.from_numpy(z["input"]).cuda()
+    attrs = _user_attrs(z)
+    pos, neg = torch.from_numpy(z["positive"]).cuda(), torch.from_numpy(z["negative"]).cuda()
+    pl, nl = model(InputSequence(inp, inp.ne(0), dict(attrs, positive_samples=pos, negative_samples=neg)))
+    close(pl, z["pos_logits"], msg="positive logits")
+    close(nl, z["neg_logits"], msg="negative logits")
+    loss, ctx = model.loss_bce(inp, inp.ne(0), attrs, pos, neg, inp.ne(0))
+    close(loss, z["loss"], rtol=1e-5, atol=1e-5, msg="loss")
+    model.loss_bce_backward(ctx)
+    _check_grads(model, z)
+    model.eval()
+    items = torch.from_numpy(z["eval_items"]).cuda()
+    close(model(InputSequence(inp, inp.ne(0), dict(attrs, positive_samples=items))), z["eval_logits"], msg="item-subset scores")
+    from asme_b200.models import UserSASRecModel
+    with pytest.raises(ValueError):      # a PREPENDED user token cannot be combined with the sampled projection (shapes, as in the reference)
+        UserSASRecModel(16, 2, 1, 59, 9, 0.0, user_attributes={"gender": {"embedding_type": "content_embedding"}},
+                        attribute_vocab_sizes={"gender": 7}, mode="neg_sampling")
+
+
 # ------------------------------------------------------------------------------------------------------------
 # fresh seeded inputs vs the oracle at the BASELINE.json shapes (reduced batch so that the CPU oracle takes seconds)
 # ------------------------------------------------------------------------------------------------------------

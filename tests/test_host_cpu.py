@@ -41,6 +41,17 @@ def build_from_fixture(golden_dir, name):
                                 attribute_vocab_sizes={"category": w["_sequence_embedding_layer.prefusion_attribute_embeddings.category.weight"].shape[0],
                                                        "tags": w["_sequence_embedding_layer.prefusion_attribute_embeddings.tags.linear.weight"].shape[1]},
                                 **kw)
+    elif name.startswith("usasrec_first_item"):
+        from asme_b200.models import UserSASRecModel
+        emb = "_sequence_embedding_layer"
+        sizes = {"user_id": w[f"{emb}.user_attribute_embeddings.user_id.linear.weight"].shape[1],
+                 "gender": w[f"{emb}.user_attribute_embeddings.gender.weight"].shape[0],
+                 "category": w[f"{emb}.additional_attribute_embeddings.category.weight"].shape[0]}
+        model = UserSASRecModel(additional_attributes={"category": {"embedding_type": "content_embedding"}},
+                                user_attributes={"user_id": {"embedding_type": "user_linear_upscale"},
+                                                 "gender": {"embedding_type": "content_embedding"}},
+                                attribute_vocab_sizes=sizes, replace_first_item=True,
+                                mode="full" if name.endswith("full.npz") else "neg_sampling", **kw)
     elif name.startswith("ubert4rec") or name.startswith("usasrec"):
         from asme_b200.models import UBERT4RecModel, UserSASRecModel
         emb = "_sequence_embedding_layer"
@@ -59,7 +70,8 @@ def build_from_fixture(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", ["bert4rec_small.npz", "kebert4rec_small.npz", "sasrec_full_small.npz", "sasrec_neg_small.npz",
-                                  "ubert4rec_small.npz", "usasrec_full_small.npz", "kebert4rec_postfusion_add.npz",
+                                  "ubert4rec_small.npz", "usasrec_full_small.npz", "usasrec_first_item_full.npz", "usasrec_first_item_neg.npz",
+                                  "kebert4rec_postfusion_add.npz",
                                   "kebert4rec_postfusion_multiply.npz", "sasrec_postfusion_add.npz", "sasrec_postfusion_multiply.npz"])
 def test_state_dict_is_checkpoint_compatible(golden_dir, name):
     """every key of the reference's state_dict exists with the same shape, and loads strictly"""
@@ -159,11 +171,21 @@ def test_user_models_expose_user_keys_and_extra_position():
     assert tuple(sd["_sequence_embedding_layer.segment_embedding.weight"].shape) == (2, 16)
     assert "_sequence_representation_layer.transformer_encoder.transformer_blocks.0.attention.output_linear.weight" in sd
     assert not m.cfg.bidirectional                      # the reference builds UBERT4Rec's encoder with bidirectional=False
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):       # sampled projection + PREPENDED user token: (N,S,H) x (N,S+1,H), fails in the reference too
         UserSASRecModel(16, 2, 1, 50, 12, 0.0, mode="neg_sampling", **kw)
-    with pytest.raises(NotImplementedError):
-        UBERT4RecModel(16, 2, 1, 50, 12, 0.0, user_attributes={"uid": {"embedding_type": "user_linear_upscale"}},
+    n = UserSASRecModel(16, 2, 1, 50, 12, 0.0, mode="neg_sampling", replace_first_item=True, **kw)
+    assert n.user_prefix == 0 and n.projection_kind == "sasrec_neg" and "_projection_layer.embedding.item_embedding.embedding.weight" in n.state_dict()
+    with pytest.raises(ValueError):       # S+1 segment ids for S positions
+        UserSASRecModel(16, 2, 1, 50, 12, 0.0, mode="full", replace_first_item=True, segment_embedding=True,
+                        user_attributes={"uid": {"embedding_type": "user_embedding"}, "g": {"embedding_type": "user_embedding"}},
+                        attribute_vocab_sizes={"uid": 5, "g": 4})
+    u = UBERT4RecModel(16, 2, 1, 50, 12, 0.0, user_attributes={"uid": {"embedding_type": "user_linear_upscale"}},
                        attribute_vocab_sizes={"uid": 5})
+    sd = u.state_dict()          # models/ubert4rec/components.py:12-44: nn.Linear(vocab, hidden)
+    assert tuple(sd["_sequence_embedding_layer.user_attribute_embeddings.uid.linear.weight"].shape) == (16, 5)
+    assert tuple(sd["_sequence_embedding_layer.user_attribute_embeddings.uid.linear.bias"].shape) == (16,)
+    with pytest.raises(NotImplementedError):
+        UBERT4RecModel(16, 2, 1, 50, 12, 0.0, user_attributes={"uid": {"embedding_type": "linear_upscale"}}, attribute_vocab_sizes={"uid": 5})
 
 
 def test_fixed_items_sampler_on_dense_predictions():

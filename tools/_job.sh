@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_r2c.log 2>&1; tail -4 gpurun_out/gputests_r2c.log
-timeout 400 python bench.py --no-cpu > gpurun_out/bench_r2c.json 2> gpurun_out/bench_r2c.err; tail -c 600 gpurun_out/bench_r2c.json
+timeout 900 python -m pytest tests/test_gpu_models.py tests/test_gpu_models_bf16.py tests/test_gpu_c1.py -x -q > gpurun_out/t7.log 2>&1; tail -15 gpurun_out/t7.log
