@@ -350,7 +350,9 @@ int asme_b200_tc_score_pipeline_probe(const void* Hb, int R, int Kp, const void*
     discard) every accumulator: TMEM read throughput */, asme_stream_t stream);
 /* diagnostic tuning knobs of the scoring sweep (results never depend on them): knob 0 / 3 = epilogue warpgroups (2 | 4) of
  * the top-k / the CE and count-only sweeps, knob 4 = CTA pairs, knob 5 = programmatic dependent launch, knob 6 = 16-column K tail
- * staged with the 32-byte swizzle (default on), knob 1 = sample-sweep divisor (0: no sample sweep; default 16), knob 2 = reject every top-k candidate (cost of the insertion-free sweep) */
+ * staged with the 32-byte swizzle (default on), knob 1 = sample-sweep divisor (0: no sample sweep; default 16), knob 2 = reject every top-k candidate (cost of the insertion-free sweep),
+ * knob 7 = candidate FIFO depth (8..16), knob 8 = candidate sweeps over many row tiles: 1 (default) sequential parts per CTA with
+ * unfolded per-thread lists, 0 the catalog cut into 16 splits per row tile */
 int asme_b200_tc_score_tune(int knob, int value);
 /* cross-entropy partials over the slice: row_max, row_sumexp (natural units, combine across shards as for the fp32
  * entry point) and target_logit (owner shard writes; caller zero-fills) */

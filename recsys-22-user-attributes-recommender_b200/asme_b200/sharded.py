@@ -185,6 +185,10 @@ def tc_local_scorer(wb_shard: torch.Tensor, bias_shard: Optional[torch.Tensor], 
     so the merged lists are the fp32 path's.  ``bias_bounds`` (ops.bias_chunk_bounds(bias_shard), exact lists without a count sweep
     only): the slice is the plain (Vloc, H) table and the bias is added per chunk where a score could pass the threshold."""
     from . import ops
+    # candidates per user and slice: a slice of 1/G of the catalog holds ~k/G of a user's global top k, and the certificate only needs
+    # spare entries beyond the slice's OWN k best -- 32 instead of 64 halves the fp32 re-scoring of G x B_local users per rank
+    G = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    k_out = 32 if G >= 4 else 64
 
     def score(hidden_all, target_all, k, target_score_in, want_ce: bool = False):
         hb = ops.cast_bf16_ext(hidden_all) if folded else ops.cast_bf16(hidden_all, ld_out=wb_shard.shape[1])
@@ -196,9 +200,9 @@ def tc_local_scorer(wb_shard: torch.Tensor, bias_shard: Optional[torch.Tensor], 
         else:
             w32, b32, nb = exact
             if bias_bounds is not None:
-                c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, 64, v0=v0, bias_bounds=bias_bounds)
+                c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, k_out, v0=v0, bias_bounds=bias_bounds)
             else:
-                c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, 64, target=target_all, v0=v0)
+                c = ops.tc_score_candidates(hb, wb_shard, bias_shard, k, k_out, target=target_all, v0=v0)
             r = ops.topk_rescore(hidden_all, w32, b32, c["cand_idx"], c["cand_val"], k, nb, target_all, v0=v0, want_rank=False,
                                  cand_bound=c["bound"])
             ops.score_topk_flagged(hidden_all, w32, b32, target_all, r["target_score"], k, r["row_flag"], r["topk_val"], r["topk_idx"],

@@ -153,19 +153,21 @@ __global__ void __launch_bounds__(SC_THREADS) score_topk_kernel(const float* __r
                                                                 const float* __restrict__ target_score, int k,
                                                                 int tiles_per_split, float* __restrict__ pv,
                                                                 int* __restrict__ pi, int* __restrict__ pg,
-                                                                int* __restrict__ pt, const int32_t* __restrict__ row_flag) {
+                                                                int* __restrict__ pt, const int32_t* __restrict__ tile_list) {
     extern __shared__ __align__(16) float smem[];
     const int ld = H + 4;
     float* hs = smem;
     float* Ws = hs + TS * ld;
     float* tile = Ws + TS * ld;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16, warp = tid / 32, lane = tid % 32;
-    const int m0 = blockIdx.x * TS;
     const int split = blockIdx.y;
-    if (row_flag != nullptr) {       // only row tiles that hold a flagged row are swept (exact re-run of uncertified rows)
-        const int any = __syncthreads_or(tid < TS && m0 + tid < R && row_flag[m0 + tid] != 0);
-        if (!any) return;
-    }
+    // tile_list (flagged variant): {count, row tile, row tile, ...} written by flagged_tiles_kernel -- the grid's x dimension is a
+    // small constant and CTA x sweeps the listed row tiles x, x + gridDim.x, ...: with nothing flagged every CTA reads the count
+    // and leaves (the first version launched one CTA per (row tile, split) just to test the flags: 19 000 empty CTAs at 8192 rows)
+    const int n_list = tile_list ? tile_list[0] : (int)gridDim.x;
+  for (int ti = blockIdx.x; ti < n_list; ti += gridDim.x) {
+    const int m0 = (tile_list ? tile_list[1 + ti] : ti) * TS;
+    __syncthreads();                 // the previous row tile's shared memory is no longer read
     const int tile_begin = split * tiles_per_split;
     const int tile_end = min(ceil_div(Vloc, TS), tile_begin + tiles_per_split);
 
@@ -223,6 +225,39 @@ __global__ void __launch_bounds__(SC_THREADS) score_topk_kernel(const float* __r
         }
         if (lane == 0) { pg[o] = g; pt[o] = tt; }
     }
+  }
+}
+
+// row tiles (of TS rows) that hold a flagged row -> list[0] = count, list[1..] = tile indices in ascending order (one block)
+__global__ void __launch_bounds__(1024) flagged_tiles_kernel(const int32_t* __restrict__ row_flag, int R, int32_t* __restrict__ list) {
+    __shared__ int warp_count[32];
+    __shared__ int base;
+    const int n_tiles = ceil_div(R, TS);
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < n_tiles; t0 += blockDim.x) {
+        const int t = t0 + tid;
+        bool any = false;
+        if (t < n_tiles) {
+            const int r1 = min(R, (t + 1) * TS);
+            for (int r = t * TS; r < r1; ++r) any |= row_flag[r] != 0;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, any);
+        if (lane == 0) warp_count[warp] = __popc(b);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += warp_count[w];
+        if (any) list[1 + before + __popc(b & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (tid == 0) {
+            int total = 0;
+            for (int w = 0; w < (int)blockDim.x / 32; ++w) total += warp_count[w];
+            base += total;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) list[0] = base;
 }
 
 // merge `parts` sorted 32-wide (or k-wide) lists per row; one warp per row
@@ -277,9 +312,10 @@ extern "C" int asme_b200_score_topk_rank(const float* Hrows, int R, int H, const
 // The exact sweep for the rows a certificate could not cover (asme_b200_topk_rescore: row_flag != 0): only row tiles holding a
 // flagged row run, only flagged rows are written -- topk_val / topk_idx (and rank = exact full rank, when given) of the others
 // keep what they hold.  Everything is decided on the device: with no flagged row the launch is a few microseconds of empty CTAs.
+#define FLAGGED_GRID_X 8      // row tiles swept at a time by the flagged variant (each over all SMs' worth of catalog splits)
 extern "C" size_t asme_b200_score_topk_flagged_workspace_bytes(int R, int Vloc) {
     const size_t splits = ceil_div(Vloc, TS) < ASME_NUM_SMS ? ceil_div(Vloc, TS) : ASME_NUM_SMS;
-    return splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int));
+    return splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int)) + ((size_t)ceil_div(R, TS) + 4) * sizeof(int32_t);
 }
 extern "C" int asme_b200_score_topk_flagged(const float* Hrows, int R, int H, const float* W, const float* bias, int v0, int Vloc,
                                             const int64_t* target, const float* target_score, int k, const int32_t* row_flag,
@@ -302,7 +338,8 @@ static int score_topk_impl(const float* Hrows, int R, int H, const float* W, con
     if (R == 0) return ASME_OK;
     // few row tiles are expected to be live in the flagged variant: split the catalog over the whole machine for each of them
     const int splits = row_flag ? (ceil_div(Vloc, TS) < ASME_NUM_SMS ? ceil_div(Vloc, TS) : ASME_NUM_SMS) : item_splits(R, Vloc);
-    if (ws_bytes < (size_t)splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int))) {
+    const size_t parts_bytes = (size_t)splits * R * (32 * (sizeof(float) + sizeof(int)) + 2 * sizeof(int));
+    if (ws_bytes < parts_bytes + (row_flag ? ((size_t)ceil_div(R, TS) + 4) * sizeof(int32_t) : 0)) {
         asme_set_error("score_topk_rank: workspace too small");
         return ASME_ERR_WORKSPACE;
     }
@@ -315,8 +352,16 @@ static int score_topk_impl(const float* Hrows, int R, int H, const float* W, con
     rc = set_smem(score_topk_kernel, smem);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    score_topk_kernel<<<dim3(ceil_div(R, TS), splits), SC_THREADS, smem, st>>>(Hrows, R, H, W, bias, v0, Vloc, target,
-                                                                               target_score, k, tiles_per_split, pv, pi, pg, pt, row_flag);
+    int32_t* tile_list = nullptr;
+    int grid_x = ceil_div(R, TS);
+    if (row_flag) {          // compact the row tiles that hold a flagged row; a small fixed grid loops over them
+        tile_list = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ws) + parts_bytes);
+        flagged_tiles_kernel<<<1, 1024, 0, st>>>(row_flag, R, tile_list);
+        ASME_LAUNCH_OK();
+        if (grid_x > FLAGGED_GRID_X) grid_x = FLAGGED_GRID_X;
+    }
+    score_topk_kernel<<<dim3(grid_x, splits), SC_THREADS, smem, st>>>(Hrows, R, H, W, bias, v0, Vloc, target,
+                                                                      target_score, k, tiles_per_split, pv, pi, pg, pt, tile_list);
     ASME_LAUNCH_OK();
     topk_merge_kernel<<<ceil_div(R, 4), 128, 0, st>>>(pv, pi, target ? pg : nullptr, pt, splits, R, 32, k, topk_val, topk_idx,
                                                       n_greater, n_tie_lower, row_flag, rank_out);

@@ -208,6 +208,12 @@ struct ScoreTcArgs {
     float* ps;                   // CE: partial sum-exp   [parts][R]
     float* captured;             // [R]: score of the target column as computed by this kernel (owner writes)
     const int32_t* n_live;       // device count of live rows (row selections of capacity R) or NULL: row tiles past it exit at once
+    int seq_parts;               // 0 / 1: one part per CTA.  P > 1 (round-robin tiles, top-k only): the CTA sweeps the parts split*P .. split*P+P-1
+                                 // one after the other -- part g = tiles g, g + tile_step, g + 2 tile_step, ... -- and every epilogue THREAD
+                                 // writes its own list at the end of each part (slot (g * WGS + warpgroup): no fold), keeps the list's tail as
+                                 // its threshold and starts the next part with an empty list.  Many row tiles (a rank of the vocab-sharded
+                                 // evaluation scores ALL users against its slice) then need neither 16 short-lived CTAs per row tile (7 waves,
+                                 // each paying the insertion storm of an unseeded list) nor a threshold pass.
     int tile_step;               // 0 / 1: a split sweeps a contiguous range of tiles; S > 1: split s sweeps tiles s, s+S, s+2S, ... (round
                                  // robin: whatever order the catalog is in, every split sees an even share of the best items)
 };
@@ -334,8 +340,14 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
     const int m0 = blockIdx.x * BM;
     const int split = blockIdx.y;
     const int tstep = a.tile_step > 1 ? a.tile_step : 1;
-    const int t0 = tstep > 1 ? min(a.n_tiles, split + a.tile_lo * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
-    const int t1 = tstep > 1 ? min(a.n_tiles, split + a.tile_hi * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_hi);
+    const int nseq = a.seq_parts > 1 ? a.seq_parts : 1;          // parts this CTA sweeps one after the other
+    // first / end tile of sequential part pp (pp = 0 when the CTA has one part)
+    auto part_t0 = [&](int pp) {
+        return tstep > 1 ? min(a.n_tiles, split * nseq + pp + a.tile_lo * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
+    };
+    auto part_t1 = [&](int pp) {
+        return tstep > 1 ? min(a.n_tiles, split * nseq + pp + a.tile_hi * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_hi);
+    };
     if (a.n_live != nullptr && m0 >= __ldg(a.n_live)) return;      // whole CTA, before any barrier / TMEM allocation (never with PAIR)
 
     if (warp == 0 && lane == 0) {
@@ -381,7 +393,8 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
             int s = 0;                                    // ring slot and its phase, advanced without integer division
             uint32_t ph = 0;
-            for (int t = t0; t < t1; t += tstep) {
+            for (int pp = 0; pp < nseq; ++pp)
+            for (int t = part_t0(pp), t1 = part_t1(pp); t < t1; t += tstep) {
                 for (int c = 0; c < kch; ++c) {
                     mbar_wait(&bars->empty[s], ph ^ 1u);
                     const bool tail = a.tail16 && c == kch - 1;
@@ -406,7 +419,8 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             const uint64_t bdesc0 = smem_desc_sw128(smem_u32(sB));
             int i = 0, s = 0;
             uint32_t ph = 0;
-            for (int t = t0; t < t1; t += tstep, ++i) {
+            for (int pp = 0; pp < nseq; ++pp)
+            for (int t = part_t0(pp), t1 = part_t1(pp); t < t1; t += tstep, ++i) {
                 const int as = i & 1;
                 const uint32_t aph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bars->tempty[as], aph ^ 1u);
@@ -491,6 +505,8 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             b0 = __ldg(a.bias_bounds + min(c, bb_last));
             b1 = __ldg(a.bias_bounds + min(c + 1, bb_last));
         };
+      for (int pp = 0; pp < nseq; ++pp) {
+        const int t0 = part_t0(pp), t1 = part_t1(pp);
         if (use_bb && t0 < t1) load_bb(t0, bb_cur0, bb_cur1);
         for (int t = t0; t < t1; t += tstep, ++i) {
             const int as = i & 1;
@@ -653,10 +669,29 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
             bb_cur0 = bb_nxt0; bb_cur1 = bb_nxt1;
         }
+        if (TOPK && nseq > 1) {       // end of a sequential part: this thread's own list goes out, its tail seeds the next part
+            pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
+            if (row_ok) {
+                const size_t o = ((size_t)a.part0 + (size_t)(split * nseq + pp) * WGS + wg) * a.R + row;
+#pragma unroll
+                for (int p = 0; p < KL; ++p) {
+                    if (p < a.k) {
+                        a.pv[o * a.k + p] = lv[p];
+                        a.pi[o * a.k + p] = li[p];
+                    }
+                }
+            }
+            // (strictly below the tail: an equal score with a lower item id still has to pass the strict compare)
+            if (li[KL - 1] != INT_MAX) thr0 = fmaxf(thr0, nextafterf(lv[KL - 1], -INFINITY));
+            thr = thr0;
+#pragma unroll
+            for (int p = 0; p < KL; ++p) { lv[p] = -INFINITY; li[p] = INT_MAX; }
+        }
+      }
         if (TOPK) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
         // --- fold the warpgroups' results into warpgroup 0 through the table ring (idle: every MMA of this CTA has completed),
         //     so that the CTA emits ONE partial result per row
-        if (EPI != EPI_PROBE) {
+        if (EPI != EPI_PROBE && nseq == 1) {
             constexpr int SLOTS = EPI == EPI_CE ? 2 : (2 * KL + 2);       // 32-bit words staged per row and warpgroup
             uint32_t* xs = reinterpret_cast<uint32_t*>(sB);               // [WGS-1][SLOTS][128]
             if (wg > 0) {
@@ -703,7 +738,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
         }
         // --- write this split's partial results ---
-        if (row_ok && wg == 0) {
+        if (row_ok && wg == 0 && nseq == 1) {
             const size_t part = (size_t)a.part0 + (size_t)split;
             const size_t o = part * a.R + row;
             if (EPI == EPI_CE) {
@@ -980,6 +1015,8 @@ static int g_pair = 0;             // 1: CTA pairs (cta_group::2) whenever there
 static int g_tail16 = 1;           // stage a 16-column K tail (Kp = 64 k + 16: folded bias) as a 32-byte-swizzled quarter-size box
 static int g_pend_cap = 12;        // candidate FIFO depth per epilogue thread: 8 bytes x 512 threads per entry come out of the B ring's
                                    // shared memory -- 12 instead of 16 buys the ring a fourth slot at Kp = 144 (three K chunks per tile)
+static int g_cand_seq = 1;         // candidate sweeps over many row tiles: 1 = sequential parts per CTA with unfolded thread lists;
+                                   // 0 = always cut the catalog into CAND_MIN_PARTS splits (the first scheme, kept for A/B)
 static int g_pdl = 0;              // programmatic dependent launch between the launches of one top-k call
 int g_pdl_merge = 0;            // measured: slower (early-scheduled dependents take SM resources from the sweep) -> off, kept as a knob
 
@@ -993,6 +1030,7 @@ extern "C" int asme_b200_tc_score_tune(int knob, int value) {
         case 5: g_pdl = g_pdl_merge = value ? 1 : 0; break;
         case 6: g_tail16 = value ? 1 : 0; break;
         case 7: ASME_REQUIRE(value >= 8 && value <= PEND_CAP_MAX, "tc_score_tune: FIFO depth must be 8..16"); g_pend_cap = value; break;
+        case 8: g_cand_seq = value ? 1 : 0; break;
         default: ASME_REQUIRE(false, "tc_score_tune: unknown knob %d", knob);
     }
     return ASME_OK;
@@ -1190,14 +1228,29 @@ extern "C" int asme_b200_tc_score_topk(const void* Hb, int R, int Kp, const void
 // CTA still sweeps many tiles), and catalogs of fewer tiles than that take the classic path with k_out-entry thread lists.
 #define CAND_MIN_PARTS 16
 static int cand_list_len(int k) { return k <= 2 ? 5 : 10; }      // thread-list entries in union mode: at least 2k spare-ish, 5 or 10
-static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* use_union) {
+// seq (out): sequential parts per CTA.  When the row tiles alone (nearly) fill the machine the natural split count is below
+// CAND_MIN_PARTS; instead of cutting the catalog into 16 short-lived CTAs per row tile, every CTA sweeps ``seq`` parts in turn and
+// its four warpgroups write their lists unfolded: splits * seq * WGS lists per row (ScoreTcArgs::seq_parts).
+static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* use_union, int* seq) {
     int rc = make_plan(R, Kp, Vloc, p, true);
     if (rc) return rc;
+    *seq = 1;
     *use_union = k <= 10 && !p->pair && p->n_tiles >= CAND_MIN_PARTS;
     if (*use_union && p->splits < CAND_MIN_PARTS) {
-        p->tiles_per_split = ceil_div(p->n_tiles, CAND_MIN_PARTS);
-        p->splits = ceil_div(p->n_tiles, p->tiles_per_split);
-        p->parts = p->splits;
+        // measured on one GPU with the slice shapes of G ranks (1024 G rows x 1 000 003 / G items): G = 8 (2 natural splits)
+        // 0.53 vs 0.87 ms; G = 2 (9 natural splits) 0.475 vs 0.415 ms -- the first scheme's threshold pass wins while a row tile
+        // still gets several CTAs
+        if (g_cand_seq && p->wgs == 4 && p->splits <= 4 && p->n_tiles >= 4 * CAND_MIN_PARTS) {
+            int sq = ceil_div(CAND_MIN_PARTS, p->splits * p->wgs);
+            if (sq < 2) sq = 2;            // (seq = 1 would be the folded single-part kernel path)
+            *seq = sq;
+            p->tiles_per_split = ceil_div(p->n_tiles, p->splits * sq);      // tiles per PART
+            p->parts = p->splits * sq * p->wgs;                            // lists per row
+        } else {
+            p->tiles_per_split = ceil_div(p->n_tiles, CAND_MIN_PARTS);
+            p->splits = ceil_div(p->n_tiles, p->tiles_per_split);
+            p->parts = p->splits;
+        }
     }
     return ASME_OK;
 }
@@ -1206,9 +1259,11 @@ extern "C" size_t asme_b200_tc_score_candidates_workspace_bytes(int R, int Kp, i
     if (R < 1) R = 1;
     ScorePlan p;
     bool use_union = false;
-    if (make_cand_plan(R, Kp, Vloc, k, &p, &use_union)) return 0;
+    int seq = 1;
+    if (make_cand_plan(R, Kp, Vloc, k, &p, &use_union, &seq)) return 0;
     const size_t classic = asme_b200_tc_score_topk_workspace_bytes(R, Kp, Vloc, 32) + (size_t)R * 32 * 8;
-    const size_t uni = (size_t)2 * (p.splits + 1) * MAX_EPI_WGS * R * ((size_t)kk * 8 + 8) + (size_t)R * kk * 8;
+    const size_t lists = (size_t)(p.parts > p.splits ? p.parts : p.splits) + MAX_EPI_WGS;
+    const size_t uni = (size_t)2 * lists * MAX_EPI_WGS * R * ((size_t)kk * 8 + 8) + (size_t)R * kk * 8;
     return classic > uni ? classic : uni;
 }
 extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, const void* Wb, const float* bias, const float* bias_bounds,
@@ -1224,7 +1279,8 @@ extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, cons
     cudaStream_t st = (cudaStream_t)stream;
     ScorePlan p;
     bool use_union = false;
-    int rc = make_cand_plan(R, Kp, Vloc, k, &p, &use_union);
+    int seq = 1;
+    int rc = make_cand_plan(R, Kp, Vloc, k, &p, &use_union, &seq);
     if (rc) return rc;
     const int kl = cand_list_len(k);          // entries of the sweep's lists (>= k)
     if (!use_union) {          // classic: the true bf16 top 32 (the longest thread lists); unused candidate slots stay empty
@@ -1252,11 +1308,11 @@ extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, cons
     if (rc) return rc;
     rc = make_tail_maps(&p, Hb, R, Wb, Vloc, Kp);
     if (rc) return rc;
-    const int n_sample = sample_tiles(p);
+    const int n_sample = seq > 1 ? 0 : sample_tiles(p);      // sequential parts seed their own thresholds
     const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = kl; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap;
-    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_step = p.splits;
+    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_step = p.splits * seq; a.seq_parts = seq;
     a.bias = bias; a.bias_bounds = reinterpret_cast<const float2*>(bias_bounds); a.target = target; a.target_score = nullptr; a.thr_floor = g_thr_floor;
     a.pv = (float*)ws;
     a.pi = (int*)(a.pv + (size_t)total_parts * R * kl);

@@ -181,3 +181,31 @@ def test_exact_topk_with_the_bias_bounded_per_chunk(R, V, H, k, sigma_b):
     assert torch.equal(out["topk_val"], val)
     assert torch.equal(out["target_score"], ts)
     assert torch.equal(torch.clamp(out["rank"], max=k + 1), torch.clamp(rank, max=k + 1).to(torch.int32))
+
+
+@pytest.mark.parametrize("R,V,k", [(2500, 70001, 10), (8192, 125001, 10), (1100, 40000, 3)])
+def test_exact_topk_with_many_row_tiles(R, V, k):
+    """a rank of the vocab-sharded evaluation scores ALL users of the box against its slice: so many row tiles that the catalog is
+    not cut into 16 CTAs per row tile -- every CTA sweeps several parts in turn and its warpgroups write their lists unfolded
+    (ScoreTcArgs::seq_parts).  Lists / scores equal to the strict fp32 sweep on a row sample, every row certified, and the same
+    lists from the first scheme (knob 8 = 0)."""
+    from asme_b200 import models, ops
+    H = 128
+    g = torch.Generator(device="cuda").manual_seed(R + V + k)
+    h = torch.randn(R, H, generator=g, device="cuda")
+    w = torch.randn(V, H, generator=g, device="cuda") * 0.03
+    b = torch.randn(V, generator=g, device="cuda") * 0.01
+    target = torch.randint(0, V, (R,), generator=g, device="cuda")
+    out = _exact(ops, models, h, w, b, k, target)
+    assert int(out["n_uncertified"]) == 0
+    rows = torch.arange(0, R, max(1, R // 300), device="cuda")
+    val, idx, rank, ts = _fp32_sweep(ops, h[rows].contiguous(), w, b, k, target[rows].contiguous())
+    assert torch.equal(out["topk_idx"][rows], idx)
+    assert torch.equal(out["topk_val"][rows], val)
+    assert torch.equal(out["target_score"][rows], ts)
+    ops._lib.call("asme_b200_tc_score_tune", 8, 0)
+    try:
+        first = _exact(ops, models, h, w, b, k, target)
+    finally:
+        ops._lib.call("asme_b200_tc_score_tune", 8, 1)
+    assert torch.equal(first["topk_idx"], out["topk_idx"]) and torch.equal(first["topk_val"], out["topk_val"])

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "recsys-22-user-attributes-recommender_b20
 from asme_b200 import models, ops  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-V, H = 1_000_003, 128
+V, H = (int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_003), 128
 g = torch.Generator(device="cuda").manual_seed(0)
 h = torch.randn(R, H, generator=g, device="cuda")
 w = torch.randn(V, H, generator=g, device="cuda") * 0.02
@@ -37,6 +37,13 @@ def timed(fn, n=20):
 for kc in (10, 20, 32):
     print(f"sweep, {kc}-entry lists: {timed(lambda: ops.tc_score_topk(hb, wb, None, kc, target=target)):.4f} ms")
 print(f"candidate sweep (k=10 lists, union of the splits -> 64): {timed(lambda: ops.tc_score_candidates(hb, wb, None, 10, 64)):.4f} ms")
+ops._lib.call("asme_b200_tc_score_tune", 8, 0)
+print(f"candidate sweep, knob 8 = 0 (16 splits per row tile) -> 64: {timed(lambda: ops.tc_score_candidates(hb, wb, None, 10, 64)):.4f} ms")
+ops._lib.call("asme_b200_tc_score_tune", 8, 1)
+print(f"candidate sweep (k=10 lists, union of the splits -> 32): {timed(lambda: ops.tc_score_candidates(hb, wb, None, 10, 32)):.4f} ms")
+o32 = ops.tc_score_candidates(hb, wb, None, 10, 32)
+r32 = ops.topk_rescore(h, w, b, o32["cand_idx"], o32["cand_val"], 10, nb, target, cand_bound=o32["bound"])
+print(f"re-score + certificate (32 candidates): {timed(lambda: ops.topk_rescore(h, w, b, o32['cand_idx'], o32['cand_val'], 10, nb, target, cand_bound=o32['bound'])):.4f} ms, uncertified rows {int(r32['n_flagged'])}")
 o = ops.tc_score_candidates(hb, wb, None, 10, 64)
 o = dict(topk_idx=o["cand_idx"], topk_val=o["cand_val"], bound=o["bound"])
 print(f"re-score + certificate (64 candidates, k=10): {timed(lambda: ops.topk_rescore(h, w, b, o['topk_idx'], o['topk_val'], 10, nb, target, cand_bound=o['bound'])):.4f} ms")
