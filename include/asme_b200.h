@@ -85,7 +85,16 @@ typedef struct {
     const float* seg_table;
     /* forward only: the first encoder block's input LayerNorm (transformer_layers.py:120-130) applied to the output rows in the
      * same pass: next_out (T,H) bf16 = LN(out; next_gamma, next_beta), next_stats (2,T) = row mean / rstd or NULL */
-    const float* next_gamma;                 /* (H) or NULL */
+    const float* next_gamma;                 /* Basket inputs (N,S,BS) -- dense fallback (models/common/layers/sequence_embedding.py:9-45, :83-93): the item embeddings of a step
+ * pooled over its basket, out (T,H) = sum / mean / max over j of table[ids[t, j]] (mode 0 / 1 / 2; PAD slots take part like any id);
+ * arg (T,H) uint8 = slot of the maximum (max only; first slot on ties).  The pooled rows enter asme_b200_embed_fwd as a table indexed by
+ * the token number.  Backward: d_rows (T*BS, H) = the gradient every (token, slot) receives -- feed it to
+ * asme_b200_embgrad_sorted_reduce with the flattened ids. */
+int asme_b200_embed_pool_fwd(const int64_t* ids, const float* table, int T, int BS, int H, int mode, float* out, uint8_t* arg,
+                             asme_stream_t stream);
+int asme_b200_embed_pool_bwd(const float* d_out, const uint8_t* arg, int T, int BS, int H, int mode, float* d_rows,
+                             asme_stream_t stream);
+/* (H) or NULL */
     const float* next_beta;
     void* next_out;
     float* next_stats;

@@ -47,6 +47,8 @@ _PROTOTYPES = {
     "asme_b200_abi_version": (c_int, []),
     "asme_b200_launch_count": (c_longlong, []),
     "asme_b200_embed_fwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P]),
+    "asme_b200_embed_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "asme_b200_embed_pool_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "asme_b200_embed_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "asme_b200_embed_bwd": (c_int, [POINTER(EmbedDesc), c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "asme_b200_embgrad_workspace_bytes": (c_size_t, [c_int, c_int]),

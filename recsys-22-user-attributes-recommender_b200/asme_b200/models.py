@@ -136,6 +136,7 @@ class TransformerRecommenderModel(ArenaModule):
         return self.additional_userdata_keys
 
     replace_first_item: bool = False           # the user token takes the place of the first item instead of being prepended
+    embedding_pooling_type: Optional[str] = None   # "max" | "sum" | "mean": basket inputs (N,S,BS) pooled per step
 
     @property
     def user_prefix(self) -> int:
@@ -168,6 +169,17 @@ class TransformerRecommenderModel(ArenaModule):
 
     def _embed_spec(self, seq: torch.Tensor, attrs, training: bool, seed: int) -> ops.EmbedSpec:
         """``seq`` / ``attrs``: the item side (:meth:`_item_side`)"""
+        pool = None
+        if seq.dim() == 3:       # basket inputs (N,S,BS): dense fallback -- pool first, then the fused kernel reads the pooled rows
+            if not self.embedding_pooling_type:
+                raise ValueError("basket sequences (N,S,BS) need embedding_pooling_type (max, sum or mean)")
+            if self.user_attrs:
+                raise NotImplementedError("basket sequences together with user attributes")
+            B, S, BS = seq.shape
+            basket = seq.reshape(B * S, BS)
+            pooled, arg = ops.embed_pool_fwd(basket, self.weight(self.item_table_path), self.embedding_pooling_type)
+            pool = (basket, arg, BS)
+            seq = torch.arange(B * S, dtype=torch.int64, device=seq.device).view(B, S)
         B, S = seq.shape
         singles, bags = self._attr_operands(attrs, self.prefusion, self.pre_attr_prefix, B * S)
         # only column 0 of a user feature is read (models/ubert4rec/components.py:112-113).  A user_linear_upscale attribute with a
@@ -193,9 +205,10 @@ class TransformerRecommenderModel(ArenaModule):
             pos = pos[1:]                       # item s of the sliced sequence sits at position s + 1 of the original one
         if pos is not None and S > pos.shape[0]:
             raise RuntimeError(f"sequence length {S} exceeds max_seq_length {pos.shape[0]}")
-        spec = ops.EmbedSpec(seq.reshape(-1), self.weight(self.item_table_path), pos, singles, bags, ln1, ln2,
+        spec = ops.EmbedSpec(seq.reshape(-1), pooled if pool is not None else self.weight(self.item_table_path), pos, singles, bags, ln1, ln2,
                              self.cfg.dropout if training else 0.0, seed, users=users, seg_table=seg)
         spec.user_paths = user_paths
+        spec.pool = pool
         return spec
 
     def _embed_backward(self, saved: Saved, d_x: torch.Tensor):
@@ -210,7 +223,11 @@ class TransformerRecommenderModel(ArenaModule):
         d_item, d_attr = ops.embed_bwd(spec, B, S, d_x, saved.embed_stats, dln)
         if not self.user_attrs:
             pre, ev = saved.extra.pop("sorted_items", (None, None))
-            if pre is None:
+            if getattr(spec, "pool", None) is not None:      # baskets: the token's gradient goes to the pooled slots' table rows
+                basket, arg, BS = spec.pool
+                d_slots = ops.embed_pool_bwd(d_item, arg, BS, self.embedding_pooling_type)
+                ops.embgrad_sorted_reduce(basket.reshape(-1), d_slots, self.weight(self.item_table_path, g))
+            elif pre is None:
                 ops.embgrad_sorted_reduce(spec.item_ids, d_item, self.weight(self.item_table_path, g))
             else:
                 if ev is not None:
@@ -274,7 +291,7 @@ class TransformerRecommenderModel(ArenaModule):
         if self.engine.use_tc() and not self.postfusion:
             if not self.arena_is_intact():
                 self._repack()
-            B, S = seq.shape
+            B, S = seq.shape[:2]
             S += self.user_prefix
             saved = Saved(B=B, S=S, seed=0, training=False, key_valid=self._key_valid(padding_mask, seq))
             x, _, y16, st = ops.embed_fwd(self._embed_spec(*self._item_side(seq, attrs), False, 0), B, S, next_ln=self.engine.first_norm())
@@ -294,7 +311,7 @@ class TransformerRecommenderModel(ArenaModule):
         """embed + encoder blocks (+ post-fusion merge): (T,H) hidden states of every position."""
         if not self.arena_is_intact():
             self._repack()
-        B, S = seq.shape
+        B, S = seq.shape[:2]
         S += self.user_prefix          # hidden states cover the prepended user token as well
         saved = Saved(B=B, S=S, seed=self._next_seed() if training else 0, training=training,
                       key_valid=self._key_valid(padding_mask, seq))
@@ -331,7 +348,7 @@ class TransformerRecommenderModel(ArenaModule):
                 d_hidden = ops.binary(d_hidden, ctx, "multiply")
             self._attr_backward(saved.extra["attrs"], self.postfusion, _POST_ATTR, d_ctx, saved.B * saved.S)
         # the sort of the (item id, token) pairs needs no gradient: second stream, long before the embedding backward consumes it
-        if not self.user_attrs and d_hidden.is_cuda:
+        if not self.user_attrs and d_hidden.is_cuda and getattr(saved.embed_spec, "pool", None) is None:
             spec = saved.embed_spec
             pre = ops.SortedIds(spec.item_ids, self.cfg.hidden, self.weight(self.item_table_path).shape[0])
             ev = self.engine.run_on_side(pre.sort, keep=(pre,))
@@ -415,9 +432,7 @@ class TransformerRecommenderModel(ArenaModule):
     @torch.no_grad()
     def forward(self, sequence: InputSequence):
         seq = sequence.sequence
-        if seq.dim() != 2:
-            raise NotImplementedError("basket sequences (N,S,BS) are outside the B200 hot path (SURVEY.md 2.1 #3)")
-        B, S = seq.shape
+        B, S = seq.shape[:2]           # (N,S) or basket inputs (N,S,BS) with embedding_pooling_type
         hidden, _ = self.encode(seq, sequence.padding_mask, sequence.attributes, training=False)
         if self.projection_kind == "sasrec_neg":
             return self._sasrec_forward(sequence, hidden)
@@ -815,7 +830,8 @@ class BERT4RecModel(TransformerRecommenderModel):
         super().__init__()
         item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
-            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+            raise NotImplementedError("BERT4RecModel: the reference passes embedding_pooling_type in the place of TransformerEmbedding's "
+                                      "positional_embedding flag (quirk Q1) -- it never pools; basket inputs work with KeBERT4RecModel / SASRecModel")
         H, V = transformer_hidden_size, item_vocab_size
         cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, True,
                               transformer_intermediate_size, transformer_attention_dropout)
@@ -854,8 +870,9 @@ class KeBERT4RecModel(TransformerRecommenderModel):
                  attribute_vocab_sizes: Dict[str, int] = None):
         super().__init__()
         item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
-        if embedding_pooling_type:
-            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        if embedding_pooling_type and embedding_pooling_type not in ("max", "sum", "mean"):
+            raise KeyError(embedding_pooling_type)          # sequence_embedding.py:30-34
+        self.embedding_pooling_type = embedding_pooling_type or None   # basket inputs (N,S,BS): dense fallback (_embed_spec)
         H, V = transformer_hidden_size, item_vocab_size
         cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, True,
                               transformer_intermediate_size, transformer_attention_dropout)
@@ -891,8 +908,9 @@ class SASRecModel(TransformerRecommenderModel):
                  attribute_vocab_sizes: Dict[str, int] = None):
         super().__init__()
         item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
-        if embedding_pooling_type:
-            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+        if embedding_pooling_type and embedding_pooling_type not in ("max", "sum", "mean"):
+            raise KeyError(embedding_pooling_type)          # sequence_embedding.py:30-34
+        self.embedding_pooling_type = embedding_pooling_type or None   # basket inputs (N,S,BS): dense fallback (_embed_spec)
         H, V = transformer_hidden_size, item_vocab_size
         cfg = _encoder_config(H, num_transformer_heads, num_transformer_layers, transformer_dropout, False,
                               transformer_intermediate_size, transformer_attention_dropout)
@@ -954,7 +972,7 @@ class UBERT4RecModel(TransformerRecommenderModel):
         super().__init__()
         item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
-            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+            raise NotImplementedError("basket pooling together with user attributes is not built")
         H, V = transformer_hidden_size, item_vocab_size
         if user_attributes:
             max_seq_length += 1                                   # ubert4rec_model.py:40-43
@@ -1003,7 +1021,7 @@ class UserSASRecModel(TransformerRecommenderModel):
         super().__init__()
         item_vocab_size = resolve_vocab_size("item", item_vocab_size)     # InjectVocabularySize("item")
         if embedding_pooling_type:
-            raise NotImplementedError("basket pooling is outside the B200 hot path (SURVEY.md 2.1 #3)")
+            raise NotImplementedError("basket pooling together with user attributes is not built")
         if mode not in ("full", "neg_sampling"):
             raise Exception(f"{mode} is an unknown projection mode. Choose either <full> or <neg_sampling>.")
         if replace_first_item and segment_embedding and user_attributes:

@@ -128,6 +128,30 @@ class EmbedSpec:
         return d
 
 
+POOL_MODES = {"sum": 0, "mean": 1, "max": 2}
+
+
+def embed_pool_fwd(ids: torch.Tensor, table: torch.Tensor, mode: str):
+    """basket inputs: ids (T,BS) int64 -> (pooled (T,H) fp32 = sum / mean / max over the basket of table[ids], arg (T,H) uint8 slot of
+    the maximum or None)"""
+    ids, table = _i64(ids), _f32(table, "table")
+    T, BS = ids.shape
+    H = table.shape[1]
+    out = torch.empty(T, H, dtype=torch.float32, device=table.device)
+    arg = torch.empty(T, H, dtype=torch.uint8, device=table.device) if mode == "max" else None
+    _lib.call("asme_b200_embed_pool_fwd", _p(ids), _p(table), T, BS, H, POOL_MODES[mode], _p(out), _p(arg), _stream())
+    return out, arg
+
+
+def embed_pool_bwd(d_out: torch.Tensor, arg: Optional[torch.Tensor], BS: int, mode: str) -> torch.Tensor:
+    """(T*BS, H) gradient rows of every (token, basket slot)"""
+    d_out = _f32(d_out)
+    T, H = d_out.shape
+    d_rows = torch.empty(T * BS, H, dtype=torch.float32, device=d_out.device)
+    _lib.call("asme_b200_embed_pool_bwd", _p(d_out), _p(arg), T, BS, H, POOL_MODES[mode], _p(d_rows), _stream())
+    return d_rows
+
+
 def embed_fwd(spec: EmbedSpec, B: int, S: int, save_stats: bool = False, next_ln=None, next_stats: bool = False):
     """S counts the user position when ``spec.users`` is not empty (item ids are then (B, S-1)).
     ``next_ln=(gamma, beta)``: also returns (y16, st) = the following LayerNorm of the output rows as bf16 and, with

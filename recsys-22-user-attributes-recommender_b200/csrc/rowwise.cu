@@ -262,6 +262,84 @@ __global__ void __launch_bounds__(256, (!PRE && CH == 1) ? 5 : ((!PRE && TOK == 
 }
 
 // ---------------------------------------------------------------------------------------------
+// basket inputs (N,S,BS): item embeddings of a step pooled over the basket (models/common/layers/sequence_embedding.py:9-45,
+// :83-93: max / sum / mean over dim -2, PAD slots take part with E[pad] like any other id).  The dense fallback of SURVEY.md 2.1 #3:
+// the pooled rows (T,H) then enter the fused embedding kernel as a table indexed by the token number.
+//   mode 0 = sum, 1 = mean, 2 = max (arg (T,H) uint8 = basket slot of the maximum, first slot on ties as torch.max reports it)
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int CH>
+__global__ void __launch_bounds__(256) embed_pool_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table, int T,
+                                                             int BS, int H, int mode, float* __restrict__ out,
+                                                             uint8_t* __restrict__ arg) {
+    const int lane = threadIdx.x % LANES;
+    const long long t = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
+    if (t >= T) return;
+    Row<LANES, CH> acc;
+    int am[CH * 4];
+    acc.load(table + __ldg(ids + t * BS) * H, lane);
+#pragma unroll
+    for (int e = 0; e < CH * 4; ++e) am[e] = 0;
+    for (int j = 1; j < BS; ++j) {
+        Row<LANES, CH> r;
+        r.load(table + __ldg(ids + t * BS + j) * H, lane);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (mode == 2) {
+                if (r.v[c].x > acc.v[c].x) { acc.v[c].x = r.v[c].x; am[4 * c] = j; }
+                if (r.v[c].y > acc.v[c].y) { acc.v[c].y = r.v[c].y; am[4 * c + 1] = j; }
+                if (r.v[c].z > acc.v[c].z) { acc.v[c].z = r.v[c].z; am[4 * c + 2] = j; }
+                if (r.v[c].w > acc.v[c].w) { acc.v[c].w = r.v[c].w; am[4 * c + 3] = j; }
+            } else {
+                add4(acc.v[c], r.v[c]);
+            }
+        }
+    }
+    if (mode == 1) {
+        const float inv = 1.0f / (float)BS;           // torch.mean: sum / count
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            acc.v[c].x = acc.v[c].x / (float)BS; acc.v[c].y = acc.v[c].y / (float)BS;
+            acc.v[c].z = acc.v[c].z / (float)BS; acc.v[c].w = acc.v[c].w / (float)BS;
+        }
+        (void)inv;
+    }
+    acc.store(out + t * H, lane);
+    if (mode == 2 && arg != nullptr) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            uchar4 a = make_uchar4((unsigned char)am[4 * c], (unsigned char)am[4 * c + 1], (unsigned char)am[4 * c + 2], (unsigned char)am[4 * c + 3]);
+            *reinterpret_cast<uchar4*>(arg + t * H + (c * LANES + lane) * 4) = a;
+        }
+    }
+}
+// gradient rows of every (token, slot): d_rows[t*BS + j] = d_out[t] (sum), d_out[t] / BS (mean), d_out[t] where slot j held the maximum
+template <int LANES, int CH>
+__global__ void __launch_bounds__(256) embed_pool_bwd_kernel(const float* __restrict__ d_out, const uint8_t* __restrict__ arg, int T,
+                                                             int BS, int H, int mode, float* __restrict__ d_rows) {
+    const int lane = threadIdx.x % LANES;
+    const long long t = (long long)blockIdx.x * (blockDim.x / LANES) + threadIdx.x / LANES;
+    if (t >= T) return;
+    Row<LANES, CH> d;
+    d.load(d_out + t * H, lane);
+    uchar4 am[CH];
+    if (mode == 2) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) am[c] = *reinterpret_cast<const uchar4*>(arg + t * H + (c * LANES + lane) * 4);
+    }
+    for (int j = 0; j < BS; ++j) {
+        Row<LANES, CH> r;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (mode == 0) r.v[c] = d.v[c];
+            else if (mode == 1) r.v[c] = make_float4(d.v[c].x / (float)BS, d.v[c].y / (float)BS, d.v[c].z / (float)BS, d.v[c].w / (float)BS);
+            else r.v[c] = make_float4(am[c].x == j ? d.v[c].x : 0.f, am[c].y == j ? d.v[c].y : 0.f, am[c].z == j ? d.v[c].z : 0.f,
+                                      am[c].w == j ? d.v[c].w : 0.f);
+        }
+        r.store(d_rows + (t * BS + j) * H, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused embedding backward (recomputes the forward from ids + saved LayerNorm statistics)
 // partials: [gridDim.x][4][H] (dgamma1, dbeta1, dgamma2, dbeta2)
 // ---------------------------------------------------------------------------------------------
@@ -561,6 +639,35 @@ static int lanes_wide(int H) { return H / 16; }
             asme_set_error("unsupported hidden size H=%d (supported: 16,32,64,128,256,512)", H); \
             return ASME_ERR_INVALID;                              \
     }
+
+extern "C" int asme_b200_embed_pool_fwd(const int64_t* ids, const float* table, int T, int BS, int H, int mode, float* out,
+                                        uint8_t* arg, asme_stream_t stream) {
+    ASME_REQUIRE(ids && table && out, "embed_pool_fwd: null argument");
+    ASME_REQUIRE(mode >= 0 && mode <= 2 && BS >= 1 && BS <= 255, "embed_pool_fwd: mode=%d BS=%d unsupported", mode, BS);
+    ASME_REQUIRE(mode != 2 || arg, "embed_pool_fwd: max pooling needs the arg output");
+    if (T == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+#define CALL(L, C) embed_pool_fwd_kernel<L, C><<<ceil_div(T, groups), 256, 0, (cudaStream_t)stream>>>(ids, table, T, BS, H, mode, out, arg)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
+extern "C" int asme_b200_embed_pool_bwd(const float* d_out, const uint8_t* arg, int T, int BS, int H, int mode, float* d_rows,
+                                        asme_stream_t stream) {
+    ASME_REQUIRE(d_out && d_rows, "embed_pool_bwd: null argument");
+    ASME_REQUIRE(mode >= 0 && mode <= 2 && BS >= 1 && BS <= 255, "embed_pool_bwd: mode=%d BS=%d unsupported", mode, BS);
+    ASME_REQUIRE(mode != 2 || arg, "embed_pool_bwd: max pooling needs arg");
+    if (T == 0) return ASME_OK;
+    const int lanes = lanes_for(H);
+    const int groups = 256 / lanes;
+#define CALL(L, C) embed_pool_bwd_kernel<L, C><<<ceil_div(T, groups), 256, 0, (cudaStream_t)stream>>>(d_out, arg, T, BS, H, mode, d_rows)
+    DISPATCH_H(H, CALL)
+#undef CALL
+    ASME_LAUNCH_OK();
+    return ASME_OK;
+}
 
 extern "C" int asme_b200_embed_fwd(const asme_embed_desc* d, int T, int S, int H, float* out, float* stats,
                                    asme_stream_t stream) {

@@ -347,6 +347,56 @@ def user_fixtures_first_item():
     print("usasrec first-item neg loss", float(loss))
 
 
+def basket_fixtures():
+    """basket inputs (N,S,BS) pooled per step (models/common/layers/sequence_embedding.py:9-45, :83-93): KeBERT4Rec with max / sum /
+    mean pooling and one attribute table, SASRec (mode="full") with mean pooling -- SURVEY.md 2.1 #3 (dense fallback)."""
+    from asme.core.models.kebert4rec.kebert4rec_model import KeBERT4RecModel
+    from asme.core.models.sasrec.sasrec_model import SASRecModel
+    from asme.core.models.common.layers.data.sequence import InputSequence
+    gen = torch.Generator().manual_seed(707)
+    V, S, H, L, heads, B, VA, BS = 71, 8, 16, 1, 2, 6, 11, 3
+    ref_shims.set_injection_context({"item": ref_shims.make_tokenizer(V), "category": ref_shims.make_tokenizer(VA, "c")})
+    seq, lengths = make_sequences(gen, B, S, V)
+    basket = torch.zeros(B, S, BS, dtype=torch.int64)
+    basket[:, :, 0] = seq
+    for j in range(1, BS):               # further items of a step, 0-padded baskets of different sizes
+        extra = torch.randint(3, V, (B, S), generator=gen)
+        extra[torch.rand(B, S, generator=gen) < 0.4] = 0
+        extra[seq == 0] = 0
+        basket[:, :, j] = extra
+    pm = basket.max(dim=2).values.ne(0)                                  # modules/util/module_util.py:25-29
+    cat = torch.randint(3, VA, (B, S), generator=gen)
+    cat[seq == 0] = 0
+    tgt = torch.zeros_like(seq)
+    for i in range(B):
+        n = int(lengths[i])
+        tgt[i, :n] = torch.randint(3, V, (n,), generator=gen)
+    for pooling in ("max", "sum", "mean"):
+        model = KeBERT4RecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L, max_seq_length=S,
+                                transformer_dropout=0.0, embedding_pooling_type=pooling,
+                                prefusion_attributes={"category": {"embedding_type": "content_embedding"}})
+        randomize(model, gen)
+        logits = model(InputSequence(basket, pm, {"category": cat}))
+        loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, V), tgt.view(-1))
+        loss.backward()
+        data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": basket, "target": tgt, "category": cat, "logits": logits, "loss": loss}
+        data.update(weights_of(model))
+        data.update(grads_of(model))
+        np.savez_compressed(os.path.join(HERE, f"kebert4rec_basket_{pooling}.npz"), **to_np(data))
+        print("kebert4rec basket", pooling, float(loss))
+    model = SASRecModel(transformer_hidden_size=H, num_transformer_heads=heads, num_transformer_layers=L, max_seq_length=S,
+                        transformer_dropout=0.0, embedding_pooling_type="mean", mode="full")
+    randomize(model, gen)
+    logits = model(InputSequence(basket, pm, {}))
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, V), tgt.view(-1))
+    loss.backward()
+    data = {"V": V, "S": S, "H": H, "L": L, "heads": heads, "input": basket, "target": tgt, "logits": logits, "loss": loss}
+    data.update(weights_of(model))
+    data.update(grads_of(model))
+    np.savez_compressed(os.path.join(HERE, "sasrec_basket_mean.npz"), **to_np(data))
+    print("sasrec basket mean", float(loss))
+
+
 def postfusion_fixtures():
     """post-fusion attributes: the attribute embeddings are merged into the ENCODED sequence, by ``add`` or
     ``multiply``, before the modifier transform (KeBERT4Rec, models/kebert4rec/components.py:97-116) or instead of it (SASRec,
@@ -497,7 +547,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1:]
     steps = {"metric_vectors": export_metric_vectors, "bert4rec": bert4rec_fixture, "kebert4rec": kebert4rec_fixture,
-             "sasrec": sasrec_fixtures, "user": user_fixtures, "user_first_item": user_fixtures_first_item, "postfusion": postfusion_fixtures, "init": init_stats_fixture, "metrics": metrics_fixture}
+             "sasrec": sasrec_fixtures, "user": user_fixtures, "user_first_item": user_fixtures_first_item, "basket": basket_fixtures, "postfusion": postfusion_fixtures, "init": init_stats_fixture, "metrics": metrics_fixture}
     for name, fn in steps.items():
         if not only or name in only:
             fn()

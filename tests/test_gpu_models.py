@@ -200,6 +200,27 @@ def test_usasrec_full_vs_reference_fixture(golden_dir):
     assert np.array_equal(res["rank"].cpu().numpy(), O.target_rank(z["eval_logits"], et.numpy()))
 
 
+@pytest.mark.parametrize("name", ["kebert4rec_basket_max.npz", "kebert4rec_basket_sum.npz", "kebert4rec_basket_mean.npz", "sasrec_basket_mean.npz"])
+def test_basket_inputs_vs_reference_fixture(golden_dir, name):
+    """basket inputs (N,S,BS) with embedding_pooling_type max / sum / mean (models/common/layers/sequence_embedding.py:9-45, :83-93; padding
+    mask from the step maximum, modules/util/module_util.py:25-29): logits, loss and every gradient -- incl. the item table through the
+    pooling (max: the slot that held the maximum) -- vs the unmodified reference"""
+    from asme_b200.data import InputSequence
+    from asme_b200.modules import get_padding_mask
+    z, w, model = build_from_fixture(golden_dir, name)
+    model.load_state_dict(w)
+    model = model.cuda().train()
+    inp, tgt = torch.from_numpy(z["input"]).cuda(), torch.from_numpy(z["target"]).cuda()
+    assert inp.dim() == 3
+    pm = get_padding_mask(inp, 0)
+    attrs = {"category": torch.from_numpy(z["category"]).cuda()} if "category" in z.files else {}
+    close(model(InputSequence(inp, pm, attrs)), z["logits"], msg="logits")
+    loss, ctx = model.loss_ce(inp, pm, attrs, tgt)
+    close(loss, z["loss"], msg="loss")
+    model.loss_ce_backward(ctx)
+    _check_grads(model, z)
+
+
 def test_usasrec_first_item_full_vs_reference_fixture(golden_dir):
     """UserSASRec with replace_first_item=True (the user token overwrites position 0, models/ubert4rec/components.py:117-121) and a
     ``user_linear_upscale`` user attribute (:12-44: Linear over the multi-hot of a list of ids, id 0 included); the module's

@@ -35,6 +35,13 @@ def build_from_fixture(golden_dir, name):
             model = SASRecModel(mode="full", postfusion_attributes={"category": {"embedding_type": "content_embedding"}},
                                 postfusion_merge_function=merge,
                                 attribute_vocab_sizes={"category": w[f"{post}.category.weight"].shape[0]}, **kw)
+    elif name.startswith("kebert4rec_basket"):
+        model = KeBERT4RecModel(prefusion_attributes={"category": {"embedding_type": "content_embedding"}},
+                                embedding_pooling_type=name.split("_")[2].split(".")[0],
+                                attribute_vocab_sizes={"category": w["_sequence_embedding_layer.prefusion_attribute_embeddings.category.weight"].shape[0]},
+                                **kw)
+    elif name.startswith("sasrec_basket"):
+        model = SASRecModel(mode="full", embedding_pooling_type="mean", **kw)
     elif name.startswith("kebert4rec"):
         model = KeBERT4RecModel(prefusion_attributes={"category": {"embedding_type": "content_embedding"},
                                                       "tags": {"embedding_type": "linear_upscale"}},
@@ -72,7 +79,8 @@ def build_from_fixture(golden_dir, name):
 @pytest.mark.parametrize("name", ["bert4rec_small.npz", "kebert4rec_small.npz", "sasrec_full_small.npz", "sasrec_neg_small.npz",
                                   "ubert4rec_small.npz", "usasrec_full_small.npz", "usasrec_first_item_full.npz", "usasrec_first_item_neg.npz",
                                   "kebert4rec_postfusion_add.npz",
-                                  "kebert4rec_postfusion_multiply.npz", "sasrec_postfusion_add.npz", "sasrec_postfusion_multiply.npz"])
+                                  "kebert4rec_postfusion_multiply.npz", "sasrec_postfusion_add.npz", "sasrec_postfusion_multiply.npz",
+                                  "kebert4rec_basket_max.npz", "sasrec_basket_mean.npz"])
 def test_state_dict_is_checkpoint_compatible(golden_dir, name):
     """every key of the reference's state_dict exists with the same shape, and loads strictly"""
     z, w, model = build_from_fixture(golden_dir, name)
