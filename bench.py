@@ -602,6 +602,7 @@ def main():
         module.model._step_state = None
         optimizer.step_state = None
     _lib.timing = []
+    _lib.timing_spacer_cycles = 120000          # ~60 us of spin before every timed call: host issue gaps stay out of the kernel times
     barrier()
     l0 = _lib.kernel_launches()
     for i in range(prof_steps):
@@ -610,6 +611,7 @@ def main():
     torch.cuda.synchronize()
     records = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
+    _lib.timing_spacer_cycles = 0
     table, kernel_ms_per_step = summarise_kernels(records, prof_steps, pk)
     unaccounted = sum(r["share"] for r in table if r["algorithmic_bytes"] == 0 and r["algorithmic_flops"] == 0)
     # the timed regions last tens of milliseconds -- shorter than nvidia-smi's sampling period -- so the same step keeps
@@ -674,6 +676,8 @@ def main():
                           window="timed regions + an untimed continuation of the same step until 8 samples (nvidia-smi -lms 50)"),
            "roofline": roofline, "cpu_baseline": cpu, "kernel_ms_per_step": kernel_ms_per_step,
            "kernel_time_without_cost_model": unaccounted,
+           "kernel_timing": "CUDA events around every C-ABI call of one launch-by-launch step on the launching stream, a ~60 us spin kernel "
+                            "queued ahead of each call so that the host's issue gap is not charged to the kernel",
            "kernels_top5": [{k: (round(r[k], 4) if isinstance(r[k], float) else r[k]) for k in ("kernel", "avg_ms", "share", "bound", "frac")}
                             for r in table[:5]],
            "eval": eval_info}
@@ -788,10 +792,12 @@ def bench_eval_c5(args, device, pk, world=1, rank=0, profile=False, graph=True):
     # ---- per-kernel pass of one launch-by-launch step -----------------------------------------------------------------------------
     module.eval_graph = False
     _lib.timing = []
+    _lib.timing_spacer_cycles = 120000          # ~60 us of spin before every timed call: host issue gaps stay out of the kernel times
     step(dev)
     torch.cuda.synchronize()
     rec = [(n, note, a.elapsed_time(b)) for (n, note, a, b) in _lib.timing]
     _lib.timing = None
+    _lib.timing_spacer_cycles = 0
     table, kernel_ms = summarise_kernels(rec, 1, pk)
     score = next((r for r in table if r["kernel"] in ("tc_score_candidates", "tc_score_topk", "score_topk_rank")), None)
     if rank == 0:

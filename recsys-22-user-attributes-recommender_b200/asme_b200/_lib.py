@@ -140,6 +140,10 @@ _PROTOTYPES = {
 _lib = None
 launch_count = 0   # number of C-ABI calls made; kernel launches are counted by the library itself
 timing = None      # when set to a list, every call is bracketed by CUDA events: (name, note, start_event, end_event)
+timing_spacer_cycles = 0   # > 0: a spin kernel of that many GPU cycles is queued before the start event of every timed call, so that the
+                           # events and the call's launches are all in the stream before the GPU reaches them -- otherwise the host's
+                           # issue gap between the start event and the first launch (a few us of Python / ctypes / tensor-map encoding)
+                           # is charged to kernels that themselves run 10-50 us
 note = ""          # shape annotation of the next call (set by ops.py, consumed by the timing hook)
 
 
@@ -187,6 +191,8 @@ def call(name, *args):
     this_note, note = note, ""
     import torch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if timing_spacer_cycles > 0:
+        torch.cuda._sleep(int(timing_spacer_cycles))
     e0.record()          # torch's current stream == the stream the kernels are launched on
     check(fn(*args), name)
     e1.record()
