@@ -295,6 +295,9 @@ def algorithmic_cost(name, note):
     if name == "asme_b200_layernorm_fwd_bf16":       # reads fp32 rows, writes bf16 rows (and an fp32 copy when asked)
         M, H = g("M"), g("H")
         return (4 + 2 + 4 * g("f32")) * M * H, 8 * M * H
+    if name == "asme_b200_tc_block_tail_fused":      # ctx (bf16) + the block's input rows (fp32) in, fp32 rows and / or LayerNorm'ed bf16 rows out;
+        M, H, FF = g("M"), g("H"), g("FF")           # x2, y and the (M, FF) intermediate are not algorithmic traffic
+        return M * H * (2 + 4 + 4 * g("f32") + 2 * g("ln")) + 2 * (H * H + 2 * H * FF), 2 * M * H * H + 4 * M * H * FF
     if name == "asme_b200_tc_ffn_fused":             # y (bf16) + residual (fp32) in, fp32 rows and / or LayerNorm'ed bf16 rows out; the
         M, H, FF = g("M"), g("H"), g("FF")           # (M, FF) intermediate is not algorithmic traffic; both weight matrices once
         return M * H * (2 + 4 + 4 * g("f32") + 2 * g("ln")) + 2 * 2 * H * FF, 4 * M * H * FF

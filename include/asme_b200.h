@@ -408,6 +408,14 @@ int asme_b200_tc_gemm_ln(const void* A, const void* B, int M, int N, int K, int 
 int asme_b200_tc_ffn_fused(const void* Y, const void* W1, const float* b1, const void* W2, const float* b2, const float* residual,
                            int M, int H, int FF, float* out_f32, const float* ln_gamma, const float* ln_beta, void* ln_out,
                            asme_stream_t stream);
+/* The whole tail of an encoder block as ONE kernel (inference; transformer_layers.py:181-199 output_linear + :120-130 residual +
+ * LayerNorm of the output sublayer + :217-220 feed-forward + its residual [+ the next block's LayerNorm]):
+ *   x2 = residual + ctx Wo^T + bo;  y = LayerNorm(x2; pro_gamma, pro_beta);  out = x2 + W2 gelu(W1 y + b1) + b2
+ * ctx (M,H) bf16 = attention output, Wo (H,H) bf16, residual (M,H) fp32 = the block's input rows.  x2, y and the (M, FF) intermediate
+ * stay in tensor / shared memory.  Outputs as asme_b200_tc_ffn_fused. */
+int asme_b200_tc_block_tail_fused(const void* ctx, const void* Wo, const float* bo, const float* residual, const float* pro_gamma,
+                                  const float* pro_beta, const void* W1, const float* b1, const void* W2, const float* b2, int M, int H,
+                                  int FF, float* out_f32, const float* ln_gamma, const float* ln_beta, void* ln_out, asme_stream_t stream);
 /* diagnostic: knob 0 = GELU warpgroups of asme_b200_tc_ffn_fused (0 = automatic, default; 2; 4) */
 int asme_b200_tc_ffn_tune(int knob, int value);
 /* diagnostic: knob 0 selects the tall kernel (1 = persistent CTAs with a resident weight tile, default; 0 = one CTA per tile) */

@@ -110,6 +110,7 @@ _PROTOTYPES = {
     "asme_b200_tc_gemm_ln": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_uint64, c_uint32, c_uint32, P, P, P, c_int, P,
                                      P, P, P, P, P]),
     "asme_b200_tc_ffn_fused": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
+    "asme_b200_tc_block_tail_fused": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P]),
     "asme_b200_tc_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asme_b200_tc_wgrad": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, P, c_size_t, P]),
     "asme_b200_tc_attn_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_uint64, c_uint32, P, P, P, P]),

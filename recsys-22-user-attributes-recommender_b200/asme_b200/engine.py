@@ -26,6 +26,8 @@ SIDE_STREAM_WGRAD = os.environ.get("ASME_B200_SIDE_WGRAD", "1") == "1"
 # ASME_B200_FUSED_FFN_LN=0 keeps the next block's LayerNorm as its own launch (bit-identical bf16 rows to the unfused path)
 FUSED_FFN = os.environ.get("ASME_B200_FUSED_FFN", "1") == "1"
 FUSED_FFN_LN = os.environ.get("ASME_B200_FUSED_FFN_LN", "1") == "1"
+# inference: the output projection, its residual and the output sublayer's LayerNorm move into the same kernel (asme_b200_tc_block_tail_fused)
+FUSED_TAIL = os.environ.get("ASME_B200_FUSED_TAIL", "1") == "1"
 
 BLOCKS = "_sequence_representation_layer.transformer_layer.transformer_blocks"
 MODIFIER = "_sequence_representation_modifier_layer"
@@ -221,6 +223,23 @@ class EncoderEngine:
                 # row selection (index plumbing, no arithmetic)
                 ls.ctx16 = ctx_rows if ctx_rows is not None else ls.ctx16.index_select(0, select_rows)
                 x = x.index_select(0, select_rows)
+            nxt = None
+            if l + 1 < cfg.layers:          # the next layer's input LayerNorm rides in the block's last epilogue
+                npre = f"{self.blocks}.{l + 1}"
+                nxt = (self._w(f"{npre}.input_sublayer.norm.weight"), self._w(f"{npre}.input_sublayer.norm.bias"))
+            if not train and FUSED_TAIL and FUSED_FFN and H in (64, 128) and cfg.intermediate % 64 == 0:
+                # inference: output projection + residual + LayerNorm + feed-forward + residual (+ next LayerNorm) in ONE kernel
+                r = ops.tc_block_tail_fused(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
+                                            self._w(f"{pre}.attention.output_linear.bias"), x,
+                                            (self._w(f"{pre}.output_sublayer.norm.weight"), self._w(f"{pre}.output_sublayer.norm.bias")),
+                                            m.weight_bf16(f"{pre}.feed_forward.w_1.weight"), self._w(f"{pre}.feed_forward.w_1.bias"),
+                                            m.weight_bf16(f"{pre}.feed_forward.w_2.weight"), self._w(f"{pre}.feed_forward.w_2.bias"),
+                                            ln=nxt if FUSED_FFN_LN else None)
+                x = r["f32"]
+                if nxt is not None and not FUSED_FFN_LN:
+                    r["ln16"], _, _ = ops.layernorm_fwd_bf16(x, nxt[0], nxt[1], save_stats=False)
+                y1_next, st1_next = (r["ln16"], None) if nxt is not None else (None, None)
+                continue
             # output projection + residual, with the output sublayer's LayerNorm fused into the epilogue (H <= 128)
             r = ops.tc_gemm(ls.ctx16, m.weight_bf16(f"{pre}.attention.output_linear.weight"),
                             bias=self._w(f"{pre}.attention.output_linear.bias"), p_drop=p, seed=saved.seed,

@@ -633,6 +633,26 @@ def tc_ffn_fused(y16: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torc
     return dict(f32=o32, ln16=ln16)
 
 
+def tc_block_tail_fused(ctx16: torch.Tensor, wo: torch.Tensor, bo: torch.Tensor, residual: torch.Tensor, pro_ln, w1: torch.Tensor,
+                        b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, ln=None, out_f32: bool = True):
+    """tail of an encoder block in one kernel (inference): x2 = residual + ctx Wo^T + bo; y = LayerNorm(x2; *pro_ln);
+    out = x2 + W2 gelu(W1 y + b1) + b2.  returns dict(f32=out or None, ln16=LayerNorm(out; *ln) as bf16 or None)"""
+    ctx16, wo, w1, w2 = _bf16(ctx16, "ctx"), _bf16(wo, "wo"), _bf16(w1, "w1"), _bf16(w2, "w2")
+    M, H = ctx16.shape
+    FF = w1.shape[0]
+    if tuple(wo.shape) != (H, H) or tuple(w1.shape) != (FF, H) or tuple(w2.shape) != (H, FF) or tuple(residual.shape) != (M, H):
+        raise ValueError("tc_block_tail_fused: operand shapes do not match")
+    dev = ctx16.device
+    o32 = torch.empty(M, H, dtype=torch.float32, device=dev) if out_f32 else None
+    ln16 = torch.empty(M, H, dtype=torch.bfloat16, device=dev) if ln is not None else None
+    if _lib.timing is not None:
+        _lib.note = f"M={M},H={H},FF={FF},f32={int(out_f32)},ln={int(ln is not None)},pro=1"
+    _lib.call("asme_b200_tc_block_tail_fused", _p(ctx16), _p(wo), _p(_f32(bo)), _p(_f32(residual)), _p(_f32(pro_ln[0])), _p(_f32(pro_ln[1])),
+              _p(w1), _p(_f32(b1)), _p(w2), _p(_f32(b2)), M, H, FF, _p(o32),
+              _p(_f32(ln[0])) if ln is not None else None, _p(_f32(ln[1])) if ln is not None else None, _p(ln16), _stream())
+    return dict(f32=o32, ln16=ln16)
+
+
 def tc_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True,
              slot: int = 0):
     """dw (N,K) fp32 (+)= dy(M,N)^T x(M,K); dbias (N) (+)= colsum(dy); dy, x bf16.  ``slot``: scratch buffer to use (calls issued

@@ -203,3 +203,49 @@ def test_tc_ffn_fused_integer_exact(ops):
     b2 = ints(gen, H)
     out = ops.tc_ffn_fused(y, torch.zeros(FF, H, device="cuda").bfloat16(), torch.zeros(FF, device="cuda"), w2, b2, x)["f32"]
     assert torch.equal(out, x + b2)
+
+
+@pytest.mark.parametrize("M,H,FF", [(1, 64, 256), (300, 128, 512), (1024, 128, 512), (148 * 128 * 2 + 77, 128, 512), (148 * 128 * 3 + 5, 64, 256),
+                                    (700, 128, 64)])
+def test_tc_block_tail_fused_equals_the_unfused_tail(ops, M, H, FF):
+    """output projection + residual + LayerNorm + feed-forward + residual (+ next LayerNorm) in one kernel (transformer_layers.py:181-199,
+    :120-130, :217-220, :251-258) against the launches it replaces.  x2 = x + ctx Wo^T + bo is the same arithmetic (checked through a
+    zero feed-forward); the LayerNorm inside sums its statistics in another order than the stand-alone kernel, so y and everything
+    after it agree to bf16 rounding, not bit for bit."""
+    from asme_b200._lib import ACT_GELU
+    gen = torch.Generator(device="cuda").manual_seed(M + H + FF + 7)
+    ctx = torch.randn(M, H, generator=gen, device="cuda").bfloat16()
+    x = torch.randn(M, H, generator=gen, device="cuda")
+    wo = (torch.randn(H, H, generator=gen, device="cuda") * 0.1).bfloat16()
+    bo = torch.randn(H, generator=gen, device="cuda") * 0.1
+    w1 = (torch.randn(FF, H, generator=gen, device="cuda") * 0.1).bfloat16()
+    w2 = (torch.randn(H, FF, generator=gen, device="cuda") * 0.1).bfloat16()
+    b1 = torch.randn(FF, generator=gen, device="cuda") * 0.1
+    b2 = torch.randn(H, generator=gen, device="cuda") * 0.1
+    g2, be2 = 1.0 + 0.1 * torch.randn(H, generator=gen, device="cuda"), 0.1 * torch.randn(H, generator=gen, device="cuda")
+    g3, be3 = 1.0 + 0.1 * torch.randn(H, generator=gen, device="cuda"), 0.1 * torch.randn(H, generator=gen, device="cuda")
+    x2 = ops.tc_gemm(ctx, wo, bias=bo, residual=x)["f32"]
+    y2, _, _ = ops.layernorm_fwd_bf16(x2, g2, be2)
+    a16 = ops.tc_gemm(y2, w1, bias=b1, act=ACT_GELU, out_f32=False, out_bf16=True)["bf16"]
+    want = ops.tc_gemm(a16, w2, bias=b2, residual=x2)["f32"]
+    want_ln, _, _ = ops.layernorm_fwd_bf16(want, g3, be3)
+    # (1) zero feed-forward weights: out = x2 + b2 exactly -> the prologue's arithmetic and the TMEM round trip of x2 are bit-exact
+    z1, z2 = torch.zeros_like(w1), torch.zeros_like(w2)
+    only_x2 = ops.tc_block_tail_fused(ctx, wo, bo, x, (g2, be2), z1, torch.zeros_like(b1), z2, b2)["f32"]
+    assert torch.equal(only_x2, x2 + b2)
+    # (2) the whole tail
+    got = ops.tc_block_tail_fused(ctx, wo, bo, x, (g2, be2), w1, b1, w2, b2, ln=(g3, be3))
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    assert float((got["f32"] - want).abs().max()) < 2e-2 * scale
+    assert float((got["f32"] - want).norm() / want.norm()) < 2e-3
+    assert float((got["ln16"].float() - want_ln.float()).norm() / want_ln.float().norm()) < 5e-3
+    # float64 restatement on the same bf16 operands, LayerNorm output rounded to bf16 where the kernels round it
+    x2d = x.double() + ctx.double() @ wo.double().t() + bo.double()
+    yd = torch.nn.functional.layer_norm(x2d, (H,), g2.double(), be2.double(), 1e-5).float().bfloat16().double()
+    zd = yd @ w1.double().t() + b1.double()
+    ad = (0.5 * zd * (1.0 + torch.erf(zd / math.sqrt(2.0)))).float().bfloat16().double()
+    ref = x2d + ad @ w2.double().t() + b2.double()
+    assert float((got["f32"].double() - ref).norm() / ref.norm()) < 2e-3
+    again = ops.tc_block_tail_fused(ctx, wo, bo, x, (g2, be2), w1, b1, w2, b2, ln=(g3, be3))
+    assert torch.equal(again["f32"], got["f32"]) and torch.equal(again["ln16"], got["ln16"])      # deterministic

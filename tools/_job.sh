@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 400 python bench.py --no-cpu > gpurun_out/bench_r2e.json 2> gpurun_out/bench_r2e.err; python tools/show_bench.py gpurun_out/bench_r2e.json | grep -v "^config\|^implementation" | cut -c1-600 | head -30
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_r2g.log 2>&1; tail -3 gpurun_out/gputests_r2g.log
+timeout 400 python bench.py --no-cpu > gpurun_out/bench_r2g.json 2> gpurun_out/bench_r2g.err; python tools/show_bench.py gpurun_out/bench_r2g.json | grep "^eval\|^value\|^ms_per" | cut -c1-300

@@ -35,6 +35,25 @@ def run(M, H, FF):
         res[f"gw{gw}_equal"] = bool(torch.equal(ops.tc_ffn_fused(y, w1, b1, w2, b2, x)["f32"], o_ref))
     res["fused_ln_ms"] = round(timeit(lambda: ops.tc_ffn_fused(y, w1, b1, w2, b2, x, ln=(gm, bt)), iters=20), 4)
     res["fused_ms"] = round(timeit(lambda: ops.tc_ffn_fused(y, w1, b1, w2, b2, x), iters=20), 4)
+    ops._lib.call("asme_b200_tc_ffn_tune", 0, 0)
+    ctx = torch.randn(M, H, device="cuda", generator=g).bfloat16()
+    wo = (torch.randn(H, H, device="cuda", generator=g) * 0.1).bfloat16()
+    bo = torch.randn(H, device="cuda", generator=g) * 0.1
+
+    def unfused_tail():
+        x2 = ops.tc_gemm(ctx, wo, bias=bo, residual=x)["f32"]
+        y2 = ops.layernorm_fwd_bf16(x2, gm, bt)[0]
+        a = ops.tc_gemm(y2, w1, bias=b1, act=1, out_f32=False, out_bf16=True)["bf16"]
+        o = ops.tc_gemm(a, w2, bias=b2, residual=x2)["f32"]
+        return o, ops.layernorm_fwd_bf16(o, gm, bt)[0]
+
+    res["tail_unfused_ms"] = round(timeit(unfused_tail, iters=20), 4)
+    res["tail_outproj_plus_fused_ffn_ms"] = round(timeit(lambda: ops.tc_ffn_fused(ops.layernorm_fwd_bf16(ops.tc_gemm(ctx, wo, bias=bo, residual=x)["f32"], gm, bt)[0], w1, b1, w2, b2, x, ln=(gm, bt)), iters=20), 4)
+    res["tail_fused_ms"] = round(timeit(lambda: ops.tc_block_tail_fused(ctx, wo, bo, x, (gm, bt), w1, b1, w2, b2, ln=(gm, bt)), iters=20), 4)
+    for gw in (2, 4):
+        ops._lib.call("asme_b200_tc_ffn_tune", 0, gw)
+        res[f"tail_fused_gw{gw}_ms"] = round(timeit(lambda: ops.tc_block_tail_fused(ctx, wo, bo, x, (gm, bt), w1, b1, w2, b2, ln=(gm, bt)), iters=20), 4)
+    ops._lib.call("asme_b200_tc_ffn_tune", 0, 0)
     res["fused_tflops"] = round(4.0 * M * H * FF / res["fused_ms"] / 1e9, 1)
     res["fused_ln_gbs"] = round(M * H * (2 + 4 + 4 + 2) / res["fused_ln_ms"] / 1e6, 1)
     print(json.dumps(res), flush=True)
