@@ -1,3 +1,7 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/gputests_r2g.log 2>&1; tail -3 gpurun_out/gputests_r2g.log
-timeout 400 python bench.py --no-cpu > gpurun_out/bench_r2g.json 2> gpurun_out/bench_r2g.err; python tools/show_bench.py gpurun_out/bench_r2g.json | grep "^eval\|^value\|^ms_per" | cut -c1-300
+timeout 400 python bench.py --no-cpu > gpurun_out/bench_r2h.json 2> gpurun_out/bench_r2h.err; tail -3 gpurun_out/bench_r2h.err | cut -c1-300; python - <<'P'
+import json
+d=json.loads(open('gpurun_out/bench_r2h.json').read().strip().splitlines()[-1])
+e=d['eval']
+print('eval', e['value'], e['ms_per_step'], e.get('batch_4096'))
+P
