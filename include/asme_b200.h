@@ -165,6 +165,10 @@ int asme_b200_layernorm_bwd(const float* dy, const float* x, const float* gamma,
 int asme_b200_layernorm_bwd_drop(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
                                  const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop,
                                  uint64_t seed, uint32_t site_a, uint32_t site_b, void* dx_bf16, asme_stream_t stream);
+/* dgb == NULL in the two calls above: the (gamma, beta) partials stay in ws as [asme_b200_layernorm_bwd_chunks(M, H)][2H] and
+ * asme_b200_rows_reduce(ws, chunks, 2H, dgb, 1) finishes them -- a leaf of the backward pass that can run on another stream. */
+int asme_b200_layernorm_bwd_chunks(int M, int H);
+int asme_b200_rows_reduce(const float* partial, int chunks, int N, float* out, int accumulate, asme_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K7/K9/K10/K11/K12  dense layers: C = epilogue(A x op(B)), fp32 SIMT path (strict 1e-5 parity mode)

@@ -64,6 +64,8 @@ _PROTOTYPES = {
     "asme_b200_layernorm_fwd_bf16": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "asme_b200_dropout_cast": (c_int, [P, c_longlong, c_float, c_uint64, c_uint32, c_uint32, P, P, P]),
     "asme_b200_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "asme_b200_layernorm_bwd_chunks": (c_int, [c_int, c_int]),
+    "asme_b200_rows_reduce": (c_int, [P, c_int, c_int, P, c_int, P]),
     "asme_b200_layernorm_bwd": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, P, P]),
     "asme_b200_layernorm_bwd_drop": (c_int, [P, P, P, P, c_int, c_int, P, P, P, P, c_size_t, c_float, c_uint64, c_uint32, c_uint32, P, P]),
     "asme_b200_gemm": (c_int, [P, P, P, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), P]),

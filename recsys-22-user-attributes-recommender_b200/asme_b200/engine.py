@@ -137,6 +137,10 @@ class EncoderEngine:
         self._side_keep.append(keep)
         return done
 
+    def _defer(self):
+        """``defer`` argument of the LayerNorm backward calls: the (gamma, beta) reductions are leaves -> second stream"""
+        return self.run_on_side if SIDE_STREAM_WGRAD else None
+
     def wait_table_grad(self):
         ev = getattr(self, "_table_event", None)
         if ev is not None:
@@ -298,7 +302,7 @@ class EncoderEngine:
             dgb2 = m.weights_span(f"{pre}.output_sublayer.norm.weight", f"{pre}.output_sublayer.norm.bias", (2, H), g)
             # ---- attention: x2 = x + drop1(ctx Wo^T + bo); the LayerNorm backward also emits do16 = bf16(dx2 * mask1)
             dx2, do16 = ops.layernorm_bwd_drop(dy2, ls.x2, self._w(f"{pre}.output_sublayer.norm.weight"), ls.st2, dgb2, dx3,
-                                               p, saved.seed, 0, self._site(l, 1))
+                                               p, saved.seed, 0, self._site(l, 1), defer=self._defer())
             self._wgrad(do16, ls.ctx16, self._w(f"{pre}.attention.output_linear.weight", True),
                          self._w(f"{pre}.attention.output_linear.bias", True))
             if ls.attn_tc:
@@ -319,10 +323,11 @@ class EncoderEngine:
             dgb1 = m.weights_span(f"{pre}.input_sublayer.norm.weight", f"{pre}.input_sublayer.norm.bias", (2, H), g)
             if l > 0:       # the gradient entering the layer below: its two dropped copies come out of this LayerNorm backward
                 dx, dy16n = ops.layernorm_bwd_drop(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, dx2,
-                                                   p, saved.seed, self._site(l - 1, 4), self._site(l - 1, 3))
+                                                   p, saved.seed, self._site(l - 1, 4), self._site(l - 1, 3), defer=self._defer())
                 pending = (dx, dy16n)
             else:
-                dx = ops.layernorm_bwd(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, d_residual=dx2)
+                dx = ops.layernorm_bwd(dy1, ls.x, self._w(f"{pre}.input_sublayer.norm.weight"), ls.st1, dgb1, d_residual=dx2,
+                                       defer=self._defer())
         return dx
 
     # ---------------------------------------------------------------- encoder blocks, strict fp32 path
@@ -422,8 +427,12 @@ class EncoderEngine:
         H = self.cfg.hidden
         g = self.m._arena.ensure_grad()
         dgb = self.m.weights_span(f"{MODIFIER}.transform.2.weight", f"{MODIFIER}.transform.2.bias", (2, H), g)
-        da = ops.layernorm_bwd(dy, a, self._w(f"{MODIFIER}.transform.2.weight"), st, dgb, n_live=n_live)
+        on_side = x.is_cuda and SIDE_STREAM_WGRAD
+        da = ops.layernorm_bwd(dy, a, self._w(f"{MODIFIER}.transform.2.weight"), st, dgb, n_live=n_live,
+                               defer=self.run_on_side if on_side else None)
         dz = ops.gelu_backward(da, z, n_live=n_live)
-        ops.gemm_wgrad(dz, x, self._w(f"{MODIFIER}.transform.0.weight", True), self._w(f"{MODIFIER}.transform.0.bias", True),
-                       m_live=n_live)
+        dw, db = self._w(f"{MODIFIER}.transform.0.weight", True), self._w(f"{MODIFIER}.transform.0.bias", True)
+        # the weight gradient is a leaf: second stream (its own scratch slot), off the dX chain
+        if not on_side or self.run_on_side(lambda: ops.gemm_wgrad(dz, x, dw, db, m_live=n_live, slot=1), keep=(dz, x)) is None:
+            ops.gemm_wgrad(dz, x, dw, db, m_live=n_live)
         return ops.gemm(dz, self._w(f"{MODIFIER}.transform.0.weight"), trans_b=False, m_live=n_live)

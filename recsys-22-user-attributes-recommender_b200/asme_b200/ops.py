@@ -296,33 +296,55 @@ def dropout_cast(x: torch.Tensor, p: float, seed: int, site_a: int, site_b: int,
     return y32, y16
 
 
-def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[torch.Tensor] = None, n_live=None):
-    """dx = d_residual + LN'(dy); accumulates (dgamma, dbeta) into dgb (2,H)."""
+def _ln_partials(M: int, H: int, device, defer):
+    """scratch of the (gamma, beta) partials: the shared workspace, or -- when the reduction is deferred to another stream -- a
+    buffer of its own that lives until that reduction has run"""
+    ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
+    if defer is None:
+        return workspace(ws_bytes, device)
+    return torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+
+
+def _ln_finish(ws, M: int, H: int, dgb: torch.Tensor, defer):
+    """``defer(fn, keep)`` (EncoderEngine.run_on_side) runs the reduction of the partials as a leaf on the second stream; when it
+    declines (returns None) the reduction runs here"""
+    if defer is None:
+        return
+    chunks = int(_lib.load().asme_b200_layernorm_bwd_chunks(M, H))
+
+    def reduce():
+        _lib.call("asme_b200_rows_reduce", _p(ws), chunks, 2 * H, _p(dgb), 1, _stream())
+    if defer(reduce, (ws, dgb)) is None:
+        reduce()
+
+
+def layernorm_bwd(dy, x, gamma, stats, dgb: torch.Tensor, d_residual: Optional[torch.Tensor] = None, n_live=None, defer=None):
+    """dx = d_residual + LN'(dy); accumulates (dgamma, dbeta) into dgb (2,H).  ``defer``: see :func:`_ln_finish`."""
     dy, x = _f32(dy), _f32(x)
     M, H = x.shape
     dx = torch.empty_like(x)
-    ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
-    ws = workspace(ws_bytes, x.device)
+    ws = _ln_partials(M, H, x.device, defer)
     if _lib.timing is not None:
         _lib.note = f"M={_note_rows(M, n_live)},H={H},res={int(d_residual is not None)}"
-    _lib.call("asme_b200_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
-              _p(ws), ws.numel(), _p(n_live), _stream())
+    _lib.call("asme_b200_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx),
+              _p(dgb) if defer is None else None, _p(ws), ws.numel(), _p(n_live), _stream())
+    _ln_finish(ws, M, H, dgb, defer)
     return dx
 
 
-def layernorm_bwd_drop(dy, x, gamma, stats, dgb: torch.Tensor, d_residual, p: float, seed: int, site_a: int, site_b: int):
+def layernorm_bwd_drop(dy, x, gamma, stats, dgb: torch.Tensor, d_residual, p: float, seed: int, site_a: int, site_b: int, defer=None):
     """LayerNorm backward fused with the dropout_cast of the next backward stage:
     returns (dx = (d_residual + LN'(dy)) * mask_a as fp32, bf16(dx * mask_b)); site 0 = no mask"""
     dy, x = _f32(dy), _f32(x)
     M, H = x.shape
     dx = torch.empty_like(x)
     dx16 = torch.empty(M, H, dtype=torch.bfloat16, device=x.device)
-    ws_bytes = _lib.query("asme_b200_layernorm_bwd_workspace_bytes", M, H)
-    ws = workspace(ws_bytes, x.device)
+    ws = _ln_partials(M, H, x.device, defer)
     if _lib.timing is not None:
         _lib.note = f"M={M},H={H},res={int(d_residual is not None)},drop=1"
-    _lib.call("asme_b200_layernorm_bwd_drop", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx), _p(dgb),
-              _p(ws), ws.numel(), float(p), int(seed), int(site_a), int(site_b), _p(dx16), _stream())
+    _lib.call("asme_b200_layernorm_bwd_drop", _p(dy), _p(x), _p(gamma), _p(stats), M, H, _p(d_residual), _p(dx),
+              _p(dgb) if defer is None else None, _p(ws), ws.numel(), float(p), int(seed), int(site_a), int(site_b), _p(dx16), _stream())
+    _ln_finish(ws, M, H, dgb, defer)
     return dx, dx16
 
 
@@ -353,13 +375,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_b: bool = True, bias=None, act:
 
 
 def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], accumulate: bool = True,
-               m_live=None):
-    """dW (+)= dY^T X, dbias (+)= colsum(dY)."""
+               m_live=None, slot: int = 0):
+    """dW (+)= dY^T X, dbias (+)= colsum(dY).  ``slot``: scratch buffer (calls issued on different streams must not share one)"""
     dy, x = _f32(dy), _f32(x)
     M, N = dy.shape
     K = x.shape[1]
     ws_bytes = _lib.query("asme_b200_gemm_wgrad_workspace_bytes", M, N, K)
-    ws = workspace(ws_bytes, x.device)
+    ws = workspace(ws_bytes, x.device, slot)
     if _lib.timing is not None:
         _lib.note = f"M={_note_rows(M, m_live)},N={N},K={K}"
     _lib.call("asme_b200_gemm_wgrad", _p(dy), _p(x), M, N, K, _p(dw), _p(dbias), 1 if accumulate else 0, _p(ws),

@@ -810,7 +810,9 @@ extern "C" int asme_b200_layernorm_bwd_drop(const float* dy, const float* x, con
 static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, const float* stats, int M, int H,
                               const float* d_residual, float* dx, float* dgb, void* ws, size_t ws_bytes, float p_drop, uint64_t seed,
                               uint32_t site_a, uint32_t site_b, void* dx_bf16, const int32_t* n_live, asme_stream_t stream) {
-    ASME_REQUIRE(dy && x && gamma && stats && dx && dgb, "layernorm_bwd: null argument");
+    // dgb == NULL: the (gamma, beta) partials stay in ``ws`` -- [asme_b200_layernorm_bwd_chunks(M,H)][2H] -- and the caller reduces them
+    // later with asme_b200_rows_reduce (the reduction is a leaf of the backward pass: second stream / parallel graph branch)
+    ASME_REQUIRE(dy && x && gamma && stats && dx, "layernorm_bwd: null argument");
     if (M == 0) return ASME_OK;
     const int lanes = lanes_for(H);
     const int groups = 256 / lanes;
@@ -828,7 +830,21 @@ static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamm
     DISPATCH_H(H, CALL)
 #undef CALL
     ASME_LAUNCH_OK();
-    colsum_stage2_kernel<<<ceil_div(2 * H, 32), 1024, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
+    if (dgb != nullptr) {
+        colsum_stage2_kernel<<<ceil_div(2 * H, 32), 1024, 0, (cudaStream_t)stream>>>(partials, grid, 2 * H, dgb, 1);
+        ASME_LAUNCH_OK();
+    }
+    return ASME_OK;
+}
+extern "C" int asme_b200_layernorm_bwd_chunks(int M, int H) {
+    if (M <= 0 || H < 16) return 0;
+    return rowwise_bwd_grid(M, 256 / lanes_for(H));
+}
+// out[n] (+)= sum over the chunks of partial[chunk][n]: the second stage of the column reductions, as its own launch
+extern "C" int asme_b200_rows_reduce(const float* partial, int chunks, int N, float* out, int accumulate, asme_stream_t stream) {
+    ASME_REQUIRE(partial && out && chunks >= 0 && N >= 1, "rows_reduce: bad argument");
+    if (chunks == 0) return ASME_OK;
+    colsum_stage2_kernel<<<ceil_div(N, 32), 1024, 0, (cudaStream_t)stream>>>(partial, chunks, N, out, accumulate);
     ASME_LAUNCH_OK();
     return ASME_OK;
 }
