@@ -457,7 +457,8 @@ int asme_b200_tc_attn_bwd(const void* qkv, const uint8_t* key_valid, int B, int 
                           const uint32_t* keep_bits, void* d_qkv, asme_stream_t stream);
 /* diagnostic: knob 0 selects the backward kernel (1 = single sweep, default; 0 = two sweeps), knob 1 the epilogue warpgroups of the
  * single-sweep kernel (2 or 4), knob 2 the forward kernel (2 = probabilities in tensor memory as the A operand of the second MMA,
- * two CTAs per SM, default when the grid fills the machine; 1 = probabilities through shared memory); results agree to rounding */
+ * two CTAs per SM, default when the grid fills the machine; 3 = the same for every grid size; 1 = probabilities through shared memory);
+ * results agree to rounding */
 int asme_b200_tc_attn_tune(int knob, int value);
 
 /* ------------------------------------------------------------------------------------------

@@ -617,7 +617,7 @@ static int tc_attn_fwd_impl(const void* qkv, const uint8_t* key_valid, int B, in
     a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits; a.only_row = only_row;
     // second kernel whenever the grid fills the machine: with fewer CTAs than SMs nothing shares an SM and the first kernel's two
     // softmax warpgroups per CTA are the shorter critical path (64 x 256 x 64: 0.077 vs 0.091 ms; 1024 x 200 x 128: 0.165 vs 0.112 ms)
-    if (g_attn_fwd_variant == 2 && (long long)B * (H / 64) >= ASME_NUM_SMS) {
+    if (g_attn_fwd_variant == 3 || (g_attn_fwd_variant == 2 && (long long)B * (H / 64) >= ASME_NUM_SMS)) {
         const size_t smem2 = 1024 + 3 * 32768 + sizeof(AttnFwd2Shared);
         { const int _rc = asme_ensure_max_smem((const void*)attn_tc_fwd2_kernel); if (_rc) return _rc; }
         attn_tc_fwd2_kernel<<<dim3(B, H / 64), ATF2_THREADS, smem2, (cudaStream_t)stream>>>(tm, a);
@@ -1208,7 +1208,7 @@ extern "C" int asme_b200_tc_attn_tune(int knob, int value) {
         ASME_REQUIRE(value == 2 || value == 4, "tc_attn_tune: knob 1 (epilogue warpgroups of the single-sweep backward) takes 2 or 4");
         g_attn_bwd_wgs = value;
     } else if (knob == 2) {
-        ASME_REQUIRE(value == 1 || value == 2, "tc_attn_tune: knob 2 (forward kernel) takes 1 or 2");
+        ASME_REQUIRE(value >= 1 && value <= 3, "tc_attn_tune: knob 2 (forward kernel) takes 1, 2 or 3 (3: the second kernel for every grid size)");
         g_attn_fwd_variant = value;
     } else {
         ASME_REQUIRE(false, "tc_attn_tune: unknown knob %d", knob);
