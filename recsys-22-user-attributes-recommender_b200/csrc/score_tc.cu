@@ -214,6 +214,9 @@ struct ScoreTcArgs {
                                  // its threshold and starts the next part with an empty list.  Many row tiles (a rank of the vocab-sharded
                                  // evaluation scores ALL users against its slice) then need neither 16 short-lived CTAs per row tile (7 waves,
                                  // each paying the insertion storm of an unseeded list) nor a threshold pass.
+    int unfolded;                // 1: every epilogue thread writes its own list (slot (split * WGS + warpgroup)) although the CTA sweeps a single
+                                 // part: 4 lists per CTA, so 5..15 natural catalog splits already give the union its 16+ lists and the catalog
+                                 // need not be cut into 16 splits (256 CTAs = 1.73 waves at 2048 rows)
     int tile_step;               // 0 / 1: a split sweeps a contiguous range of tiles; S > 1: split s sweeps tiles s, s+S, s+2S, ... (round
                                  // robin: whatever order the catalog is in, every split sees an even share of the best items)
 };
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
     const int split = blockIdx.y;
     const int tstep = a.tile_step > 1 ? a.tile_step : 1;
     const int nseq = a.seq_parts > 1 ? a.seq_parts : 1;          // parts this CTA sweeps one after the other
+    const bool unfolded = nseq > 1 || a.unfolded != 0;           // per-thread lists go out as they are (top-k sweeps only)
     // first / end tile of sequential part pp (pp = 0 when the CTA has one part)
     auto part_t0 = [&](int pp) {
         return tstep > 1 ? min(a.n_tiles, split * nseq + pp + a.tile_lo * tstep) : min(a.n_tiles, split * a.tiles_per_split + a.tile_lo);
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
             bb_cur0 = bb_nxt0; bb_cur1 = bb_nxt1;
         }
-        if (TOPK && nseq > 1) {       // end of a sequential part: this thread's own list goes out, its tail seeds the next part
+        if (TOPK && unfolded) {       // end of a (sequential) part: this thread's own list goes out, its tail seeds the next part
             pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
             if (row_ok) {
                 const size_t o = ((size_t)a.part0 + (size_t)(split * nseq + pp) * WGS + wg) * a.R + row;
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
         if (TOPK) pend_drain<KL>(lv, li, thr, thr0, cnt, pend, WGS * 128);
         // --- fold the warpgroups' results into warpgroup 0 through the table ring (idle: every MMA of this CTA has completed),
         //     so that the CTA emits ONE partial result per row
-        if (EPI != EPI_PROBE && nseq == 1) {
+        if (EPI != EPI_PROBE && !(TOPK && unfolded)) {
             constexpr int SLOTS = EPI == EPI_CE ? 2 : (2 * KL + 2);       // 32-bit words staged per row and warpgroup
             uint32_t* xs = reinterpret_cast<uint32_t*>(sB);               // [WGS-1][SLOTS][128]
             if (wg > 0) {
@@ -738,7 +742,7 @@ __global__ void __launch_bounds__(TC_THREADS(WGS), 1) score_tc_kernel(const __gr
             }
         }
         // --- write this split's partial results ---
-        if (row_ok && wg == 0 && nseq == 1) {
+        if (row_ok && wg == 0 && !(TOPK && unfolded)) {
             const size_t part = (size_t)a.part0 + (size_t)split;
             const size_t o = part * a.R + row;
             if (EPI == EPI_CE) {
@@ -1231,10 +1235,11 @@ static int cand_list_len(int k) { return k <= 2 ? 5 : 10; }      // thread-list 
 // seq (out): sequential parts per CTA.  When the row tiles alone (nearly) fill the machine the natural split count is below
 // CAND_MIN_PARTS; instead of cutting the catalog into 16 short-lived CTAs per row tile, every CTA sweeps ``seq`` parts in turn and
 // its four warpgroups write their lists unfolded: splits * seq * WGS lists per row (ScoreTcArgs::seq_parts).
-static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* use_union, int* seq) {
+static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* use_union, int* seq, int* unfolded = nullptr) {
     int rc = make_plan(R, Kp, Vloc, p, true);
     if (rc) return rc;
     *seq = 1;
+    if (unfolded) *unfolded = 0;
     *use_union = k <= 10 && !p->pair && p->n_tiles >= CAND_MIN_PARTS;
     if (*use_union && p->splits < CAND_MIN_PARTS) {
         // measured on one GPU with the slice shapes of G ranks (1024 G rows x 1 000 003 / G items): G = 8 (2 natural splits)
@@ -1246,6 +1251,11 @@ static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* us
             *seq = sq;
             p->tiles_per_split = ceil_div(p->n_tiles, p->splits * sq);      // tiles per PART
             p->parts = p->splits * sq * p->wgs;                            // lists per row
+        } else if (g_cand_seq && unfolded && p->wgs == 4 && p->splits * p->wgs >= CAND_MIN_PARTS) {
+            // 5..15 natural splits (a 2-rank slice: 2048 rows): keep them -- one wave of CTAs -- and let the four warpgroups of
+            // every CTA write their lists unfolded: splits * 4 >= 16 lists per row, threshold pass as usual
+            *unfolded = 1;
+            p->parts = p->splits * p->wgs;
         } else {
             p->tiles_per_split = ceil_div(p->n_tiles, CAND_MIN_PARTS);
             p->splits = ceil_div(p->n_tiles, p->tiles_per_split);
@@ -1259,8 +1269,8 @@ extern "C" size_t asme_b200_tc_score_candidates_workspace_bytes(int R, int Kp, i
     if (R < 1) R = 1;
     ScorePlan p;
     bool use_union = false;
-    int seq = 1;
-    if (make_cand_plan(R, Kp, Vloc, k, &p, &use_union, &seq)) return 0;
+    int seq = 1, unf = 0;
+    if (make_cand_plan(R, Kp, Vloc, k, &p, &use_union, &seq, &unf)) return 0;
     const size_t classic = asme_b200_tc_score_topk_workspace_bytes(R, Kp, Vloc, 32) + (size_t)R * 32 * 8;
     const size_t lists = (size_t)(p.parts > p.splits ? p.parts : p.splits) + MAX_EPI_WGS;
     const size_t uni = (size_t)2 * lists * MAX_EPI_WGS * R * ((size_t)kk * 8 + 8) + (size_t)R * kk * 8;
@@ -1279,8 +1289,8 @@ extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, cons
     cudaStream_t st = (cudaStream_t)stream;
     ScorePlan p;
     bool use_union = false;
-    int seq = 1;
-    int rc = make_cand_plan(R, Kp, Vloc, k, &p, &use_union, &seq);
+    int seq = 1, unfolded = 0;
+    int rc = make_cand_plan(R, Kp, Vloc, k, &p, &use_union, &seq, &unfolded);
     if (rc) return rc;
     const int kl = cand_list_len(k);          // entries of the sweep's lists (>= k)
     if (!use_union) {          // classic: the true bf16 top 32 (the longest thread lists); unused candidate slots stay empty
@@ -1312,7 +1322,7 @@ extern "C" int asme_b200_tc_score_candidates(const void* Hb, int R, int Kp, cons
     const int total_parts = n_sample > 0 ? 2 * p.parts : p.parts;
     ScoreTcArgs a{};
     a.R = R; a.Vloc = Vloc; a.v0 = v0; a.k = kl; a.kch = p.kch; a.stages = p.stages; a.last_ksteps = p.last_ksteps; a.tail16 = p.tail16; a.pend_cap = g_pend_cap;
-    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_step = p.splits * seq; a.seq_parts = seq;
+    a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.tile_step = p.splits * seq; a.seq_parts = seq; a.unfolded = unfolded;
     a.bias = bias; a.bias_bounds = reinterpret_cast<const float2*>(bias_bounds); a.target = target; a.target_score = nullptr; a.thr_floor = g_thr_floor;
     a.pv = (float*)ws;
     a.pi = (int*)(a.pv + (size_t)total_parts * R * kl);

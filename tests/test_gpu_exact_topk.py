@@ -183,7 +183,7 @@ def test_exact_topk_with_the_bias_bounded_per_chunk(R, V, H, k, sigma_b):
     assert torch.equal(torch.clamp(out["rank"], max=k + 1), torch.clamp(rank, max=k + 1).to(torch.int32))
 
 
-@pytest.mark.parametrize("R,V,k", [(2500, 70001, 10), (8192, 125001, 10), (1100, 40000, 3)])
+@pytest.mark.parametrize("R,V,k", [(2500, 70001, 10), (8192, 125001, 10), (4096, 250001, 10), (1100, 40000, 3)])
 def test_exact_topk_with_many_row_tiles(R, V, k):
     """a rank of the vocab-sharded evaluation scores ALL users of the box against its slice: so many row tiles that the catalog is
     not cut into 16 CTAs per row tile -- every CTA sweeps several parts in turn and its warpgroups write their lists unfolded

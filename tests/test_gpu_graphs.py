@@ -176,3 +176,29 @@ def test_module_eval_graph_option_gives_the_same_metrics():
         for a, b in zip(s0, s1):
             assert set(a) == set(b) and all(torch.equal(a[k].float().cpu(), b[k].float().cpu()) for k in a)
         assert all(torch.equal(e0[k].cpu(), e1[k].cpu()) for k in e0)
+
+
+def test_second_stream_leaves_do_not_change_a_single_bit(monkeypatch):
+    """the leaves of the backward pass that run on the second stream / as parallel graph branches -- encoder weight gradients, the
+    catalog-gradient sweep, the id sort, the (gamma, beta) reductions of every LayerNorm backward, the modifier's weight gradient --
+    are the same kernels with the same order of additions per destination: losses and weights after several steps equal the
+    one-stream run bit for bit"""
+    from asme_b200 import engine
+    V, S, B = 503, 40, 32
+    batches = _fresh_batches(6, B, S, V, seed=11)
+    runs = {}
+    for side in (True, False):
+        monkeypatch.setattr(engine, "SIDE_STREAM_WGRAD", side)
+        module, opt = _setup(seed=5)
+        losses = []
+        for i, batch in enumerate(batches):
+            opt.zero_grad()
+            out = module.training_step(batch, i)
+            out["loss"].backward()
+            opt.step()
+            losses.append(float(out["loss"].detach()))
+        torch.cuda.synchronize()
+        runs[side] = (losses, {n: p.detach().clone() for n, p in module.model.named_parameters()})
+    assert runs[True][0] == runs[False][0]
+    for n, p in runs[True][1].items():
+        assert torch.equal(p, runs[False][1][n]), n
