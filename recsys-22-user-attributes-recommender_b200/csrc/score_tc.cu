@@ -1245,7 +1245,7 @@ static int make_cand_plan(int R, int Kp, int Vloc, int k, ScorePlan* p, bool* us
         // measured on one GPU with the slice shapes of G ranks (1024 G rows x 1 000 003 / G items): G = 8 (2 natural splits)
         // 0.53 vs 0.87 ms; G = 2 (9 natural splits) 0.475 vs 0.415 ms -- the first scheme's threshold pass wins while a row tile
         // still gets several CTAs
-        if (g_cand_seq && p->wgs == 4 && p->splits <= 4 && p->n_tiles >= 4 * CAND_MIN_PARTS) {
+        if (g_cand_seq && p->wgs == 4 && p->splits <= 3 && p->n_tiles >= 4 * CAND_MIN_PARTS) {
             int sq = ceil_div(CAND_MIN_PARTS, p->splits * p->wgs);
             if (sq < 2) sq = 2;            // (seq = 1 would be the folded single-part kernel path)
             *seq = sq;
