@@ -43,10 +43,27 @@ __device__ __forceinline__ uint32_t at_pack(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// dropout threshold of the tensor-core attention forward as the bit-sliced comparison wants it (see drop_keep_bits32)
+struct DropPlan {
+    uint32_t t[16];              // t[i] = bit i of the 16-bit threshold, replicated to 32 bits
+    int low;                     // lowest set bit of the threshold (planes below it cannot change the outcome)
+};
+static DropPlan make_drop_plan(float p_drop) {
+    DropPlan d{};
+    uint32_t thr16 = (uint32_t)(p_drop * 65536.0f + 0.5f);
+    if (thr16 > 65535u) thr16 = 65535u;
+    d.low = 16;
+    for (int i = 15; i >= 0; --i) {
+        d.t[i] = ((thr16 >> i) & 1u) ? 0xffffffffu : 0u;
+        if (d.t[i]) d.low = i;
+    }
+    return d;
+}
 struct AttnTcArgs {
     const uint8_t* key_valid;    // (B,S) or NULL
     int B, S, heads, d, H, causal;
     float scale, p_drop, inv_keep;
+    DropPlan drop;
     unsigned long long seed;
     unsigned int site;
     __nv_bfloat16* ctx;          // (B*S, H)
@@ -66,26 +83,58 @@ struct __align__(8) AttnBars {
 };
 
 // ---- dropout stream of the tensor-core attention ----------------------------------------------------------------
-// Two 16-bit keep decisions per 32-bit hash (lowbias32 finaliser) of (row key, 32-key chunk, pair): ~5 instructions per
-// element instead of ~15 for an element-indexed Philox4x32-7.  The backward pass never regenerates the stream -- the forward
-// stores the keep bits (1 bit per (query, key)) -- so the only contract is "Bernoulli(1-p), independent per element".
+// The backward pass never regenerates the stream -- the forward stores the keep bits (1 bit per (query, key)) -- so the only
+// contract is "Bernoulli(1 - thr16 / 65536), independent per element" (thr16 = p * 65536 rounded).  The bits of a 32-key chunk are
+// drawn BIT-SLICED: plane i is one 32-bit hash word whose bit c is bit i of key c's 16-bit uniform number u_c, and keep_c =
+// (u_c >= thr16) falls out of one logic operation per plane on all 32 keys at once -- the keep word needs no per-key extraction,
+// compare and re-assembly (those were 8 of the 13.5 instructions per element of the dropout softmax, nearly all on the half-rate
+// integer pipe; now 3.5 -- the kernel time did not move, the forward is not issue-bound: DESIGN.md section 6).  Planes below the lowest
+// set bit of thr16 cannot change the outcome and are not drawn (p = 0.5: one plane).
+// Plane words: (row key + counter * golden ratio) through multiply - xorshift - multiply - xorshift (the row key is a full lowbias32
+// mix of (seed, site, row); one round less leaves consecutive planes correlated); tests/test_gpu_tc_attention.py checks keep rates
+// and adjacent-key / adjacent-row / adjacent-head independence.
+#define DROP_K1 0x21f0aaadu
+#define DROP_K2 0x735a2d97u
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
     x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
     return x;
 }
 __device__ __forceinline__ uint32_t drop_rowkey(uint64_t seed, uint32_t site, uint64_t row) {
-    return lowbias32((uint32_t)row ^ (uint32_t)seed) ^ lowbias32((uint32_t)(row >> 32) ^ (uint32_t)(seed >> 32) ^ (site * 0x9E3779B9u));
+    return (lowbias32((uint32_t)row ^ (uint32_t)seed) ^ lowbias32((uint32_t)(row >> 32) ^ (uint32_t)(seed >> 32) ^ (site * 0x9E3779B9u))) * DROP_K1;
 }
-// keep bits of the 32 keys of chunk `ch` of one row (bit c = key ch*32+c survives)
-__device__ __forceinline__ uint32_t drop_keep_bits32(uint32_t rowkey, int ch, uint32_t thr16) {
-    uint32_t kb = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t x = lowbias32(rowkey + (uint32_t)(ch * 16 + j) * 0x9E3779B9u);
-        kb |= ((x & 0xffffu) >= thr16 ? 1u : 0u) << (2 * j);
-        kb |= ((x >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+// keep bits of the 32 keys of chunk `ch` of one row (bit c = key ch*32+c survives).  Plane word n of chunk ch mixes x = rowkey +
+// (16 ch + n) * golden: multiply, xorshift, multiply, xorshift (the first multiply is distributed: rowkey * K1 once per row).
+// u < thr is the borrow of u - thr rippling up from the lowest set threshold bit: borrow' = t ? (borrow | ~u) : (borrow & ~u), ONE
+// three-input logic operation per plane with the threshold mask t (all ones / all zeros) read from the kernel parameters.
+#define DROP_PLANE(i)                                                                   \
+    {                                                                                   \
+        uint32_t r = base + (uint32_t)(i) * (0x9E3779B9u * DROP_K1);                    \
+        r ^= r >> 15; r *= DROP_K2; r ^= r >> 16;                                       \
+        borrow = (borrow & ~r) | (dp.t[i] & (borrow | ~r));                             \
     }
-    return kb;
+__device__ __forceinline__ uint32_t drop_keep_bits32(uint32_t rowkey_k1, int ch, const DropPlan& dp) {
+    uint32_t borrow = 0u;
+    const uint32_t base = rowkey_k1 + (uint32_t)(ch * 16) * (0x9E3779B9u * DROP_K1);
+    switch (dp.low) {            // uniform; falls through the planes from the lowest set threshold bit upwards
+        case 0: DROP_PLANE(0)
+        case 1: DROP_PLANE(1)
+        case 2: DROP_PLANE(2)
+        case 3: DROP_PLANE(3)
+        case 4: DROP_PLANE(4)
+        case 5: DROP_PLANE(5)
+        case 6: DROP_PLANE(6)
+        case 7: DROP_PLANE(7)
+        case 8: DROP_PLANE(8)
+        case 9: DROP_PLANE(9)
+        case 10: DROP_PLANE(10)
+        case 11: DROP_PLANE(11)
+        case 12: DROP_PLANE(12)
+        case 13: DROP_PLANE(13)
+        case 14: DROP_PLANE(14)
+        case 15: DROP_PLANE(15)
+        default: break;
+    }
+    return ~borrow;              // keep = not (u < thr)
 }
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -197,7 +246,6 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
         const int ch_hi = wg == 0 ? (n_chunks + 1) / 2 : n_chunks;
         const float cs = a.scale * LOG2E;                    // exp(x) = exp2(x * log2e); the row max itself stays in natural units so
                                                              // that a fully masked row's max is EXACTLY -1e9 (no cancellation error)
-        const uint32_t thr16 = (uint32_t)(a.p_drop * 65536.0f + 0.5f);
         for (int u = 0; u < units; ++u) {
             const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
             const int head = slice * hps + hh;
@@ -280,7 +328,7 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_fwd_kernel(const __gri
                     }
                 }
                 if (a.p_drop > 0.f) {
-                    const uint32_t kb = drop_keep_bits32(rowkey, ch, thr16);
+                    const uint32_t kb = drop_keep_bits32(rowkey, ch, a.drop);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] = ((kb >> c) & 1u) ? v[c] * a.inv_keep : 0.f;
                     if (a.keep_bits && q_ok) a.keep_bits[((size_t)bh * S + qi) * 8 + ch] = kb;
@@ -441,7 +489,6 @@ __global__ void __launch_bounds__(ATF2_THREADS, 2) attn_tc_fwd2_kernel(const __g
         asm volatile("bar.sync 1, 128;" ::: "memory");       // the four softmax warps only
         const int n_chunks = (NS + 31) / 32;
         const float cs = a.scale * LOG2E;
-        const uint32_t thr16 = (uint32_t)(a.p_drop * 65536.0f + 0.5f);
         for (int u = 0; u < units; ++u) {
             const int hh = u / n_qt, qt = qt_only >= 0 ? qt_only : u % n_qt;
             const int head = slice * hps + hh;
@@ -531,7 +578,7 @@ __global__ void __launch_bounds__(ATF2_THREADS, 2) attn_tc_fwd2_kernel(const __g
                     }
                 }
                 if (a.p_drop > 0.f) {
-                    const uint32_t kb = drop_keep_bits32(rowkey, ch, thr16);
+                    const uint32_t kb = drop_keep_bits32(rowkey, ch, a.drop);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] = ((kb >> c) & 1u) ? v[c] * a.inv_keep : 0.f;
                     if (a.keep_bits && q_ok) a.keep_bits[((size_t)bh * S + qi) * 8 + ch] = kb;
@@ -615,6 +662,7 @@ static int tc_attn_fwd_impl(const void* qkv, const uint8_t* key_valid, int B, in
     a.key_valid = key_valid; a.B = B; a.S = S; a.heads = heads; a.d = d; a.H = H; a.causal = causal;
     a.scale = 1.0f / sqrtf((float)d); a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     a.seed = seed; a.site = site; a.ctx = (__nv_bfloat16*)ctx; a.stats = stats; a.keep_bits = keep_bits; a.only_row = only_row;
+    a.drop = make_drop_plan(p_drop);
     // second kernel whenever the grid fills the machine: with fewer CTAs than SMs nothing shares an SM and the first kernel's two
     // softmax warpgroups per CTA are the shorter critical path (64 x 256 x 64: 0.077 vs 0.091 ms; 1024 x 200 x 128: 0.165 vs 0.112 ms)
     if (g_attn_fwd_variant == 3 || (g_attn_fwd_variant == 2 && (long long)B * (H / 64) >= ASME_NUM_SMS)) {

@@ -60,6 +60,64 @@ def norm_err(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
 
 
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("pad", ["right", "left"])
+def test_tc_attn_fwd_scores_far_above_the_first_block(ops, causal, pad):
+    """Rows whose largest score sits far (~ +90) above everything in the first key blocks, late in the sequence: the softmax of the
+    tensor-core forward (exp2 of score - row maximum, bf16 probabilities in tensor memory) and its saved statistics must be those of
+    the reference softmax (transformer_layers.py:145-155), next to ordinary sequences in the same launch, with right and with left
+    padding (first blocks of padding keys only), causal or not."""
+    B, S, heads, d = 4, 200, 2, 32
+    H = heads * d
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    qkv, valid = make(gen, B, S, heads, d, pad=pad)
+    x = qkv.float().view(B, S, 3, heads, d)
+    for b, q_rows, key in ((1, slice(60, 140), 185), (2, slice(0, 200), 199), (2, slice(150, 200), 97)):
+        valid[b] = True
+        u = torch.randn(d, generator=gen, device="cuda")
+        u = u / u.norm()
+        x[b, q_rows, 0, 1] += 22.0 * u                          # queries of head 1 ...
+        x[b, key, 1, 1] = 23.0 * u                              # ... and one key: score ~ 22 * 23 / sqrt(32) = 89
+    qkv = x.view(B * S, 3 * H).bfloat16()
+    _, rst = ops.attn_fwd(qkv.float(), valid, B, S, heads, causal, 0.0, 77, 19, save_stats=True)
+    ref = torch_attention(qkv, valid, B, S, heads, causal)
+    got, gst, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, 0.0, 77, 19, save_stats=True)
+    assert norm_err(got, ref) < 4e-3
+    torch.testing.assert_close(got.float(), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+    torch.testing.assert_close(gst[0], rst[0], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gst[1], rst[1], rtol=1e-4, atol=1e-5)
+    again, gst2, _ = ops.tc_attn_fwd(qkv, valid, B, S, heads, causal, 0.0, 77, 19, save_stats=True)
+    assert torch.equal(got, again) and torch.equal(gst, gst2)
+
+
+@pytest.mark.parametrize("p_drop", [0.5, 0.25, 0.2, 0.1, 0.01])
+def test_tc_attn_dropout_stream_is_bernoulli(ops, p_drop):
+    """The keep bits are drawn bit-sliced (one hash word per bit plane of 32 keys' uniform numbers, attention_tc.cu): check the
+    keep rate (5 sigma), the independence of adjacent keys, of keys 32 apart (same bit of adjacent words), of adjacent
+    queries and of adjacent heads, and that two sites / seeds are unrelated.  Reference: nn.Dropout on the attention
+    probabilities (transformer_layers.py:152-153) -- Bernoulli(1 - p) per element, kept values scaled by 1 / (1 - p)."""
+    B, S, heads, d = 8, 256, 4, 16
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    qkv, _ = make(gen, B, S, heads, d)
+    _, _, keep = ops.tc_attn_fwd(qkv, None, B, S, heads, False, p_drop, 1234, 5, save_stats=True)
+    km = unpack_keep(keep, B, heads, S).double()                   # (B, heads, S, S)
+    n = km.numel()
+    q = 1.0 - round(p_drop * 65536) / 65536
+    var = q * (1 - q)
+    assert abs(float(km.mean()) - q) < 5 * (var / n) ** 0.5
+    c = km - q
+    tol = 5 / n ** 0.5
+    assert abs(float((c[..., 1:] * c[..., :-1]).mean()) / var) < tol            # adjacent keys
+    assert abs(float((c[..., 32:] * c[..., :-32]).mean()) / var) < tol          # same bit, adjacent 32-key words
+    assert abs(float((c[:, :, 1:] * c[:, :, :-1]).mean()) / var) < tol          # adjacent queries
+    assert abs(float((c[:, 1:] * c[:, :-1]).mean()) / var) < tol                # adjacent heads
+    assert float((km.mean(dim=(0, 1, 2)) - q).abs().max()) < 6 * (var / (n / S)) ** 0.5   # no key position is special
+    for seed, site in ((1235, 5), (1234, 6)):
+        _, _, other = ops.tc_attn_fwd(qkv, None, B, S, heads, False, p_drop, seed, site, save_stats=True)
+        co = unpack_keep(other, B, heads, S).double() - q
+        assert abs(float((c * co).mean()) / var) < tol
+
+
 @pytest.mark.parametrize("B,S,heads,d", CASES)
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("p_drop", [0.0, 0.2])

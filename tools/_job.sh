@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-timeout 300 python tools/perf_exact.py 4096 250001 2>&1 | grep -i "candidate sweep\|uncert" | head -5
-timeout 600 python -m pytest tests/test_gpu_exact_topk.py -x -q > gpurun_out/t15.log 2>&1; tail -2 gpurun_out/t15.log
+./tools/microbench/tmem_read_bw
+python -m pytest tests/test_gpu_tc_attention.py -x -q > gpurun_out/t16.log 2>&1; tail -3 gpurun_out/t16.log
