@@ -700,8 +700,9 @@ struct AttnBwdArgs {
     __nv_bfloat16* d_qkv;          // (B*S, 3H)
 };
 struct __align__(16) AttnBwdShared {
-    float4 qc[AT_MAXS];            // per query of the current head: {rowmax * log2e, 1 / rowsum, D = sum_d dO.O, exp(-1e9 - rowmax)}
-    uint32_t keep[AT_MAXS * 8];    // dropout keep bits of the current head
+    float4 qc[2 * AT_MAXS];        // per query of the current head (single-sweep kernel: of the current PAIR of heads, head-major):
+                                   // {rowmax * log2e, 1 / rowsum, D = sum_d dO.O, exp(-1e9 - rowmax)}
+    uint32_t keep[2 * AT_MAXS * 8];// dropout keep bits, same indexing
     uint64_t loaded, t_full, x_full, acc_done;
     uint32_t tmem_base;
     uint32_t kvb[8];
@@ -990,7 +991,17 @@ __global__ void __launch_bounds__(ATF_THREADS, 1) attn_tc_bwd_kernel(const __gri
 // its own dQ accumulator: tensor memory = 2 x 128 (T1, T2) + (2 + n_t) x d <= 512 columns.
 // ------------------------------------------------------------------------------------------------------------
 // WGS epilogue warpgroups (2 or 4), each owning 128 / WGS columns of a sub-tile: the element-wise stage is latency-bound (23 % issue
-// utilisation with two warpgroups), more resident warps hide it
+// utilisation with two warpgroups), more resident warps hide it.
+// Order of work, from a clock64 timeline of one CTA (B = 256, S = 200, d = 32: 66 k cycles per CTA before, 53 k after):
+//  * the MMA warp issues the score / dP MMAs of sub-tile i+1 BEFORE the three accumulations of sub-tile i (which take ~2 k cycles of
+//    tensor-pipe time: 24 MMAs of 128 x d x 16 are operand-fetch bound), so the element-wise stage of i+1 starts at once and waits for
+//    acc_done(i) only before its first write to X / Y;
+//  * the finished dQ / dK / dV tiles of sub-tile i are stored during sub-tile i+1 (after that same wait) instead of right after the
+//    x_full arrival of i, where every storing warp idled through its own accumulations;
+//  * a warp whose 32 queries do not exist (ragged last query tile) writes zeros, the warp holding the last real queries runs the plain
+//    arithmetic and zeroes its missing rows afterwards (it was the slowest warp of the tile by 3.6 k cycles on the general path);
+//  * the per-query constants of two heads are gathered in one pass (the pass is global-load latency; 2 S (head, query) pairs fill the
+//    epilogue threads).
 template <int WGS>
 __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                      const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
@@ -1066,6 +1077,11 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                     const int ks_r = (min(128, S - rt * 128) + 15) / 16;      // K-steps over the queries of the tile
                     mbar_wait_lean(&sh->x_full, (uint32_t)g & 1u);
                     tc_fence_after();
+                    // the score / dP MMAs of the NEXT sub-tile go first (T1 / T2 have been read: x_full): its element-wise stage
+                    // starts while the three accumulations below stream X and Y, and waits for acc_done only before its first
+                    // write to them
+                    if (i + 1 < subs_per_head) issue_t(hh, i + 1);
+                    else if (hh + 1 < hps) issue_t(hh + 1, 0);
                     const uint32_t tm_dq = tm_dq0 + (uint32_t)(rt * d);
                     for (int ks = 0; ks < ks_c; ++ks) {       // dQ[rt] += dS K[ct]
                         const uint64_t xd = smem_desc_advance(smem_desc_sw128(smem_u32(sX + (size_t)(ks / 4) * 16384)), (ks % 4) * 32);
@@ -1083,8 +1099,6 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                         umma_bf16(tm_dv, ad, bd, idesc_mn, (uint32_t)((rt != 0) | (ks != 0)));
                     }
                     umma_commit(&sh->acc_done);
-                    if (i + 1 < subs_per_head) issue_t(hh, i + 1);
-                    else if (hh + 1 < hps) issue_t(hh + 1, 0);
                 }
             }
         }
@@ -1106,36 +1120,72 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                 if (lane == 0) sh->kvb[w] = bits;
             }
         }
-        int g = 0;
-        for (int hh = 0; hh < hps; ++hh) {
-            const int head = slice * hps + hh;
-            const long long bh = (long long)b * a.heads + head;
-            asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");
-            for (int q = et; q < S; q += 128 * WGS) {
-                const __nv_bfloat16* o = a.ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
-                const __nv_bfloat16* go = a.d_ctx + ((size_t)b * S + q) * a.H + slice * 64 + hh * d;
-                float D = 0.f;
-                for (int c = 0; c < d; c += 8) {
-                    const uint4 ov = *reinterpret_cast<const uint4*>(o + c);
-                    const uint4 gv = *reinterpret_cast<const uint4*>(go + c);
-                    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
-                        const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
-                        D += __low2float(o2) * __low2float(g2) + __high2float(o2) * __high2float(g2);
+        // dQ (rows = queries of tile rt), dK, dV (rows = keys of tile ct) of head hh: tensor memory -> bf16 -> global; the head's d
+        // output columns go in 16-column pieces dealt to the warpgroups
+        auto store_tiles = [&](int hh_s, int ct_s, int rt_s, bool store_q, bool store_kv) {
+            for (int which = store_q ? 0 : 1; which < (store_kv ? 3 : 1); ++which) {      // 0 = dQ, 1 = dK, 2 = dV
+                const uint32_t tm = which == 0 ? tm_dq0 + (uint32_t)(rt_s * d) : (which == 1 ? tm_dk : tm_dv);
+                const int out_row = (which == 0 ? rt_s : ct_s) * 128 + r;
+                const int colbase = which * a.H + slice * 64 + hh_s * d;
+                for (int c0 = (WGS - 1 - wg) * 16; c0 < d; c0 += WGS * 16) {      // last warpgroups first: a ragged key tile leaves them the fewest chunks
+                    float o[16];
+                    tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
+                    tmem_ld_wait();
+                    if (out_row < S) {
+                        __nv_bfloat16* dst = a.d_qkv + ((size_t)b * S + out_row) * 3 * a.H + colbase + c0;
+                        uint4 w0, w1;
+                        w0.x = at_pack(o[0], o[1]); w0.y = at_pack(o[2], o[3]); w0.z = at_pack(o[4], o[5]); w0.w = at_pack(o[6], o[7]);
+                        w1.x = at_pack(o[8], o[9]); w1.y = at_pack(o[10], o[11]); w1.z = at_pack(o[12], o[13]); w1.w = at_pack(o[14], o[15]);
+                        reinterpret_cast<uint4*>(dst)[0] = w0;
+                        reinterpret_cast<uint4*>(dst)[1] = w1;
                     }
                 }
-                const float m = a.stats[bh * S + q];
-                const float l = a.stats[(long long)a.B * a.heads * S + bh * S + q];
-                sh->qc[q] = make_float4(m * LOG2E, 1.0f / l, D, exp2f((MASK_FILL - m) * LOG2E));
-                if (a.keep_bits) {
-                    const uint4* kb = reinterpret_cast<const uint4*>(a.keep_bits + ((size_t)bh * S + q) * 8);
-                    reinterpret_cast<uint4*>(sh->keep + q * 8)[0] = kb[0];
-                    reinterpret_cast<uint4*>(sh->keep + q * 8)[1] = kb[1];
-                }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");
+        };
+        bool pend_q = false, pend_kv = false;
+        int pend_hh = 0, pend_ct = 0, pend_rt = 0;
+        int g = 0;
+        for (int hh = 0; hh < hps; ++hh) {
+            if ((hh & 1) == 0) {
+                // per-query constants and keep bits of this head and the next in ONE pass (a pass is pure global-load latency: 2 x S
+                // (head, query) pairs keep 400 of the 512 threads busy at S = 200 instead of 200 of them twice)
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");      // the previous pair's constants are no longer in use
+                const int n_pair = min(2, hps - hh);
+                for (int idx = et; idx < n_pair * S; idx += 128 * WGS) {
+                    const int h2 = idx >= S ? 1 : 0, q = idx - h2 * S;
+                    const long long bh = (long long)b * a.heads + slice * hps + hh + h2;
+                    const __nv_bfloat16* o = a.ctx + ((size_t)b * S + q) * a.H + slice * 64 + (hh + h2) * d;
+                    const __nv_bfloat16* go = a.d_ctx + ((size_t)b * S + q) * a.H + slice * 64 + (hh + h2) * d;
+                    const float m_in = a.stats[bh * S + q];
+                    const float l_in = a.stats[(long long)a.B * a.heads * S + bh * S + q];
+                    uint4 kb0 = make_uint4(0u, 0u, 0u, 0u), kb1 = kb0;
+                    if (a.keep_bits) {
+                        const uint4* kb = reinterpret_cast<const uint4*>(a.keep_bits + ((size_t)bh * S + q) * 8);
+                        kb0 = kb[0]; kb1 = kb[1];
+                    }
+                    float D = 0.f;
+#pragma unroll 4
+                    for (int c = 0; c < d; c += 8) {          // (unrolled: the 16-byte loads of a row are in flight together)
+                        const uint4 ov = __ldg(reinterpret_cast<const uint4*>(o + c));
+                        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(go + c));
+                        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[e]);
+                            const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[e]);
+                            D += __low2float(o2) * __low2float(g2) + __high2float(o2) * __high2float(g2);
+                        }
+                    }
+                    sh->qc[h2 * AT_MAXS + q] = make_float4(m_in * LOG2E, 1.0f / l_in, D, exp2f((MASK_FILL - m_in) * LOG2E));
+                    if (a.keep_bits) {
+                        reinterpret_cast<uint4*>(sh->keep + (h2 * AT_MAXS + q) * 8)[0] = kb0;
+                        reinterpret_cast<uint4*>(sh->keep + (h2 * AT_MAXS + q) * 8)[1] = kb1;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * WGS) : "memory");
+            }
+            const float4* qc_h = sh->qc + (hh & 1) * AT_MAXS;
+            const uint32_t* keep_h = sh->keep + (hh & 1) * AT_MAXS * 8;
             for (int i = 0; i < subs_per_head; ++i, ++g) {
                 const int ct = i / n_t, rt = i % n_t;
                 const int row = rt * 128 + r;                  // query of this thread
@@ -1145,15 +1195,19 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                 mbar_wait_lean(&sh->t_full, (uint32_t)g & 1u);
                 tc_fence_after();
                 float4 rc = make_float4(0.f, 1.f, 0.f, 0.f);
-                if (row_ok) rc = sh->qc[row];
+                if (row_ok) rc = qc_h[row];
                 const bool warp_rows_plain = warp_row0 + 31 < S;
+                const bool warp_rows_none = warp_row0 >= S;          // no query of this warp exists: dS = P = 0
+                bool xy_free = g == 0;                               // the accumulate MMAs of the previous sub-tile have read X and Y
 #pragma unroll 1
                 for (int c16 = wg * C16_PER_WG; c16 < (wg + 1) * C16_PER_WG; ++c16) {
                     const int col0 = ct * 128 + c16 * 16;                  // first key of the chunk
                     if (c16 * 16 >= ((ncols + 31) / 32) * 32) break;
                     const uint32_t kv16 = (sh->kvb[col0 >> 5] >> (col0 & 31)) & 0xffffu;
-                    // padding keys only and no fully masked row in this warp: P = dS = 0 exactly (warp-uniform test)
-                    if (kv16 == 0u && __all_sync(0xffffffffu, rc.w == 0.f)) {
+                    // padding keys only and no fully masked row in this warp, or no query of this warp exists: P = dS = 0 exactly
+                    // (warp-uniform test)
+                    if (warp_rows_none || (kv16 == 0u && __all_sync(0xffffffffu, rc.w == 0.f))) {
+                        if (!xy_free) { mbar_wait_lean(&sh->acc_done, (uint32_t)(g - 1) & 1u); xy_free = true; }
 #pragma unroll
                         for (int u16 = 0; u16 < 2; ++u16) {
                             const uint32_t off = sw128_offset(r, (c16 & 3) * 2 + u16);
@@ -1168,9 +1222,10 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                     tmem_ld_wait();
                     float pd[16], ds[16];
                     uint32_t keep_w = 0xffffffffu;                      // keep bits of this row for the 32 keys around the chunk
-                    if (a.keep_bits && row_ok) keep_w = sh->keep[row * 8 + ct * 4 + (c16 >> 1)];
+                    if (a.keep_bits && row_ok) keep_w = keep_h[row * 8 + ct * 4 + (c16 >> 1)];
                     const uint32_t kp16 = (keep_w >> ((c16 & 1) * 16)) & 0xffffu;
-                    const bool plain = warp_rows_plain && kv16 == 0xffffu && (!a.causal || col0 + 15 <= warp_row0);
+                    // every key of the chunk attendable by every query of the warp that exists (missing queries: zeroed after the math)
+                    const bool plain = kv16 == 0xffffu && (!a.causal || col0 + 15 <= warp_row0);
                     if (plain) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
@@ -1178,6 +1233,13 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                             const float keep = ((kp16 >> c) & 1u) ? a.inv_keep : 0.f;
                             pd[c] = p * keep;
                             ds[c] = p * (t2[c] * keep - rc.z) * a.scale;
+                        }
+                        if (!warp_rows_plain) {                         // warp-uniform: the last warp with queries of a ragged tile
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                pd[c] = row_ok ? pd[c] : 0.f;
+                                ds[c] = row_ok ? ds[c] : 0.f;
+                            }
                         }
                     } else {
 #pragma unroll
@@ -1191,6 +1253,8 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                             ds[c] = ok ? p * (t2[c] * keep - rc.z) * a.scale : 0.f;
                         }
                     }
+                    // X and Y are written only now, and only now must the previous sub-tile's accumulate MMAs have finished reading them
+                    if (!xy_free) { mbar_wait_lean(&sh->acc_done, (uint32_t)(g - 1) & 1u); xy_free = true; }
                     uint8_t* xchunk = sX + (size_t)(c16 / 4) * 16384;
                     uint8_t* ychunk = sY + (size_t)(c16 / 4) * 16384;
 #pragma unroll
@@ -1204,38 +1268,27 @@ __global__ void __launch_bounds__(128 + 128 * WGS, 1) attn_tc_bwd1_kernel(const 
                         *reinterpret_cast<uint4*>(ychunk + sw128_offset(r, (c16 & 3) * 2 + u16)) = w;
                     }
                 }
+                // the gradient tiles the PREVIOUS sub-tile completed leave now: their accumulate MMAs have run next to this
+                // sub-tile's element-wise stage (acc_done was awaited before the first write to X / Y above; warps without
+                // such a write wait here), so no warp ever idles through the accumulate MMAs of its own sub-tile
+                if (pend_q || pend_kv) {
+                    if (!xy_free) { mbar_wait_lean(&sh->acc_done, (uint32_t)(g - 1) & 1u); xy_free = true; }
+                    tc_fence_after();
+                    store_tiles(pend_hh, pend_ct, pend_rt, pend_q, pend_kv);
+                    tc_fence_before();
+                }
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive_warp(&sh->x_full);
-                const bool store_kv = rt == n_t - 1, store_q = ct == n_t - 1;
-                if (store_kv || store_q) {
-                    mbar_wait_lean(&sh->acc_done, (uint32_t)g & 1u);
-                    tc_fence_after();
-                    // the head's d output columns are stored in 16-column pieces dealt round-robin to the warpgroups
-                    {
-                        // which: 0 = dQ (row = query rt*128 + r), 1 = dK, 2 = dV (row = key ct*128 + r)
-                        for (int which = store_q ? 0 : 1; which < (store_kv ? 3 : 1); ++which) {
-                            const uint32_t tm = which == 0 ? tm_dq0 + (uint32_t)(rt * d) : (which == 1 ? tm_dk : tm_dv);
-                            const int out_row = which == 0 ? row : ct * 128 + r;
-                            const int colbase = which * a.H + slice * 64 + hh * d;
-                            for (int c0 = wg * 16; c0 < d; c0 += WGS * 16) {
-                                float o[16];
-                                tmem_ld16(tm + lane_addr + (uint32_t)c0, o);
-                                tmem_ld_wait();
-                                if (out_row < S) {
-                                    __nv_bfloat16* dst = a.d_qkv + ((size_t)b * S + out_row) * 3 * a.H + colbase + c0;
-                                    uint4 w0, w1;
-                                    w0.x = at_pack(o[0], o[1]); w0.y = at_pack(o[2], o[3]); w0.z = at_pack(o[4], o[5]); w0.w = at_pack(o[6], o[7]);
-                                    w1.x = at_pack(o[8], o[9]); w1.y = at_pack(o[10], o[11]); w1.z = at_pack(o[12], o[13]); w1.w = at_pack(o[14], o[15]);
-                                    reinterpret_cast<uint4*>(dst)[0] = w0;
-                                    reinterpret_cast<uint4*>(dst)[1] = w1;
-                                }
-                            }
-                        }
-                    }
-                    tc_fence_before();
-                }
+                pend_kv = rt == n_t - 1; pend_q = ct == n_t - 1;
+                pend_hh = hh; pend_ct = ct; pend_rt = rt;
             }
+        }
+        if (pend_q || pend_kv) {                              // the last sub-tile's
+            mbar_wait_lean(&sh->acc_done, (uint32_t)(g - 1) & 1u);
+            tc_fence_after();
+            store_tiles(pend_hh, pend_ct, pend_rt, pend_q, pend_kv);
+            tc_fence_before();
         }
     }
     tc_fence_before();
