@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29612 tools/perf_collectives.py 2>&1 | tail -3
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29614 tools/perf_collectives.py 2>&1 | tail -1
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 8 --no-cpu > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err; tail -c 700 gpurun_out/bench_8gpu.json
