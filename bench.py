@@ -16,7 +16,10 @@ BASELINE.json's metric has two halves, both measured here:
 One JSON line on stdout (rank 0):
   value / ms_per_step   train seqs/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e                   the same through the public module API with HOST (pinned) inputs: H2D copy of the step's item sequences,
-                        GPU cloze masking, the step, D2H read of the loss -- all inside the timed region
+                        GPU cloze masking, the step, D2H read of the loss -- all inside the timed region, every step; in the
+                        training loop the copies are double-buffered as a prefetching loader would (H2D of step i+1 on a copy
+                        stream while step i runs, the loss of step i read one step later; the evaluation loop, whose step_end
+                        hands metric values to the host, stays synchronous: pipelining it was slower)
   roofline              dominant kernel of the step: algorithmic bytes (or flops) per launch / CUDA-event launch duration
   cpu_baseline          the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, full C2 batch
   eval                  {value users/s, e2e, roofline (scoring sweep, flops on H=128), cpu_baseline (B=64), recall@10, checks}
@@ -24,6 +27,7 @@ The per-kernel tables go to stderr.  --impl reference times the CPU oracle port 
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -584,18 +588,57 @@ def main():
     value = args.steps * cfg["B"] * world / (ms / 1e3)
 
     # ---- (2) end to end through the public API with HOST buffers ---------------------------------------------------------------------
+    # The loop a trainer with a prefetching loader runs: the H2D copy of step i+1's item sequences is issued on a copy stream while step
+    # i runs (two staging buffers; an event hands each back once the cloze kernels have read it), and the loss of step i is copied to
+    # pinned memory behind the step and READ after step i+1 has been queued, so neither direction stalls the device.  Every step
+    # still copies its own inputs from pinned host memory and its own loss back; the last loss is read inside the timed region.
     h2d = host_items[0].numel() * host_items[0].element_size()
-    staged = torch.empty_like(dev_batches[0]["item"])
+    staged = [torch.empty_like(dev_batches[0]["item"]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=device)
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+    e2e_losses = []
 
-    def e2e_step(i):
-        j = (args.warmup + i) % N_BATCHES
-        staged.copy_(host_items[j], non_blocking=True)                    # H2D of this step's item sequences (pinned)
-        batch = cloze(staged, N_BATCHES + i)                              # input pipeline on the GPU: fresh masks every step
-        return float(run_step(batch, i))                                  # the step; D2H read of its loss
+    def make_e2e(n):
+        def prefetch(i):
+            b = i & 1
+            copy_stream.wait_event(in_free[b])                                # its previous reader (step i-2's cloze kernels) is done
+            with torch.cuda.stream(copy_stream):
+                staged[b].copy_(host_items[(args.warmup + i) % N_BATCHES], non_blocking=True)    # H2D of step i's item sequences
+                in_ready[b].record(copy_stream)
 
+        def e2e_step(i):
+            b = i & 1
+            if i == 0:
+                for ev in in_free:
+                    ev.record()
+                prefetch(0)
+            torch.cuda.current_stream().wait_event(in_ready[b])
+            batch = cloze(staged[b], N_BATCHES + i)                           # input pipeline on the GPU: fresh masks every step
+            in_free[b].record()
+            if i + 1 < n:
+                prefetch(i + 1)                                               # overlaps this step
+            loss = run_step(batch, i)                                         # the step
+            if not torch.is_tensor(loss):
+                loss = torch.tensor(float(loss), device=device)
+            loss_host[b].copy_(loss.detach().reshape(()).float(), non_blocking=True)  # D2H of its loss, behind it on the same stream
+            loss_done[b].record()
+            if i > 0:                                                         # read the PREVIOUS step's loss: it has long arrived
+                loss_done[b ^ 1].synchronize()
+                e2e_losses.append(float(loss_host[b ^ 1]))
+            if i == n - 1:
+                loss_done[b].synchronize()
+                e2e_losses.append(float(loss_host[b]))
+        return e2e_step
+
+    warm = make_e2e(3)
     for i in range(3):
-        e2e_step(i)
-    ms_e2e, win2 = timed(e2e_step, args.steps)
+        warm(i)
+    e2e_losses.clear()
+    ms_e2e, win2 = timed(make_e2e(args.steps), args.steps)
+    assert len(e2e_losses) == args.steps and all(math.isfinite(x) for x in e2e_losses), "end-to-end loop lost a loss value"
     e2e_value = args.steps * cfg["B"] * world / (ms_e2e / 1e3)
     graphs_captured = len(graphed.graphs) if graphed is not None else 0
 
@@ -671,7 +714,7 @@ def main():
            "implementation": {"precision": f"{model.precision}: tcgen05 GEMMs/attention/scoring with bf16 operands, fp32 accumulation, residual "
                                            f"stream, LayerNorm, loss and Adam state", "launch": launch, "distinct_batches": N_BATCHES},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                   "path": "pinned host item sequences -> H2D -> GPU cloze masking -> MaskedTrainingModule step (graph replay) -> loss D2H"},
+                   "path": "pinned host item sequences -> H2D (copy stream, double-buffered: the copy of step i+1 overlaps step i) -> GPU cloze masking -> MaskedTrainingModule step (graph replay) -> loss D2H to pinned memory, read one step later (the last one inside the timed region)"},
            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
            "graphs_captured": graphs_captured, "distinct_target_counts": len(target_counts),
            "target_count_range": [target_counts[0], target_counts[-1]],

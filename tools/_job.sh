@@ -1,2 +1,7 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/t17.log 2>&1; tail -5 gpurun_out/t17.log
-python bench.py > gpurun_out/bench_r2k_1gpu.json 2> gpurun_out/bench_r2k_1gpu.err; tail -c 1500 gpurun_out/bench_r2k_1gpu.json | head -c 600; echo; tail -3 gpurun_out/bench_r2k_1gpu.err
+python bench.py > gpurun_out/bench_r2l_1gpu.json 2> gpurun_out/bench_r2l_1gpu.err; tail -5 gpurun_out/bench_r2l_1gpu.err | cut -c1-400
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_r2l_1gpu.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])
+print(d['eval']['value'], d['eval']['ms_per_step'], d['eval']['e2e']['value'], d['eval']['e2e']['ms_per_step'], d['eval']['recall@10'], d['eval']['checks'])
+PY
