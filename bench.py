@@ -19,7 +19,8 @@ One JSON line on stdout (rank 0):
                         GPU cloze masking, the step, D2H read of the loss -- all inside the timed region, every step; in the
                         training loop the copies are double-buffered as a prefetching loader would (H2D of step i+1 on a copy
                         stream while step i runs, the loss of step i read one step later; the evaluation loop, whose step_end
-                        hands metric values to the host, stays synchronous: pipelining it was slower)
+                        hands metric values to the host, stays synchronous: pipelined the same way it was slower, 1.195 vs 1.145 ms
+                        per step in one run -- its host side is the longer one)
   roofline              dominant kernel of the step: algorithmic bytes (or flops) per launch / CUDA-event launch duration
   cpu_baseline          the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, full C2 batch
   eval                  {value users/s, e2e, roofline (scoring sweep, flops on H=128), cpu_baseline (B=64), recall@10, checks}
