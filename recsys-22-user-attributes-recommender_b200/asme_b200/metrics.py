@@ -292,7 +292,14 @@ class RankingMetricsContainer(MetricsContainer):
             if ks:
                 if len(ks) > 8:
                     raise RuntimeError("asme_b200: at most 8 distinct k per metrics container")
-                ks_t = torch.tensor(ks, dtype=torch.int32, device=rank.device)
+                # the k values live on the device once per (device, ks): building the tensor from the Python list every step is a
+                # pageable host-to-device copy, and CUDA synchronises the stream before one -- the host then sat out the whole
+                # replayed model graph before it could queue the metric kernels (~60 us of idle device per evaluation step)
+                cache = self.__dict__.setdefault("_ks_device", {})
+                ck = (str(rank.device), tuple(ks))
+                ks_t = cache.get(ck)
+                if ks_t is None:
+                    ks_t = cache[ck] = torch.tensor(ks, dtype=torch.int32, device=rank.device)
                 table = torch.zeros(4, len(ks), dtype=torch.float32, device=rank.device)
                 ops.ranking_metrics(rank, ks_t, table)
         for metric in self.metrics:
