@@ -21,12 +21,16 @@ class StepState:
     def __init__(self, device, seed: int = 0, adam_step: int = 0, lr: float = 0.0):
         self.tensor = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0, adam_step], dtype=torch.int64).to(device)
         self._lr_view = self.tensor.view(torch.float64)[1:2]
-        self._lr_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        # a ring of pinned slots: the copy is asynchronous, and a host that runs ahead of the device (a loop that reads the loss one step
+        # late) must not overwrite the value of a step whose copy has not been executed yet
+        self._lr_host = torch.zeros(16, dtype=torch.float64).pin_memory()
+        self._lr_slot = 0
         self.set_lr(lr)
 
     def set_lr(self, lr: float):
-        self._lr_host[0] = lr
-        self._lr_view.copy_(self._lr_host, non_blocking=True)
+        i = self._lr_slot = (self._lr_slot + 1) % self._lr_host.numel()
+        self._lr_host[i] = lr
+        self._lr_view.copy_(self._lr_host[i:i + 1], non_blocking=True)
 
     def indirect_seed(self) -> int:
         return (1 << 63) | self.tensor.data_ptr()

@@ -228,7 +228,11 @@ class FixedItemsSampler:
     def sample(self, input_seq, targets, predictions, mask=None) -> MetricsSample:
         if targets.dim() != 1:
             raise NotImplementedError("basket targets are outside the B200 hot path")
-        items = torch.tensor(self.fixed_items, dtype=torch.int64, device=targets.device).unsqueeze(0).repeat(targets.shape[0], 1)
+        cache = self.__dict__.setdefault("_items_device", {})       # (built once per device: a per-step pageable H2D copy synchronises)
+        row = cache.get(str(targets.device))
+        if row is None:
+            row = cache[str(targets.device)] = torch.tensor(self.fixed_items, dtype=torch.int64, device=targets.device)
+        items = row.unsqueeze(0).repeat(targets.shape[0], 1)
         sampled = predictions.gather(1, items)
         positive = items.eq(targets.unsqueeze(1)).to(dtype=sampled.dtype)
         return MetricsSample(sampled, positive, None)
