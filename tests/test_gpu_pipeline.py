@@ -209,6 +209,15 @@ def test_sampled_and_fixed_subset_metrics_from_fused_predictions():
         assert abs(float(got["NDCG@5_sampled(50)"]) - O.ndcg_at_k(sp, pm, 5).mean()) < 1e-6
         # the gathered scores are the dense logits at those items
         np.testing.assert_allclose(sub, pred.gather(1, items.cuda()).cpu().numpy(), rtol=1e-5, atol=1e-5)
+        # the all-items container keeps its k values on the device: a tensor built from the Python list every step would be a pageable
+        # host-to-device copy, i.e. a stream synchronisation in front of the metric kernels of every evaluation step
+        from asme_b200.metrics import AllItemsSampler
+        allc = RankingMetricsContainer([RecallMetric(5), NormalizedDiscountedCumulativeGainMetric(5)], AllItemsSampler())
+        v1 = allc.update(seq_d, tgt_d, pred)
+        ks_first = next(iter(allc._ks_device.values()))
+        v2 = allc.update(seq_d, tgt_d, pred)
+        assert len(allc._ks_device) == 1 and next(iter(allc._ks_device.values())) is ks_first
+        assert float(v1["recall@5"]) == float(v2["recall@5"]) and float(v1["NDCG@5"]) == float(v2["NDCG@5"])
     finally:
         models.set_default_precision(old)
 
