@@ -20,7 +20,8 @@ One JSON line on stdout (rank 0):
                         training loop the copies are double-buffered as a prefetching loader would (H2D of step i+1 on a copy
                         stream while step i runs, the loss of step i read one step later; the evaluation loop, whose step_end
                         hands metric values to the host, stays synchronous: pipelined the same way it was slower, 1.195 vs 1.145 ms
-                        per step in one run -- its host side is the longer one)
+                        per step in one run -- measured while the metrics update still synchronised the stream every step
+                        (asme_b200/metrics.py, fixed since); not re-measured after that fix)
   roofline              dominant kernel of the step: algorithmic bytes (or flops) per launch / CUDA-event launch duration
   cpu_baseline          the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, full C2 batch
   eval                  {value users/s, e2e, roofline (scoring sweep, flops on H=128), cpu_baseline (B=64), recall@10, checks}
